@@ -1,0 +1,223 @@
+"""Generate tests/golden/deflow_*.npz by running the REFERENCE's own Python modules.
+
+Run in the build container only (needs /root/reference; the GPU box never runs this):
+
+    python tests/golden/make_golden.py
+
+The reference model code (OpenSceneFlow/src/models/deflow.py, basic/encoder.py, unet.py,
+decoder.py, assets/cuda/mmcv/{voxelize,scatter_points}.py) and loss functions
+(src/lossfuncs.py, AST-extracted because the module imports chamfer3D/av2 at import time) run
+UNMODIFIED on CPU.  Two stubs make that possible:
+
+* ``dztimer`` -> a no-op Timing class (pure wall-clock instrumentation, no arithmetic);
+* ``mmcv._ext`` -> the numpy restatement in oracle/mmcv_ext_oracle.py, because the reference
+  extension registers CUDA kernels only and this container has no GPU.  The integer half of
+  that restatement is separately pinned against the real CUDA extension on a B200
+  (make_ext_golden_gpu.py).
+
+Weights come from oracle.deflow_oracle.random_state(seed) (deterministic CPU generator) so the
+27 MB state dict does not have to be stored; fixtures hold inputs (fp16-exact coordinates),
+outputs, loss values and a few gradient tensors.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OSF = "/root/reference/OpenSceneFlow"
+sys.path.insert(0, ROOT)
+
+from oracle import mmcv_ext_oracle as ext_np  # noqa: E402
+from oracle import deflow_oracle as orc  # noqa: E402
+from deflow_b200 import synth  # noqa: E402
+
+
+# ----------------------------------------------------------------------------- stubs
+class _Timing:
+    def __getitem__(self, i):
+        return self
+
+    def start(self, *a, **k):
+        return None
+
+    def stop(self, *a, **k):
+        return None
+
+    def print(self, *a, **k):
+        return None
+
+
+def install_stubs():
+    dz = types.ModuleType("dztimer")
+    dz.Timing = _Timing
+    sys.modules["dztimer"] = dz
+
+    e = types.ModuleType("mmcv._ext")
+
+    def dynamic_voxelize_forward(points, voxel_size, coors_range, coors, NDim=3):
+        out = ext_np.dynamic_voxelize_forward(points.detach().numpy(), voxel_size.numpy(), coors_range.numpy(),
+                                              coors.numpy())
+        coors.copy_(torch.from_numpy(out))
+
+    def dynamic_point_to_voxel_forward(feats, coors, reduce_type):
+        r = ext_np.dynamic_point_to_voxel_forward(feats.detach().numpy(), coors.numpy(), reduce_type)
+        return [torch.from_numpy(np.ascontiguousarray(x)) for x in r]
+
+    def dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats, reduced_feats, coors_idx,
+                                        reduce_count, reduce_type):
+        g = ext_np.dynamic_point_to_voxel_backward(grad_reduced_feats.numpy(), feats.detach().numpy(),
+                                                   reduced_feats.detach().numpy(), coors_idx.numpy(),
+                                                   reduce_count.numpy(), reduce_type)
+        grad_feats.copy_(torch.from_numpy(g))
+
+    def hard_voxelize_forward(*a, **k):
+        raise RuntimeError("hard_voxelize_forward is not on the DeFlow path")
+
+    e.dynamic_voxelize_forward = dynamic_voxelize_forward
+    e.dynamic_point_to_voxel_forward = dynamic_point_to_voxel_forward
+    e.dynamic_point_to_voxel_backward = dynamic_point_to_voxel_backward
+    e.hard_voxelize_forward = hard_voxelize_forward
+    pkg = types.ModuleType("mmcv")
+    pkg._ext = e
+    sys.modules["mmcv"] = pkg
+    sys.modules["mmcv._ext"] = e
+
+
+def load_reference():
+    install_stubs()
+    sys.path.insert(0, OSF)
+    from src.models.deflow import DeFlow  # noqa
+    from src.models.fastflow3d import FastFlow3D  # noqa
+    src = open(os.path.join(OSF, "src/lossfuncs.py")).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("deflowLoss", "ff3dLoss", "zeroflowLoss"):
+            exec(compile(ast.Module([node], []), "lossfuncs.py", "exec"), ns)
+    return DeFlow, FastFlow3D, ns
+
+
+# ----------------------------------------------------------------------------- cases
+def shrink_batch(batch, scale):
+    """Scale xy so that a small range/grid sees the same occupancy statistics."""
+    out = dict(batch)
+    for k in ("pc0", "pc1"):
+        v = batch[k].clone()
+        v[..., :2] = v[..., :2] * scale
+        out[k] = v.to(torch.float16).to(torch.float32)
+    out["flow"] = batch["flow"].clone()
+    return out
+
+
+def run_case(name, model, lossns, batch, loss_name, seed_state, decoder, training, grads_of, out_dir, cfg):
+    state = orc.random_state(seed_state, decoder)
+    missing = model.load_state_dict(state, strict=True)
+    model.train(training)
+    for p in model.parameters():
+        p.grad = None
+    res = model(batch)
+    # trainer.py:116-152 arithmetic with the reference loss functions
+    total = 0.0
+    per_sample = []
+    for b in range(len(batch["pose0"])):
+        idx = res["pc0_valid_point_idxes"][b]
+        d = {"est_flow": res["flow"][b], "gt_flow": batch["flow"][b][idx] - res["pose_flow"][b][idx],
+             "gt_classes": batch["flow_category_indices"][b][idx]}
+        l = lossns[loss_name](d)["loss"]
+        per_sample.append(float(l))
+        total = total + l
+    fix = {
+        "cfg_voxel_size": np.asarray(cfg["voxel_size"], np.float64),
+        "cfg_range": np.asarray(cfg["range"], np.float64),
+        "cfg_grid": np.asarray(cfg["grid"], np.int64),
+        "decoder": np.asarray(decoder), "loss_name": np.asarray(loss_name),
+        "training": np.asarray(training), "seed_state": np.asarray(seed_state),
+        "pc0": batch["pc0"].numpy().astype(np.float16), "pc1": batch["pc1"].numpy().astype(np.float16),
+        "pose0": torch.stack(batch["pose0"]).numpy(), "pose1": torch.stack(batch["pose1"]).numpy(),
+        "flow_gt": batch["flow"].numpy(), "classes": batch["flow_category_indices"].numpy(),
+        "loss_total": np.asarray(float(total)), "loss_per_sample": np.asarray(per_sample),
+    }
+    assert torch.equal(batch["pc0"].nan_to_num(7e4), torch.from_numpy(fix["pc0"].astype(np.float32)).nan_to_num(7e4))
+    for b in range(len(batch["pose0"])):
+        fix[f"flow_{b}"] = res["flow"][b].detach().numpy()
+        fix[f"pose_flow_{b}"] = res["pose_flow"][b].numpy()
+        fix[f"pc0_idx_{b}"] = res["pc0_valid_point_idxes"][b].numpy()
+        fix[f"pc1_idx_{b}"] = res["pc1_valid_point_idxes"][b].numpy()
+    fix["num_occupied_voxels"] = np.asarray(res["num_occupied_voxels"])
+    if training and grads_of:
+        total.backward()
+        named = dict(model.named_parameters())
+        for k in grads_of:
+            fix["grad::" + k] = named[k].grad.numpy()
+        # running statistics after this one step (BN1d is updated 2B times, BN2d twice per layer)
+        sd = model.state_dict()
+        for k in ("embedder.feature_net.pfn_layers.0.1.running_mean",
+                  "embedder.feature_net.pfn_layers.0.1.running_var",
+                  "backbone.encoder_step_1.0.batchnorm.running_mean",
+                  "backbone.encoder_step_1.0.batchnorm.running_var",
+                  "backbone.encoder_step_3.5.batchnorm.running_var",
+                  "backbone.encoder_step_3.5.batchnorm.num_batches_tracked"):
+            fix["buf::" + k] = sd[k].numpy()
+    path = os.path.join(out_dir, name + ".npz")
+    np.savez_compressed(path, **fix)
+    print(f"{name}: loss {float(total):.6f}  flows {[tuple(f.shape) for f in res['flow']]}  -> "
+          f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
+GRADS = ["head.decoder.2.weight", "head.decoder.0.bias", "head.offset_encoder.weight",
+         "embedder.feature_net.pfn_layers.0.0.weight", "embedder.feature_net.pfn_layers.0.1.weight",
+         "embedder.feature_net.pfn_layers.0.1.bias",
+         "backbone.encoder_step_1.0.conv.bias", "backbone.encoder_step_1.0.batchnorm.weight",
+         "backbone.encoder_step_3.5.batchnorm.bias", "backbone.decoder_step4.bias",
+         "backbone.decoder_step1.u1_u2.0.bias", "backbone.decoder_step3.u3.bias"]
+GRADS_GRU = GRADS + ["head.gru.convz.bias", "head.gru.convq.bias", "head.gru.convr.bias"]
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    DeFlow, FastFlow3D, lossns = load_reference()
+    out_dir = HERE
+
+    # A/B: small grid (64x64, +-6.4 m) so the full fwd+bwd oracle runs in seconds
+    small = {"voxel_size": [0.2, 0.2, 6], "range": [-6.4, -6.4, -3, 6.4, 6.4, 3], "grid": [64, 64]}
+    batch = shrink_batch(synth.make_batch(2, 1500, seed=7), 1.0 / 8.0)
+    m = DeFlow(small["voxel_size"], small["range"], small["grid"], "gru", 4)
+    run_case("deflow_small_gru", m, lossns, batch, "deflowLoss", 11, "gru", True, GRADS_GRU, out_dir, small)
+    m = DeFlow(small["voxel_size"], small["range"], small["grid"], "linear", 4)
+    run_case("deflow_small_linear", m, lossns, batch, "ff3dLoss", 12, "linear", True, GRADS, out_dir, small)
+    m = DeFlow(small["voxel_size"], small["range"], small["grid"], "gru", 4)
+    run_case("deflow_small_gru_eval", m, lossns, batch, "deflowLoss", 13, "gru", False, [], out_dir, small)
+
+    # C: BASELINE.json configs[0] -- 20k-pt pair, 512x512, B=1, forward + loss (train-mode BN)
+    full = {"voxel_size": [0.2, 0.2, 6], "range": [-51.2, -51.2, -3, 51.2, 51.2, 3], "grid": [512, 512]}
+    batch = synth.make_batch(1, 20000, seed=3)
+    m = DeFlow(full["voxel_size"], full["range"], full["grid"], "gru", 4)
+    with torch.no_grad():
+        run_case("deflow_cfg1_20k", m, lossns, batch, "deflowLoss", 21, "gru", True, [], out_dir, full)
+
+    # D: the reference's only real-data fixture (AV2 sweeps), sub-sampled to 20k points per frame
+    rng = np.random.default_rng(5)
+    pcs = []
+    for f in ("test_pc0.npy", "test_pc1.npy"):
+        a = np.load(os.path.join(OSF, "assets/tests", f))[:, :3]
+        sel = np.sort(rng.choice(a.shape[0], 20000, replace=False))
+        pcs.append(torch.from_numpy(a[sel].astype(np.float32)))
+    pose1 = torch.eye(4)
+    pose1[0, 3] = 0.9
+    batch = {"pc0": pcs[0][None], "pc1": pcs[1][None], "pose0": [torch.eye(4)], "pose1": [pose1],
+             "flow": torch.zeros(1, 20000, 3), "flow_is_valid": torch.ones(1, 20000, dtype=torch.bool),
+             "flow_category_indices": torch.zeros(1, 20000, dtype=torch.uint8)}
+    with torch.no_grad():
+        run_case("deflow_av2_real_20k", m, lossns, batch, "deflowLoss", 22, "gru", True, [], out_dir, full)
+
+
+if __name__ == "__main__":
+    main()

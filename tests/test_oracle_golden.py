@@ -1,0 +1,57 @@
+"""The CPU oracle against the fixtures produced by the reference's own modules
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import deflow_oracle as orc
+from helpers import load_fixture
+
+CASES = ["deflow_small_gru", "deflow_small_linear", "deflow_small_gru_eval"]
+
+
+def _run(name, need_grad):
+    fx, batch, cfg = load_fixture(name)
+    state = orc.random_state(cfg["seed_state"], cfg["decoder"])
+    if need_grad:
+        for k, v in state.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+    buffers = {k: v.clone() for k, v in state.items() if "running" in k}
+    res = orc.deflow_forward(batch, state, cfg["voxel_size"], cfg["range"], cfg["grid"], cfg["decoder"], 4,
+                             training=cfg["training"], buffers=buffers if cfg["training"] else None)
+    return fx, batch, cfg, state, buffers, res
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference(name):
+    fx, batch, cfg, state, buffers, res = _run(name, False)
+    for b in range(len(batch["pose0"])):
+        assert np.array_equal(res["pc0_valid_point_idxes"][b].numpy(), fx[f"pc0_idx_{b}"])
+        assert np.array_equal(res["pc1_valid_point_idxes"][b].numpy(), fx[f"pc1_idx_{b}"])
+        np.testing.assert_allclose(res["pose_flow"][b].numpy(), fx[f"pose_flow_{b}"], atol=1e-6)
+        np.testing.assert_allclose(res["flow"][b].detach().numpy(), fx[f"flow_{b}"], atol=2e-5)
+    loss = orc.training_step_loss(batch, res, cfg["loss"])
+    assert abs(float(loss) - float(fx["loss_total"])) < 1e-5
+    assert res["num_occupied_voxels"] == list(fx["num_occupied_voxels"])
+
+
+@pytest.mark.parametrize("name", ["deflow_small_gru", "deflow_small_linear"])
+def test_backward_and_running_stats_match_reference(name):
+    fx, batch, cfg, state, buffers, res = _run(name, True)
+    loss = orc.training_step_loss(batch, res, cfg["loss"])
+    loss.backward()
+    for k in fx:
+        if k.startswith("grad::"):
+            g = state[k[6:]].grad.numpy()
+            ref = fx[k]
+            assert np.abs(g - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max()), k
+        if k.startswith("buf::") and "num_batches" not in k:
+            np.testing.assert_allclose(buffers[k[5:]].numpy(), fx[k], rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+def test_config1_20k_and_real_sweep():
+    for name in ("deflow_cfg1_20k", "deflow_av2_real_20k"):
+        fx, batch, cfg, state, buffers, res = _run(name, False)
+        assert np.array_equal(res["pc0_valid_point_idxes"][0].numpy(), fx["pc0_idx_0"])
+        np.testing.assert_allclose(res["flow"][0].detach().numpy(), fx["flow_0"], atol=5e-5)
