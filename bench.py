@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/s (fwd + loss + bwd + Adam) of the DeFlow hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+N>1 is launched by the driver as `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N`.
+Prints ONE JSON line on rank 0 (contract: task prompt section 4 / "bench.py").
+
+Workload (BASELINE.json configs[1]): DeFlow-GRU (pillar encoder + UNet + 4-iteration GRU decoder),
+synthetic AV2-shaped frame pairs, 80 000 points / frame, 512x512 pillars, batch 16 per GPU, bf16
+operands in the dense contractions (fp32 accumulation / statistics / voxelisation), full training step.
+
+Only the `cpu_baseline` leg and `--impl reference` execute anything under oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frame_pairs_per_sec_fwd_bwd"
+UNIT = "frame-pairs/s"
+VS, RG = [0.2, 0.2, 6], [-51.2, -51.2, -3, 51.2, 51.2, 3]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="frame pairs per GPU")
+    ap.add_argument("--points", type=int, default=80000, help="points per frame")
+    ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--decoder", default="gru", choices=["gru", "linear"])
+    ap.add_argument("--loss", default="deflowLoss", choices=["deflowLoss", "ff3dLoss"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scatter", action="store_true", help="skip the config-5 scatter microbench")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-points", type=int, default=None)
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, smax, pw = [], set(), None, []
+        for r in rows:
+            try:
+                sm.append(float(r[0])); smax = float(r[1]); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_pairs_per_sec(points, grid, decoder, loss, steps=1, warmup=0):
+    """The reference's CPU path for the same step -- the oracle port (reference Python modules restated in
+    oracle/deflow_oracle.py + numpy mmcv stand-in; the reference ships no CPU kernels for its native ops and
+    its Python modules cannot travel to the GPU box).  One step = fwd + loss + bwd of ONE frame pair."""
+    from oracle import deflow_oracle as orc
+    from deflow_b200 import synth
+    torch.set_num_threads(os.cpu_count())
+    scale = grid / 512.0
+    vs = [0.2 / scale, 0.2 / scale, 6]
+    state = orc.random_state(1, decoder)
+    for k, v in state.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    buffers = {k: v.clone() for k, v in state.items() if "running" in k}
+    batch = synth.make_batch(1, points, seed=synth.SEED_BASE)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = orc.deflow_forward(batch, state, vs, RG, (grid, grid), decoder, 4, training=True, buffers=buffers)
+        l = orc.training_step_loss(batch, res, loss)
+        l.backward()
+        for v in state.values():
+            v.grad = None
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return 1.0 / t, t, os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    pts = args.cpu_points or args.points
+    v, t, cores = cpu_reference_pairs_per_sec(pts, args.grid, args.decoder, args.loss, steps, warm)
+    sample = f"{steps} step(s) of 1 frame pair, {pts} pts/frame, {args.grid}x{args.grid}, fwd+loss+bwd, fp32, torch CPU {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"DeFlow-{args.decoder.upper()} training step (pillar encoder + UNet + "
+                        f"{'4-iter GRU' if args.decoder == 'gru' else 'linear'} decoder + {args.loss} + Adam), "
+                        f"{args.points} pts/frame, {args.grid}x{args.grid} pillars, batch {args.batch}/GPU (BASELINE configs[1])",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "points_per_frame": args.points,
+            "grid": [args.grid, args.grid], "precision": args.precision, "parallelism": f"dp{world}",
+            "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no explicit flush",
+            "sync_bn": False}
+
+
+# ------------------------------------------------------------------------------------------ native arm
+def scatter_microbench(dev, peaks, frames=32, n=200000, grid=1024, iters=5):
+    """BASELINE configs[4]: voxelisation stress -- 200k pts/frame, 1024x1024 grid, 32 frames per launch,
+    scatter-only forward + backward (pillar index + fused PFN fwd + PFN bwd).  HBM GB/s on algorithmic bytes."""
+    from deflow_b200 import ops, synth
+    import deflow_b200 as d
+    vs = [0.1, 0.1, 6]
+    b = synth.make_batch(4, n, seed=7)
+    pts = torch.cat([b["pc0"][:, :n], b["pc1"][:, :n]], 0)
+    reps = (frames + pts.shape[0] - 1) // pts.shape[0]
+    pts = pts.repeat(reps, 1, 1)[:frames].contiguous().to(dev)
+    net = d.DynamicPillarFeatureNet(3, vs, RG, feat_channels=(32,), mode="avg").to(dev).train()
+    gimg = None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t_idx = t_fwd = t_bwd = 0.0
+    for it in range(iters + 2):
+        ev[0].record()
+        idx = ops.pillar_index(pts, vs, RG)
+        ev[1].record()
+        image, _, _ = net.forward_fused(idx, torch.bfloat16)
+        ev[2].record()
+        if gimg is None:
+            gimg = torch.randn_like(image)
+        image.backward(gimg)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            t_idx += ev[0].elapsed_time(ev[1]); t_fwd += ev[1].elapsed_time(ev[2]); t_bwd += ev[2].elapsed_time(ev[3])
+    t_idx, t_fwd, t_bwd = t_idx / iters, t_fwd / iters, t_bwd / iters
+    N = idx.pt_off(frames)
+    M = idx.pil_off(frames)
+    Nin = frames * pts.shape[1]
+    C = 32
+    # voxelise 24*N_in; scatter fwd 4NC+12N read + 4MC+12M+4N+4M written, x2 scatters (C=3, C=32);
+    # pillar->image 4MC+12M + 2*C*H*W (bf16); bwd 4MC+4N+4M read + 4NC written.
+    by_idx = 24 * Nin
+    by_fwd = (4 * N * 3 + 12 * N + 4 * M * 3 + 12 * M + 4 * N + 4 * M) + (4 * N * C + 12 * N + 4 * M * C + 12 * M + 4 * N + 4 * M) \
+        + (4 * M * C + 12 * M + 2 * C * grid * grid * frames)
+    by_bwd = 4 * M * C + 4 * N + 4 * M + 4 * N * C
+    tot_ms = t_idx + t_fwd + t_bwd
+    gbs = (by_idx + by_fwd + by_bwd) / (tot_ms * 1e-3) / 1e9
+    return {"workload": f"{frames} frames x {n} pts, {grid}x{grid} grid, index + fused PFN fwd + bwd (BASELINE configs[4])",
+            "valid_points": N, "pillars": M, "ms": {"index": t_idx, "pfn_fwd": t_fwd, "pfn_bwd": t_bwd},
+            "algorithmic_bytes": by_idx + by_fwd + by_bwd, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+
+
+def run_native(args):
+    import torch.distributed as dist
+    import deflow_b200 as d
+    from deflow_b200 import _lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly if the CUDA library is missing
+    peaks = load_peaks()
+
+    scale = args.grid / 512.0
+    vs = [0.2 / scale, 0.2 / scale, 6]
+    torch.manual_seed(synth.SEED_BASE + rank)
+    model = d.DeFlow(vs, RG, [args.grid, args.grid], args.decoder, 4, precision=args.precision)
+    model.apply(d.weights_init)
+    model = model.to(dev).train()
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    else:
+        net = model
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, fused=True)
+
+    host = synth.make_batch(args.batch, args.points, seed=synth.SEED_BASE + rank, pin=True)
+    host["pose0"] = torch.stack(host["pose0"]).pin_memory()
+    host["pose1"] = torch.stack(host["pose1"]).pin_memory()
+    resident = synth.batch_to(host, dev, non_blocking=False)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step(batch):
+        opt.zero_grad(set_to_none=True)
+        res = net(batch)
+        loss = d.training_step_loss(batch, res, args.loss)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)  # OSF/conf/config.yaml:26
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, out
+
+    for _ in range(max(args.warmup, 3)):
+        loss = step(resident)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    ms, loss = timed(lambda: step(resident), args.steps)
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop() if clocks else None
+    pairs = args.batch * world
+    value = pairs / (ms * 1e-3)
+
+    # stage breakdown (one extra step with events; not part of `value`)
+    stages = {}
+    if rank == 0:
+        evs = {}
+        orig = {}
+
+        def wrap(name, obj, attr):
+            f = getattr(obj, attr)
+            orig[(obj, attr)] = f
+
+            def g(*a, **k):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); r = f(*a, **k); e.record()
+                evs.setdefault(name, []).append((s, e))
+                return r
+            setattr(obj, attr, g)
+        wrap("embed(index+pfn)", model.embedder, "embed")
+        wrap("unet_fwd", model.backbone, "forward_nhwc")
+        wrap("decoder_fwd", model.head, "forward_flat")
+        s0, s1, s2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        opt.zero_grad(set_to_none=True)
+        s0.record()
+        res = model(resident)
+        lo = d.training_step_loss(resident, res, args.loss)
+        s1.record()
+        lo.backward()
+        s2.record()
+        torch.cuda.synchronize()
+        for (obj, attr), f in orig.items():
+            setattr(obj, attr, f)
+        stages = {k: sum(s.elapsed_time(e) for s, e in v) for k, v in evs.items()}
+        stages["forward_total"] = s0.elapsed_time(s1)
+        stages["backward_total"] = s1.elapsed_time(s2)
+        idx = res["_dfb"]["index"]
+        stages["valid_points_pc0"] = idx.pt_off(args.batch)
+        stages["pillars_total"] = idx.pil_off(2 * args.batch)
+    if world > 1:
+        dist.barrier()
+
+    # end to end through the public API with HOST (pinned) inputs: H2D inside the timed region, loss read back
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            b = synth.batch_to(host, dev, non_blocking=True)
+            l = step(b)
+            return float(l)  # D2H read of the step's result
+        for _ in range(2):
+            e2e_step()
+        ems, _ = timed(e2e_step, args.steps)
+        e2e = {"value": pairs / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": 4 * world}
+
+    line = None
+    if rank == 0:
+        scatter = None
+        if not args.no_scatter:
+            try:
+                scatter = scatter_microbench(dev, peaks)
+            except Exception as ex:  # noqa: BLE001
+                scatter = {"error": repr(ex)}
+        # roofline: UNet fwd+bwd FLOPs (343.06 GFLOP fwd / pair @512^2, x3 for training) against the
+        # sustained bf16 tensor peak; the dense contractions currently run in cuDNN/cuBLAS (library baseline).
+        flop_pair = 343.06e9 * (args.grid / 512.0) ** 2
+        n0 = stages.get("valid_points_pc0", 0)
+        dec_flop = (602688 if args.decoder == "gru" else 17344) * n0
+        flops_step = 3 * (flop_pair * args.batch + dec_flop)
+        ach = flops_step / (ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                "note": f"whole-step algorithmic FLOPs / step time, peak = sustained bf16 ({peaks['source']}); "
+                        "dense contractions still run in cuDNN/cuBLAS this round (see DESIGN.md status)"}
+        cpu = None
+        if not args.no_cpu_baseline:
+            pts = args.cpu_points or args.points
+            v, t, cores = cpu_reference_pairs_per_sec(pts, args.grid, args.decoder, args.loss, 1, 0)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"1 frame pair ({pts} pts/frame, {args.grid}x{args.grid}) fwd+loss+bwd, fp32 torch-CPU oracle port, {t:.1f} s"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "scatter": scatter, "stages_ms": stages, "loss": float(loss)}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

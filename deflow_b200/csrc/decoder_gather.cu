@@ -1,0 +1,141 @@
+// Pillar -> point gather of the flow decoders and its backward.
+//
+// Reference: ConvGRUDecoder.forward_single / LinearDecoder.forward_single
+// (OpenSceneFlow/src/models/basic/decoder.py:215-225 and :86-94) index two NCHW images with
+// img[:, y, x] -- a channel-strided read (1 MB between channels at 512x512) -- and autograd's
+// backward is index_put_(accumulate=True) with float atomics.  Here the images are NHWC, so a point
+// reads two/three contiguous rows, and the backward is an atomic-free segment sum over the CSR point
+// list of every pc0 pillar.
+//
+// h0[p] = [ img[b, y, x, 0:32] | img[B + b, y, x, 0:32] | unet[b, y, x, 0:64] ]   (deflow.py:92-94)
+#include "common.cuh"
+#include "../../include/deflow_b200.h"
+
+namespace dfb {
+
+template <bool BF>
+__device__ __forceinline__ float4 load4(const void* base, size_t elem) {
+  if (BF) {
+    const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  } else {
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+  }
+}
+
+template <bool BF>
+__device__ __forceinline__ void store4(void* base, size_t elem, float4 v) {
+  if (BF) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<unsigned*>(&a);
+    r.y = *reinterpret_cast<unsigned*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem) = r;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem) = v;
+  }
+}
+
+// One warp per point; lane l owns channels 4l..4l+3 of the 128-wide row.
+template <bool IN_BF, bool OUT_BF>
+__global__ void __launch_bounds__(256) k_decoder_gather(const void* __restrict__ img, const void* __restrict__ unet,
+                                                        int B, int HW, const int* __restrict__ counts, int F,
+                                                        const int* __restrict__ pt_pillar,
+                                                        const int* __restrict__ pil_pix, void* __restrict__ h0,
+                                                        int n_cap) {
+  const int n = min(counts[2 * F + B], n_cap);  // pc0 points = frames 0..B-1
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n; p += warps) {
+    const int pix = pil_pix[pt_pillar[p]];  // b*HW + y*W + x
+    float4 v;
+    if (lane < 8) v = load4<IN_BF>(img, (size_t)pix * 32 + lane * 4);
+    else if (lane < 16) v = load4<IN_BF>(img, ((size_t)pix + (size_t)B * HW) * 32 + (lane - 8) * 4);
+    else v = load4<IN_BF>(unet, (size_t)pix * 64 + (lane - 16) * 4);
+    store4<OUT_BF>(h0, (size_t)p * 128 + lane * 4, v);
+  }
+}
+
+// One warp per pc0 pillar: sum the 128-wide gradient rows of its points, write the three NHWC rows.
+template <bool IN_BF, bool OUT_BF>
+__global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restrict__ grad_h0, int B, int HW,
+                                                            const int* __restrict__ counts, int F,
+                                                            const int* __restrict__ pil_pix,
+                                                            const int* __restrict__ pil_start,
+                                                            const int* __restrict__ sorted_pt,
+                                                            void* __restrict__ grad_img, void* __restrict__ grad_unet,
+                                                            int pil_cap) {
+  const int M0 = min(counts[3 * F + 1 + B], pil_cap);  // pillars of the pc0 frames
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < M0; q += warps) {
+    const int s0 = pil_start[q], s1 = pil_start[q + 1];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    int j = s0;
+    for (; j + 1 < s1; j += 2) {  // two rows in flight
+      const int p0 = sorted_pt[j], p1 = sorted_pt[j + 1];
+      const float4 v0 = load4<IN_BF>(grad_h0, (size_t)p0 * 128 + lane * 4);
+      const float4 v1 = load4<IN_BF>(grad_h0, (size_t)p1 * 128 + lane * 4);
+      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+      b.x += v1.x; b.y += v1.y; b.z += v1.z; b.w += v1.w;
+    }
+    if (j < s1) {
+      const float4 v0 = load4<IN_BF>(grad_h0, (size_t)sorted_pt[j] * 128 + lane * 4);
+      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+    }
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    const int pix = pil_pix[q];
+    if (lane < 8) store4<OUT_BF>(grad_img, (size_t)pix * 32 + lane * 4, a);
+    else if (lane < 16) store4<OUT_BF>(grad_img, ((size_t)pix + (size_t)B * HW) * 32 + (lane - 8) * 4, a);
+    else store4<OUT_BF>(grad_unet, (size_t)pix * 64 + (lane - 16) * 4, a);
+  }
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" int dfb_decoder_gather(const void* img, const void* unet, int in_bf16, int B, int H, int W,
+                                  const int* counts, int F, const int* pt_pillar, const int* pil_pix, void* h0,
+                                  int out_bf16, int n_cap, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (B <= 0 || F < B || H <= 0 || W <= 0) { set_error("dfb_decoder_gather: bad sizes"); return DFB_ERR_ARG; }
+  if (n_cap <= 0) return DFB_OK;
+  long long blocks = ((long long)n_cap * 32 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  const int g = (int)blocks, HW = H * W;
+  if (in_bf16 && out_bf16) k_decoder_gather<true, true><<<g, 256, 0, st>>>(img, unet, B, HW, counts, F, pt_pillar, pil_pix, h0, n_cap);
+  else if (in_bf16) k_decoder_gather<true, false><<<g, 256, 0, st>>>(img, unet, B, HW, counts, F, pt_pillar, pil_pix, h0, n_cap);
+  else if (out_bf16) k_decoder_gather<false, true><<<g, 256, 0, st>>>(img, unet, B, HW, counts, F, pt_pillar, pil_pix, h0, n_cap);
+  else k_decoder_gather<false, false><<<g, 256, 0, st>>>(img, unet, B, HW, counts, F, pt_pillar, pil_pix, h0, n_cap);
+  add_launches(1);
+  return check_launch("dfb_decoder_gather");
+}
+
+extern "C" int dfb_decoder_gather_backward(const void* grad_h0, int grad_bf16, int B, int H, int W,
+                                           const int* counts, int F, const int* pil_pix, const int* pil_start,
+                                           const int* sorted_pt, void* grad_img, void* grad_unet, int out_bf16,
+                                           int pil_cap, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (B <= 0 || F < B || H <= 0 || W <= 0) { set_error("dfb_decoder_gather_backward: bad sizes"); return DFB_ERR_ARG; }
+  const size_t HW = (size_t)H * W, es = out_bf16 ? 2 : 4;
+  // dense gradients: zero everywhere except the pc0 pillars (index_put_ accumulate into zeros)
+  cudaMemsetAsync(grad_img, 0, (size_t)2 * B * HW * 32 * es, st);
+  cudaMemsetAsync(grad_unet, 0, (size_t)B * HW * 64 * es, st);
+  if (pil_cap > 0) {
+    long long blocks = ((long long)pil_cap * 32 + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    const int g = (int)blocks;
+    if (grad_bf16 && out_bf16) k_decoder_gather_bwd<true, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap);
+    else if (grad_bf16) k_decoder_gather_bwd<true, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap);
+    else if (out_bf16) k_decoder_gather_bwd<false, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap);
+    else k_decoder_gather_bwd<false, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap);
+    add_launches(1);
+  }
+  return check_launch("dfb_decoder_gather_backward");
+}

@@ -1,0 +1,389 @@
+// Fused pillar feature net (forward + backward) for all frames of a step.
+//
+// Reference path: DynamicPillarFeatureNet.forward (OpenSceneFlow/src/models/basic/encoder.py:430-475)
+//   cluster_scatter (mean xyz per pillar)  -> map_voxel_center_to_point -> decorations [N,9]
+//   -> Linear(9,32,no bias) -> BatchNorm1d(32, eps 1e-3, momentum 0.01) -> ReLU -> pfn_scatter (mean)
+// followed by PointPillarsScatter.forward_single (encoder.py:126-147).
+//
+// Here the [N,9] and [N,32] per-point tensors are never written to HBM: every pass recomputes the
+// 9 decorations from the 12-byte point and the pillar mean/centre.  Passes:
+//   pillar_mean  (CSR segment sum, 8 lanes per pillar)
+//   stats x2     (per-frame BatchNorm batch statistics: sum(y), then sum((y-mean)^2))
+//   bn_finalize  (scale/shift per frame + the 2B sequential running-stat updates)
+//   pfn_pillar   (warp per pillar, lane = channel: Linear+BN+ReLU+mean, writes the NHWC image)
+// Backward: two pillar-centric passes (BN reduction terms, then weight gradient) + finalize.
+#include "common.cuh"
+#include "../../include/deflow_b200.h"
+
+namespace dfb {
+
+constexpr int PFN_C = 32;
+constexpr int PFN_K = 9;
+
+struct PfnGeom {
+  float vx, vy, vz;
+  float ox, oy, oz;  // centre offsets v/2 + range_min (fp32-rounded python doubles)
+};
+
+// decorations of encoder.py:446-465; every product / sum individually rounded like the torch ops
+__device__ __forceinline__ void decorate(float x, float y, float z, float mx, float my, float mz, int cz, int cy,
+                                         int cx, const PfnGeom& G, float* f) {
+  f[0] = x; f[1] = y; f[2] = z;
+  f[3] = __fsub_rn(x, mx); f[4] = __fsub_rn(y, my); f[5] = __fsub_rn(z, mz);
+  f[6] = __fsub_rn(x, __fadd_rn(__fmul_rn((float)cx, G.vx), G.ox));
+  f[7] = __fsub_rn(y, __fadd_rn(__fmul_rn((float)cy, G.vy), G.oy));
+  f[8] = __fsub_rn(z, __fadd_rn(__fmul_rn((float)cz, G.vz), G.oz));
+}
+
+// ---------------------------------------------------------------- pillar mean (cluster_scatter)
+__global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ counts, int F,
+                                                     const float* __restrict__ pt_xyz,
+                                                     const int* __restrict__ pil_start,
+                                                     const int* __restrict__ sorted_pt, float* __restrict__ pil_mean) {
+  const int M = counts[3 * F + 1 + F];
+  const int sub = threadIdx.x & 7;
+  const int groups = (gridDim.x * blockDim.x) >> 3;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; q < ((M + 3) & ~3); q += groups) {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    int s0 = 0, s1 = 0;
+    if (q < M) { s0 = pil_start[q]; s1 = pil_start[q + 1]; }
+    for (int j = s0 + sub; j < s1; j += 8) {
+      const int p = sorted_pt[j];
+      sx += pt_xyz[3 * (size_t)p]; sy += pt_xyz[3 * (size_t)p + 1]; sz += pt_xyz[3 * (size_t)p + 2];
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    if (sub == 0 && q < M) {
+      const float n = (float)(s1 - s0);  // reduced_feats /= count.to(float) (scatter_points_cuda.cu:59-60)
+      pil_mean[3 * (size_t)q] = __fdiv_rn(sx, n);
+      pil_mean[3 * (size_t)q + 1] = __fdiv_rn(sy, n);
+      pil_mean[3 * (size_t)q + 2] = __fdiv_rn(sz, n);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- BatchNorm batch statistics
+// grid (X, F); thread per point, 32 channel accumulators per thread.  PASS 0: sum(y); PASS 1:
+// sum((y - mean)^2).  stats layout [F][2][32] (double).
+template <int PASS>
+__global__ void __launch_bounds__(256) k_pfn_stats(const int* __restrict__ counts, int F, PfnGeom G,
+                                                   const float* __restrict__ pt_xyz, const int* __restrict__ pt_coor,
+                                                   const int* __restrict__ pt_pillar,
+                                                   const float* __restrict__ pil_mean,
+                                                   const float* __restrict__ weight, double* __restrict__ stats) {
+  __shared__ __align__(16) float Wt[PFN_K][PFN_C];  // transposed: Wt[k][c]
+  __shared__ float mean_s[PFN_C];
+  __shared__ float red[8][PFN_C];
+  const int f = blockIdx.y;
+  const int p0 = counts[2 * F + f], p1 = counts[2 * F + f + 1];
+  for (int i = threadIdx.x; i < PFN_C * PFN_K; i += blockDim.x) Wt[i % PFN_K][i / PFN_K] = weight[i];
+  if (threadIdx.x < PFN_C) {
+    const double n = (double)(p1 - p0);
+    mean_s[threadIdx.x] = (PASS == 1 && p1 > p0) ? (float)(stats[(size_t)f * 2 * PFN_C + threadIdx.x] / n) : 0.f;
+  }
+  __syncthreads();
+  float acc[PFN_C];
+#pragma unroll
+  for (int c = 0; c < PFN_C; ++c) acc[c] = 0.f;
+  for (int p = p0 + blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += gridDim.x * blockDim.x) {
+    const float x = pt_xyz[3 * (size_t)p], y = pt_xyz[3 * (size_t)p + 1], z = pt_xyz[3 * (size_t)p + 2];
+    const int q = pt_pillar[p];
+    float fe[PFN_K];
+    decorate(x, y, z, pil_mean[3 * (size_t)q], pil_mean[3 * (size_t)q + 1], pil_mean[3 * (size_t)q + 2],
+             pt_coor[3 * (size_t)p], pt_coor[3 * (size_t)p + 1], pt_coor[3 * (size_t)p + 2], G, fe);
+#pragma unroll
+    for (int c4 = 0; c4 < PFN_C; c4 += 4) {
+      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+#pragma unroll
+      for (int k = 0; k < PFN_K; ++k) {
+        const float4 w = *reinterpret_cast<const float4*>(&Wt[k][c4]);
+        y0 = fmaf(w.x, fe[k], y0); y1 = fmaf(w.y, fe[k], y1); y2 = fmaf(w.z, fe[k], y2); y3 = fmaf(w.w, fe[k], y3);
+      }
+      if (PASS == 0) {
+        acc[c4] += y0; acc[c4 + 1] += y1; acc[c4 + 2] += y2; acc[c4 + 3] += y3;
+      } else {
+        const float d0 = y0 - mean_s[c4], d1 = y1 - mean_s[c4 + 1], d2 = y2 - mean_s[c4 + 2], d3 = y3 - mean_s[c4 + 3];
+        acc[c4] = fmaf(d0, d0, acc[c4]); acc[c4 + 1] = fmaf(d1, d1, acc[c4 + 1]);
+        acc[c4 + 2] = fmaf(d2, d2, acc[c4 + 2]); acc[c4 + 3] = fmaf(d3, d3, acc[c4 + 3]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < PFN_C; ++c) {
+    const float s = warp_sum(acc[c]);
+    if (lane == 0) red[w][c] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < PFN_C) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += (double)red[i][threadIdx.x];
+    atomicAdd(&stats[(size_t)f * 2 * PFN_C + PASS * PFN_C + threadIdx.x], s);
+  }
+}
+
+// One warp: per-frame scale/shift and the sequential running-statistics updates in the reference's
+// call order pc0[0..B-1], pc1[0..B-1] (encoder.py:624-627, DeFlow.forward deflow.py:82-83).
+__global__ void k_bn_finalize(const int* __restrict__ counts, int F, int training, float eps, float momentum,
+                              const double* __restrict__ stats, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ running_mean,
+                              float* __restrict__ running_var, float* __restrict__ bn_params) {
+  const int c = threadIdx.x;
+  if (c >= PFN_C) return;
+  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+  const float g = gamma[c], b = beta[c];
+  for (int f = 0; f < F; ++f) {
+    const int n = counts[f];
+    float mean, var;
+    if (training && n > 0) {
+      mean = (float)(stats[(size_t)f * 2 * PFN_C + c] / (double)n);
+      var = (float)(stats[(size_t)f * 2 * PFN_C + PFN_C + c] / (double)n);  // biased, used to normalise
+      if (n > 1) {
+        const float unbiased = (float)(stats[(size_t)f * 2 * PFN_C + PFN_C + c] / (double)(n - 1));
+        rm = (1.f - momentum) * rm + momentum * mean;
+        rv = (1.f - momentum) * rv + momentum * unbiased;
+      }
+    } else {
+      mean = rm; var = rv;
+    }
+    const float rstd = 1.0f / sqrtf(var + eps);
+    const float a = g * rstd;
+    float* o = bn_params + (size_t)f * 4 * PFN_C;
+    o[c] = a;
+    o[PFN_C + c] = b - mean * a;
+    o[2 * PFN_C + c] = mean;
+    o[3 * PFN_C + c] = rstd;
+  }
+  if (training && running_mean) { running_mean[c] = rm; running_var[c] = rv; }
+}
+
+// ---------------------------------------------------------------- pillar pass (forward)
+// Warp per pillar, lane = output channel.  Point coordinates of a pillar are loaded 32 at a time
+// (one per lane) and broadcast with shuffles.
+template <bool BF16>
+__global__ void __launch_bounds__(256) k_pfn_pillar(const int* __restrict__ counts, int F, int HW, PfnGeom G,
+                                                    const float* __restrict__ pt_xyz,
+                                                    const int* __restrict__ pil_coor, const int* __restrict__ pil_pix,
+                                                    const int* __restrict__ pil_start,
+                                                    const int* __restrict__ sorted_pt,
+                                                    const float* __restrict__ pil_mean,
+                                                    const float* __restrict__ weight,
+                                                    const float* __restrict__ bn_params,
+                                                    float* __restrict__ pil_feats, void* __restrict__ image) {
+  const int M = counts[3 * F + 1 + F];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  float w[PFN_K];
+#pragma unroll
+  for (int k = 0; k < PFN_K; ++k) w[k] = weight[lane * PFN_K + k];
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < M; q += warps) {
+    const int s0 = pil_start[q], s1 = pil_start[q + 1];
+    const int pix = pil_pix[q];
+    const int f = pix / HW;
+    const float a = bn_params[(size_t)f * 4 * PFN_C + lane], b = bn_params[(size_t)f * 4 * PFN_C + PFN_C + lane];
+    const float mx = pil_mean[3 * (size_t)q], my = pil_mean[3 * (size_t)q + 1], mz = pil_mean[3 * (size_t)q + 2];
+    const int cz = pil_coor[3 * (size_t)q], cy = pil_coor[3 * (size_t)q + 1], cx = pil_coor[3 * (size_t)q + 2];
+    float sum = 0.f;
+    for (int base = s0; base < s1; base += 32) {
+      const int cnt = min(32, s1 - base);
+      float lx = 0.f, ly = 0.f, lz = 0.f;
+      if (lane < cnt) {
+        const int p = sorted_pt[base + lane];
+        lx = pt_xyz[3 * (size_t)p]; ly = pt_xyz[3 * (size_t)p + 1]; lz = pt_xyz[3 * (size_t)p + 2];
+      }
+      for (int j = 0; j < cnt; ++j) {
+        const float x = __shfl_sync(0xffffffffu, lx, j), y = __shfl_sync(0xffffffffu, ly, j),
+                    z = __shfl_sync(0xffffffffu, lz, j);
+        float fe[PFN_K];
+        decorate(x, y, z, mx, my, mz, cz, cy, cx, G, fe);
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < PFN_K; ++k) acc = fmaf(w[k], fe[k], acc);
+        sum += fmaxf(fmaf(acc, a, b), 0.f);
+      }
+    }
+    const float mean = __fdiv_rn(sum, (float)(s1 - s0));
+    pil_feats[(size_t)q * PFN_C + lane] = mean;
+    if (BF16) reinterpret_cast<__nv_bfloat16*>(image)[(size_t)pix * PFN_C + lane] = __float2bfloat16_rn(mean);
+    else reinterpret_cast<float*>(image)[(size_t)pix * PFN_C + lane] = mean;
+  }
+}
+
+// ---------------------------------------------------------------- backward
+// grid (X, F): each block works on pillars of one frame, warp per pillar, lane = channel.
+// PASS 0: A1[c] = sum_p gy^[p,c], A2[c] = sum_p gy^[p,c] * xhat[p,c]   (bwd_stats [F][2][32])
+// PASS 1: gW[c,k] += gy[p,c] * f[p,k] with the BatchNorm input gradient
+//         gy = a * (gy^ - A1/N - xhat * A2/N)   (training)   or   a * gy^   (eval)
+template <int PASS, bool BF16>
+__global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F, int HW, int training,
+                                                 PfnGeom G, const float* __restrict__ pt_xyz,
+                                                 const int* __restrict__ pil_coor, const int* __restrict__ pil_pix,
+                                                 const int* __restrict__ pil_start,
+                                                 const int* __restrict__ sorted_pt,
+                                                 const float* __restrict__ pil_mean,
+                                                 const float* __restrict__ weight,
+                                                 const float* __restrict__ bn_params,
+                                                 const void* __restrict__ grad_image, double* __restrict__ bwd_stats,
+                                                 double* __restrict__ grad_accum) {
+  __shared__ float red[8][PFN_C][PFN_K + 1];
+  const int f = blockIdx.y;
+  const int q0 = counts[3 * F + 1 + f], q1 = counts[3 * F + 1 + f + 1];
+  const int n_pts = counts[f];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  float w[PFN_K];
+#pragma unroll
+  for (int k = 0; k < PFN_K; ++k) w[k] = weight[lane * PFN_K + k];
+  const float* bp = bn_params + (size_t)f * 4 * PFN_C;
+  const float a = bp[lane], b = bp[PFN_C + lane], mu = bp[2 * PFN_C + lane], rstd = bp[3 * PFN_C + lane];
+  float m1 = 0.f, m2 = 0.f;
+  if (PASS == 1 && training && n_pts > 0) {
+    m1 = (float)(bwd_stats[(size_t)f * 2 * PFN_C + lane] / (double)n_pts);
+    m2 = (float)(bwd_stats[(size_t)f * 2 * PFN_C + PFN_C + lane] / (double)n_pts);
+  }
+  float acc[PFN_K];
+#pragma unroll
+  for (int k = 0; k < PFN_K; ++k) acc[k] = 0.f;
+  float s1acc = 0.f, s2acc = 0.f;
+  for (int q = q0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); q < q1; q += warps) {
+    const int s0 = pil_start[q], s1 = pil_start[q + 1];
+    const int pix = pil_pix[q];
+    float g = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad_image)[(size_t)pix * PFN_C + lane])
+                   : reinterpret_cast<const float*>(grad_image)[(size_t)pix * PFN_C + lane];
+    g = __fdiv_rn(g, (float)(s1 - s0));  // mean backward: grad / count (scatter_points_cuda_kernel.cuh:134-137)
+    const float mx = pil_mean[3 * (size_t)q], my = pil_mean[3 * (size_t)q + 1], mz = pil_mean[3 * (size_t)q + 2];
+    const int cz = pil_coor[3 * (size_t)q], cy = pil_coor[3 * (size_t)q + 1], cx = pil_coor[3 * (size_t)q + 2];
+    for (int base = s0; base < s1; base += 32) {
+      const int cnt = min(32, s1 - base);
+      float lx = 0.f, ly = 0.f, lz = 0.f;
+      if (lane < cnt) {
+        const int p = sorted_pt[base + lane];
+        lx = pt_xyz[3 * (size_t)p]; ly = pt_xyz[3 * (size_t)p + 1]; lz = pt_xyz[3 * (size_t)p + 2];
+      }
+      for (int j = 0; j < cnt; ++j) {
+        const float x = __shfl_sync(0xffffffffu, lx, j), y = __shfl_sync(0xffffffffu, ly, j),
+                    z = __shfl_sync(0xffffffffu, lz, j);
+        float fe[PFN_K];
+        decorate(x, y, z, mx, my, mz, cz, cy, cx, G, fe);
+        float lin = 0.f;
+#pragma unroll
+        for (int k = 0; k < PFN_K; ++k) lin = fmaf(w[k], fe[k], lin);
+        const float gyh = fmaf(lin, a, b) > 0.f ? g : 0.f;  // ReLU backward
+        const float xhat = (lin - mu) * rstd;
+        if (PASS == 0) {
+          s1acc += gyh;
+          s2acc = fmaf(gyh, xhat, s2acc);
+        } else {
+          const float gy = a * (gyh - m1 - xhat * m2);
+#pragma unroll
+          for (int k = 0; k < PFN_K; ++k) acc[k] = fmaf(gy, fe[k], acc[k]);
+        }
+      }
+    }
+  }
+  if (PASS == 0) {
+    red[wib][lane][0] = s1acc;
+    red[wib][lane][1] = s2acc;
+    __syncthreads();
+    if (threadIdx.x < 2 * PFN_C) {
+      const int c = threadIdx.x & 31, which = threadIdx.x >> 5;
+      double s = 0.0;
+      for (int i = 0; i < 8; ++i) s += (double)red[i][c][which];
+      atomicAdd(&bwd_stats[(size_t)f * 2 * PFN_C + which * PFN_C + c], s);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PFN_K; ++k) red[wib][lane][k] = acc[k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < PFN_C * PFN_K; i += blockDim.x) {
+      const int c = i / PFN_K, k = i % PFN_K;
+      double s = 0.0;
+      for (int j = 0; j < 8; ++j) s += (double)red[j][c][k];
+      atomicAdd(&grad_accum[i], s);
+    }
+  }
+}
+
+__global__ void k_pfn_bwd_finalize(int F, const double* __restrict__ bwd_stats, const double* __restrict__ grad_accum,
+                                   float* __restrict__ grad_weight, float* __restrict__ grad_gamma,
+                                   float* __restrict__ grad_beta) {
+  const int t = threadIdx.x;
+  for (int i = t; i < PFN_C * PFN_K; i += blockDim.x) grad_weight[i] += (float)grad_accum[i];
+  if (t < PFN_C) {
+    double gb = 0.0, gg = 0.0;
+    for (int f = 0; f < F; ++f) {
+      gb += bwd_stats[(size_t)f * 2 * PFN_C + t];
+      gg += bwd_stats[(size_t)f * 2 * PFN_C + PFN_C + t];
+    }
+    grad_beta[t] += (float)gb;
+    grad_gamma[t] += (float)gg;
+  }
+}
+
+static PfnGeom make_geom(const dfb_pfn_args* a) {
+  PfnGeom G;
+  G.vx = a->voxel_size[0]; G.vy = a->voxel_size[1]; G.vz = a->voxel_size[2];
+  G.ox = a->center_off[0]; G.oy = a->center_off[1]; G.oz = a->center_off[2];
+  return G;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!a || a->F <= 0 || a->H <= 0 || a->W <= 0) { set_error("dfb_pfn_forward: bad sizes"); return DFB_ERR_ARG; }
+  const int F = a->F, HW = a->H * a->W;
+  const PfnGeom G = make_geom(a);
+  const int sms = sm_count();
+  const size_t img_bytes = (size_t)F * HW * PFN_C * (a->image_bf16 ? 2 : 4);
+  cudaMemsetAsync(a->image, 0, img_bytes, st);
+  cudaMemsetAsync(a->stats, 0, sizeof(double) * (size_t)F * 2 * PFN_C, st);
+  k_pillar_mean<<<sms * 8, 256, 0, st>>>(a->counts, F, a->pt_xyz, a->pil_start, a->sorted_pt, a->pil_mean);
+  if (a->training) {
+    int bx = (sms * 4 + F - 1) / F;
+    if (bx < 1) bx = 1;
+    dim3 g(bx, F);
+    k_pfn_stats<0><<<g, 256, 0, st>>>(a->counts, F, G, a->pt_xyz, a->pt_coor, a->pt_pillar, a->pil_mean, a->weight, a->stats);
+    k_pfn_stats<1><<<g, 256, 0, st>>>(a->counts, F, G, a->pt_xyz, a->pt_coor, a->pt_pillar, a->pil_mean, a->weight, a->stats);
+  }
+  k_bn_finalize<<<1, 32, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum, a->stats, a->gamma, a->beta,
+                                  a->running_mean, a->running_var, a->bn_params);
+  if (a->image_bf16)
+    k_pfn_pillar<true><<<sms * 8, 256, 0, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pil_coor, a->pil_pix, a->pil_start,
+                                                a->sorted_pt, a->pil_mean, a->weight, a->bn_params, a->pil_feats, a->image);
+  else
+    k_pfn_pillar<false><<<sms * 8, 256, 0, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pil_coor, a->pil_pix, a->pil_start,
+                                                 a->sorted_pt, a->pil_mean, a->weight, a->bn_params, a->pil_feats, a->image);
+  add_launches(a->training ? 5 : 3);
+  return check_launch("dfb_pfn_forward");
+}
+
+extern "C" int dfb_pfn_backward(const dfb_pfn_bwd_args* b, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!b) { set_error("dfb_pfn_backward: null args"); return DFB_ERR_ARG; }
+  const dfb_pfn_args* a = &b->fwd;
+  const int F = a->F, HW = a->H * a->W;
+  const PfnGeom G = make_geom(a);
+  const int sms = sm_count();
+  cudaMemsetAsync(b->bwd_stats, 0, sizeof(double) * (size_t)F * 2 * PFN_C, st);
+  cudaMemsetAsync(b->grad_accum, 0, sizeof(double) * (PFN_C * PFN_K + 64), st);
+  int bx = (sms * 4 + F - 1) / F;
+  if (bx < 1) bx = 1;
+  dim3 g(bx, F);
+#define DFB_BWD(PASS, BF)                                                                                          \
+  k_pfn_bwd<PASS, BF><<<g, 256, 0, st>>>(a->counts, F, HW, a->training, G, a->pt_xyz, a->pil_coor, a->pil_pix,      \
+                                         a->pil_start, a->sorted_pt, a->pil_mean, a->weight, a->bn_params,          \
+                                         b->grad_image, b->bwd_stats, b->grad_accum)
+  if (a->image_bf16) { DFB_BWD(0, true); DFB_BWD(1, true); }
+  else { DFB_BWD(0, false); DFB_BWD(1, false); }
+#undef DFB_BWD
+  k_pfn_bwd_finalize<<<1, 320, 0, st>>>(F, b->bwd_stats, b->grad_accum, b->grad_weight, b->grad_gamma, b->grad_beta);
+  add_launches(3);
+  return check_launch("dfb_pfn_backward");
+}

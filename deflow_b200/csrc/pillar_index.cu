@@ -1,0 +1,247 @@
+// Sort-free, bit-exact pillar indexing for a batch of NaN-padded frames.
+//
+// Replaces, for all 2B frames of a step at once, what the reference does per sample with
+//   DynamicVoxelizer.forward              (OpenSceneFlow/src/models/basic/encoder.py:567-600)
+//   dynamic_voxelize_kernel               (assets/cuda/mmcv/voxelization_cuda_kernel.cuh:13-50)
+//   at::unique_dim + inverse + counts     (assets/cuda/mmcv/scatter_points_cuda.cu:24-37)
+//
+// A linear key (z*gy + y)*gx + x preserves unique_dim's lexicographic (z,y,x) order, so the rank
+// of a cell among the occupied cells of its frame IS the reference's voxel id.  Occupancy lives
+// in a bitmap (1 bit per cell: 32 KB per 512x512 frame, L2 resident); ranks come from a popcount
+// scan; valid points are compacted in their original order (stable), which is what the
+// reference's boolean indexing produces.  A counting sort (one integer atomic per point) builds a
+// CSR list of the points of every pillar so that all later reductions are atomic-free segment sums.
+#include "common.cuh"
+#include "../../include/deflow_b200.h"
+
+namespace dfb {
+
+constexpr int IDX_BLOCK = 256;
+constexpr int IDX_ITEMS = 4;
+constexpr int IDX_CHUNK = IDX_BLOCK * IDX_ITEMS;  // points per block
+
+// ---------------------------------------------------------------- K1: keys + occupancy bitmap
+__global__ void __launch_bounds__(IDX_BLOCK) k_mark_points(const float* __restrict__ pts, int Nmax, int stride,
+                                                          VoxelParams P, int Wd, int nblk,
+                                                          int* __restrict__ keys, unsigned* __restrict__ bitmap,
+                                                          int* __restrict__ blk_cnt) {
+  const int f = blockIdx.y, blk = blockIdx.x;
+  const float* p = pts + (size_t)f * Nmax * stride;
+  int total = 0;
+#pragma unroll
+  for (int j = 0; j < IDX_ITEMS; ++j) {
+    const int i = blk * IDX_CHUNK + j * IDX_BLOCK + threadIdx.x;
+    int key = -1;
+    if (i < Nmax) {
+      const float x = p[(size_t)i * stride], y = p[(size_t)i * stride + 1], z = p[(size_t)i * stride + 2];
+      // NaN rows are dropped before voxelisation (encoder.py:576-577)
+      if (!(isnan(x) || isnan(y) || isnan(z))) {
+        int cx, cy, cz;
+        if (voxel_coords(x, y, z, P, cx, cy, cz) == 0) {
+          key = (cz * P.gy + cy) * P.gx + cx;
+          atomicOr(&bitmap[(size_t)f * Wd + (key >> 5)], 1u << (key & 31));
+        }
+      }
+      keys[(size_t)f * Nmax + i] = key;
+    }
+    total += __syncthreads_count(key >= 0);
+  }
+  if (threadIdx.x == 0) blk_cnt[f * nblk + blk] = total;
+}
+
+// ---------------------------------------------------------------- K2: per-frame scans
+// One 1024-thread block per frame: (a) exclusive scan of the per-block valid counts,
+// (b) exclusive scan of the bitmap popcounts.
+__global__ void __launch_bounds__(1024) k_scan_frame(const unsigned* __restrict__ bitmap, int Wd,
+                                                     int* __restrict__ blk_cnt, int nblk,
+                                                     int* __restrict__ word_rank, int* __restrict__ counts, int F) {
+  __shared__ int sm[33];
+  const int f = blockIdx.x;
+  int carry = 0;
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblk ? blk_cnt[f * nblk + i] : 0;
+    int tot;
+    const int ex = block_excl_scan<1024>(v, sm, tot);
+    if (i < nblk) blk_cnt[f * nblk + i] = carry + ex;  // in place: becomes the block offset
+    carry += tot;
+  }
+  if (threadIdx.x == 0) counts[f] = carry;  // n_valid[f]
+  carry = 0;
+  for (int base = 0; base < Wd; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < Wd ? __popc(bitmap[(size_t)f * Wd + i]) : 0;
+    int tot;
+    const int ex = block_excl_scan<1024>(v, sm, tot);
+    if (i < Wd) word_rank[(size_t)f * Wd + i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) counts[F + f] = carry;  // n_pil[f]
+}
+
+// K2b: frame offsets (F is tiny).  counts = n_valid[F] | n_pil[F] | pt_off[F+1] | pil_off[F+1]
+__global__ void k_frame_offsets(int* __restrict__ counts, int F) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int a = 0, b = 0;
+    for (int f = 0; f < F; ++f) {
+      counts[2 * F + f] = a;
+      counts[3 * F + 1 + f] = b;
+      a += counts[f];
+      b += counts[F + f];
+    }
+    counts[2 * F + F] = a;
+    counts[3 * F + 1 + F] = b;
+  }
+}
+
+// ---------------------------------------------------------------- K3: stable compaction + rank + slot
+__global__ void __launch_bounds__(IDX_BLOCK) k_compact(
+    const float* __restrict__ pts, const int* __restrict__ keys, int Nmax, int stride, VoxelParams P, int Wd,
+    int nblk, int F, int HW, const unsigned* __restrict__ bitmap, const int* __restrict__ word_rank,
+    const int* __restrict__ blk_off, const int* __restrict__ counts, float* __restrict__ pt_xyz,
+    int* __restrict__ pt_coor, long long* __restrict__ pt_idx, float* __restrict__ pt_offs,
+    int* __restrict__ pt_pillar, int* __restrict__ pt_slot, int* __restrict__ pil_cnt, int* __restrict__ pil_coor,
+    int* __restrict__ pil_pix) {
+  __shared__ int sm[33];
+  const int f = blockIdx.y, blk = blockIdx.x;
+  const float* p = pts + (size_t)f * Nmax * stride;
+  const int pt_base = counts[2 * F + f] + blk_off[f * nblk + blk];
+  const int pil_base = counts[3 * F + 1 + f];
+  int carry = 0;
+  const float hx = P.vx / 2, hy = P.vy / 2, hz = P.vz / 2;  // voxel_size / 2 (encoder.py:519)
+#pragma unroll 1
+  for (int j = 0; j < IDX_ITEMS; ++j) {
+    const int i = blk * IDX_CHUNK + j * IDX_BLOCK + threadIdx.x;
+    const int key = i < Nmax ? keys[(size_t)f * Nmax + i] : -1;
+    int tot;
+    const int ex = block_excl_scan<IDX_BLOCK>(key >= 0 ? 1 : 0, sm, tot);
+    if (key >= 0) {
+      const int dst = pt_base + carry + ex;
+      const float x = p[(size_t)i * stride], y = p[(size_t)i * stride + 1], z = p[(size_t)i * stride + 2];
+      const int cx = key % P.gx, t = key / P.gx, cy = t % P.gy, cz = t / P.gy;
+      pt_xyz[3 * (size_t)dst] = x;
+      pt_xyz[3 * (size_t)dst + 1] = y;
+      pt_xyz[3 * (size_t)dst + 2] = z;
+      pt_coor[3 * (size_t)dst] = cz;
+      pt_coor[3 * (size_t)dst + 1] = cy;
+      pt_coor[3 * (size_t)dst + 2] = cx;
+      pt_idx[dst] = i;
+      // point_offsets = p - ((c * vs + min) + vs / 2), every step rounded to fp32 (encoder.py:516-523)
+      pt_offs[3 * (size_t)dst] = __fsub_rn(x, __fadd_rn(__fadd_rn(__fmul_rn((float)cx, P.vx), P.lox), hx));
+      pt_offs[3 * (size_t)dst + 1] = __fsub_rn(y, __fadd_rn(__fadd_rn(__fmul_rn((float)cy, P.vy), P.loy), hy));
+      pt_offs[3 * (size_t)dst + 2] = __fsub_rn(z, __fadd_rn(__fadd_rn(__fmul_rn((float)cz, P.vz), P.loz), hz));
+      const unsigned word = bitmap[(size_t)f * Wd + (key >> 5)];
+      const int rank = word_rank[(size_t)f * Wd + (key >> 5)] + __popc(word & ((1u << (key & 31)) - 1u));
+      const int q = pil_base + rank;
+      pt_pillar[dst] = q;
+      const int slot = atomicAdd(&pil_cnt[q], 1);
+      pt_slot[dst] = slot;
+      if (slot == 0) {  // exactly one point per pillar sees slot 0
+        pil_coor[3 * (size_t)q] = cz;
+        pil_coor[3 * (size_t)q + 1] = cy;
+        pil_coor[3 * (size_t)q + 2] = cx;
+        pil_pix[q] = f * HW + cy * P.gx + cx;  // PointPillarsScatter: y * nx + x (encoder.py:141)
+      }
+    }
+    carry += tot;
+  }
+}
+
+// ---------------------------------------------------------------- K4: CSR offsets of the pillars
+// One block per frame; pil_start[q] = pt_off[f] + exclusive scan of the counts of that frame.
+__global__ void __launch_bounds__(1024) k_pillar_scan(const int* __restrict__ pil_cnt, const int* __restrict__ counts,
+                                                      int F, int* __restrict__ pil_start) {
+  __shared__ int sm[33];
+  const int f = blockIdx.x;
+  const int q0 = counts[3 * F + 1 + f], q1 = counts[3 * F + 1 + f + 1];
+  int carry = counts[2 * F + f];
+  for (int base = q0; base < q1; base += 1024) {
+    const int q = base + threadIdx.x;
+    const int v = q < q1 ? pil_cnt[q] : 0;
+    int tot;
+    const int ex = block_excl_scan<1024>(v, sm, tot);
+    if (q < q1) pil_start[q] = carry + ex;
+    carry += tot;
+  }
+  if (f == F - 1 && threadIdx.x == 0) pil_start[q1] = counts[2 * F + F];
+}
+
+// ---------------------------------------------------------------- K5: CSR fill
+__global__ void __launch_bounds__(256) k_fill_csr(const int* __restrict__ counts, int F, int total_cap,
+                                                  const int* __restrict__ pt_pillar, const int* __restrict__ pt_slot,
+                                                  const int* __restrict__ pil_start, int* __restrict__ sorted_pt) {
+  const int n = min(counts[2 * F + F], total_cap);
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+    sorted_pt[pil_start[pt_pillar[p]] + pt_slot[p]] = p;
+}
+
+VoxelParams make_voxel_params(const float* vs, const float* rng) {
+  VoxelParams P;
+  P.vx = vs[0]; P.vy = vs[1]; P.vz = vs[2];
+  P.lox = rng[0]; P.loy = rng[1]; P.loz = rng[2];
+  // const int grid_x = round((coors_x_max - coors_x_min) / voxel_x);  (voxelization_cuda.cu:269)
+  P.gx = (int)roundf((rng[3] - rng[0]) / vs[0]);
+  P.gy = (int)roundf((rng[4] - rng[1]) / vs[1]);
+  P.gz = (int)roundf((rng[5] - rng[2]) / vs[2]);
+  return P;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" int dfb_grid_size(const float* voxel_size, const float* range, int* grid_xyz) {
+  VoxelParams P = make_voxel_params(voxel_size, range);
+  grid_xyz[0] = P.gx; grid_xyz[1] = P.gy; grid_xyz[2] = P.gz;
+  return DFB_OK;
+}
+
+extern "C" int dfb_index_workspace(int F, int Nmax, const float* voxel_size, const float* range,
+                                   long long* bitmap_words_per_frame, long long* blocks_per_frame) {
+  VoxelParams P = make_voxel_params(voxel_size, range);
+  if (P.gx <= 0 || P.gy <= 0 || P.gz <= 0) { set_error("dfb_index_workspace: empty voxel grid"); return DFB_ERR_ARG; }
+  const long long cells = (long long)P.gx * P.gy * P.gz;
+  if (cells >= (1ll << 31)) { set_error("dfb_index_workspace: %lld cells do not fit an int32 key", cells); return DFB_ERR_UNSUPPORTED; }
+  *bitmap_words_per_frame = (cells + 31) / 32;
+  *blocks_per_frame = (Nmax + IDX_CHUNK - 1) / IDX_CHUNK;
+  return DFB_OK;
+}
+
+extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!a || a->F <= 0 || a->Nmax < 0 || a->pt_stride < 3) { set_error("dfb_pillar_index: bad sizes"); return DFB_ERR_ARG; }
+  VoxelParams P = make_voxel_params(a->voxel_size, a->range);
+  long long Wd_, nblk_;
+  int rc = dfb_index_workspace(a->F, a->Nmax, a->voxel_size, a->range, &Wd_, &nblk_);
+  if (rc) return rc;
+  const int Wd = (int)Wd_, nblk = (int)(nblk_ > 0 ? nblk_ : 1), F = a->F;
+  const long long cap = (long long)F * a->Nmax;
+  if (cap >= (1ll << 31) || (long long)F * P.gx * P.gy >= (1ll << 31)) {
+    set_error("dfb_pillar_index: batch too large for int32 indexing"); return DFB_ERR_UNSUPPORTED;
+  }
+  const long long pil_cap = a->pil_cap;
+  cudaMemsetAsync(a->bitmap, 0, sizeof(unsigned) * (size_t)F * Wd, st);
+  cudaMemsetAsync(a->pil_cnt, 0, sizeof(int) * (size_t)pil_cap, st);
+  cudaMemsetAsync(a->blk_cnt, 0, sizeof(int) * (size_t)F * nblk, st);
+  if (a->Nmax > 0) {
+    dim3 g((unsigned)nblk_, F);
+    k_mark_points<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, a->keys, a->bitmap, a->blk_cnt);
+  }
+  k_scan_frame<<<F, 1024, 0, st>>>(a->bitmap, Wd, a->blk_cnt, nblk, a->word_rank, a->counts, F);
+  k_frame_offsets<<<1, 32, 0, st>>>(a->counts, F);
+  if (a->Nmax > 0) {
+    dim3 g((unsigned)nblk_, F);
+    k_compact<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->keys, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
+                                       a->word_rank, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
+                                       a->pt_offs, a->pt_pillar, a->pt_slot, a->pil_cnt, a->pil_coor, a->pil_pix);
+  }
+  k_pillar_scan<<<F, 1024, 0, st>>>(a->pil_cnt, a->counts, F, a->pil_start);
+  if (cap > 0) {
+    int blocks = (int)((cap + 255) / 256);
+    int maxb = sm_count() * 8;
+    if (blocks > maxb) blocks = maxb;
+    k_fill_csr<<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pil_start, a->sorted_pt);
+  }
+  add_launches(a->Nmax > 0 ? 6 : 3);
+  return check_launch("dfb_pillar_index");
+}

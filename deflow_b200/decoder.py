@@ -1,0 +1,130 @@
+"""Per-point flow decoders with the reference's parameter tree (OSF/src/models/basic/decoder.py).
+
+state_dict keys: head.offset_encoder.*, head.gru.conv{z,r,q}.* (Conv1d k=1, weight [128,192,1]),
+head.decoder.{0,2}.*.  The pillar->point gather runs for all samples at once on NHWC images
+(deflow_b200/csrc/decoder_gather.cu); the reference loops over samples and gathers channel-strided
+NCHW columns (decoder.py:215-225, 239-253).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class ConvGRU(nn.Module):
+    """decoder.py:177-193: z, r, q gates as k=1 Conv1d over the [h(128), x(64)] channel stack."""
+
+    def __init__(self, input_dim: int = 64, hidden_dim: int = 128):
+        super().__init__()
+        self.convz = nn.Conv1d(input_dim + hidden_dim, hidden_dim, 1)
+        self.convr = nn.Conv1d(input_dim + hidden_dim, hidden_dim, 1)
+        self.convq = nn.Conv1d(input_dim + hidden_dim, hidden_dim, 1)
+
+    def forward(self, h, x):
+        """Reference layout: h[N,128,1], x[N,64,1]."""
+        return self.step(h.squeeze(-1), x.squeeze(-1)).unsqueeze(-1)
+
+    def step(self, h, x):
+        """Row layout: h[N,128], x[N,64] (a k=1 Conv1d is a matmul with weight[:, :, 0])."""
+        hx = torch.cat([h, x], dim=1)
+        z = torch.sigmoid(F.linear(hx, self.convz.weight[:, :, 0], self.convz.bias))
+        r = torch.sigmoid(F.linear(hx, self.convr.weight[:, :, 0], self.convr.bias))
+        q = torch.tanh(F.linear(torch.cat([r * h, x], dim=1), self.convq.weight[:, :, 0], self.convq.bias))
+        return (1 - z) * h + z * q
+
+
+class _GatherDecoder(nn.Module):
+    def _gather(self, before_nhwc, after_nhwc, idx: ops.PillarIndex, B: int, n_rows: int):
+        return ops.decoder_gather(before_nhwc, after_nhwc, idx, B, n_rows, torch.float32)
+
+    def forward(self, before_pseudoimages, after_pseudoimages, voxelizer_infos) -> List[torch.Tensor]:
+        """Reference signature (decoder.py:239-253 / 106-119): before [B,64,H,W] = cat(img0, img1),
+        after [B,64,H,W], list of per-sample dicts.  Rebuilds the flat index from the dicts."""
+        B = before_pseudoimages.shape[0]
+        img = torch.cat([before_pseudoimages[:, :32], before_pseudoimages[:, 32:]], dim=0)
+        img = img.permute(0, 2, 3, 1).contiguous()
+        after = after_pseudoimages.permute(0, 2, 3, 1).contiguous()
+        idx = _index_from_infos(voxelizer_infos, img.shape[1], img.shape[2])
+        n = idx.pt_off(B)
+        flow = self.forward_flat(img, after, idx, B, n, torch.cat([e["point_offsets"] for e in voxelizer_infos], 0))
+        return [flow[idx.pt_off(b):idx.pt_off(b + 1)] for b in range(B)]
+
+
+class ConvGRUDecoder(_GatherDecoder):
+    """decoder.py:195-253."""
+
+    def __init__(self, pseudoimage_channels: int = 64, num_iters: int = 4):
+        super().__init__()
+        self.offset_encoder = nn.Linear(3, pseudoimage_channels)
+        self.gru = ConvGRU(input_dim=pseudoimage_channels, hidden_dim=pseudoimage_channels * 2)
+        self.decoder = nn.Sequential(nn.Linear(pseudoimage_channels * 3, pseudoimage_channels // 2), nn.GELU(),
+                                     nn.Linear(pseudoimage_channels // 2, 3))
+        self.num_iters = num_iters
+        self.compute_dtype = torch.float32
+
+    def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
+        """All pc0 points of the batch at once -> flow [n_rows, 3]."""
+        h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
+        offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(self.compute_dtype == torch.bfloat16)):
+            x = self.offset_encoder(offsets)
+            for _ in range(self.num_iters):
+                h = self.gru.step(h.float(), x.float())
+            return self.decoder(torch.cat([h, x.float()], dim=1)).float()
+
+
+class LinearDecoder(_GatherDecoder):
+    """decoder.py:71-119."""
+
+    def __init__(self, pseudoimage_channels: int = 64):
+        super().__init__()
+        self.offset_encoder = nn.Linear(3, 128)
+        self.decoder = nn.Sequential(nn.Linear(pseudoimage_channels * 4, 32), nn.GELU(), nn.Linear(32, 3))
+        self.compute_dtype = torch.float32
+
+    def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
+        h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
+        offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(self.compute_dtype == torch.bfloat16)):
+            x = self.offset_encoder(offsets)
+            return self.decoder(torch.cat([h, x.float()], dim=1)).float()
+
+
+def _index_from_infos(infos, H, W) -> ops.PillarIndex:
+    """Flat index over the pc0 frames only, rebuilt from per-sample voxel info dicts (used by the
+    reference-signature ``forward``; DeFlow.forward passes its PillarIndex straight through)."""
+    dev = infos[0]["voxel_coords"].device
+    B = len(infos)
+    keys, n_pts = [], []
+    for b, e in enumerate(infos):
+        c = e["voxel_coords"].long()
+        keys.append(b * H * W + c[:, 1] * W + c[:, 2])
+        n_pts.append(c.shape[0])
+    key = torch.cat(keys)
+    pix, inv, cnt = torch.unique(key, sorted=True, return_inverse=True, return_counts=True)
+    order = torch.argsort(inv, stable=True)
+    n_pil = [int(((pix >= b * H * W) & (pix < (b + 1) * H * W)).sum()) for b in range(B)]
+    idx = ops.PillarIndex()
+    F_ = B
+    pt_off = [0]
+    pil_off = [0]
+    for b in range(B):
+        pt_off.append(pt_off[-1] + n_pts[b])
+        pil_off.append(pil_off[-1] + n_pil[b])
+    host = n_pts + n_pil + pt_off + pil_off
+    idx.F, idx.cap, idx.pil_cap = F_, max(int(key.shape[0]), 1), max(int(pix.shape[0]), 1)
+    idx._host = host
+    idx.counts = torch.tensor(host, dtype=torch.int32, device=dev)
+    idx.pt_pillar = inv.to(torch.int32).contiguous()
+    idx.pil_pix = pix.to(torch.int32).contiguous()
+    start = torch.zeros(pix.shape[0] + 1, dtype=torch.int32, device=dev)
+    start[1:] = torch.cumsum(cnt, 0).to(torch.int32)
+    idx.pil_start = start
+    idx.sorted_pt = order.to(torch.int32).contiguous()
+    idx.pt_offs = torch.cat([e["point_offsets"] for e in infos], 0)
+    return idx

@@ -1,0 +1,149 @@
+"""DeFlow / FastFlow3D with the reference's module surface (OSF/src/models/deflow.py:20-114,
+OSF/src/models/fastflow3d.py:42-103): same constructor, same ``forward(batch) -> dict`` contract, same
+``state_dict`` keys -- computed by one batched pass over all 2B frames instead of per-sample loops.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict
+
+import torch
+from torch import nn
+
+from . import ops
+from .decoder import ConvGRUDecoder, LinearDecoder
+from .encoder import DynamicEmbedder
+from .unet import FastFlow3DUNet
+
+
+class _Timing:
+    """Stand-in for ``dztimer.Timing`` (a wall-clock tree with no arithmetic, OSF/src/models/deflow.py:38-39):
+    the trainer calls ``model.timer[i].start(name) / .stop() / .print()`` (OSF/src/trainer.py:95-99,184)."""
+
+    def __init__(self):
+        self._t, self._children = {}, {}
+
+    def __getitem__(self, i):
+        return self._children.setdefault(i, _Timing())
+
+    def start(self, name=""):
+        self._name, self._t0 = name, time.perf_counter()
+
+    def stop(self):
+        if hasattr(self, "_t0"):
+            self._t[self._name] = self._t.get(self._name, 0.0) + time.perf_counter() - self._t0
+
+    def print(self, *a, **k):
+        for name, t in self._t.items():
+            print(f"{name}: {t:.3f}s")
+        for c in self._children.values():
+            c.print()
+
+
+def weights_init(m):
+    """OSF/src/utils/mics.py:98-105: Xavier-uniform on Conv2d / Linear with zero bias, BatchNorm2d 1/0;
+    Conv1d and BatchNorm1d keep the torch defaults."""
+    if isinstance(m, (nn.Conv2d, nn.Linear)):
+        nn.init.xavier_uniform_(m.weight)
+        if m.bias is not None:
+            nn.init.zeros_(m.bias)
+    elif isinstance(m, nn.BatchNorm2d):
+        nn.init.ones_(m.weight)
+        nn.init.zeros_(m.bias)
+
+
+class DeFlow(nn.Module):
+    def __init__(self, voxel_size=[0.2, 0.2, 6], point_cloud_range=[-51.2, -51.2, -3, 51.2, 51.2, 3],
+                 grid_feature_size=[512, 512], decoder_option="gru", num_iters=4, precision="fp32"):
+        super().__init__()
+        self.embedder = DynamicEmbedder(voxel_size=voxel_size, pseudo_image_dims=grid_feature_size,
+                                        point_cloud_range=point_cloud_range, feat_channels=32)
+        self.backbone = FastFlow3DUNet()
+        if decoder_option == "gru":
+            self.head = ConvGRUDecoder(num_iters=num_iters)
+        elif decoder_option == "linear":
+            self.head = LinearDecoder()
+        else:
+            raise ValueError(f"unknown decoder_option {decoder_option}")
+        self.timer = _Timing()
+        self.timer.start("Total")
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str):
+        """'fp32' = parity mode (strict fp32 arithmetic end to end); 'bf16' = perf mode (bf16 operands in
+        the dense contractions, fp32 accumulation / statistics / voxelisation) -- SURVEY.md section 8(d)."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        dt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.backbone.compute_dtype = dt
+        self.head.compute_dtype = dt
+        return self
+
+    def load_from_checkpoint(self, ckpt_path):
+        """deflow.py:41-47: Lightning checkpoint with 'model.'-prefixed keys, strict=False."""
+        ckpt = torch.load(ckpt_path, map_location="cpu")["state_dict"]
+        state_dict = {k[len("model."):]: v for k, v in ckpt.items() if k.startswith("model.")}
+        print("\nLoading... model weight from: ", ckpt_path, "\n")
+        return self.load_state_dict(state_dict=state_dict, strict=False)
+
+    def forward(self, batch: Dict) -> Dict:
+        pc0, pc1 = batch["pc0"], batch["pc1"]
+        if not pc0.is_cuda:
+            raise RuntimeError("deflow_b200.DeFlow runs on CUDA (sm_100a) only; there is no CPU path")
+        B, N0, N1 = pc0.shape[0], pc0.shape[1], pc1.shape[1]
+        assert len(batch["pose0"]) == B
+        self.timer[0].start("Data Preprocess")
+        Nm = max(N0, N1)
+        pts = torch.empty((2 * B, Nm, 3), dtype=torch.float32, device=pc0.device)
+        if N0 < Nm:
+            pts[:B, N0:].fill_(float("nan"))
+        if N1 < Nm:
+            pts[B:, N1:].fill_(float("nan"))
+        pts[B:, :N1].copy_(pc1)
+        if "ego_motion" in batch:
+            ego = batch["ego_motion"]
+            ego = torch.stack(list(ego), 0) if not torch.is_tensor(ego) else ego
+            pose_flow, _ = ops.ego_warp(pc0, None, None, ego.to(pc0.device), pts)
+        else:
+            p0 = torch.stack(list(batch["pose0"]), 0) if not torch.is_tensor(batch["pose0"]) else batch["pose0"]
+            p1 = torch.stack(list(batch["pose1"]), 0) if not torch.is_tensor(batch["pose1"]) else batch["pose1"]
+            pose_flow, _ = ops.ego_warp(pc0, p0.to(pc0.device), p1.to(pc0.device), None, pts)
+        self.timer[0].stop()
+
+        self.timer[1].start("Voxelization")
+        img_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        image, idx = self.embedder.embed(pts, img_dtype)  # [2B,H,W,32]: frames 0..B-1 = pc0, B..2B-1 = pc1
+        self.timer[1].stop()
+
+        self.timer[2].start("Encoder")
+        unet_out = self.backbone.forward_nhwc(image[:B], image[B:])
+        self.timer[2].stop()
+
+        self.timer[3].start("Decoder")
+        n0 = idx.pt_off(B)  # the one host sync of the forward
+        flow_flat = self.head.forward_flat(image, unet_out, idx, B, n0)
+        self.timer[3].stop()
+
+        infos = [idx.frame_info(f) for f in range(2 * B)]
+        return {
+            "flow": [flow_flat[idx.pt_off(b):idx.pt_off(b + 1)] for b in range(B)],
+            "pose_flow": [pose_flow[b] for b in range(B)],
+            "pc0_valid_point_idxes": [e["point_idxes"] for e in infos[:B]],
+            "pc0_points_lst": [e["points"] for e in infos[:B]],
+            "pc1_valid_point_idxes": [e["point_idxes"] for e in infos[B:]],
+            "pc1_points_lst": [e["points"] for e in infos[B:]],
+            "num_occupied_voxels": [unet_out.shape[1] * unet_out.shape[2]],  # dense size, deflow.py:112
+            # flat handles for the fused loss (lossfuncs.training_step_loss); not part of the reference dict
+            "_dfb": {"index": idx, "flow_flat": flow_flat, "pose_flow": pose_flow, "B": B,
+                     "image": image, "unet": unet_out},
+        }
+
+
+class FastFlow3D(DeFlow):
+    """OSF/src/models/fastflow3d.py:42-103 (plain forward; the unused cycle / symmetry passes are not built)."""
+
+    def __init__(self, voxel_size=[0.2, 0.2, 6], point_cloud_range=[-51.2, -51.2, -3, 51.2, 51.2, 3],
+                 grid_feature_size=[512, 512], precision="fp32"):
+        super().__init__(voxel_size, point_cloud_range, grid_feature_size, decoder_option="linear",
+                         precision=precision)

@@ -1,0 +1,176 @@
+"""Pillar encoder with the reference's module surface (OSF/src/models/basic/encoder.py).
+
+``DynamicEmbedder`` is the hot path: one batched pillar-index launch sequence and one fused pillar
+feature net for every frame handed to it, instead of the reference's per-sample Python loop
+(encoder.py:618-631).  ``DynamicVoxelizer``, ``DynamicPillarFeatureNet`` and ``PointPillarsScatter``
+keep the per-sample call signatures for callers that use them directly (Flow4D / SSF do,
+SURVEY.md section 8b); they run on the same kernels through the mmcv drop-ins.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from .mmcv_ext import DynamicScatter, Voxelization
+
+
+class DynamicVoxelizer(nn.Module):
+    """OSF/src/models/basic/encoder.py:496-600."""
+
+    def __init__(self, voxel_size, point_cloud_range):
+        super().__init__()
+        self.voxel_size = voxel_size
+        self.point_cloud_range = point_cloud_range
+        self.voxelizer = Voxelization(voxel_size, point_cloud_range, max_num_points=-1)
+
+    def index(self, points: torch.Tensor) -> ops.PillarIndex:
+        return ops.pillar_index(points, self.voxel_size, self.point_cloud_range)
+
+    def forward(self, points: torch.Tensor) -> List[dict]:
+        idx = self.index(points)
+        return [idx.frame_info(f) for f in range(idx.F)]
+
+
+class DynamicPillarFeatureNet(nn.Module):
+    """OSF/src/models/basic/encoder.py:312-475 (+ the offsets of PillarFeatureNet.__init__, :254-260)."""
+
+    def __init__(self, in_channels, voxel_size, point_cloud_range, feat_channels=(64,), with_distance=False,
+                 with_cluster_center=True, with_voxel_center=True, mode="max"):
+        super().__init__()
+        assert len(feat_channels) > 0
+        self.raw_in_channels = in_channels
+        if with_cluster_center:
+            in_channels += 3
+        if with_voxel_center:
+            in_channels += 3
+        if with_distance:
+            in_channels += 1
+        self._with_distance = with_distance
+        self._with_cluster_center = with_cluster_center
+        self._with_voxel_center = with_voxel_center
+        self.in_channels = in_channels
+        self.mode = mode
+        chans = [in_channels] + list(feat_channels)
+        layers = []
+        for i in range(len(chans) - 1):
+            cin = chans[i] * (2 if i > 0 else 1)
+            layers.append(nn.Sequential(nn.Linear(cin, chans[i + 1], bias=False),
+                                        nn.BatchNorm1d(chans[i + 1], eps=1e-3, momentum=0.01), nn.ReLU(inplace=True)))
+        self.num_pfn = len(layers)
+        self.pfn_layers = nn.ModuleList(layers)
+        self.pfn_scatter = DynamicScatter(voxel_size, point_cloud_range, mode != "max")
+        self.cluster_scatter = DynamicScatter(voxel_size, point_cloud_range, average_points=True)
+        self.vx, self.vy, self.vz = voxel_size[0], voxel_size[1], voxel_size[2]
+        # python doubles, exactly as the reference computes them (encoder.py:257-259)
+        self.x_offset = self.vx / 2 + point_cloud_range[0]
+        self.y_offset = self.vy / 2 + point_cloud_range[1]
+        self.z_offset = self.vz / 2 + point_cloud_range[2]
+        self.point_cloud_range = point_cloud_range
+        self.voxel_size = voxel_size
+
+    @property
+    def fused_ok(self) -> bool:
+        """The fused kernel covers the DeFlow configuration (3 -> 9 -> 32, mean reduce)."""
+        return (self.raw_in_channels == 3 and self._with_cluster_center and self._with_voxel_center
+                and not self._with_distance and self.num_pfn == 1 and self.mode != "max"
+                and self.pfn_layers[0][0].out_features == 32)
+
+    def forward_fused(self, idx: ops.PillarIndex, image_dtype=torch.float32):
+        """All frames of ``idx`` at once -> (NHWC pseudo-image [F,H,W,32], pillar feats, pillar means)."""
+        if not self.fused_ok:
+            raise RuntimeError("the fused pillar feature net covers in_channels=3, one 32-wide PFN layer, mean mode")
+        lin, bn = self.pfn_layers[0][0], self.pfn_layers[0][1]
+        training = self.training or not bn.track_running_stats
+        out = ops.pillar_feature_net(lin.weight, bn.weight, bn.bias, idx, bn.running_mean, bn.running_var, training,
+                                     bn.eps, bn.momentum, (self.x_offset, self.y_offset, self.z_offset), image_dtype)
+        if training and bn.track_running_stats:
+            bn.num_batches_tracked += idx.F  # one BatchNorm1d call per sample-frame in the reference
+        return out
+
+    def forward(self, features: torch.Tensor, coors: torch.Tensor):
+        """Per-sample call, reference signature: features[N,C_in], coors[N,3] (z,y,x) ->
+        (voxel_feats[M,C], voxel_coors[M,3], point_feats[N,C])   (encoder.py:430-475)."""
+        ls = [features]
+        if self._with_cluster_center:
+            voxel_mean, mean_coors = self.cluster_scatter(features, coors)
+            # map_voxel_center_to_point (encoder.py:380-428) == voxel_mean[point2voxel_map]; recover the
+            # map with a sorted search on the linear pillar key instead of a dense canvas + 5 host syncs
+            span = int(max(int(coors.max()) + 1, 1)) if coors.numel() else 1
+            key = (coors[:, 0].long() * span + coors[:, 1].long()) * span + coors[:, 2].long()
+            mkey = (mean_coors[:, 0].long() * span + mean_coors[:, 1].long()) * span + mean_coors[:, 2].long()
+            points_mean = voxel_mean[torch.searchsorted(mkey, key)]
+            ls.append(features[:, :3] - points_mean[:, :3])
+        if self._with_voxel_center:
+            f_center = features.new_zeros(size=(features.size(0), 3))
+            f_center[:, 0] = features[:, 0] - (coors[:, 2].type_as(features) * self.vx + self.x_offset)
+            f_center[:, 1] = features[:, 1] - (coors[:, 1].type_as(features) * self.vy + self.y_offset)
+            f_center[:, 2] = features[:, 2] - (coors[:, 0].type_as(features) * self.vz + self.z_offset)
+            ls.append(f_center)
+        if self._with_distance:
+            ls.append(torch.norm(features[:, :3], 2, 1, keepdim=True))
+        feats = torch.cat(ls, dim=-1)
+        for i, pfn in enumerate(self.pfn_layers):
+            point_feats = pfn(feats)
+            voxel_feats, voxel_coors = self.pfn_scatter(point_feats, coors)
+            if i != len(self.pfn_layers) - 1:
+                raise NotImplementedError("the reference supports a single PFN layer (encoder.py:360)")
+        return voxel_feats, voxel_coors, point_feats
+
+
+class PointPillarsScatter(nn.Module):
+    """OSF/src/models/basic/encoder.py:99-189: pillar features -> dense NCHW canvas."""
+
+    def __init__(self, in_channels, output_shape):
+        super().__init__()
+        self.output_shape = output_shape
+        self.ny, self.nx = output_shape[0], output_shape[1]
+        self.in_channels = in_channels
+
+    def forward(self, voxel_features, coors, batch_size=None):
+        if batch_size is not None:
+            return self.forward_batch(voxel_features, coors, batch_size)
+        return self.forward_single(voxel_features, coors)
+
+    def forward_single(self, voxel_features, coors):
+        canvas = voxel_features.new_zeros((self.in_channels, self.nx * self.ny))
+        indices = (coors[:, 1] * self.nx + coors[:, 2]).long()
+        canvas[:, indices] = voxel_features.t()
+        return canvas.view(1, self.in_channels, self.ny, self.nx)
+
+    def forward_batch(self, voxel_features, coors, batch_size):
+        out = []
+        for b in range(batch_size):
+            m = coors[:, 0] == b
+            out.append(self.forward_single(voxel_features[m], coors[m][:, 1:]))
+        return torch.cat(out, dim=0)
+
+
+class DynamicEmbedder(nn.Module):
+    """OSF/src/models/basic/encoder.py:602-631."""
+
+    def __init__(self, voxel_size, pseudo_image_dims, point_cloud_range, feat_channels: int) -> None:
+        super().__init__()
+        self.voxelizer = DynamicVoxelizer(voxel_size=voxel_size, point_cloud_range=point_cloud_range)
+        self.feature_net = DynamicPillarFeatureNet(in_channels=3, feat_channels=(feat_channels,),
+                                                   point_cloud_range=point_cloud_range, voxel_size=voxel_size,
+                                                   mode="avg")
+        self.scatter = PointPillarsScatter(in_channels=feat_channels, output_shape=pseudo_image_dims)
+        self.pseudo_image_dims = pseudo_image_dims
+
+    def embed(self, points: torch.Tensor, image_dtype=torch.float32):
+        """points f32[F,Nmax,3] NaN-padded -> (NHWC pseudo-images [F,H,W,32], PillarIndex)."""
+        idx = self.voxelizer.index(points)
+        gx, gy, _ = idx.grid
+        if [gy, gx] != [int(self.pseudo_image_dims[0]), int(self.pseudo_image_dims[1])]:
+            raise RuntimeError(f"pseudo_image_dims {self.pseudo_image_dims} do not match the voxel grid {(gy, gx)}")
+        image, _, _ = self.feature_net.forward_fused(idx, image_dtype)
+        return image, idx
+
+    def forward(self, points: torch.Tensor) -> Tuple[torch.Tensor, List[dict]]:
+        """Reference contract: ([B,C,H,W] pseudo-image, list of per-sample voxel info dicts).  The image
+        is returned as an NCHW *view* of the NHWC buffer (channels-last strides)."""
+        image, idx = self.embed(points)
+        return image.permute(0, 3, 1, 2), [idx.frame_info(f) for f in range(idx.F)]

@@ -1,0 +1,100 @@
+"""FastFlow3D UNet backbone with the reference's parameter tree (OSF/src/models/basic/unet.py,
+ConvWithNorms in OSF/src/models/basic/__init__.py:61-79), computing on NHWC tensors.
+
+state_dict keys are the reference's: backbone.encoder_step_{1,2,3}.{i}.{conv,batchnorm}.*,
+backbone.decoder_step{1,2,3}.{u1_u2.0,u3,u4_u5.0,u4_u5.1}.*, backbone.decoder_step4.*.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+
+class ConvWithNorms(nn.Module):
+    """Conv2d(k, stride, pad) -> BatchNorm2d -> GELU (exact erf)  (basic/__init__.py:61-79)."""
+
+    def __init__(self, in_num_channels: int, out_num_channels: int, kernel_size: int, stride: int, padding: int):
+        super().__init__()
+        self.conv = nn.Conv2d(in_num_channels, out_num_channels, kernel_size, stride, padding)
+        self.batchnorm = nn.BatchNorm2d(out_num_channels)
+        self.nonlinearity = nn.GELU()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        y = self.conv(x)
+        if y.shape[2] == 1 and y.shape[3] == 1:  # basic/__init__.py:73-76
+            return self.nonlinearity(y)
+        return self.nonlinearity(self.batchnorm(y))
+
+
+class BilinearDecoder(nn.Module):
+    """unet.py:8-18."""
+
+    def __init__(self, scale_factor: int):
+        super().__init__()
+        self.scale_factor = scale_factor
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return F.interpolate(x, scale_factor=self.scale_factor, mode="bilinear", align_corners=False)
+
+
+class UpsampleSkip(nn.Module):
+    """unet.py:21-37: cat([bilinear2x(conv1x1(a)), conv1x1(b)]) -> conv3x3 -> conv3x3; bias, no norm/activation."""
+
+    def __init__(self, skip_channels: int, latent_channels: int, out_channels: int):
+        super().__init__()
+        self.u1_u2 = nn.Sequential(nn.Conv2d(skip_channels, latent_channels, 1, 1, 0), BilinearDecoder(2))
+        self.u3 = nn.Conv2d(latent_channels, latent_channels, 1, 1, 0)
+        self.u4_u5 = nn.Sequential(nn.Conv2d(2 * latent_channels, out_channels, 3, 1, 1),
+                                   nn.Conv2d(out_channels, out_channels, 3, 1, 1))
+
+    def forward(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        u2 = self.u1_u2(a)
+        u3 = self.u3(b)
+        return self.u4_u5(torch.cat([u2, u3], dim=1))
+
+
+class FastFlow3DUNet(nn.Module):
+    """unet.py:40-100."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.encoder_step_1 = nn.Sequential(ConvWithNorms(32, 64, 3, 2, 1), *[ConvWithNorms(64, 64, 3, 1, 1) for _ in range(3)])
+        self.encoder_step_2 = nn.Sequential(ConvWithNorms(64, 128, 3, 2, 1), *[ConvWithNorms(128, 128, 3, 1, 1) for _ in range(5)])
+        self.encoder_step_3 = nn.Sequential(ConvWithNorms(128, 256, 3, 2, 1), *[ConvWithNorms(256, 256, 3, 1, 1) for _ in range(5)])
+        self.decoder_step1 = UpsampleSkip(512, 256, 256)
+        self.decoder_step2 = UpsampleSkip(256, 128, 128)
+        self.decoder_step3 = UpsampleSkip(128, 64, 64)
+        self.decoder_step4 = nn.Conv2d(64, 64, 3, 1, 1)
+        self.compute_dtype = torch.float32
+
+    def forward(self, pc0_B: torch.Tensor, pc1_B: torch.Tensor) -> torch.Tensor:
+        """[B,32,H,W] x2 -> [B,64,H,W] (any memory format; channels-last is the fast one)."""
+        return self._forward_library(pc0_B, pc1_B)
+
+    def forward_nhwc(self, img0: torch.Tensor, img1: torch.Tensor) -> torch.Tensor:
+        """NHWC [B,H,W,32] x2 -> NHWC [B,H,W,64]."""
+        out = self.forward(img0.permute(0, 3, 1, 2), img1.permute(0, 3, 1, 2))
+        return out.permute(0, 2, 3, 1).contiguous()
+
+    # Interim dense-contraction path: cuDNN through torch (a library baseline, not the product --
+    # DESIGN.md "status").  Replaced layer by layer by the tcgen05 implicit-GEMM kernels.
+    def _forward_library(self, pc0_B, pc1_B):
+        dt = self.compute_dtype
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dt == torch.bfloat16)), \
+                torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            pc0_F = self.encoder_step_1(pc0_B)
+            pc0_L = self.encoder_step_2(pc0_F)
+            pc0_R = self.encoder_step_3(pc0_L)
+            pc1_F = self.encoder_step_1(pc1_B)
+            pc1_L = self.encoder_step_2(pc1_F)
+            pc1_R = self.encoder_step_3(pc1_L)
+            Rstar = torch.cat([pc0_R, pc1_R], dim=1)
+            Lstar = torch.cat([pc0_L, pc1_L], dim=1)
+            Fstar = torch.cat([pc0_F, pc1_F], dim=1)
+            Bstar = torch.cat([pc0_B, pc1_B], dim=1)
+            S = self.decoder_step1(Rstar, Lstar)
+            T = self.decoder_step2(S, Fstar)
+            U = self.decoder_step3(T, Bstar)
+            V = self.decoder_step4(U)
+        return V

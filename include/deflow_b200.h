@@ -1,0 +1,189 @@
+/* deflow_b200 -- C ABI of the B200-native DeFlow hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer unless the
+ * comment says HOST.  Every function is asynchronous on the given stream (a cudaStream_t passed
+ * as void*), returns 0 on success and a DFB_ERR_* code otherwise; dfb_last_error() returns the
+ * message of the last failure on the calling thread.  Nothing here allocates device memory.
+ *
+ * REF = /root/reference/OpenSceneFlow.  Each entry point names the reference interface it
+ * replaces; INTEGRATION.md shows the binding a reference maintainer would add.
+ */
+#ifndef DEFLOW_B200_H
+#define DEFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ library */
+const char* dfb_last_error(void);
+int dfb_version(void);
+/* Number of kernels this library has launched on the calling process so far (bench.py's
+ * "gpu_launches" is the difference across the timed region). */
+long long dfb_launch_count(void);
+
+/* ------------------------------------------------------------------ mmcv._ext drop-ins
+ * REF/assets/cuda/mmcv/pybind.cpp:32-50 -- the four functions `mmcv._ext` exports.
+ * hard_voxelize_forward is not on the DeFlow path (HardVoxelizer is unused) and is not provided.
+ */
+
+/* grid = round((max-min)/voxel) in fp32 (REF/assets/cuda/mmcv/voxelization_cuda.cu:269-271).
+ * voxel_size[3], range[6], grid_xyz[3] are HOST pointers. */
+int dfb_grid_size(const float* voxel_size, const float* range, int* grid_xyz);
+
+/* dynamic_voxelize_forward(points, voxel_size, coors_range, coors, NDim=3)
+ * (REF/assets/cuda/mmcv/voxelization.cpp:62-74, voxelization_cuda_kernel.cuh:13-50).
+ * points f32[n, num_features>=3]; coors i32[n,3] pre-zeroed by the caller, written in (z,y,x)
+ * order with the reference's partial -1 pattern.  voxel_size/range: HOST fp32. */
+int dfb_dynamic_voxelize_forward(const float* points, int n, int num_features, const float* voxel_size,
+                                 const float* range, int* coors, void* stream);
+
+/* dynamic_point_to_voxel_forward(feats, coors, reduce_type)
+ * (REF/assets/cuda/mmcv/scatter_points.cpp:36-41, scatter_points_cuda.cu:9-66) in two calls,
+ * because the number of pillars M is only known on the device:
+ *   1. dfb_scatter_index   builds point2voxel_map[n] (-1 for rows with a negative component),
+ *      voxel_coors[<=n,3] sorted lexicographically, voxel_points_count[<=n], the CSR arrays
+ *      pil_start[<=n+1] / sorted_pt[n], and counts6 (device i32[6]: [0] = number of valid points,
+ *      [1] = number of voxels M; the rest is scratch).  extent[3] (HOST) is an
+ *      exclusive upper bound of the coordinates per column (z,y,x); coordinates >= extent are a
+ *      caller error.  Workspace: bitmap and word_rank of ceil(prod(extent)/32) words each,
+ *      slot[n], blk[ceil(n/1024)].
+ *   2. dfb_scatter_reduce  reduces feats f32[n,c] into voxel_feats f32[M,c];
+ *      reduce_type 0 = sum, 1 = mean, 2 = max (REF reduce_t).
+ */
+int dfb_scatter_index(const int* coors, int n, const int* extent_zyx, unsigned* bitmap, int* word_rank, int* blk,
+                      int* slot, int* point2voxel_map, int* voxel_coors, int* voxel_points_count, int* pil_start,
+                      int* sorted_pt, int* counts6, void* stream);
+int dfb_scatter_reduce(const float* feats, int n, int c, const int* pil_start, const int* sorted_pt,
+                       const int* num_voxels, int max_voxels, int reduce_type, float* voxel_feats, void* stream);
+
+/* dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats, reduced_feats, coors_idx,
+ * reduce_count, reduce_type) (REF/assets/cuda/mmcv/scatter_points.cpp:43-53,
+ * scatter_points_cuda.cu:68-132).  grad_feats f32[n,c] is fully written (zeros where map == -1).
+ * workspace_mc: i32[m*c], only needed for reduce_type 2 (max trace-back), else may be NULL. */
+int dfb_dynamic_point_to_voxel_backward(float* grad_feats, const float* grad_reduced_feats, const float* feats,
+                                        const float* reduced_feats, const int* point2voxel_map,
+                                        const int* voxel_points_count, int n, int m, int c, int reduce_type,
+                                        int* workspace_mc, void* stream);
+
+/* ------------------------------------------------------------------ batched pillar index
+ * Replaces DynamicVoxelizer.forward + the unique_dim half of DynamicScatter for all frames of a
+ * step at once (REF/src/models/basic/encoder.py:567-600; scatter_points_cuda.cu:24-37).
+ * Outputs are flat, frame after frame, valid points in their original order:
+ *   counts   i32[4F+2] = n_valid[F] | n_pillars[F] | pt_off[F+1] | pil_off[F+1]
+ *   pt_xyz   f32[cap,3]  pt_coor i32[cap,3] (z,y,x)  pt_idx i64[cap]  pt_offs f32[cap,3]
+ *   pt_pillar i32[cap]   global pillar id (reference point2voxel_map = pt_pillar - pil_off[f])
+ *   pil_cnt i32[pil_cap] pil_coor i32[pil_cap,3] pil_pix i32[pil_cap] (= f*H*W + y*W + x)
+ *   pil_start i32[pil_cap+1], sorted_pt i32[cap]: CSR list of the points of every pillar
+ * with cap = F*Nmax.  Workspace sizes come from dfb_index_workspace().
+ */
+typedef struct {
+  int F, Nmax, pt_stride;
+  long long pil_cap;
+  float voxel_size[3];
+  float range[6];
+  const float* pts;
+  int* keys;         /* [F*Nmax] */
+  unsigned* bitmap;  /* [F*words] */
+  int* word_rank;    /* [F*words] */
+  int* blk_cnt;      /* [F*blocks] */
+  int* pt_slot;      /* [F*Nmax] */
+  int* counts;
+  float* pt_xyz;
+  int* pt_coor;
+  long long* pt_idx;
+  float* pt_offs;
+  int* pt_pillar;
+  int* pil_cnt;
+  int* pil_coor;
+  int* pil_pix;
+  int* pil_start;
+  int* sorted_pt;
+} dfb_index_args;
+
+int dfb_index_workspace(int F, int Nmax, const float* voxel_size, const float* range,
+                        long long* bitmap_words_per_frame, long long* blocks_per_frame);
+int dfb_pillar_index(const dfb_index_args* args, void* stream);
+
+/* ------------------------------------------------------------------ ego-motion compensation
+ * cal_pose0to1 + warp (REF/src/models/basic/__init__.py:4-15, REF/src/models/deflow.py:60-77).
+ * pose0/pose1 f32[B,4,4]; ego (optional, may be NULL) f32[B,4,4] overrides the pose product.
+ * pc0 f32[B,Nmax,3] -> pose_flow (same shape) and pc0_warped, whose sample b starts at element
+ * b * warped_stride_b (so it can be written straight into the [2B,Nmax',3] buffer the pillar index
+ * consumes); NaN rows stay NaN.  pose_0to1 (optional out) f32[B,4,4]. */
+int dfb_ego_warp(const float* pose0, const float* pose1, const float* ego, const float* pc0, int B, int Nmax,
+                 float* pc0_warped, long long warped_stride_b, float* pose_flow, float* pose_0to1, void* stream);
+
+/* ------------------------------------------------------------------ fused pillar feature net
+ * DynamicPillarFeatureNet.forward + PointPillarsScatter (REF/src/models/basic/encoder.py:430-475,
+ * 126-147) for every frame at once, never materialising the [N,9] / [N,32] point tensors:
+ * decorate(9) -> Linear(9,32) -> BatchNorm1d(eps 1e-3) -> ReLU -> pillar mean -> NHWC image.
+ * BatchNorm statistics are per frame, exactly like the reference's one-call-per-sample loop. */
+typedef struct {
+  int F, H, W;            /* frames, image rows (grid_y), image cols (grid_x) */
+  int training;           /* 1: batch statistics per frame; 0: running statistics */
+  float voxel_size[3];
+  float center_off[3];    /* v/2 + range_min, computed in double by the caller (encoder.py:257-259) */
+  float eps, momentum;
+  const int* counts;
+  const float* pt_xyz;
+  const int* pt_coor;
+  const int* pt_pillar;
+  const int* pil_cnt;
+  const int* pil_coor;
+  const int* pil_pix;
+  const int* pil_start;
+  const int* sorted_pt;
+  const float* weight;    /* [32,9] */
+  const float* gamma;     /* [32] */
+  const float* beta;      /* [32] */
+  float* running_mean;    /* [32] updated in place when training (2B sequential updates) */
+  float* running_var;     /* [32] */
+  float* pil_mean;        /* out [pil_cap,3]: cluster_scatter result */
+  double* stats;          /* workspace/out [F,2,32]: per-frame sum(y), sum((y-mean)^2) */
+  float* bn_params;       /* out [F,4,32]: a = gamma*rstd, b = beta - mean*a, mean, rstd (saved for backward) */
+  float* pil_feats;       /* out [pil_cap,32] fp32: pfn_scatter result (voxel_feats) */
+  void* image;            /* out [F,H,W,32] NHWC, zero-filled here; bf16 if image_bf16 else f32 */
+  int image_bf16;
+} dfb_pfn_args;
+int dfb_pfn_forward(const dfb_pfn_args* args, void* stream);
+
+typedef struct {
+  dfb_pfn_args fwd;         /* same buffers as the forward call */
+  const void* grad_image;   /* [F,H,W,32] NHWC (dtype = fwd.image_bf16 ? bf16 : f32) */
+  float* grad_weight;       /* [32,9]  accumulated (+=) */
+  float* grad_gamma;        /* [32]    accumulated (+=) */
+  float* grad_beta;         /* [32]    accumulated (+=) */
+  double* bwd_stats;        /* workspace [F,2,32] */
+  double* grad_accum;       /* workspace [32*9 + 64] doubles, zeroed inside */
+} dfb_pfn_bwd_args;
+int dfb_pfn_backward(const dfb_pfn_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------ decoder gather
+ * The advanced-index gather of ConvGRUDecoder / LinearDecoder (REF/src/models/basic/decoder.py:
+ * 215-225): h0[p] = [img0[y,x,0:32], img1[y,x,0:32], unet[y,x,0:64]] for every pc0 point.
+ * img: [2B,H,W,32] NHWC (frames 0..B-1 = pc0, B..2B-1 = pc1), unet: [B,H,W,64] NHWC.
+ * Backward is a segment sum over the CSR pillar lists (no atomics) into dense NHWC gradients. */
+int dfb_decoder_gather(const void* img, const void* unet, int in_bf16, int B, int H, int W, const int* counts,
+                       int F, const int* pt_pillar, const int* pil_pix, void* h0, int out_bf16, int n_cap,
+                       void* stream);
+int dfb_decoder_gather_backward(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
+                                const int* pil_pix, const int* pil_start, const int* sorted_pt, void* grad_img,
+                                void* grad_unet, int out_bf16, int pil_cap, void* stream);
+
+/* ------------------------------------------------------------------ losses
+ * deflowLoss / ff3dLoss with the trainer's gt construction fused in
+ * (REF/src/lossfuncs.py:102-125, 148-157; REF/src/trainer.py:120-142):
+ *   gt[p] = flow_gt[b, idx[p]] - pose_flow[b, idx[p]];  loss = SUM over samples.
+ * kind 0 = deflowLoss, 1 = ff3dLoss.  est f32[n,3] flat over the B pc0 frames.
+ * bucket_ws: double[B*8] workspace; loss: f32[1]; grad_est f32[n,3] (d loss / d est, may be NULL). */
+int dfb_flow_loss(int kind, const float* est, const float* flow_gt, const float* pose_flow,
+                  const unsigned char* classes, const long long* pt_idx, const int* counts, int F, int B,
+                  int Nmax, double* bucket_ws, float* loss, float* grad_est, int n_cap, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEFLOW_B200_H */
