@@ -24,10 +24,11 @@ def _boundary_points(n, rng, rg):
     g = np.round(p[:k, :2] / 0.2) * 0.2
     p[:k, :2] = g.astype(np.float32)
     p[k:2 * k, 0] = np.nextafter(p[k:2 * k, 0], np.float32(np.inf))
-    p[0] = [rg[0], rg[1], rg[2]]
-    p[1] = [rg[3], rg[4], rg[5]]
-    p[2] = [np.nextafter(np.float32(rg[3]), np.float32(-np.inf)), 0, 0]
-    p[3] = [0, 0, np.nextafter(np.float32(rg[5]), np.float32(-np.inf))]
+    special = [[rg[0], rg[1], rg[2]], [rg[3], rg[4], rg[5]],
+               [np.nextafter(np.float32(rg[3]), np.float32(-np.inf)), 0, 0],
+               [0, 0, np.nextafter(np.float32(rg[5]), np.float32(-np.inf))]]
+    for i, sp in enumerate(special[:n]):
+        p[i] = sp
     return p
 
 
