@@ -1,0 +1,235 @@
+"""Host side of the tensor-core convolution kernels (deflow_b200/csrc/conv_igemm.cu): NHWC bf16 activations,
+weights kept in the reference's torch layout [Cout, Cin, k, k] fp32 (state_dict contract) and re-packed to
+bf16 GEMM operands on the device every step.  OSF = /root/reference/OpenSceneFlow (unet.py:49-68)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, check
+from .ops import _ptr, _stream
+
+
+def _args(mode, n, H, W, ksize, stride, xs, cins, cout, w, bias=None, y=None, stats=None, cin_total=0, cin_off=0):
+    a = ConvArgs()
+    a.mode, a.n, a.H, a.W, a.ksize, a.stride = mode, n, H, W, ksize, stride
+    a.n_src = len(xs)
+    for i, (x, c) in enumerate(zip(xs, cins)):
+        a.x[i] = x.data_ptr()
+        a.cin[i] = c
+    a.cin_total, a.cin_off, a.cout = cin_total, cin_off, cout
+    a.w = _ptr(w)
+    a.bias = _ptr(bias)
+    a.y = _ptr(y)
+    a.y_fp32 = int(y is not None and y.dtype == torch.float32)
+    a.stats = _ptr(stats)
+    return a
+
+
+def pack_weights(w: torch.Tensor, need_dgrad: bool = True):
+    """[Cout,Cin,k,k] fp32 -> (w_fwd bf16 [Cout, k*k*Cin], w_dgrad bf16 [Cin, k*k*Cout])."""
+    w = w.detach().contiguous().float()
+    cout, cin, k, _ = w.shape
+    wf = torch.empty((cout, k * k * cin), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((cin, k * k * cout), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
+    check(_lib.lib().dfb_conv_pack_weights(w.data_ptr(), cout, cin, k, wf.data_ptr(), _ptr(wd), _stream(w)), "pack_weights")
+    return wf, wd
+
+
+def out_size(H, W, ksize, stride):
+    p = ksize // 2
+    return (H + 2 * p - ksize) // stride + 1, (W + 2 * p - ksize) // stride + 1
+
+
+def conv2d_forward(xs: Sequence[torch.Tensor], w_fwd, bias, cout, ksize, stride, stats=None, out_dtype=torch.bfloat16):
+    """xs: 1-2 NHWC bf16 tensors [n,H,W,c_i] (concatenated along channels) -> y [n,Ho,Wo,cout]."""
+    n, H, W, _ = xs[0].shape
+    for x in xs:
+        assert x.is_contiguous() and x.dtype == torch.bfloat16 and x.shape[:3] == xs[0].shape[:3]
+    Ho, Wo = out_size(H, W, ksize, stride)
+    y = torch.empty((n, Ho, Wo, cout), dtype=out_dtype, device=xs[0].device)
+    a = _args(0, n, H, W, ksize, stride, xs, [x.shape[3] for x in xs], cout, w_fwd, bias, y, stats)
+    check(_lib.lib().dfb_conv2d(C.byref(a), _stream(y)), "conv2d forward")
+    return y
+
+
+def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize, stride, out_dtype=torch.bfloat16):
+    """gy [n,Ho,Wo,cout] bf16 -> grad of the input channel slice [cin_off, cin_off+cin): [n,H,W,cin]."""
+    assert gy.is_contiguous() and gy.dtype == torch.bfloat16
+    n, _, _, cout = gy.shape
+    gx = torch.empty((n, H, W, cin), dtype=out_dtype, device=gy.device)
+    a = _args(1, n, H, W, ksize, stride, [gy], [cin], cout, w_dgrad, None, gx, None, cin_total, cin_off)
+    check(_lib.lib().dfb_conv2d(C.byref(a), _stream(gy)), "conv2d dgrad")
+    return gx
+
+
+def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, grad_w: Optional[torch.Tensor] = None):
+    """-> grad_w fp32 in torch layout [cout, sum(c_i), k, k]."""
+    n, H, W, _ = xs[0].shape
+    cout = gy.shape[3]
+    cins = [x.shape[3] for x in xs]
+    ct = sum(cins)
+    assert gy.is_contiguous() and gy.dtype == torch.bfloat16
+    wacc = torch.empty((ksize * ksize, cout, ct), dtype=torch.float32, device=gy.device)
+    acc = grad_w is not None
+    if grad_w is None:
+        grad_w = torch.empty((cout, ct, ksize, ksize), dtype=torch.float32, device=gy.device)
+    a = _args(0, n, H, W, ksize, stride, xs, cins, cout, None, None, gy, None)
+    check(_lib.lib().dfb_conv2d_wgrad(C.byref(a), wacc.data_ptr(), grad_w.data_ptr(), int(acc), _stream(gy)), "conv2d wgrad")
+    return grad_w
+
+
+# ----------------------------------------------------------------------------------------------
+# HBM-bound UNet passes (deflow_b200/csrc/unet_elem.cu)
+# ----------------------------------------------------------------------------------------------
+def bn2d_finalize(stats, count, training, eps, momentum, gamma, beta, running_mean, running_var):
+    Cn = gamma.shape[0]
+    bn = torch.empty((4, Cn), dtype=torch.float32, device=gamma.device)
+    check(_lib.lib().dfb_bn2d_finalize(_ptr(stats), float(count), Cn, int(training), eps, momentum, gamma.data_ptr(),
+                                       beta.data_ptr(), _ptr(running_mean), _ptr(running_var), bn.data_ptr(),
+                                       _stream(gamma)), "bn2d_finalize")
+    return bn
+
+
+def bn_gelu_apply(x, bn):
+    y = torch.empty_like(x)
+    Cn = x.shape[-1]
+    check(_lib.lib().dfb_bn_gelu_apply(x.data_ptr(), bn.data_ptr(), Cn, x.numel() // Cn, y.data_ptr(), _stream(x)),
+          "bn_gelu_apply")
+    return y
+
+
+def bn_gelu_backward(x, gy, bn, training, g_gamma, g_beta, g_bias):
+    Cn = x.shape[-1]
+    gx = torch.empty_like(x)
+    red = torch.empty(2 * Cn, dtype=torch.float64, device=x.device)
+    check(_lib.lib().dfb_bn_gelu_backward(x.data_ptr(), gy.data_ptr(), bn.data_ptr(), Cn, x.numel() // Cn, int(training),
+                                          red.data_ptr(), gx.data_ptr(), g_gamma.data_ptr(), g_beta.data_ptr(),
+                                          _ptr(g_bias), _stream(x)), "bn_gelu_backward")
+    return gx
+
+
+def channel_sum(g):
+    Cn = g.shape[-1]
+    out = torch.zeros(Cn, dtype=torch.float32, device=g.device)
+    check(_lib.lib().dfb_channel_sum(g.data_ptr(), Cn, g.numel() // Cn, out.data_ptr(), _stream(g)), "channel_sum")
+    return out
+
+
+def upsample2x(x, backward=False):
+    n, h, w, Cn = x.shape
+    if backward:
+        h, w = h // 2, w // 2
+        out = torch.empty((n, h, w, Cn), dtype=x.dtype, device=x.device)
+    else:
+        out = torch.empty((n, 2 * h, 2 * w, Cn), dtype=x.dtype, device=x.device)
+    check(_lib.lib().dfb_upsample2x(x.data_ptr(), n, h, w, Cn, out.data_ptr(), int(backward), _stream(x)), "upsample2x")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd wiring
+# ----------------------------------------------------------------------------------------------
+_PACK_CACHE = {}
+
+
+def packed(w: torch.Tensor):
+    """bf16 GEMM operands of a weight, re-packed only when the parameter changed (optimizer step)."""
+    key = id(w)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+        return hit[2], hit[3]
+    wf, wd = pack_weights(w)
+    _PACK_CACHE[key] = (w._version, w.data_ptr(), wf, wd)
+    return wf, wd
+
+
+class _Conv(torch.autograd.Function):
+    """Conv2d(k, stride 1, pad k//2, bias) over 1-2 channel-concatenated NHWC bf16 sources."""
+
+    @staticmethod
+    def forward(ctx, w, b, x0, x1):
+        xs = [x0] if x1 is None else [x0, x1]
+        k = w.shape[2]
+        wf, wd = packed(w)
+        y = conv2d_forward(xs, wf, b.detach().float().contiguous(), w.shape[0], k, 1)
+        ctx.save_for_backward(wd, *xs)
+        ctx.k, ctx.wshape = k, tuple(w.shape)
+        ctx.need = (ctx.needs_input_grad[2], x1 is not None and ctx.needs_input_grad[3])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        wd, *xs = ctx.saved_tensors
+        gy = gy.contiguous()
+        k = ctx.k
+        ct = ctx.wshape[1]
+        gw = conv2d_wgrad(xs, gy, k, 1)
+        gb = channel_sum(gy)
+        gxs, off = [None, None], 0
+        for i, x in enumerate(xs):
+            c = x.shape[3]
+            if ctx.need[i]:
+                gxs[i] = conv2d_dgrad(gy, wd, x.shape[1], x.shape[2], c, ct, off, k, 1)
+            off += c
+        return gw, gb, gxs[0], gxs[1]
+
+
+def conv_bias(w, b, x0, x1=None):
+    return _Conv.apply(w, b, x0, x1)
+
+
+class _ConvBnGelu(torch.autograd.Function):
+    """ConvWithNorms (OSF/src/models/basic/__init__.py:61-79): Conv2d(3, stride, 1) -> BatchNorm2d -> GELU."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, stride, training, eps, momentum):
+        wf, wd = packed(w)
+        cout = w.shape[0]
+        stats = torch.zeros((2, cout), dtype=torch.float64, device=x.device) if training else None
+        raw = conv2d_forward([x], wf, b.detach().float().contiguous(), cout, 3, stride, stats)
+        count = raw.numel() // cout
+        bn = bn2d_finalize(stats, count, training, eps, momentum, gamma.detach().float(), beta.detach().float(),
+                           running_mean, running_var)
+        act = bn_gelu_apply(raw, bn)
+        ctx.save_for_backward(x, raw, bn, wd)
+        ctx.cfg = (stride, training, tuple(w.shape))
+        return act
+
+    @staticmethod
+    def backward(ctx, gact):
+        x, raw, bn, wd = ctx.saved_tensors
+        stride, training, wshape = ctx.cfg
+        cout, cin = wshape[0], wshape[1]
+        gg = torch.zeros(cout, dtype=torch.float32, device=x.device)
+        gbeta = torch.zeros_like(gg)
+        gbias = torch.zeros_like(gg)
+        graw = bn_gelu_backward(raw, gact.contiguous(), bn, training, gg, gbeta, gbias)
+        gw = conv2d_wgrad([x], graw, 3, stride)
+        gx = conv2d_dgrad(graw, wd, x.shape[1], x.shape[2], cin, cin, 0, 3, stride) if ctx.needs_input_grad[0] else None
+        return gx, gw, gbias, gg, gbeta, None, None, None, None, None, None
+
+
+def conv_bn_gelu(x, conv_mod, bn_mod, training):
+    out = _ConvBnGelu.apply(x, conv_mod.weight, conv_mod.bias, bn_mod.weight, bn_mod.bias, bn_mod.running_mean,
+                            bn_mod.running_var, conv_mod.stride[0], training, bn_mod.eps, bn_mod.momentum)
+    if training:
+        bn_mod.num_batches_tracked += 1
+    return out
+
+
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return upsample2x(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return upsample2x(g.contiguous(), backward=True)
+
+
+def upsample_bilinear2x(x):
+    return _Upsample2x.apply(x)

@@ -1,0 +1,724 @@
+// Implicit-GEMM 2-D convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), NHWC bf16.
+//
+// Reference path: every nn.Conv2d of FastFlow3DUNet (OpenSceneFlow/src/models/basic/unet.py:49-68,
+// ConvWithNorms in basic/__init__.py:61-79) -- cuDNN library calls on NCHW fp32/TF32 there.
+//
+// One kernel serves forward (stride 1 and 2, 1x1 and 3x3, channel-concatenated inputs) and data-gradient
+// (stride 1; stride 2 as four parity-plane launches): the host builds a table of K-steps, each step
+// naming (source tensor map, pixel shift, channel chunk, weight K offset).  Per step the TMA producer
+// loads a [16 x 8 pixels] x KC-channel activation box (out-of-bounds = zero padding) and an [N x KC]
+// weight box; one thread issues KC/16 tcgen05.mma (M = 128 pixels, N = Cout) into a TMEM accumulator;
+// four epilogue warps read TMEM, add the bias, accumulate BatchNorm batch statistics (sum, sum of
+// squares per channel) and store bf16 NHWC.  Accumulators are double buffered in TMEM so the epilogue
+// of tile i overlaps the MMAs of tile i+1.  Persistent: one CTA per SM, static round-robin over tiles.
+#include "tc_common.cuh"
+#include "../../include/deflow_b200.h"
+
+#include <mutex>
+
+namespace dfb {
+namespace tc {
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DFB_ERR_CUDA; }
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu ...)", (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1]); return DFB_ERR_CUDA; }
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int TILE_H = 16, TILE_W = 8, TILE_M = TILE_H * TILE_W;  // 128 output pixels per tile
+constexpr int MAX_STEPS = 80;
+constexpr int MAX_AMAPS = 4;
+constexpr int IGEMM_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..5 epilogue
+
+struct KStep {
+  int8_t map, dy, dx, pad;  // source tensor map, pixel shift (in that source's pixel grid)
+  int16_t c0;               // channel offset inside the source
+  int16_t wk;               // K offset in the packed weight matrix
+};
+
+struct IgemmMaps {
+  CUtensorMap a[MAX_AMAPS];
+  CUtensorMap b;
+};
+
+struct IgemmParams {
+  int n_img, Ht, Wt;              // tile-space extent (pixels the tiles enumerate)
+  int tiles_x, tiles_y, num_tiles;
+  int nsteps;
+  // epilogue: element (n, y, x, ch) of the tile space goes to out[n*img + (y*sy+oy)*row + (x*sx+ox)*pix + ch]
+  void* out;
+  int out_fp32;
+  long long out_img, out_row, out_pix;
+  int sy, sx, oy, ox;
+  const float* bias;   // [N] or null
+  double* stats;       // [2][N] running sum / sum of squares over all output elements, or null
+  KStep steps[MAX_STEPS];
+};
+
+template <int N>
+__device__ __forceinline__ void colsum_butterfly(float (&v)[32], int lane) {
+  // after the 5 exchange rounds lane L holds in v[0] the sum over the 32 lanes of column L
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const bool up = (lane & s) != 0;
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+template <int N, int KC>
+struct IgemmCfg {
+  static constexpr int A_BYTES = TILE_M * KC * 2;
+  static constexpr int B_BYTES = N * KC * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * N * 4 * 2;
+  static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+  static constexpr int SWIZZLE = KC * 2;             // bytes per pixel row: 128 or 64
+  static constexpr int LAYOUT = KC == 64 ? 2 : 4;    // UMMA layout type
+  static constexpr int SBO = 8 * KC * 2;             // 8 pixel rows of KC channels
+};
+
+template <int N, int KC>
+__global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_constant__ IgemmMaps maps,
+                                                                 const __grid_constant__ IgemmParams P) {
+  using Cfg = IgemmCfg<N, KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;  // [STAGES][A | B], every tile 1024-byte aligned (A_BYTES, B_BYTES are multiples of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);  // [2][N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < MAX_AMAPS; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
+        const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+        for (int s = 0; s < P.nsteps; ++s) {
+          const KStep st = P.steps[s];
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(a_dst, &maps.a[st.map], &full[stage], st.c0, x0 + st.dx, y0 + st.dy, n);
+          tma_load_2d(b_dst, &maps.b, &full[stage], st.wk, 0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, N, 0, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * N;
+        for (int s = 0; s < P.nsteps; ++s) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint64_t adesc = make_smem_desc(a_addr, 16, Cfg::SBO, Cfg::LAYOUT);
+          const uint64_t bdesc = make_smem_desc(b_addr, 16, Cfg::SBO, Cfg::LAYOUT);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)  // +32 bytes (2 x 16 B) along K per UMMA_K = 16 bf16
+            umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+          umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int r = m >> 3, c = m & 7;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
+      const int y = ty * TILE_H + r, x = tx * TILE_W + c;
+      const bool valid = y < P.Ht && x < P.Wt;
+      const long long off = (long long)n * P.out_img + (long long)(y * P.sy + P.oy) * P.out_row +
+                            (long long)(x * P.sx + P.ox) * P.out_pix;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int col = 0; col < N; col += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + col, v);
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + col + i);
+        }
+        if (valid) {
+          if (P.out_fp32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<unsigned*>(&p0); u.y = *reinterpret_cast<unsigned*>(&p1);
+              u.z = *reinterpret_cast<unsigned*>(&p2); u.w = *reinterpret_cast<unsigned*>(&p3);
+              dst[i] = u;
+            }
+          }
+        }
+        if (P.stats) {
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (!valid) v[i] = 0.f;
+            sq[i] = v[i] * v[i];
+          }
+          colsum_butterfly<N>(v, lane);
+          colsum_butterfly<N>(sq, lane);
+          atomicAdd(&s_stats[col + lane], v[0]);
+          atomicAdd(&s_stats[N + col + lane], sq[0]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (P.stats) {
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) atomicAdd(&P.stats[i], (double)s_stats[i]);
+  }
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: torch [Cout, Cin, kh, kw] fp32 -> bf16 GEMM-B matrices, K contiguous.
+//   forward:  Wf[co][tap * Cin + ci]            (tap = ky * kw + kx)
+//   dgrad:    Wd[ci][tap * Cout + co]           (same tap numbering; the step table flips the shifts)
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ w, int Cout, int Cin, int taps,
+                                                      __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(e % taps);
+    const int ci = (int)((e / taps) % Cin);
+    const int co = (int)(e / ((long long)taps * Cin));
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[e]);
+    if (wf) wf[((long long)co * taps + t) * Cin + ci] = v;
+    if (wd) wd[((long long)ci * taps + t) * Cout + co] = v;
+  }
+}
+
+template <int N, int KC>
+static int launch_igemm(const IgemmMaps& maps, const IgemmParams& P, cudaStream_t st) {
+  using Cfg = IgemmCfg<N, KC>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_igemm<N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) { set_error("igemm<%d,%d>: cannot reserve %d bytes of shared memory: %s", N, KC, Cfg::SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    configured = true;
+  }
+  int grid = sm_count();
+  if (grid > P.num_tiles) grid = P.num_tiles;
+  k_conv_igemm<N, KC><<<grid, IGEMM_THREADS, Cfg::SMEM, st>>>(maps, P);
+  add_launches(1);
+  return check_launch("conv_igemm");
+}
+
+static int dispatch_igemm(int N, int KC, const IgemmMaps& maps, const IgemmParams& P, cudaStream_t st) {
+#define DFB_CASE(n, kc) if (N == n && KC == kc) return launch_igemm<n, kc>(maps, P, st)
+  DFB_CASE(32, 64); DFB_CASE(64, 64); DFB_CASE(128, 64); DFB_CASE(256, 64);
+  DFB_CASE(32, 32); DFB_CASE(64, 32); DFB_CASE(128, 32); DFB_CASE(256, 32);
+#undef DFB_CASE
+  set_error("conv_igemm: unsupported tile N=%d KC=%d (N in {32,64,128,256}, KC in {32,64})", N, KC);
+  return DFB_ERR_UNSUPPORTED;
+}
+
+}  // namespace tc
+}  // namespace dfb
+
+using namespace dfb;
+using namespace dfb::tc;
+
+extern "C" int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, void* w_fwd, void* w_dgrad,
+                                     void* stream_) {
+  if (cout <= 0 || cin <= 0 || (ksize != 1 && ksize != 3)) { set_error("dfb_conv_pack_weights: bad sizes"); return DFB_ERR_ARG; }
+  const long long total = (long long)cout * cin * ksize * ksize;
+  long long blocks = (total + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  k_pack_weights<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(w, cout, cin, ksize * ksize, (__nv_bfloat16*)w_fwd,
+                                                                 (__nv_bfloat16*)w_dgrad);
+  add_launches(1);
+  return check_launch("dfb_conv_pack_weights");
+}
+
+// mode 0: forward  y = conv(x; W) (+ bias)           x: n_src sources [n,H,W,cin_s] concatenated along channels
+// mode 1: dgrad    gx = conv^T(gy; W)                 x: ONE source = gy [n,Ho,Wo,cout]; output = gx [n,H,W,cin]
+//                                                      (for concatenated inputs call once per source with
+//                                                       cin_off / cin_total selecting the weight slice)
+extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!a) { set_error("dfb_conv2d: null args"); return DFB_ERR_ARG; }
+  const int k = a->ksize, s = a->stride, taps = k * k;
+  if ((k != 1 && k != 3) || (s != 1 && s != 2) || a->n_src < 1 || a->n_src > 2) { set_error("dfb_conv2d: ksize must be 1 or 3, stride 1 or 2, 1-2 sources"); return DFB_ERR_ARG; }
+  const int H = a->H, W = a->W;                       // input (x) spatial size
+  const int Ho = (H + 2 * (k / 2) - k) / s + 1, Wo = (W + 2 * (k / 2) - k) / s + 1;
+  int cin_total = 0;
+  for (int i = 0; i < a->n_src; ++i) cin_total += a->cin[i];
+  if (a->cin_total > 0) cin_total = a->cin_total;
+
+  IgemmMaps maps;
+  IgemmParams P;
+  memset(&maps, 0, sizeof(maps));
+  memset(&P, 0, sizeof(P));
+  P.n_img = a->n;
+  P.out = a->y;
+  P.out_fp32 = a->y_fp32;
+  P.bias = a->bias;
+  P.stats = a->stats;
+  int N, KC, rc, nsteps = 0;
+
+  if (a->mode == 0) {
+    // ---------------------------------------------------------------- forward
+    N = a->cout;
+    KC = 64;
+    for (int i = 0; i < a->n_src; ++i) if (a->cin[i] % 64 != 0) KC = 32;
+    for (int i = 0; i < a->n_src; ++i) if (a->cin[i] % KC != 0) { set_error("dfb_conv2d: input channels must be multiples of 32"); return DFB_ERR_UNSUPPORTED; }
+    if (s == 2 && a->n_src != 1) { set_error("dfb_conv2d: stride-2 convolution takes a single source"); return DFB_ERR_UNSUPPORTED; }
+    P.Ht = Ho; P.Wt = Wo;
+    P.out_img = (long long)Ho * Wo * a->cout; P.out_row = (long long)Wo * a->cout; P.out_pix = a->cout;
+    P.sy = P.sx = 1; P.oy = P.ox = 0;
+    const uint32_t box[4] = {(uint32_t)KC, TILE_W, TILE_H, 1};
+    if (s == 1) {
+      for (int i = 0; i < a->n_src; ++i) {
+        const uint64_t C = a->cin[i];
+        const uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)a->n};
+        const uint64_t str[3] = {C * 2, C * 2 * W, C * 2 * W * H};
+        if ((rc = make_tensor_map_bf16(&maps.a[i], a->x[i], 4, dims, str, box, KC * 2))) return rc;
+      }
+      for (int t = 0; t < taps; ++t) {
+        const int dy = k == 3 ? t / 3 - 1 : 0, dx = k == 3 ? t % 3 - 1 : 0;
+        int coff = 0;
+        for (int i = 0; i < a->n_src; ++i) {
+          for (int c0 = 0; c0 < a->cin[i]; c0 += KC) {
+            if (nsteps >= MAX_STEPS) { set_error("dfb_conv2d: too many K steps"); return DFB_ERR_UNSUPPORTED; }
+            P.steps[nsteps++] = KStep{(int8_t)i, (int8_t)dy, (int8_t)dx, 0, (int16_t)c0, (int16_t)(t * cin_total + coff + c0)};
+          }
+          coff += a->cin[i];
+        }
+      }
+    } else {
+      // stride 2: the four parity planes of x are strided views; tap d in {0,1,2} along an axis reads plane
+      // (d + 1) & 1 at shift (d == 0 ? -1 : 0)   [input index 2*o + d - 1]
+      const uint64_t C = a->cin[0];
+      if (H % 2 || W % 2) { set_error("dfb_conv2d: stride-2 convolution needs even H, W"); return DFB_ERR_UNSUPPORTED; }
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const uint64_t dims[4] = {C, (uint64_t)W / 2, (uint64_t)H / 2, (uint64_t)a->n};
+          const uint64_t str[3] = {C * 2 * 2, C * 2 * W * 2, C * 2 * W * H};
+          const char* base = (const char*)a->x[0] + ((size_t)py * W + px) * C * 2;
+          if ((rc = make_tensor_map_bf16(&maps.a[py * 2 + px], base, 4, dims, str, box, KC * 2))) return rc;
+        }
+      for (int t = 0; t < taps; ++t) {
+        const int ky = k == 3 ? t / 3 : 1, kx = k == 3 ? t % 3 : 1;
+        const int py = (ky + 1) & 1, px = (kx + 1) & 1, dy = ky == 0 ? -1 : 0, dx = kx == 0 ? -1 : 0;
+        for (int c0 = 0; c0 < a->cin[0]; c0 += KC)
+          P.steps[nsteps++] = KStep{(int8_t)(py * 2 + px), (int8_t)dy, (int8_t)dx, 0, (int16_t)c0, (int16_t)(t * cin_total + c0)};
+      }
+    }
+    const uint64_t bd[2] = {(uint64_t)taps * cin_total, (uint64_t)a->cout};
+    const uint64_t bs[1] = {(uint64_t)taps * cin_total * 2};
+    const uint32_t bb[2] = {(uint32_t)KC, (uint32_t)N};
+    if ((rc = make_tensor_map_bf16(&maps.b, a->w, 2, bd, bs, bb, KC * 2))) return rc;
+    P.nsteps = nsteps;
+    P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
+    P.num_tiles = P.tiles_x * P.tiles_y * a->n;
+    return dispatch_igemm(N, KC, maps, P, st);
+  }
+
+  if (a->mode == 1) {
+    // ---------------------------------------------------------------- data gradient
+    // source = gy [n, Ho, Wo, cout]; output gx [n, H, W, cin_slice]; weights Wd[ci][tap*cout + co] (rows = all cin_total
+    // channels; the slice starts at row cin_off).
+    const int cout = a->cout, cin = a->cin[0];
+    N = cin;
+    KC = cout % 64 == 0 ? 64 : 32;
+    if (cout % KC != 0) { set_error("dfb_conv2d dgrad: output channels must be multiples of 32"); return DFB_ERR_UNSUPPORTED; }
+    const uint64_t C = cout;
+    const uint64_t dims[4] = {C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)a->n};
+    const uint64_t str[3] = {C * 2, C * 2 * Wo, C * 2 * Wo * Ho};
+    const uint32_t box[4] = {(uint32_t)KC, TILE_W, TILE_H, 1};
+    if ((rc = make_tensor_map_bf16(&maps.a[0], a->x[0], 4, dims, str, box, KC * 2))) return rc;
+    const uint64_t bd[2] = {(uint64_t)taps * cout, (uint64_t)cin};
+    const uint64_t bs[1] = {(uint64_t)taps * cout * 2};
+    const uint32_t bb[2] = {(uint32_t)KC, (uint32_t)N};
+    const char* wbase = (const char*)a->w + (size_t)a->cin_off * taps * cout * 2;
+    if ((rc = make_tensor_map_bf16(&maps.b, wbase, 2, bd, bs, bb, KC * 2))) return rc;
+    P.out_img = (long long)H * W * cin; P.out_row = (long long)W * cin; P.out_pix = cin;
+    if (s == 1) {
+      // gx[y, x] = sum_t W[t]^T gy[y - dy_t, x - dx_t]
+      P.Ht = H; P.Wt = W; P.sy = P.sx = 1; P.oy = P.ox = 0;
+      for (int t = 0; t < taps; ++t) {
+        const int dy = k == 3 ? t / 3 - 1 : 0, dx = k == 3 ? t % 3 - 1 : 0;
+        for (int c0 = 0; c0 < cout; c0 += KC)
+          P.steps[nsteps++] = KStep{0, (int8_t)(-dy), (int8_t)(-dx), 0, (int16_t)c0, (int16_t)(t * cout + c0)};
+      }
+      P.nsteps = nsteps;
+      P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
+      P.num_tiles = P.tiles_x * P.tiles_y * a->n;
+      return dispatch_igemm(N, KC, maps, P, st);
+    }
+    // stride 2: input row i = 2a + py receives from output rows o with 2o + ky - 1 = i:
+    //   py = 0: ky = 1, o = a;      py = 1: ky = 0, o = a + 1  and  ky = 2, o = a.   One launch per parity plane.
+    if (H % 2 || W % 2) { set_error("dfb_conv2d dgrad: stride-2 needs even H, W"); return DFB_ERR_UNSUPPORTED; }
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        nsteps = 0;
+        for (int ky = 0; ky < k; ++ky)
+          for (int kx = 0; kx < k; ++kx) {
+            const int kyy = k == 3 ? ky : 1, kxx = k == 3 ? kx : 1;
+            if (((kyy + 1) & 1) != py || ((kxx + 1) & 1) != px) continue;
+            const int dy = kyy == 0 ? 1 : 0, dx = kxx == 0 ? 1 : 0;
+            const int t = ky * k + kx;
+            for (int c0 = 0; c0 < cout; c0 += KC)
+              P.steps[nsteps++] = KStep{0, (int8_t)dy, (int8_t)dx, 0, (int16_t)c0, (int16_t)(t * cout + c0)};
+          }
+        P.Ht = H / 2; P.Wt = W / 2; P.sy = P.sx = 2; P.oy = py; P.ox = px;
+        P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
+        P.num_tiles = P.tiles_x * P.tiles_y * a->n;
+        P.nsteps = nsteps;
+        if (nsteps == 0) {  // 1x1 stride-2: planes that no tap reaches get zero gradient
+          set_error("dfb_conv2d dgrad: 1x1 stride-2 is not on the DeFlow path"); return DFB_ERR_UNSUPPORTED;
+        }
+        if ((rc = dispatch_igemm(N, KC, maps, P, st))) return rc;
+      }
+    return DFB_OK;
+  }
+  set_error("dfb_conv2d: unknown mode %d", a->mode);
+  return DFB_ERR_ARG;
+}
+
+// ================================================================================================
+// Weight gradient:  gW[t][co][ci] = sum over pixels of gy[n, y, x, co] * x[n, y*s + dy_t, x*s + dx_t, ci]
+//
+// A GEMM whose K dimension is the pixel index, so both operands are MN-major in shared memory: a TMA box of
+// [8 x 8 pixels] x 64 channels lands as 64 rows (K) of 128 bytes (64 channels, M or N).  One CTA owns a pair
+// of (tap, 64-channel chunk) groups of x  -> M = 128 accumulator rows -- times all Cout columns, over a range
+// of pixel tiles; at the end it adds its partial result into an fp32 workspace [tap][co][ci] with coalesced
+// red.global.add.  Split-K over pixel ranges gives every SM work.  k_unpack_wgrad writes the torch layout.
+namespace dfb {
+namespace tc {
+
+constexpr int WG_PIX = 64;          // pixels per stage (8 x 8 patch)
+constexpr int WG_THREADS = 192;
+constexpr int MAX_GROUPS = 80;
+
+struct WGroup { int8_t map, dy, dx, tap; int16_t c0; int16_t ci_glob; };  // ci_glob: channel index in the layer's cin_total
+
+struct WgradMaps {
+  CUtensorMap a[MAX_AMAPS];  // x sources / parity planes
+  CUtensorMap b;             // gy
+};
+
+struct WgradParams {
+  int n_img, Ht, Wt, tiles_x, tiles_y, num_tiles;  // gy pixel grid in 8x8 tiles
+  int n_pairs, splits;                              // grid = n_pairs * splits
+  int n_groups, cin_total, cout;
+  float* wacc;                                      // [taps][cout][cin_total] fp32, += by red.add
+  WGroup groups[MAX_GROUPS];
+};
+
+template <int N>
+struct WgradCfg {
+  static constexpr int A_BYTES = 2 * WG_PIX * 128;        // two x groups
+  static constexpr int B_BYTES = (N / 64) * WG_PIX * 128;  // gy, N/64 channel chunks
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = N < 32 ? 32 : N;
+};
+
+template <int N>
+__global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad(const __grid_constant__ WgradMaps maps,
+                                                              const __grid_constant__ WgradParams P) {
+  using Cfg = WgradCfg<N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int pair = blockIdx.x % P.n_pairs, split = blockIdx.x / P.n_pairs;
+  const int g0 = pair * 2, g1 = g0 + 1 < P.n_groups ? g0 + 1 : -1;
+  const int per = (P.num_tiles + P.splits - 1) / P.splits;
+  const int t_begin = split * per, t_end = min(P.num_tiles, t_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < MAX_AMAPS; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const WGroup ga = P.groups[g0];
+      const WGroup gb = P.groups[g1 >= 0 ? g1 : g0];
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
+        const int x0 = tx * 8, y0 = ty * 8;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+        tma_load_4d(a_dst, &maps.a[ga.map], &full[stage], ga.c0, x0 + ga.dx, y0 + ga.dy, n);
+        // an odd group count leaves the second half of the last pair unused: load the same box, discard the rows
+        tma_load_4d(a_dst + WG_PIX * 128, &maps.a[gb.map], &full[stage], gb.c0, x0 + gb.dx, y0 + gb.dy, n);
+#pragma unroll
+        for (int j = 0; j < N / 64; ++j) tma_load_4d(b_dst + j * WG_PIX * 128, &maps.b, &full[stage], j * 64, x0, y0, n);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+        // MN-major SWIZZLE_128B: 64-element MN groups LBO apart, 8-row K groups SBO = 1024 bytes apart
+        const uint64_t adesc = make_smem_desc(a_addr, WG_PIX * 128, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(b_addr, WG_PIX * 128, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < WG_PIX / 16; ++k) {  // 16 pixels = 2 K groups = 2048 bytes per UMMA
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, !first);
+          first = false;
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (t_end > t_begin) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;            // accumulator row: group (m >> 6), channel (m & 63) of that group
+    const int g = m < 64 ? g0 : g1;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const WGroup gr = P.groups[g >= 0 ? g : g0];
+    float* dst = P.wacc + ((size_t)gr.tap * P.cout) * P.cin_total + gr.ci_glob + (m & 63);
+    const bool live = g >= 0 && (gr.ci_glob + (m & 63)) < P.cin_total;
+#pragma unroll 1
+    for (int col = 0; col < N; col += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + col, v);
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)(col + i) * P.cin_total, v[i]);  // lanes = consecutive ci
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// wacc [taps][cout][cin] -> torch [cout][cin][taps]; accumulate = grad += (autograd accumulation)
+__global__ void __launch_bounds__(256) k_unpack_wgrad(const float* __restrict__ wacc, int cout, int cin, int taps,
+                                                      float* __restrict__ gw, int accumulate) {
+  const long long total = (long long)cout * cin * taps;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(e % taps);
+    const int ci = (int)((e / taps) % cin);
+    const int co = (int)(e / ((long long)taps * cin));
+    const float v = wacc[((size_t)t * cout + co) * cin + ci];
+    gw[e] = accumulate ? gw[e] + v : v;
+  }
+}
+
+template <int N>
+static int launch_wgrad(const WgradMaps& maps, const WgradParams& P, cudaStream_t st) {
+  using Cfg = WgradCfg<N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) { set_error("wgrad<%d>: cannot reserve %d bytes of shared memory: %s", N, Cfg::SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    configured = true;
+  }
+  k_conv_wgrad<N><<<P.n_pairs * P.splits, WG_THREADS, Cfg::SMEM, st>>>(maps, P);
+  add_launches(1);
+  return check_launch("conv_wgrad");
+}
+
+}  // namespace tc
+}  // namespace dfb
+
+// x: the forward's sources (n_src, cin[]), a->w unused; a->y = gy [n,Ho,Wo,cout] bf16 (input here);
+// wacc: fp32 workspace [taps][cout][cin_total] (zeroed here); grad_w: torch layout fp32 [cout][cin_total][k][k].
+extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad_w, int accumulate, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!a || !wacc || !grad_w) { set_error("dfb_conv2d_wgrad: null args"); return DFB_ERR_ARG; }
+  const int k = a->ksize, s = a->stride, taps = k * k;
+  if ((k != 1 && k != 3) || (s != 1 && s != 2) || a->n_src < 1 || a->n_src > 2) { set_error("dfb_conv2d_wgrad: bad conv geometry"); return DFB_ERR_ARG; }
+  if (a->cout != 64 && a->cout != 128 && a->cout != 256) { set_error("dfb_conv2d_wgrad: cout must be 64, 128 or 256"); return DFB_ERR_UNSUPPORTED; }
+  const int H = a->H, W = a->W;
+  const int Ho = (H + 2 * (k / 2) - k) / s + 1, Wo = (W + 2 * (k / 2) - k) / s + 1;
+  int cin_total = 0;
+  for (int i = 0; i < a->n_src; ++i) cin_total += a->cin[i];
+  WgradMaps maps;
+  WgradParams P;
+  memset(&maps, 0, sizeof(maps));
+  memset(&P, 0, sizeof(P));
+  int rc;
+  const uint32_t box[4] = {64, 8, 8, 1};
+  {
+    const uint64_t C = a->cout;
+    const uint64_t dims[4] = {C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)a->n};
+    const uint64_t str[3] = {C * 2, C * 2 * Wo, C * 2 * Wo * Ho};
+    if ((rc = make_tensor_map_bf16(&maps.b, a->y, 4, dims, str, box, 128))) return rc;
+  }
+  int ng = 0;
+  if (s == 1) {
+    for (int i = 0; i < a->n_src; ++i) {
+      const uint64_t C = a->cin[i];
+      const uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)a->n};
+      const uint64_t str[3] = {C * 2, C * 2 * W, C * 2 * W * H};
+      if ((rc = make_tensor_map_bf16(&maps.a[i], a->x[i], 4, dims, str, box, 128))) return rc;
+    }
+    for (int t = 0; t < taps; ++t) {
+      const int dy = k == 3 ? t / 3 - 1 : 0, dx = k == 3 ? t % 3 - 1 : 0;
+      int coff = 0;
+      for (int i = 0; i < a->n_src; ++i) {
+        for (int c0 = 0; c0 < a->cin[i]; c0 += 64) {  // a 32-channel source is covered by one zero-filled 64-wide box
+          if (ng >= tc::MAX_GROUPS) { set_error("dfb_conv2d_wgrad: too many groups"); return DFB_ERR_UNSUPPORTED; }
+          P.groups[ng++] = tc::WGroup{(int8_t)i, (int8_t)dy, (int8_t)dx, (int8_t)t, (int16_t)c0, (int16_t)(coff + c0)};
+        }
+        coff += a->cin[i];
+      }
+    }
+  } else {
+    if (a->n_src != 1 || H % 2 || W % 2) { set_error("dfb_conv2d_wgrad: stride 2 takes one source with even H, W"); return DFB_ERR_UNSUPPORTED; }
+    const uint64_t C = a->cin[0];
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const uint64_t dims[4] = {C, (uint64_t)W / 2, (uint64_t)H / 2, (uint64_t)a->n};
+        const uint64_t str[3] = {C * 2 * 2, C * 2 * W * 2, C * 2 * W * H};
+        const char* base = (const char*)a->x[0] + ((size_t)py * W + px) * C * 2;
+        if ((rc = make_tensor_map_bf16(&maps.a[py * 2 + px], base, 4, dims, str, box, 128))) return rc;
+      }
+    for (int t = 0; t < taps; ++t) {
+      const int ky = k == 3 ? t / 3 : 1, kx = k == 3 ? t % 3 : 1;
+      const int py = (ky + 1) & 1, px = (kx + 1) & 1, dy = ky == 0 ? -1 : 0, dx = kx == 0 ? -1 : 0;
+      for (int c0 = 0; c0 < a->cin[0]; c0 += 64)
+        P.groups[ng++] = tc::WGroup{(int8_t)(py * 2 + px), (int8_t)dy, (int8_t)dx, (int8_t)t, (int16_t)c0, (int16_t)c0};
+    }
+  }
+  P.n_groups = ng;
+  P.n_pairs = (ng + 1) / 2;
+  P.n_img = a->n; P.Ht = Ho; P.Wt = Wo;
+  P.tiles_x = (Wo + 7) / 8; P.tiles_y = (Ho + 7) / 8;
+  P.num_tiles = P.tiles_x * P.tiles_y * a->n;
+  int splits = (2 * sm_count() + P.n_pairs - 1) / P.n_pairs;
+  if (splits > P.num_tiles) splits = P.num_tiles;
+  if (splits < 1) splits = 1;
+  P.splits = splits;
+  P.cin_total = cin_total;
+  P.cout = a->cout;
+  P.wacc = wacc;
+  const size_t total = (size_t)taps * a->cout * cin_total;
+  cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
+  if (a->cout == 64) rc = tc::launch_wgrad<64>(maps, P, st);
+  else if (a->cout == 128) rc = tc::launch_wgrad<128>(maps, P, st);
+  else rc = tc::launch_wgrad<256>(maps, P, st);
+  if (rc) return rc;
+  long long blocks = ((long long)total + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  tc::k_unpack_wgrad<<<(int)blocks, 256, 0, st>>>(wacc, a->cout, cin_total, taps, grad_w, accumulate);
+  add_launches(1);
+  return check_launch("dfb_conv2d_wgrad");
+}

@@ -1,0 +1,314 @@
+// HBM-bound passes of the UNet backbone on NHWC bf16 tensors: BatchNorm2d (training statistics come from the
+// convolution epilogue) + exact-erf GELU apply and backward, bilinear x2 upsample forward / backward, and the
+// per-channel sum used for bias gradients.
+//
+// Reference: ConvWithNorms (OpenSceneFlow/src/models/basic/__init__.py:61-79: Conv2d -> BatchNorm2d(eps 1e-5,
+// momentum 0.1) -> GELU), BilinearDecoder (OpenSceneFlow/src/models/basic/unet.py:8-18:
+// F.interpolate(scale_factor=2, mode="bilinear", align_corners=False)).
+#include "common.cuh"
+#include "../../include/deflow_b200.h"
+
+namespace dfb {
+
+struct bf8 { uint4 u; };
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(p[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float z) {
+  return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+}
+
+// ---------------------------------------------------------------- BatchNorm2d parameters from batch statistics
+// stats [2][C] (double): sum, sum of squares over count elements per channel.  bn [4][C]: a = gamma*rstd,
+// b = beta - mean*a, mean, rstd.  Training updates the running statistics (unbiased variance) in place.
+__global__ void k_bn2d_finalize(const double* __restrict__ stats, double count, int C, int training, float eps,
+                                float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float* __restrict__ running_mean, float* __restrict__ running_var,
+                                float* __restrict__ bn) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    const double m = stats[c] / count;
+    double v = stats[C + c] / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float rstd = 1.0f / sqrtf(var + eps);
+  const float a = gamma[c] * rstd;
+  bn[c] = a;
+  bn[C + c] = beta[c] - mean * a;
+  bn[2 * C + c] = mean;
+  bn[3 * C + c] = rstd;
+}
+
+// y = GELU(a*x + b), 8 channels per thread
+__global__ void __launch_bounds__(256) k_bn_gelu_apply(const uint4* __restrict__ x, const float* __restrict__ bn, int C,
+                                                       long long n_vec, uint4* __restrict__ y) {
+  __shared__ float sa[256], sb[256];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { sa[i] = bn[i]; sb[i] = bn[C + i]; }
+  __syncthreads();
+  const int vec_per_pix = C >> 3;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_vec; e += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(e % vec_per_pix) << 3;
+    float f[8];
+    unpack8(__ldg(x + e), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = gelu_f(fmaf(f[i], sa[c0 + i], sb[c0 + i]));
+    y[e] = pack8(f);
+  }
+}
+
+// Backward pass 1: red[0][c] = sum g1, red[1][c] = sum g1 * xhat, with g1 = gy * GELU'(a*x + b)
+__global__ void __launch_bounds__(256) k_bn_gelu_bwd_reduce(const uint4* __restrict__ x, const uint4* __restrict__ gy,
+                                                            const float* __restrict__ bn, int C, long long n_pix,
+                                                            double* __restrict__ red) {
+  __shared__ float sa[256], sb[256], sm[256], sr[256];
+  __shared__ float acc1[256], acc2[256];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sa[i] = bn[i]; sb[i] = bn[C + i]; sm[i] = bn[2 * C + i]; sr[i] = bn[3 * C + i];
+    acc1[i] = 0.f; acc2[i] = 0.f;
+  }
+  __syncthreads();
+  const int vpp = C >> 3;                       // vectors per pixel (8, 16 or 32)
+  const int oct = threadIdx.x % vpp;            // fixed channel octet of this thread
+  const int prow = threadIdx.x / vpp, prows = blockDim.x / vpp;
+  const int c0 = oct << 3;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  for (long long p = (long long)blockIdx.x * prows + prow; p < n_pix; p += (long long)gridDim.x * prows) {
+    float fx[8], fg[8];
+    unpack8(__ldg(x + p * vpp + oct), fx);
+    unpack8(__ldg(gy + p * vpp + oct), fg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float z = fmaf(fx[i], sa[c0 + i], sb[c0 + i]);
+      const float g1 = fg[i] * gelu_grad_f(z);
+      const float xh = (fx[i] - sm[c0 + i]) * sr[c0 + i];
+      s1[i] += g1;
+      s2[i] = fmaf(g1, xh, s2[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { atomicAdd(&acc1[c0 + i], s1[i]); atomicAdd(&acc2[c0 + i], s2[i]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&red[i], (double)acc1[i]);
+    atomicAdd(&red[C + i], (double)acc2[i]);
+  }
+}
+
+// Backward pass 2: gx = a * (g1 - m1 - xhat*m2) (training) or a * g1 (eval)
+__global__ void __launch_bounds__(256) k_bn_gelu_bwd_apply(const uint4* __restrict__ x, const uint4* __restrict__ gy,
+                                                           const float* __restrict__ bn, const double* __restrict__ red,
+                                                           double count, int training, int C, long long n_vec,
+                                                           uint4* __restrict__ gx) {
+  __shared__ float sa[256], sb[256], sm[256], sr[256], m1[256], m2[256];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sa[i] = bn[i]; sb[i] = bn[C + i]; sm[i] = bn[2 * C + i]; sr[i] = bn[3 * C + i];
+    m1[i] = training ? (float)(red[i] / count) : 0.f;
+    m2[i] = training ? (float)(red[C + i] / count) : 0.f;
+  }
+  __syncthreads();
+  const int vpp = C >> 3;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_vec; e += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(e % vpp) << 3;
+    float fx[8], fg[8];
+    unpack8(__ldg(x + e), fx);
+    unpack8(__ldg(gy + e), fg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float z = fmaf(fx[i], sa[c0 + i], sb[c0 + i]);
+      const float g1 = fg[i] * gelu_grad_f(z);
+      const float xh = (fx[i] - sm[c0 + i]) * sr[c0 + i];
+      fx[i] = sa[c0 + i] * (g1 - m1[c0 + i] - xh * m2[c0 + i]);
+    }
+    gx[e] = pack8(fx);
+  }
+}
+
+// d gamma = sum g1*xhat, d beta = sum g1; conv bias gradient = sum gx = 0 (training) or a * sum g1 (eval)
+__global__ void k_bn_param_grads(const double* __restrict__ red, const float* __restrict__ bn, int C, int training,
+                                 float* __restrict__ g_gamma, float* __restrict__ g_beta, float* __restrict__ g_bias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  g_gamma[c] += (float)red[C + c];
+  g_beta[c] += (float)red[c];
+  if (g_bias) g_bias[c] += training ? 0.f : bn[c] * (float)red[c];
+}
+
+// ---------------------------------------------------------------- per-channel sum (bias gradients)
+__global__ void __launch_bounds__(256) k_channel_sum(const uint4* __restrict__ g, int C, long long n_pix,
+                                                     float* __restrict__ out) {
+  __shared__ float acc[256];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int vpp = C >> 3;
+  const int oct = threadIdx.x % vpp, prow = threadIdx.x / vpp, prows = blockDim.x / vpp;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (long long p = (long long)blockIdx.x * prows + prow; p < n_pix; p += (long long)gridDim.x * prows) {
+    float f[8];
+    unpack8(__ldg(g + p * vpp + oct), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(&acc[(oct << 3) + i], s[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], acc[i]);
+}
+
+// ---------------------------------------------------------------- bilinear x2 (align_corners = False)
+// out[2i] = 0.25 in[i-1] + 0.75 in[i], out[2i+1] = 0.75 in[i] + 0.25 in[i+1], indices clamped to the edge.
+__global__ void __launch_bounds__(256) k_upsample2x(const uint4* __restrict__ in, int n, int h, int w, int C,
+                                                    uint4* __restrict__ out) {
+  const int vpp = C >> 3;
+  const long long total = (long long)n * 4 * h * w * vpp;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(e % vpp);
+    long long p = e / vpp;
+    const int ox = (int)(p % (2 * w)); p /= 2 * w;
+    const int oy = (int)(p % (2 * h));
+    const int b = (int)(p / (2 * h));
+    const int iy = oy >> 1, ix = ox >> 1;
+    const int y2 = (oy & 1) ? min(iy + 1, h - 1) : max(iy - 1, 0);
+    const int x2 = (ox & 1) ? min(ix + 1, w - 1) : max(ix - 1, 0);
+    const uint4* base = in + (long long)b * h * w * vpp + v;
+    float a[8], bq[8], c[8], d[8];
+    unpack8(__ldg(base + ((long long)iy * w + ix) * vpp), a);
+    unpack8(__ldg(base + ((long long)iy * w + x2) * vpp), bq);
+    unpack8(__ldg(base + ((long long)y2 * w + ix) * vpp), c);
+    unpack8(__ldg(base + ((long long)y2 * w + x2) * vpp), d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)  // rows first (like ATen: y-lerp of x-lerps), weights 0.75 / 0.25
+      a[i] = 0.75f * (0.75f * a[i] + 0.25f * bq[i]) + 0.25f * (0.75f * c[i] + 0.25f * d[i]);
+    out[e] = pack8(a);
+  }
+}
+
+__device__ __forceinline__ float up_w(int i, int o, int len) {
+  // weight of in[i] in out[o] along one axis (len = input length)
+  float wgt = 0.f;
+  const int c = o >> 1;                                   // centre tap of out[o]
+  const int nb = (o & 1) ? min(c + 1, len - 1) : max(c - 1, 0);
+  if (c == i) wgt += 0.75f;
+  if (nb == i) wgt += 0.25f;
+  return wgt;
+}
+
+__global__ void __launch_bounds__(256) k_upsample2x_bwd(const uint4* __restrict__ gout, int n, int h, int w, int C,
+                                                        uint4* __restrict__ gin) {
+  const int vpp = C >> 3;
+  const long long total = (long long)n * h * w * vpp;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(e % vpp);
+    long long p = e / vpp;
+    const int ix = (int)(p % w); p /= w;
+    const int iy = (int)(p % h);
+    const int b = (int)(p / h);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const uint4* base = gout + (long long)b * 4 * h * w * vpp + v;
+    for (int oy = max(2 * iy - 1, 0); oy <= min(2 * iy + 2, 2 * h - 1); ++oy) {
+      const float wy = up_w(iy, oy, h);
+      if (wy == 0.f) continue;
+      for (int ox = max(2 * ix - 1, 0); ox <= min(2 * ix + 2, 2 * w - 1); ++ox) {
+        const float wx = up_w(ix, ox, w);
+        if (wx == 0.f) continue;
+        float f[8];
+        unpack8(__ldg(base + ((long long)oy * 2 * w + ox) * vpp), f);
+        const float wt = wy * wx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wt, f[i], acc[i]);
+      }
+    }
+    gin[e] = pack8(acc);
+  }
+}
+
+static int grid_for_elems(long long work, int block, int mult = 16) {
+  long long b = (work + block - 1) / block;
+  const long long cap = (long long)sm_count() * mult;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" int dfb_bn2d_finalize(const double* stats, double count, int C, int training, float eps, float momentum,
+                                 const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                 float* bn, void* stream_) {
+  if (C <= 0 || C > 256) { set_error("dfb_bn2d_finalize: C must be in 1..256"); return DFB_ERR_ARG; }
+  k_bn2d_finalize<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(stats, count, C, training, eps, momentum, gamma, beta,
+                                                                      running_mean, running_var, bn);
+  add_launches(1);
+  return check_launch("dfb_bn2d_finalize");
+}
+
+extern "C" int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, void* stream_) {
+  if (C % 8 || C > 256) { set_error("dfb_bn_gelu_apply: C must be a multiple of 8 and <= 256"); return DFB_ERR_ARG; }
+  const long long n_vec = n_pix * (C >> 3);
+  k_bn_gelu_apply<<<grid_for_elems(n_vec, 256), 256, 0, (cudaStream_t)stream_>>>((const uint4*)x, bn, C, n_vec, (uint4*)y);
+  add_launches(1);
+  return check_launch("dfb_bn_gelu_apply");
+}
+
+extern "C" int dfb_bn_gelu_backward(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
+                                    double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (C % 8 || C > 256 || 256 % (C >> 3)) { set_error("dfb_bn_gelu_backward: unsupported channel count %d", C); return DFB_ERR_ARG; }
+  cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st);
+  const int prows = 256 / (C >> 3);
+  k_bn_gelu_bwd_reduce<<<grid_for_elems(n_pix, prows, 8), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, C, n_pix, red);
+  const long long n_vec = n_pix * (C >> 3);
+  k_bn_gelu_bwd_apply<<<grid_for_elems(n_vec, 256), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, red, (double)n_pix,
+                                                                  training, C, n_vec, (uint4*)gx);
+  k_bn_param_grads<<<(C + 127) / 128, 128, 0, st>>>(red, bn, C, training, g_gamma, g_beta, g_bias);
+  add_launches(3);
+  return check_launch("dfb_bn_gelu_backward");
+}
+
+extern "C" int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, void* stream_) {
+  if (C % 8 || C > 256 || 256 % (C >> 3)) { set_error("dfb_channel_sum: unsupported channel count %d", C); return DFB_ERR_ARG; }
+  const int prows = 256 / (C >> 3);
+  k_channel_sum<<<grid_for_elems(n_pix, prows, 8), 256, 0, (cudaStream_t)stream_>>>((const uint4*)g, C, n_pix, out);
+  add_launches(1);
+  return check_launch("dfb_channel_sum");
+}
+
+extern "C" int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int backward, void* stream_) {
+  if (C % 8) { set_error("dfb_upsample2x: C must be a multiple of 8"); return DFB_ERR_ARG; }
+  const long long vec_in = (long long)n * h * w * (C >> 3);
+  if (!backward) k_upsample2x<<<grid_for_elems(vec_in * 4, 256), 256, 0, (cudaStream_t)stream_>>>((const uint4*)in, n, h, w, C, (uint4*)out);
+  else k_upsample2x_bwd<<<grid_for_elems(vec_in, 256), 256, 0, (cudaStream_t)stream_>>>((const uint4*)in, n, h, w, C, (uint4*)out);
+  add_launches(1);
+  return check_launch("dfb_upsample2x");
+}

@@ -183,6 +183,56 @@ int dfb_flow_loss(int kind, const float* est, const float* flow_gt, const float*
                   const unsigned char* classes, const long long* pt_idx, const int* counts, int F, int B,
                   int Nmax, double* bucket_ws, float* loss, float* grad_est, int n_cap, void* stream);
 
+/* ------------------------------------------------------------------ UNet convolutions (tensor cores)
+ * Every nn.Conv2d of FastFlow3DUNet (REF/src/models/basic/unet.py:49-68; ConvWithNorms in
+ * REF/src/models/basic/__init__.py:61-79), as a tcgen05 implicit GEMM on NHWC bf16 tensors.
+ *   dfb_conv_pack_weights: torch-layout fp32 weights [cout,cin,k,k] -> bf16 GEMM operands
+ *       w_fwd [cout][tap*cin + ci] and w_dgrad [cin][tap*cout + co] (either may be NULL).
+ *   dfb_conv2d mode 0 (forward): y[n,Ho,Wo,cout] = conv(cat(x[0..n_src-1], channel axis)) + bias, optional
+ *       per-channel sum / sum-of-squares of y accumulated (+=) into stats[2][cout] (BatchNorm batch statistics).
+ *   dfb_conv2d mode 1 (data gradient): x[0] = grad_y [n,Ho,Wo,cout] -> y = grad_x [n,H,W,cin[0]] for the input
+ *       channel slice [cin_off, cin_off + cin[0]) of a layer with cin_total input channels.
+ *   dfb_conv2d_wgrad: grad_w (+)= sum over pixels, written in torch layout fp32 [cout,cin_total,k,k].
+ * H, W are always the spatial size of the convolution INPUT; padding = ksize/2. */
+typedef struct {
+  int mode;              /* 0 forward, 1 data gradient */
+  int n, H, W;           /* batch, input height, input width */
+  int ksize, stride;     /* 1 or 3; 1 or 2 */
+  int n_src;             /* forward: 1 or 2 channel-concatenated sources */
+  const void* x[2];      /* bf16 NHWC sources */
+  int cin[2];            /* channels per source (multiples of 32) */
+  int cin_total, cin_off;/* dgrad only: the layer's total input channels and this slice's offset */
+  int cout;              /* 32, 64, 128 or 256 (forward N tile = cout) */
+  const void* w;         /* packed bf16 weights: w_fwd (mode 0) or w_dgrad (mode 1) */
+  const float* bias;     /* [cout] fp32 or NULL (mode 0) */
+  void* y;               /* output NHWC, bf16 (or fp32 if y_fp32) */
+  int y_fp32;
+  double* stats;         /* [2][cout] or NULL */
+} dfb_conv_args;
+int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, void* w_fwd, void* w_dgrad, void* stream);
+int dfb_conv2d(const dfb_conv_args* args, void* stream);
+/* args as for the forward (x sources, geometry) with args->y = grad_y (bf16, input).  wacc: fp32 workspace
+ * [k*k][cout][cin_total] (zeroed inside); grad_w: fp32 torch layout, overwritten or (accumulate) added to. */
+int dfb_conv2d_wgrad(const dfb_conv_args* args, float* wacc, float* grad_w, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------ UNet HBM-bound passes (NHWC bf16)
+ * BatchNorm2d(eps 1e-5, momentum 0.1) + exact GELU of ConvWithNorms (REF/src/models/basic/__init__.py:61-79) and
+ * the bilinear x2 upsample (REF/src/models/basic/unet.py:8-18).
+ *   dfb_bn2d_finalize: stats[2][C] (sum, sum of squares over `count` elements, from dfb_conv2d) -> bn[4][C] =
+ *       a = gamma*rstd | b = beta - mean*a | mean | rstd; training updates running_mean / running_var in place.
+ *   dfb_bn_gelu_apply: y = GELU(a*x + b).
+ *   dfb_bn_gelu_backward: gx = dL/dx from gy = dL/dy; g_gamma / g_beta / g_bias (+=); red: double[2*C] workspace.
+ *   dfb_channel_sum: out[c] += sum over pixels of g[:, c] (bias gradient of the un-normalised decoder convolutions).
+ *   dfb_upsample2x: backward = 0: in [n,h,w,C] -> out [n,2h,2w,C]; backward = 1: in = grad_out [n,2h,2w,C] -> out [n,h,w,C]. */
+int dfb_bn2d_finalize(const double* stats, double count, int C, int training, float eps, float momentum,
+                      const float* gamma, const float* beta, float* running_mean, float* running_var, float* bn,
+                      void* stream);
+int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, void* stream);
+int dfb_bn_gelu_backward(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
+                         double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, void* stream);
+int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, void* stream);
+int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int backward, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,163 @@
+"""tcgen05 implicit-GEMM convolutions and the HBM-bound UNet passes against torch fp32 references of the same
+bf16-rounded operands (floating point: tolerances are bf16 output rounding, 2^-8 relative)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import deflow_b200 as d
+from deflow_b200 import conv
+from oracle import deflow_oracle as orc
+from helpers import load_fixture, batch_to
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CASES = [
+    ("1x1 64->64", 2, 32, 32, [64], 64, 1, 1),
+    ("3x3 64->64", 2, 32, 32, [64], 64, 3, 1),
+    ("3x3 64->128 s2", 2, 32, 32, [64], 128, 3, 2),
+    ("3x3 32->64 s2", 2, 64, 64, [32], 64, 3, 2),
+    ("3x3 128->128", 1, 32, 24, [128], 128, 3, 1),
+    ("3x3 256->256", 1, 16, 16, [256], 256, 3, 1),
+    ("3x3 cat(64,64)->64", 2, 32, 32, [64, 64], 64, 3, 1),
+    ("1x1 cat(256,256)->256", 1, 16, 16, [256, 256], 256, 1, 1),
+    ("3x3 64->64 ragged tiles", 1, 20, 12, [64], 64, 3, 1),
+    ("3x3 128->256 s2", 1, 32, 32, [128], 256, 3, 2),
+    ("1x1 cat(32,32)->64", 1, 32, 32, [32, 32], 64, 1, 1),
+    ("3x3 64->64 many tiles", 3, 128, 128, [64], 64, 3, 1),
+]
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(1e-6, float(b.abs().max()))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_forward_dgrad_wgrad(case):
+    name, n, H, W, cins, cout, k, s = case
+    torch.manual_seed(len(name))
+    xs = [torch.randn(n, H, W, c, device=DEV).to(torch.bfloat16) for c in cins]
+    ct = sum(cins)
+    w = torch.randn(cout, ct, k, k, device=DEV) / (ct * k * k) ** 0.5
+    b = torch.randn(cout, device=DEV)
+    wf, wd = conv.pack_weights(w)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    xcat = torch.cat([x.float() for x in xs], 3).permute(0, 3, 1, 2).requires_grad_(True)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        ref = F.conv2d(xcat, wr, b, stride=s, padding=k // 2)
+    refn = ref.permute(0, 2, 3, 1)
+    stats = torch.zeros(2, cout, dtype=torch.float64, device=DEV)
+    y = conv.conv2d_forward(xs, wf, b, cout, k, s, stats)
+    assert _rel(y.float(), refn) <= 2 ** -8          # bf16 rounding of the stored output
+    assert _rel(stats[0], refn.double().sum((0, 1, 2))) <= 1e-5 + 1e-3 * 0  # fp32 accumulators, pre-rounding
+    assert _rel(stats[1], refn.double().square().sum((0, 1, 2))) <= 1e-5
+    y32 = conv.conv2d_forward(xs, wf, b, cout, k, s, None, torch.float32)
+    assert _rel(y32, refn) <= 2e-5                    # fp32 output: only the accumulation order differs
+    gy = torch.randn_like(refn).to(torch.bfloat16).contiguous()
+    ref.backward(gy.float().permute(0, 3, 1, 2))
+    off = 0
+    for x, c in zip(xs, cins):
+        gx = conv.conv2d_dgrad(gy, wd, H, W, c, ct, off, k, s)
+        assert _rel(gx.float(), xcat.grad.permute(0, 2, 3, 1)[..., off:off + c]) <= 2 ** -8
+        off += c
+    gw = conv.conv2d_wgrad(xs, gy, k, s)
+    assert _rel(gw, wr.grad) <= 2e-5
+    gw2 = conv.conv2d_wgrad(xs, gy, k, s, gw.clone())  # accumulate mode
+    assert _rel(gw2, 2 * wr.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("C,training", [(64, True), (128, True), (256, True), (64, False)])
+def test_bn_gelu_forward_backward(C, training):
+    torch.manual_seed(C)
+    n, H, W = 2, 24, 16
+    x = (torch.randn(n, H, W, C, device=DEV) * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    beta = (0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    rm, rv = torch.randn(C, device=DEV) * 0.1, torch.rand(C, device=DEV) + 0.5
+    rm2, rv2 = rm.clone(), rv.clone()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.gelu(F.batch_norm(xr, rm2, rv2, gamma, beta, training, 0.1, 1e-5))
+    xf = x.float()
+    stats = torch.stack([xf.double().sum((0, 1, 2)), xf.double().square().sum((0, 1, 2))])
+    bn = conv.bn2d_finalize(stats, n * H * W, training, 1e-5, 0.1, gamma.detach(), beta.detach(), rm, rv)
+    y = conv.bn_gelu_apply(x, bn)
+    assert float((y.float() - ref.permute(0, 2, 3, 1)).abs().max()) <= 2 ** -7 * max(1.0, float(ref.abs().max()))
+    if training:
+        np.testing.assert_allclose(rm.cpu().numpy(), rm2.cpu().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rv.cpu().numpy(), rv2.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    gy = torch.randn(n, H, W, C, device=DEV).to(torch.bfloat16)
+    ref.backward(gy.float().permute(0, 3, 1, 2))
+    gg, gb, gbias = (torch.zeros(C, device=DEV) for _ in range(3))
+    gx = conv.bn_gelu_backward(x, gy, bn, training, gg, gb, gbias)
+    rgx = xr.grad.permute(0, 2, 3, 1)
+    assert float((gx.float() - rgx).abs().max()) <= 2 ** -7 * max(1.0, float(rgx.abs().max()))
+    assert _rel(gg, gamma.grad) <= 1e-4 and _rel(gb, beta.grad) <= 1e-4
+    if training:
+        assert float(gbias.abs().max()) == 0.0
+
+
+def test_upsample_and_channel_sum():
+    torch.manual_seed(1)
+    x = torch.randn(2, 12, 20, 64, device=DEV).to(torch.bfloat16)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    y = conv.upsample2x(x)
+    assert y.shape == (2, 24, 40, 64)
+    assert float((y.float() - ref.permute(0, 2, 3, 1)).abs().max()) <= 2 ** -7 * float(ref.abs().max())
+    g = torch.randn(2, 24, 40, 64, device=DEV).to(torch.bfloat16)
+    ref.backward(g.float().permute(0, 3, 1, 2))
+    gx = conv.upsample2x(g, backward=True)
+    rg = xr.grad.permute(0, 2, 3, 1)
+    assert float((gx.float() - rg).abs().max()) <= 2 ** -7 * float(rg.abs().max())
+    s = conv.channel_sum(g)
+    assert _rel(s, g.float().sum((0, 1, 2))) <= 1e-5
+
+
+def test_unet_tensor_core_path_vs_fp32_library():
+    """Whole backbone, forward + backward: bf16 tensor-core path against the strict-fp32 path (same weights)."""
+    torch.manual_seed(0)
+    net = d.FastFlow3DUNet().to(DEV).train()
+    net.apply(d.weights_init)
+    a = (torch.randn(2, 64, 64, 32, device=DEV) * (torch.rand(2, 64, 64, 1, device=DEV) < 0.1)).to(torch.bfloat16)
+    b = (torch.randn(2, 64, 64, 32, device=DEV) * (torch.rand(2, 64, 64, 1, device=DEV) < 0.1)).to(torch.bfloat16)
+    g = torch.randn(2, 64, 64, 64, device=DEV)
+    net.compute_dtype = torch.float32
+    a32, b32 = a.float().requires_grad_(True), b.float().requires_grad_(True)
+    ref = net.forward_nhwc(a32, b32)
+    ref.backward(g)
+    ref_grads = {k: p.grad.clone() for k, p in net.named_parameters()}
+    ga32 = a32.grad.clone()
+    net.zero_grad()
+    net.compute_dtype = torch.bfloat16
+    a16, b16 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    out = net.forward_nhwc(a16, b16)
+    out.backward(g.to(torch.bfloat16))
+    err = float((out.float() - ref).abs().max()) / float(ref.abs().max())
+    print(f"unet bf16 vs fp32: output rel max err {err:.4f}")
+    assert err <= 0.05
+    assert _rel(a16.grad.float(), ga32) <= 0.1
+    worst = 0.0
+    for k, p in net.named_parameters():
+        r = ref_grads[k]
+        if "conv.bias" in k and "encoder" in k:
+            continue  # analytically zero in training mode; the fp32 path holds rounding noise
+        e = float((p.grad - r).abs().max()) / max(1e-6, float(r.abs().max()))
+        worst = max(worst, e)
+        assert e <= 0.15, (k, e)
+    print(f"unet bf16 vs fp32: worst parameter-gradient rel max err {worst:.4f}")
+
+
+def test_model_bf16_mode_reports_flow_error():
+    """Perf mode (bf16 operands) on the golden fixtures: the measured flow error is reported; indices stay exact."""
+    for name in ("deflow_small_gru", "deflow_cfg1_20k"):
+        fx, batch, cfg = load_fixture(name)
+        m = d.DeFlow(cfg["voxel_size"], cfg["range"], cfg["grid"], cfg["decoder"], 4, precision="bf16")
+        m.load_state_dict(orc.random_state(cfg["seed_state"], cfg["decoder"]), strict=True)
+        m = m.to(DEV).train(cfg["training"])
+        with torch.no_grad():
+            res = m(batch_to(batch, DEV))
+        assert np.array_equal(res["pc0_valid_point_idxes"][0].cpu().numpy(), fx["pc0_idx_0"])   # integer path is exact
+        e = np.abs(res["flow"][0].float().cpu().numpy() - fx["flow_0"])
+        print(f"{name}: bf16 perf-mode flow error max {e.max():.4g} mean {e.mean():.4g} (|flow| max {np.abs(fx['flow_0']).max():.3g})")
+        assert e.max() <= 0.15 and e.mean() <= 0.01
