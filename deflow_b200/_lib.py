@@ -125,6 +125,16 @@ def _declare(lib):
         "dfb_bn_gelu_backward": [vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp],
         "dfb_channel_sum": [vp, i32, i64, vp, vp],
         "dfb_upsample2x": [vp, i32, i32, i32, i32, vp, i32, vp],
+        "dfb_offset_encode": [vp, vp, vp, i32, i32, i32, vp, vp],
+        "dfb_offset_encode_backward": [vp, vp, i32, i32, vp, vp, vp],
+        "dfb_to_bf16_pad": [vp, i32, i32, i32, vp, vp],
+        "dfb_gru_rh": [vp, vp, i32, i32, vp, vp],
+        "dfb_gru_update": [vp, vp, vp, i32, i32, vp, vp, vp],
+        "dfb_gru_bwd1": [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp],
+        "dfb_gru_bwd2": [vp, vp, vp, i32, i32, vp, vp, vp],
+        "dfb_acc_bf16": [vp, vp, vp, i64, vp],
+        "dfb_head_out": [vp, vp, vp, i32, vp, vp],
+        "dfb_head_out_backward": [vp, vp, vp, i32, i32, vp, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -137,7 +147,9 @@ EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size",
            "dfb_scatter_index", "dfb_scatter_reduce", "dfb_dynamic_point_to_voxel_backward", "dfb_index_workspace",
            "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_decoder_gather",
            "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_conv2d", "dfb_conv2d_wgrad",
-           "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x"]
+           "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
+           "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",
+           "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward"]
 
 
 def lib():

@@ -147,6 +147,15 @@ def packed(w: torch.Tensor):
     return wf, wd
 
 
+def packed_raw(w4: torch.Tensor):
+    """Packed operands of a derived (non-parameter) weight tensor: cached on the tensor object itself."""
+    hit = getattr(w4, "_dfb_packed", None)
+    if hit is None:
+        hit = pack_weights(w4)
+        w4._dfb_packed = hit
+    return hit
+
+
 class _Conv(torch.autograd.Function):
     """Conv2d(k, stride 1, pad k//2, bias) over 1-2 channel-concatenated NHWC bf16 sources."""
 

@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad(const __grid_const
     float* dst = P.wacc + ((size_t)gr.tap * P.cout) * P.cin_total + gr.ci_glob + (m & 63);
     const bool live = g >= 0 && (gr.ci_glob + (m & 63)) < P.cin_total;
 #pragma unroll 1
-    for (int col = 0; col < N; col += 32) {
+    for (int col = 0; col < N && col < P.cout; col += 32) {  // cout = 32 rides in a zero-filled 64-wide tile
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + col, v);
       if (live) {
@@ -645,7 +645,7 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
   if (!a || !wacc || !grad_w) { set_error("dfb_conv2d_wgrad: null args"); return DFB_ERR_ARG; }
   const int k = a->ksize, s = a->stride, taps = k * k;
   if ((k != 1 && k != 3) || (s != 1 && s != 2) || a->n_src < 1 || a->n_src > 2) { set_error("dfb_conv2d_wgrad: bad conv geometry"); return DFB_ERR_ARG; }
-  if (a->cout != 64 && a->cout != 128 && a->cout != 256) { set_error("dfb_conv2d_wgrad: cout must be 64, 128 or 256"); return DFB_ERR_UNSUPPORTED; }
+  if (a->cout != 32 && a->cout != 64 && a->cout != 128 && a->cout != 256) { set_error("dfb_conv2d_wgrad: cout must be 32, 64, 128 or 256"); return DFB_ERR_UNSUPPORTED; }
   const int H = a->H, W = a->W;
   const int Ho = (H + 2 * (k / 2) - k) / s + 1, Wo = (W + 2 * (k / 2) - k) / s + 1;
   int cin_total = 0;
@@ -712,7 +712,7 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
   P.wacc = wacc;
   const size_t total = (size_t)taps * a->cout * cin_total;
   cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
-  if (a->cout == 64) rc = tc::launch_wgrad<64>(maps, P, st);
+  if (a->cout <= 64) rc = tc::launch_wgrad<64>(maps, P, st);
   else if (a->cout == 128) rc = tc::launch_wgrad<128>(maps, P, st);
   else rc = tc::launch_wgrad<256>(maps, P, st);
   if (rc) return rc;

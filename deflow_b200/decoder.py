@@ -42,6 +42,13 @@ class _GatherDecoder(nn.Module):
     def _gather(self, before_nhwc, after_nhwc, idx: ops.PillarIndex, B: int, n_rows: int):
         return ops.decoder_gather(before_nhwc, after_nhwc, idx, B, n_rows, torch.float32)
 
+    def _forward_tensor_core(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets, iters):
+        """bf16 perf mode: gather -> (GRU iterations) -> MLP head on the tensor cores (deflow_b200/gru.py)."""
+        from . import gru
+        n_pad = max((n_rows + 7) // 8 * 8, 8)
+        h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.float32, n_pad)
+        return gru.decode(h0, offsets, n_rows, self, iters)
+
     def forward(self, before_pseudoimages, after_pseudoimages, voxelizer_infos) -> List[torch.Tensor]:
         """Reference signature (decoder.py:239-253 / 106-119): before [B,64,H,W] = cat(img0, img1),
         after [B,64,H,W], list of per-sample dicts.  Rebuilds the flat index from the dicts."""
@@ -69,8 +76,10 @@ class ConvGRUDecoder(_GatherDecoder):
 
     def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
         """All pc0 points of the batch at once -> flow [n_rows, 3]."""
-        h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
         offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
+        if self.compute_dtype == torch.bfloat16:
+            return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, self.num_iters)
+        h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(self.compute_dtype == torch.bfloat16)):
             x = self.offset_encoder(offsets)
             for _ in range(self.num_iters):
@@ -88,8 +97,10 @@ class LinearDecoder(_GatherDecoder):
         self.compute_dtype = torch.float32
 
     def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
-        h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
         offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
+        if self.compute_dtype == torch.bfloat16:
+            return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, 0)
+        h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(self.compute_dtype == torch.bfloat16)):
             x = self.offset_encoder(offsets)
             return self.decoder(torch.cat([h, x.float()], dim=1)).float()

@@ -231,12 +231,16 @@ class _DecoderGather(torch.autograd.Function):
     """h0[p] = [img0[y,x], img1[y,x], unet[y,x]] for every pc0 point (OSF/src/models/basic/decoder.py:215-225)."""
 
     @staticmethod
-    def forward(ctx, img, unet, idx: PillarIndex, B, n_rows, out_dtype):
+    def forward(ctx, img, unet, idx: PillarIndex, B, n_rows, out_dtype, n_alloc):
         _need_cuda(img, "decoder_gather")
         assert img.is_contiguous() and unet.is_contiguous() and img.dtype == unet.dtype
         F, H, W, c = img.shape
         assert c == 32 and F == 2 * B and tuple(unet.shape) == (B, H, W, 64)
-        h0 = torch.empty((n_rows, 128), dtype=out_dtype, device=img.device)
+        if n_alloc is not None and n_alloc > n_rows:  # zero padding rows for the tensor-core decoder
+            h0 = torch.empty((n_alloc, 128), dtype=out_dtype, device=img.device)
+            h0[n_rows:].zero_()
+        else:
+            h0 = torch.empty((n_rows, 128), dtype=out_dtype, device=img.device)
         check(_lib.lib().dfb_decoder_gather(img.data_ptr(), unet.data_ptr(), int(img.dtype == torch.bfloat16), B, H, W,
                                             idx.counts.data_ptr(), idx.F, idx.pt_pillar.data_ptr(),
                                             idx.pil_pix.data_ptr(), h0.data_ptr(), int(out_dtype == torch.bfloat16),
@@ -257,11 +261,11 @@ class _DecoderGather(torch.autograd.Function):
                                                      idx.pil_start.data_ptr(), idx.sorted_pt.data_ptr(),
                                                      g_img.data_ptr(), g_unet.data_ptr(), int(dt == torch.bfloat16),
                                                      idx.pil_cap, _stream(grad_h0)), "decoder_gather_backward")
-        return g_img, g_unet, None, None, None, None
+        return g_img, g_unet, None, None, None, None, None
 
 
-def decoder_gather(img, unet, idx, B, n_rows, out_dtype=torch.float32):
-    return _DecoderGather.apply(img, unet, idx, B, n_rows, out_dtype)
+def decoder_gather(img, unet, idx, B, n_rows, out_dtype=torch.float32, n_alloc=None):
+    return _DecoderGather.apply(img, unet, idx, B, n_rows, out_dtype, n_alloc)
 
 
 # ----------------------------------------------------------------------------------------------

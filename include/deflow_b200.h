@@ -233,6 +233,33 @@ int dfb_bn_gelu_backward(const void* x, const void* gy, const float* bn, int C, 
 int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, void* stream);
 int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int backward, void* stream);
 
+/* ------------------------------------------------------------------ per-point decoder stages
+ * ConvGRU / ConvGRUDecoder / LinearDecoder (REF/src/models/basic/decoder.py:71-119, 177-253).  The gate and MLP
+ * matrices run as 1x1 dfb_conv2d calls over the point list viewed as an [1, n_pad/8, 8, C] image; these are the
+ * HBM-bound stages between them.  All bf16 buffers have n_pad rows (n_pad % 8 == 0); rows >= n are written as zero.
+ *   dfb_offset_encode:  x[n_pad,cx] bf16 = Linear(3,cx)(offsets[n,3])            (decoder.py:200,228)
+ *   dfb_to_bf16_pad:    bf16 zero-padded copy of an fp32 [n,C] matrix
+ *   dfb_gru_rh:         rh = sigmoid(r_pre) * h            zr_pre [n_pad,256] bf16 = (z_pre | r_pre), h fp32 [n_pad,128]
+ *   dfb_gru_update:     h' = (1 - z) h + z tanh(q_pre)     -> h' fp32 and its bf16 copy
+ *   dfb_gru_bwd1/2:     the two elementwise stages of the backward of one GRU iteration (see csrc/gru_elem.cu)
+ *   dfb_acc_bf16:       acc fp32 += a (+ b), a / b bf16
+ *   dfb_head_out:       flow[n,3] = Linear(32,3)(GELU(y1))  and its backward (dy1, grad W2 [3,32] +=, grad b2 +=)
+ *   dfb_offset_encode_backward: grad W [cx,3] += dx^T offsets, grad b += sum dx   (dx fp32 [n_pad,cx]) */
+int dfb_offset_encode(const float* offs, const float* w, const float* b, int n, int n_pad, int cx, void* x, void* stream);
+int dfb_offset_encode_backward(const float* dx, const float* offs, int n, int cx, float* gw, float* gb, void* stream);
+int dfb_to_bf16_pad(const float* src, int n, int n_pad, int C, void* dst, void* stream);
+int dfb_gru_rh(const void* zr_pre, const float* h, int n, int n_pad, void* rh, void* stream);
+int dfb_gru_update(const void* zr_pre, const void* q_pre, const float* h, int n, int n_pad, float* h_new, void* hb_new,
+                   void* stream);
+int dfb_gru_bwd1(const void* zr_pre, const void* q_pre, const float* h, const float* dh_new, int n, int n_pad,
+                 void* dq_pre, void* dzr_pre, float* dh_acc, void* stream);
+int dfb_gru_bwd2(const void* zr_pre, const float* h, const void* d_rh, int n, int n_pad, void* dzr_pre, float* dh_acc,
+                 void* stream);
+int dfb_acc_bf16(float* acc, const void* a, const void* b, long long n_elems, void* stream);
+int dfb_head_out(const void* y1, const float* w2, const float* b2, int n, float* flow, void* stream);
+int dfb_head_out_backward(const void* y1, const float* w2, const float* dflow, int n, int n_pad, void* dy1, float* gw2,
+                          float* gb2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

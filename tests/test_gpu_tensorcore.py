@@ -161,3 +161,38 @@ def test_model_bf16_mode_reports_flow_error():
         e = np.abs(res["flow"][0].float().cpu().numpy() - fx["flow_0"])
         print(f"{name}: bf16 perf-mode flow error max {e.max():.4g} mean {e.mean():.4g} (|flow| max {np.abs(fx['flow_0']).max():.3g})")
         assert e.max() <= 0.15 and e.mean() <= 0.01
+
+
+@pytest.mark.parametrize("kind", ["gru", "linear"])
+def test_decoder_tensor_core_path_vs_fp32(kind):
+    """ConvGRUDecoder / LinearDecoder: bf16 tensor-core path (hand-written backward) against the fp32 torch path."""
+    from deflow_b200 import ops, synth
+    torch.manual_seed(3)
+    B, H, W = 2, 64, 64
+    rg = [-6.4, -6.4, -3, 6.4, 6.4, 3]
+    pts = synth.make_batch(2 * B, 1500, seed=31)["pc0"].clone()
+    pts[..., :2] /= 8.0
+    idx = ops.pillar_index(pts.half().float().to(DEV), [0.2, 0.2, 6], rg)
+    n0 = idx.pt_off(B)
+    head = (d.ConvGRUDecoder(num_iters=4) if kind == "gru" else d.LinearDecoder()).to(DEV)
+    head.apply(d.weights_init)
+    img = (torch.randn(2 * B, H, W, 32, device=DEV) * 0.5).to(torch.bfloat16)
+    unet = (torch.randn(B, H, W, 64, device=DEV) * 0.5).to(torch.bfloat16)
+    gflow = torch.randn(n0, 3, device=DEV)
+    res = {}
+    for mode in ("fp32", "bf16"):
+        head.zero_grad()
+        head.compute_dtype = torch.float32 if mode == "fp32" else torch.bfloat16
+        i2 = (img.float() if mode == "fp32" else img.clone()).requires_grad_(True)
+        u2 = (unet.float() if mode == "fp32" else unet.clone()).requires_grad_(True)
+        flow = head.forward_flat(i2, u2, idx, B, n0)
+        flow.backward(gflow)
+        res[mode] = (flow.detach(), i2.grad.float(), u2.grad.float(), {k: p.grad.clone() for k, p in head.named_parameters()})
+    f32, f16 = res["fp32"], res["bf16"]
+    e = float((f16[0] - f32[0]).abs().max())
+    print(f"{kind} decoder bf16 vs fp32: flow abs max err {e:.4g} (|flow| max {float(f32[0].abs().max()):.3g})")
+    assert e <= 0.03 * max(1.0, float(f32[0].abs().max()))
+    assert _rel(f16[1], f32[1]) <= 0.1 and _rel(f16[2], f32[2]) <= 0.1
+    for k, g in f32[3].items():
+        r = _rel(f16[3][k], g)
+        assert r <= 0.1, (k, r)
