@@ -214,9 +214,8 @@ def run_native(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    from deflow_b200 import dist as dd
+    dd.init("nccl", dev)
     _lib.lib()  # fail loudly if the CUDA library is missing
     peaks = load_peaks()
 
@@ -226,28 +225,15 @@ def run_native(args):
     model = d.DeFlow(vs, RG, [args.grid, args.grid], args.decoder, 4, precision=args.precision)
     model.apply(d.weights_init)
     model = model.to(dev).train()
-    if world > 1:
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
-    else:
-        net = model
-    opt = torch.optim.Adam(model.parameters(), lr=2e-4, fused=True)
+    dd.broadcast_module(model)
+    from deflow_b200.trainer import TrainStep
+    step = TrainStep(model, lr=2e-4, loss_fn=args.loss, gradient_clip_val=5.0)
 
     host = synth.make_batch(args.batch, args.points, seed=synth.SEED_BASE + rank, pin=True)
     host["pose0"] = torch.stack(host["pose0"]).pin_memory()
     host["pose1"] = torch.stack(host["pose1"]).pin_memory()
     resident = synth.batch_to(host, dev, non_blocking=False)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-
-    def step(batch):
-        opt.zero_grad(set_to_none=True)
-        res = net(batch)
-        loss = d.training_step_loss(batch, res, args.loss)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)  # OSF/conf/config.yaml:26
-        opt.step()
-        return loss
 
     def barrier():
         if world > 1:
@@ -268,7 +254,8 @@ def run_native(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, out
 
-    for _ in range(max(args.warmup, 3)):
+    n_warm = args.warmup if os.environ.get("DFB_PROFILE") else max(args.warmup, 3)  # profiling runs may warm up less
+    for _ in range(n_warm):
         loss = step(resident)
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
@@ -299,7 +286,7 @@ def run_native(args):
         wrap("unet_fwd", model.backbone, "forward_nhwc")
         wrap("decoder_fwd", model.head, "forward_flat")
         s0, s1, s2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        opt.zero_grad(set_to_none=True)
+        step.grads.zero()
         s0.record()
         res = model(resident)
         lo = d.training_step_loss(resident, res, args.loss)
@@ -324,8 +311,8 @@ def run_native(args):
         def e2e_step():
             b = synth.batch_to(host, dev, non_blocking=True)
             l = step(b)
-            return float(l)  # D2H read of the step's result
-        for _ in range(2):
+            return float(l)  # D2H read of the step's result (the summed loss)
+        for _ in range(0 if os.environ.get("DFB_PROFILE") else 2):
             e2e_step()
         ems, _ = timed(e2e_step, args.steps)
         e2e = {"value": pairs / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems, "h2d_bytes_per_step": h2d * world,
@@ -348,15 +335,15 @@ def run_native(args):
         ach = flops_step / (ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                "note": f"whole-step algorithmic FLOPs / step time, peak = sustained bf16 ({peaks['source']}); "
-                        "dense contractions still run in cuDNN/cuBLAS this round (see DESIGN.md status)"}
+                "note": f"whole-step algorithmic FLOPs (UNet 343.06 GFLOP/pair + decoder 602688 FLOP/pt, x3 for training) / step "
+                        f"time; peak = sustained bf16 ({peaks['source']}); all dense contractions are tcgen05 kernels"}
         cpu = None
         if not args.no_cpu_baseline:
             pts = args.cpu_points or args.points
             v, t, cores = cpu_reference_pairs_per_sec(pts, args.grid, args.decoder, args.loss, 1, 0)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"1 frame pair ({pts} pts/frame, {args.grid}x{args.grid}) fwd+loss+bwd, fp32 torch-CPU oracle port, {t:.1f} s"}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
