@@ -42,6 +42,7 @@ def scatter_case(n, c, span, seed):
 
 
 SCATTER_CASES = [(513, 3, 6, 11), (5000, 32, 20, 12), (60000, 32, 300, 13), (3000, 7, 3, 14)]
+RECORDED = (0, 1, 3)   # case 2 is compared live on the GPU only (tests/test_gpu_vs_reference_ext.py): 24 MB of fixtures
 
 
 def main(out):
@@ -56,6 +57,8 @@ def main(out):
                                      torch.tensor(rg, dtype=torch.float32), coors, 3)
         fix[f"vox{i}_coors"] = coors.cpu().numpy()
     for i, (n, c, span, seed) in enumerate(SCATTER_CASES):
+        if i not in RECORDED:
+            continue
         coors, feats, gseed = scatter_case(n, c, span, seed)
         for red in ("sum", "mean", "max"):
             vf, vc, cmap, cnt = ext.dynamic_point_to_voxel_forward(torch.from_numpy(feats).to(dev), torch.from_numpy(coors).to(dev), red)
