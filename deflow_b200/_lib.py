@@ -135,6 +135,8 @@ def _declare(lib):
         "dfb_acc_bf16": [vp, vp, vp, i64, vp],
         "dfb_head_out": [vp, vp, vp, i32, vp, vp],
         "dfb_head_out_backward": [vp, vp, vp, i32, i32, vp, vp, vp, vp],
+        "dfb_gru_fused_forward": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
+        "dfb_gru_fused_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -149,7 +151,8 @@ EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size",
            "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_conv2d", "dfb_conv2d_wgrad",
            "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",
-           "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward"]
+           "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",
+           "dfb_gru_fused_forward", "dfb_gru_fused_backward"]
 
 
 def lib():

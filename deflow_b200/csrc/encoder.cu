@@ -66,86 +66,83 @@ __global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ cou
   }
 }
 
-// ---------------------------------------------------------------- BatchNorm batch statistics
-// grid (X, F); thread per point, 32 channel accumulators per thread.  PASS 0: sum(y); PASS 1:
-// sum((y - mean)^2).  stats layout [F][2][32] (double).
-template <int PASS>
-__global__ void __launch_bounds__(256) k_pfn_stats(const int* __restrict__ counts, int F, PfnGeom G,
-                                                   const float* __restrict__ pt_xyz, const int* __restrict__ pt_coor,
-                                                   const int* __restrict__ pt_pillar,
-                                                   const float* __restrict__ pil_mean,
-                                                   const float* __restrict__ weight, double* __restrict__ stats) {
-  __shared__ __align__(16) float Wt[PFN_K][PFN_C];  // transposed: Wt[k][c]
-  __shared__ float mean_s[PFN_C];
-  __shared__ float red[8][PFN_C];
+// ---------------------------------------------------------------- BatchNorm batch statistics from moments
+// y = W f is linear in the 9 decorated features, so the per-frame mean / variance of all 32 channels follow from
+// S1 = sum f (9) and S2 = sum f f^T (45 upper-triangular entries): one light pass, 54 accumulators per thread,
+// instead of two passes over the 32 outputs.  mom layout [F][54] (double): S1[9] | S2[45] (row-major upper triangle).
+constexpr int PFN_MOM = 54;
+
+__global__ void __launch_bounds__(256) k_pfn_moments(const int* __restrict__ counts, int F, PfnGeom G,
+                                                     const float* __restrict__ pt_xyz, const int* __restrict__ pt_pillar,
+                                                     const int* __restrict__ pil_coor, const float* __restrict__ pil_mean,
+                                                     double* __restrict__ mom) {
+  __shared__ float red[8][PFN_MOM];
   const int f = blockIdx.y;
   const int p0 = counts[2 * F + f], p1 = counts[2 * F + f + 1];
-  for (int i = threadIdx.x; i < PFN_C * PFN_K; i += blockDim.x) Wt[i % PFN_K][i / PFN_K] = weight[i];
-  if (threadIdx.x < PFN_C) {
-    const double n = (double)(p1 - p0);
-    mean_s[threadIdx.x] = (PASS == 1 && p1 > p0) ? (float)(stats[(size_t)f * 2 * PFN_C + threadIdx.x] / n) : 0.f;
-  }
-  __syncthreads();
-  float acc[PFN_C];
+  float acc[PFN_MOM];
 #pragma unroll
-  for (int c = 0; c < PFN_C; ++c) acc[c] = 0.f;
+  for (int i = 0; i < PFN_MOM; ++i) acc[i] = 0.f;
   for (int p = p0 + blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += gridDim.x * blockDim.x) {
     const float x = pt_xyz[3 * (size_t)p], y = pt_xyz[3 * (size_t)p + 1], z = pt_xyz[3 * (size_t)p + 2];
     const int q = pt_pillar[p];
     float fe[PFN_K];
     decorate(x, y, z, pil_mean[3 * (size_t)q], pil_mean[3 * (size_t)q + 1], pil_mean[3 * (size_t)q + 2],
-             pt_coor[3 * (size_t)p], pt_coor[3 * (size_t)p + 1], pt_coor[3 * (size_t)p + 2], G, fe);
+             pil_coor[3 * (size_t)q], pil_coor[3 * (size_t)q + 1], pil_coor[3 * (size_t)q + 2], G, fe);
+    int o = PFN_K;
 #pragma unroll
-    for (int c4 = 0; c4 < PFN_C; c4 += 4) {
-      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+    for (int j = 0; j < PFN_K; ++j) {
+      acc[j] += fe[j];
 #pragma unroll
-      for (int k = 0; k < PFN_K; ++k) {
-        const float4 w = *reinterpret_cast<const float4*>(&Wt[k][c4]);
-        y0 = fmaf(w.x, fe[k], y0); y1 = fmaf(w.y, fe[k], y1); y2 = fmaf(w.z, fe[k], y2); y3 = fmaf(w.w, fe[k], y3);
-      }
-      if (PASS == 0) {
-        acc[c4] += y0; acc[c4 + 1] += y1; acc[c4 + 2] += y2; acc[c4 + 3] += y3;
-      } else {
-        const float d0 = y0 - mean_s[c4], d1 = y1 - mean_s[c4 + 1], d2 = y2 - mean_s[c4 + 2], d3 = y3 - mean_s[c4 + 3];
-        acc[c4] = fmaf(d0, d0, acc[c4]); acc[c4 + 1] = fmaf(d1, d1, acc[c4 + 1]);
-        acc[c4 + 2] = fmaf(d2, d2, acc[c4 + 2]); acc[c4 + 3] = fmaf(d3, d3, acc[c4 + 3]);
-      }
+      for (int k = j; k < PFN_K; ++k) acc[o++] = fmaf(fe[j], fe[k], acc[o]);
     }
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-  for (int c = 0; c < PFN_C; ++c) {
-    const float s = warp_sum(acc[c]);
-    if (lane == 0) red[w][c] = s;
+  for (int i = 0; i < PFN_MOM; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0) red[w][i] = s;
   }
   __syncthreads();
-  if (threadIdx.x < PFN_C) {
+  if (threadIdx.x < PFN_MOM) {
     double s = 0.0;
     for (int i = 0; i < 8; ++i) s += (double)red[i][threadIdx.x];
-    atomicAdd(&stats[(size_t)f * 2 * PFN_C + PASS * PFN_C + threadIdx.x], s);
+    if (s != 0.0) atomicAdd(&mom[(size_t)f * PFN_MOM + threadIdx.x], s);
   }
 }
 
-// One warp: per-frame scale/shift and the sequential running-statistics updates in the reference's
-// call order pc0[0..B-1], pc1[0..B-1] (encoder.py:624-627, DeFlow.forward deflow.py:82-83).
+// One warp: per-frame mean / variance of W f from the moments (double), scale/shift per frame and the sequential
+// running-statistics updates in the reference's call order pc0[0..B-1], pc1[0..B-1] (encoder.py:624-627,
+// DeFlow.forward deflow.py:82-83).
 __global__ void k_bn_finalize(const int* __restrict__ counts, int F, int training, float eps, float momentum,
-                              const double* __restrict__ stats, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, float* __restrict__ running_mean,
-                              float* __restrict__ running_var, float* __restrict__ bn_params) {
+                              const double* __restrict__ mom, const float* __restrict__ weight,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                              float* __restrict__ bn_params) {
   const int c = threadIdx.x;
   if (c >= PFN_C) return;
   float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
   const float g = gamma[c], b = beta[c];
+  double w[PFN_K];
+  for (int k = 0; k < PFN_K; ++k) w[k] = (double)weight[c * PFN_K + k];
   for (int f = 0; f < F; ++f) {
     const int n = counts[f];
     float mean, var;
     if (training && n > 0) {
-      mean = (float)(stats[(size_t)f * 2 * PFN_C + c] / (double)n);
-      var = (float)(stats[(size_t)f * 2 * PFN_C + PFN_C + c] / (double)n);  // biased, used to normalise
+      const double* m = mom + (size_t)f * PFN_MOM;
+      double s1 = 0.0, s2 = 0.0;
+      int o = PFN_K;
+      for (int j = 0; j < PFN_K; ++j) {
+        s1 += w[j] * m[j];
+        for (int k = j; k < PFN_K; ++k) s2 += (j == k ? 1.0 : 2.0) * w[j] * w[k] * m[o++];
+      }
+      const double mu = s1 / n;
+      double ssq = s2 - s1 * mu;  // sum (y - mean)^2
+      if (ssq < 0.0) ssq = 0.0;
+      mean = (float)mu;
+      var = (float)(ssq / n);  // biased, used to normalise
       if (n > 1) {
-        const float unbiased = (float)(stats[(size_t)f * 2 * PFN_C + PFN_C + c] / (double)(n - 1));
         rm = (1.f - momentum) * rm + momentum * mean;
-        rv = (1.f - momentum) * rv + momentum * unbiased;
+        rv = (1.f - momentum) * rv + momentum * (float)(ssq / (n - 1));
       }
     } else {
       mean = rm; var = rv;
@@ -161,55 +158,104 @@ __global__ void k_bn_finalize(const int* __restrict__ counts, int F, int trainin
   if (training && running_mean) { running_mean[c] = rm; running_var[c] = rv; }
 }
 
-// ---------------------------------------------------------------- pillar pass (forward)
-// Warp per pillar, lane = output channel.  Point coordinates of a pillar are loaded 32 at a time
-// (one per lane) and broadcast with shuffles.
-template <bool BF16>
-__global__ void __launch_bounds__(256) k_pfn_pillar(const int* __restrict__ counts, int F, int HW, PfnGeom G,
-                                                    const float* __restrict__ pt_xyz,
+// ---------------------------------------------------------------- point pass (forward)
+// Thread per point in CSR (pillar-sorted) order: all 32 channels of Linear + BN + ReLU with packed fp32x2 FMAs
+// (weights broadcast from shared memory), then a transposed pass over a [256 points x 32 channels] shared tile
+// (thread = channel x group of 32 consecutive points) forms the per-pillar sums: one coalesced 128-byte
+// red.global.add per pillar and group, no per-point atomics.
+__global__ void __launch_bounds__(256) k_pfn_points(const int* __restrict__ counts, int F, int HW, PfnGeom G,
+                                                    const float* __restrict__ pt_xyz, const int* __restrict__ pt_pillar,
                                                     const int* __restrict__ pil_coor, const int* __restrict__ pil_pix,
-                                                    const int* __restrict__ pil_start,
-                                                    const int* __restrict__ sorted_pt,
-                                                    const float* __restrict__ pil_mean,
-                                                    const float* __restrict__ weight,
-                                                    const float* __restrict__ bn_params,
-                                                    float* __restrict__ pil_feats, void* __restrict__ image) {
-  const int M = counts[3 * F + 1 + F];
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  float w[PFN_K];
+                                                    const int* __restrict__ sorted_pt, const float* __restrict__ pil_mean,
+                                                    const float* __restrict__ weight, const float* __restrict__ bn_params,
+                                                    float* __restrict__ pil_sum) {
+  __shared__ __align__(16) float Wp[PFN_K][PFN_C];   // Wp[k][c]
+  __shared__ float T[256][PFN_C + 1];
+  __shared__ int Q[257];
+  extern __shared__ float sAB[];                      // [F][2][32] scale / shift per frame
+  const int n = counts[2 * F + F];
+  for (int i = threadIdx.x; i < PFN_C * PFN_K; i += blockDim.x) Wp[i % PFN_K][i / PFN_K] = weight[i];
+  for (int i = threadIdx.x; i < F * 2 * PFN_C; i += blockDim.x) {
+    const int f = i / (2 * PFN_C), r = i % (2 * PFN_C);
+    sAB[i] = bn_params[(size_t)f * 4 * PFN_C + r];
+  }
+  __syncthreads();
+  for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
+    const int j = base + threadIdx.x;
+    int q = -1;
+    float2 y2[PFN_C / 2];
+    if (j < n) {
+      const int p = sorted_pt[j];
+      q = pt_pillar[p];
+      const float x = pt_xyz[3 * (size_t)p], yy = pt_xyz[3 * (size_t)p + 1], z = pt_xyz[3 * (size_t)p + 2];
+      float fe[PFN_K];
+      decorate(x, yy, z, pil_mean[3 * (size_t)q], pil_mean[3 * (size_t)q + 1], pil_mean[3 * (size_t)q + 2],
+               pil_coor[3 * (size_t)q], pil_coor[3 * (size_t)q + 1], pil_coor[3 * (size_t)q + 2], G, fe);
 #pragma unroll
-  for (int k = 0; k < PFN_K; ++k) w[k] = weight[lane * PFN_K + k];
-  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < M; q += warps) {
-    const int s0 = pil_start[q], s1 = pil_start[q + 1];
-    const int pix = pil_pix[q];
-    const int f = pix / HW;
-    const float a = bn_params[(size_t)f * 4 * PFN_C + lane], b = bn_params[(size_t)f * 4 * PFN_C + PFN_C + lane];
-    const float mx = pil_mean[3 * (size_t)q], my = pil_mean[3 * (size_t)q + 1], mz = pil_mean[3 * (size_t)q + 2];
-    const int cz = pil_coor[3 * (size_t)q], cy = pil_coor[3 * (size_t)q + 1], cx = pil_coor[3 * (size_t)q + 2];
-    float sum = 0.f;
-    for (int base = s0; base < s1; base += 32) {
-      const int cnt = min(32, s1 - base);
-      float lx = 0.f, ly = 0.f, lz = 0.f;
-      if (lane < cnt) {
-        const int p = sorted_pt[base + lane];
-        lx = pt_xyz[3 * (size_t)p]; ly = pt_xyz[3 * (size_t)p + 1]; lz = pt_xyz[3 * (size_t)p + 2];
+      for (int c = 0; c < PFN_C / 2; ++c) y2[c] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < PFN_K; ++k) {
+        const float2 fk = make_float2(fe[k], fe[k]);
+#pragma unroll
+        for (int c4 = 0; c4 < PFN_C; c4 += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(&Wp[k][c4]);
+          y2[c4 / 2] = __ffma2_rn(make_float2(w.x, w.y), fk, y2[c4 / 2]);
+          y2[c4 / 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), fk, y2[c4 / 2 + 1]);
+        }
       }
-      for (int j = 0; j < cnt; ++j) {
-        const float x = __shfl_sync(0xffffffffu, lx, j), y = __shfl_sync(0xffffffffu, ly, j),
-                    z = __shfl_sync(0xffffffffu, lz, j);
-        float fe[PFN_K];
-        decorate(x, y, z, mx, my, mz, cz, cy, cx, G, fe);
-        float acc = 0.f;
+      const float* ab = sAB + (size_t)(pil_pix[q] / HW) * 2 * PFN_C;
 #pragma unroll
-        for (int k = 0; k < PFN_K; ++k) acc = fmaf(w[k], fe[k], acc);
-        sum += fmaxf(fmaf(acc, a, b), 0.f);
+      for (int c = 0; c < PFN_C / 2; ++c) {
+        const float2 a = *reinterpret_cast<const float2*>(ab + 2 * c), b = *reinterpret_cast<const float2*>(ab + PFN_C + 2 * c);
+        const float2 v = __ffma2_rn(y2[c], a, b);
+        T[threadIdx.x][2 * c] = fmaxf(v.x, 0.f);
+        T[threadIdx.x][2 * c + 1] = fmaxf(v.y, 0.f);
       }
     }
-    const float mean = __fdiv_rn(sum, (float)(s1 - s0));
-    pil_feats[(size_t)q * PFN_C + lane] = mean;
-    if (BF16) reinterpret_cast<__nv_bfloat16*>(image)[(size_t)pix * PFN_C + lane] = __float2bfloat16_rn(mean);
-    else reinterpret_cast<float*>(image)[(size_t)pix * PFN_C + lane] = mean;
+    Q[threadIdx.x] = q;
+    if (threadIdx.x == 0) Q[256] = -2;
+    __syncthreads();
+    {
+      const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+      float acc = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int pt = g * 32 + i;
+        const int qq = Q[pt];
+        if (qq < 0) break;                     // past the end of the point list (warp-uniform)
+        acc += T[pt][c];
+        if (i == 31 || Q[pt + 1] != qq) {      // segment ends inside or at the end of this group (warp-uniform)
+          atomicAdd(&pil_sum[(size_t)qq * PFN_C + c], acc);
+          acc = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// pillar sums -> means (in place: pil_feats) and the NHWC pseudo-image row of every pillar
+template <bool BF16>
+__global__ void __launch_bounds__(256) k_pfn_image(const int* __restrict__ counts, int F, const int* __restrict__ pil_start,
+                                                   const int* __restrict__ pil_pix, float* __restrict__ pil_feats,
+                                                   void* __restrict__ image) {
+  const int M = counts[3 * F + 1 + F];
+  const long long total = (long long)M * 8;  // 4 channels per thread
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(e >> 3), c4 = (int)(e & 7) * 4;
+    const float n = (float)(pil_start[q + 1] - pil_start[q]);
+    float4 v = *reinterpret_cast<float4*>(pil_feats + (size_t)q * PFN_C + c4);
+    v.x = __fdiv_rn(v.x, n); v.y = __fdiv_rn(v.y, n); v.z = __fdiv_rn(v.z, n); v.w = __fdiv_rn(v.w, n);
+    *reinterpret_cast<float4*>(pil_feats + (size_t)q * PFN_C + c4) = v;
+    const size_t o = (size_t)pil_pix[q] * PFN_C + c4;
+    if (BF16) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 r;
+      r.x = *reinterpret_cast<unsigned*>(&a); r.y = *reinterpret_cast<unsigned*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(image) + o) = r;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(image) + o) = v;
+    }
   }
 }
 
@@ -338,29 +384,36 @@ using namespace dfb;
 extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (!a || a->F <= 0 || a->H <= 0 || a->W <= 0) { set_error("dfb_pfn_forward: bad sizes"); return DFB_ERR_ARG; }
+  if (a->F > 256) { set_error("dfb_pfn_forward: at most 256 frames per call"); return DFB_ERR_UNSUPPORTED; }
   const int F = a->F, HW = a->H * a->W;
   const PfnGeom G = make_geom(a);
   const int sms = sm_count();
   const size_t img_bytes = (size_t)F * HW * PFN_C * (a->image_bf16 ? 2 : 4);
   cudaMemsetAsync(a->image, 0, img_bytes, st);
-  cudaMemsetAsync(a->stats, 0, sizeof(double) * (size_t)F * 2 * PFN_C, st);
+  cudaMemsetAsync(a->stats, 0, sizeof(double) * (size_t)F * 2 * PFN_C, st);      // [F][54] moments fit in [F][64]
+  cudaMemsetAsync(a->pil_feats, 0, sizeof(float) * (size_t)a->pil_cap * PFN_C, st);
   k_pillar_mean<<<sms * 8, 256, 0, st>>>(a->counts, F, a->pt_xyz, a->pil_start, a->sorted_pt, a->pil_mean);
+  int launches = 4;
   if (a->training) {
     int bx = (sms * 4 + F - 1) / F;
     if (bx < 1) bx = 1;
     dim3 g(bx, F);
-    k_pfn_stats<0><<<g, 256, 0, st>>>(a->counts, F, G, a->pt_xyz, a->pt_coor, a->pt_pillar, a->pil_mean, a->weight, a->stats);
-    k_pfn_stats<1><<<g, 256, 0, st>>>(a->counts, F, G, a->pt_xyz, a->pt_coor, a->pt_pillar, a->pil_mean, a->weight, a->stats);
+    k_pfn_moments<<<g, 256, 0, st>>>(a->counts, F, G, a->pt_xyz, a->pt_pillar, a->pil_coor, a->pil_mean, a->stats);
+    ++launches;
   }
-  k_bn_finalize<<<1, 32, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum, a->stats, a->gamma, a->beta,
+  k_bn_finalize<<<1, 32, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum, a->stats, a->weight, a->gamma, a->beta,
                                   a->running_mean, a->running_var, a->bn_params);
-  if (a->image_bf16)
-    k_pfn_pillar<true><<<sms * 8, 256, 0, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pil_coor, a->pil_pix, a->pil_start,
-                                                a->sorted_pt, a->pil_mean, a->weight, a->bn_params, a->pil_feats, a->image);
-  else
-    k_pfn_pillar<false><<<sms * 8, 256, 0, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pil_coor, a->pil_pix, a->pil_start,
-                                                 a->sorted_pt, a->pil_mean, a->weight, a->bn_params, a->pil_feats, a->image);
-  add_launches(a->training ? 5 : 3);
+  const int dyn = F * 2 * PFN_C * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_pfn_points, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
+    configured = true;
+  }
+  k_pfn_points<<<sms * 4, 256, dyn, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pt_pillar, a->pil_coor, a->pil_pix, a->sorted_pt,
+                                         a->pil_mean, a->weight, a->bn_params, a->pil_feats);
+  if (a->image_bf16) k_pfn_image<true><<<sms * 8, 256, 0, st>>>(a->counts, F, a->pil_start, a->pil_pix, a->pil_feats, a->image);
+  else k_pfn_image<false><<<sms * 8, 256, 0, st>>>(a->counts, F, a->pil_start, a->pil_pix, a->pil_feats, a->image);
+  add_launches(launches);
   return check_launch("dfb_pfn_forward");
 }
 

@@ -1,0 +1,644 @@
+// Persistent fused ConvGRU decoder, forward: offset encoder -> num_iters GRU iterations -> MLP head, one kernel.
+//
+// Reference: ConvGRUDecoder.forward_single (OpenSceneFlow/src/models/basic/decoder.py:210-237) and ConvGRU.forward
+// (:184-193): per sample, 3 k=1 Conv1d + 2 cats + 5 elementwise launches per iteration, cuDNN / cuBLAS.
+//
+// One CTA owns a tile of 128 points at a time (persistent over tiles).  All gate weights stay resident in shared
+// memory as bf16 K-major SWIZZLE_128B operand tiles (Wz|Wr 96 KB, Wq 48 KB, W1 12 KB, loaded once by TMA).  The
+// hidden state h (fp32) lives in the registers of 256 worker threads (thread = point row x half of the channels)
+// and never touches HBM between iterations; the x = Linear(3,64)(offsets) operand is computed in-kernel.  Per
+// iteration the workers write bf16(h) (then bf16(r*h)) into the A operand tile with the 128-byte swizzle applied by
+// hand, one thread issues tcgen05.mma (M = 128 points, N = 256 / 128, K = 192) into TMEM, and the workers read the
+// gate pre-activations back with tcgen05.ld for the sigmoid / tanh / lerp.  For the backward pass the kernel saves
+// bf16 copies of the state entering every iteration, the final state and the head pre-activation.
+#include "tc_common.cuh"
+#include "../../include/deflow_b200.h"
+
+namespace dfb {
+namespace tc {
+
+constexpr int GF_THREADS = 288;  // warps 0..7 workers, warp 8 control (TMA + MMA issue)
+constexpr int GF_WZR = 0;                         // 3 x [256 x 128 B]
+constexpr int GF_WQ = GF_WZR + 3 * 32768;         // 3 x [128 x 128 B]
+constexpr int GF_W1 = GF_WQ + 3 * 16384;          // 3 x [ 32 x 128 B]
+constexpr int GF_AH = GF_W1 + 3 * 4096;           // 2 x [128 x 128 B]  bf16(h) / bf16(r*h)
+constexpr int GF_AX = GF_AH + 2 * 16384;          // 1 x [128 x 128 B]  bf16(x)
+constexpr int GF_PAR = GF_AX + 16384;             // fp32 parameters
+constexpr int GF_PAR_FLOATS = 384 + 32 + 96 + 3 + 192 + 64 + 5;  // bz|br|bq, b1, W2, b2, Woff, boff
+constexpr int GF_BAR = GF_PAR + ((GF_PAR_FLOATS * 4 + 15) / 16) * 16;
+constexpr int GF_SMEM = GF_BAR + 64 + 1024;
+
+struct GruFusedMaps { CUtensorMap wzr, wq, w1; };
+
+struct GruFusedParams {
+  const __nv_bfloat16* h0;  // [n_pad,128] bf16 gathered pillar vectors
+  const float* offs;    // [n,3]
+  const float* par;     // bz[128] br[128] bq[128] b1[32] W2[3*32] b2[3] Woff[64*3] boff[64]
+  int n, n_pad, iters;
+  __nv_bfloat16* hsave; // [iters+1][n_pad][128]: state entering iteration t, then the final state
+  __nv_bfloat16* xsave; // [n_pad][64]
+  __nv_bfloat16* y1;    // [n_pad][32] head pre-activation (bias included)
+  float* flow;          // [n,3]
+};
+
+__device__ __forceinline__ float fsigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float ftanh(float v) { return 2.0f * fsigmoid(2.0f * v) - 1.0f; }
+
+// store 8 consecutive channels (one 16-byte chunk) of row `row` into a [128 x 128 B] SWIZZLE_128B K-major tile
+__device__ __forceinline__ void st_tile_chunk(uint8_t* tile, int row, int chunk, const float* f) {
+  uint4 u;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = u;
+}
+
+__global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_constant__ GruFusedMaps maps,
+                                                                 const __grid_constant__ GruFusedParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* par = reinterpret_cast<float*>(smem + GF_PAR);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + GF_BAR);
+  uint64_t* bar_a = bar_w + 1;
+  uint64_t* bar_d = bar_w + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (P.n_pad + 127) / 128;
+
+  for (int i = threadIdx.x; i < GF_PAR_FLOATS - 5; i += blockDim.x) par[i] = P.par[i];
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.wzr); tma_prefetch_desc(&maps.wq); tma_prefetch_desc(&maps.w1);
+      mbar_init(bar_w, 1); mbar_init(bar_a, 8); mbar_init(bar_d, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float* bz = par; const float* br = par + 128; const float* bq = par + 256; const float* b1 = par + 384;
+  const float* w2 = par + 416; const float* b2 = par + 512; const float* woff = par + 515; const float* boff = par + 707;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ control: weights once, then MMA issue
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, 3 * 32768 + 3 * 16384 + 3 * 4096);
+      for (int c = 0; c < 3; ++c) {
+        tma_load_2d(smem + GF_WZR + c * 32768, &maps.wzr, bar_w, c * 64, 0);
+        tma_load_2d(smem + GF_WQ + c * 16384, &maps.wq, bar_w, c * 64, 0);
+        tma_load_2d(smem + GF_W1 + c * 4096, &maps.w1, bar_w, c * 64, 0);
+      }
+      mbar_wait(bar_w, 0);
+      uint32_t use_a = 0;
+      const uint32_t a_h = smem_u32(smem + GF_AH), a_x = smem_u32(smem + GF_AX);
+      auto gemm = [&](uint32_t w_base, uint32_t w_chunk_bytes, int N, uint32_t dcol) {
+        mbar_wait(bar_a, use_a & 1); ++use_a;
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint64_t ad = make_smem_desc(c < 2 ? a_h + c * 16384 : a_x, 16, 1024, 2);
+          const uint64_t bd = make_smem_desc(w_base + c * w_chunk_bytes, 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + dcol, ad + 2 * k, bd + 2 * k, idesc, (c | k) != 0);
+        }
+        umma_commit(bar_d);
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int it = 0; it < P.iters; ++it) {
+          gemm(smem_u32(smem + GF_WZR), 32768, 256, 0);    // z | r pre-activations -> columns 0..255
+          gemm(smem_u32(smem + GF_WQ), 16384, 128, 256);   // q pre-activation      -> columns 256..383
+        }
+        gemm(smem_u32(smem + GF_W1), 4096, 32, 384);       // MLP hidden layer      -> columns 384..415
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ workers
+    const int q = warp & 3, half = warp >> 2;
+    const int m = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* tile_h = smem + GF_AH + half * 16384;
+    uint8_t* tile_x = smem + GF_AX;
+    uint32_t use_d = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int p = tile * 128 + m;
+      const bool valid = p < P.n;
+      const bool inpad = p < P.n_pad;
+      // x = Woff o + boff: this thread's 32 of the 64 channels -> chunks half*4 .. half*4+3 of the X tile
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+      if (valid) { o0 = P.offs[3 * (size_t)p]; o1 = P.offs[3 * (size_t)p + 1]; o2 = P.offs[3 * (size_t)p + 2]; }
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ch = half * 32 + c8 * 8 + i;
+          f[i] = valid ? fmaf(o2, woff[3 * ch + 2], fmaf(o1, woff[3 * ch + 1], fmaf(o0, woff[3 * ch], boff[ch]))) : 0.f;
+        }
+        st_tile_chunk(tile_x, m, half * 4 + c8, f);
+        if (P.xsave && inpad) {
+          uint4 u;
+          __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pp[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+          *reinterpret_cast<uint4*>(P.xsave + (size_t)p * 64 + half * 32 + c8 * 8) = u;
+        }
+      }
+      float h[64];
+      if (valid) {
+        const uint4* src = reinterpret_cast<const uint4*>(P.h0 + (size_t)p * 128 + half * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 u = __ldg(src + i);
+          const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(pp[k]); h[8 * i + 2 * k] = t.x; h[8 * i + 2 * k + 1] = t.y; }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) h[i] = 0.f;
+      }
+      auto publish_h = [&](int slot) {  // bf16(h) -> A tile (+ the saved copy for the backward pass)
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          st_tile_chunk(tile_h, m, c8, &h[c8 * 8]);
+          if (P.hsave && inpad) {
+            uint4 u;
+            __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pp[i] = __floats2bfloat162_rn(h[c8 * 8 + 2 * i], h[c8 * 8 + 2 * i + 1]);
+            *reinterpret_cast<uint4*>(P.hsave + ((size_t)slot * P.n_pad + p) * 128 + half * 64 + c8 * 8) = u;
+          }
+        }
+      };
+      auto signal_a = [&]() {
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a);
+      };
+      auto wait_d = [&]() {
+        mbar_wait(bar_d, use_d & 1); ++use_d;
+        tc_fence_after();
+      };
+      for (int it = 0; it < P.iters; ++it) {
+        publish_h(it);
+        signal_a();
+        wait_d();
+        // r = sigmoid(r_pre + br); A tile <- bf16(r * h)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float v[32];
+          tmem_ld32(tmem + lane_base + 128 + half * 64 + cc * 32, v);
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = cc * 32 + c8 * 8 + i;
+              f[i] = fsigmoid(v[c8 * 8 + i] + br[half * 64 + j]) * h[j];
+            }
+            st_tile_chunk(tile_h, m, cc * 4 + c8, f);
+          }
+        }
+        signal_a();
+        wait_d();
+        // h = (1 - z) h + z tanh(q_pre + bq),  z = sigmoid(z_pre + bz)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float vz[32], vq[32];
+          tmem_ld32(tmem + lane_base + half * 64 + cc * 32, vz);
+          tmem_ld32(tmem + lane_base + 256 + half * 64 + cc * 32, vq);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = cc * 32 + i;
+            const float z = fsigmoid(vz[i] + bz[half * 64 + j]);
+            const float qq = ftanh(vq[i] + bq[half * 64 + j]);
+            h[j] = fmaf(z, qq - h[j], h[j]);
+          }
+        }
+      }
+      publish_h(P.iters);
+      signal_a();
+      wait_d();
+      if (half == 0) {  // 32 hidden units of the MLP head: this thread's row, all 32 columns
+        float v[32];
+        tmem_ld32(tmem + lane_base + 384, v);
+        float f0 = b2[0], f1 = b2[1], f2 = b2[2];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] += b1[i];
+          const float a = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+          f0 = fmaf(a, w2[i], f0); f1 = fmaf(a, w2[32 + i], f1); f2 = fmaf(a, w2[64 + i], f2);
+        }
+        if (P.y1 && inpad) {
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            uint4 u;
+            __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pp[i] = __floats2bfloat162_rn(valid ? v[c8 * 8 + 2 * i] : 0.f, valid ? v[c8 * 8 + 2 * i + 1] : 0.f);
+            *reinterpret_cast<uint4*>(P.y1 + (size_t)p * 32 + c8 * 8) = u;
+          }
+        }
+        if (valid) { P.flow[3 * (size_t)p] = f0; P.flow[3 * (size_t)p + 1] = f1; P.flow[3 * (size_t)p + 2] = f2; }
+      }
+      tc_fence_before();  // TMEM reads of this tile are complete before the next tile's first arrive
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+}  // namespace dfb
+
+using namespace dfb;
+using namespace dfb::tc;
+
+// wzr: bf16 [256][192] (Wz rows then Wr rows), wq: bf16 [128][192], w1: bf16 [32][192]; K order = [h(128), x(64)].
+extern "C" int dfb_gru_fused_forward(const void* h0, const float* offsets, const void* wzr, const void* wq,
+                                     const void* w1, const float* par, int n, int n_pad, int iters, void* hsave,
+                                     void* xsave, void* y1, float* flow, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n <= 0 || n_pad < n || iters < 0 || iters > 64) { set_error("dfb_gru_fused_forward: bad sizes"); return DFB_ERR_ARG; }
+  GruFusedMaps maps;
+  GruFusedParams P;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  const uint64_t str[1] = {192 * 2};
+  {
+    const uint64_t d[2] = {192, 256}; const uint32_t b[2] = {64, 256};
+    if ((rc = make_tensor_map_bf16(&maps.wzr, wzr, 2, d, str, b, 128))) return rc;
+  }
+  {
+    const uint64_t d[2] = {192, 128}; const uint32_t b[2] = {64, 128};
+    if ((rc = make_tensor_map_bf16(&maps.wq, wq, 2, d, str, b, 128))) return rc;
+  }
+  {
+    const uint64_t d[2] = {192, 32}; const uint32_t b[2] = {64, 32};
+    if ((rc = make_tensor_map_bf16(&maps.w1, w1, 2, d, str, b, 128))) return rc;
+  }
+  P.h0 = (const __nv_bfloat16*)h0; P.offs = offsets; P.par = par; P.n = n; P.n_pad = n_pad; P.iters = iters;
+  P.hsave = (__nv_bfloat16*)hsave; P.xsave = (__nv_bfloat16*)xsave; P.y1 = (__nv_bfloat16*)y1; P.flow = flow;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_gru_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    if (e != cudaSuccess) { set_error("gru_fused: cannot reserve %d bytes of shared memory: %s", GF_SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    configured = true;
+  }
+  const int tiles = (n_pad + 127) / 128;
+  int grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  k_gru_fused_fwd<<<grid, GF_THREADS, GF_SMEM, st>>>(maps, P);
+  add_launches(1);
+  return check_launch("dfb_gru_fused_forward");
+}
+
+// ================================================================================================
+// Fused backward of the GRU iterations.  Per tile of 128 points, for t = iters-1 .. 0:
+//   recompute  z, r = sigmoid([h_t, x] Wzr^T + b),  rh = r * h_t,  q = tanh([rh, x] Wq^T + bq)      (G1, G2)
+//   dq_pre = dh z (1 - q^2);  dz_pre = dh (q - h_t) z (1 - z);  dh <- dh (1 - z)
+//   d_rh = dq_pre Wq[:, :128];  d_x += dq_pre Wq[:, 128:] + dz_pre Wz[:, 128:]                      (G3)
+//   dr_pre = d_rh h_t r (1 - r);  dh += d_rh r
+//   dh += dz_pre Wz[:, :128] + dr_pre Wr[:, :128];  d_x += dr_pre Wr[:, 128:]                        (G3, G4)
+// The data-gradient GEMMs read the SAME resident weight tiles as the forward ones, through MN-major descriptors
+// (the transposed view).  dh lives in registers across iterations, d_x accumulates in TMEM across iterations.
+// rh, dq_pre, dzr_pre are written to HBM in bf16 for the weight-gradient GEMMs (dfb_conv2d_wgrad over the point list).
+namespace dfb {
+namespace tc {
+
+constexpr int GB_WZR = 0;
+constexpr int GB_WQ = GB_WZR + 3 * 32768;
+constexpr int GB_P = GB_WQ + 3 * 16384;      // 2 tiles: h_t -> r*h_t -> dq_pre -> dr_pre
+constexpr int GB_Q = GB_P + 2 * 16384;       // 2 tiles: dz_pre
+constexpr int GB_X = GB_Q + 2 * 16384;       // 1 tile
+constexpr int GB_PAR = GB_X + 16384;         // bz | br | bq
+constexpr int GB_BAR = GB_PAR + 384 * 4;
+constexpr int GB_SMEM = GB_BAR + 64 + 1008;
+
+struct GruBwdMaps { CUtensorMap wzr, wq; };
+
+struct GruBwdParams {
+  const __nv_bfloat16* hsave;   // [iters+1][n_pad][128]
+  const __nv_bfloat16* xsave;   // [n_pad][64]
+  const __nv_bfloat16* dh_in;   // [n_pad][128] gradient w.r.t. the final state (from the MLP head)
+  const __nv_bfloat16* dx_in;   // [n_pad][64]  gradient w.r.t. x from the MLP head
+  const float* par;             // bz | br | bq
+  int n, n_pad, iters;
+  __nv_bfloat16* rh;            // [iters][n_pad][128]
+  __nv_bfloat16* dq;            // [iters][n_pad][128]
+  __nv_bfloat16* dzr;           // [iters][n_pad][256]
+  __nv_bfloat16* dh0;           // [n_pad][128]  gradient w.r.t. the gathered pillar vectors
+  float* dx;                    // [n_pad][64]   gradient w.r.t. x (all iterations + head)
+};
+
+__device__ __forceinline__ void ld_bf16x8(const __nv_bfloat16* p, float* f) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(pp[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const float* f) {
+  uint4 u;
+  __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pp[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_constant__ GruBwdMaps maps,
+                                                                 const __grid_constant__ GruBwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* par = reinterpret_cast<float*>(smem + GB_PAR);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + GB_BAR);
+  uint64_t* bar_a = bar_w + 1;
+  uint64_t* bar_d = bar_w + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (P.n_pad + 127) / 128;
+
+  for (int i = threadIdx.x; i < 384; i += blockDim.x) par[i] = P.par[i];
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.wzr); tma_prefetch_desc(&maps.wq);
+      mbar_init(bar_w, 1); mbar_init(bar_a, 8); mbar_init(bar_d, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float* bz = par; const float* br = par + 128; const float* bq = par + 256;
+  // TMEM columns: [0,256) z|r pre-activations, later [0,128) = d_h; [256,384) q pre-activation, later d_rh;
+  // [448,512) d_x accumulator
+  constexpr uint32_t C_ZR = 0, C_Q = 256, C_DX = 448;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, 3 * 32768 + 3 * 16384);
+      for (int c = 0; c < 3; ++c) {
+        tma_load_2d(smem + GB_WZR + c * 32768, &maps.wzr, bar_w, c * 64, 0);
+        tma_load_2d(smem + GB_WQ + c * 16384, &maps.wq, bar_w, c * 64, 0);
+      }
+      mbar_wait(bar_w, 0);
+      uint32_t use_a = 0;
+      const uint32_t t_p = smem_u32(smem + GB_P), t_q = smem_u32(smem + GB_Q), t_x = smem_u32(smem + GB_X);
+      const uint32_t wzr = smem_u32(smem + GB_WZR), wq = smem_u32(smem + GB_WQ);
+      auto wait_a = [&]() { mbar_wait(bar_a, use_a & 1); ++use_a; tc_fence_after(); };
+      // forward-style GEMM: D[128, N] = [A_p | X] (K = 192, K-major) x W^T (K-major tiles)
+      auto gemm_fwd = [&](uint32_t w_base, uint32_t w_chunk, int N, uint32_t dcol) {
+        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint64_t ad = make_smem_desc(c < 2 ? t_p + c * 16384 : t_x, 16, 1024, 2);
+          const uint64_t bd = make_smem_desc(w_base + c * w_chunk, 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + dcol, ad + 2 * k, bd + 2 * k, idesc, (c | k) != 0);
+        }
+      };
+      // data-gradient GEMM: D[128, N'] (+)= G[128, 128] (A tile pair, K-major) x W[rows row0..row0+127][cols of chunk
+      // c0 .. c0 + N'/64 - 1], the weight tiles read MN-major (transposed view): K' = weight rows, N' = weight columns.
+      auto gemm_dgrad = [&](uint32_t a_tile, uint32_t w_base, uint32_t w_chunk, int row0, int c0, int N, uint32_t dcol,
+                            bool accumulate) {
+        const uint32_t idesc = make_idesc_bf16(128, N, 0, 1);
+        const uint32_t b0 = w_base + c0 * w_chunk + row0 * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint64_t ad = make_smem_desc(a_tile + (i >> 2) * 16384, 16, 1024, 2) + 2 * (i & 3);
+          const uint64_t bd = make_smem_desc(b0 + i * 2048, w_chunk, 1024, 2);
+          umma_bf16(tmem + dcol, ad, bd, idesc, accumulate || i != 0);
+        }
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int it = P.iters - 1; it >= 0; --it) {
+          const bool first = it == P.iters - 1;
+          wait_a();  // P = h_t, X
+          gemm_fwd(wzr, 32768, 256, C_ZR);
+          umma_commit(bar_d);
+          wait_a();  // P = r * h_t
+          gemm_fwd(wq, 16384, 128, C_Q);
+          umma_commit(bar_d);
+          wait_a();  // P = dq_pre, Q = dz_pre
+          gemm_dgrad(t_p, wq, 16384, 0, 0, 128, C_Q, false);        // d_rh  = dq Wq[:, 0:128]
+          gemm_dgrad(t_p, wq, 16384, 0, 2, 64, C_DX, !first);       // d_x  += dq Wq[:, 128:192]
+          gemm_dgrad(t_q, wzr, 32768, 0, 0, 128, C_ZR, false);      // d_h   = dz Wz[:, 0:128]
+          gemm_dgrad(t_q, wzr, 32768, 0, 2, 64, C_DX, true);        // d_x  += dz Wz[:, 128:192]
+          umma_commit(bar_d);
+          wait_a();  // P = dr_pre
+          gemm_dgrad(t_p, wzr, 32768, 128, 0, 128, C_ZR, true);     // d_h  += dr Wr[:, 0:128]
+          gemm_dgrad(t_p, wzr, 32768, 128, 2, 64, C_DX, true);      // d_x  += dr Wr[:, 128:192]
+          umma_commit(bar_d);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, half = warp >> 2;
+    const int m = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* tile_p = smem + GB_P + half * 16384;
+    uint8_t* tile_q = smem + GB_Q + half * 16384;
+    uint8_t* tile_x = smem + GB_X;
+    uint32_t use_d = 0;
+    auto signal_a = [&]() {
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a);
+    };
+    auto wait_d = [&]() { mbar_wait(bar_d, use_d & 1); ++use_d; tc_fence_after(); };
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int p = tile * 128 + m;
+      const bool valid = p < P.n;
+      const bool inpad = p < P.n_pad;
+      const size_t prow = inpad ? (size_t)p : 0;
+      // X tile (this thread's 32 channels)
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float f[8];
+        if (inpad) ld_bf16x8(P.xsave + prow * 64 + half * 32 + c8 * 8, f);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = 0.f;
+        }
+        st_tile_chunk(tile_x, m, half * 4 + c8, f);
+      }
+      float dh[64];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        if (valid) ld_bf16x8(P.dh_in + prow * 128 + half * 64 + c8 * 8, &dh[c8 * 8]);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dh[c8 * 8 + i] = 0.f;
+        }
+      }
+      for (int it = P.iters - 1; it >= 0; --it) {
+        const __nv_bfloat16* hrow = P.hsave + ((size_t)it * P.n_pad + prow) * 128 + half * 64;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {  // h_t is re-read (L2) where needed instead of living in 64 registers
+          uint4 u = make_uint4(0u, 0u, 0u, 0u);
+          if (inpad) u = __ldg(reinterpret_cast<const uint4*>(hrow + c8 * 8));
+          *reinterpret_cast<uint4*>(tile_p + m * 128 + ((c8 ^ (m & 7)) << 4)) = u;
+        }
+        signal_a();
+        wait_d();  // z | r pre-activations
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float v[32];
+          tmem_ld32(tmem + lane_base + C_ZR + 128 + half * 64 + cc * 32, v);
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            float f[8], hh[8];
+            ld_bf16x8(hrow + cc * 32 + c8 * 8, hh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = cc * 32 + c8 * 8 + i;
+              f[i] = valid ? fsigmoid(v[c8 * 8 + i] + br[half * 64 + j]) * hh[i] : 0.f;
+            }
+            st_tile_chunk(tile_p, m, cc * 4 + c8, f);
+            if (inpad) st_bf16x8(P.rh + ((size_t)it * P.n_pad + prow) * 128 + half * 64 + cc * 32 + c8 * 8, f);
+          }
+        }
+        signal_a();
+        wait_d();  // q pre-activation
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          float vz[16], vq[16];
+          tmem_ld16(tmem + lane_base + C_ZR + half * 64 + cc * 16, vz);
+          tmem_ld16(tmem + lane_base + C_Q + half * 64 + cc * 16, vq);
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8) {
+            float fq[8], fz[8], hh[8];
+            ld_bf16x8(hrow + cc * 16 + c8 * 8, hh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = cc * 16 + c8 * 8 + i;
+              const float z = fsigmoid(vz[c8 * 8 + i] + bz[half * 64 + j]);
+              const float qq = ftanh(vq[c8 * 8 + i] + bq[half * 64 + j]);
+              const float g = dh[j];
+              fq[i] = g * z * (1.0f - qq * qq);
+              fz[i] = g * (qq - hh[i]) * z * (1.0f - z);
+              dh[j] = g * (1.0f - z);
+            }
+            st_tile_chunk(tile_p, m, cc * 2 + c8, fq);
+            st_tile_chunk(tile_q, m, cc * 2 + c8, fz);
+            if (inpad) {
+              st_bf16x8(P.dq + ((size_t)it * P.n_pad + prow) * 128 + half * 64 + cc * 16 + c8 * 8, fq);
+              st_bf16x8(P.dzr + ((size_t)it * P.n_pad + prow) * 256 + half * 64 + cc * 16 + c8 * 8, fz);
+            }
+          }
+        }
+        signal_a();
+        wait_d();  // d_rh in C_Q, partial d_h in C_ZR[0,128); r pre-activation still in C_ZR[128,256)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          float vr[16], vg[16];
+          tmem_ld16(tmem + lane_base + C_ZR + 128 + half * 64 + cc * 16, vr);
+          tmem_ld16(tmem + lane_base + C_Q + half * 64 + cc * 16, vg);
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8) {
+            float f[8], hh[8];
+            ld_bf16x8(hrow + cc * 16 + c8 * 8, hh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = cc * 16 + c8 * 8 + i;
+              const float r = fsigmoid(vr[c8 * 8 + i] + br[half * 64 + j]);
+              const float g = valid ? vg[c8 * 8 + i] : 0.f;
+              f[i] = g * hh[i] * r * (1.0f - r);
+              dh[j] = fmaf(g, r, dh[j]);
+            }
+            st_tile_chunk(tile_p, m, cc * 2 + c8, f);
+            if (inpad) st_bf16x8(P.dzr + ((size_t)it * P.n_pad + prow) * 256 + 128 + half * 64 + cc * 16 + c8 * 8, f);
+          }
+        }
+        signal_a();
+        wait_d();  // d_h complete in C_ZR[0,128)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float v[32];
+          tmem_ld32(tmem + lane_base + C_ZR + half * 64 + cc * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dh[cc * 32 + i] += valid ? v[i] : 0.f;
+        }
+      }
+      // outputs of the tile: dh0 (bf16) and d_x = TMEM accumulator + the head's contribution
+      if (inpad) {
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) st_bf16x8(P.dh0 + prow * 128 + half * 64 + c8 * 8, &dh[c8 * 8]);
+      }
+      {
+        float v[32];
+        if (P.iters > 0) tmem_ld32(tmem + lane_base + C_DX + half * 32, v);
+        else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (inpad) {
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            float f[8];
+            ld_bf16x8(P.dx_in + prow * 64 + half * 32 + c8 * 8, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = valid ? f[i] + v[c8 * 8 + i] : 0.f;
+            float4* dst = reinterpret_cast<float4*>(P.dx + prow * 64 + half * 32 + c8 * 8);
+            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+}  // namespace dfb
+
+extern "C" int dfb_gru_fused_backward(const void* hsave, const void* xsave, const void* dh_in, const void* dx_in,
+                                      const void* wzr, const void* wq, const float* par, int n, int n_pad, int iters,
+                                      void* rh, void* dq, void* dzr, void* dh0, float* dx, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n <= 0 || n_pad < n || iters < 0 || iters > 64) { set_error("dfb_gru_fused_backward: bad sizes"); return DFB_ERR_ARG; }
+  GruBwdMaps maps;
+  GruBwdParams P;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  const uint64_t str[1] = {192 * 2};
+  {
+    const uint64_t d[2] = {192, 256}; const uint32_t b[2] = {64, 256};
+    if ((rc = make_tensor_map_bf16(&maps.wzr, wzr, 2, d, str, b, 128))) return rc;
+  }
+  {
+    const uint64_t d[2] = {192, 128}; const uint32_t b[2] = {64, 128};
+    if ((rc = make_tensor_map_bf16(&maps.wq, wq, 2, d, str, b, 128))) return rc;
+  }
+  P.hsave = (const __nv_bfloat16*)hsave; P.xsave = (const __nv_bfloat16*)xsave;
+  P.dh_in = (const __nv_bfloat16*)dh_in; P.dx_in = (const __nv_bfloat16*)dx_in; P.par = par;
+  P.n = n; P.n_pad = n_pad; P.iters = iters;
+  P.rh = (__nv_bfloat16*)rh; P.dq = (__nv_bfloat16*)dq; P.dzr = (__nv_bfloat16*)dzr; P.dh0 = (__nv_bfloat16*)dh0; P.dx = dx;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_gru_fused_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
+    if (e != cudaSuccess) { set_error("gru_fused_bwd: cannot reserve %d bytes of shared memory: %s", GB_SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    configured = true;
+  }
+  const int tiles = (n_pad + 127) / 128;
+  int grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  k_gru_fused_bwd<<<grid, GF_THREADS, GB_SMEM, st>>>(maps, P);
+  add_launches(1);
+  return check_launch("dfb_gru_fused_backward");
+}

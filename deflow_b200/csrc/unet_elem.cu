@@ -25,10 +25,21 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
-__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_f(float z) {
-  return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+// Exact-erf GELU and its derivative share one exponential: with u = |z|/sqrt(2), erf(u) = 1 - P(t) exp(-u^2),
+// t = 1/(1 + p u) (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 -- far below bf16 resolution), and the Gaussian
+// density of the derivative is the same exp(-z^2/2).  ~20 instructions instead of erff + expf (~60): these passes are
+// otherwise instruction-bound, not HBM-bound.
+__device__ __forceinline__ void gelu_parts(float z, float& cdf, float& pdf) {
+  const float u = fabsf(z) * 0.70710678118654752f;
+  const float e = __expf(-u * u);                       // exp(-z^2 / 2)
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, u, 1.0f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, z));
+  pdf = 0.3989422804014327f * e;
 }
+__device__ __forceinline__ float gelu_f(float z) { float c, p; gelu_parts(z, c, p); return z * c; }
+__device__ __forceinline__ float gelu_grad_f(float z) { float c, p; gelu_parts(z, c, p); return fmaf(z, p, c); }
 
 // ---------------------------------------------------------------- BatchNorm2d parameters from batch statistics
 // stats [2][C] (double): sum, sum of squares over count elements per channel.  bn [4][C]: a = gamma*rstd,
@@ -63,52 +74,76 @@ __global__ void k_bn2d_finalize(const double* __restrict__ stats, double count, 
   bn[3 * C + c] = rstd;
 }
 
-// y = GELU(a*x + b), 8 channels per thread
+// In all three passes a thread keeps ONE channel octet for its whole grid-stride loop (the stride is a multiple of
+// the vectors-per-pixel count), so the BatchNorm parameters of its 8 channels live in registers.
+
+// y = GELU(a*x + b), 8 channels per thread, two 16-byte vectors in flight
 __global__ void __launch_bounds__(256) k_bn_gelu_apply(const uint4* __restrict__ x, const float* __restrict__ bn, int C,
                                                        long long n_vec, uint4* __restrict__ y) {
-  __shared__ float sa[256], sb[256];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { sa[i] = bn[i]; sb[i] = bn[C + i]; }
-  __syncthreads();
-  const int vec_per_pix = C >> 3;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_vec; e += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(e % vec_per_pix) << 3;
-    float f[8];
-    unpack8(__ldg(x + e), f);
+  const int vpp = C >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(e0 % vpp) << 3;
+  float a[8], b[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = gelu_f(fmaf(f[i], sa[c0 + i], sb[c0 + i]));
+  for (int i = 0; i < 8; ++i) { a[i] = __ldg(bn + c0 + i); b[i] = __ldg(bn + C + c0 + i); }
+  for (long long e = e0; e < n_vec; e += 2 * stride) {
+    const long long e2 = e + stride;
+    const bool two = e2 < n_vec;
+    const uint4 u0 = __ldg(x + e);
+    const uint4 u1 = two ? __ldg(x + e2) : u0;
+    float f[8];
+    unpack8(u0, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = gelu_f(fmaf(f[i], a[i], b[i]));
     y[e] = pack8(f);
+    if (two) {
+      unpack8(u1, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = gelu_f(fmaf(f[i], a[i], b[i]));
+      y[e2] = pack8(f);
+    }
   }
 }
 
 // Backward pass 1: red[0][c] = sum g1, red[1][c] = sum g1 * xhat, with g1 = gy * GELU'(a*x + b)
 __global__ void __launch_bounds__(256) k_bn_gelu_bwd_reduce(const uint4* __restrict__ x, const uint4* __restrict__ gy,
-                                                            const float* __restrict__ bn, int C, long long n_pix,
+                                                            const float* __restrict__ bn, int C, long long n_vec,
                                                             double* __restrict__ red) {
-  __shared__ float sa[256], sb[256], sm[256], sr[256];
   __shared__ float acc1[256], acc2[256];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    sa[i] = bn[i]; sb[i] = bn[C + i]; sm[i] = bn[2 * C + i]; sr[i] = bn[3 * C + i];
-    acc1[i] = 0.f; acc2[i] = 0.f;
-  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { acc1[i] = 0.f; acc2[i] = 0.f; }
   __syncthreads();
-  const int vpp = C >> 3;                       // vectors per pixel (8, 16 or 32)
-  const int oct = threadIdx.x % vpp;            // fixed channel octet of this thread
-  const int prow = threadIdx.x / vpp, prows = blockDim.x / vpp;
-  const int c0 = oct << 3;
-  float s1[8], s2[8];
+  const int vpp = C >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(e0 % vpp) << 3;
+  float a[8], b[8], mu[8], rs[8], s1[8], s2[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-  for (long long p = (long long)blockIdx.x * prows + prow; p < n_pix; p += (long long)gridDim.x * prows) {
+  for (int i = 0; i < 8; ++i) {
+    a[i] = __ldg(bn + c0 + i); b[i] = __ldg(bn + C + c0 + i); mu[i] = __ldg(bn + 2 * C + c0 + i); rs[i] = __ldg(bn + 3 * C + c0 + i);
+    s1[i] = 0.f; s2[i] = 0.f;
+  }
+  for (long long e = e0; e < n_vec; e += 2 * stride) {
+    const long long e2 = e + stride;
+    const bool two = e2 < n_vec;
+    const uint4 ux0 = __ldg(x + e), ug0 = __ldg(gy + e);
+    const uint4 ux1 = two ? __ldg(x + e2) : ux0, ug1 = two ? __ldg(gy + e2) : ug0;
     float fx[8], fg[8];
-    unpack8(__ldg(x + p * vpp + oct), fx);
-    unpack8(__ldg(gy + p * vpp + oct), fg);
+    unpack8(ux0, fx); unpack8(ug0, fg);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float z = fmaf(fx[i], sa[c0 + i], sb[c0 + i]);
-      const float g1 = fg[i] * gelu_grad_f(z);
-      const float xh = (fx[i] - sm[c0 + i]) * sr[c0 + i];
+      const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], a[i], b[i]));
       s1[i] += g1;
-      s2[i] = fmaf(g1, xh, s2[i]);
+      s2[i] = fmaf(g1, (fx[i] - mu[i]) * rs[i], s2[i]);
+    }
+    if (two) {
+      unpack8(ux1, fx); unpack8(ug1, fg);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], a[i], b[i]));
+        s1[i] += g1;
+        s2[i] = fmaf(g1, (fx[i] - mu[i]) * rs[i], s2[i]);
+      }
     }
   }
 #pragma unroll
@@ -125,27 +160,39 @@ __global__ void __launch_bounds__(256) k_bn_gelu_bwd_apply(const uint4* __restri
                                                            const float* __restrict__ bn, const double* __restrict__ red,
                                                            double count, int training, int C, long long n_vec,
                                                            uint4* __restrict__ gx) {
-  __shared__ float sa[256], sb[256], sm[256], sr[256], m1[256], m2[256];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    sa[i] = bn[i]; sb[i] = bn[C + i]; sm[i] = bn[2 * C + i]; sr[i] = bn[3 * C + i];
-    m1[i] = training ? (float)(red[i] / count) : 0.f;
-    m2[i] = training ? (float)(red[C + i] / count) : 0.f;
-  }
-  __syncthreads();
   const int vpp = C >> 3;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_vec; e += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(e % vpp) << 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(e0 % vpp) << 3;
+  float a[8], b[8], mu[8], rs[8], m1[8], m2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = __ldg(bn + c0 + i); b[i] = __ldg(bn + C + c0 + i); mu[i] = __ldg(bn + 2 * C + c0 + i); rs[i] = __ldg(bn + 3 * C + c0 + i);
+    m1[i] = training ? (float)(red[c0 + i] / count) : 0.f;
+    m2[i] = training ? (float)(red[C + c0 + i] / count) : 0.f;
+  }
+  for (long long e = e0; e < n_vec; e += 2 * stride) {
+    const long long e2 = e + stride;
+    const bool two = e2 < n_vec;
+    const uint4 ux0 = __ldg(x + e), ug0 = __ldg(gy + e);
+    const uint4 ux1 = two ? __ldg(x + e2) : ux0, ug1 = two ? __ldg(gy + e2) : ug0;
     float fx[8], fg[8];
-    unpack8(__ldg(x + e), fx);
-    unpack8(__ldg(gy + e), fg);
+    unpack8(ux0, fx); unpack8(ug0, fg);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float z = fmaf(fx[i], sa[c0 + i], sb[c0 + i]);
-      const float g1 = fg[i] * gelu_grad_f(z);
-      const float xh = (fx[i] - sm[c0 + i]) * sr[c0 + i];
-      fx[i] = sa[c0 + i] * (g1 - m1[c0 + i] - xh * m2[c0 + i]);
+      const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], a[i], b[i]));
+      fx[i] = a[i] * (g1 - m1[i] - (fx[i] - mu[i]) * rs[i] * m2[i]);
     }
     gx[e] = pack8(fx);
+    if (two) {
+      unpack8(ux1, fx); unpack8(ug1, fg);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], a[i], b[i]));
+        fx[i] = a[i] * (g1 - m1[i] - (fx[i] - mu[i]) * rs[i] * m2[i]);
+      }
+      gx[e2] = pack8(fx);
+    }
   }
 }
 
@@ -276,7 +323,7 @@ extern "C" int dfb_bn2d_finalize(const double* stats, double count, int C, int t
 extern "C" int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, void* stream_) {
   if (C % 8 || C > 256) { set_error("dfb_bn_gelu_apply: C must be a multiple of 8 and <= 256"); return DFB_ERR_ARG; }
   const long long n_vec = n_pix * (C >> 3);
-  k_bn_gelu_apply<<<grid_for_elems(n_vec, 256), 256, 0, (cudaStream_t)stream_>>>((const uint4*)x, bn, C, n_vec, (uint4*)y);
+  k_bn_gelu_apply<<<grid_for_elems(n_vec, 512), 256, 0, (cudaStream_t)stream_>>>((const uint4*)x, bn, C, n_vec, (uint4*)y);
   add_launches(1);
   return check_launch("dfb_bn_gelu_apply");
 }
@@ -286,10 +333,9 @@ extern "C" int dfb_bn_gelu_backward(const void* x, const void* gy, const float* 
   cudaStream_t st = (cudaStream_t)stream_;
   if (C % 8 || C > 256 || 256 % (C >> 3)) { set_error("dfb_bn_gelu_backward: unsupported channel count %d", C); return DFB_ERR_ARG; }
   cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st);
-  const int prows = 256 / (C >> 3);
-  k_bn_gelu_bwd_reduce<<<grid_for_elems(n_pix, prows, 8), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, C, n_pix, red);
   const long long n_vec = n_pix * (C >> 3);
-  k_bn_gelu_bwd_apply<<<grid_for_elems(n_vec, 256), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, red, (double)n_pix,
+  k_bn_gelu_bwd_reduce<<<grid_for_elems(n_vec, 512, 8), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, C, n_vec, red);
+  k_bn_gelu_bwd_apply<<<grid_for_elems(n_vec, 512), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, red, (double)n_pix,
                                                                   training, C, n_vec, (uint4*)gx);
   k_bn_param_grads<<<(C + 127) / 128, 128, 0, st>>>(red, bn, C, training, g_gamma, g_beta, g_bias);
   add_launches(3);

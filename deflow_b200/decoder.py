@@ -7,6 +7,7 @@ NCHW columns (decoder.py:215-225, 239-253).
 """
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
@@ -46,6 +47,10 @@ class _GatherDecoder(nn.Module):
         """bf16 perf mode: gather -> (GRU iterations) -> MLP head on the tensor cores (deflow_b200/gru.py)."""
         from . import gru
         n_pad = max((n_rows + 7) // 8 * 8, 8)
+        if iters > 0 and os.environ.get("DFB_GRU", "fused") == "fused":
+            # persistent fused kernels (csrc/gru_fused.cu); DFB_GRU=unfused selects the GEMM + elementwise launches
+            h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.bfloat16, n_pad)
+            return gru.decode_fused(h0, offsets, n_rows, self)
         h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.float32, n_pad)
         return gru.decode(h0, offsets, n_rows, self, iters)
 

@@ -146,3 +146,84 @@ def decode(h0, offsets, n, head, iters):
         args = (None,) * 6
     return _Decoder.apply(h0, offsets, n, iters, head.offset_encoder.weight, head.offset_encoder.bias, *args,
                           head.decoder[0].weight, head.decoder[0].bias, head.decoder[2].weight, head.decoder[2].bias)
+
+
+class _FusedGRUDecoder(torch.autograd.Function):
+    """ConvGRUDecoder on the persistent fused kernels (csrc/gru_fused.cu): h0 bf16 [n_pad,128], offsets [n,3] -> flow."""
+
+    @staticmethod
+    def forward(ctx, h0, offsets, n, iters, w_off, b_off, wz, bz, wr, br, wq, bq, w1, b1, w2, b2):
+        lib = _lib.lib()
+        dev = h0.device
+        n_pad = h0.shape[0]
+        st = _stream(h0)
+        assert h0.dtype == BF and h0.is_contiguous() and w_off.shape[0] == 64 and iters > 0
+        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        wzr_b = torch.cat([f32(wz)[:, :, 0], f32(wr)[:, :, 0]], 0).to(BF).contiguous()       # [256,192]
+        wq_b = f32(wq)[:, :, 0].to(BF).contiguous()                                           # [128,192]
+        w1f = f32(w1)
+        w1_b = w1f.to(BF).contiguous()                                                        # [32,192]
+        w2f = f32(w2)
+        par = torch.cat([f32(bz), f32(br), f32(bq), f32(b1), w2f.reshape(-1), f32(b2), f32(w_off).reshape(-1), f32(b_off)])
+        offsets = offsets.contiguous()
+        train = any(ctx.needs_input_grad)  # (grad mode is off inside Function.forward; inference passes no-grad inputs)
+        hsave = torch.empty((iters + 1, n_pad, 128), dtype=BF, device=dev) if train else None
+        xsave = torch.empty((n_pad, 64), dtype=BF, device=dev) if train else None
+        y1 = torch.empty((n_pad, 32), dtype=BF, device=dev) if train else None
+        flow = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        check(lib.dfb_gru_fused_forward(h0.data_ptr(), offsets.data_ptr(), wzr_b.data_ptr(), wq_b.data_ptr(),
+                                        w1_b.data_ptr(), par.data_ptr(), n, n_pad, iters, P(hsave), P(xsave), P(y1),
+                                        flow.data_ptr(), st), "gru_fused_forward")
+        ctx.saved = (hsave, xsave, y1, offsets, wzr_b, wq_b, w1f, w2f, par)
+        ctx.meta = (n, n_pad, iters)
+        return flow
+
+    @staticmethod
+    def backward(ctx, dflow):
+        lib = _lib.lib()
+        hsave, xsave, y1, offsets, wzr_b, wq_b, w1f, w2f, par = ctx.saved
+        n, n_pad, iters = ctx.meta
+        dev = dflow.device
+        st = _stream(dflow)
+        dflow = dflow.contiguous().float()
+        z32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+        # MLP head
+        dy1 = torch.empty((n_pad, 32), dtype=BF, device=dev)
+        gw2, gb2 = z32(3, 32), z32(3)
+        check(lib.dfb_head_out_backward(y1.data_ptr(), w2f.data_ptr(), dflow.data_ptr(), n, n_pad, dy1.data_ptr(),
+                                        gw2.data_ptr(), gb2.data_ptr(), st), "head_out_backward")
+        w14 = w1f.reshape(32, 192, 1, 1)
+        gw1 = _wgrad([hsave[iters], xsave], dy1)
+        gb1 = tc.channel_sum(dy1)
+        d_h = _dgrad(dy1, w14, 0, 128)
+        d_x = _dgrad(dy1, w14, 128, 192)
+        # GRU iterations
+        rh = torch.empty((iters, n_pad, 128), dtype=BF, device=dev)
+        dq = torch.empty((iters, n_pad, 128), dtype=BF, device=dev)
+        dzr = torch.empty((iters, n_pad, 256), dtype=BF, device=dev)
+        dh0 = torch.empty((n_pad, 128), dtype=BF, device=dev)
+        dx = torch.empty((n_pad, 64), dtype=torch.float32, device=dev)
+        check(lib.dfb_gru_fused_backward(hsave.data_ptr(), xsave.data_ptr(), d_h.data_ptr(), d_x.data_ptr(),
+                                         wzr_b.data_ptr(), wq_b.data_ptr(), par.data_ptr(), n, n_pad, iters,
+                                         rh.data_ptr(), dq.data_ptr(), dzr.data_ptr(), dh0.data_ptr(), dx.data_ptr(), st),
+              "gru_fused_backward")
+        gwq = gwzr = None
+        for t in range(iters):
+            gwq = _wgrad([rh[t], xsave], dq[t], gwq)
+            gwzr = _wgrad([hsave[t], xsave], dzr[t], gwzr)
+        gbq = tc.channel_sum(dq.view(-1, 128))
+        gbzr = tc.channel_sum(dzr.view(-1, 256))
+        gw_off, gb_off = z32(64, 3), z32(64)
+        check(lib.dfb_offset_encode_backward(dx.data_ptr(), offsets.data_ptr(), n, 64, gw_off.data_ptr(),
+                                             gb_off.data_ptr(), st), "offset_encode_backward")
+        return (dh0, None, None, None, gw_off, gb_off, gwzr[:128, :, 0], gbzr[:128], gwzr[128:, :, 0], gbzr[128:],
+                gwq[:, :, 0], gbq, gw1[:, :, 0, 0], gb1, gw2, gb2)
+
+
+def decode_fused(h0_bf16, offsets, n, head):
+    g = head.gru
+    return _FusedGRUDecoder.apply(h0_bf16, offsets, n, head.num_iters, head.offset_encoder.weight,
+                                  head.offset_encoder.bias, g.convz.weight, g.convz.bias, g.convr.weight, g.convr.bias,
+                                  g.convq.weight, g.convq.bias, head.decoder[0].weight, head.decoder[0].bias,
+                                  head.decoder[2].weight, head.decoder[2].bias)

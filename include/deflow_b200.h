@@ -260,6 +260,23 @@ int dfb_head_out(const void* y1, const float* w2, const float* b2, int n, float*
 int dfb_head_out_backward(const void* y1, const float* w2, const float* dflow, int n, int n_pad, void* dy1, float* gw2,
                           float* gb2, void* stream);
 
+/* ------------------------------------------------------------------ fused persistent GRU decoder (tensor cores)
+ * ConvGRUDecoder.forward_single for all points at once (REF/src/models/basic/decoder.py:210-237, 184-193): offset
+ * encoder, `iters` GRU iterations and the MLP head in ONE kernel; gate weights resident in shared memory, hidden state
+ * in registers, gate GEMMs on tcgen05.  wzr bf16 [256][192] (Wz rows, then Wr rows), wq bf16 [128][192], w1 bf16
+ * [32][192], K order [h(128), x(64)].  par (fp32): bz[128] br[128] bq[128] b1[32] W2[3*32] b2[3] Woff[64*3] boff[64].
+ * h0 bf16 [n_pad,128].  Saved for the backward pass (may be NULL for inference): hsave bf16 [iters+1][n_pad][128]
+ * (state entering every iteration, then the final state), xsave bf16 [n_pad][64], y1 bf16 [n_pad][32].
+ * dfb_gru_fused_backward: gradient of the `iters` iterations given dh_in / dx_in (bf16, from the head); writes rh, dq
+ * [iters][n_pad][128] and dzr [iters][n_pad][256] (bf16 operands of the weight-gradient GEMMs), dh0 bf16 [n_pad][128]
+ * and dx fp32 [n_pad][64]; par = bz | br | bq. */
+int dfb_gru_fused_forward(const void* h0, const float* offsets, const void* wzr, const void* wq, const void* w1,
+                          const float* par, int n, int n_pad, int iters, void* hsave, void* xsave, void* y1,
+                          float* flow, void* stream);
+int dfb_gru_fused_backward(const void* hsave, const void* xsave, const void* dh_in, const void* dx_in, const void* wzr,
+                           const void* wq, const float* par, int n, int n_pad, int iters, void* rh, void* dq, void* dzr,
+                           void* dh0, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
