@@ -43,7 +43,7 @@ class PfnArgs(C.Structure):
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
                 ("running_var", C.c_void_p), ("pil_mean", C.c_void_p), ("stats", C.c_void_p),
                 ("bn_params", C.c_void_p), ("pil_feats", C.c_void_p), ("image", C.c_void_p),
-                ("image_bf16", C.c_int)]
+                ("image_bf16", C.c_int), ("pil_cap", C.c_longlong)]
 
 
 class PfnBwdArgs(C.Structure):

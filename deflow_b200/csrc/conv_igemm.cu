@@ -77,6 +77,12 @@ struct IgemmParams {
   int sy, sx, oy, ox;
   const float* bias;   // [N] or null
   double* stats;       // [2][N] running sum / sum of squares over all output elements, or null
+  // halo variant (3x3 stride 1): steps[] holds one entry per 64-channel chunk (wk = K offset of tap 0)
+  int halo_pitch;      // pixels per halo row in shared memory (10 or 16)
+  int halo_flip;       // data gradient: tap t reads halo offset (2 - t/3, 2 - t%3)
+  int tap_k_stride;    // K distance between consecutive taps in the packed weights
+  int w_resident;      // all 9 * nsteps weight tiles fit the ring: load them once
+  int dbg_base_offset; // descriptor base-offset field = (start >> 7) & 7 (experiment switch)
   KStep steps[MAX_STEPS];
 };
 
@@ -92,6 +98,70 @@ __device__ __forceinline__ void colsum_butterfly(float (&v)[32], int lane) {
       const float keep = up ? v[i + s] : v[i];
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
     }
+  }
+}
+
+// Epilogue shared by the implicit-GEMM kernels: 4 warps = 128 TMEM lanes = the 16 x 8 pixels of a tile.
+template <int N>
+__device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, uint32_t tmem_base, uint64_t* acc_full,
+                                               uint64_t* acc_empty, float* s_stats, int warp, int lane) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+  const int m = q * 32 + lane;
+  const int r = m >> 3, c = m & 7;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+    const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
+    const int y = ty * TILE_H + r, x = tx * TILE_W + c;
+    const bool valid = y < P.Ht && x < P.Wt;
+    const long long off = (long long)n * P.out_img + (long long)(y * P.sy + P.oy) * P.out_row +
+                          (long long)(x * P.sx + P.ox) * P.out_pix;
+    mbar_wait(&acc_full[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int col = 0; col < N; col += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + col, v);
+      if (P.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + col + i);
+      }
+      if (valid) {
+        if (P.out_fp32) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<unsigned*>(&p0); u.y = *reinterpret_cast<unsigned*>(&p1);
+            u.z = *reinterpret_cast<unsigned*>(&p2); u.w = *reinterpret_cast<unsigned*>(&p3);
+            dst[i] = u;
+          }
+        }
+      }
+      if (P.stats) {
+        float sq[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (!valid) v[i] = 0.f;
+          sq[i] = v[i] * v[i];
+        }
+        colsum_butterfly<N>(v, lane);
+        colsum_butterfly<N>(sq, lane);
+        atomicAdd(&s_stats[col + lane], v[0]);
+        atomicAdd(&s_stats[N + col + lane], sq[0]);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
   }
 }
 
@@ -190,65 +260,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;
-    const int r = m >> 3, c = m & 7;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-      const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
-      const int y = ty * TILE_H + r, x = tx * TILE_W + c;
-      const bool valid = y < P.Ht && x < P.Wt;
-      const long long off = (long long)n * P.out_img + (long long)(y * P.sy + P.oy) * P.out_row +
-                            (long long)(x * P.sx + P.ox) * P.out_pix;
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int col = 0; col < N; col += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + col, v);
-        if (P.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + col + i);
-        }
-        if (valid) {
-          if (P.out_fp32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off + col);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<unsigned*>(&p0); u.y = *reinterpret_cast<unsigned*>(&p1);
-              u.z = *reinterpret_cast<unsigned*>(&p2); u.w = *reinterpret_cast<unsigned*>(&p3);
-              dst[i] = u;
-            }
-          }
-        }
-        if (P.stats) {
-          float sq[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (!valid) v[i] = 0.f;
-            sq[i] = v[i] * v[i];
-          }
-          colsum_butterfly<N>(v, lane);
-          colsum_butterfly<N>(sq, lane);
-          atomicAdd(&s_stats[col + lane], v[0]);
-          atomicAdd(&s_stats[N + col + lane], sq[0]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
+    igemm_epilogue<N>(P, tmem_base, acc_full, acc_empty, s_stats, warp, lane);
   }
 
   tc_fence_before();
@@ -258,6 +270,177 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
     for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) atomicAdd(&P.stats[i], (double)s_stats[i]);
   }
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo variant for 3x3 stride-1 convolutions (forward and data gradient).  Instead of nine shifted activation boxes
+// per 64-channel chunk (each re-read from L2), ONE [18 x pitch pixels] x 64-channel halo box lands in shared memory
+// and the nine taps are nine UMMA descriptors into it: tap (dy, dx) starts (dy*pitch + dx) pixel rows (128 B each)
+// into the box, 8-pixel groups are `pitch` pixel rows apart (stride byte offset = pitch * 128).  The 128-byte swizzle
+// is a function of the shared-memory address, so a descriptor that starts at a 128-byte (not 1024-byte) boundary
+// reads exactly what TMA wrote.  Activation traffic from L2 drops ~4-6x; weights stream through their own ring, or
+// stay resident for the whole kernel when all taps fit (64 -> 64 channels).
+template <int N>
+struct HaloCfg {
+  static constexpr int HALO_BYTES = 23 * 1024;                     // 18 x 10 pixels x 128 B = 23040, 1024-aligned
+  static constexpr int W_BYTES = N * 128;                          // one tap x one 64-channel chunk
+  static constexpr int HALO_STAGES = 3;
+  static constexpr int W_STAGES_RAW = (225 * 1024 - 2048 - 2 * N * 4 - HALO_STAGES * HALO_BYTES) / W_BYTES;
+  static constexpr int W_STAGES = W_STAGES_RAW > 18 ? 18 : W_STAGES_RAW;
+  static constexpr int TILE_BYTES = HALO_STAGES * HALO_BYTES + W_STAGES * W_BYTES;
+  static constexpr int SMEM = TILE_BYTES + 1024 + 512 + 2 * N * 4;
+  static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+};
+
+template <int N>
+__global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __grid_constant__ IgemmMaps maps,
+                                                                      const __grid_constant__ IgemmParams P) {
+  using Cfg = HaloCfg<N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* halos = smem;
+  uint8_t* wts = smem + Cfg::HALO_STAGES * Cfg::HALO_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILE_BYTES);
+  uint64_t* h_full = bars;                                  // [HALO_STAGES]
+  uint64_t* h_empty = h_full + Cfg::HALO_STAGES;            // [HALO_STAGES]
+  uint64_t* w_full = h_empty + Cfg::HALO_STAGES;            // [W_STAGES]
+  uint64_t* w_empty = w_full + Cfg::W_STAGES;               // [W_STAGES]
+  uint64_t* acc_full = w_empty + Cfg::W_STAGES;             // [2]
+  uint64_t* acc_empty = acc_full + 2;                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(smem + Cfg::TILE_BYTES + 512);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t halo_tx = 18u * (uint32_t)P.halo_pitch * 128u;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < MAX_AMAPS; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < Cfg::HALO_STAGES; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); }
+    for (int i = 0; i < Cfg::W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int hs = 0, ws = 0;
+      uint32_t hph = 0, wph = 0;
+      bool first_tile = true;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
+        const int x0 = tx * TILE_W - 1, y0 = ty * TILE_H - 1;
+        for (int s = 0; s < P.nsteps; ++s) {
+          const KStep st = P.steps[s];
+          mbar_wait(&h_empty[hs], hph ^ 1);
+          mbar_arrive_expect_tx(&h_full[hs], halo_tx);
+          tma_load_4d(halos + hs * Cfg::HALO_BYTES, &maps.a[st.map], &h_full[hs], st.c0, x0, y0, n);
+          if (++hs == Cfg::HALO_STAGES) { hs = 0; hph ^= 1; }
+          if (!P.w_resident || first_tile) {
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(&w_empty[ws], wph ^ 1);
+              mbar_arrive_expect_tx(&w_full[ws], Cfg::W_BYTES);
+              tma_load_2d(wts + ws * Cfg::W_BYTES, &maps.b, &w_full[ws], st.wk + t * P.tap_k_stride, 0);
+              if (++ws == Cfg::W_STAGES) { ws = 0; wph ^= 1; }
+            }
+          }
+        }
+        first_tile = false;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, N, 0, 0);
+      const uint32_t sbo = (uint32_t)P.halo_pitch * 128u;
+      int hs = 0, ws = 0, acc = 0;
+      uint32_t hph = 0, wph = 0, acc_phase = 0;
+      bool first_tile = true;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * N;
+        if (P.w_resident) ws = 0;
+        for (int s = 0; s < P.nsteps; ++s) {
+          mbar_wait(&h_full[hs], hph);
+          tc_fence_after();
+          const uint32_t h_addr = smem_u32(halos + hs * Cfg::HALO_BYTES);
+          for (int t = 0; t < 9; ++t) {
+            if (!P.w_resident || first_tile) { mbar_wait(&w_full[ws], wph); tc_fence_after(); }
+            const int ty3 = t / 3, tx3 = t - 3 * ty3;
+            const int hy = P.halo_flip ? 2 - ty3 : ty3, hx = P.halo_flip ? 2 - tx3 : tx3;
+            const uint32_t a_addr = h_addr + (uint32_t)(hy * P.halo_pitch + hx) * 128u;
+            const uint32_t boff = P.dbg_base_offset ? ((a_addr >> 7) & 7u) : 0u;
+            const uint64_t adesc = make_smem_desc(a_addr, 16, sbo, 2, boff);
+            const uint64_t bdesc = make_smem_desc(smem_u32(wts + ws * Cfg::W_BYTES), 16, 1024, 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (s | t | k) != 0);
+            if (!P.w_resident) umma_commit(&w_empty[ws]);
+            if (++ws == Cfg::W_STAGES) { ws = 0; wph ^= 1; }
+          }
+          umma_commit(&h_empty[hs]);
+          if (++hs == Cfg::HALO_STAGES) { hs = 0; hph ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);
+        first_tile = false;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    igemm_epilogue<N>(P, tmem_base, acc_full, acc_empty, s_stats, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (P.stats) {
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) atomicAdd(&P.stats[i], (double)s_stats[i]);
+  }
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int N>
+static int launch_igemm_halo(const IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
+  using Cfg = HaloCfg<N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_igemm_halo<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) { set_error("igemm_halo<%d>: cannot reserve %d bytes of shared memory: %s", N, Cfg::SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    configured = true;
+  }
+  P.w_resident = (9 * P.nsteps <= Cfg::W_STAGES) ? 1 : 0;
+  int grid = sm_count();
+  if (grid > P.num_tiles) grid = P.num_tiles;
+  k_conv_igemm_halo<N><<<grid, IGEMM_THREADS, Cfg::SMEM, st>>>(maps, P);
+  add_launches(1);
+  return check_launch("conv_igemm_halo");
+}
+
+static int dispatch_igemm_halo(int N, const IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
+  if (N == 32) return launch_igemm_halo<32>(maps, P, st);
+  if (N == 64) return launch_igemm_halo<64>(maps, P, st);
+  if (N == 128) return launch_igemm_halo<128>(maps, P, st);
+  if (N == 256) return launch_igemm_halo<256>(maps, P, st);
+  set_error("conv_igemm_halo: unsupported N=%d", N);
+  return DFB_ERR_UNSUPPORTED;
+}
+
+// DFB_CONV_HALO=0 falls back to per-tap activation boxes (k_conv_igemm) for A/B comparisons; default = halo.
+// Measured on B200 (tools/diag_conv.py): descriptors that start at a 128-byte (non-1024-byte) boundary read the
+// TMA-written swizzle correctly with the base-offset field left at 0, for both 1280- and 2048-byte group strides;
+// setting base-offset = (start >> 7) & 7 gives wrong results -- the swizzle XOR is taken from the absolute address.
+static int halo_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DFB_CONV_HALO");
+    mode = e ? atoi(e) : 2;
+  }
+  return mode;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -357,6 +540,33 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
     P.out_img = (long long)Ho * Wo * a->cout; P.out_row = (long long)Wo * a->cout; P.out_pix = a->cout;
     P.sy = P.sx = 1; P.oy = P.ox = 0;
     const uint32_t box[4] = {(uint32_t)KC, TILE_W, TILE_H, 1};
+    if (s == 1 && k == 3 && KC == 64 && halo_mode() > 0) {
+      // halo variant: one [18 x pitch] pixel box per 64-channel chunk, nine taps as shifted descriptors
+      const int hm = halo_mode();
+      (void)hm;
+      P.halo_pitch = 10;
+      P.dbg_base_offset = 0;
+      P.halo_flip = 0;
+      P.tap_k_stride = cin_total;
+      const uint32_t hbox[4] = {64, (uint32_t)P.halo_pitch, 18, 1};
+      int coff = 0;
+      for (int i = 0; i < a->n_src; ++i) {
+        const uint64_t C = a->cin[i];
+        const uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)a->n};
+        const uint64_t str[3] = {C * 2, C * 2 * W, C * 2 * W * H};
+        if ((rc = make_tensor_map_bf16(&maps.a[i], a->x[i], 4, dims, str, hbox, 128))) return rc;
+        for (int c0 = 0; c0 < a->cin[i]; c0 += 64) P.steps[nsteps++] = KStep{(int8_t)i, 0, 0, 0, (int16_t)c0, (int16_t)(coff + c0)};
+        coff += a->cin[i];
+      }
+      const uint64_t bd[2] = {(uint64_t)taps * cin_total, (uint64_t)a->cout};
+      const uint64_t bs[1] = {(uint64_t)taps * cin_total * 2};
+      const uint32_t bb[2] = {64, (uint32_t)N};
+      if ((rc = make_tensor_map_bf16(&maps.b, a->w, 2, bd, bs, bb, 128))) return rc;
+      P.nsteps = nsteps;
+      P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
+      P.num_tiles = P.tiles_x * P.tiles_y * a->n;
+      return dispatch_igemm_halo(N, maps, P, st);
+    }
     if (s == 1) {
       for (int i = 0; i < a->n_src; ++i) {
         const uint64_t C = a->cin[i];
@@ -423,6 +633,22 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
     const char* wbase = (const char*)a->w + (size_t)a->cin_off * taps * cout * 2;
     if ((rc = make_tensor_map_bf16(&maps.b, wbase, 2, bd, bs, bb, KC * 2))) return rc;
     P.out_img = (long long)H * W * cin; P.out_row = (long long)W * cin; P.out_pix = cin;
+    if (s == 1 && k == 3 && KC == 64 && halo_mode() > 0) {
+      const int hm = halo_mode();
+      P.Ht = H; P.Wt = W; P.sy = P.sx = 1; P.oy = P.ox = 0;
+      (void)hm;
+      P.halo_pitch = 10;
+      P.dbg_base_offset = 0;
+      P.halo_flip = 1;                       // gx[y, x] = sum_t W[t]^T gy[y - dy_t, x - dx_t]
+      P.tap_k_stride = cout;
+      const uint32_t hbox[4] = {64, (uint32_t)P.halo_pitch, 18, 1};
+      if ((rc = make_tensor_map_bf16(&maps.a[0], a->x[0], 4, dims, str, hbox, 128))) return rc;
+      for (int c0 = 0; c0 < cout; c0 += 64) P.steps[nsteps++] = KStep{0, 0, 0, 0, (int16_t)c0, (int16_t)c0};
+      P.nsteps = nsteps;
+      P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
+      P.num_tiles = P.tiles_x * P.tiles_y * a->n;
+      return dispatch_igemm_halo(N, maps, P, st);
+    }
     if (s == 1) {
       // gx[y, x] = sum_t W[t]^T gy[y - dy_t, x - dx_t]
       P.Ht = H; P.Wt = W; P.sy = P.sx = 1; P.oy = P.ox = 0;

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) k_pfn_moments(const int* __restrict__ cou
     for (int j = 0; j < PFN_K; ++j) {
       acc[j] += fe[j];
 #pragma unroll
-      for (int k = j; k < PFN_K; ++k) acc[o++] = fmaf(fe[j], fe[k], acc[o]);
+      for (int k = j; k < PFN_K; ++k) { acc[o] = fmaf(fe[j], fe[k], acc[o]); ++o; }
     }
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

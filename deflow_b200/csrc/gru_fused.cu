@@ -41,8 +41,14 @@ struct GruFusedParams {
   float* flow;          // [n,3]
 };
 
-__device__ __forceinline__ float fsigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float ftanh(float v) { return 2.0f * fsigmoid(2.0f * v) - 1.0f; }
+// One SFU op per gate value: tanh.approx.f32 (relative error ~2^-11, below the bf16 resolution of the operands the
+// result feeds); sigmoid(v) = 0.5 tanh(v/2) + 0.5.  The gate stages are SFU-bound otherwise (exp + reciprocal).
+__device__ __forceinline__ float ftanh(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float fsigmoid(float v) { return fmaf(0.5f, ftanh(0.5f * v), 0.5f); }
 
 // store 8 consecutive channels (one 16-byte chunk) of row `row` into a [128 x 128 B] SWIZZLE_128B K-major tile
 __device__ __forceinline__ void st_tile_chunk(uint8_t* tile, int row, int chunk, const float* f) {

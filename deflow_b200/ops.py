@@ -167,6 +167,7 @@ def _pfn_args(idx: PillarIndex, H, W, training, center_off, eps, momentum, weigh
     a.pil_mean, a.stats, a.bn_params = pil_mean.data_ptr(), stats.data_ptr(), bn_params.data_ptr()
     a.pil_feats, a.image = pil_feats.data_ptr(), image.data_ptr()
     a.image_bf16 = int(image.dtype == torch.bfloat16)
+    a.pil_cap = idx.pil_cap
     return a
 
 

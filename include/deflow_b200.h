@@ -142,11 +142,12 @@ typedef struct {
   float* running_mean;    /* [32] updated in place when training (2B sequential updates) */
   float* running_var;     /* [32] */
   float* pil_mean;        /* out [pil_cap,3]: cluster_scatter result */
-  double* stats;          /* workspace/out [F,2,32]: per-frame sum(y), sum((y-mean)^2) */
+  double* stats;          /* workspace/out [F,64]: per-frame moments of the decorated features: S1[9] | S2[45] (upper triangle) */
   float* bn_params;       /* out [F,4,32]: a = gamma*rstd, b = beta - mean*a, mean, rstd (saved for backward) */
   float* pil_feats;       /* out [pil_cap,32] fp32: pfn_scatter result (voxel_feats) */
   void* image;            /* out [F,H,W,32] NHWC, zero-filled here; bf16 if image_bf16 else f32 */
   int image_bf16;
+  long long pil_cap;      /* rows of pil_feats / pil_mean */
 } dfb_pfn_args;
 int dfb_pfn_forward(const dfb_pfn_args* args, void* stream);
 
