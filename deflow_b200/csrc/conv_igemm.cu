@@ -834,6 +834,151 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad(const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Halo weight gradient for 3x3 stride-1 convolutions.  One [10 x 10 pixel] x 64-channel box of x serves all taps of
+// a work item: tap (dy, dx) is the MN-major descriptor that starts (dy*10 + dx) pixel rows into the box, and a PAIR of
+// taps forms one M = 128 operand whose two 64-channel groups are (offset(t2) - offset(t1)) bytes apart (the leading
+// byte offset).  A work item = (64-channel chunk of x, set of <= 512/N tap pairs, range of pixel tiles); gy tiles are
+// loaded once per item and tile instead of once per tap pair, x once instead of once per tap.
+constexpr int WH_HALO_BYTES = 13 * 1024;  // 100 pixel rows x 128 B = 12800, 1024-aligned
+constexpr int WH_MAX_ITEMS = 32;
+
+struct WHItem { int8_t map, npairs, dup_first, pad1; int16_t c0, ci_glob; int8_t t1[5], t2[5]; int16_t pad2; };  // dup_first: the last pair's first tap repeats one already covered (odd tap count)
+
+struct WgradHaloParams {
+  int n_img, Ht, Wt, tiles_x, tiles_y, num_tiles;
+  int n_items, splits;
+  int cin_total, cout;
+  float* wacc;
+  WHItem items[WH_MAX_ITEMS];
+};
+
+template <int N>
+struct WgradHaloCfg {
+  static constexpr int B_BYTES = (N / 64) * WG_PIX * 128;
+  static constexpr int STAGE_BYTES = WH_HALO_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (208 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int MAX_PAIRS = 512 / N > 5 ? 5 : 512 / N;
+  static constexpr int TMEM_COLS = 512;
+};
+
+template <int N>
+__global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_halo(const __grid_constant__ WgradMaps maps,
+                                                                   const __grid_constant__ WgradHaloParams P) {
+  using Cfg = WgradHaloCfg<N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int item_id = blockIdx.x % P.n_items, split = blockIdx.x / P.n_items;
+  const WHItem it = P.items[item_id];
+  const int per = (P.num_tiles + P.splits - 1) / P.splits;
+  const int t_begin = split * per, t_end = min(P.num_tiles, t_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < MAX_AMAPS; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
+        const int x0 = tx * 8, y0 = ty * 8;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + WH_HALO_BYTES;
+        mbar_arrive_expect_tx(&full[stage], 100 * 128 + Cfg::B_BYTES);
+        tma_load_4d(a_dst, &maps.a[it.map], &full[stage], it.c0, x0 - 1, y0 - 1, n);
+#pragma unroll
+        for (int j = 0; j < N / 64; ++j) tma_load_4d(b_dst + j * WG_PIX * 128, &maps.b, &full[stage], j * 64, x0, y0, n);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + WH_HALO_BYTES;
+        const uint64_t bdesc = make_smem_desc(b_addr, WG_PIX * 128, 1024, 2);
+        for (int pr = 0; pr < it.npairs; ++pr) {
+          const int o1 = (it.t1[pr] / 3) * 10 + it.t1[pr] % 3, o2 = (it.t2[pr] / 3) * 10 + it.t2[pr] % 3;
+          // two 64-channel M groups = two taps, (o2 - o1) pixel rows apart; 8-pixel K groups one halo row (1280 B) apart
+          const uint64_t adesc = make_smem_desc(a_addr + o1 * 128, (uint32_t)(o2 - o1) * 128u, 1280, 2);
+#pragma unroll
+          for (int k = 0; k < WG_PIX / 16; ++k)  // 16 pixels = 2 patch rows: A advances 2 halo rows, B 16 tile rows
+            umma_bf16(tmem_base + pr * N, adesc + (uint64_t)(k * 160), bdesc + (uint64_t)(k * 128), idesc, !(first && k == 0));
+        }
+        first = false;
+        umma_commit(&empty[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (t_end > t_begin) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const bool live_c = (it.ci_glob + (m & 63)) < P.cin_total;
+    for (int pr = 0; pr < it.npairs; ++pr) {
+      const int tap = m < 64 ? it.t1[pr] : it.t2[pr];
+      const bool live = live_c && !(m < 64 && it.dup_first && pr == it.npairs - 1);  // drop the repeated tap
+      float* dst = P.wacc + ((size_t)tap * P.cout) * P.cin_total + it.ci_glob + (m & 63);
+#pragma unroll 1
+      for (int col = 0; col < N && col < P.cout; col += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + pr * N + col, v);
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)(col + i) * P.cin_total, v[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int N>
+static int launch_wgrad_halo(const WgradMaps& maps, const WgradHaloParams& P, cudaStream_t st) {
+  using Cfg = WgradHaloCfg<N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_halo<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) { set_error("wgrad_halo<%d>: cannot reserve %d bytes of shared memory: %s", N, Cfg::SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    configured = true;
+  }
+  k_conv_wgrad_halo<N><<<P.n_items * P.splits, WG_THREADS, Cfg::SMEM, st>>>(maps, P);
+  add_launches(1);
+  return check_launch("conv_wgrad_halo");
+}
+
 // wacc [taps][cout][cin] -> torch [cout][cin][taps]; accumulate = grad += (autograd accumulation)
 __global__ void __launch_bounds__(256) k_unpack_wgrad(const float* __restrict__ wacc, int cout, int cin, int taps,
                                                       float* __restrict__ gw, int accumulate) {
@@ -864,6 +1009,15 @@ static int launch_wgrad(const WgradMaps& maps, const WgradParams& P, cudaStream_
 }  // namespace tc
 }  // namespace dfb
 
+static bool halo_wgrad_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DFB_WGRAD_HALO");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode != 0;
+}
+
 // x: the forward's sources (n_src, cin[]), a->w unused; a->y = gy [n,Ho,Wo,cout] bf16 (input here);
 // wacc: fp32 workspace [taps][cout][cin_total] (zeroed here); grad_w: torch layout fp32 [cout][cin_total][k][k].
 extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad_w, int accumulate, void* stream_) {
@@ -889,6 +1043,56 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
     if ((rc = make_tensor_map_bf16(&maps.b, a->y, 4, dims, str, box, 128))) return rc;
   }
   int ng = 0;
+  if (s == 1 && k == 3 && halo_wgrad_enabled()) {
+    // ---------------------------------------------------------------- halo variant
+    tc::WgradHaloParams Q;
+    memset(&Q, 0, sizeof(Q));
+    const uint32_t hbox[4] = {64, 10, 10, 1};
+    const int ncol = a->cout <= 64 ? 64 : a->cout;
+    const int max_pairs = 512 / ncol > 5 ? 5 : 512 / ncol;
+    int ni = 0, coff = 0;
+    for (int i = 0; i < a->n_src; ++i) {
+      const uint64_t C = a->cin[i];
+      const uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)a->n};
+      const uint64_t str[3] = {C * 2, C * 2 * W, C * 2 * W * H};
+      if ((rc = make_tensor_map_bf16(&maps.a[i], a->x[i], 4, dims, str, hbox, 128))) return rc;
+      for (int c0 = 0; c0 < a->cin[i]; c0 += 64) {
+        int t = 0;
+        while (t < 9) {  // tap sets of up to max_pairs pairs
+          if (ni >= tc::WH_MAX_ITEMS) { set_error("dfb_conv2d_wgrad: too many work items"); return DFB_ERR_UNSUPPORTED; }
+          tc::WHItem& it = Q.items[ni++];
+          it.map = (int8_t)i; it.c0 = (int16_t)c0; it.ci_glob = (int16_t)(coff + c0); it.npairs = 0; it.dup_first = 0;
+          while (t < 9 && it.npairs < max_pairs) {
+            if (t + 1 < 9) { it.t1[it.npairs] = (int8_t)t; it.t2[it.npairs] = (int8_t)(t + 1); }
+            else { it.t1[it.npairs] = (int8_t)(t - 1); it.t2[it.npairs] = (int8_t)t; it.dup_first = 1; }  // (7, 8), 7 dropped
+            ++it.npairs;
+            t += 2;
+          }
+        }
+      }
+      coff += a->cin[i];
+    }
+    Q.n_items = ni;
+    Q.n_img = a->n; Q.Ht = Ho; Q.Wt = Wo;
+    Q.tiles_x = (Wo + 7) / 8; Q.tiles_y = (Ho + 7) / 8;
+    Q.num_tiles = Q.tiles_x * Q.tiles_y * a->n;
+    int splits = (2 * sm_count() + ni - 1) / ni;
+    if (splits > Q.num_tiles) splits = Q.num_tiles;
+    if (splits < 1) splits = 1;
+    Q.splits = splits;
+    Q.cin_total = cin_total; Q.cout = a->cout; Q.wacc = wacc;
+    const size_t total = (size_t)taps * a->cout * cin_total;
+    cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
+    if (ncol == 64) rc = tc::launch_wgrad_halo<64>(maps, Q, st);
+    else if (ncol == 128) rc = tc::launch_wgrad_halo<128>(maps, Q, st);
+    else rc = tc::launch_wgrad_halo<256>(maps, Q, st);
+    if (rc) return rc;
+    long long blocks = ((long long)total + 255) / 256;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    tc::k_unpack_wgrad<<<(int)blocks, 256, 0, st>>>(wacc, a->cout, cin_total, taps, grad_w, accumulate);
+    add_launches(1);
+    return check_launch("dfb_conv2d_wgrad");
+  }
   if (s == 1) {
     for (int i = 0; i < a->n_src; ++i) {
       const uint64_t C = a->cin[i];

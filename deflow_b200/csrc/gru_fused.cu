@@ -328,18 +328,13 @@ constexpr int GB_PAR = GB_X + 16384;         // bz | br | bq
 constexpr int GB_BAR = GB_PAR + 384 * 4;
 constexpr int GB_SMEM = GB_BAR + 64 + 1008;
 
-struct GruBwdMaps { CUtensorMap wzr, wq; };
+struct GruBwdMaps { CUtensorMap wzr, wq, h, x, rh, dq, dzr; };
 
 struct GruBwdParams {
-  const __nv_bfloat16* hsave;   // [iters+1][n_pad][128]
-  const __nv_bfloat16* xsave;   // [n_pad][64]
   const __nv_bfloat16* dh_in;   // [n_pad][128] gradient w.r.t. the final state (from the MLP head)
   const __nv_bfloat16* dx_in;   // [n_pad][64]  gradient w.r.t. x from the MLP head
   const float* par;             // bz | br | bq
   int n, n_pad, iters;
-  __nv_bfloat16* rh;            // [iters][n_pad][128]
-  __nv_bfloat16* dq;            // [iters][n_pad][128]
-  __nv_bfloat16* dzr;           // [iters][n_pad][256]
   __nv_bfloat16* dh0;           // [n_pad][128]  gradient w.r.t. the gathered pillar vectors
   float* dx;                    // [n_pad][64]   gradient w.r.t. x (all iterations + head)
 };
@@ -357,7 +352,15 @@ __device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const float* f) {
   for (int i = 0; i < 4; ++i) pp[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+  const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(pp[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
 
+// All HBM traffic of the iteration loop goes through TMA: the control thread loads the h_t / x tiles straight into
+// the swizzled operand tiles and stores the rh / dq_pre / dzr_pre tiles from them (bulk async groups), so the 256
+// worker threads touch only TMEM, registers and shared memory inside the loop.
 __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_constant__ GruBwdMaps maps,
                                                                  const __grid_constant__ GruBwdParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -366,15 +369,17 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + GB_BAR);
   uint64_t* bar_a = bar_w + 1;
   uint64_t* bar_d = bar_w + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
+  uint64_t* bar_h = bar_w + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (P.n_pad + 127) / 128;
 
   for (int i = threadIdx.x; i < 384; i += blockDim.x) par[i] = P.par[i];
   if (warp == 8) {
     if (lane == 0) {
-      tma_prefetch_desc(&maps.wzr); tma_prefetch_desc(&maps.wq);
-      mbar_init(bar_w, 1); mbar_init(bar_a, 8); mbar_init(bar_d, 1);
+      tma_prefetch_desc(&maps.wzr); tma_prefetch_desc(&maps.wq); tma_prefetch_desc(&maps.h); tma_prefetch_desc(&maps.x);
+      tma_prefetch_desc(&maps.rh); tma_prefetch_desc(&maps.dq); tma_prefetch_desc(&maps.dzr);
+      mbar_init(bar_w, 1); mbar_init(bar_a, 8); mbar_init(bar_d, 1); mbar_init(bar_h, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -397,11 +402,12 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
         tma_load_2d(smem + GB_WQ + c * 16384, &maps.wq, bar_w, c * 64, 0);
       }
       mbar_wait(bar_w, 0);
-      uint32_t use_a = 0;
-      const uint32_t t_p = smem_u32(smem + GB_P), t_q = smem_u32(smem + GB_Q), t_x = smem_u32(smem + GB_X);
+      uint32_t use_a = 0, use_d = 0, use_h = 0;
+      uint8_t* sp = smem + GB_P; uint8_t* sq = smem + GB_Q; uint8_t* sx = smem + GB_X;
+      const uint32_t t_p = smem_u32(sp), t_q = smem_u32(sq), t_x = smem_u32(sx);
       const uint32_t wzr = smem_u32(smem + GB_WZR), wq = smem_u32(smem + GB_WQ);
       auto wait_a = [&]() { mbar_wait(bar_a, use_a & 1); ++use_a; tc_fence_after(); };
-      // forward-style GEMM: D[128, N] = [A_p | X] (K = 192, K-major) x W^T (K-major tiles)
+      auto commit_d = [&]() { umma_commit(bar_d); ++use_d; };
       auto gemm_fwd = [&](uint32_t w_base, uint32_t w_chunk, int N, uint32_t dcol) {
         const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
 #pragma unroll
@@ -412,8 +418,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + dcol, ad + 2 * k, bd + 2 * k, idesc, (c | k) != 0);
         }
       };
-      // data-gradient GEMM: D[128, N'] (+)= G[128, 128] (A tile pair, K-major) x W[rows row0..row0+127][cols of chunk
-      // c0 .. c0 + N'/64 - 1], the weight tiles read MN-major (transposed view): K' = weight rows, N' = weight columns.
+      // D[128, N'] (+)= G[128, 128] (A tile pair, K-major) x W[rows row0..row0+127][columns of chunks c0..]: the weight
+      // tiles are read MN-major (transposed view): K' = weight rows, N' = weight columns.
       auto gemm_dgrad = [&](uint32_t a_tile, uint32_t w_base, uint32_t w_chunk, int row0, int c0, int N, uint32_t dcol,
                             bool accumulate) {
         const uint32_t idesc = make_idesc_bf16(128, N, 0, 1);
@@ -426,26 +432,45 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
         }
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * 128;
         for (int it = P.iters - 1; it >= 0; --it) {
           const bool first = it == P.iters - 1;
-          wait_a();  // P = h_t, X
+          // P (and X on the first iteration) are free: the previous G4 was waited for below
+          mbar_arrive_expect_tx(bar_h, 32768 + (first ? 16384 : 0));
+          tma_load_3d(sp, &maps.h, bar_h, 0, row0, it);
+          tma_load_3d(sp + 16384, &maps.h, bar_h, 64, row0, it);
+          if (first) tma_load_3d(sx, &maps.x, bar_h, 0, row0, 0);
+          mbar_wait(bar_h, use_h & 1); ++use_h;
+          wait_a();  // workers are done with the TMEM contents of the previous stage
           gemm_fwd(wzr, 32768, 256, C_ZR);
-          umma_commit(bar_d);
+          commit_d();
           wait_a();  // P = r * h_t
+          tma_store_3d(&maps.rh, sp, 0, row0, it); tma_store_3d(&maps.rh, sp + 16384, 64, row0, it);
+          tma_store_commit();
           gemm_fwd(wq, 16384, 128, C_Q);
-          umma_commit(bar_d);
+          tma_store_wait_read();
+          commit_d();
           wait_a();  // P = dq_pre, Q = dz_pre
+          tma_store_3d(&maps.dq, sp, 0, row0, it); tma_store_3d(&maps.dq, sp + 16384, 64, row0, it);
+          tma_store_3d(&maps.dzr, sq, 0, row0, it); tma_store_3d(&maps.dzr, sq + 16384, 64, row0, it);
+          tma_store_commit();
           gemm_dgrad(t_p, wq, 16384, 0, 0, 128, C_Q, false);        // d_rh  = dq Wq[:, 0:128]
           gemm_dgrad(t_p, wq, 16384, 0, 2, 64, C_DX, !first);       // d_x  += dq Wq[:, 128:192]
           gemm_dgrad(t_q, wzr, 32768, 0, 0, 128, C_ZR, false);      // d_h   = dz Wz[:, 0:128]
           gemm_dgrad(t_q, wzr, 32768, 0, 2, 64, C_DX, true);        // d_x  += dz Wz[:, 128:192]
-          umma_commit(bar_d);
+          tma_store_wait_read();
+          commit_d();
           wait_a();  // P = dr_pre
+          tma_store_3d(&maps.dzr, sp, 128, row0, it); tma_store_3d(&maps.dzr, sp + 16384, 192, row0, it);
+          tma_store_commit();
           gemm_dgrad(t_p, wzr, 32768, 128, 0, 128, C_ZR, true);     // d_h  += dr Wr[:, 0:128]
           gemm_dgrad(t_p, wzr, 32768, 128, 2, 64, C_DX, true);      // d_x  += dr Wr[:, 128:192]
-          umma_commit(bar_d);
+          tma_store_wait_read();
+          commit_d();
+          mbar_wait(bar_d, (use_d - 1) & 1);  // G4 has finished reading P before the next h_t lands in it
         }
       }
+      tma_store_wait_all();
     }
   } else {
     const int q = warp & 3, half = warp >> 2;
@@ -453,8 +478,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint8_t* tile_p = smem + GB_P + half * 16384;
     uint8_t* tile_q = smem + GB_Q + half * 16384;
-    uint8_t* tile_x = smem + GB_X;
-    uint32_t use_d = 0;
+    uint32_t use_d = 0, use_h = 0;
     auto signal_a = [&]() {
       tc_fence_before();
       fence_proxy_async();
@@ -467,17 +491,6 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
       const bool valid = p < P.n;
       const bool inpad = p < P.n_pad;
       const size_t prow = inpad ? (size_t)p : 0;
-      // X tile (this thread's 32 channels)
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        float f[8];
-        if (inpad) ld_bf16x8(P.xsave + prow * 64 + half * 32 + c8 * 8, f);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = 0.f;
-        }
-        st_tile_chunk(tile_x, m, half * 4 + c8, f);
-      }
       float dh[64];
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {
@@ -488,15 +501,12 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
         }
       }
       for (int it = P.iters - 1; it >= 0; --it) {
-        const __nv_bfloat16* hrow = P.hsave + ((size_t)it * P.n_pad + prow) * 128 + half * 64;
+        signal_a();  // TMEM of the previous stage has been read
+        wait_d();    // z | r pre-activations
+        mbar_wait(bar_h, use_h & 1); ++use_h;  // the h_t tile written by TMA is visible to this thread
+        uint4 hp[8];                            // this row's 64 channels of h_t, packed bf16
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {  // h_t is re-read (L2) where needed instead of living in 64 registers
-          uint4 u = make_uint4(0u, 0u, 0u, 0u);
-          if (inpad) u = __ldg(reinterpret_cast<const uint4*>(hrow + c8 * 8));
-          *reinterpret_cast<uint4*>(tile_p + m * 128 + ((c8 ^ (m & 7)) << 4)) = u;
-        }
-        signal_a();
-        wait_d();  // z | r pre-activations
+        for (int c8 = 0; c8 < 8; ++c8) hp[c8] = *reinterpret_cast<const uint4*>(tile_p + m * 128 + ((c8 ^ (m & 7)) << 4));
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           float v[32];
@@ -504,14 +514,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             float f[8], hh[8];
-            ld_bf16x8(hrow + cc * 32 + c8 * 8, hh);
+            unpack_bf16x8(hp[cc * 4 + c8], hh);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = cc * 32 + c8 * 8 + i;
               f[i] = valid ? fsigmoid(v[c8 * 8 + i] + br[half * 64 + j]) * hh[i] : 0.f;
             }
             st_tile_chunk(tile_p, m, cc * 4 + c8, f);
-            if (inpad) st_bf16x8(P.rh + ((size_t)it * P.n_pad + prow) * 128 + half * 64 + cc * 32 + c8 * 8, f);
           }
         }
         signal_a();
@@ -524,7 +533,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
             float fq[8], fz[8], hh[8];
-            ld_bf16x8(hrow + cc * 16 + c8 * 8, hh);
+            unpack_bf16x8(hp[cc * 2 + c8], hh);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = cc * 16 + c8 * 8 + i;
@@ -537,10 +546,6 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
             }
             st_tile_chunk(tile_p, m, cc * 2 + c8, fq);
             st_tile_chunk(tile_q, m, cc * 2 + c8, fz);
-            if (inpad) {
-              st_bf16x8(P.dq + ((size_t)it * P.n_pad + prow) * 128 + half * 64 + cc * 16 + c8 * 8, fq);
-              st_bf16x8(P.dzr + ((size_t)it * P.n_pad + prow) * 256 + half * 64 + cc * 16 + c8 * 8, fz);
-            }
           }
         }
         signal_a();
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
             float f[8], hh[8];
-            ld_bf16x8(hrow + cc * 16 + c8 * 8, hh);
+            unpack_bf16x8(hp[cc * 2 + c8], hh);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = cc * 16 + c8 * 8 + i;
@@ -563,7 +568,6 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
               dh[j] = fmaf(g, r, dh[j]);
             }
             st_tile_chunk(tile_p, m, cc * 2 + c8, f);
-            if (inpad) st_bf16x8(P.dzr + ((size_t)it * P.n_pad + prow) * 256 + 128 + half * 64 + cc * 16 + c8 * 8, f);
           }
         }
         signal_a();
@@ -613,11 +617,19 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
 }  // namespace tc
 }  // namespace dfb
 
+static int make_rows_map(CUtensorMap* map, const void* base, int cols, int n_pad, int slabs) {
+  // bf16 [slabs][n_pad][cols], box = 64 columns x 128 rows x 1 slab
+  const uint64_t d[3] = {(uint64_t)cols, (uint64_t)n_pad, (uint64_t)slabs};
+  const uint64_t st[2] = {(uint64_t)cols * 2, (uint64_t)cols * 2 * (uint64_t)n_pad};
+  const uint32_t b[3] = {64, 128, 1};
+  return dfb::tc::make_tensor_map_bf16(map, base, 3, d, st, b, 128);
+}
+
 extern "C" int dfb_gru_fused_backward(const void* hsave, const void* xsave, const void* dh_in, const void* dx_in,
                                       const void* wzr, const void* wq, const float* par, int n, int n_pad, int iters,
                                       void* rh, void* dq, void* dzr, void* dh0, float* dx, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  if (n <= 0 || n_pad < n || iters < 0 || iters > 64) { set_error("dfb_gru_fused_backward: bad sizes"); return DFB_ERR_ARG; }
+  if (n <= 0 || n_pad < n || iters <= 0 || iters > 64) { set_error("dfb_gru_fused_backward: bad sizes"); return DFB_ERR_ARG; }
   GruBwdMaps maps;
   GruBwdParams P;
   memset(&maps, 0, sizeof(maps));
@@ -631,10 +643,14 @@ extern "C" int dfb_gru_fused_backward(const void* hsave, const void* xsave, cons
     const uint64_t d[2] = {192, 128}; const uint32_t b[2] = {64, 128};
     if ((rc = make_tensor_map_bf16(&maps.wq, wq, 2, d, str, b, 128))) return rc;
   }
-  P.hsave = (const __nv_bfloat16*)hsave; P.xsave = (const __nv_bfloat16*)xsave;
+  if ((rc = make_rows_map(&maps.h, hsave, 128, n_pad, iters + 1))) return rc;
+  if ((rc = make_rows_map(&maps.x, xsave, 64, n_pad, 1))) return rc;
+  if ((rc = make_rows_map(&maps.rh, rh, 128, n_pad, iters))) return rc;
+  if ((rc = make_rows_map(&maps.dq, dq, 128, n_pad, iters))) return rc;
+  if ((rc = make_rows_map(&maps.dzr, dzr, 256, n_pad, iters))) return rc;
   P.dh_in = (const __nv_bfloat16*)dh_in; P.dx_in = (const __nv_bfloat16*)dx_in; P.par = par;
   P.n = n; P.n_pad = n_pad; P.iters = iters;
-  P.rh = (__nv_bfloat16*)rh; P.dq = (__nv_bfloat16*)dq; P.dzr = (__nv_bfloat16*)dzr; P.dh0 = (__nv_bfloat16*)dh0; P.dx = dx;
+  P.dh0 = (__nv_bfloat16*)dh0; P.dx = dx;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_gru_fused_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);

@@ -75,54 +75,62 @@ __global__ void k_bn2d_finalize(const double* __restrict__ stats, double count, 
 }
 
 // In all three passes a thread keeps ONE channel octet for its whole grid-stride loop (the stride is a multiple of
-// the vectors-per-pixel count), so the BatchNorm parameters of its 8 channels live in registers.
+// the vectors-per-pixel count).  The per-channel parameters are read from shared memory inside the loop rather than
+// held in registers: these kernels are latency-bound on HBM, so what matters is resident warps x bytes in flight
+// (<= 40 registers per thread -> 6 CTAs per SM, 4 x 16-byte loads in flight per thread).
+struct BnSmem { float a[256], b[256], mu[256], rs[256], m1[256], m2[256]; };
 
-// y = GELU(a*x + b), 8 channels per thread, two 16-byte vectors in flight
-__global__ void __launch_bounds__(256) k_bn_gelu_apply(const uint4* __restrict__ x, const float* __restrict__ bn, int C,
-                                                       long long n_vec, uint4* __restrict__ y) {
-  const int vpp = C >> 3;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c0 = (int)(e0 % vpp) << 3;
-  float a[8], b[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { a[i] = __ldg(bn + c0 + i); b[i] = __ldg(bn + C + c0 + i); }
-  for (long long e = e0; e < n_vec; e += 2 * stride) {
-    const long long e2 = e + stride;
-    const bool two = e2 < n_vec;
-    const uint4 u0 = __ldg(x + e);
-    const uint4 u1 = two ? __ldg(x + e2) : u0;
-    float f[8];
-    unpack8(u0, f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = gelu_f(fmaf(f[i], a[i], b[i]));
-    y[e] = pack8(f);
-    if (two) {
-      unpack8(u1, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = gelu_f(fmaf(f[i], a[i], b[i]));
-      y[e2] = pack8(f);
-    }
-  }
+__device__ __forceinline__ void ld8(const float* p, float* f) {
+  const float4 u = *reinterpret_cast<const float4*>(p), v = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = v.x; f[5] = v.y; f[6] = v.z; f[7] = v.w;
 }
 
-// Backward pass 1: red[0][c] = sum g1, red[1][c] = sum g1 * xhat, with g1 = gy * GELU'(a*x + b)
-__global__ void __launch_bounds__(256) k_bn_gelu_bwd_reduce(const uint4* __restrict__ x, const uint4* __restrict__ gy,
-                                                            const float* __restrict__ bn, int C, long long n_vec,
-                                                            double* __restrict__ red) {
-  __shared__ float acc1[256], acc2[256];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { acc1[i] = 0.f; acc2[i] = 0.f; }
+// y = GELU(a*x + b)
+__global__ void __launch_bounds__(256, 4) k_bn_gelu_apply(const uint4* __restrict__ x, const float* __restrict__ bn, int C,
+                                                          long long n_vec, uint4* __restrict__ y) {
+  __shared__ __align__(16) float sa[256], sb[256];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { sa[i] = bn[i]; sb[i] = bn[C + i]; }
   __syncthreads();
   const int vpp = C >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(e0 % vpp) << 3;
-  float a[8], b[8], mu[8], rs[8], s1[8], s2[8];
+  for (long long e = e0; e < n_vec; e += 4 * stride) {
+    uint4 u[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    a[i] = __ldg(bn + c0 + i); b[i] = __ldg(bn + C + c0 + i); mu[i] = __ldg(bn + 2 * C + c0 + i); rs[i] = __ldg(bn + 3 * C + c0 + i);
-    s1[i] = 0.f; s2[i] = 0.f;
+    for (int j = 0; j < 4; ++j) { const long long ej = e + j * stride; if (ej < n_vec) u[j] = __ldg(x + ej); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long ej = e + j * stride;
+      if (ej < n_vec) {
+        float f[8], a[8], b[8];
+        unpack8(u[j], f); ld8(sa + c0, a); ld8(sb + c0, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = gelu_f(fmaf(f[i], a[i], b[i]));
+        y[ej] = pack8(f);
+      }
+    }
   }
+}
+
+// Backward pass 1: red[0][c] = sum g1, red[1][c] = sum g1 * xhat, with g1 = gy * GELU'(a*x + b)
+__global__ void __launch_bounds__(256, 3) k_bn_gelu_bwd_reduce(const uint4* __restrict__ x, const uint4* __restrict__ gy,
+                                                               const float* __restrict__ bn, int C, long long n_vec,
+                                                               double* __restrict__ red) {
+  __shared__ __align__(16) float sa[256], sb[256], smu[256], srs[256];
+  __shared__ float acc1[256], acc2[256];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sa[i] = bn[i]; sb[i] = bn[C + i]; smu[i] = bn[2 * C + i]; srs[i] = bn[3 * C + i];
+    acc1[i] = 0.f; acc2[i] = 0.f;
+  }
+  __syncthreads();
+  const int vpp = C >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(e0 % vpp) << 3;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
   for (long long e = e0; e < n_vec; e += 2 * stride) {
     const long long e2 = e + stride;
     const bool two = e2 < n_vec;
@@ -132,17 +140,17 @@ __global__ void __launch_bounds__(256) k_bn_gelu_bwd_reduce(const uint4* __restr
     unpack8(ux0, fx); unpack8(ug0, fg);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], a[i], b[i]));
+      const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], sa[c0 + i], sb[c0 + i]));
       s1[i] += g1;
-      s2[i] = fmaf(g1, (fx[i] - mu[i]) * rs[i], s2[i]);
+      s2[i] = fmaf(g1, (fx[i] - smu[c0 + i]) * srs[c0 + i], s2[i]);
     }
     if (two) {
       unpack8(ux1, fx); unpack8(ug1, fg);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], a[i], b[i]));
+        const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], sa[c0 + i], sb[c0 + i]));
         s1[i] += g1;
-        s2[i] = fmaf(g1, (fx[i] - mu[i]) * rs[i], s2[i]);
+        s2[i] = fmaf(g1, (fx[i] - smu[c0 + i]) * srs[c0 + i], s2[i]);
       }
     }
   }
@@ -156,21 +164,21 @@ __global__ void __launch_bounds__(256) k_bn_gelu_bwd_reduce(const uint4* __restr
 }
 
 // Backward pass 2: gx = a * (g1 - m1 - xhat*m2) (training) or a * g1 (eval)
-__global__ void __launch_bounds__(256) k_bn_gelu_bwd_apply(const uint4* __restrict__ x, const uint4* __restrict__ gy,
-                                                           const float* __restrict__ bn, const double* __restrict__ red,
-                                                           double count, int training, int C, long long n_vec,
-                                                           uint4* __restrict__ gx) {
+__global__ void __launch_bounds__(256, 3) k_bn_gelu_bwd_apply(const uint4* __restrict__ x, const uint4* __restrict__ gy,
+                                                              const float* __restrict__ bn, const double* __restrict__ red,
+                                                              double count, int training, int C, long long n_vec,
+                                                              uint4* __restrict__ gx) {
+  __shared__ __align__(16) float sa[256], sb[256], smu[256], srs[256], sm1[256], sm2[256];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sa[i] = bn[i]; sb[i] = bn[C + i]; smu[i] = bn[2 * C + i]; srs[i] = bn[3 * C + i];
+    sm1[i] = training ? (float)(red[i] / count) : 0.f;
+    sm2[i] = training ? (float)(red[C + i] / count) : 0.f;
+  }
+  __syncthreads();
   const int vpp = C >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(e0 % vpp) << 3;
-  float a[8], b[8], mu[8], rs[8], m1[8], m2[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    a[i] = __ldg(bn + c0 + i); b[i] = __ldg(bn + C + c0 + i); mu[i] = __ldg(bn + 2 * C + c0 + i); rs[i] = __ldg(bn + 3 * C + c0 + i);
-    m1[i] = training ? (float)(red[c0 + i] / count) : 0.f;
-    m2[i] = training ? (float)(red[C + c0 + i] / count) : 0.f;
-  }
   for (long long e = e0; e < n_vec; e += 2 * stride) {
     const long long e2 = e + stride;
     const bool two = e2 < n_vec;
@@ -180,16 +188,16 @@ __global__ void __launch_bounds__(256) k_bn_gelu_bwd_apply(const uint4* __restri
     unpack8(ux0, fx); unpack8(ug0, fg);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], a[i], b[i]));
-      fx[i] = a[i] * (g1 - m1[i] - (fx[i] - mu[i]) * rs[i] * m2[i]);
+      const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], sa[c0 + i], sb[c0 + i]));
+      fx[i] = sa[c0 + i] * (g1 - sm1[c0 + i] - (fx[i] - smu[c0 + i]) * srs[c0 + i] * sm2[c0 + i]);
     }
     gx[e] = pack8(fx);
     if (two) {
       unpack8(ux1, fx); unpack8(ug1, fg);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], a[i], b[i]));
-        fx[i] = a[i] * (g1 - m1[i] - (fx[i] - mu[i]) * rs[i] * m2[i]);
+        const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], sa[c0 + i], sb[c0 + i]));
+        fx[i] = sa[c0 + i] * (g1 - sm1[c0 + i] - (fx[i] - smu[c0 + i]) * srs[c0 + i] * sm2[c0 + i]);
       }
       gx[e2] = pack8(fx);
     }
@@ -323,7 +331,7 @@ extern "C" int dfb_bn2d_finalize(const double* stats, double count, int C, int t
 extern "C" int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, void* stream_) {
   if (C % 8 || C > 256) { set_error("dfb_bn_gelu_apply: C must be a multiple of 8 and <= 256"); return DFB_ERR_ARG; }
   const long long n_vec = n_pix * (C >> 3);
-  k_bn_gelu_apply<<<grid_for_elems(n_vec, 512), 256, 0, (cudaStream_t)stream_>>>((const uint4*)x, bn, C, n_vec, (uint4*)y);
+  k_bn_gelu_apply<<<grid_for_elems(n_vec, 1024, 12), 256, 0, (cudaStream_t)stream_>>>((const uint4*)x, bn, C, n_vec, (uint4*)y);
   add_launches(1);
   return check_launch("dfb_bn_gelu_apply");
 }
@@ -335,7 +343,7 @@ extern "C" int dfb_bn_gelu_backward(const void* x, const void* gy, const float* 
   cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st);
   const long long n_vec = n_pix * (C >> 3);
   k_bn_gelu_bwd_reduce<<<grid_for_elems(n_vec, 512, 8), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, C, n_vec, red);
-  k_bn_gelu_bwd_apply<<<grid_for_elems(n_vec, 512), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, red, (double)n_pix,
+  k_bn_gelu_bwd_apply<<<grid_for_elems(n_vec, 512, 8), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, red, (double)n_pix,
                                                                   training, C, n_vec, (uint4*)gx);
   k_bn_param_grads<<<(C + 127) / 128, 128, 0, st>>>(red, bn, C, training, g_gamma, g_beta, g_bias);
   add_launches(3);
