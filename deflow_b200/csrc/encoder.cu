@@ -260,41 +260,33 @@ __global__ void __launch_bounds__(256) k_pfn_image(const int* __restrict__ count
 }
 
 // ---------------------------------------------------------------- backward
-// grid (X, F): each block works on pillars of one frame, warp per pillar, lane = channel.
-// PASS 0: A1[c] = sum_p gy^[p,c], A2[c] = sum_p gy^[p,c] * xhat[p,c]   (bwd_stats [F][2][32])
-// PASS 1: gW[c,k] += gy[p,c] * f[p,k] with the BatchNorm input gradient
-//         gy = a * (gy^ - A1/N - xhat * A2/N)   (training)   or   a * gy^   (eval)
-template <int PASS, bool BF16>
-__global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F, int HW, int training,
-                                                 PfnGeom G, const float* __restrict__ pt_xyz,
-                                                 const int* __restrict__ pil_coor, const int* __restrict__ pil_pix,
-                                                 const int* __restrict__ pil_start,
-                                                 const int* __restrict__ sorted_pt,
-                                                 const float* __restrict__ pil_mean,
-                                                 const float* __restrict__ weight,
-                                                 const float* __restrict__ bn_params,
-                                                 const void* __restrict__ grad_image, double* __restrict__ bwd_stats,
-                                                 double* __restrict__ grad_accum) {
-  __shared__ float red[8][PFN_C][PFN_K + 1];
+// ONE pass over the points.  With gy^[p,c] = relu'(.) * grad_pillar[q(p),c] / count_q the only sums that need the
+// points are, per frame and channel,   A1[c] = sum_p gy^[p,c]   and   T[c][k] = sum_p gy^[p,c] f[p,k]   (10 values):
+//   sum_p gy^ lin  = W_c . T_c                       (lin = W f is linear)
+//   sum_p xhat f_k = rstd (sum_j W_cj S2[j,k] - mean S1[k])          (S1, S2 = the forward's feature moments)
+// so  A2 = sum gy^ xhat = rstd (W_c . T_c - mean A1),  grad_gamma = A2,  grad_beta = A1  and
+//   grad_W[c,k] = a_c (T[c][k] - (A1/N) S1[k] - (A2/N) sum_p xhat f_k)      (training; eval: a_c T[c][k]).
+// grid (X, F): warp per pillar, lane = channel; bwd_acc layout [F][32][10] (double): A1 | T[9].
+template <bool BF16>
+__global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F, int HW, PfnGeom G,
+                                                 const float* __restrict__ pt_xyz, const int* __restrict__ pil_coor,
+                                                 const int* __restrict__ pil_pix, const int* __restrict__ pil_start,
+                                                 const int* __restrict__ sorted_pt, const float* __restrict__ pil_mean,
+                                                 const float* __restrict__ weight, const float* __restrict__ bn_params,
+                                                 const void* __restrict__ grad_image, double* __restrict__ bwd_acc) {
+  __shared__ float red[8][PFN_C][PFN_K + 2];
   const int f = blockIdx.y;
   const int q0 = counts[3 * F + 1 + f], q1 = counts[3 * F + 1 + f + 1];
-  const int n_pts = counts[f];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   float w[PFN_K];
 #pragma unroll
   for (int k = 0; k < PFN_K; ++k) w[k] = weight[lane * PFN_K + k];
   const float* bp = bn_params + (size_t)f * 4 * PFN_C;
-  const float a = bp[lane], b = bp[PFN_C + lane], mu = bp[2 * PFN_C + lane], rstd = bp[3 * PFN_C + lane];
-  float m1 = 0.f, m2 = 0.f;
-  if (PASS == 1 && training && n_pts > 0) {
-    m1 = (float)(bwd_stats[(size_t)f * 2 * PFN_C + lane] / (double)n_pts);
-    m2 = (float)(bwd_stats[(size_t)f * 2 * PFN_C + PFN_C + lane] / (double)n_pts);
-  }
-  float acc[PFN_K];
+  const float a = bp[lane], b = bp[PFN_C + lane];
+  float acc[PFN_K], a1 = 0.f;
 #pragma unroll
   for (int k = 0; k < PFN_K; ++k) acc[k] = 0.f;
-  float s1acc = 0.f, s2acc = 0.f;
   for (int q = q0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); q < q1; q += warps) {
     const int s0 = pil_start[q], s1 = pil_start[q + 1];
     const int pix = pil_pix[q];
@@ -303,6 +295,8 @@ __global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts,
     g = __fdiv_rn(g, (float)(s1 - s0));  // mean backward: grad / count (scatter_points_cuda_kernel.cuh:134-137)
     const float mx = pil_mean[3 * (size_t)q], my = pil_mean[3 * (size_t)q + 1], mz = pil_mean[3 * (size_t)q + 2];
     const int cz = pil_coor[3 * (size_t)q], cy = pil_coor[3 * (size_t)q + 1], cx = pil_coor[3 * (size_t)q + 2];
+    // within a pillar f[p,k] = xyz[p, k%3] - off[k]: accumulate the masked sums of (1, x, y, z) and expand once
+    float u0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
     for (int base = s0; base < s1; base += 32) {
       const int cnt = min(32, s1 - base);
       float lx = 0.f, ly = 0.f, lz = 0.f;
@@ -318,56 +312,70 @@ __global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts,
         float lin = 0.f;
 #pragma unroll
         for (int k = 0; k < PFN_K; ++k) lin = fmaf(w[k], fe[k], lin);
-        const float gyh = fmaf(lin, a, b) > 0.f ? g : 0.f;  // ReLU backward
-        const float xhat = (lin - mu) * rstd;
-        if (PASS == 0) {
-          s1acc += gyh;
-          s2acc = fmaf(gyh, xhat, s2acc);
-        } else {
-          const float gy = a * (gyh - m1 - xhat * m2);
-#pragma unroll
-          for (int k = 0; k < PFN_K; ++k) acc[k] = fmaf(gy, fe[k], acc[k]);
-        }
+        if (fmaf(lin, a, b) > 0.f) { u0 += 1.f; ux += x; uy += y; uz += z; }  // ReLU mask
       }
     }
+    // offsets of the three decoration groups: raw (0), cluster mean, pillar centre
+    const float ox = __fadd_rn(__fmul_rn((float)cx, G.vx), G.ox), oy = __fadd_rn(__fmul_rn((float)cy, G.vy), G.oy),
+                oz = __fadd_rn(__fmul_rn((float)cz, G.vz), G.oz);
+    a1 = fmaf(g, u0, a1);
+    acc[0] = fmaf(g, ux, acc[0]); acc[1] = fmaf(g, uy, acc[1]); acc[2] = fmaf(g, uz, acc[2]);
+    acc[3] = fmaf(g, ux - mx * u0, acc[3]); acc[4] = fmaf(g, uy - my * u0, acc[4]); acc[5] = fmaf(g, uz - mz * u0, acc[5]);
+    acc[6] = fmaf(g, ux - ox * u0, acc[6]); acc[7] = fmaf(g, uy - oy * u0, acc[7]); acc[8] = fmaf(g, uz - oz * u0, acc[8]);
   }
-  if (PASS == 0) {
-    red[wib][lane][0] = s1acc;
-    red[wib][lane][1] = s2acc;
-    __syncthreads();
-    if (threadIdx.x < 2 * PFN_C) {
-      const int c = threadIdx.x & 31, which = threadIdx.x >> 5;
-      double s = 0.0;
-      for (int i = 0; i < 8; ++i) s += (double)red[i][c][which];
-      atomicAdd(&bwd_stats[(size_t)f * 2 * PFN_C + which * PFN_C + c], s);
-    }
-  } else {
+  red[wib][lane][0] = a1;
 #pragma unroll
-    for (int k = 0; k < PFN_K; ++k) red[wib][lane][k] = acc[k];
-    __syncthreads();
-    for (int i = threadIdx.x; i < PFN_C * PFN_K; i += blockDim.x) {
-      const int c = i / PFN_K, k = i % PFN_K;
-      double s = 0.0;
-      for (int j = 0; j < 8; ++j) s += (double)red[j][c][k];
-      atomicAdd(&grad_accum[i], s);
-    }
+  for (int k = 0; k < PFN_K; ++k) red[wib][lane][1 + k] = acc[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < PFN_C * (PFN_K + 1); i += blockDim.x) {
+    const int c = i / (PFN_K + 1), k = i % (PFN_K + 1);
+    double s = 0.0;
+    for (int j = 0; j < 8; ++j) s += (double)red[j][c][k];
+    if (s != 0.0) atomicAdd(&bwd_acc[((size_t)f * PFN_C + c) * (PFN_K + 1) + k], s);
   }
 }
 
-__global__ void k_pfn_bwd_finalize(int F, const double* __restrict__ bwd_stats, const double* __restrict__ grad_accum,
-                                   float* __restrict__ grad_weight, float* __restrict__ grad_gamma,
-                                   float* __restrict__ grad_beta) {
-  const int t = threadIdx.x;
-  for (int i = t; i < PFN_C * PFN_K; i += blockDim.x) grad_weight[i] += (float)grad_accum[i];
-  if (t < PFN_C) {
-    double gb = 0.0, gg = 0.0;
-    for (int f = 0; f < F; ++f) {
-      gb += bwd_stats[(size_t)f * 2 * PFN_C + t];
-      gg += bwd_stats[(size_t)f * 2 * PFN_C + PFN_C + t];
+// thread = channel: the algebra above, in double, summed over the frames
+__global__ void k_pfn_bwd_finalize(const int* __restrict__ counts, int F, int training, const double* __restrict__ bwd_acc,
+                                   const double* __restrict__ mom, const float* __restrict__ bn_params,
+                                   const float* __restrict__ weight, float* __restrict__ grad_weight,
+                                   float* __restrict__ grad_gamma, float* __restrict__ grad_beta) {
+  const int c = threadIdx.x;
+  if (c >= PFN_C) return;
+  double w[PFN_K], gw[PFN_K], gg = 0.0, gb = 0.0;
+  for (int k = 0; k < PFN_K; ++k) { w[k] = (double)weight[c * PFN_K + k]; gw[k] = 0.0; }
+  for (int f = 0; f < F; ++f) {
+    const int n = counts[f];
+    if (n <= 0) continue;
+    const double* A = bwd_acc + ((size_t)f * PFN_C + c) * (PFN_K + 1);
+    const float* bp = bn_params + (size_t)f * 4 * PFN_C;
+    const double a = bp[c], mu = bp[2 * PFN_C + c], rstd = bp[3 * PFN_C + c];
+    const double A1 = A[0];
+    double wt = 0.0;
+    for (int k = 0; k < PFN_K; ++k) wt += w[k] * A[1 + k];
+    const double A2 = rstd * (wt - mu * A1);
+    gg += A2;
+    gb += A1;
+    if (training) {
+      const double* m = mom + (size_t)f * PFN_MOM;  // S1[9] | S2 upper triangle
+      double S2[PFN_K][PFN_K];
+      int o = PFN_K;
+      for (int j = 0; j < PFN_K; ++j)
+        for (int k = j; k < PFN_K; ++k) { S2[j][k] = m[o]; S2[k][j] = m[o]; ++o; }
+      const double m1 = A1 / n, m2 = A2 / n;
+      for (int k = 0; k < PFN_K; ++k) {
+        double ws2 = 0.0;
+        for (int j = 0; j < PFN_K; ++j) ws2 += w[j] * S2[j][k];
+        const double sxf = rstd * (ws2 - mu * m[k]);  // sum_p xhat[p,c] f[p,k]
+        gw[k] += a * (A[1 + k] - m1 * m[k] - m2 * sxf);
+      }
+    } else {
+      for (int k = 0; k < PFN_K; ++k) gw[k] += a * A[1 + k];
     }
-    grad_beta[t] += (float)gb;
-    grad_gamma[t] += (float)gg;
   }
+  for (int k = 0; k < PFN_K; ++k) grad_weight[c * PFN_K + k] += (float)gw[k];
+  grad_gamma[c] += (float)gg;
+  grad_beta[c] += (float)gb;
 }
 
 static PfnGeom make_geom(const dfb_pfn_args* a) {
@@ -424,19 +432,18 @@ extern "C" int dfb_pfn_backward(const dfb_pfn_bwd_args* b, void* stream_) {
   const int F = a->F, HW = a->H * a->W;
   const PfnGeom G = make_geom(a);
   const int sms = sm_count();
-  cudaMemsetAsync(b->bwd_stats, 0, sizeof(double) * (size_t)F * 2 * PFN_C, st);
-  cudaMemsetAsync(b->grad_accum, 0, sizeof(double) * (PFN_C * PFN_K + 64), st);
+  cudaMemsetAsync(b->bwd_stats, 0, sizeof(double) * (size_t)F * PFN_C * (PFN_K + 1), st);
   int bx = (sms * 4 + F - 1) / F;
   if (bx < 1) bx = 1;
   dim3 g(bx, F);
-#define DFB_BWD(PASS, BF)                                                                                          \
-  k_pfn_bwd<PASS, BF><<<g, 256, 0, st>>>(a->counts, F, HW, a->training, G, a->pt_xyz, a->pil_coor, a->pil_pix,      \
-                                         a->pil_start, a->sorted_pt, a->pil_mean, a->weight, a->bn_params,          \
-                                         b->grad_image, b->bwd_stats, b->grad_accum)
-  if (a->image_bf16) { DFB_BWD(0, true); DFB_BWD(1, true); }
-  else { DFB_BWD(0, false); DFB_BWD(1, false); }
-#undef DFB_BWD
-  k_pfn_bwd_finalize<<<1, 320, 0, st>>>(F, b->bwd_stats, b->grad_accum, b->grad_weight, b->grad_gamma, b->grad_beta);
-  add_launches(3);
+  if (a->image_bf16)
+    k_pfn_bwd<true><<<g, 256, 0, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pil_coor, a->pil_pix, a->pil_start, a->sorted_pt,
+                                       a->pil_mean, a->weight, a->bn_params, b->grad_image, b->bwd_stats);
+  else
+    k_pfn_bwd<false><<<g, 256, 0, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pil_coor, a->pil_pix, a->pil_start, a->sorted_pt,
+                                        a->pil_mean, a->weight, a->bn_params, b->grad_image, b->bwd_stats);
+  k_pfn_bwd_finalize<<<1, 32, 0, st>>>(a->counts, F, a->training, b->bwd_stats, a->stats, a->bn_params, a->weight,
+                                       b->grad_weight, b->grad_gamma, b->grad_beta);
+  add_launches(2);
   return check_launch("dfb_pfn_backward");
 }

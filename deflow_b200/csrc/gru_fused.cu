@@ -28,15 +28,14 @@ constexpr int GF_PAR_FLOATS = 384 + 32 + 96 + 3 + 192 + 64 + 5;  // bz|br|bq, b1
 constexpr int GF_BAR = GF_PAR + ((GF_PAR_FLOATS * 4 + 15) / 16) * 16;
 constexpr int GF_SMEM = GF_BAR + 64 + 1024;
 
-struct GruFusedMaps { CUtensorMap wzr, wq, w1; };
+struct GruFusedMaps { CUtensorMap wzr, wq, w1, h, x; };
 
 struct GruFusedParams {
   const __nv_bfloat16* h0;  // [n_pad,128] bf16 gathered pillar vectors
   const float* offs;    // [n,3]
   const float* par;     // bz[128] br[128] bq[128] b1[32] W2[3*32] b2[3] Woff[64*3] boff[64]
   int n, n_pad, iters;
-  __nv_bfloat16* hsave; // [iters+1][n_pad][128]: state entering iteration t, then the final state
-  __nv_bfloat16* xsave; // [n_pad][64]
+  int save;             // training: hsave [iters+1][n_pad][128] / xsave [n_pad][64] are written by TMA from the A tiles
   __nv_bfloat16* y1;    // [n_pad][32] head pre-activation (bias included)
   float* flow;          // [n,3]
 };
@@ -100,9 +99,17 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
       mbar_wait(bar_w, 0);
       uint32_t use_a = 0;
       const uint32_t a_h = smem_u32(smem + GF_AH), a_x = smem_u32(smem + GF_AX);
-      auto gemm = [&](uint32_t w_base, uint32_t w_chunk_bytes, int N, uint32_t dcol) {
+      // slot >= 0: the A_H tile holds bf16(h) entering iteration `slot` (or the final state): save it for the backward
+      auto gemm = [&](uint32_t w_base, uint32_t w_chunk_bytes, int N, uint32_t dcol, int row0, int slot, bool save_x) {
         mbar_wait(bar_a, use_a & 1); ++use_a;
         tc_fence_after();
+        const bool st = P.save && slot >= 0;
+        if (st) {
+          tma_store_3d(&maps.h, smem + GF_AH, 0, row0, slot);
+          tma_store_3d(&maps.h, smem + GF_AH + 16384, 64, row0, slot);
+          if (save_x) tma_store_3d(&maps.x, smem + GF_AX, 0, row0, 0);
+          tma_store_commit();
+        }
         const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -111,15 +118,18 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + dcol, ad + 2 * k, bd + 2 * k, idesc, (c | k) != 0);
         }
+        if (st) tma_store_wait_read();  // the workers overwrite the tile after the commit below
         umma_commit(bar_d);
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * 128;
         for (int it = 0; it < P.iters; ++it) {
-          gemm(smem_u32(smem + GF_WZR), 32768, 256, 0);    // z | r pre-activations -> columns 0..255
-          gemm(smem_u32(smem + GF_WQ), 16384, 128, 256);   // q pre-activation      -> columns 256..383
+          gemm(smem_u32(smem + GF_WZR), 32768, 256, 0, row0, it, it == 0);   // z | r pre-activations -> columns 0..255
+          gemm(smem_u32(smem + GF_WQ), 16384, 128, 256, row0, -1, false);    // q pre-activation      -> columns 256..383
         }
-        gemm(smem_u32(smem + GF_W1), 4096, 32, 384);       // MLP hidden layer      -> columns 384..415
+        gemm(smem_u32(smem + GF_W1), 4096, 32, 384, row0, P.iters, P.iters == 0);  // MLP hidden layer -> columns 384..415
       }
+      tma_store_wait_all();
     }
   } else {
     // ------------------------------------------------------------------ workers
@@ -145,13 +155,6 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
           f[i] = valid ? fmaf(o2, woff[3 * ch + 2], fmaf(o1, woff[3 * ch + 1], fmaf(o0, woff[3 * ch], boff[ch]))) : 0.f;
         }
         st_tile_chunk(tile_x, m, half * 4 + c8, f);
-        if (P.xsave && inpad) {
-          uint4 u;
-          __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pp[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-          *reinterpret_cast<uint4*>(P.xsave + (size_t)p * 64 + half * 32 + c8 * 8) = u;
-        }
       }
       float h[64];
       if (valid) {
@@ -167,17 +170,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
 #pragma unroll
         for (int i = 0; i < 64; ++i) h[i] = 0.f;
       }
-      auto publish_h = [&](int slot) {  // bf16(h) -> A tile (+ the saved copy for the backward pass)
+      auto publish_h = [&](int) {  // bf16(h) -> A tile (the control thread saves the tile by TMA when training)
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
-          st_tile_chunk(tile_h, m, c8, &h[c8 * 8]);
-          if (P.hsave && inpad) {
-            uint4 u;
-            __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&u);
+          float f[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pp[i] = __floats2bfloat162_rn(h[c8 * 8 + 2 * i], h[c8 * 8 + 2 * i + 1]);
-            *reinterpret_cast<uint4*>(P.hsave + ((size_t)slot * P.n_pad + p) * 128 + half * 64 + c8 * 8) = u;
-          }
+          for (int i = 0; i < 8; ++i) f[i] = valid ? h[c8 * 8 + i] : 0.f;
+          st_tile_chunk(tile_h, m, c8, f);
         }
       };
       auto signal_a = [&]() {
@@ -267,6 +266,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
 using namespace dfb;
 using namespace dfb::tc;
 
+static int make_rows_map(CUtensorMap* map, const void* base, int cols, int n_pad, int slabs);
+
 // wzr: bf16 [256][192] (Wz rows then Wr rows), wq: bf16 [128][192], w1: bf16 [32][192]; K order = [h(128), x(64)].
 extern "C" int dfb_gru_fused_forward(const void* h0, const float* offsets, const void* wzr, const void* wq,
                                      const void* w1, const float* par, int n, int n_pad, int iters, void* hsave,
@@ -291,7 +292,12 @@ extern "C" int dfb_gru_fused_forward(const void* h0, const float* offsets, const
     if ((rc = make_tensor_map_bf16(&maps.w1, w1, 2, d, str, b, 128))) return rc;
   }
   P.h0 = (const __nv_bfloat16*)h0; P.offs = offsets; P.par = par; P.n = n; P.n_pad = n_pad; P.iters = iters;
-  P.hsave = (__nv_bfloat16*)hsave; P.xsave = (__nv_bfloat16*)xsave; P.y1 = (__nv_bfloat16*)y1; P.flow = flow;
+  P.save = (hsave && xsave) ? 1 : 0;
+  P.y1 = (__nv_bfloat16*)y1; P.flow = flow;
+  if (P.save) {
+    if ((rc = make_rows_map(&maps.h, hsave, 128, n_pad, iters + 1))) return rc;
+    if ((rc = make_rows_map(&maps.x, xsave, 64, n_pad, 1))) return rc;
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_gru_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);

@@ -210,7 +210,7 @@ class _PillarFeatureNet(torch.autograd.Function):
         gw = torch.zeros_like(w)
         gg = torch.zeros_like(g)
         gb = torch.zeros_like(b)
-        bwd_stats = torch.empty((idx.F, 2, 32), dtype=torch.float64, device=dev)
+        bwd_stats = torch.empty((idx.F, 32, 10), dtype=torch.float64, device=dev)
         accum = torch.empty(32 * 9 + 64, dtype=torch.float64, device=dev)
         ba.grad_image, ba.grad_weight, ba.grad_gamma, ba.grad_beta = (grad_image.data_ptr(), gw.data_ptr(),
                                                                      gg.data_ptr(), gb.data_ptr())

@@ -157,8 +157,8 @@ typedef struct {
   float* grad_weight;       /* [32,9]  accumulated (+=) */
   float* grad_gamma;        /* [32]    accumulated (+=) */
   float* grad_beta;         /* [32]    accumulated (+=) */
-  double* bwd_stats;        /* workspace [F,2,32] */
-  double* grad_accum;       /* workspace [32*9 + 64] doubles, zeroed inside */
+  double* bwd_stats;        /* workspace [F,32,10] doubles: per frame and channel A1 | T[9] (zeroed inside) */
+  double* grad_accum;       /* unused (kept for ABI stability) */
 } dfb_pfn_bwd_args;
 int dfb_pfn_backward(const dfb_pfn_bwd_args* args, void* stream);
 
