@@ -260,11 +260,19 @@ def run_native(args):
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
+    from deflow_b200 import conv as tcconv
     ms, loss = timed(lambda: step(resident), args.steps)
     launches = _lib.launch_count() - l0
     clk = clocks.stop() if clocks else None
     pairs = args.batch * world
     value = pairs / (ms * 1e-3)
+    # the same K steps once more with CUDA events around every tensor-core convolution launch (per-kernel roofline);
+    # kept out of the `value` region because ~100 event pairs per step cost ~2 % of the step
+    conv_records = None
+    if rank == 0 and not os.environ.get("DFB_PROFILE"):
+        tcconv.TIMING = []
+    ms_ev, _ = timed(lambda: step(resident), args.steps)
+    conv_records, tcconv.TIMING = tcconv.TIMING, None
 
     # stage breakdown (one extra step with events; not part of `value`)
     stages = {}
@@ -308,10 +316,15 @@ def run_native(args):
     # end to end through the public API with HOST (pinned) inputs: H2D inside the timed region, loss read back
     e2e = None
     if not args.no_e2e:
+        from deflow_b200.feed import DeviceFeeder
+        feeder = DeviceFeeder(dev)
+        feeder.submit(host)
+
         def e2e_step():
-            b = synth.batch_to(host, dev, non_blocking=True)
+            b = feeder.get()          # H2D copy of THIS step's inputs (issued during the previous step, side stream)
+            feeder.submit(host)       # start the copy for the next step
             l = step(b)
-            return float(l)  # D2H read of the step's result (the summed loss)
+            return float(l)           # D2H read of the step's result (the summed loss)
         for _ in range(0 if os.environ.get("DFB_PROFILE") else 2):
             e2e_step()
         ems, _ = timed(e2e_step, args.steps)
@@ -332,11 +345,33 @@ def run_native(args):
         n0 = stages.get("valid_points_pc0", 0)
         dec_flop = (602688 if args.decoder == "gru" else 17344) * n0
         flops_step = 3 * (flop_pair * args.batch + dec_flop)
-        ach = flops_step / (ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                "note": f"whole-step algorithmic FLOPs (UNet 343.06 GFLOP/pair + decoder 602688 FLOP/pt, x3 for training) / step "
-                        f"time; peak = sustained bf16 ({peaks['source']}); all dense contractions are tcgen05 kernels"}
+        whole = flops_step / (ms * 1e-3) / 1e12
+        # per-kernel roofline of the tensor-core convolution families, measured live with CUDA events over the timed region
+        fam = {}
+        for name, fl, e0, e1 in conv_records or []:
+            d = fam.setdefault(name, [0, 0.0, 0.0])
+            d[0] += 1; d[1] += fl; d[2] += e0.elapsed_time(e1)
+        kernels = sorted(({"kernel": k, "launches_per_step": v[0] / args.steps, "ms_per_step": v[2] / args.steps,
+                           "avg_launch_ms": v[2] / v[0], "tflops": v[1] / (v[2] * 1e-3) / 1e12,
+                           "frac_of_sustained_peak": v[1] / (v[2] * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}
+                          for k, v in fam.items()), key=lambda r: -r["ms_per_step"])
+        if kernels:
+            top = kernels[0]
+            # ncu --set full (profiles/r01_ncu_full_main_kernels.txt): a 64->64 3x3 launch at 512^2 x 16 reads 0.537 GB and
+            # writes 0.487 GB of DRAM = its input + output tensors once (algorithmic bytes 1.07 GB): no re-reads.
+            traffic = 1.02e9 if top["kernel"] == "k_conv_igemm_halo<64>" else None
+            roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": top["frac_of_sustained_peak"], "traffic": traffic,
+                    "avg_launch_ms": top["avg_launch_ms"], "share_of_step": top["ms_per_step"] / ms,
+                    "note": f"dominant kernel family by time in the timed region (CUDA events around every launch); achieved = "
+                            f"algorithmic conv FLOPs / launch time; peak = sustained bf16 ({peaks['source']}). Whole step: "
+                            f"{whole:.0f} TFLOP/s on algorithmic FLOPs (UNet 343.06 GFLOP/pair + decoder 602688 FLOP/pt, x3) = "
+                            f"{whole / peaks['bf16_tflops_sustained']:.3f} of sustained peak",
+                    "whole_step_tflops": whole, "kernels": kernels[:8]}
+        else:
+            roof = {"bound": "tensor", "achieved": whole, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": whole / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "note": "whole-step algorithmic FLOPs / step time (fp32 parity mode: dense contractions in cuDNN/cuBLAS)"}
         cpu = None
         if not args.no_cpu_baseline:
             pts = args.cpu_points or args.points

@@ -13,6 +13,31 @@ from ._lib import ConvArgs, check
 from .ops import _ptr, _stream
 
 
+# Optional per-launch timing (bench.py): a list that receives (kernel name, algorithmic FLOPs, start event, end event)
+TIMING = None
+
+
+class _timed:
+    def __init__(self, name, flops, ref):
+        self.on = TIMING is not None
+        if self.on:
+            self.rec = (name, flops, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.rec[2].record(torch.cuda.current_stream(ref.device))
+            self.dev = ref.device
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.rec[3].record(torch.cuda.current_stream(self.dev))
+            TIMING.append(self.rec)
+
+
+def _halo(ksize, stride, cins):
+    return ksize == 3 and stride == 1 and all(c % 64 == 0 for c in cins)
+
+
 def _args(mode, n, H, W, ksize, stride, xs, cins, cout, w, bias=None, y=None, stats=None, cin_total=0, cin_off=0):
     a = ConvArgs()
     a.mode, a.n, a.H, a.W, a.ksize, a.stride = mode, n, H, W, ksize, stride
@@ -51,8 +76,12 @@ def conv2d_forward(xs: Sequence[torch.Tensor], w_fwd, bias, cout, ksize, stride,
         assert x.is_contiguous() and x.dtype == torch.bfloat16 and x.shape[:3] == xs[0].shape[:3]
     Ho, Wo = out_size(H, W, ksize, stride)
     y = torch.empty((n, Ho, Wo, cout), dtype=out_dtype, device=xs[0].device)
-    a = _args(0, n, H, W, ksize, stride, xs, [x.shape[3] for x in xs], cout, w_fwd, bias, y, stats)
-    check(_lib.lib().dfb_conv2d(C.byref(a), _stream(y)), "conv2d forward")
+    cins = [x.shape[3] for x in xs]
+    a = _args(0, n, H, W, ksize, stride, xs, cins, cout, w_fwd, bias, y, stats)
+    kc = 64 if all(c % 64 == 0 for c in cins) else 32
+    name = f"k_conv_igemm_halo<{cout}>" if _halo(ksize, stride, cins) else f"k_conv_igemm<{cout},{kc}>"
+    with _timed(name, 2.0 * n * Ho * Wo * cout * sum(cins) * ksize * ksize, y):
+        check(_lib.lib().dfb_conv2d(C.byref(a), _stream(y)), "conv2d forward")
     return y
 
 
@@ -62,7 +91,10 @@ def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize
     n, _, _, cout = gy.shape
     gx = torch.empty((n, H, W, cin), dtype=out_dtype, device=gy.device)
     a = _args(1, n, H, W, ksize, stride, [gy], [cin], cout, w_dgrad, None, gx, None, cin_total, cin_off)
-    check(_lib.lib().dfb_conv2d(C.byref(a), _stream(gy)), "conv2d dgrad")
+    kc = 64 if cout % 64 == 0 else 32
+    name = f"k_conv_igemm_halo<{cin}>" if _halo(ksize, stride, [cout]) else f"k_conv_igemm<{cin},{kc}>"
+    with _timed(name, 2.0 * n * gy.shape[1] * gy.shape[2] * cout * cin * ksize * ksize, gy):
+        check(_lib.lib().dfb_conv2d(C.byref(a), _stream(gy)), "conv2d dgrad")
     return gx
 
 
@@ -78,7 +110,10 @@ def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, gr
     if grad_w is None:
         grad_w = torch.empty((cout, ct, ksize, ksize), dtype=torch.float32, device=gy.device)
     a = _args(0, n, H, W, ksize, stride, xs, cins, cout, None, None, gy, None)
-    check(_lib.lib().dfb_conv2d_wgrad(C.byref(a), wacc.data_ptr(), grad_w.data_ptr(), int(acc), _stream(gy)), "conv2d wgrad")
+    ncol = max(cout, 64)
+    name = f"k_conv_wgrad_halo<{ncol}>" if (ksize == 3 and stride == 1) else f"k_conv_wgrad<{ncol}>"
+    with _timed(name, 2.0 * n * gy.shape[1] * gy.shape[2] * cout * ct * ksize * ksize, gy):
+        check(_lib.lib().dfb_conv2d_wgrad(C.byref(a), wacc.data_ptr(), grad_w.data_ptr(), int(acc), _stream(gy)), "conv2d wgrad")
     return grad_w
 
 

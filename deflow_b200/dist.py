@@ -40,28 +40,39 @@ def broadcast_module(module: torch.nn.Module, src: int = 0):
 
 
 class GradAverager:
-    """Flat-buffer gradient mean across ranks: grads are views into one contiguous fp32 buffer, so the
-    collective needs no packing copies."""
+    """Gradient mean across ranks with ONE collective on a flat fp32 buffer.
+
+    ``zero()`` drops the ``.grad`` tensors (autograd then *assigns* each gradient instead of launching an add kernel
+    per parameter); ``average()`` packs them into the flat buffer (one multi-tensor copy), all-reduces it when there
+    is more than one rank, and re-points every ``.grad`` at its slice, so clipping and the optimizer work on views."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
+        self.views, off = [], 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self.zero()
 
     def zero(self):
-        self.flat.zero_()
-        off = 0
-        for p in self.params:  # re-attach in case something replaced .grad
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
-                p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        for p in self.params:
+            p.grad = None
 
     def average(self):
+        src, dst = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
         w = world_size()
         if w > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)

@@ -32,6 +32,7 @@ def _worker(rank, world, port, out):
     ((net(xs) - ys) ** 2).sum().backward()      # per-rank SUM loss, like the trainer's summed per-sample losses
     avg.average()
     t = dd.max_over_ranks(float(rank + 1), "cpu")
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(avg.params, avg.views))  # grads are views of the flat buffer
     out[rank] = ([p.detach().clone() for p in net.parameters()], [p.grad.clone() for p in net.parameters()], t)
     dd.barrier()
     dist.destroy_process_group()
