@@ -85,17 +85,31 @@ def conv2d_forward(xs: Sequence[torch.Tensor], w_fwd, bias, cout, ksize, stride,
     return y
 
 
-def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize, stride, out_dtype=torch.bfloat16):
-    """gy [n,Ho,Wo,cout] bf16 -> grad of the input channel slice [cin_off, cin_off+cin): [n,H,W,cin]."""
+def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize, stride, out_dtype=torch.bfloat16,
+                 colsum: bool = False):
+    """gy [n,Ho,Wo,cout] bf16 -> grad of the input channel slice [cin_off, cin_off+cin): [n,H,W,cin].
+    colsum: also accumulate the per-channel sum of the result in the epilogue and attach it as ``gx._dfb_colsum`` --
+    it IS the bias gradient of the convolution that produced this input (saves a separate pass over gx)."""
     assert gy.is_contiguous() and gy.dtype == torch.bfloat16
     n, _, _, cout = gy.shape
     gx = torch.empty((n, H, W, cin), dtype=out_dtype, device=gy.device)
-    a = _args(1, n, H, W, ksize, stride, [gy], [cin], cout, w_dgrad, None, gx, None, cin_total, cin_off)
+    stats = torch.zeros((2, cin), dtype=torch.float64, device=gy.device) if colsum else None
+    a = _args(1, n, H, W, ksize, stride, [gy], [cin], cout, w_dgrad, None, gx, stats, cin_total, cin_off)
     kc = 64 if cout % 64 == 0 else 32
     name = f"k_conv_igemm_halo<{cin}>" if _halo(ksize, stride, [cout]) else f"k_conv_igemm<{cin},{kc}>"
     with _timed(name, 2.0 * n * gy.shape[1] * gy.shape[2] * cout * cin * ksize * ksize, gy):
         check(_lib.lib().dfb_conv2d(C.byref(a), _stream(gy)), "conv2d dgrad")
+    if colsum:
+        gx._dfb_colsum = stats[0]
     return gx
+
+
+def bias_grad(gy: torch.Tensor) -> torch.Tensor:
+    """sum over pixels of gy: taken from the producing data-gradient kernel's epilogue when available."""
+    cs = getattr(gy, "_dfb_colsum", None)
+    if cs is not None and cs.shape[0] == gy.shape[-1]:
+        return cs.float()
+    return channel_sum(gy)
 
 
 def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, grad_w: Optional[torch.Tensor] = None):
@@ -208,16 +222,16 @@ class _Conv(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         wd, *xs = ctx.saved_tensors
+        gb = bias_grad(gy)       # before .contiguous(): the attribute lives on the tensor the producer returned
         gy = gy.contiguous()
         k = ctx.k
         ct = ctx.wshape[1]
         gw = conv2d_wgrad(xs, gy, k, 1)
-        gb = channel_sum(gy)
         gxs, off = [None, None], 0
         for i, x in enumerate(xs):
             c = x.shape[3]
             if ctx.need[i]:
-                gxs[i] = conv2d_dgrad(gy, wd, x.shape[1], x.shape[2], c, ct, off, k, 1)
+                gxs[i] = conv2d_dgrad(gy, wd, x.shape[1], x.shape[2], c, ct, off, k, 1, colsum=True)
             off += c
         return gw, gb, gxs[0], gxs[1]
 
