@@ -196,3 +196,37 @@ def test_decoder_tensor_core_path_vs_fp32(kind):
     for k, g in f32[3].items():
         r = _rel(f16[3][k], g)
         assert r <= 0.1, (k, r)
+
+
+def test_model_bf16_eval_mode_and_ego_motion_key():
+    """Eval mode (running BatchNorm statistics) through the tensor-core path, and the optional `ego_motion` batch key
+    (OSF/src/models/deflow.py:66-67) giving the same result as pose0/pose1."""
+    fx, batch, cfg = load_fixture("deflow_small_gru_eval")
+    m = d.DeFlow(cfg["voxel_size"], cfg["range"], cfg["grid"], cfg["decoder"], 4, precision="bf16")
+    m.load_state_dict(orc.random_state(cfg["seed_state"], cfg["decoder"]), strict=True)
+    m = m.to(DEV).eval()
+    gb = batch_to(batch, DEV)
+    with torch.no_grad():
+        res = m(gb)
+        gb2 = dict(gb)
+        gb2["ego_motion"] = [orc.cal_pose0to1(batch["pose0"][b], batch["pose1"][b]).to(DEV) for b in range(len(batch["pose0"]))]
+        res2 = m(gb2)
+    for b in range(len(batch["pose0"])):
+        assert np.array_equal(res["pc0_valid_point_idxes"][b].cpu().numpy(), fx[f"pc0_idx_{b}"])
+        e = np.abs(res["flow"][b].float().cpu().numpy() - fx[f"flow_{b}"])
+        assert e.max() <= 0.05 and e.mean() <= 0.01, (e.max(), e.mean())
+        assert torch.equal(res2["pc0_valid_point_idxes"][b], res["pc0_valid_point_idxes"][b])
+        assert float((res2["flow"][b] - res["flow"][b]).abs().max()) <= 1e-2
+
+
+def test_fastflow3d_class_linear_decoder_fp32_parity():
+    fx, batch, cfg = load_fixture("deflow_small_linear")
+    m = d.FastFlow3D(cfg["voxel_size"], cfg["range"], cfg["grid"], precision="fp32")
+    m.load_state_dict(orc.random_state(cfg["seed_state"], "linear"), strict=True)
+    m = m.to(DEV).train()
+    gb = batch_to(batch, DEV)
+    res = m(gb)
+    for b in range(len(batch["pose0"])):
+        assert float(np.abs(res["flow"][b].detach().cpu().numpy() - fx[f"flow_{b}"]).max()) <= 2e-4
+    loss = d.training_step_loss(gb, res, "ff3dLoss")
+    assert abs(float(loss) - float(fx["loss_total"])) <= 2e-4 * max(1.0, abs(float(fx["loss_total"])))
