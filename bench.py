@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scatter", action="store_true", help="skip the config-5 scatter microbench")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scatter-only", action="store_true",
+                    help="run only the config-5 scatter microbench (BASELINE configs[4]) and print its JSON line")
     ap.add_argument("--cpu-points", type=int, default=None)
     return ap.parse_args()
 
@@ -169,9 +171,11 @@ def scatter_microbench(dev, peaks, frames=32, n=200000, grid=1024, iters=5):
     pts = pts.repeat(reps, 1, 1)[:frames].contiguous().to(dev)
     net = d.DynamicPillarFeatureNet(3, vs, RG, feat_channels=(32,), mode="avg").to(dev).train()
     gimg = None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    t_idx = t_fwd = t_bwd = 0.0
+    # all iterations are queued back to back (one synchronize at the end): the events time the device, not the host's
+    # launch latency after an idle GPU
+    evs = []
     for it in range(iters + 2):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         idx = ops.pillar_index(pts, vs, RG)
         ev[1].record()
@@ -181,9 +185,12 @@ def scatter_microbench(dev, peaks, frames=32, n=200000, grid=1024, iters=5):
             gimg = torch.randn_like(image)
         image.backward(gimg)
         ev[3].record()
-        torch.cuda.synchronize()
-        if it >= 2:
-            t_idx += ev[0].elapsed_time(ev[1]); t_fwd += ev[1].elapsed_time(ev[2]); t_bwd += ev[2].elapsed_time(ev[3])
+        evs.append(ev)
+        del image
+    torch.cuda.synchronize()
+    t_idx = t_fwd = t_bwd = 0.0
+    for ev in evs[2:]:
+        t_idx += ev[0].elapsed_time(ev[1]); t_fwd += ev[1].elapsed_time(ev[2]); t_bwd += ev[2].elapsed_time(ev[3])
     t_idx, t_fwd, t_bwd = t_idx / iters, t_fwd / iters, t_bwd / iters
     N = idx.pt_off(frames)
     M = idx.pil_off(frames)
@@ -218,6 +225,21 @@ def run_native(args):
     dd.init("nccl", dev)
     _lib.lib()  # fail loudly if the CUDA library is missing
     peaks = load_peaks()
+    if args.scatter_only:
+        if rank == 0:
+            sc = scatter_microbench(dev, peaks, iters=max(args.steps, 5))
+            tot = sum(sc["ms"].values())
+            print(json.dumps({"metric": "scatter_path_hbm_gbs", "value": sc["achieved_gbs"], "unit": "GB/s", "n_gpus": 1,
+                              "steps": max(args.steps, 5), "warmup": 2, "ms_per_step": tot, "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": sc["workload"]},
+                              "roofline": {"bound": "hbm", "achieved": sc["achieved_gbs"], "peak": peaks["hbm_gbs"],
+                                           "unit": "GB/s", "frac": sc["frac_of_hbm_peak"], "traffic": None},
+                              "scatter": sc}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     scale = args.grid / 512.0
     vs = [0.2 / scale, 0.2 / scale, 6]

@@ -58,7 +58,8 @@ class ConvArgs(C.Structure):
     _fields_ = [("mode", C.c_int), ("n", C.c_int), ("H", C.c_int), ("W", C.c_int), ("ksize", C.c_int),
                 ("stride", C.c_int), ("n_src", C.c_int), ("x", C.c_void_p * 2), ("cin", C.c_int * 2),
                 ("cin_total", C.c_int), ("cin_off", C.c_int), ("cout", C.c_int), ("w", C.c_void_p),
-                ("bias", C.c_void_p), ("y", C.c_void_p), ("y_fp32", C.c_int), ("stats", C.c_void_p)]
+                ("bias", C.c_void_p), ("y", C.c_void_p), ("y_fp32", C.c_int), ("stats", C.c_void_p),
+                ("x_lo", C.c_void_p * 2), ("split3", C.c_int)]
 
 
 def sources():
@@ -117,24 +118,25 @@ def _declare(lib):
         "dfb_decoder_gather": [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, i32, vp],
         "dfb_decoder_gather_backward": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
         "dfb_flow_loss": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
-        "dfb_conv_pack_weights": [vp, i32, i32, i32, vp, vp, vp],
+        "dfb_conv_pack_weights": [vp, i32, i32, i32, i32, vp, vp, vp],
+        "dfb_split_bf16x2": [vp, i64, vp, vp, vp],
         "dfb_conv2d": [C.POINTER(ConvArgs), vp],
         "dfb_conv2d_wgrad": [C.POINTER(ConvArgs), vp, vp, i32, vp],
         "dfb_bn2d_finalize": [vp, C.c_double, i32, i32, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp],
-        "dfb_bn_gelu_apply": [vp, vp, i32, i64, vp, vp],
-        "dfb_bn_gelu_backward": [vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp],
-        "dfb_channel_sum": [vp, i32, i64, vp, vp],
-        "dfb_upsample2x": [vp, i32, i32, i32, i32, vp, i32, vp],
-        "dfb_offset_encode": [vp, vp, vp, i32, i32, i32, vp, vp],
+        "dfb_bn_gelu_apply": [vp, vp, i32, i64, vp, i32, vp],
+        "dfb_bn_gelu_backward": [vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, i32, vp],
+        "dfb_channel_sum": [vp, i32, i64, vp, vp, i32, vp],
+        "dfb_upsample2x": [vp, i32, i32, i32, i32, vp, i32, i32, vp],
+        "dfb_offset_encode": [vp, vp, vp, i32, i32, i32, vp, i32, vp],
         "dfb_offset_encode_backward": [vp, vp, i32, i32, vp, vp, vp],
         "dfb_to_bf16_pad": [vp, i32, i32, i32, vp, vp],
-        "dfb_gru_rh": [vp, vp, i32, i32, vp, vp],
-        "dfb_gru_update": [vp, vp, vp, i32, i32, vp, vp, vp],
-        "dfb_gru_bwd1": [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp],
-        "dfb_gru_bwd2": [vp, vp, vp, i32, i32, vp, vp, vp],
-        "dfb_acc_bf16": [vp, vp, vp, i64, vp],
-        "dfb_head_out": [vp, vp, vp, i32, vp, vp],
-        "dfb_head_out_backward": [vp, vp, vp, i32, i32, vp, vp, vp, vp],
+        "dfb_gru_rh": [vp, vp, i32, i32, vp, i32, vp],
+        "dfb_gru_update": [vp, vp, vp, i32, i32, vp, vp, i32, vp],
+        "dfb_gru_bwd1": [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, vp],
+        "dfb_gru_bwd2": [vp, vp, vp, i32, i32, vp, vp, i32, vp],
+        "dfb_acc_bf16": [vp, vp, vp, i64, i32, vp],
+        "dfb_head_out": [vp, vp, vp, i32, vp, i32, vp],
+        "dfb_head_out_backward": [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp],
         "dfb_gru_fused_forward": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
         "dfb_gru_fused_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     }
@@ -148,7 +150,7 @@ def _declare(lib):
 EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size", "dfb_dynamic_voxelize_forward",
            "dfb_scatter_index", "dfb_scatter_reduce", "dfb_dynamic_point_to_voxel_backward", "dfb_index_workspace",
            "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_decoder_gather",
-           "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_conv2d", "dfb_conv2d_wgrad",
+           "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_split_bf16x2", "dfb_conv2d", "dfb_conv2d_wgrad",
            "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",
            "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",

@@ -38,7 +38,8 @@ def _halo(ksize, stride, cins):
     return ksize == 3 and stride == 1 and all(c % 64 == 0 for c in cins)
 
 
-def _args(mode, n, H, W, ksize, stride, xs, cins, cout, w, bias=None, y=None, stats=None, cin_total=0, cin_off=0):
+def _args(mode, n, H, W, ksize, stride, xs, cins, cout, w, bias=None, y=None, stats=None, cin_total=0, cin_off=0,
+          xs_lo=None):
     a = ConvArgs()
     a.mode, a.n, a.H, a.W, a.ksize, a.stride = mode, n, H, W, ksize, stride
     a.n_src = len(xs)
@@ -51,16 +52,37 @@ def _args(mode, n, H, W, ksize, stride, xs, cins, cout, w, bias=None, y=None, st
     a.y = _ptr(y)
     a.y_fp32 = int(y is not None and y.dtype == torch.float32)
     a.stats = _ptr(stats)
+    a.split3 = int(xs_lo is not None)
+    if xs_lo is not None:
+        for i, x in enumerate(xs_lo):
+            a.x_lo[i] = x.data_ptr()
     return a
 
 
-def pack_weights(w: torch.Tensor, need_dgrad: bool = True):
-    """[Cout,Cin,k,k] fp32 -> (w_fwd bf16 [Cout, k*k*Cin], w_dgrad bf16 [Cin, k*k*Cout])."""
+def split(x: torch.Tensor):
+    """fp32 tensor -> (hi, lo) bf16 pair with hi + lo = x to ~16 significant bits: the operands of the split-precision
+    ("bf16x3") parity mode.  Cached on the tensor (an activation feeds up to three convolutions)."""
+    hit = getattr(x, "_dfb_split", None)
+    if hit is not None and hit[2] == x._version:
+        return hit[0], hit[1]
+    xc = x.detach().contiguous()
+    hi = torch.empty(xc.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    check(_lib.lib().dfb_split_bf16x2(xc.data_ptr(), xc.numel(), hi.data_ptr(), lo.data_ptr(), _stream(x)), "split_bf16x2")
+    x._dfb_split = (hi, lo, x._version)
+    return hi, lo
+
+
+def pack_weights(w: torch.Tensor, need_dgrad: bool = True, split3: bool = False):
+    """[Cout,Cin,k,k] fp32 -> (w_fwd bf16 [Cout, k*k*Cin], w_dgrad bf16 [Cin, k*k*Cout]); with split3 every row holds
+    its hi part followed by its lo part (rows twice as long)."""
     w = w.detach().contiguous().float()
     cout, cin, k, _ = w.shape
-    wf = torch.empty((cout, k * k * cin), dtype=torch.bfloat16, device=w.device)
-    wd = torch.empty((cin, k * k * cout), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
-    check(_lib.lib().dfb_conv_pack_weights(w.data_ptr(), cout, cin, k, wf.data_ptr(), _ptr(wd), _stream(w)), "pack_weights")
+    m = 2 if split3 else 1
+    wf = torch.empty((cout, m * k * k * cin), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((cin, m * k * k * cout), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
+    check(_lib.lib().dfb_conv_pack_weights(w.data_ptr(), cout, cin, k, int(split3), wf.data_ptr(), _ptr(wd), _stream(w)),
+          "pack_weights")
     return wf, wd
 
 
@@ -72,12 +94,18 @@ def out_size(H, W, ksize, stride):
 def conv2d_forward(xs: Sequence[torch.Tensor], w_fwd, bias, cout, ksize, stride, stats=None, out_dtype=torch.bfloat16):
     """xs: 1-2 NHWC bf16 tensors [n,H,W,c_i] (concatenated along channels) -> y [n,Ho,Wo,cout]."""
     n, H, W, _ = xs[0].shape
+    s3 = xs[0].dtype == torch.float32   # parity mode: fp32 activations, (hi, lo) operand pairs, fp32 output
     for x in xs:
-        assert x.is_contiguous() and x.dtype == torch.bfloat16 and x.shape[:3] == xs[0].shape[:3]
+        assert x.is_contiguous() and x.dtype == xs[0].dtype and x.shape[:3] == xs[0].shape[:3]
+    xs_lo = None
+    if s3:
+        pairs = [split(x) for x in xs]
+        xs, xs_lo = [p[0] for p in pairs], [p[1] for p in pairs]
+        out_dtype = torch.float32
     Ho, Wo = out_size(H, W, ksize, stride)
     y = torch.empty((n, Ho, Wo, cout), dtype=out_dtype, device=xs[0].device)
     cins = [x.shape[3] for x in xs]
-    a = _args(0, n, H, W, ksize, stride, xs, cins, cout, w_fwd, bias, y, stats)
+    a = _args(0, n, H, W, ksize, stride, xs, cins, cout, w_fwd, bias, y, stats, xs_lo=xs_lo)
     kc = 64 if all(c % 64 == 0 for c in cins) else 32
     name = f"k_conv_igemm_halo<{cout}>" if _halo(ksize, stride, cins) else f"k_conv_igemm<{cout},{kc}>"
     with _timed(name, 2.0 * n * Ho * Wo * cout * sum(cins) * ksize * ksize, y):
@@ -90,11 +118,15 @@ def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize
     """gy [n,Ho,Wo,cout] bf16 -> grad of the input channel slice [cin_off, cin_off+cin): [n,H,W,cin].
     colsum: also accumulate the per-channel sum of the result in the epilogue and attach it as ``gx._dfb_colsum`` --
     it IS the bias gradient of the convolution that produced this input (saves a separate pass over gx)."""
-    assert gy.is_contiguous() and gy.dtype == torch.bfloat16
+    assert gy.is_contiguous()
     n, _, _, cout = gy.shape
+    gy_lo = None
+    if gy.dtype == torch.float32:
+        gy, lo = split(gy)
+        gy_lo, out_dtype = [lo], torch.float32
     gx = torch.empty((n, H, W, cin), dtype=out_dtype, device=gy.device)
     stats = torch.zeros((2, cin), dtype=torch.float64, device=gy.device) if colsum else None
-    a = _args(1, n, H, W, ksize, stride, [gy], [cin], cout, w_dgrad, None, gx, stats, cin_total, cin_off)
+    a = _args(1, n, H, W, ksize, stride, [gy], [cin], cout, w_dgrad, None, gx, stats, cin_total, cin_off, xs_lo=gy_lo)
     kc = 64 if cout % 64 == 0 else 32
     name = f"k_conv_igemm_halo<{cin}>" if _halo(ksize, stride, [cout]) else f"k_conv_igemm<{cin},{kc}>"
     with _timed(name, 2.0 * n * gy.shape[1] * gy.shape[2] * cout * cin * ksize * ksize, gy):
@@ -114,6 +146,14 @@ def bias_grad(gy: torch.Tensor) -> torch.Tensor:
 
 def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, grad_w: Optional[torch.Tensor] = None):
     """-> grad_w fp32 in torch layout [cout, sum(c_i), k, k]."""
+    if gy.dtype == torch.float32:
+        # split precision: x_hi*gy_hi + x_hi*gy_lo + x_lo*gy_hi accumulated into the same fp32 gradient
+        pairs = [split(x) for x in xs]
+        gh, gl = split(gy)
+        hi, lo = [p[0] for p in pairs], [p[1] for p in pairs]
+        grad_w = conv2d_wgrad(hi, gh, ksize, stride, grad_w)
+        grad_w = conv2d_wgrad(hi, gl, ksize, stride, grad_w)
+        return conv2d_wgrad(lo, gh, ksize, stride, grad_w)
     n, H, W, _ = xs[0].shape
     cout = gy.shape[3]
     cins = [x.shape[3] for x in xs]
@@ -146,8 +186,8 @@ def bn2d_finalize(stats, count, training, eps, momentum, gamma, beta, running_me
 def bn_gelu_apply(x, bn):
     y = torch.empty_like(x)
     Cn = x.shape[-1]
-    check(_lib.lib().dfb_bn_gelu_apply(x.data_ptr(), bn.data_ptr(), Cn, x.numel() // Cn, y.data_ptr(), _stream(x)),
-          "bn_gelu_apply")
+    check(_lib.lib().dfb_bn_gelu_apply(x.data_ptr(), bn.data_ptr(), Cn, x.numel() // Cn, y.data_ptr(),
+                                       int(x.dtype == torch.float32), _stream(x)), "bn_gelu_apply")
     return y
 
 
@@ -157,14 +197,15 @@ def bn_gelu_backward(x, gy, bn, training, g_gamma, g_beta, g_bias):
     red = torch.empty(2 * Cn, dtype=torch.float64, device=x.device)
     check(_lib.lib().dfb_bn_gelu_backward(x.data_ptr(), gy.data_ptr(), bn.data_ptr(), Cn, x.numel() // Cn, int(training),
                                           red.data_ptr(), gx.data_ptr(), g_gamma.data_ptr(), g_beta.data_ptr(),
-                                          _ptr(g_bias), _stream(x)), "bn_gelu_backward")
+                                          _ptr(g_bias), int(x.dtype == torch.float32), _stream(x)), "bn_gelu_backward")
     return gx
 
 
 def channel_sum(g):
     Cn = g.shape[-1]
     out = torch.zeros(Cn, dtype=torch.float32, device=g.device)
-    check(_lib.lib().dfb_channel_sum(g.data_ptr(), Cn, g.numel() // Cn, out.data_ptr(), _stream(g)), "channel_sum")
+    check(_lib.lib().dfb_channel_sum(g.data_ptr(), Cn, g.numel() // Cn, out.data_ptr(), None,
+                                     int(g.dtype == torch.float32), _stream(g)), "channel_sum")
     return out
 
 
@@ -175,33 +216,34 @@ def upsample2x(x, backward=False):
         out = torch.empty((n, h, w, Cn), dtype=x.dtype, device=x.device)
     else:
         out = torch.empty((n, 2 * h, 2 * w, Cn), dtype=x.dtype, device=x.device)
-    check(_lib.lib().dfb_upsample2x(x.data_ptr(), n, h, w, Cn, out.data_ptr(), int(backward), _stream(x)), "upsample2x")
+    check(_lib.lib().dfb_upsample2x(x.data_ptr(), n, h, w, Cn, out.data_ptr(), int(backward),
+                                    int(x.dtype == torch.float32), _stream(x)), "upsample2x")
     return out
 
 
 # ----------------------------------------------------------------------------------------------
 # autograd wiring
 # ----------------------------------------------------------------------------------------------
-_PACK_CACHE = {}
-
-
-def packed(w: torch.Tensor):
-    """bf16 GEMM operands of a weight, re-packed only when the parameter changed (optimizer step)."""
-    key = id(w)
-    hit = _PACK_CACHE.get(key)
+def packed(w: torch.Tensor, split3: bool = False):
+    """bf16 GEMM operands of a weight, re-packed only when the parameter changed (optimizer step / load_state_dict).
+    The cache lives ON the parameter object (not in a table keyed by id(): a freed parameter's id, version and
+    data_ptr can all be reused by a new model's parameter)."""
+    name = "_dfb_packed3" if split3 else "_dfb_packed"
+    hit = getattr(w, name, None)
     if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
         return hit[2], hit[3]
-    wf, wd = pack_weights(w)
-    _PACK_CACHE[key] = (w._version, w.data_ptr(), wf, wd)
+    wf, wd = pack_weights(w, True, split3)
+    setattr(w, name, (w._version, w.data_ptr(), wf, wd))
     return wf, wd
 
 
-def packed_raw(w4: torch.Tensor):
+def packed_raw(w4: torch.Tensor, split3: bool = False):
     """Packed operands of a derived (non-parameter) weight tensor: cached on the tensor object itself."""
-    hit = getattr(w4, "_dfb_packed", None)
+    name = "_dfb_packed3" if split3 else "_dfb_packed"
+    hit = getattr(w4, name, None)
     if hit is None:
-        hit = pack_weights(w4)
-        w4._dfb_packed = hit
+        hit = pack_weights(w4, True, split3)
+        setattr(w4, name, hit)
     return hit
 
 
@@ -212,7 +254,7 @@ class _Conv(torch.autograd.Function):
     def forward(ctx, w, b, x0, x1):
         xs = [x0] if x1 is None else [x0, x1]
         k = w.shape[2]
-        wf, wd = packed(w)
+        wf, wd = packed(w, x0.dtype == torch.float32)
         y = conv2d_forward(xs, wf, b.detach().float().contiguous(), w.shape[0], k, 1)
         ctx.save_for_backward(wd, *xs)
         ctx.k, ctx.wshape = k, tuple(w.shape)
@@ -245,7 +287,7 @@ class _ConvBnGelu(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, stride, training, eps, momentum):
-        wf, wd = packed(w)
+        wf, wd = packed(w, x.dtype == torch.float32)
         cout = w.shape[0]
         stats = torch.zeros((2, cout), dtype=torch.float64, device=x.device) if training else None
         raw = conv2d_forward([x], wf, b.detach().float().contiguous(), cout, 3, stride, stats)

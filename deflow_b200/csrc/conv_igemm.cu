@@ -51,8 +51,8 @@ int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uin
 
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_H = 16, TILE_W = 8, TILE_M = TILE_H * TILE_W;  // 128 output pixels per tile
-constexpr int MAX_STEPS = 80;
-constexpr int MAX_AMAPS = 4;
+constexpr int MAX_STEPS = 224;
+constexpr int MAX_AMAPS = 8;   // 4 sources / parity planes x (hi, lo) in split-precision mode
 constexpr int IGEMM_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..5 epilogue
 
 struct KStep {
@@ -447,16 +447,43 @@ static int halo_mode() {
 // Weight packing: torch [Cout, Cin, kh, kw] fp32 -> bf16 GEMM-B matrices, K contiguous.
 //   forward:  Wf[co][tap * Cin + ci]            (tap = ky * kw + kx)
 //   dgrad:    Wd[ci][tap * Cout + co]           (same tap numbering; the step table flips the shifts)
-__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ w, int Cout, int Cin, int taps,
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ w, int Cout, int Cin, int taps, int split3,
                                                       __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  // split3: every row holds its hi part followed by its lo part (lo = bf16(w - hi)): rows are 2K long
   const long long total = (long long)Cout * Cin * taps;
+  const long long kf = (long long)taps * Cin, kd = (long long)taps * Cout;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(e % taps);
     const int ci = (int)((e / taps) % Cin);
     const int co = (int)(e / ((long long)taps * Cin));
-    const __nv_bfloat16 v = __float2bfloat16_rn(w[e]);
-    if (wf) wf[((long long)co * taps + t) * Cin + ci] = v;
-    if (wd) wd[((long long)ci * taps + t) * Cout + co] = v;
+    const float f = w[e];
+    const __nv_bfloat16 v = __float2bfloat16_rn(f);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(f - __bfloat162float(v));
+    if (wf) {
+      const long long o = (long long)co * kf * (split3 ? 2 : 1) + (long long)t * Cin + ci;
+      wf[o] = v;
+      if (split3) wf[o + kf] = lo;
+    }
+    if (wd) {
+      const long long o = (long long)ci * kd * (split3 ? 2 : 1) + (long long)t * Cout + co;
+      wd[o] = v;
+      if (split3) wd[o + kd] = lo;
+    }
+  }
+}
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo = x to ~16 significant bits
+__global__ void __launch_bounds__(256) k_split_bf16x2(const float4* __restrict__ x, long long n4, uint2* __restrict__ hi,
+                                                      uint2* __restrict__ lo) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + e);
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    uint2 a, b;
+    a.x = *reinterpret_cast<const unsigned*>(&h0); a.y = *reinterpret_cast<const unsigned*>(&h1);
+    b.x = *reinterpret_cast<const unsigned*>(&l0); b.y = *reinterpret_cast<const unsigned*>(&l1);
+    hi[e] = a; lo[e] = b;
   }
 }
 
@@ -491,13 +518,23 @@ static int dispatch_igemm(int N, int KC, const IgemmMaps& maps, const IgemmParam
 using namespace dfb;
 using namespace dfb::tc;
 
-extern "C" int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, void* w_fwd, void* w_dgrad,
+extern "C" int dfb_split_bf16x2(const float* x, long long n, void* hi, void* lo, void* stream_) {
+  if (n % 4) { set_error("dfb_split_bf16x2: element count must be a multiple of 4"); return DFB_ERR_ARG; }
+  if (n == 0) return DFB_OK;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  k_split_bf16x2<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const float4*)x, n / 4, (uint2*)hi, (uint2*)lo);
+  add_launches(1);
+  return check_launch("dfb_split_bf16x2");
+}
+
+extern "C" int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, int split3, void* w_fwd, void* w_dgrad,
                                      void* stream_) {
   if (cout <= 0 || cin <= 0 || (ksize != 1 && ksize != 3)) { set_error("dfb_conv_pack_weights: bad sizes"); return DFB_ERR_ARG; }
   const long long total = (long long)cout * cin * ksize * ksize;
   long long blocks = (total + 255) / 256;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  k_pack_weights<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(w, cout, cin, ksize * ksize, (__nv_bfloat16*)w_fwd,
+  k_pack_weights<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(w, cout, cin, ksize * ksize, split3, (__nv_bfloat16*)w_fwd,
                                                                  (__nv_bfloat16*)w_dgrad);
   add_launches(1);
   return check_launch("dfb_conv_pack_weights");
@@ -528,9 +565,33 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
   P.bias = a->bias;
   P.stats = a->stats;
   int N, KC, rc, nsteps = 0;
+  // split-precision ("bf16x3") mode: every operand is a (hi, lo) bf16 pair, x = hi + lo to ~16 significant bits; the
+  // K loop runs hi*hi + hi*lo + lo*hi into the same fp32 accumulator.  lo tensor maps live at index + 4, the lo half of
+  // the packed weights at K offset k_hi.
+  const int S3 = a->split3 ? 1 : 0;
+  int src_slot = 0;  // which of a->x / a->x_lo the map being built belongs to
+  auto mk_a = [&](int idx, const void* base, const uint64_t* dims, const uint64_t* str, const uint32_t* bx, int sw) -> int {
+    int r = make_tensor_map_bf16(&maps.a[idx], base, 4, dims, str, bx, sw);
+    if (r || !S3) return r;
+    const char* lo = (const char*)a->x_lo[src_slot] + ((const char*)base - (const char*)a->x[src_slot]);
+    return make_tensor_map_bf16(&maps.a[idx + 4], lo, 4, dims, str, bx, sw);
+  };
+  auto expand3 = [&](int n, int k_hi) -> int {
+    if (!S3) return n;
+    if (3 * n > MAX_STEPS) return -1;
+    for (int i = n - 1; i >= 0; --i) {
+      const KStep st0 = P.steps[i];
+      KStep hl = st0, lh = st0;
+      hl.wk = (int16_t)(st0.wk + k_hi);
+      lh.map = (int8_t)(st0.map + 4);
+      P.steps[3 * i] = st0; P.steps[3 * i + 1] = hl; P.steps[3 * i + 2] = lh;
+    }
+    return 3 * n;
+  };
 
   if (a->mode == 0) {
     // ---------------------------------------------------------------- forward
+    const int K_HI = taps * cin_total;
     N = a->cout;
     KC = 64;
     for (int i = 0; i < a->n_src; ++i) if (a->cin[i] % 64 != 0) KC = 32;
@@ -554,14 +615,16 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
         const uint64_t C = a->cin[i];
         const uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)a->n};
         const uint64_t str[3] = {C * 2, C * 2 * W, C * 2 * W * H};
-        if ((rc = make_tensor_map_bf16(&maps.a[i], a->x[i], 4, dims, str, hbox, 128))) return rc;
+        src_slot = i;
+        if ((rc = mk_a(i, a->x[i], dims, str, hbox, 128))) return rc;
         for (int c0 = 0; c0 < a->cin[i]; c0 += 64) P.steps[nsteps++] = KStep{(int8_t)i, 0, 0, 0, (int16_t)c0, (int16_t)(coff + c0)};
         coff += a->cin[i];
       }
-      const uint64_t bd[2] = {(uint64_t)taps * cin_total, (uint64_t)a->cout};
-      const uint64_t bs[1] = {(uint64_t)taps * cin_total * 2};
+      const uint64_t bd[2] = {(uint64_t)taps * cin_total * (1 + S3), (uint64_t)a->cout};
+      const uint64_t bs[1] = {(uint64_t)taps * cin_total * 2 * (1 + S3)};
       const uint32_t bb[2] = {64, (uint32_t)N};
       if ((rc = make_tensor_map_bf16(&maps.b, a->w, 2, bd, bs, bb, 128))) return rc;
+      if ((nsteps = expand3(nsteps, K_HI)) < 0) { set_error("dfb_conv2d: too many K steps"); return DFB_ERR_UNSUPPORTED; }
       P.nsteps = nsteps;
       P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
       P.num_tiles = P.tiles_x * P.tiles_y * a->n;
@@ -572,7 +635,8 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
         const uint64_t C = a->cin[i];
         const uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)a->n};
         const uint64_t str[3] = {C * 2, C * 2 * W, C * 2 * W * H};
-        if ((rc = make_tensor_map_bf16(&maps.a[i], a->x[i], 4, dims, str, box, KC * 2))) return rc;
+        src_slot = i;
+        if ((rc = mk_a(i, a->x[i], dims, str, box, KC * 2))) return rc;
       }
       for (int t = 0; t < taps; ++t) {
         const int dy = k == 3 ? t / 3 - 1 : 0, dx = k == 3 ? t % 3 - 1 : 0;
@@ -595,7 +659,7 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
           const uint64_t dims[4] = {C, (uint64_t)W / 2, (uint64_t)H / 2, (uint64_t)a->n};
           const uint64_t str[3] = {C * 2 * 2, C * 2 * W * 2, C * 2 * W * H};
           const char* base = (const char*)a->x[0] + ((size_t)py * W + px) * C * 2;
-          if ((rc = make_tensor_map_bf16(&maps.a[py * 2 + px], base, 4, dims, str, box, KC * 2))) return rc;
+          if ((rc = mk_a(py * 2 + px, base, dims, str, box, KC * 2))) return rc;
         }
       for (int t = 0; t < taps; ++t) {
         const int ky = k == 3 ? t / 3 : 1, kx = k == 3 ? t % 3 : 1;
@@ -604,10 +668,11 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
           P.steps[nsteps++] = KStep{(int8_t)(py * 2 + px), (int8_t)dy, (int8_t)dx, 0, (int16_t)c0, (int16_t)(t * cin_total + c0)};
       }
     }
-    const uint64_t bd[2] = {(uint64_t)taps * cin_total, (uint64_t)a->cout};
-    const uint64_t bs[1] = {(uint64_t)taps * cin_total * 2};
+    const uint64_t bd[2] = {(uint64_t)taps * cin_total * (1 + S3), (uint64_t)a->cout};
+    const uint64_t bs[1] = {(uint64_t)taps * cin_total * 2 * (1 + S3)};
     const uint32_t bb[2] = {(uint32_t)KC, (uint32_t)N};
     if ((rc = make_tensor_map_bf16(&maps.b, a->w, 2, bd, bs, bb, KC * 2))) return rc;
+    if ((nsteps = expand3(nsteps, K_HI)) < 0) { set_error("dfb_conv2d: too many K steps"); return DFB_ERR_UNSUPPORTED; }
     P.nsteps = nsteps;
     P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
     P.num_tiles = P.tiles_x * P.tiles_y * a->n;
@@ -619,6 +684,7 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
     // source = gy [n, Ho, Wo, cout]; output gx [n, H, W, cin_slice]; weights Wd[ci][tap*cout + co] (rows = all cin_total
     // channels; the slice starts at row cin_off).
     const int cout = a->cout, cin = a->cin[0];
+    const int K_HI = taps * cout;
     N = cin;
     KC = cout % 64 == 0 ? 64 : 32;
     if (cout % KC != 0) { set_error("dfb_conv2d dgrad: output channels must be multiples of 32"); return DFB_ERR_UNSUPPORTED; }
@@ -626,11 +692,11 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
     const uint64_t dims[4] = {C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)a->n};
     const uint64_t str[3] = {C * 2, C * 2 * Wo, C * 2 * Wo * Ho};
     const uint32_t box[4] = {(uint32_t)KC, TILE_W, TILE_H, 1};
-    if ((rc = make_tensor_map_bf16(&maps.a[0], a->x[0], 4, dims, str, box, KC * 2))) return rc;
-    const uint64_t bd[2] = {(uint64_t)taps * cout, (uint64_t)cin};
-    const uint64_t bs[1] = {(uint64_t)taps * cout * 2};
+    if ((rc = mk_a(0, a->x[0], dims, str, box, KC * 2))) return rc;
+    const uint64_t bd[2] = {(uint64_t)taps * cout * (1 + S3), (uint64_t)cin};
+    const uint64_t bs[1] = {(uint64_t)taps * cout * 2 * (1 + S3)};
     const uint32_t bb[2] = {(uint32_t)KC, (uint32_t)N};
-    const char* wbase = (const char*)a->w + (size_t)a->cin_off * taps * cout * 2;
+    const char* wbase = (const char*)a->w + (size_t)a->cin_off * taps * cout * 2 * (1 + S3);
     if ((rc = make_tensor_map_bf16(&maps.b, wbase, 2, bd, bs, bb, KC * 2))) return rc;
     P.out_img = (long long)H * W * cin; P.out_row = (long long)W * cin; P.out_pix = cin;
     if (s == 1 && k == 3 && KC == 64 && halo_mode() > 0) {
@@ -642,8 +708,9 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
       P.halo_flip = 1;                       // gx[y, x] = sum_t W[t]^T gy[y - dy_t, x - dx_t]
       P.tap_k_stride = cout;
       const uint32_t hbox[4] = {64, (uint32_t)P.halo_pitch, 18, 1};
-      if ((rc = make_tensor_map_bf16(&maps.a[0], a->x[0], 4, dims, str, hbox, 128))) return rc;
+      if ((rc = mk_a(0, a->x[0], dims, str, hbox, 128))) return rc;
       for (int c0 = 0; c0 < cout; c0 += 64) P.steps[nsteps++] = KStep{0, 0, 0, 0, (int16_t)c0, (int16_t)c0};
+      if ((nsteps = expand3(nsteps, K_HI)) < 0) { set_error("dfb_conv2d: too many K steps"); return DFB_ERR_UNSUPPORTED; }
       P.nsteps = nsteps;
       P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
       P.num_tiles = P.tiles_x * P.tiles_y * a->n;
@@ -657,6 +724,7 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
         for (int c0 = 0; c0 < cout; c0 += KC)
           P.steps[nsteps++] = KStep{0, (int8_t)(-dy), (int8_t)(-dx), 0, (int16_t)c0, (int16_t)(t * cout + c0)};
       }
+      if ((nsteps = expand3(nsteps, K_HI)) < 0) { set_error("dfb_conv2d: too many K steps"); return DFB_ERR_UNSUPPORTED; }
       P.nsteps = nsteps;
       P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
       P.num_tiles = P.tiles_x * P.tiles_y * a->n;
@@ -680,6 +748,7 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
         P.Ht = H / 2; P.Wt = W / 2; P.sy = P.sx = 2; P.oy = py; P.ox = px;
         P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
         P.num_tiles = P.tiles_x * P.tiles_y * a->n;
+        if (nsteps > 0 && (nsteps = expand3(nsteps, K_HI)) < 0) { set_error("dfb_conv2d: too many K steps"); return DFB_ERR_UNSUPPORTED; }
         P.nsteps = nsteps;
         if (nsteps == 0) {  // 1x1 stride-2: planes that no tap reaches get zero gradient
           set_error("dfb_conv2d dgrad: 1x1 stride-2 is not on the DeFlow path"); return DFB_ERR_UNSUPPORTED;

@@ -26,12 +26,35 @@ __device__ __forceinline__ uint4 g_pack8(const float* f) {
 }
 __device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+// 8 consecutive values of vector index e: bf16 (one 16-byte access) or fp32 (two) -- F32 = parity mode tensors
+template <bool F32>
+__device__ __forceinline__ void ld8(const void* p, size_t e, float* f) {
+  if (F32) {
+    const float4* q = reinterpret_cast<const float4*>(p) + 2 * e;
+    const float4 a = __ldg(q), b = __ldg(q + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    g_unpack8(__ldg(reinterpret_cast<const uint4*>(p) + e), f);
+  }
+}
+template <bool F32>
+__device__ __forceinline__ void st8(void* p, size_t e, const float* f) {
+  if (F32) {
+    float4* q = reinterpret_cast<float4*>(p) + 2 * e;
+    q[0] = make_float4(f[0], f[1], f[2], f[3]);
+    q[1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    reinterpret_cast<uint4*>(p)[e] = g_pack8(f);
+  }
+}
+
 constexpr int HID = 128;  // hidden width; 16 vectors of 8 per row
 
 // x = W_off o + b_off (Linear(3, 64|128)), written as bf16; also converts h0 fp32 -> bf16 copy.
+template <bool F32>
 __global__ void __launch_bounds__(256) k_offset_encode(const float* __restrict__ offs, const float* __restrict__ w,
                                                        const float* __restrict__ b, int n, int n_pad, int cx,
-                                                       uint4* __restrict__ x) {
+                                                       void* __restrict__ x) {
   const int vpr = cx >> 3;
   const long long total = (long long)n_pad * vpr;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -48,7 +71,7 @@ __global__ void __launch_bounds__(256) k_offset_encode(const float* __restrict__
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = 0.f;
     }
-    x[e] = g_pack8(f);
+    st8<F32>(x, e, f);
   }
 }
 
@@ -72,15 +95,16 @@ __global__ void __launch_bounds__(256) k_to_bf16_pad(const float* __restrict__ s
 }
 
 // rh = bf16(sigmoid(r_pre) * h);  zr_pre [n_pad, 256] bf16 (z | r), h fp32 [n_pad, 128]
-__global__ void __launch_bounds__(256) k_gru_rh(const uint4* __restrict__ zr_pre, const float* __restrict__ h, int n,
-                                                int n_pad, uint4* __restrict__ rh) {
+template <bool F32>
+__global__ void __launch_bounds__(256) k_gru_rh(const void* __restrict__ zr_pre, const float* __restrict__ h, int n,
+                                                int n_pad, void* __restrict__ rh) {
   const long long total = (long long)n_pad * 16;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(e >> 4), v = (int)(e & 15);
     float f[8];
     if (row < n) {
       float r[8];
-      g_unpack8(__ldg(zr_pre + (size_t)row * 32 + 16 + v), r);
+      ld8<F32>(zr_pre, (size_t)row * 32 + 16 + v, r);
       const float4 a = *reinterpret_cast<const float4*>(h + e * 8), c = *reinterpret_cast<const float4*>(h + e * 8 + 4);
       const float hv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
@@ -89,12 +113,13 @@ __global__ void __launch_bounds__(256) k_gru_rh(const uint4* __restrict__ zr_pre
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = 0.f;
     }
-    rh[e] = g_pack8(f);
+    st8<F32>(rh, e, f);
   }
 }
 
 // h' = (1 - z) h + z q;  writes fp32 h' and its bf16 copy
-__global__ void __launch_bounds__(256) k_gru_update(const uint4* __restrict__ zr_pre, const uint4* __restrict__ q_pre,
+template <bool F32>
+__global__ void __launch_bounds__(256) k_gru_update(const void* __restrict__ zr_pre, const void* __restrict__ q_pre,
                                                     const float* __restrict__ h, int n, int n_pad,
                                                     float* __restrict__ h_new, uint4* __restrict__ hb_new) {
   const long long total = (long long)n_pad * 16;
@@ -103,8 +128,8 @@ __global__ void __launch_bounds__(256) k_gru_update(const uint4* __restrict__ zr
     float f[8];
     if (row < n) {
       float z[8], q[8];
-      g_unpack8(__ldg(zr_pre + (size_t)row * 32 + v), z);
-      g_unpack8(__ldg(q_pre + e), q);
+      ld8<F32>(zr_pre, (size_t)row * 32 + v, z);
+      ld8<F32>(q_pre, (size_t)e, q);
       const float4 a = *reinterpret_cast<const float4*>(h + e * 8), c = *reinterpret_cast<const float4*>(h + e * 8 + 4);
       const float hv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
@@ -118,15 +143,16 @@ __global__ void __launch_bounds__(256) k_gru_update(const uint4* __restrict__ zr
     }
     *reinterpret_cast<float4*>(h_new + e * 8) = make_float4(f[0], f[1], f[2], f[3]);
     *reinterpret_cast<float4*>(h_new + e * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
-    hb_new[e] = g_pack8(f);
+    if (hb_new) hb_new[e] = g_pack8(f);
   }
 }
 
 // Backward stage 1 (given dh' = dL/dh'): dq_pre = dh' z (1 - q^2) [bf16], dz_pre = dh' (q - h) z (1 - z) [bf16, into
 // dzr_pre[:, 0:128]], dh_acc = dh' (1 - z) [fp32].
-__global__ void __launch_bounds__(256) k_gru_bwd1(const uint4* __restrict__ zr_pre, const uint4* __restrict__ q_pre,
+template <bool F32>
+__global__ void __launch_bounds__(256) k_gru_bwd1(const void* __restrict__ zr_pre, const void* __restrict__ q_pre,
                                                   const float* __restrict__ h, const float* __restrict__ dh_new, int n,
-                                                  int n_pad, uint4* __restrict__ dq_pre, uint4* __restrict__ dzr_pre,
+                                                  int n_pad, void* __restrict__ dq_pre, void* __restrict__ dzr_pre,
                                                   float* __restrict__ dh_acc) {
   const long long total = (long long)n_pad * 16;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -134,8 +160,8 @@ __global__ void __launch_bounds__(256) k_gru_bwd1(const uint4* __restrict__ zr_p
     float dq[8], dz[8], da[8];
     if (row < n) {
       float z[8], q[8];
-      g_unpack8(__ldg(zr_pre + (size_t)row * 32 + v), z);
-      g_unpack8(__ldg(q_pre + e), q);
+      ld8<F32>(zr_pre, (size_t)row * 32 + v, z);
+      ld8<F32>(q_pre, (size_t)e, q);
       const float4 a = *reinterpret_cast<const float4*>(h + e * 8), c = *reinterpret_cast<const float4*>(h + e * 8 + 4);
       const float hv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
       const float4 g0 = *reinterpret_cast<const float4*>(dh_new + e * 8), g1 = *reinterpret_cast<const float4*>(dh_new + e * 8 + 4);
@@ -151,8 +177,8 @@ __global__ void __launch_bounds__(256) k_gru_bwd1(const uint4* __restrict__ zr_p
 #pragma unroll
       for (int i = 0; i < 8; ++i) { dq[i] = 0.f; dz[i] = 0.f; da[i] = 0.f; }
     }
-    dq_pre[e] = g_pack8(dq);
-    dzr_pre[(size_t)row * 32 + v] = g_pack8(dz);
+    st8<F32>(dq_pre, (size_t)e, dq);
+    st8<F32>(dzr_pre, (size_t)row * 32 + v, dz);
     *reinterpret_cast<float4*>(dh_acc + e * 8) = make_float4(da[0], da[1], da[2], da[3]);
     *reinterpret_cast<float4*>(dh_acc + e * 8 + 4) = make_float4(da[4], da[5], da[6], da[7]);
   }
@@ -160,17 +186,18 @@ __global__ void __launch_bounds__(256) k_gru_bwd1(const uint4* __restrict__ zr_p
 
 // Backward stage 2 (given d_rh = dL/d(r*h) from the Wq data gradient, bf16): dr_pre = d_rh h r (1 - r) [into
 // dzr_pre[:, 128:256]], dh_acc += d_rh r.
-__global__ void __launch_bounds__(256) k_gru_bwd2(const uint4* __restrict__ zr_pre, const float* __restrict__ h,
-                                                  const uint4* __restrict__ d_rh, int n, int n_pad,
-                                                  uint4* __restrict__ dzr_pre, float* __restrict__ dh_acc) {
+template <bool F32>
+__global__ void __launch_bounds__(256) k_gru_bwd2(const void* __restrict__ zr_pre, const float* __restrict__ h,
+                                                  const void* __restrict__ d_rh, int n, int n_pad,
+                                                  void* __restrict__ dzr_pre, float* __restrict__ dh_acc) {
   const long long total = (long long)n_pad * 16;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(e >> 4), v = (int)(e & 15);
     float dr[8];
     if (row < n) {
       float r[8], g[8];
-      g_unpack8(__ldg(zr_pre + (size_t)row * 32 + 16 + v), r);
-      g_unpack8(__ldg(d_rh + e), g);
+      ld8<F32>(zr_pre, (size_t)row * 32 + 16 + v, r);
+      ld8<F32>(d_rh, (size_t)e, g);
       const float4 a = *reinterpret_cast<const float4*>(h + e * 8), c = *reinterpret_cast<const float4*>(h + e * 8 + 4);
       const float hv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
       float4 d0 = *reinterpret_cast<float4*>(dh_acc + e * 8), d1 = *reinterpret_cast<float4*>(dh_acc + e * 8 + 4);
@@ -187,17 +214,18 @@ __global__ void __launch_bounds__(256) k_gru_bwd2(const uint4* __restrict__ zr_p
 #pragma unroll
       for (int i = 0; i < 8; ++i) dr[i] = 0.f;
     }
-    dzr_pre[(size_t)row * 32 + 16 + v] = g_pack8(dr);
+    st8<F32>(dzr_pre, (size_t)row * 32 + 16 + v, dr);
   }
 }
 
 // acc fp32 [n_pad, C] += bf16 a (+ bf16 b)
-__global__ void __launch_bounds__(256) k_acc_bf16(float* __restrict__ acc, const uint4* __restrict__ a,
-                                                  const uint4* __restrict__ b, long long n_vec) {
+template <bool F32>
+__global__ void __launch_bounds__(256) k_acc_bf16(float* __restrict__ acc, const void* __restrict__ a,
+                                                  const void* __restrict__ b, long long n_vec) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_vec; e += (long long)gridDim.x * blockDim.x) {
     float fa[8], fb[8];
-    g_unpack8(__ldg(a + e), fa);
-    if (b) g_unpack8(__ldg(b + e), fb);
+    ld8<F32>(a, (size_t)e, fa);
+    if (b) ld8<F32>(b, (size_t)e, fb);
     float4 d0 = *reinterpret_cast<float4*>(acc + e * 8), d1 = *reinterpret_cast<float4*>(acc + e * 8 + 4);
     float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
@@ -208,7 +236,8 @@ __global__ void __launch_bounds__(256) k_acc_bf16(float* __restrict__ acc, const
 }
 
 // MLP head tail: flow = W2 GELU(y1) + b2 with y1 [n_pad, 32] bf16 (pre-activation, bias included)
-__global__ void __launch_bounds__(256) k_head_out(const uint4* __restrict__ y1, const float* __restrict__ w2,
+template <bool F32>
+__global__ void __launch_bounds__(256) k_head_out(const void* __restrict__ y1, const float* __restrict__ w2,
                                                   const float* __restrict__ b2, int n, float* __restrict__ flow) {
   __shared__ float sw[96], sb[3];
   if (threadIdx.x < 96) sw[threadIdx.x] = w2[threadIdx.x];
@@ -219,7 +248,7 @@ __global__ void __launch_bounds__(256) k_head_out(const uint4* __restrict__ y1, 
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       float f[8];
-      g_unpack8(__ldg(y1 + (size_t)row * 4 + v), f);
+      ld8<F32>(y1, (size_t)row * 4 + v, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float z = f[i];
@@ -233,9 +262,10 @@ __global__ void __launch_bounds__(256) k_head_out(const uint4* __restrict__ y1, 
 }
 
 // backward: dy1 = (W2^T dflow) GELU'(y1) [bf16, zero rows >= n]; gW2 [3,32] += dflow^T GELU(y1); gb2 += sum dflow
-__global__ void __launch_bounds__(256) k_head_out_bwd(const uint4* __restrict__ y1, const float* __restrict__ w2,
+template <bool F32>
+__global__ void __launch_bounds__(256) k_head_out_bwd(const void* __restrict__ y1, const float* __restrict__ w2,
                                                       const float* __restrict__ dflow, int n, int n_pad,
-                                                      uint4* __restrict__ dy1, float* __restrict__ gw2,
+                                                      void* __restrict__ dy1, float* __restrict__ gw2,
                                                       float* __restrict__ gb2) {
   __shared__ float sw[96];
   __shared__ float acc[99];
@@ -254,7 +284,7 @@ __global__ void __launch_bounds__(256) k_head_out_bwd(const uint4* __restrict__ 
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       float f[8], o[8];
-      g_unpack8(__ldg(y1 + (size_t)row * 4 + v), f);
+      ld8<F32>(y1, (size_t)row * 4 + v, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float z = live ? f[i] : 0.f;
@@ -265,7 +295,7 @@ __global__ void __launch_bounds__(256) k_head_out_bwd(const uint4* __restrict__ 
         o[i] = (d0 * sw[c] + d1 * sw[32 + c] + d2 * sw[64 + c]) * ga;
         lw[c] = fmaf(d0, a, lw[c]); lw[32 + c] = fmaf(d1, a, lw[32 + c]); lw[64 + c] = fmaf(d2, a, lw[64 + c]);
       }
-      dy1[(size_t)row * 4 + v] = g_pack8(o);
+      st8<F32>(dy1, (size_t)row * 4 + v, o);
     }
   }
 #pragma unroll
@@ -313,11 +343,16 @@ static int gridv(long long work, int block = 256, int mult = 16) {
 
 using namespace dfb;
 #define ST ((cudaStream_t)stream_)
+#define DFB_F32_DISPATCH(kernel, grid, ...)                          \
+  do {                                                               \
+    if (f32) kernel<true><<<grid, 256, 0, ST>>>(__VA_ARGS__);        \
+    else kernel<false><<<grid, 256, 0, ST>>>(__VA_ARGS__);           \
+  } while (0)
 
 extern "C" int dfb_offset_encode(const float* offs, const float* w, const float* b, int n, int n_pad, int cx, void* x,
-                                 void* stream_) {
+                                 int f32, void* stream_) {
   if (cx % 8 || n_pad < n) { set_error("dfb_offset_encode: bad sizes"); return DFB_ERR_ARG; }
-  k_offset_encode<<<gridv((long long)n_pad * (cx >> 3)), 256, 0, ST>>>(offs, w, b, n, n_pad, cx, (uint4*)x);
+  DFB_F32_DISPATCH(k_offset_encode, gridv((long long)n_pad * (cx >> 3)), offs, w, b, n, n_pad, cx, x);
   add_launches(1);
   return check_launch("dfb_offset_encode");
 }
@@ -334,45 +369,44 @@ extern "C" int dfb_to_bf16_pad(const float* src, int n, int n_pad, int C, void* 
   add_launches(1);
   return check_launch("dfb_to_bf16_pad");
 }
-extern "C" int dfb_gru_rh(const void* zr_pre, const float* h, int n, int n_pad, void* rh, void* stream_) {
-  k_gru_rh<<<gridv((long long)n_pad * 16), 256, 0, ST>>>((const uint4*)zr_pre, h, n, n_pad, (uint4*)rh);
+extern "C" int dfb_gru_rh(const void* zr_pre, const float* h, int n, int n_pad, void* rh, int f32, void* stream_) {
+  DFB_F32_DISPATCH(k_gru_rh, gridv((long long)n_pad * 16), zr_pre, h, n, n_pad, rh);
   add_launches(1);
   return check_launch("dfb_gru_rh");
 }
 extern "C" int dfb_gru_update(const void* zr_pre, const void* q_pre, const float* h, int n, int n_pad, float* h_new,
-                              void* hb_new, void* stream_) {
-  k_gru_update<<<gridv((long long)n_pad * 16), 256, 0, ST>>>((const uint4*)zr_pre, (const uint4*)q_pre, h, n, n_pad, h_new, (uint4*)hb_new);
+                              void* hb_new, int f32, void* stream_) {
+  DFB_F32_DISPATCH(k_gru_update, gridv((long long)n_pad * 16), zr_pre, q_pre, h, n, n_pad, h_new, (uint4*)hb_new);
   add_launches(1);
   return check_launch("dfb_gru_update");
 }
 extern "C" int dfb_gru_bwd1(const void* zr_pre, const void* q_pre, const float* h, const float* dh_new, int n, int n_pad,
-                            void* dq_pre, void* dzr_pre, float* dh_acc, void* stream_) {
-  k_gru_bwd1<<<gridv((long long)n_pad * 16), 256, 0, ST>>>((const uint4*)zr_pre, (const uint4*)q_pre, h, dh_new, n, n_pad,
-                                                          (uint4*)dq_pre, (uint4*)dzr_pre, dh_acc);
+                            void* dq_pre, void* dzr_pre, float* dh_acc, int f32, void* stream_) {
+  DFB_F32_DISPATCH(k_gru_bwd1, gridv((long long)n_pad * 16), zr_pre, q_pre, h, dh_new, n, n_pad, dq_pre, dzr_pre, dh_acc);
   add_launches(1);
   return check_launch("dfb_gru_bwd1");
 }
 extern "C" int dfb_gru_bwd2(const void* zr_pre, const float* h, const void* d_rh, int n, int n_pad, void* dzr_pre,
-                            float* dh_acc, void* stream_) {
-  k_gru_bwd2<<<gridv((long long)n_pad * 16), 256, 0, ST>>>((const uint4*)zr_pre, h, (const uint4*)d_rh, n, n_pad, (uint4*)dzr_pre, dh_acc);
+                            float* dh_acc, int f32, void* stream_) {
+  DFB_F32_DISPATCH(k_gru_bwd2, gridv((long long)n_pad * 16), zr_pre, h, d_rh, n, n_pad, dzr_pre, dh_acc);
   add_launches(1);
   return check_launch("dfb_gru_bwd2");
 }
-extern "C" int dfb_acc_bf16(float* acc, const void* a, const void* b, long long n_elems, void* stream_) {
+extern "C" int dfb_acc_bf16(float* acc, const void* a, const void* b, long long n_elems, int f32, void* stream_) {
   if (n_elems % 8) { set_error("dfb_acc_bf16: element count must be a multiple of 8"); return DFB_ERR_ARG; }
-  k_acc_bf16<<<gridv(n_elems / 8), 256, 0, ST>>>(acc, (const uint4*)a, (const uint4*)b, n_elems / 8);
+  DFB_F32_DISPATCH(k_acc_bf16, gridv(n_elems / 8), acc, a, b, n_elems / 8);
   add_launches(1);
   return check_launch("dfb_acc_bf16");
 }
-extern "C" int dfb_head_out(const void* y1, const float* w2, const float* b2, int n, float* flow, void* stream_) {
+extern "C" int dfb_head_out(const void* y1, const float* w2, const float* b2, int n, float* flow, int f32, void* stream_) {
   if (n <= 0) return DFB_OK;
-  k_head_out<<<gridv(n), 256, 0, ST>>>((const uint4*)y1, w2, b2, n, flow);
+  DFB_F32_DISPATCH(k_head_out, gridv(n), y1, w2, b2, n, flow);
   add_launches(1);
   return check_launch("dfb_head_out");
 }
 extern "C" int dfb_head_out_backward(const void* y1, const float* w2, const float* dflow, int n, int n_pad, void* dy1,
-                                     float* gw2, float* gb2, void* stream_) {
-  k_head_out_bwd<<<gridv(n_pad, 256, 2), 256, 0, ST>>>((const uint4*)y1, w2, dflow, n, n_pad, (uint4*)dy1, gw2, gb2);
+                                     float* gw2, float* gb2, int f32, void* stream_) {
+  DFB_F32_DISPATCH(k_head_out_bwd, gridv(n_pad, 256, 2), y1, w2, dflow, n, n_pad, dy1, gw2, gb2);
   add_launches(1);
   return check_launch("dfb_head_out_backward");
 }

@@ -25,6 +25,28 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
+// 8 consecutive channels of element-vector `e`: one 16-byte load for bf16 tensors, two for fp32 (parity mode)
+template <bool F32>
+__device__ __forceinline__ void ld8v(const void* p, long long e, float* f) {
+  if (F32) {
+    const float4* q = reinterpret_cast<const float4*>(p) + 2 * e;
+    const float4 a = __ldg(q), b = __ldg(q + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p) + e), f);
+  }
+}
+template <bool F32>
+__device__ __forceinline__ void st8v(void* p, long long e, const float* f) {
+  if (F32) {
+    float4* q = reinterpret_cast<float4*>(p) + 2 * e;
+    q[0] = make_float4(f[0], f[1], f[2], f[3]);
+    q[1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    reinterpret_cast<uint4*>(p)[e] = pack8(f);
+  }
+}
+
 // Exact-erf GELU and its derivative share one exponential: with u = |z|/sqrt(2), erf(u) = 1 - P(t) exp(-u^2),
 // t = 1/(1 + p u) (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 -- far below bf16 resolution), and the Gaussian
 // density of the derivative is the same exp(-z^2/2).  ~20 instructions instead of erff + expf (~60): these passes are
@@ -86,8 +108,9 @@ __device__ __forceinline__ void ld8(const float* p, float* f) {
 }
 
 // y = GELU(a*x + b)
-__global__ void __launch_bounds__(256, 4) k_bn_gelu_apply(const uint4* __restrict__ x, const float* __restrict__ bn, int C,
-                                                          long long n_vec, uint4* __restrict__ y) {
+template <bool F32>
+__global__ void __launch_bounds__(256, 4) k_bn_gelu_apply(const void* __restrict__ x, const float* __restrict__ bn, int C,
+                                                          long long n_vec, void* __restrict__ y) {
   __shared__ __align__(16) float sa[256], sb[256];
   for (int i = threadIdx.x; i < C; i += blockDim.x) { sa[i] = bn[i]; sb[i] = bn[C + i]; }
   __syncthreads();
@@ -96,25 +119,24 @@ __global__ void __launch_bounds__(256, 4) k_bn_gelu_apply(const uint4* __restric
   const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(e0 % vpp) << 3;
   for (long long e = e0; e < n_vec; e += 4 * stride) {
-    uint4 u[4];
+    float f[4][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const long long ej = e + j * stride; if (ej < n_vec) u[j] = __ldg(x + ej); }
+    for (int j = 0; j < 4; ++j) { const long long ej = e + j * stride; if (ej < n_vec) ld8v<F32>(x, ej, f[j]); }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const long long ej = e + j * stride;
       if (ej < n_vec) {
-        float f[8], a[8], b[8];
-        unpack8(u[j], f); ld8(sa + c0, a); ld8(sb + c0, b);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = gelu_f(fmaf(f[i], a[i], b[i]));
-        y[ej] = pack8(f);
+        for (int i = 0; i < 8; ++i) f[j][i] = gelu_f(fmaf(f[j][i], sa[c0 + i], sb[c0 + i]));
+        st8v<F32>(y, ej, f[j]);
       }
     }
   }
 }
 
 // Backward pass 1: red[0][c] = sum g1, red[1][c] = sum g1 * xhat, with g1 = gy * GELU'(a*x + b)
-__global__ void __launch_bounds__(256, 3) k_bn_gelu_bwd_reduce(const uint4* __restrict__ x, const uint4* __restrict__ gy,
+template <bool F32>
+__global__ void __launch_bounds__(256, 3) k_bn_gelu_bwd_reduce(const void* __restrict__ x, const void* __restrict__ gy,
                                                                const float* __restrict__ bn, int C, long long n_vec,
                                                                double* __restrict__ red) {
   __shared__ __align__(16) float sa[256], sb[256], smu[256], srs[256];
@@ -134,23 +156,18 @@ __global__ void __launch_bounds__(256, 3) k_bn_gelu_bwd_reduce(const uint4* __re
   for (long long e = e0; e < n_vec; e += 2 * stride) {
     const long long e2 = e + stride;
     const bool two = e2 < n_vec;
-    const uint4 ux0 = __ldg(x + e), ug0 = __ldg(gy + e);
-    const uint4 ux1 = two ? __ldg(x + e2) : ux0, ug1 = two ? __ldg(gy + e2) : ug0;
-    float fx[8], fg[8];
-    unpack8(ux0, fx); unpack8(ug0, fg);
+    float fx[2][8], fg[2][8];
+    ld8v<F32>(x, e, fx[0]); ld8v<F32>(gy, e, fg[0]);
+    if (two) { ld8v<F32>(x, e2, fx[1]); ld8v<F32>(gy, e2, fg[1]); }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], sa[c0 + i], sb[c0 + i]));
-      s1[i] += g1;
-      s2[i] = fmaf(g1, (fx[i] - smu[c0 + i]) * srs[c0 + i], s2[i]);
-    }
-    if (two) {
-      unpack8(ux1, fx); unpack8(ug1, fg);
+    for (int j = 0; j < 2; ++j) {
+      if (j == 0 || two) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], sa[c0 + i], sb[c0 + i]));
-        s1[i] += g1;
-        s2[i] = fmaf(g1, (fx[i] - smu[c0 + i]) * srs[c0 + i], s2[i]);
+        for (int i = 0; i < 8; ++i) {
+          const float g1 = fg[j][i] * gelu_grad_f(fmaf(fx[j][i], sa[c0 + i], sb[c0 + i]));
+          s1[i] += g1;
+          s2[i] = fmaf(g1, (fx[j][i] - smu[c0 + i]) * srs[c0 + i], s2[i]);
+        }
       }
     }
   }
@@ -164,10 +181,11 @@ __global__ void __launch_bounds__(256, 3) k_bn_gelu_bwd_reduce(const uint4* __re
 }
 
 // Backward pass 2: gx = a * (g1 - m1 - xhat*m2) (training) or a * g1 (eval)
-__global__ void __launch_bounds__(256, 3) k_bn_gelu_bwd_apply(const uint4* __restrict__ x, const uint4* __restrict__ gy,
+template <bool F32>
+__global__ void __launch_bounds__(256, 3) k_bn_gelu_bwd_apply(const void* __restrict__ x, const void* __restrict__ gy,
                                                               const float* __restrict__ bn, const double* __restrict__ red,
                                                               double count, int training, int C, long long n_vec,
-                                                              uint4* __restrict__ gx) {
+                                                              void* __restrict__ gx) {
   __shared__ __align__(16) float sa[256], sb[256], smu[256], srs[256], sm1[256], sm2[256];
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     sa[i] = bn[i]; sb[i] = bn[C + i]; smu[i] = bn[2 * C + i]; srs[i] = bn[3 * C + i];
@@ -182,24 +200,19 @@ __global__ void __launch_bounds__(256, 3) k_bn_gelu_bwd_apply(const uint4* __res
   for (long long e = e0; e < n_vec; e += 2 * stride) {
     const long long e2 = e + stride;
     const bool two = e2 < n_vec;
-    const uint4 ux0 = __ldg(x + e), ug0 = __ldg(gy + e);
-    const uint4 ux1 = two ? __ldg(x + e2) : ux0, ug1 = two ? __ldg(gy + e2) : ug0;
-    float fx[8], fg[8];
-    unpack8(ux0, fx); unpack8(ug0, fg);
+    float fx[2][8], fg[2][8];
+    ld8v<F32>(x, e, fx[0]); ld8v<F32>(gy, e, fg[0]);
+    if (two) { ld8v<F32>(x, e2, fx[1]); ld8v<F32>(gy, e2, fg[1]); }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], sa[c0 + i], sb[c0 + i]));
-      fx[i] = sa[c0 + i] * (g1 - sm1[c0 + i] - (fx[i] - smu[c0 + i]) * srs[c0 + i] * sm2[c0 + i]);
-    }
-    gx[e] = pack8(fx);
-    if (two) {
-      unpack8(ux1, fx); unpack8(ug1, fg);
+    for (int j = 0; j < 2; ++j) {
+      if (j == 0 || two) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float g1 = fg[i] * gelu_grad_f(fmaf(fx[i], sa[c0 + i], sb[c0 + i]));
-        fx[i] = sa[c0 + i] * (g1 - sm1[c0 + i] - (fx[i] - smu[c0 + i]) * srs[c0 + i] * sm2[c0 + i]);
+        for (int i = 0; i < 8; ++i) {
+          const float g1 = fg[j][i] * gelu_grad_f(fmaf(fx[j][i], sa[c0 + i], sb[c0 + i]));
+          fx[j][i] = sa[c0 + i] * (g1 - sm1[c0 + i] - (fx[j][i] - smu[c0 + i]) * srs[c0 + i] * sm2[c0 + i]);
+        }
+        st8v<F32>(gx, j == 0 ? e : e2, fx[j]);
       }
-      gx[e2] = pack8(fx);
     }
   }
 }
@@ -214,33 +227,38 @@ __global__ void k_bn_param_grads(const double* __restrict__ red, const float* __
   if (g_bias) g_bias[c] += training ? 0.f : bn[c] * (float)red[c];
 }
 
-// ---------------------------------------------------------------- per-channel sum (bias gradients)
-__global__ void __launch_bounds__(256) k_channel_sum(const uint4* __restrict__ g, int C, long long n_pix,
-                                                     float* __restrict__ out) {
-  __shared__ float acc[256];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) acc[i] = 0.f;
+// ---------------------------------------------------------------- per-channel sum (bias gradients) / sum of squares
+template <bool F32>
+__global__ void __launch_bounds__(256) k_channel_sum(const void* __restrict__ g, int C, long long n_pix,
+                                                     float* __restrict__ out, double* __restrict__ stats2) {
+  __shared__ float acc[256], acc2[256];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { acc[i] = 0.f; acc2[i] = 0.f; }
   __syncthreads();
   const int vpp = C >> 3;
   const int oct = threadIdx.x % vpp, prow = threadIdx.x / vpp, prows = blockDim.x / vpp;
-  float s[8];
+  float s[8], q[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   for (long long p = (long long)blockIdx.x * prows + prow; p < n_pix; p += (long long)gridDim.x * prows) {
     float f[8];
-    unpack8(__ldg(g + p * vpp + oct), f);
+    ld8v<F32>(g, p * vpp + oct, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] += f[i];
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) atomicAdd(&acc[(oct << 3) + i], s[i]);
+  for (int i = 0; i < 8; ++i) { atomicAdd(&acc[(oct << 3) + i], s[i]); if (stats2) atomicAdd(&acc2[(oct << 3) + i], q[i]); }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], acc[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    if (out) atomicAdd(&out[i], acc[i]);
+    if (stats2) { atomicAdd(&stats2[i], (double)acc[i]); atomicAdd(&stats2[C + i], (double)acc2[i]); }
+  }
 }
 
 // ---------------------------------------------------------------- bilinear x2 (align_corners = False)
 // out[2i] = 0.25 in[i-1] + 0.75 in[i], out[2i+1] = 0.75 in[i] + 0.25 in[i+1], indices clamped to the edge.
-__global__ void __launch_bounds__(256) k_upsample2x(const uint4* __restrict__ in, int n, int h, int w, int C,
-                                                    uint4* __restrict__ out) {
+template <bool F32>
+__global__ void __launch_bounds__(256) k_upsample2x(const void* __restrict__ in, int n, int h, int w, int C,
+                                                    void* __restrict__ out) {
   const int vpp = C >> 3;
   const long long total = (long long)n * 4 * h * w * vpp;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -252,16 +270,16 @@ __global__ void __launch_bounds__(256) k_upsample2x(const uint4* __restrict__ in
     const int iy = oy >> 1, ix = ox >> 1;
     const int y2 = (oy & 1) ? min(iy + 1, h - 1) : max(iy - 1, 0);
     const int x2 = (ox & 1) ? min(ix + 1, w - 1) : max(ix - 1, 0);
-    const uint4* base = in + (long long)b * h * w * vpp + v;
+    const long long base = (long long)b * h * w * vpp + v;
     float a[8], bq[8], c[8], d[8];
-    unpack8(__ldg(base + ((long long)iy * w + ix) * vpp), a);
-    unpack8(__ldg(base + ((long long)iy * w + x2) * vpp), bq);
-    unpack8(__ldg(base + ((long long)y2 * w + ix) * vpp), c);
-    unpack8(__ldg(base + ((long long)y2 * w + x2) * vpp), d);
+    ld8v<F32>(in, base + ((long long)iy * w + ix) * vpp, a);
+    ld8v<F32>(in, base + ((long long)iy * w + x2) * vpp, bq);
+    ld8v<F32>(in, base + ((long long)y2 * w + ix) * vpp, c);
+    ld8v<F32>(in, base + ((long long)y2 * w + x2) * vpp, d);
 #pragma unroll
     for (int i = 0; i < 8; ++i)  // rows first (like ATen: y-lerp of x-lerps), weights 0.75 / 0.25
       a[i] = 0.75f * (0.75f * a[i] + 0.25f * bq[i]) + 0.25f * (0.75f * c[i] + 0.25f * d[i]);
-    out[e] = pack8(a);
+    st8v<F32>(out, e, a);
   }
 }
 
@@ -275,8 +293,9 @@ __device__ __forceinline__ float up_w(int i, int o, int len) {
   return wgt;
 }
 
-__global__ void __launch_bounds__(256) k_upsample2x_bwd(const uint4* __restrict__ gout, int n, int h, int w, int C,
-                                                        uint4* __restrict__ gin) {
+template <bool F32>
+__global__ void __launch_bounds__(256) k_upsample2x_bwd(const void* __restrict__ gout, int n, int h, int w, int C,
+                                                        void* __restrict__ gin) {
   const int vpp = C >> 3;
   const long long total = (long long)n * h * w * vpp;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -288,7 +307,7 @@ __global__ void __launch_bounds__(256) k_upsample2x_bwd(const uint4* __restrict_
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const uint4* base = gout + (long long)b * 4 * h * w * vpp + v;
+    const long long base = (long long)b * 4 * h * w * vpp + v;
     for (int oy = max(2 * iy - 1, 0); oy <= min(2 * iy + 2, 2 * h - 1); ++oy) {
       const float wy = up_w(iy, oy, h);
       if (wy == 0.f) continue;
@@ -296,13 +315,13 @@ __global__ void __launch_bounds__(256) k_upsample2x_bwd(const uint4* __restrict_
         const float wx = up_w(ix, ox, w);
         if (wx == 0.f) continue;
         float f[8];
-        unpack8(__ldg(base + ((long long)oy * 2 * w + ox) * vpp), f);
+        ld8v<F32>(gout, base + ((long long)oy * 2 * w + ox) * vpp, f);
         const float wt = wy * wx;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(wt, f[i], acc[i]);
       }
     }
-    gin[e] = pack8(acc);
+    st8v<F32>(gin, e, acc);
   }
 }
 
@@ -328,41 +347,61 @@ extern "C" int dfb_bn2d_finalize(const double* stats, double count, int C, int t
   return check_launch("dfb_bn2d_finalize");
 }
 
-extern "C" int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, void* stream_) {
+extern "C" int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, int f32, void* stream_) {
   if (C % 8 || C > 256) { set_error("dfb_bn_gelu_apply: C must be a multiple of 8 and <= 256"); return DFB_ERR_ARG; }
   const long long n_vec = n_pix * (C >> 3);
-  k_bn_gelu_apply<<<grid_for_elems(n_vec, 1024, 12), 256, 0, (cudaStream_t)stream_>>>((const uint4*)x, bn, C, n_vec, (uint4*)y);
+  const int g = grid_for_elems(n_vec, 1024, 12);
+  if (f32) k_bn_gelu_apply<true><<<g, 256, 0, (cudaStream_t)stream_>>>(x, bn, C, n_vec, y);
+  else k_bn_gelu_apply<false><<<g, 256, 0, (cudaStream_t)stream_>>>(x, bn, C, n_vec, y);
   add_launches(1);
   return check_launch("dfb_bn_gelu_apply");
 }
 
 extern "C" int dfb_bn_gelu_backward(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
-                                    double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, void* stream_) {
+                                    double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, int f32,
+                                    void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (C % 8 || C > 256 || 256 % (C >> 3)) { set_error("dfb_bn_gelu_backward: unsupported channel count %d", C); return DFB_ERR_ARG; }
   cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st);
   const long long n_vec = n_pix * (C >> 3);
-  k_bn_gelu_bwd_reduce<<<grid_for_elems(n_vec, 512, 8), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, C, n_vec, red);
-  k_bn_gelu_bwd_apply<<<grid_for_elems(n_vec, 512, 8), 256, 0, st>>>((const uint4*)x, (const uint4*)gy, bn, red, (double)n_pix,
-                                                                  training, C, n_vec, (uint4*)gx);
+  const int g = grid_for_elems(n_vec, 512, 8);
+  if (f32) {
+    k_bn_gelu_bwd_reduce<true><<<g, 256, 0, st>>>(x, gy, bn, C, n_vec, red);
+    k_bn_gelu_bwd_apply<true><<<g, 256, 0, st>>>(x, gy, bn, red, (double)n_pix, training, C, n_vec, gx);
+  } else {
+    k_bn_gelu_bwd_reduce<false><<<g, 256, 0, st>>>(x, gy, bn, C, n_vec, red);
+    k_bn_gelu_bwd_apply<false><<<g, 256, 0, st>>>(x, gy, bn, red, (double)n_pix, training, C, n_vec, gx);
+  }
   k_bn_param_grads<<<(C + 127) / 128, 128, 0, st>>>(red, bn, C, training, g_gamma, g_beta, g_bias);
   add_launches(3);
   return check_launch("dfb_bn_gelu_backward");
 }
 
-extern "C" int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, void* stream_) {
+// out[c] += sum over pixels (may be NULL); stats2 (may be NULL): [2][C] += sum, sum of squares (BatchNorm statistics of
+// an fp32 tensor in parity mode)
+extern "C" int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, double* stats2, int f32, void* stream_) {
   if (C % 8 || C > 256 || 256 % (C >> 3)) { set_error("dfb_channel_sum: unsupported channel count %d", C); return DFB_ERR_ARG; }
   const int prows = 256 / (C >> 3);
-  k_channel_sum<<<grid_for_elems(n_pix, prows, 8), 256, 0, (cudaStream_t)stream_>>>((const uint4*)g, C, n_pix, out);
+  const int gr = grid_for_elems(n_pix, prows, 8);
+  if (f32) k_channel_sum<true><<<gr, 256, 0, (cudaStream_t)stream_>>>(g, C, n_pix, out, stats2);
+  else k_channel_sum<false><<<gr, 256, 0, (cudaStream_t)stream_>>>(g, C, n_pix, out, stats2);
   add_launches(1);
   return check_launch("dfb_channel_sum");
 }
 
-extern "C" int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int backward, void* stream_) {
+extern "C" int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int backward, int f32, void* stream_) {
   if (C % 8) { set_error("dfb_upsample2x: C must be a multiple of 8"); return DFB_ERR_ARG; }
   const long long vec_in = (long long)n * h * w * (C >> 3);
-  if (!backward) k_upsample2x<<<grid_for_elems(vec_in * 4, 256), 256, 0, (cudaStream_t)stream_>>>((const uint4*)in, n, h, w, C, (uint4*)out);
-  else k_upsample2x_bwd<<<grid_for_elems(vec_in, 256), 256, 0, (cudaStream_t)stream_>>>((const uint4*)in, n, h, w, C, (uint4*)out);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!backward) {
+    const int g = grid_for_elems(vec_in * 4, 256);
+    if (f32) k_upsample2x<true><<<g, 256, 0, st>>>(in, n, h, w, C, out);
+    else k_upsample2x<false><<<g, 256, 0, st>>>(in, n, h, w, C, out);
+  } else {
+    const int g = grid_for_elems(vec_in, 256);
+    if (f32) k_upsample2x_bwd<true><<<g, 256, 0, st>>>(in, n, h, w, C, out);
+    else k_upsample2x_bwd<false><<<g, 256, 0, st>>>(in, n, h, w, C, out);
+  }
   add_launches(1);
   return check_launch("dfb_upsample2x");
 }

@@ -47,6 +47,10 @@ class _GatherDecoder(nn.Module):
         """bf16 perf mode: gather -> (GRU iterations) -> MLP head on the tensor cores (deflow_b200/gru.py)."""
         from . import gru
         n_pad = max((n_rows + 7) // 8 * 8, 8)
+        if self.compute_dtype == torch.float32:
+            # parity mode: fp32 gate tensors, split-precision ("bf16x3") tensor-core GEMMs
+            h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.float32, n_pad)
+            return gru.decode(h0, offsets, n_rows, self, iters, parity=True)
         if iters > 0 and os.environ.get("DFB_GRU", "fused") == "fused":
             # persistent fused kernels (csrc/gru_fused.cu); DFB_GRU=unfused selects the GEMM + elementwise launches
             h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.bfloat16, n_pad)
@@ -78,11 +82,12 @@ class ConvGRUDecoder(_GatherDecoder):
                                      nn.Linear(pseudoimage_channels // 2, 3))
         self.num_iters = num_iters
         self.compute_dtype = torch.float32
+        self.use_library = False   # True: cuBLAS fp32 comparator (tests only)
 
     def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
         """All pc0 points of the batch at once -> flow [n_rows, 3]."""
         offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
-        if self.compute_dtype == torch.bfloat16:
+        if not self.use_library:
             return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, self.num_iters)
         h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(self.compute_dtype == torch.bfloat16)):
@@ -100,10 +105,11 @@ class LinearDecoder(_GatherDecoder):
         self.offset_encoder = nn.Linear(3, 128)
         self.decoder = nn.Sequential(nn.Linear(pseudoimage_channels * 4, 32), nn.GELU(), nn.Linear(32, 3))
         self.compute_dtype = torch.float32
+        self.use_library = False
 
     def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
         offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
-        if self.compute_dtype == torch.bfloat16:
+        if not self.use_library:
             return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, 0)
         h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(self.compute_dtype == torch.bfloat16)):

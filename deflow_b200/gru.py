@@ -21,13 +21,17 @@ def _img(t):  # [n_pad, C] -> [1, n_pad/8, 8, C] view for the convolution kernel
     return t.view(1, t.shape[0] // 8, 8, t.shape[1])
 
 
+def _s3(t):
+    return t.dtype == torch.float32
+
+
 def _conv(srcs, w4, b, cout):
-    wf, _ = tc.packed_raw(w4)
+    wf, _ = tc.packed_raw(w4, _s3(srcs[0]))
     return tc.conv2d_forward([_img(s) for s in srcs], wf, b, cout, 1, 1).view(-1, cout)
 
 
 def _dgrad(gy, w4, lo, hi):
-    _, wd = tc.packed_raw(w4)
+    _, wd = tc.packed_raw(w4, _s3(gy))
     n_pad = gy.shape[0]
     return tc.conv2d_dgrad(_img(gy), wd, n_pad // 8, 8, hi - lo, w4.shape[1], lo, 1, 1).view(n_pad, hi - lo)
 
@@ -37,93 +41,103 @@ def _wgrad(srcs, gy, acc=None):
 
 
 class _Decoder(torch.autograd.Function):
-    """h0 [n_pad,128] fp32 (gathered pillar vectors), offsets [n,3] -> flow [n,3]."""
+    """h0 [n_pad,128] fp32 (gathered pillar vectors), offsets [n,3] -> flow [n,3]: GEMMs as 1x1 tensor-core
+    convolutions over the point list + the gate kernels of csrc/gru_elem.cu.
+    parity = False: bf16 gate tensors (the launch-per-stage predecessor of the fused kernels, kept for A/B runs and the
+    linear decoder); parity = True: fp32 gate tensors and split-precision ("bf16x3") GEMMs -- the fp32 parity mode."""
 
     @staticmethod
-    def forward(ctx, h0, offsets, n, iters, w_off, b_off, wz, bz, wr, br, wq, bq, w1, b1, w2, b2):
+    def forward(ctx, h0, offsets, n, iters, parity, w_off, b_off, wz, bz, wr, br, wq, bq, w1, b1, w2, b2):
         lib = _lib.lib()
         dev = h0.device
         n_pad = h0.shape[0]
         st = _stream(h0)
         cx = w_off.shape[0]
-        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
-        x = torch.empty((n_pad, cx), dtype=BF, device=dev)
+        DT = torch.float32 if parity else BF
+        f32 = int(parity)
+        f = lambda t: t.detach().float().contiguous()  # noqa: E731
+        x = torch.empty((n_pad, cx), dtype=DT, device=dev)
         offsets = offsets.contiguous()
-        check(lib.dfb_offset_encode(offsets.data_ptr(), f32(w_off).data_ptr(), f32(b_off).data_ptr(), n, n_pad, cx,
-                                    x.data_ptr(), st), "offset_encode")
-        hb = torch.empty((n_pad, 128), dtype=BF, device=dev)
-        check(lib.dfb_to_bf16_pad(h0.data_ptr(), n_pad, n_pad, 128, hb.data_ptr(), st), "to_bf16")
+        check(lib.dfb_offset_encode(offsets.data_ptr(), f(w_off).data_ptr(), f(b_off).data_ptr(), n, n_pad, cx,
+                                    x.data_ptr(), f32, st), "offset_encode")
+        if parity:
+            hb = h0          # the GEMM operand is the fp32 state itself (split into hi / lo inside the convolution)
+        else:
+            hb = torch.empty((n_pad, 128), dtype=BF, device=dev)
+            check(lib.dfb_to_bf16_pad(h0.data_ptr(), n_pad, n_pad, 128, hb.data_ptr(), st), "to_bf16")
         saved = {"hs": [], "hbs": [], "zr": [], "q": [], "rh": []}
         h = h0
         wzr4 = bzr = wq4 = None
         if iters > 0:
-            wzr4 = torch.cat([f32(wz)[:, :, 0], f32(wr)[:, :, 0]], 0).reshape(256, 192, 1, 1).contiguous()
-            bzr = torch.cat([f32(bz), f32(br)])
-            wq4 = f32(wq).reshape(128, 192, 1, 1)
-            bqf = f32(bq)
+            wzr4 = torch.cat([f(wz)[:, :, 0], f(wr)[:, :, 0]], 0).reshape(256, 192, 1, 1).contiguous()
+            bzr = torch.cat([f(bz), f(br)])
+            wq4 = f(wq).reshape(128, 192, 1, 1)
+            bqf = f(bq)
         for _ in range(iters):
             zr = _conv([hb, x], wzr4, bzr, 256)
-            rh = torch.empty((n_pad, 128), dtype=BF, device=dev)
-            check(lib.dfb_gru_rh(zr.data_ptr(), h.data_ptr(), n, n_pad, rh.data_ptr(), st), "gru_rh")
+            rh = torch.empty((n_pad, 128), dtype=DT, device=dev)
+            check(lib.dfb_gru_rh(zr.data_ptr(), h.data_ptr(), n, n_pad, rh.data_ptr(), f32, st), "gru_rh")
             q = _conv([rh, x], wq4, bqf, 128)
             h_new = torch.empty_like(h)
-            hb_new = torch.empty_like(hb)
+            hb_new = None if parity else torch.empty_like(hb)
             check(lib.dfb_gru_update(zr.data_ptr(), q.data_ptr(), h.data_ptr(), n, n_pad, h_new.data_ptr(),
-                                     hb_new.data_ptr(), st), "gru_update")
+                                     None if parity else hb_new.data_ptr(), f32, st), "gru_update")
             saved["hs"].append(h); saved["hbs"].append(hb); saved["zr"].append(zr); saved["q"].append(q); saved["rh"].append(rh)
-            h, hb = h_new, hb_new
-        w14 = f32(w1).reshape(32, w1.shape[1], 1, 1)
-        y1 = _conv([hb, x], w14, f32(b1), 32)
+            h, hb = h_new, (h_new if parity else hb_new)
+        w14 = f(w1).reshape(32, w1.shape[1], 1, 1)
+        y1 = _conv([hb, x], w14, f(b1), 32)
         flow = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        w2f = f32(w2)
-        check(lib.dfb_head_out(y1.data_ptr(), w2f.data_ptr(), f32(b2).data_ptr(), n, flow.data_ptr(), st), "head_out")
+        w2f = f(w2)
+        check(lib.dfb_head_out(y1.data_ptr(), w2f.data_ptr(), f(b2).data_ptr(), n, flow.data_ptr(), f32, st), "head_out")
         ctx.saved = (saved, x, hb, y1, offsets, wzr4, wq4, w14, w2f)
-        ctx.meta = (n, n_pad, iters, cx)
+        ctx.meta = (n, n_pad, iters, cx, parity)
         return flow
 
     @staticmethod
     def backward(ctx, dflow):
         lib = _lib.lib()
         saved, x, hb_last, y1, offsets, wzr4, wq4, w14, w2f = ctx.saved
-        n, n_pad, iters, cx = ctx.meta
+        n, n_pad, iters, cx, parity = ctx.meta
+        DT = torch.float32 if parity else BF
+        f32 = int(parity)
         dev = dflow.device
         st = _stream(dflow)
         dflow = dflow.contiguous().float()
         z32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
-        dy1 = torch.empty((n_pad, 32), dtype=BF, device=dev)
+        dy1 = torch.empty((n_pad, 32), dtype=DT, device=dev)
         gw2, gb2 = z32(3, 32), z32(3)
         check(lib.dfb_head_out_backward(y1.data_ptr(), w2f.data_ptr(), dflow.data_ptr(), n, n_pad, dy1.data_ptr(),
-                                        gw2.data_ptr(), gb2.data_ptr(), st), "head_out_backward")
+                                        gw2.data_ptr(), gb2.data_ptr(), f32, st), "head_out_backward")
         gw1 = _wgrad([hb_last, x], dy1)
         gb1 = tc.channel_sum(dy1)
         dh = z32(n_pad, 128)
         dx = z32(n_pad, cx)
         d_h = _dgrad(dy1, w14, 0, 128)
         d_x = _dgrad(dy1, w14, 128, 128 + cx)
-        check(lib.dfb_acc_bf16(dh.data_ptr(), d_h.data_ptr(), None, dh.numel(), st), "acc")
-        check(lib.dfb_acc_bf16(dx.data_ptr(), d_x.data_ptr(), None, dx.numel(), st), "acc")
+        check(lib.dfb_acc_bf16(dh.data_ptr(), d_h.data_ptr(), None, dh.numel(), f32, st), "acc")
+        check(lib.dfb_acc_bf16(dx.data_ptr(), d_x.data_ptr(), None, dx.numel(), f32, st), "acc")
         gwzr = gwq = gbzr = gbq = None
         for t in reversed(range(iters)):
             h, hb, zr, q, rh = saved["hs"][t], saved["hbs"][t], saved["zr"][t], saved["q"][t], saved["rh"][t]
-            dq = torch.empty((n_pad, 128), dtype=BF, device=dev)
-            dzr = torch.empty((n_pad, 256), dtype=BF, device=dev)
+            dq = torch.empty((n_pad, 128), dtype=DT, device=dev)
+            dzr = torch.empty((n_pad, 256), dtype=DT, device=dev)
             dh_acc = torch.empty_like(dh)
             check(lib.dfb_gru_bwd1(zr.data_ptr(), q.data_ptr(), h.data_ptr(), dh.data_ptr(), n, n_pad, dq.data_ptr(),
-                                   dzr.data_ptr(), dh_acc.data_ptr(), st), "gru_bwd1")
+                                   dzr.data_ptr(), dh_acc.data_ptr(), f32, st), "gru_bwd1")
             gwq = _wgrad([rh, x], dq, gwq)
             s = tc.channel_sum(dq)
             gbq = s if gbq is None else gbq + s
             d_rh = _dgrad(dq, wq4, 0, 128)
             d_xq = _dgrad(dq, wq4, 128, 192)
             check(lib.dfb_gru_bwd2(zr.data_ptr(), h.data_ptr(), d_rh.data_ptr(), n, n_pad, dzr.data_ptr(),
-                                   dh_acc.data_ptr(), st), "gru_bwd2")
+                                   dh_acc.data_ptr(), f32, st), "gru_bwd2")
             gwzr = _wgrad([hb, x], dzr, gwzr)
             s = tc.channel_sum(dzr)
             gbzr = s if gbzr is None else gbzr + s
             d_h2 = _dgrad(dzr, wzr4, 0, 128)
             d_xzr = _dgrad(dzr, wzr4, 128, 192)
-            check(lib.dfb_acc_bf16(dh_acc.data_ptr(), d_h2.data_ptr(), None, dh_acc.numel(), st), "acc")
-            check(lib.dfb_acc_bf16(dx.data_ptr(), d_xq.data_ptr(), d_xzr.data_ptr(), dx.numel(), st), "acc")
+            check(lib.dfb_acc_bf16(dh_acc.data_ptr(), d_h2.data_ptr(), None, dh_acc.numel(), f32, st), "acc")
+            check(lib.dfb_acc_bf16(dx.data_ptr(), d_xq.data_ptr(), d_xzr.data_ptr(), dx.numel(), f32, st), "acc")
             dh = dh_acc
         gw_off, gb_off = z32(cx, 3), z32(cx)
         check(lib.dfb_offset_encode_backward(dx.data_ptr(), offsets.data_ptr(), n, cx, gw_off.data_ptr(),
@@ -134,17 +148,17 @@ class _Decoder(torch.autograd.Function):
             gbz, gbr = gbzr[:128], gbzr[128:]
         else:
             gz = gr = gq = gbz = gbr = gbq = None
-        return (dh, None, None, None, gw_off, gb_off, gz, gbz, gr, gbr, gq, gbq, gw1[:, :, 0, 0], gb1, gw2, gb2)
+        return (dh, None, None, None, None, gw_off, gb_off, gz, gbz, gr, gbr, gq, gbq, gw1[:, :, 0, 0], gb1, gw2, gb2)
 
 
-def decode(h0, offsets, n, head, iters):
+def decode(h0, offsets, n, head, iters, parity=False):
     """head: ConvGRUDecoder (iters > 0) or LinearDecoder (iters == 0)."""
     if iters > 0:
         g = head.gru
         args = (g.convz.weight, g.convz.bias, g.convr.weight, g.convr.bias, g.convq.weight, g.convq.bias)
     else:
         args = (None,) * 6
-    return _Decoder.apply(h0, offsets, n, iters, head.offset_encoder.weight, head.offset_encoder.bias, *args,
+    return _Decoder.apply(h0, offsets, n, iters, parity, head.offset_encoder.weight, head.offset_encoder.bias, *args,
                           head.decoder[0].weight, head.decoder[0].bias, head.decoder[2].weight, head.decoder[2].bias)
 
 
@@ -192,7 +206,7 @@ class _FusedGRUDecoder(torch.autograd.Function):
         dy1 = torch.empty((n_pad, 32), dtype=BF, device=dev)
         gw2, gb2 = z32(3, 32), z32(3)
         check(lib.dfb_head_out_backward(y1.data_ptr(), w2f.data_ptr(), dflow.data_ptr(), n, n_pad, dy1.data_ptr(),
-                                        gw2.data_ptr(), gb2.data_ptr(), st), "head_out_backward")
+                                        gw2.data_ptr(), gb2.data_ptr(), 0, st), "head_out_backward")
         w14 = w1f.reshape(32, 192, 1, 1)
         gw1 = _wgrad([hsave[iters], xsave], dy1)
         gb1 = tc.channel_sum(dy1)

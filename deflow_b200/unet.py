@@ -67,25 +67,29 @@ class FastFlow3DUNet(nn.Module):
         self.decoder_step3 = UpsampleSkip(128, 64, 64)
         self.decoder_step4 = nn.Conv2d(64, 64, 3, 1, 1)
         self.compute_dtype = torch.float32
+        self.use_library = False   # True: cuDNN fp32 comparator (tests only); False: the tcgen05 kernels in both modes
 
     def forward(self, pc0_B: torch.Tensor, pc1_B: torch.Tensor) -> torch.Tensor:
         """Reference signature: [B,32,H,W] x2 -> [B,64,H,W] (any memory format; channels-last is the fast one)."""
-        if self.compute_dtype == torch.bfloat16:
-            out = self.forward_nhwc(pc0_B.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16),
-                                    pc1_B.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+        if not self.use_library:
+            out = self.forward_nhwc(pc0_B.permute(0, 2, 3, 1).contiguous().to(self.compute_dtype),
+                                    pc1_B.permute(0, 2, 3, 1).contiguous().to(self.compute_dtype))
             return out.permute(0, 3, 1, 2)
         return self._forward_library(pc0_B, pc1_B)
 
     def forward_nhwc(self, img0: torch.Tensor, img1: torch.Tensor) -> torch.Tensor:
         """NHWC [B,H,W,32] x2 -> NHWC [B,H,W,64]."""
-        if self.compute_dtype == torch.bfloat16:
+        if not self.use_library:
             return self._forward_tensor_core(img0.contiguous(), img1.contiguous())
         out = self._forward_library(img0.permute(0, 3, 1, 2), img1.permute(0, 3, 1, 2))
         return out.permute(0, 2, 3, 1).contiguous()
 
-    # bf16 perf mode: every convolution is a tcgen05 implicit GEMM (csrc/conv_igemm.cu); BatchNorm statistics come
-    # from the convolution epilogue; BN+GELU, bilinear x2 and their backward are HBM-bound passes (csrc/unet_elem.cu).
-    # Channel concatenations are never materialised: the consuming convolution reads two sources.
+    # Every convolution is a tcgen05 implicit GEMM (csrc/conv_igemm.cu); BatchNorm statistics come from the convolution
+    # epilogue; BN+GELU, bilinear x2 and their backward are HBM-bound passes (csrc/unet_elem.cu).  Channel
+    # concatenations are never materialised: the consuming convolution reads two sources.
+    #   bf16 images  -> perf mode: bf16 operands, fp32 accumulation;
+    #   fp32 images  -> parity mode: every operand is a (hi, lo) bf16 pair and the K loop runs hi*hi + hi*lo + lo*hi
+    #                   ("bf16x3": ~16 significant bits per operand, fp32 accumulation and fp32 activations in HBM).
     def _forward_tensor_core(self, img0, img1):
         from . import conv as tc
 
@@ -112,8 +116,8 @@ class FastFlow3DUNet(nn.Module):
         u = up(self.decoder_step3, (t,), (img0, img1))
         return tc.conv_bias(self.decoder_step4.weight, self.decoder_step4.bias, u)
 
-    # fp32 parity mode: strict-fp32 dense contractions through cuDNN (library).  bf16 tensor-core tiles cannot meet the
-    # 1e-3 per-point flow bound, so the bound is asserted here and the bf16 error is reported.
+    # cuDNN strict-fp32 comparator (use_library = True): not a product path, kept for tests that compare the
+    # split-precision tensor-core path with a library implementation of the same arithmetic.
     def _forward_library(self, pc0_B, pc1_B):
         dt = self.compute_dtype
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dt == torch.bfloat16)), \

@@ -209,8 +209,13 @@ typedef struct {
   void* y;               /* output NHWC, bf16 (or fp32 if y_fp32) */
   int y_fp32;
   double* stats;         /* [2][cout] or NULL */
+  const void* x_lo[2];   /* split-precision mode: the lo halves of the sources (x[] are the hi halves) */
+  int split3;            /* 1: operands are (hi, lo) bf16 pairs, weights packed with split3, K loop = hi*hi + hi*lo + lo*hi */
 } dfb_conv_args;
-int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, void* w_fwd, void* w_dgrad, void* stream);
+int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, int split3, void* w_fwd, void* w_dgrad,
+                          void* stream);
+/* fp32 x[n] -> hi = bf16(x), lo = bf16(x - hi): the operand pairs of the split-precision ("bf16x3") parity mode */
+int dfb_split_bf16x2(const float* x, long long n, void* hi, void* lo, void* stream);
 int dfb_conv2d(const dfb_conv_args* args, void* stream);
 /* args as for the forward (x sources, geometry) with args->y = grad_y (bf16, input).  wacc: fp32 workspace
  * [k*k][cout][cin_total] (zeroed inside); grad_w: fp32 torch layout, overwritten or (accumulate) added to. */
@@ -224,15 +229,17 @@ int dfb_conv2d_wgrad(const dfb_conv_args* args, float* wacc, float* grad_w, int 
  *   dfb_bn_gelu_apply: y = GELU(a*x + b).
  *   dfb_bn_gelu_backward: gx = dL/dx from gy = dL/dy; g_gamma / g_beta / g_bias (+=); red: double[2*C] workspace.
  *   dfb_channel_sum: out[c] += sum over pixels of g[:, c] (bias gradient of the un-normalised decoder convolutions).
- *   dfb_upsample2x: backward = 0: in [n,h,w,C] -> out [n,2h,2w,C]; backward = 1: in = grad_out [n,2h,2w,C] -> out [n,h,w,C]. */
+ *   dfb_upsample2x: backward = 0: in [n,h,w,C] -> out [n,2h,2w,C]; backward = 1: in = grad_out [n,2h,2w,C] -> out [n,h,w,C].
+ * f32 = 1 selects fp32 tensors (parity mode) instead of bf16; dfb_channel_sum can also accumulate [2][C] sum / sum of
+ * squares in double (stats2) -- the BatchNorm statistics of an fp32 tensor. */
 int dfb_bn2d_finalize(const double* stats, double count, int C, int training, float eps, float momentum,
                       const float* gamma, const float* beta, float* running_mean, float* running_var, float* bn,
                       void* stream);
-int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, void* stream);
+int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, int f32, void* stream);
 int dfb_bn_gelu_backward(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
-                         double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, void* stream);
-int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, void* stream);
-int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int backward, void* stream);
+                         double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, int f32, void* stream);
+int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, double* stats2, int f32, void* stream);
+int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int backward, int f32, void* stream);
 
 /* ------------------------------------------------------------------ per-point decoder stages
  * ConvGRU / ConvGRUDecoder / LinearDecoder (REF/src/models/basic/decoder.py:71-119, 177-253).  The gate and MLP
@@ -245,21 +252,23 @@ int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int ba
  *   dfb_gru_bwd1/2:     the two elementwise stages of the backward of one GRU iteration (see csrc/gru_elem.cu)
  *   dfb_acc_bf16:       acc fp32 += a (+ b), a / b bf16
  *   dfb_head_out:       flow[n,3] = Linear(32,3)(GELU(y1))  and its backward (dy1, grad W2 [3,32] +=, grad b2 +=)
- *   dfb_offset_encode_backward: grad W [cx,3] += dx^T offsets, grad b += sum dx   (dx fp32 [n_pad,cx]) */
-int dfb_offset_encode(const float* offs, const float* w, const float* b, int n, int n_pad, int cx, void* x, void* stream);
+ *   dfb_offset_encode_backward: grad W [cx,3] += dx^T offsets, grad b += sum dx   (dx fp32 [n_pad,cx])
+ * f32 = 1: the gate / head tensors (x, zr_pre, q_pre, rh, dq_pre, dzr_pre, d_rh, y1, dy1, a, b) are fp32 (parity mode). */
+int dfb_offset_encode(const float* offs, const float* w, const float* b, int n, int n_pad, int cx, void* x, int f32,
+                      void* stream);
 int dfb_offset_encode_backward(const float* dx, const float* offs, int n, int cx, float* gw, float* gb, void* stream);
 int dfb_to_bf16_pad(const float* src, int n, int n_pad, int C, void* dst, void* stream);
-int dfb_gru_rh(const void* zr_pre, const float* h, int n, int n_pad, void* rh, void* stream);
+int dfb_gru_rh(const void* zr_pre, const float* h, int n, int n_pad, void* rh, int f32, void* stream);
 int dfb_gru_update(const void* zr_pre, const void* q_pre, const float* h, int n, int n_pad, float* h_new, void* hb_new,
-                   void* stream);
+                   int f32, void* stream);
 int dfb_gru_bwd1(const void* zr_pre, const void* q_pre, const float* h, const float* dh_new, int n, int n_pad,
-                 void* dq_pre, void* dzr_pre, float* dh_acc, void* stream);
+                 void* dq_pre, void* dzr_pre, float* dh_acc, int f32, void* stream);
 int dfb_gru_bwd2(const void* zr_pre, const float* h, const void* d_rh, int n, int n_pad, void* dzr_pre, float* dh_acc,
-                 void* stream);
-int dfb_acc_bf16(float* acc, const void* a, const void* b, long long n_elems, void* stream);
-int dfb_head_out(const void* y1, const float* w2, const float* b2, int n, float* flow, void* stream);
+                 int f32, void* stream);
+int dfb_acc_bf16(float* acc, const void* a, const void* b, long long n_elems, int f32, void* stream);
+int dfb_head_out(const void* y1, const float* w2, const float* b2, int n, float* flow, int f32, void* stream);
 int dfb_head_out_backward(const void* y1, const float* w2, const float* dflow, int n, int n_pad, void* dy1, float* gw2,
-                          float* gb2, void* stream);
+                          float* gb2, int f32, void* stream);
 
 /* ------------------------------------------------------------------ fused persistent GRU decoder (tensor cores)
  * ConvGRUDecoder.forward_single for all points at once (REF/src/models/basic/decoder.py:210-237, 184-193): offset

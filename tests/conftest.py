@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # torch comparators (cuDNN / cuBLAS) must be strict fp32 in forward AND backward: the autograd backward runs outside any
+    # `cudnn.flags(...)` context, and cudnn.allow_tf32 defaults to True
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def pytest_collection_modifyitems(config, items):

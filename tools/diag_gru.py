@@ -26,11 +26,13 @@ def main(stage):
     gflow = torch.randn(n0, 3, device=DEV)
     print("points", n0, flush=True)
     head.compute_dtype = torch.float32
+    head.use_library = True
     i32, u32 = img.float().requires_grad_(True), unet.float().requires_grad_(True)
     ref = head.forward_flat(i32, u32, idx, B, n0)
     ref.backward(gflow)
     ref_g = {k: p.grad.clone() for k, p in head.named_parameters()}
     head.zero_grad()
+    head.use_library = False
     head.compute_dtype = torch.bfloat16
     for mode in (["fused"] if stage != "both" else ["unfused", "fused"]):
         os.environ["DFB_GRU"] = mode
