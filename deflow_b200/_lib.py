@@ -29,7 +29,9 @@ class IndexArgs(C.Structure):
                 ("blk_cnt", C.c_void_p), ("pt_slot", C.c_void_p), ("counts", C.c_void_p), ("pt_xyz", C.c_void_p),
                 ("pt_coor", C.c_void_p), ("pt_idx", C.c_void_p), ("pt_offs", C.c_void_p), ("pt_pillar", C.c_void_p),
                 ("pil_cnt", C.c_void_p), ("pil_coor", C.c_void_p), ("pil_pix", C.c_void_p),
-                ("pil_start", C.c_void_p), ("sorted_pt", C.c_void_p)]
+                ("pil_start", C.c_void_p), ("sorted_pt", C.c_void_p), ("csr_rec", C.c_void_p),
+                ("scan_ws", C.c_void_p), ("tickets", C.c_void_p), ("zero_base", C.c_void_p),
+                ("zero_bytes", C.c_longlong)]
 
 
 class PfnArgs(C.Structure):
@@ -43,7 +45,8 @@ class PfnArgs(C.Structure):
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
                 ("running_var", C.c_void_p), ("pil_mean", C.c_void_p), ("stats", C.c_void_p),
                 ("bn_params", C.c_void_p), ("pil_feats", C.c_void_p), ("image", C.c_void_p),
-                ("image_bf16", C.c_int), ("pil_cap", C.c_longlong)]
+                ("image_bf16", C.c_int), ("pil_cap", C.c_longlong), ("csr_rec", C.c_void_p), ("pt_mask", C.c_void_p),
+                ("partials", C.c_void_p), ("image_ready_event", C.c_void_p)]
 
 
 class PfnBwdArgs(C.Structure):
@@ -144,12 +147,14 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.restype = i32
         fn.argtypes = args
+    lib.dfb_index_scan_workspace.restype = i64
+    lib.dfb_index_scan_workspace.argtypes = [i32, i64, i64]
     return sig
 
 
 EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size", "dfb_dynamic_voxelize_forward",
            "dfb_scatter_index", "dfb_scatter_reduce", "dfb_dynamic_point_to_voxel_backward", "dfb_index_workspace",
-           "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_decoder_gather",
+           "dfb_index_scan_workspace", "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_decoder_gather",
            "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_split_bf16x2", "dfb_conv2d", "dfb_conv2d_wgrad",
            "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",

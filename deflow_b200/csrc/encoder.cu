@@ -8,10 +8,11 @@
 // Here the [N,9] and [N,32] per-point tensors are never written to HBM: every pass recomputes the
 // 9 decorations from the 12-byte point and the pillar mean/centre.  Passes:
 //   pillar_mean  (CSR segment sum, 8 lanes per pillar)
-//   stats x2     (per-frame BatchNorm batch statistics: sum(y), then sum((y-mean)^2))
+//   moments      (per-frame first / second moments of the 9 decorated features -> BatchNorm batch statistics)
 //   bn_finalize  (scale/shift per frame + the 2B sequential running-stat updates)
-//   pfn_pillar   (warp per pillar, lane = channel: Linear+BN+ReLU+mean, writes the NHWC image)
-// Backward: two pillar-centric passes (BN reduction terms, then weight gradient) + finalize.
+//   pfn_points   (thread per point: Linear+BN+ReLU; warp per 32 points: pillar means straight into the NHWC image)
+//   straddlers   (pillars that cross a 32-point group boundary)
+// Backward: one pillar-centric pass over the saved ReLU masks + a finalize block.
 #include "common.cuh"
 #include "../../include/deflow_b200.h"
 
@@ -35,11 +36,14 @@ __device__ __forceinline__ void decorate(float x, float y, float z, float mx, fl
   f[8] = __fsub_rn(z, __fadd_rn(__fmul_rn((float)cz, G.vz), G.oz));
 }
 
+// All passes stream through csr_rec: (x, y, z, pillar id) of every valid point in CSR (pillar-sorted) order, written
+// by the pillar index (pillar_index.cu:k_fill_csr).  One coalesced 16-byte load per point, no indirection.
+__device__ __forceinline__ int rec_q(const float4& r) { return __float_as_int(r.w); }
+
 // ---------------------------------------------------------------- pillar mean (cluster_scatter)
 __global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ counts, int F,
-                                                     const float* __restrict__ pt_xyz,
-                                                     const int* __restrict__ pil_start,
-                                                     const int* __restrict__ sorted_pt, float* __restrict__ pil_mean) {
+                                                     const float4* __restrict__ rec,
+                                                     const int* __restrict__ pil_start, float* __restrict__ pil_mean) {
   const int M = counts[3 * F + 1 + F];
   const int sub = threadIdx.x & 7;
   const int groups = (gridDim.x * blockDim.x) >> 3;
@@ -48,8 +52,8 @@ __global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ cou
     int s0 = 0, s1 = 0;
     if (q < M) { s0 = pil_start[q]; s1 = pil_start[q + 1]; }
     for (int j = s0 + sub; j < s1; j += 8) {
-      const int p = sorted_pt[j];
-      sx += pt_xyz[3 * (size_t)p]; sy += pt_xyz[3 * (size_t)p + 1]; sz += pt_xyz[3 * (size_t)p + 2];
+      const float4 r = __ldg(rec + j);
+      sx += r.x; sy += r.y; sz += r.z;
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
@@ -69,11 +73,12 @@ __global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ cou
 // ---------------------------------------------------------------- BatchNorm batch statistics from moments
 // y = W f is linear in the 9 decorated features, so the per-frame mean / variance of all 32 channels follow from
 // S1 = sum f (9) and S2 = sum f f^T (45 upper-triangular entries): one light pass, 54 accumulators per thread,
-// instead of two passes over the 32 outputs.  mom layout [F][54] (double): S1[9] | S2[45] (row-major upper triangle).
+// instead of two passes over the 32 outputs.  mom layout [F][64] (double): S1[9] | S2[45] (row-major upper triangle).
 constexpr int PFN_MOM = 54;
+constexpr int PFN_MOM_PITCH = 64;
 
 __global__ void __launch_bounds__(256) k_pfn_moments(const int* __restrict__ counts, int F, PfnGeom G,
-                                                     const float* __restrict__ pt_xyz, const int* __restrict__ pt_pillar,
+                                                     const float4* __restrict__ rec,
                                                      const int* __restrict__ pil_coor, const float* __restrict__ pil_mean,
                                                      double* __restrict__ mom) {
   __shared__ float red[8][PFN_MOM];
@@ -82,18 +87,18 @@ __global__ void __launch_bounds__(256) k_pfn_moments(const int* __restrict__ cou
   float acc[PFN_MOM];
 #pragma unroll
   for (int i = 0; i < PFN_MOM; ++i) acc[i] = 0.f;
-  for (int p = p0 + blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += gridDim.x * blockDim.x) {
-    const float x = pt_xyz[3 * (size_t)p], y = pt_xyz[3 * (size_t)p + 1], z = pt_xyz[3 * (size_t)p + 2];
-    const int q = pt_pillar[p];
+  for (int j = p0 + blockIdx.x * blockDim.x + threadIdx.x; j < p1; j += gridDim.x * blockDim.x) {
+    const float4 r = __ldg(rec + j);
+    const int q = rec_q(r);
     float fe[PFN_K];
-    decorate(x, y, z, pil_mean[3 * (size_t)q], pil_mean[3 * (size_t)q + 1], pil_mean[3 * (size_t)q + 2],
+    decorate(r.x, r.y, r.z, pil_mean[3 * (size_t)q], pil_mean[3 * (size_t)q + 1], pil_mean[3 * (size_t)q + 2],
              pil_coor[3 * (size_t)q], pil_coor[3 * (size_t)q + 1], pil_coor[3 * (size_t)q + 2], G, fe);
     int o = PFN_K;
 #pragma unroll
-    for (int j = 0; j < PFN_K; ++j) {
-      acc[j] += fe[j];
+    for (int jj = 0; jj < PFN_K; ++jj) {
+      acc[jj] += fe[jj];
 #pragma unroll
-      for (int k = j; k < PFN_K; ++k) { acc[o] = fmaf(fe[j], fe[k], acc[o]); ++o; }
+      for (int k = jj; k < PFN_K; ++k) { acc[o] = fmaf(fe[jj], fe[k], acc[o]); ++o; }
     }
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -106,72 +111,104 @@ __global__ void __launch_bounds__(256) k_pfn_moments(const int* __restrict__ cou
   if (threadIdx.x < PFN_MOM) {
     double s = 0.0;
     for (int i = 0; i < 8; ++i) s += (double)red[i][threadIdx.x];
-    if (s != 0.0) atomicAdd(&mom[(size_t)f * PFN_MOM + threadIdx.x], s);
+    if (s != 0.0) atomicAdd(&mom[(size_t)f * PFN_MOM_PITCH + threadIdx.x], s);
   }
 }
 
-// One warp: per-frame mean / variance of W f from the moments (double), scale/shift per frame and the sequential
-// running-statistics updates in the reference's call order pc0[0..B-1], pc1[0..B-1] (encoder.py:624-627,
-// DeFlow.forward deflow.py:82-83).
-__global__ void k_bn_finalize(const int* __restrict__ counts, int F, int training, float eps, float momentum,
-                              const double* __restrict__ mom, const float* __restrict__ weight,
-                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                              float* __restrict__ running_mean, float* __restrict__ running_var,
-                              float* __restrict__ bn_params) {
-  const int c = threadIdx.x;
-  if (c >= PFN_C) return;
+// One block, thread = (frame slot, channel): per-frame mean / variance of W f from the moments (double) and the
+// scale/shift rows, 32 frames at a time; then one warp applies the sequential running-statistics updates in the
+// reference's call order pc0[0..B-1], pc1[0..B-1] (encoder.py:624-627, DeFlow.forward deflow.py:82-83).
+__global__ void __launch_bounds__(1024) k_bn_finalize(const int* __restrict__ counts, int F, int training, float eps,
+                                                      float momentum, const double* __restrict__ mom,
+                                                      const float* __restrict__ weight, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                      float* __restrict__ running_var, float* __restrict__ bn_params) {
+  __shared__ float s_mean[32][PFN_C], s_unb[32][PFN_C];
+  __shared__ int s_n[32];
+  const int c = threadIdx.x & 31, slot = threadIdx.x >> 5;
   float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 1.f;
+  const float rm0 = rm, rv0 = rv;
   const float g = gamma[c], b = beta[c];
   double w[PFN_K];
+#pragma unroll
   for (int k = 0; k < PFN_K; ++k) w[k] = (double)weight[c * PFN_K + k];
-  for (int f = 0; f < F; ++f) {
-    const int n = counts[f];
-    float mean, var;
-    if (training && n > 0) {
-      const double* m = mom + (size_t)f * PFN_MOM;
-      double s1 = 0.0, s2 = 0.0;
-      int o = PFN_K;
-      for (int j = 0; j < PFN_K; ++j) {
-        s1 += w[j] * m[j];
-        for (int k = j; k < PFN_K; ++k) s2 += (j == k ? 1.0 : 2.0) * w[j] * w[k] * m[o++];
+  for (int f0 = 0; f0 < F; f0 += 32) {
+    const int f = f0 + slot;
+    if (f < F) {
+      const int n = counts[f];
+      float mean = rm0, var = rv0;
+      float unb = 0.f;
+      if (training && n > 0) {
+        const double* m = mom + (size_t)f * PFN_MOM_PITCH;
+        double s1 = 0.0, s2 = 0.0;
+        int o = PFN_K;
+#pragma unroll
+        for (int j = 0; j < PFN_K; ++j) {
+          s1 += w[j] * m[j];
+#pragma unroll
+          for (int k = j; k < PFN_K; ++k) s2 += (j == k ? 1.0 : 2.0) * w[j] * w[k] * m[o++];
+        }
+        const double mu = s1 / n;
+        double ssq = s2 - s1 * mu;  // sum (y - mean)^2
+        if (ssq < 0.0) ssq = 0.0;
+        mean = (float)mu;
+        var = (float)(ssq / n);  // biased, used to normalise
+        unb = n > 1 ? (float)(ssq / (n - 1)) : 0.f;
       }
-      const double mu = s1 / n;
-      double ssq = s2 - s1 * mu;  // sum (y - mean)^2
-      if (ssq < 0.0) ssq = 0.0;
-      mean = (float)mu;
-      var = (float)(ssq / n);  // biased, used to normalise
-      if (n > 1) {
-        rm = (1.f - momentum) * rm + momentum * mean;
-        rv = (1.f - momentum) * rv + momentum * (float)(ssq / (n - 1));
-      }
-    } else {
-      mean = rm; var = rv;
+      const float rstd = 1.0f / sqrtf(var + eps);
+      const float a = g * rstd;
+      float* o = bn_params + (size_t)f * 4 * PFN_C;
+      o[c] = a;
+      o[PFN_C + c] = b - mean * a;
+      o[2 * PFN_C + c] = mean;
+      o[3 * PFN_C + c] = rstd;
+      s_mean[slot][c] = mean; s_unb[slot][c] = unb;
+      if (c == 0) s_n[slot] = n;
     }
-    const float rstd = 1.0f / sqrtf(var + eps);
-    const float a = g * rstd;
-    float* o = bn_params + (size_t)f * 4 * PFN_C;
-    o[c] = a;
-    o[PFN_C + c] = b - mean * a;
-    o[2 * PFN_C + c] = mean;
-    o[3 * PFN_C + c] = rstd;
+    __syncthreads();
+    if (slot == 0 && training) {
+      const int lim = min(32, F - f0);
+      for (int i = 0; i < lim; ++i) {
+        if (s_n[i] > 1) {
+          rm = (1.f - momentum) * rm + momentum * s_mean[i][c];
+          rv = (1.f - momentum) * rv + momentum * s_unb[i][c];
+        }
+      }
+    }
+    __syncthreads();
   }
-  if (training && running_mean) { running_mean[c] = rm; running_var[c] = rv; }
+  if (slot == 0 && training && running_mean) { running_mean[c] = rm; running_var[c] = rv; }
 }
 
 // ---------------------------------------------------------------- point pass (forward)
-// Thread per point in CSR (pillar-sorted) order: all 32 channels of Linear + BN + ReLU with packed fp32x2 FMAs
-// (weights broadcast from shared memory), then a transposed pass over a [256 points x 32 channels] shared tile
-// (thread = channel x group of 32 consecutive points) forms the per-pillar sums: one coalesced 128-byte
-// red.global.add per pillar and group, no per-point atomics.
+// Phase 1, thread per point in CSR order: all 32 channels of Linear + BN + ReLU with packed fp32x2 FMAs (weights
+// broadcast from shared memory) into a [256 points x 32 channels] shared tile; the 32 ReLU decisions of the point are
+// saved as one mask word for the backward.
+// Phase 2, warp per group of 32 consecutive points, lane = channel: sequential segment sums.  A pillar that lies
+// inside one group (the common case: ~4 points per pillar) is finished on the spot -- mean, voxel feature row, NHWC
+// image row -- with no atomics and no later pass.  Pillars that straddle group boundaries leave per-group partial
+// sums (part[G][0] = the leading segment that began in an earlier group, part[G][1] = the trailing segment that
+// continues into the next one); k_pfn_straddlers adds them up in order.  Deterministic.
+template <bool BF16>
+__device__ __forceinline__ void store_pillar(float v, int q, int pix, int c, float* __restrict__ pil_feats,
+                                             void* __restrict__ image) {
+  if (pil_feats) pil_feats[(size_t)q * PFN_C + c] = v;
+  if (BF16) reinterpret_cast<__nv_bfloat16*>(image)[(size_t)pix * PFN_C + c] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(image)[(size_t)pix * PFN_C + c] = v;
+}
+
+template <bool BF16>
 __global__ void __launch_bounds__(256) k_pfn_points(const int* __restrict__ counts, int F, int HW, PfnGeom G,
-                                                    const float* __restrict__ pt_xyz, const int* __restrict__ pt_pillar,
-                                                    const int* __restrict__ pil_coor, const int* __restrict__ pil_pix,
-                                                    const int* __restrict__ sorted_pt, const float* __restrict__ pil_mean,
-                                                    const float* __restrict__ weight, const float* __restrict__ bn_params,
-                                                    float* __restrict__ pil_sum) {
+                                                    const float4* __restrict__ rec, const int* __restrict__ pil_coor,
+                                                    const int* __restrict__ pil_pix, const int* __restrict__ pil_start,
+                                                    const float* __restrict__ pil_mean, const float* __restrict__ weight,
+                                                    const float* __restrict__ bn_params, unsigned* __restrict__ pt_mask,
+                                                    float* __restrict__ part, float* __restrict__ pil_feats,
+                                                    void* __restrict__ image) {
   __shared__ __align__(16) float Wp[PFN_K][PFN_C];   // Wp[k][c]
   __shared__ float T[256][PFN_C + 1];
-  __shared__ int Q[257];
+  __shared__ int Q[256], PX[256], CN[256];
+  __shared__ unsigned char FL[256];                   // bit 0: first point of its pillar, bit 1: last point
   extern __shared__ float sAB[];                      // [F][2][32] scale / shift per frame
   const int n = counts[2 * F + F];
   for (int i = threadIdx.x; i < PFN_C * PFN_K; i += blockDim.x) Wp[i % PFN_K][i / PFN_K] = weight[i];
@@ -183,14 +220,14 @@ __global__ void __launch_bounds__(256) k_pfn_points(const int* __restrict__ coun
   for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
     const int j = base + threadIdx.x;
     int q = -1;
-    float2 y2[PFN_C / 2];
     if (j < n) {
-      const int p = sorted_pt[j];
-      q = pt_pillar[p];
-      const float x = pt_xyz[3 * (size_t)p], yy = pt_xyz[3 * (size_t)p + 1], z = pt_xyz[3 * (size_t)p + 2];
+      const float4 r = __ldg(rec + j);
+      q = rec_q(r);
+      const int s0 = pil_start[q], s1 = pil_start[q + 1], pix = pil_pix[q];
       float fe[PFN_K];
-      decorate(x, yy, z, pil_mean[3 * (size_t)q], pil_mean[3 * (size_t)q + 1], pil_mean[3 * (size_t)q + 2],
+      decorate(r.x, r.y, r.z, pil_mean[3 * (size_t)q], pil_mean[3 * (size_t)q + 1], pil_mean[3 * (size_t)q + 2],
                pil_coor[3 * (size_t)q], pil_coor[3 * (size_t)q + 1], pil_coor[3 * (size_t)q + 2], G, fe);
+      float2 y2[PFN_C / 2];
 #pragma unroll
       for (int c = 0; c < PFN_C / 2; ++c) y2[c] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -203,30 +240,43 @@ __global__ void __launch_bounds__(256) k_pfn_points(const int* __restrict__ coun
           y2[c4 / 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), fk, y2[c4 / 2 + 1]);
         }
       }
-      const float* ab = sAB + (size_t)(pil_pix[q] / HW) * 2 * PFN_C;
+      const float* ab = sAB + (size_t)(pix / HW) * 2 * PFN_C;
+      unsigned m = 0u;
 #pragma unroll
       for (int c = 0; c < PFN_C / 2; ++c) {
         const float2 a = *reinterpret_cast<const float2*>(ab + 2 * c), b = *reinterpret_cast<const float2*>(ab + PFN_C + 2 * c);
         const float2 v = __ffma2_rn(y2[c], a, b);
+        m |= (v.x > 0.f ? 1u : 0u) << (2 * c);
+        m |= (v.y > 0.f ? 1u : 0u) << (2 * c + 1);
         T[threadIdx.x][2 * c] = fmaxf(v.x, 0.f);
         T[threadIdx.x][2 * c + 1] = fmaxf(v.y, 0.f);
       }
+      pt_mask[j] = m;
+      PX[threadIdx.x] = pix;
+      CN[threadIdx.x] = s1 - s0;
+      FL[threadIdx.x] = (unsigned char)((j == s0 ? 1 : 0) | (j + 1 == s1 ? 2 : 0));
     }
     Q[threadIdx.x] = q;
-    if (threadIdx.x == 0) Q[256] = -2;
     __syncthreads();
     {
       const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+      const size_t G0 = ((size_t)(base >> 5) + g) * 2 * PFN_C;  // this group's two partial rows
       float acc = 0.f;
+      bool started = false;   // the running segment began inside this group
 #pragma unroll 4
       for (int i = 0; i < 32; ++i) {
         const int pt = g * 32 + i;
         const int qq = Q[pt];
         if (qq < 0) break;                     // past the end of the point list (warp-uniform)
+        const int fl = FL[pt];
+        if (fl & 1) { acc = 0.f; started = true; }
         acc += T[pt][c];
-        if (i == 31 || Q[pt + 1] != qq) {      // segment ends inside or at the end of this group (warp-uniform)
-          atomicAdd(&pil_sum[(size_t)qq * PFN_C + c], acc);
+        if (fl & 2) {                          // the pillar ends here
+          if (started) store_pillar<BF16>(__fdiv_rn(acc, (float)CN[pt]), qq, PX[pt], c, pil_feats, image);
+          else part[G0 + c] = acc;             // leading segment of a pillar that began in an earlier group
           acc = 0.f;
+        } else if (i == 31) {                  // the pillar continues into the next group
+          part[G0 + (started ? PFN_C : 0) + c] = acc;
         }
       }
     }
@@ -234,28 +284,26 @@ __global__ void __launch_bounds__(256) k_pfn_points(const int* __restrict__ coun
   }
 }
 
-// pillar sums -> means (in place: pil_feats) and the NHWC pseudo-image row of every pillar
+// warp per group boundary: the group in which a straddling pillar BEGINS adds up that pillar's partial sums
 template <bool BF16>
-__global__ void __launch_bounds__(256) k_pfn_image(const int* __restrict__ counts, int F, const int* __restrict__ pil_start,
-                                                   const int* __restrict__ pil_pix, float* __restrict__ pil_feats,
-                                                   void* __restrict__ image) {
-  const int M = counts[3 * F + 1 + F];
-  const long long total = (long long)M * 8;  // 4 channels per thread
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(e >> 3), c4 = (int)(e & 7) * 4;
-    const float n = (float)(pil_start[q + 1] - pil_start[q]);
-    float4 v = *reinterpret_cast<float4*>(pil_feats + (size_t)q * PFN_C + c4);
-    v.x = __fdiv_rn(v.x, n); v.y = __fdiv_rn(v.y, n); v.z = __fdiv_rn(v.z, n); v.w = __fdiv_rn(v.w, n);
-    *reinterpret_cast<float4*>(pil_feats + (size_t)q * PFN_C + c4) = v;
-    const size_t o = (size_t)pil_pix[q] * PFN_C + c4;
-    if (BF16) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-      uint2 r;
-      r.x = *reinterpret_cast<unsigned*>(&a); r.y = *reinterpret_cast<unsigned*>(&b);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(image) + o) = r;
-    } else {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(image) + o) = v;
-    }
+__global__ void __launch_bounds__(256) k_pfn_straddlers(const int* __restrict__ counts, int F,
+                                                        const float4* __restrict__ rec, const int* __restrict__ pil_pix,
+                                                        const int* __restrict__ pil_start, const float* __restrict__ part,
+                                                        float* __restrict__ pil_feats, void* __restrict__ image) {
+  const int n = counts[2 * F + F];
+  const int c = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_groups = (n + 31) >> 5;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+    const int jl = 32 * g + 31;
+    if (jl >= n) break;                        // a partial last group has nothing after it
+    const int q = rec_q(__ldg(rec + jl));
+    const int s0 = pil_start[q], s1 = pil_start[q + 1];
+    if (s1 <= jl + 1 || s0 < 32 * g) continue; // ends here, or began earlier (then an earlier group owns it)
+    float tot = part[((size_t)g * 2 + 1) * PFN_C + c];
+    const int g_last = (s1 - 1) >> 5;
+    for (int g2 = g + 1; g2 <= g_last; ++g2) tot += part[(size_t)g2 * 2 * PFN_C + c];
+    store_pillar<BF16>(__fdiv_rn(tot, (float)(s1 - s0)), q, pil_pix[q], c, pil_feats, image);
   }
 }
 
@@ -266,24 +314,19 @@ __global__ void __launch_bounds__(256) k_pfn_image(const int* __restrict__ count
 //   sum_p xhat f_k = rstd (sum_j W_cj S2[j,k] - mean S1[k])          (S1, S2 = the forward's feature moments)
 // so  A2 = sum gy^ xhat = rstd (W_c . T_c - mean A1),  grad_gamma = A2,  grad_beta = A1  and
 //   grad_W[c,k] = a_c (T[c][k] - (A1/N) S1[k] - (A2/N) sum_p xhat f_k)      (training; eval: a_c T[c][k]).
-// grid (X, F): warp per pillar, lane = channel; bwd_acc layout [F][32][10] (double): A1 | T[9].
+// grid (X, F): warp per pillar, lane = channel; the points come as broadcast 16-byte CSR records plus the ReLU mask
+// word the forward saved (no recomputation of the linear layer).  bwd_acc layout [F][32][10] (double): A1 | T[9].
 template <bool BF16>
-__global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F, int HW, PfnGeom G,
-                                                 const float* __restrict__ pt_xyz, const int* __restrict__ pil_coor,
-                                                 const int* __restrict__ pil_pix, const int* __restrict__ pil_start,
-                                                 const int* __restrict__ sorted_pt, const float* __restrict__ pil_mean,
-                                                 const float* __restrict__ weight, const float* __restrict__ bn_params,
+__global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F, PfnGeom G,
+                                                 const float4* __restrict__ rec, const unsigned* __restrict__ pt_mask,
+                                                 const int* __restrict__ pil_coor, const int* __restrict__ pil_pix,
+                                                 const int* __restrict__ pil_start, const float* __restrict__ pil_mean,
                                                  const void* __restrict__ grad_image, double* __restrict__ bwd_acc) {
   __shared__ float red[8][PFN_C][PFN_K + 2];
   const int f = blockIdx.y;
   const int q0 = counts[3 * F + 1 + f], q1 = counts[3 * F + 1 + f + 1];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  float w[PFN_K];
-#pragma unroll
-  for (int k = 0; k < PFN_K; ++k) w[k] = weight[lane * PFN_K + k];
-  const float* bp = bn_params + (size_t)f * 4 * PFN_C;
-  const float a = bp[lane], b = bp[PFN_C + lane];
   float acc[PFN_K], a1 = 0.f;
 #pragma unroll
   for (int k = 0; k < PFN_K; ++k) acc[k] = 0.f;
@@ -297,23 +340,11 @@ __global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts,
     const int cz = pil_coor[3 * (size_t)q], cy = pil_coor[3 * (size_t)q + 1], cx = pil_coor[3 * (size_t)q + 2];
     // within a pillar f[p,k] = xyz[p, k%3] - off[k]: accumulate the masked sums of (1, x, y, z) and expand once
     float u0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
-    for (int base = s0; base < s1; base += 32) {
-      const int cnt = min(32, s1 - base);
-      float lx = 0.f, ly = 0.f, lz = 0.f;
-      if (lane < cnt) {
-        const int p = sorted_pt[base + lane];
-        lx = pt_xyz[3 * (size_t)p]; ly = pt_xyz[3 * (size_t)p + 1]; lz = pt_xyz[3 * (size_t)p + 2];
-      }
-      for (int j = 0; j < cnt; ++j) {
-        const float x = __shfl_sync(0xffffffffu, lx, j), y = __shfl_sync(0xffffffffu, ly, j),
-                    z = __shfl_sync(0xffffffffu, lz, j);
-        float fe[PFN_K];
-        decorate(x, y, z, mx, my, mz, cz, cy, cx, G, fe);
-        float lin = 0.f;
-#pragma unroll
-        for (int k = 0; k < PFN_K; ++k) lin = fmaf(w[k], fe[k], lin);
-        if (fmaf(lin, a, b) > 0.f) { u0 += 1.f; ux += x; uy += y; uz += z; }  // ReLU mask
-      }
+#pragma unroll 2
+    for (int j = s0; j < s1; ++j) {
+      const float4 r = __ldg(rec + j);
+      const unsigned m = __ldg(pt_mask + j);
+      if ((m >> lane) & 1u) { u0 += 1.f; ux += r.x; uy += r.y; uz += r.z; }  // ReLU mask
     }
     // offsets of the three decoration groups: raw (0), cluster mean, pillar centre
     const float ox = __fadd_rn(__fmul_rn((float)cx, G.vx), G.ox), oy = __fadd_rn(__fmul_rn((float)cy, G.vy), G.oy),
@@ -335,16 +366,27 @@ __global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts,
   }
 }
 
-// thread = channel: the algebra above, in double, summed over the frames
-__global__ void k_pfn_bwd_finalize(const int* __restrict__ counts, int F, int training, const double* __restrict__ bwd_acc,
-                                   const double* __restrict__ mom, const float* __restrict__ bn_params,
-                                   const float* __restrict__ weight, float* __restrict__ grad_weight,
-                                   float* __restrict__ grad_gamma, float* __restrict__ grad_beta) {
-  const int c = threadIdx.x;
-  if (c >= PFN_C) return;
-  double w[PFN_K], gw[PFN_K], gg = 0.0, gb = 0.0;
-  for (int k = 0; k < PFN_K; ++k) { w[k] = (double)weight[c * PFN_K + k]; gw[k] = 0.0; }
-  for (int f = 0; f < F; ++f) {
+// One block, thread = (frame slot, channel): the algebra above in double, frames strided over the 32 slots, then a
+// reduction over the slots through shared memory.
+__device__ __forceinline__ int tri_index(int j, int k) {  // position of S2[j][k], j <= k, in the packed upper triangle
+  return PFN_K + j * PFN_K - (j * (j - 1)) / 2 + (k - j);
+}
+
+__global__ void __launch_bounds__(1024) k_pfn_bwd_finalize(const int* __restrict__ counts, int F, int training,
+                                                           const double* __restrict__ bwd_acc,
+                                                           const double* __restrict__ mom,
+                                                           const float* __restrict__ bn_params,
+                                                           const float* __restrict__ weight,
+                                                           float* __restrict__ grad_weight, float* __restrict__ grad_gamma,
+                                                           float* __restrict__ grad_beta) {
+  __shared__ double sred[32][PFN_C + 1];
+  const int c = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  double w[PFN_K], out[PFN_K + 2];  // gw[9] | gg | gb
+#pragma unroll
+  for (int k = 0; k < PFN_K; ++k) w[k] = (double)weight[c * PFN_K + k];
+#pragma unroll
+  for (int k = 0; k < PFN_K + 2; ++k) out[k] = 0.0;
+  for (int f = slot; f < F; f += 32) {
     const int n = counts[f];
     if (n <= 0) continue;
     const double* A = bwd_acc + ((size_t)f * PFN_C + c) * (PFN_K + 1);
@@ -352,30 +394,40 @@ __global__ void k_pfn_bwd_finalize(const int* __restrict__ counts, int F, int tr
     const double a = bp[c], mu = bp[2 * PFN_C + c], rstd = bp[3 * PFN_C + c];
     const double A1 = A[0];
     double wt = 0.0;
+#pragma unroll
     for (int k = 0; k < PFN_K; ++k) wt += w[k] * A[1 + k];
     const double A2 = rstd * (wt - mu * A1);
-    gg += A2;
-    gb += A1;
+    out[PFN_K] += A2;
+    out[PFN_K + 1] += A1;
     if (training) {
-      const double* m = mom + (size_t)f * PFN_MOM;  // S1[9] | S2 upper triangle
-      double S2[PFN_K][PFN_K];
-      int o = PFN_K;
-      for (int j = 0; j < PFN_K; ++j)
-        for (int k = j; k < PFN_K; ++k) { S2[j][k] = m[o]; S2[k][j] = m[o]; ++o; }
+      const double* m = mom + (size_t)f * PFN_MOM_PITCH;  // S1[9] | S2 upper triangle
       const double m1 = A1 / n, m2 = A2 / n;
+#pragma unroll
       for (int k = 0; k < PFN_K; ++k) {
         double ws2 = 0.0;
-        for (int j = 0; j < PFN_K; ++j) ws2 += w[j] * S2[j][k];
+#pragma unroll
+        for (int j = 0; j < PFN_K; ++j) ws2 += w[j] * m[j <= k ? tri_index(j, k) : tri_index(k, j)];
         const double sxf = rstd * (ws2 - mu * m[k]);  // sum_p xhat[p,c] f[p,k]
-        gw[k] += a * (A[1 + k] - m1 * m[k] - m2 * sxf);
+        out[k] += a * (A[1 + k] - m1 * m[k] - m2 * sxf);
       }
     } else {
-      for (int k = 0; k < PFN_K; ++k) gw[k] += a * A[1 + k];
+#pragma unroll
+      for (int k = 0; k < PFN_K; ++k) out[k] += a * A[1 + k];
     }
   }
-  for (int k = 0; k < PFN_K; ++k) grad_weight[c * PFN_K + k] += (float)gw[k];
-  grad_gamma[c] += (float)gg;
-  grad_beta[c] += (float)gb;
+#pragma unroll
+  for (int k = 0; k < PFN_K + 2; ++k) {
+    sred[slot][c] = out[k];
+    __syncthreads();
+    if (slot == 0) {
+      double s = 0.0;
+      for (int i = 0; i < 32; ++i) s += sred[i][c];
+      if (k < PFN_K) grad_weight[c * PFN_K + k] += (float)s;
+      else if (k == PFN_K) grad_gamma[c] += (float)s;
+      else grad_beta[c] += (float)s;
+    }
+    __syncthreads();
+  }
 }
 
 static PfnGeom make_geom(const dfb_pfn_args* a) {
@@ -393,34 +445,44 @@ extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (!a || a->F <= 0 || a->H <= 0 || a->W <= 0) { set_error("dfb_pfn_forward: bad sizes"); return DFB_ERR_ARG; }
   if (a->F > 256) { set_error("dfb_pfn_forward: at most 256 frames per call"); return DFB_ERR_UNSUPPORTED; }
+  if (!a->csr_rec || !a->pt_mask || !a->partials) { set_error("dfb_pfn_forward: csr_rec / pt_mask / partials missing"); return DFB_ERR_ARG; }
   const int F = a->F, HW = a->H * a->W;
   const PfnGeom G = make_geom(a);
   const int sms = sm_count();
+  const float4* rec = (const float4*)a->csr_rec;
   const size_t img_bytes = (size_t)F * HW * PFN_C * (a->image_bf16 ? 2 : 4);
-  cudaMemsetAsync(a->image, 0, img_bytes, st);
-  cudaMemsetAsync(a->stats, 0, sizeof(double) * (size_t)F * 2 * PFN_C, st);      // [F][54] moments fit in [F][64]
-  cudaMemsetAsync(a->pil_feats, 0, sizeof(float) * (size_t)a->pil_cap * PFN_C, st);
-  k_pillar_mean<<<sms * 8, 256, 0, st>>>(a->counts, F, a->pt_xyz, a->pil_start, a->sorted_pt, a->pil_mean);
+  // the dense zero canvas (PointPillarsScatter, encoder.py:135-139).  A caller that zero-fills the image itself on
+  // another stream (to overlap the fill with the index kernels) passes the event that marks its completion.
+  if (!a->image_ready_event) cudaMemsetAsync(a->image, 0, img_bytes, st);
+  cudaMemsetAsync(a->stats, 0, sizeof(double) * (size_t)F * PFN_MOM_PITCH, st);
+  k_pillar_mean<<<sms * 8, 256, 0, st>>>(a->counts, F, rec, a->pil_start, a->pil_mean);
   int launches = 4;
   if (a->training) {
     int bx = (sms * 4 + F - 1) / F;
     if (bx < 1) bx = 1;
     dim3 g(bx, F);
-    k_pfn_moments<<<g, 256, 0, st>>>(a->counts, F, G, a->pt_xyz, a->pt_pillar, a->pil_coor, a->pil_mean, a->stats);
+    k_pfn_moments<<<g, 256, 0, st>>>(a->counts, F, G, rec, a->pil_coor, a->pil_mean, a->stats);
     ++launches;
   }
-  k_bn_finalize<<<1, 32, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum, a->stats, a->weight, a->gamma, a->beta,
-                                  a->running_mean, a->running_var, a->bn_params);
+  k_bn_finalize<<<1, 1024, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum, a->stats, a->weight, a->gamma, a->beta,
+                                    a->running_mean, a->running_var, a->bn_params);
+  if (a->image_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)a->image_ready_event, 0);
   const int dyn = F * 2 * PFN_C * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_pfn_points, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
+    cudaFuncSetAttribute(k_pfn_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
+    cudaFuncSetAttribute(k_pfn_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
     configured = true;
   }
-  k_pfn_points<<<sms * 4, 256, dyn, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pt_pillar, a->pil_coor, a->pil_pix, a->sorted_pt,
-                                         a->pil_mean, a->weight, a->bn_params, a->pil_feats);
-  if (a->image_bf16) k_pfn_image<true><<<sms * 8, 256, 0, st>>>(a->counts, F, a->pil_start, a->pil_pix, a->pil_feats, a->image);
-  else k_pfn_image<false><<<sms * 8, 256, 0, st>>>(a->counts, F, a->pil_start, a->pil_pix, a->pil_feats, a->image);
+  if (a->image_bf16) {
+    k_pfn_points<true><<<sms * 4, 256, dyn, st>>>(a->counts, F, HW, G, rec, a->pil_coor, a->pil_pix, a->pil_start, a->pil_mean,
+                                                  a->weight, a->bn_params, a->pt_mask, a->partials, a->pil_feats, a->image);
+    k_pfn_straddlers<true><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, a->pil_pix, a->pil_start, a->partials, a->pil_feats, a->image);
+  } else {
+    k_pfn_points<false><<<sms * 4, 256, dyn, st>>>(a->counts, F, HW, G, rec, a->pil_coor, a->pil_pix, a->pil_start, a->pil_mean,
+                                                   a->weight, a->bn_params, a->pt_mask, a->partials, a->pil_feats, a->image);
+    k_pfn_straddlers<false><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, a->pil_pix, a->pil_start, a->partials, a->pil_feats, a->image);
+  }
   add_launches(launches);
   return check_launch("dfb_pfn_forward");
 }
@@ -429,21 +491,23 @@ extern "C" int dfb_pfn_backward(const dfb_pfn_bwd_args* b, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (!b) { set_error("dfb_pfn_backward: null args"); return DFB_ERR_ARG; }
   const dfb_pfn_args* a = &b->fwd;
-  const int F = a->F, HW = a->H * a->W;
+  if (!a->csr_rec || !a->pt_mask) { set_error("dfb_pfn_backward: csr_rec / pt_mask missing"); return DFB_ERR_ARG; }
+  const int F = a->F;
   const PfnGeom G = make_geom(a);
   const int sms = sm_count();
+  const float4* rec = (const float4*)a->csr_rec;
   cudaMemsetAsync(b->bwd_stats, 0, sizeof(double) * (size_t)F * PFN_C * (PFN_K + 1), st);
-  int bx = (sms * 4 + F - 1) / F;
+  int bx = (sms * 8 + F - 1) / F;
   if (bx < 1) bx = 1;
   dim3 g(bx, F);
   if (a->image_bf16)
-    k_pfn_bwd<true><<<g, 256, 0, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pil_coor, a->pil_pix, a->pil_start, a->sorted_pt,
-                                       a->pil_mean, a->weight, a->bn_params, b->grad_image, b->bwd_stats);
+    k_pfn_bwd<true><<<g, 256, 0, st>>>(a->counts, F, G, rec, a->pt_mask, a->pil_coor, a->pil_pix, a->pil_start, a->pil_mean,
+                                       b->grad_image, b->bwd_stats);
   else
-    k_pfn_bwd<false><<<g, 256, 0, st>>>(a->counts, F, HW, G, a->pt_xyz, a->pil_coor, a->pil_pix, a->pil_start, a->sorted_pt,
-                                        a->pil_mean, a->weight, a->bn_params, b->grad_image, b->bwd_stats);
-  k_pfn_bwd_finalize<<<1, 32, 0, st>>>(a->counts, F, a->training, b->bwd_stats, a->stats, a->bn_params, a->weight,
-                                       b->grad_weight, b->grad_gamma, b->grad_beta);
+    k_pfn_bwd<false><<<g, 256, 0, st>>>(a->counts, F, G, rec, a->pt_mask, a->pil_coor, a->pil_pix, a->pil_start, a->pil_mean,
+                                        b->grad_image, b->bwd_stats);
+  k_pfn_bwd_finalize<<<1, 1024, 0, st>>>(a->counts, F, a->training, b->bwd_stats, a->stats, a->bn_params, a->weight,
+                                         b->grad_weight, b->grad_gamma, b->grad_beta);
   add_launches(2);
   return check_launch("dfb_pfn_backward");
 }

@@ -49,45 +49,71 @@ __global__ void __launch_bounds__(IDX_BLOCK) k_mark_points(const float* __restri
   if (threadIdx.x == 0) blk_cnt[f * nblk + blk] = total;
 }
 
-// ---------------------------------------------------------------- K2: per-frame scans
-// One 1024-thread block per frame: (a) exclusive scan of the per-block valid counts,
-// (b) exclusive scan of the bitmap popcounts.
-__global__ void __launch_bounds__(1024) k_scan_frame(const unsigned* __restrict__ bitmap, int Wd,
-                                                     int* __restrict__ blk_cnt, int nblk,
-                                                     int* __restrict__ word_rank, int* __restrict__ counts, int F) {
-  __shared__ int sm[33];
-  const int f = blockIdx.x;
-  int carry = 0;
-  for (int base = 0; base < nblk; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < nblk ? blk_cnt[f * nblk + i] : 0;
-    int tot;
-    const int ex = block_excl_scan<1024>(v, sm, tot);
-    if (i < nblk) blk_cnt[f * nblk + i] = carry + ex;  // in place: becomes the block offset
-    carry += tot;
+// ---------------------------------------------------------------- K2: bitmap popcount scan (two levels, one launch)
+// One block per 1024-word segment of a frame's bitmap: exclusive scan of the popcounts inside the segment
+// (word_rank holds segment-local ranks) and the segment total.  The LAST block to finish (threadfence + ticket)
+// scans, warp per frame, the segment totals (-> seg_base) and the per-block valid counts of K1 (-> block offsets in
+// place), then writes the frame offsets: counts = n_valid[F] | n_pil[F] | pt_off[F+1] | pil_off[F+1].
+constexpr int SEG_WORDS = 1024;
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
   }
-  if (threadIdx.x == 0) counts[f] = carry;  // n_valid[f]
-  carry = 0;
-  for (int base = 0; base < Wd; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < Wd ? __popc(bitmap[(size_t)f * Wd + i]) : 0;
-    int tot;
-    const int ex = block_excl_scan<1024>(v, sm, tot);
-    if (i < Wd) word_rank[(size_t)f * Wd + i] = carry + ex;
-    carry += tot;
-  }
-  if (threadIdx.x == 0) counts[F + f] = carry;  // n_pil[f]
+  return v;
 }
 
-// K2b: frame offsets (F is tiny).  counts = n_valid[F] | n_pil[F] | pt_off[F+1] | pil_off[F+1]
-__global__ void k_frame_offsets(int* __restrict__ counts, int F) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+__global__ void __launch_bounds__(1024) k_bitmap_scan(const unsigned* __restrict__ bitmap, int Wd, int S,
+                                                      int* __restrict__ word_rank, int* __restrict__ seg_tot,
+                                                      int* __restrict__ seg_base, int* __restrict__ blk_cnt, int nblk,
+                                                      int* __restrict__ counts, int F, unsigned* __restrict__ ticket) {
+  __shared__ int sm[33];
+  __shared__ int is_last;
+  const int s = blockIdx.x, f = blockIdx.y;
+  const int w = s * SEG_WORDS + threadIdx.x;
+  const int v = w < Wd ? __popc(bitmap[(size_t)f * Wd + w]) : 0;
+  int tot;
+  const int ex = block_excl_scan<1024>(v, sm, tot);
+  if (w < Wd) word_rank[(size_t)f * Wd + w] = ex;
+  if (threadIdx.x == 0) {
+    seg_tot[f * S + s] = tot;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == (unsigned)(S * F - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int ff = wp; ff < F; ff += 32) {
+    int carry = 0;
+    for (int base = 0; base < S; base += 32) {
+      const int i = base + lane;
+      const int t = i < S ? __ldcg(&seg_tot[ff * S + i]) : 0;
+      const int inc = warp_incl_scan(t, lane);
+      if (i < S) seg_base[ff * S + i] = carry + inc - t;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) counts[F + ff] = carry;  // n_pil[f]
+    carry = 0;
+    for (int base = 0; base < nblk; base += 32) {
+      const int i = base + lane;
+      const int t = i < nblk ? blk_cnt[ff * nblk + i] : 0;
+      const int inc = warp_incl_scan(t, lane);
+      if (i < nblk) blk_cnt[ff * nblk + i] = carry + inc - t;  // in place: becomes the block offset
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) counts[ff] = carry;  // n_valid[f]
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     int a = 0, b = 0;
-    for (int f = 0; f < F; ++f) {
-      counts[2 * F + f] = a;
-      counts[3 * F + 1 + f] = b;
-      a += counts[f];
-      b += counts[F + f];
+    for (int ff = 0; ff < F; ++ff) {
+      counts[2 * F + ff] = a;
+      counts[3 * F + 1 + ff] = b;
+      a += counts[ff];
+      b += counts[F + ff];
     }
     counts[2 * F + F] = a;
     counts[3 * F + 1 + F] = b;
@@ -98,7 +124,7 @@ __global__ void k_frame_offsets(int* __restrict__ counts, int F) {
 __global__ void __launch_bounds__(IDX_BLOCK) k_compact(
     const float* __restrict__ pts, const int* __restrict__ keys, int Nmax, int stride, VoxelParams P, int Wd,
     int nblk, int F, int HW, const unsigned* __restrict__ bitmap, const int* __restrict__ word_rank,
-    const int* __restrict__ blk_off, const int* __restrict__ counts, float* __restrict__ pt_xyz,
+    const int* __restrict__ seg_base, int S, const int* __restrict__ blk_off, const int* __restrict__ counts, float* __restrict__ pt_xyz,
     int* __restrict__ pt_coor, long long* __restrict__ pt_idx, float* __restrict__ pt_offs,
     int* __restrict__ pt_pillar, int* __restrict__ pt_slot, int* __restrict__ pil_cnt, int* __restrict__ pil_coor,
     int* __restrict__ pil_pix) {
@@ -131,7 +157,8 @@ __global__ void __launch_bounds__(IDX_BLOCK) k_compact(
       pt_offs[3 * (size_t)dst + 1] = __fsub_rn(y, __fadd_rn(__fadd_rn(__fmul_rn((float)cy, P.vy), P.loy), hy));
       pt_offs[3 * (size_t)dst + 2] = __fsub_rn(z, __fadd_rn(__fadd_rn(__fmul_rn((float)cz, P.vz), P.loz), hz));
       const unsigned word = bitmap[(size_t)f * Wd + (key >> 5)];
-      const int rank = word_rank[(size_t)f * Wd + (key >> 5)] + __popc(word & ((1u << (key & 31)) - 1u));
+      const int rank = seg_base[f * S + (key >> 15)] + word_rank[(size_t)f * Wd + (key >> 5)] +
+                       __popc(word & ((1u << (key & 31)) - 1u));
       const int q = pil_base + rank;
       pt_pillar[dst] = q;
       const int slot = atomicAdd(&pil_cnt[q], 1);
@@ -148,31 +175,65 @@ __global__ void __launch_bounds__(IDX_BLOCK) k_compact(
 }
 
 // ---------------------------------------------------------------- K4: CSR offsets of the pillars
-// One block per frame; pil_start[q] = pt_off[f] + exclusive scan of the counts of that frame.
+// Points and pillars are both stored frame after frame, so pil_start is ONE global exclusive scan of pil_cnt.  Two
+// levels in one launch: block-local scans of 2048 pillars (-> pil_loc, block totals); the last block to finish scans
+// the block totals (-> blk_base).  K5 adds the two.
+constexpr int PSCAN_ITEMS = 2048;
+
 __global__ void __launch_bounds__(1024) k_pillar_scan(const int* __restrict__ pil_cnt, const int* __restrict__ counts,
-                                                      int F, int* __restrict__ pil_start) {
+                                                      int F, int* __restrict__ pil_loc, int* __restrict__ blk_tot,
+                                                      int* __restrict__ blk_base, unsigned* __restrict__ ticket) {
   __shared__ int sm[33];
-  const int f = blockIdx.x;
-  const int q0 = counts[3 * F + 1 + f], q1 = counts[3 * F + 1 + f + 1];
-  int carry = counts[2 * F + f];
-  for (int base = q0; base < q1; base += 1024) {
-    const int q = base + threadIdx.x;
-    const int v = q < q1 ? pil_cnt[q] : 0;
-    int tot;
-    const int ex = block_excl_scan<1024>(v, sm, tot);
-    if (q < q1) pil_start[q] = carry + ex;
-    carry += tot;
+  __shared__ int is_last;
+  const int M = counts[3 * F + 1 + F];
+  const int q = blockIdx.x * PSCAN_ITEMS + 2 * threadIdx.x;
+  int tot = 0;
+  if (blockIdx.x * PSCAN_ITEMS < M) {
+    const int v0 = q < M ? pil_cnt[q] : 0, v1 = q + 1 < M ? pil_cnt[q + 1] : 0;
+    const int ex = block_excl_scan<1024>(v0 + v1, sm, tot);
+    if (q < M) pil_loc[q] = ex;
+    if (q + 1 < M) pil_loc[q + 1] = ex + v0;
   }
-  if (f == F - 1 && threadIdx.x == 0) pil_start[q1] = counts[2 * F + F];
+  if (threadIdx.x == 0) {
+    blk_tot[blockIdx.x] = tot;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int nb = (int)gridDim.x;
+  int carry = 0;
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? __ldcg(&blk_tot[i]) : 0;
+    int t;
+    const int ex = block_excl_scan<1024>(v, sm, t);
+    if (i < nb) blk_base[i] = carry + ex;
+    carry += t;
+  }
 }
 
 // ---------------------------------------------------------------- K5: CSR fill
+// pil_start (final) for every pillar; for every point its CSR position j = pil_start[q] + slot:
+//   sorted_pt[j] = p   and   csr_rec[j] = (x, y, z, q)   -- the 16-byte record every later pass over the points of a
+// pillar reads sequentially (no p -> xyz -> q double indirection in the feature-net kernels).
 __global__ void __launch_bounds__(256) k_fill_csr(const int* __restrict__ counts, int F, int total_cap,
                                                   const int* __restrict__ pt_pillar, const int* __restrict__ pt_slot,
-                                                  const int* __restrict__ pil_start, int* __restrict__ sorted_pt) {
+                                                  const float* __restrict__ pt_xyz, const int* __restrict__ pil_loc,
+                                                  const int* __restrict__ blk_base, int* __restrict__ pil_start,
+                                                  int* __restrict__ sorted_pt, float4* __restrict__ csr_rec) {
   const int n = min(counts[2 * F + F], total_cap);
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-    sorted_pt[pil_start[pt_pillar[p]] + pt_slot[p]] = p;
+  const int M = counts[3 * F + 1 + F];
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int q = t0; q < M; q += stride) pil_start[q] = pil_loc[q] + blk_base[q / PSCAN_ITEMS];
+  if (t0 == 0) pil_start[M] = n;
+  for (int p = t0; p < n; p += stride) {
+    const int q = pt_pillar[p];
+    const int j = pil_loc[q] + blk_base[q / PSCAN_ITEMS] + pt_slot[p];
+    sorted_pt[j] = p;
+    csr_rec[j] = make_float4(pt_xyz[3 * (size_t)p], pt_xyz[3 * (size_t)p + 1], pt_xyz[3 * (size_t)p + 2], __int_as_float(q));
+  }
 }
 
 VoxelParams make_voxel_params(const float* vs, const float* rng) {
@@ -207,6 +268,12 @@ extern "C" int dfb_index_workspace(int F, int Nmax, const float* voxel_size, con
   return DFB_OK;
 }
 
+extern "C" long long dfb_index_scan_workspace(int F, long long bitmap_words_per_frame, long long pil_cap) {
+  const long long S = (bitmap_words_per_frame + SEG_WORDS - 1) / SEG_WORDS;
+  const long long nb = (pil_cap + PSCAN_ITEMS - 1) / PSCAN_ITEMS;
+  return 2 * (long long)F * S + 2 * nb + pil_cap;  // seg_tot | seg_base | blk_tot | blk_base | pil_loc   (int32 elements)
+}
+
 extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (!a || a->F <= 0 || a->Nmax < 0 || a->pt_stride < 3) { set_error("dfb_pillar_index: bad sizes"); return DFB_ERR_ARG; }
@@ -220,28 +287,48 @@ extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
     set_error("dfb_pillar_index: batch too large for int32 indexing"); return DFB_ERR_UNSUPPORTED;
   }
   const long long pil_cap = a->pil_cap;
-  cudaMemsetAsync(a->bitmap, 0, sizeof(unsigned) * (size_t)F * Wd, st);
-  cudaMemsetAsync(a->pil_cnt, 0, sizeof(int) * (size_t)pil_cap, st);
-  cudaMemsetAsync(a->blk_cnt, 0, sizeof(int) * (size_t)F * nblk, st);
+  const int S = (Wd + SEG_WORDS - 1) / SEG_WORDS;
+  const int nb = (int)((pil_cap + PSCAN_ITEMS - 1) / PSCAN_ITEMS);
+  if (!a->scan_ws || !a->tickets || !a->csr_rec) { set_error("dfb_pillar_index: scan workspace / tickets / csr_rec missing"); return DFB_ERR_ARG; }
+  int* seg_tot = a->scan_ws;
+  int* seg_base = seg_tot + (size_t)F * S;
+  int* blk_tot = seg_base + (size_t)F * S;
+  int* blk_base = blk_tot + nb;
+  int* pil_loc = blk_base + nb;
+  if (a->zero_base) {
+    // bitmap | pil_cnt | blk_cnt | tickets live in one allocation: one memset
+    cudaMemsetAsync(a->zero_base, 0, (size_t)a->zero_bytes, st);
+  } else {
+    cudaMemsetAsync(a->bitmap, 0, sizeof(unsigned) * (size_t)F * Wd, st);
+    cudaMemsetAsync(a->pil_cnt, 0, sizeof(int) * (size_t)pil_cap, st);
+    cudaMemsetAsync(a->blk_cnt, 0, sizeof(int) * (size_t)F * nblk, st);
+    cudaMemsetAsync(a->tickets, 0, sizeof(unsigned) * 2, st);
+  }
   if (a->Nmax > 0) {
     dim3 g((unsigned)nblk_, F);
     k_mark_points<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, a->keys, a->bitmap, a->blk_cnt);
   }
-  k_scan_frame<<<F, 1024, 0, st>>>(a->bitmap, Wd, a->blk_cnt, nblk, a->word_rank, a->counts, F);
-  k_frame_offsets<<<1, 32, 0, st>>>(a->counts, F);
+  {
+    dim3 g(S, F);
+    k_bitmap_scan<<<g, 1024, 0, st>>>(a->bitmap, Wd, S, a->word_rank, seg_tot, seg_base, a->blk_cnt, nblk, a->counts, F,
+                                      a->tickets);
+  }
   if (a->Nmax > 0) {
     dim3 g((unsigned)nblk_, F);
     k_compact<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->keys, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
-                                       a->word_rank, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
+                                       a->word_rank, seg_base, S, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
                                        a->pt_offs, a->pt_pillar, a->pt_slot, a->pil_cnt, a->pil_coor, a->pil_pix);
   }
-  k_pillar_scan<<<F, 1024, 0, st>>>(a->pil_cnt, a->counts, F, a->pil_start);
-  if (cap > 0) {
-    int blocks = (int)((cap + 255) / 256);
+  k_pillar_scan<<<nb, 1024, 0, st>>>(a->pil_cnt, a->counts, F, pil_loc, blk_tot, blk_base, a->tickets + 1);
+  {
+    long long work = cap > pil_cap ? cap : pil_cap;
+    int blocks = (int)((work + 255) / 256);
     int maxb = sm_count() * 8;
     if (blocks > maxb) blocks = maxb;
-    k_fill_csr<<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pil_start, a->sorted_pt);
+    if (blocks < 1) blocks = 1;
+    k_fill_csr<<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pt_xyz, pil_loc, blk_base,
+                                       a->pil_start, a->sorted_pt, (float4*)a->csr_rec);
   }
-  add_launches(a->Nmax > 0 ? 6 : 3);
+  add_launches(a->Nmax > 0 ? 5 : 3);
   return check_launch("dfb_pillar_index");
 }

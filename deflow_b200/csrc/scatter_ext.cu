@@ -14,9 +14,71 @@
 namespace dfb {
 
 VoxelParams make_voxel_params(const float* vs, const float* rng);  // pillar_index.cu
-__global__ void k_scan_frame(const unsigned* bitmap, int Wd, int* blk_cnt, int nblk, int* word_rank, int* counts, int F);
-__global__ void k_frame_offsets(int* counts, int F);
-__global__ void k_pillar_scan(const int* pil_cnt, const int* counts, int F, int* pil_start);
+
+// ---------------------------------------------------------------- single-launch scans of the generic (per-call) path
+// One 1024-thread block per frame: (a) exclusive scan of the per-block valid counts,
+// (b) exclusive scan of the bitmap popcounts.
+__global__ void __launch_bounds__(1024) k_scan_frame_1(const unsigned* __restrict__ bitmap, int Wd,
+                                                     int* __restrict__ blk_cnt, int nblk,
+                                                     int* __restrict__ word_rank, int* __restrict__ counts, int F) {
+  __shared__ int sm[33];
+  const int f = blockIdx.x;
+  int carry = 0;
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblk ? blk_cnt[f * nblk + i] : 0;
+    int tot;
+    const int ex = block_excl_scan<1024>(v, sm, tot);
+    if (i < nblk) blk_cnt[f * nblk + i] = carry + ex;  // in place: becomes the block offset
+    carry += tot;
+  }
+  if (threadIdx.x == 0) counts[f] = carry;  // n_valid[f]
+  carry = 0;
+  for (int base = 0; base < Wd; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < Wd ? __popc(bitmap[(size_t)f * Wd + i]) : 0;
+    int tot;
+    const int ex = block_excl_scan<1024>(v, sm, tot);
+    if (i < Wd) word_rank[(size_t)f * Wd + i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) counts[F + f] = carry;  // n_pil[f]
+}
+
+// frame offsets.  counts = n_valid[F] | n_pil[F] | pt_off[F+1] | pil_off[F+1]
+__global__ void k_frame_offsets_1(int* __restrict__ counts, int F) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int a = 0, b = 0;
+    for (int f = 0; f < F; ++f) {
+      counts[2 * F + f] = a;
+      counts[3 * F + 1 + f] = b;
+      a += counts[f];
+      b += counts[F + f];
+    }
+    counts[2 * F + F] = a;
+    counts[3 * F + 1 + F] = b;
+  }
+}
+
+// ---------------------------------------------------------------- CSR offsets of the voxels
+// One block per frame; pil_start[q] = pt_off[f] + exclusive scan of the counts of that frame.
+__global__ void __launch_bounds__(1024) k_pillar_scan_1(const int* __restrict__ pil_cnt, const int* __restrict__ counts,
+                                                      int F, int* __restrict__ pil_start) {
+  __shared__ int sm[33];
+  const int f = blockIdx.x;
+  const int q0 = counts[3 * F + 1 + f], q1 = counts[3 * F + 1 + f + 1];
+  int carry = counts[2 * F + f];
+  for (int base = q0; base < q1; base += 1024) {
+    const int q = base + threadIdx.x;
+    const int v = q < q1 ? pil_cnt[q] : 0;
+    int tot;
+    const int ex = block_excl_scan<1024>(v, sm, tot);
+    if (q < q1) pil_start[q] = carry + ex;
+    carry += tot;
+  }
+  if (f == F - 1 && threadIdx.x == 0) pil_start[q1] = counts[2 * F + F];
+}
+
 
 // ---------------------------------------------------------------- dynamic_voxelize_forward
 __global__ void __launch_bounds__(256) k_dynamic_voxelize(const float* __restrict__ points, int n, int nf,
@@ -244,11 +306,11 @@ extern "C" int dfb_scatter_index(const int* coors, int n, const int* extent_zyx,
   cudaMemsetAsync(voxel_points_count, 0, sizeof(int) * (size_t)n, st);
   k_mark_coors<<<nblk, SX_BLOCK, 0, st>>>(coors, n, extent_zyx[0], extent_zyx[1], extent_zyx[2], point2voxel_map,
                                           bitmap, blk);
-  k_scan_frame<<<1, 1024, 0, st>>>(bitmap, Wd, blk, nblk, word_rank, counts6, 1);
-  k_frame_offsets<<<1, 32, 0, st>>>(counts6, 1);
+  k_scan_frame_1<<<1, 1024, 0, st>>>(bitmap, Wd, blk, nblk, word_rank, counts6, 1);
+  k_frame_offsets_1<<<1, 32, 0, st>>>(counts6, 1);
   k_rank_coors<<<grid_for(n, 256), 256, 0, st>>>(n, extent_zyx[1], extent_zyx[2], bitmap, word_rank, point2voxel_map,
                                                  slot, voxel_points_count, voxel_coors);
-  k_pillar_scan<<<1, 1024, 0, st>>>(voxel_points_count, counts6, 1, pil_start);
+  k_pillar_scan_1<<<1, 1024, 0, st>>>(voxel_points_count, counts6, 1, pil_start);
   k_fill_csr_generic<<<grid_for(n, 256), 256, 0, st>>>(n, point2voxel_map, slot, pil_start, sorted_pt);
   add_launches(6);
   return check_launch("dfb_scatter_index");

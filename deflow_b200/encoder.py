@@ -78,14 +78,16 @@ class DynamicPillarFeatureNet(nn.Module):
                 and not self._with_distance and self.num_pfn == 1 and self.mode != "max"
                 and self.pfn_layers[0][0].out_features == 32)
 
-    def forward_fused(self, idx: ops.PillarIndex, image_dtype=torch.float32):
+    def forward_fused(self, idx: ops.PillarIndex, image_dtype=torch.float32, want_feats=True, image=None,
+                      image_ready=None):
         """All frames of ``idx`` at once -> (NHWC pseudo-image [F,H,W,32], pillar feats, pillar means)."""
         if not self.fused_ok:
             raise RuntimeError("the fused pillar feature net covers in_channels=3, one 32-wide PFN layer, mean mode")
         lin, bn = self.pfn_layers[0][0], self.pfn_layers[0][1]
         training = self.training or not bn.track_running_stats
         out = ops.pillar_feature_net(lin.weight, bn.weight, bn.bias, idx, bn.running_mean, bn.running_var, training,
-                                     bn.eps, bn.momentum, (self.x_offset, self.y_offset, self.z_offset), image_dtype)
+                                     bn.eps, bn.momentum, (self.x_offset, self.y_offset, self.z_offset), image_dtype,
+                                     want_feats, image, image_ready)
         if training and bn.track_running_stats:
             bn.num_batches_tracked += idx.F  # one BatchNorm1d call per sample-frame in the reference
         return out
@@ -148,6 +150,16 @@ class PointPillarsScatter(nn.Module):
         return torch.cat(out, dim=0)
 
 
+_SIDE = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 class DynamicEmbedder(nn.Module):
     """OSF/src/models/basic/encoder.py:602-631."""
 
@@ -162,11 +174,23 @@ class DynamicEmbedder(nn.Module):
 
     def embed(self, points: torch.Tensor, image_dtype=torch.float32):
         """points f32[F,Nmax,3] NaN-padded -> (NHWC pseudo-images [F,H,W,32], PillarIndex)."""
+        # The dense zero canvas (PointPillarsScatter) is pure HBM write bandwidth, the index kernels are latency / atomics
+        # bound: fill the canvas on a side stream while the index runs; the first kernel that writes image rows waits
+        # for the fill (event).
+        H, W = int(self.pseudo_image_dims[0]), int(self.pseudo_image_dims[1])
+        main = torch.cuda.current_stream(points.device)
+        image = torch.empty((points.shape[0], H, W, 32), dtype=image_dtype, device=points.device)
+        side = _side_stream(points.device)
+        side.wait_stream(main)              # the allocator may hand out memory whose last use is still queued on `main`
+        with torch.cuda.stream(side):
+            image.zero_()
+            ready = torch.cuda.Event()
+            ready.record(side)
         idx = self.voxelizer.index(points)
         gx, gy, _ = idx.grid
-        if [gy, gx] != [int(self.pseudo_image_dims[0]), int(self.pseudo_image_dims[1])]:
+        if [gy, gx] != [H, W]:
             raise RuntimeError(f"pseudo_image_dims {self.pseudo_image_dims} do not match the voxel grid {(gy, gx)}")
-        image, _, _ = self.feature_net.forward_fused(idx, image_dtype)
+        image, _, _ = self.feature_net.forward_fused(idx, image_dtype, want_feats=False, image=image, image_ready=ready)
         return image, idx
 
     def forward(self, points: torch.Tensor) -> Tuple[torch.Tensor, List[dict]]:

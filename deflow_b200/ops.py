@@ -104,15 +104,18 @@ def pillar_index(points: torch.Tensor, voxel_size, pc_range) -> PillarIndex:
     idx.pt_idx = torch.empty(cap, dtype=torch.int64, device=dev)
     idx.pt_offs = torch.empty((cap, 3), dtype=torch.float32, device=dev)
     idx.pt_pillar = torch.empty(cap, **i32)
-    idx.pil_cnt = torch.empty(pil_cap, **i32)
     idx.pil_coor = torch.empty((pil_cap, 3), **i32)
     idx.pil_pix = torch.empty(pil_cap, **i32)
     idx.pil_start = torch.empty(pil_cap + 1, **i32)
     idx.sorted_pt = torch.empty(cap, **i32)
+    idx.csr_rec = torch.empty((cap, 4), dtype=torch.float32, device=dev)
     keys = torch.empty(cap, **i32)
-    bitmap = torch.empty(max(F * words.value, 1), **i32)
-    word_rank = torch.empty(max(F * words.value, 1), **i32)
-    blk = torch.empty(max(F * max(blocks.value, 1), 1), **i32)
+    nw, nb = max(F * words.value, 1), max(F * max(blocks.value, 1), 1)
+    # everything that must start at zero lives in ONE allocation (one memset): bitmap | pil_cnt | blk_cnt | tickets
+    zero = torch.empty(nw + pil_cap + nb + 4, **i32)
+    bitmap, idx.pil_cnt, blk, tickets = zero[:nw], zero[nw:nw + pil_cap], zero[nw + pil_cap:nw + pil_cap + nb], zero[-4:]
+    word_rank = torch.empty(nw, **i32)
+    scan_ws = torch.empty(max(int(lib.dfb_index_scan_workspace(F, words.value, pil_cap)), 1), **i32)
     slot = torch.empty(cap, **i32)
     a = IndexArgs()
     a.F, a.Nmax, a.pt_stride, a.pil_cap = F, Nmax, S, pil_cap
@@ -123,7 +126,9 @@ def pillar_index(points: torch.Tensor, voxel_size, pc_range) -> PillarIndex:
                                                 idx.pt_offs.data_ptr())
     a.pt_pillar, a.pil_cnt, a.pil_coor, a.pil_pix = (idx.pt_pillar.data_ptr(), idx.pil_cnt.data_ptr(),
                                                      idx.pil_coor.data_ptr(), idx.pil_pix.data_ptr())
-    a.pil_start, a.sorted_pt = idx.pil_start.data_ptr(), idx.sorted_pt.data_ptr()
+    a.pil_start, a.sorted_pt, a.csr_rec = idx.pil_start.data_ptr(), idx.sorted_pt.data_ptr(), idx.csr_rec.data_ptr()
+    a.scan_ws, a.tickets = scan_ws.data_ptr(), tickets.data_ptr()
+    a.zero_base, a.zero_bytes = zero.data_ptr(), zero.numel() * 4
     check(lib.dfb_pillar_index(C.byref(a), _stream(points)), "pillar_index")
     idx._keep = (points,)
     return idx
@@ -152,7 +157,7 @@ def ego_warp(pc0: torch.Tensor, pose0: Optional[torch.Tensor], pose1: Optional[t
 # Fused pillar feature net
 # ----------------------------------------------------------------------------------------------
 def _pfn_args(idx: PillarIndex, H, W, training, center_off, eps, momentum, weight, gamma, beta, rm, rv, pil_mean,
-              stats, bn_params, pil_feats, image) -> PfnArgs:
+              stats, bn_params, pil_feats, image, pt_mask, partials=None, image_ready=None) -> PfnArgs:
     a = PfnArgs()
     a.F, a.H, a.W, a.training = idx.F, H, W, int(training)
     a.voxel_size = _f3(idx.voxel_size)
@@ -165,9 +170,11 @@ def _pfn_args(idx: PillarIndex, H, W, training, center_off, eps, momentum, weigh
     a.weight, a.gamma, a.beta = weight.data_ptr(), gamma.data_ptr(), beta.data_ptr()
     a.running_mean, a.running_var = _ptr(rm), _ptr(rv)
     a.pil_mean, a.stats, a.bn_params = pil_mean.data_ptr(), stats.data_ptr(), bn_params.data_ptr()
-    a.pil_feats, a.image = pil_feats.data_ptr(), image.data_ptr()
+    a.pil_feats, a.image = _ptr(pil_feats), image.data_ptr()
     a.image_bf16 = int(image.dtype == torch.bfloat16)
     a.pil_cap = idx.pil_cap
+    a.csr_rec, a.pt_mask, a.partials = idx.csr_rec.data_ptr(), pt_mask.data_ptr(), _ptr(partials)
+    a.image_ready_event = None if image_ready is None else image_ready.cuda_event
     return a
 
 
@@ -177,7 +184,7 @@ class _PillarFeatureNet(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, weight, gamma, beta, idx: PillarIndex, running_mean, running_var, training, eps, momentum,
-                center_off, image_dtype):
+                center_off, image_dtype, want_feats, image, image_ready):
         _need_cuda(weight, "pillar_feature_net")
         gx, gy, gz = idx.grid
         H, W = gy, gx
@@ -186,19 +193,26 @@ class _PillarFeatureNet(torch.autograd.Function):
         pil_mean = torch.empty((idx.pil_cap, 3), dtype=torch.float32, device=dev)
         stats = torch.empty((idx.F, 2, 32), dtype=torch.float64, device=dev)
         bn_params = torch.empty((idx.F, 4, 32), dtype=torch.float32, device=dev)
-        pil_feats = torch.empty((idx.pil_cap, 32), dtype=torch.float32, device=dev)
-        image = torch.empty((idx.F, H, W, 32), dtype=image_dtype, device=dev)
+        pil_feats = torch.empty((idx.pil_cap, 32), dtype=torch.float32, device=dev) if want_feats else None
+        pt_mask = torch.empty(idx.cap, dtype=torch.int32, device=dev)
+        partials = torch.empty((idx.cap // 32 + 1, 2, 32), dtype=torch.float32, device=dev)
+        if image is None:
+            image = torch.empty((idx.F, H, W, 32), dtype=image_dtype, device=dev)
+        else:
+            assert tuple(image.shape) == (idx.F, H, W, 32) and image.dtype == image_dtype and image.is_contiguous()
         a = _pfn_args(idx, H, W, training, center_off, eps, momentum, w, g, b, running_mean, running_var, pil_mean,
-                      stats, bn_params, pil_feats, image)
+                      stats, bn_params, pil_feats, image, pt_mask, partials, image_ready)
         check(_lib.lib().dfb_pfn_forward(C.byref(a), _stream(weight)), "pfn_forward")
         ctx.idx, ctx.cfg = idx, (H, W, training, eps, momentum, center_off)
-        ctx.save_for_backward(w, g, b, pil_mean, stats, bn_params, pil_feats)
+        ctx.save_for_backward(w, g, b, pil_mean, stats, bn_params, pt_mask)
+        if pil_feats is None:
+            pil_feats = pil_mean.new_empty(0)
         ctx.mark_non_differentiable(pil_feats, pil_mean)
         return image, pil_feats, pil_mean
 
     @staticmethod
     def backward(ctx, grad_image, _g1, _g2):
-        w, g, b, pil_mean, stats, bn_params, pil_feats = ctx.saved_tensors
+        w, g, b, pil_mean, stats, bn_params, pt_mask = ctx.saved_tensors
         idx = ctx.idx
         H, W, training, eps, momentum, center_off = ctx.cfg
         grad_image = grad_image.contiguous()
@@ -206,23 +220,25 @@ class _PillarFeatureNet(torch.autograd.Function):
         ba = PfnBwdArgs()
         # `image` is not touched by the backward kernels; pass the gradient buffer to carry the dtype flag
         ba.fwd = _pfn_args(idx, H, W, training, center_off, eps, momentum, w, g, b, None, None, pil_mean, stats,
-                           bn_params, pil_feats, grad_image)
+                           bn_params, None, grad_image, pt_mask)
         gw = torch.zeros_like(w)
         gg = torch.zeros_like(g)
         gb = torch.zeros_like(b)
         bwd_stats = torch.empty((idx.F, 32, 10), dtype=torch.float64, device=dev)
-        accum = torch.empty(32 * 9 + 64, dtype=torch.float64, device=dev)
         ba.grad_image, ba.grad_weight, ba.grad_gamma, ba.grad_beta = (grad_image.data_ptr(), gw.data_ptr(),
                                                                      gg.data_ptr(), gb.data_ptr())
-        ba.bwd_stats, ba.grad_accum = bwd_stats.data_ptr(), accum.data_ptr()
+        ba.bwd_stats, ba.grad_accum = bwd_stats.data_ptr(), None
         check(_lib.lib().dfb_pfn_backward(C.byref(ba), _stream(w)), "pfn_backward")
-        return gw, gg, gb, None, None, None, None, None, None, None, None
+        return (gw, gg, gb) + (None,) * 11
 
 
 def pillar_feature_net(weight, gamma, beta, idx, running_mean, running_var, training, eps, momentum, center_off,
-                       image_dtype=torch.float32):
+                       image_dtype=torch.float32, want_feats=True, image=None, image_ready=None):
+    """image / image_ready: an image buffer the caller is zero-filling on another stream, and the torch.cuda.Event that
+    marks the end of that fill (DynamicEmbedder.embed overlaps it with the index kernels); default: allocated and
+    zero-filled here."""
     return _PillarFeatureNet.apply(weight, gamma, beta, idx, running_mean, running_var, training, eps, momentum,
-                                   center_off, image_dtype)
+                                   center_off, image_dtype, want_feats, image, image_ready)
 
 
 # ----------------------------------------------------------------------------------------------

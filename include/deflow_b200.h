@@ -77,6 +77,7 @@ int dfb_dynamic_point_to_voxel_backward(float* grad_feats, const float* grad_red
  *   pt_pillar i32[cap]   global pillar id (reference point2voxel_map = pt_pillar - pil_off[f])
  *   pil_cnt i32[pil_cap] pil_coor i32[pil_cap,3] pil_pix i32[pil_cap] (= f*H*W + y*W + x)
  *   pil_start i32[pil_cap+1], sorted_pt i32[cap]: CSR list of the points of every pillar
+ *   csr_rec  f32[cap,4]: (x, y, z, pillar id) in CSR order -- what the feature-net passes stream through
  * with cap = F*Nmax.  Workspace sizes come from dfb_index_workspace().
  */
 typedef struct {
@@ -101,10 +102,16 @@ typedef struct {
   int* pil_pix;
   int* pil_start;
   int* sorted_pt;
+  float* csr_rec;    /* out [F*Nmax,4]: (x, y, z, bits of the global pillar id) of every valid point in CSR order */
+  int* scan_ws;      /* workspace, dfb_index_scan_workspace() int32 elements */
+  unsigned* tickets; /* workspace [2], zeroed inside */
+  void* zero_base;   /* optional: when bitmap | pil_cnt | blk_cnt | tickets are carved from ONE allocation, its base ... */
+  long long zero_bytes; /* ... and size, so that a single memset clears them (NULL: four memsets) */
 } dfb_index_args;
 
 int dfb_index_workspace(int F, int Nmax, const float* voxel_size, const float* range,
                         long long* bitmap_words_per_frame, long long* blocks_per_frame);
+long long dfb_index_scan_workspace(int F, long long bitmap_words_per_frame, long long pil_cap);
 int dfb_pillar_index(const dfb_index_args* args, void* stream);
 
 /* ------------------------------------------------------------------ ego-motion compensation
@@ -144,10 +151,15 @@ typedef struct {
   float* pil_mean;        /* out [pil_cap,3]: cluster_scatter result */
   double* stats;          /* workspace/out [F,64]: per-frame moments of the decorated features: S1[9] | S2[45] (upper triangle) */
   float* bn_params;       /* out [F,4,32]: a = gamma*rstd, b = beta - mean*a, mean, rstd (saved for backward) */
-  float* pil_feats;       /* out [pil_cap,32] fp32: pfn_scatter result (voxel_feats) */
+  float* pil_feats;       /* out [pil_cap,32] fp32: pfn_scatter result (voxel_feats); NULL = not wanted */
   void* image;            /* out [F,H,W,32] NHWC, zero-filled here; bf16 if image_bf16 else f32 */
   int image_bf16;
   long long pil_cap;      /* rows of pil_feats / pil_mean */
+  const float* csr_rec;   /* [cap,4] from dfb_pillar_index: (x, y, z, pillar id) in CSR order */
+  unsigned* pt_mask;      /* out [cap]: the 32 ReLU decisions of every point (CSR order), read by the backward */
+  float* partials;        /* workspace [(cap/32 + 1), 2, 32] fp32: partial sums of pillars that straddle 32-point groups */
+  void* image_ready_event;/* optional cudaEvent_t: the caller zero-fills `image` on another stream; the first kernel that
+                             writes the image waits for this event and the call does not memset the image itself */
 } dfb_pfn_args;
 int dfb_pfn_forward(const dfb_pfn_args* args, void* stream);
 
