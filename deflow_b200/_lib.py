@@ -46,7 +46,7 @@ class PfnArgs(C.Structure):
                 ("running_var", C.c_void_p), ("pil_mean", C.c_void_p), ("stats", C.c_void_p),
                 ("bn_params", C.c_void_p), ("pil_feats", C.c_void_p), ("image", C.c_void_p),
                 ("image_bf16", C.c_int), ("pil_cap", C.c_longlong), ("csr_rec", C.c_void_p), ("pt_mask", C.c_void_p),
-                ("partials", C.c_void_p), ("image_ready_event", C.c_void_p)]
+                ("partials", C.c_void_p), ("pil_hdr", C.c_void_p), ("image_ready_event", C.c_void_p)]
 
 
 class PfnBwdArgs(C.Structure):
@@ -118,6 +118,7 @@ def _declare(lib):
         "dfb_ego_warp": [vp, vp, vp, vp, i32, i32, vp, i64, vp, vp, vp],
         "dfb_pfn_forward": [C.POINTER(PfnArgs), vp],
         "dfb_pfn_backward": [C.POINTER(PfnBwdArgs), vp],
+        "dfb_zero_fill": [vp, i64, i32, vp],
         "dfb_decoder_gather": [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, i32, vp],
         "dfb_decoder_gather_backward": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
         "dfb_flow_loss": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
@@ -154,7 +155,7 @@ def _declare(lib):
 
 EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size", "dfb_dynamic_voxelize_forward",
            "dfb_scatter_index", "dfb_scatter_reduce", "dfb_dynamic_point_to_voxel_backward", "dfb_index_workspace",
-           "dfb_index_scan_workspace", "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_decoder_gather",
+           "dfb_index_scan_workspace", "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_zero_fill", "dfb_decoder_gather",
            "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_split_bf16x2", "dfb_conv2d", "dfb_conv2d_wgrad",
            "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",

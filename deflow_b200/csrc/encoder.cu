@@ -41,9 +41,15 @@ __device__ __forceinline__ void decorate(float x, float y, float z, float mx, fl
 __device__ __forceinline__ int rec_q(const float4& r) { return __float_as_int(r.w); }
 
 // ---------------------------------------------------------------- pillar mean (cluster_scatter)
-__global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ counts, int F,
+// Also writes the 48-byte pillar header every later pass reads instead of six scattered arrays:
+//   h[0] = (first CSR position, point count, pixel index, frame)   (ints)
+//   h[1] = (mean x, mean y, mean z, centre x)                       h[2] = (centre y, centre z, -, -)
+// with centre = c * voxel + (voxel / 2 + range_min), rounded exactly like encoder.py:452-457.
+__global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ counts, int F, int HW, PfnGeom G,
                                                      const float4* __restrict__ rec,
-                                                     const int* __restrict__ pil_start, float* __restrict__ pil_mean) {
+                                                     const int* __restrict__ pil_start, const int* __restrict__ pil_pix,
+                                                     const int* __restrict__ pil_coor, float* __restrict__ pil_mean,
+                                                     float4* __restrict__ pil_hdr) {
   const int M = counts[3 * F + 1 + F];
   const int sub = threadIdx.x & 7;
   const int groups = (gridDim.x * blockDim.x) >> 3;
@@ -63,11 +69,27 @@ __global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ cou
     }
     if (sub == 0 && q < M) {
       const float n = (float)(s1 - s0);  // reduced_feats /= count.to(float) (scatter_points_cuda.cu:59-60)
-      pil_mean[3 * (size_t)q] = __fdiv_rn(sx, n);
-      pil_mean[3 * (size_t)q + 1] = __fdiv_rn(sy, n);
-      pil_mean[3 * (size_t)q + 2] = __fdiv_rn(sz, n);
+      const float mx = __fdiv_rn(sx, n), my = __fdiv_rn(sy, n), mz = __fdiv_rn(sz, n);
+      pil_mean[3 * (size_t)q] = mx;
+      pil_mean[3 * (size_t)q + 1] = my;
+      pil_mean[3 * (size_t)q + 2] = mz;
+      const int pix = pil_pix[q];
+      const int cz = pil_coor[3 * (size_t)q], cy = pil_coor[3 * (size_t)q + 1], cx = pil_coor[3 * (size_t)q + 2];
+      const float ox = __fadd_rn(__fmul_rn((float)cx, G.vx), G.ox), oy = __fadd_rn(__fmul_rn((float)cy, G.vy), G.oy),
+                  oz = __fadd_rn(__fmul_rn((float)cz, G.vz), G.oz);
+      float4* h = pil_hdr + 3 * (size_t)q;
+      h[0] = make_float4(__int_as_float(s0), __int_as_float(s1 - s0), __int_as_float(pix), __int_as_float(pix / HW));
+      h[1] = make_float4(mx, my, mz, ox);
+      h[2] = make_float4(oy, oz, 0.f, 0.f);
     }
   }
+}
+
+// decorations of encoder.py:446-465 from the pillar header; every sum individually rounded like the torch ops
+__device__ __forceinline__ void decorate_hdr(const float4& r, const float4& h1, const float4& h2, float* f) {
+  f[0] = r.x; f[1] = r.y; f[2] = r.z;
+  f[3] = __fsub_rn(r.x, h1.x); f[4] = __fsub_rn(r.y, h1.y); f[5] = __fsub_rn(r.z, h1.z);
+  f[6] = __fsub_rn(r.x, h1.w); f[7] = __fsub_rn(r.y, h2.x); f[8] = __fsub_rn(r.z, h2.y);
 }
 
 // ---------------------------------------------------------------- BatchNorm batch statistics from moments
@@ -77,9 +99,8 @@ __global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ cou
 constexpr int PFN_MOM = 54;
 constexpr int PFN_MOM_PITCH = 64;
 
-__global__ void __launch_bounds__(256) k_pfn_moments(const int* __restrict__ counts, int F, PfnGeom G,
-                                                     const float4* __restrict__ rec,
-                                                     const int* __restrict__ pil_coor, const float* __restrict__ pil_mean,
+__global__ void __launch_bounds__(256) k_pfn_moments(const int* __restrict__ counts, int F,
+                                                     const float4* __restrict__ rec, const float4* __restrict__ pil_hdr,
                                                      double* __restrict__ mom) {
   __shared__ float red[8][PFN_MOM];
   const int f = blockIdx.y;
@@ -91,8 +112,7 @@ __global__ void __launch_bounds__(256) k_pfn_moments(const int* __restrict__ cou
     const float4 r = __ldg(rec + j);
     const int q = rec_q(r);
     float fe[PFN_K];
-    decorate(r.x, r.y, r.z, pil_mean[3 * (size_t)q], pil_mean[3 * (size_t)q + 1], pil_mean[3 * (size_t)q + 2],
-             pil_coor[3 * (size_t)q], pil_coor[3 * (size_t)q + 1], pil_coor[3 * (size_t)q + 2], G, fe);
+    decorate_hdr(r, __ldg(pil_hdr + 3 * (size_t)q + 1), __ldg(pil_hdr + 3 * (size_t)q + 2), fe);
     int o = PFN_K;
 #pragma unroll
     for (int jj = 0; jj < PFN_K; ++jj) {
@@ -181,14 +201,17 @@ __global__ void __launch_bounds__(1024) k_bn_finalize(const int* __restrict__ co
 }
 
 // ---------------------------------------------------------------- point pass (forward)
-// Phase 1, thread per point in CSR order: all 32 channels of Linear + BN + ReLU with packed fp32x2 FMAs (weights
-// broadcast from shared memory) into a [256 points x 32 channels] shared tile; the 32 ReLU decisions of the point are
-// saved as one mask word for the backward.
-// Phase 2, warp per group of 32 consecutive points, lane = channel: sequential segment sums.  A pillar that lies
-// inside one group (the common case: ~4 points per pillar) is finished on the spot -- mean, voxel feature row, NHWC
-// image row -- with no atomics and no later pass.  Pillars that straddle group boundaries leave per-group partial
-// sums (part[G][0] = the leading segment that began in an earlier group, part[G][1] = the trailing segment that
-// continues into the next one); k_pfn_straddlers adds them up in order.  Deterministic.
+// A warp owns a group of 32 consecutive CSR positions, lane = point, no shared-memory staging and no block barriers:
+//   1. all 32 channels of Linear + BN + ReLU with packed fp32x2 FMAs (weights broadcast from shared memory); the 32 ReLU
+//      decisions of the point are saved as one mask word for the backward;
+//   2. a segmented warp scan (segments = pillars; their boundaries come from two ballots) leaves, in the lane of a
+//      pillar's LAST point, the 32 channel sums of that pillar in registers;
+//   3. that lane finishes the pillar on the spot -- mean, voxel feature row, NHWC image row (one 64 / 128-byte row
+//      store) -- with no atomics and no later pass.
+// Pillars that straddle group boundaries leave per-group partial rows (part[G][0] = the leading segment that began in
+// an earlier group, part[G][1] = the trailing segment that continues into the next one); k_pfn_straddlers adds them up
+// in order.  Deterministic.  (The mean is sum * (1 / count) with a correctly rounded reciprocal: <= 1 ulp from the
+// reference's division.)
 template <bool BF16>
 __device__ __forceinline__ void store_pillar(float v, int q, int pix, int c, float* __restrict__ pil_feats,
                                              void* __restrict__ image) {
@@ -197,19 +220,20 @@ __device__ __forceinline__ void store_pillar(float v, int q, int pix, int c, flo
   else reinterpret_cast<float*>(image)[(size_t)pix * PFN_C + c] = v;
 }
 
+__device__ __forceinline__ void store_row32(float* __restrict__ dst, const float (&v)[PFN_C]) {
+#pragma unroll
+  for (int c4 = 0; c4 < PFN_C; c4 += 4)
+    *reinterpret_cast<float4*>(dst + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);
+}
+
 template <bool BF16>
-__global__ void __launch_bounds__(256) k_pfn_points(const int* __restrict__ counts, int F, int HW, PfnGeom G,
-                                                    const float4* __restrict__ rec, const int* __restrict__ pil_coor,
-                                                    const int* __restrict__ pil_pix, const int* __restrict__ pil_start,
-                                                    const float* __restrict__ pil_mean, const float* __restrict__ weight,
-                                                    const float* __restrict__ bn_params, unsigned* __restrict__ pt_mask,
-                                                    float* __restrict__ part, float* __restrict__ pil_feats,
-                                                    void* __restrict__ image) {
-  __shared__ __align__(16) float Wp[PFN_K][PFN_C];   // Wp[k][c]
-  __shared__ float T[256][PFN_C + 1];
-  __shared__ int Q[256], PX[256], CN[256];
-  __shared__ unsigned char FL[256];                   // bit 0: first point of its pillar, bit 1: last point
-  extern __shared__ float sAB[];                      // [F][2][32] scale / shift per frame
+__global__ void __launch_bounds__(256, 3) k_pfn_points(const int* __restrict__ counts, int F,
+                                                       const float4* __restrict__ rec, const float4* __restrict__ pil_hdr,
+                                                       const float* __restrict__ weight, const float* __restrict__ bn_params,
+                                                       unsigned* __restrict__ pt_mask, float* __restrict__ part,
+                                                       float* __restrict__ pil_feats, void* __restrict__ image) {
+  __shared__ __align__(16) float Wp[PFN_K][PFN_C];          // Wp[k][c]
+  extern __shared__ __align__(16) float sAB[];              // [F][2][32] scale / shift per frame
   const int n = counts[2 * F + F];
   for (int i = threadIdx.x; i < PFN_C * PFN_K; i += blockDim.x) Wp[i % PFN_K][i / PFN_K] = weight[i];
   for (int i = threadIdx.x; i < F * 2 * PFN_C; i += blockDim.x) {
@@ -217,16 +241,29 @@ __global__ void __launch_bounds__(256) k_pfn_points(const int* __restrict__ coun
     sAB[i] = bn_params[(size_t)f * 4 * PFN_C + r];
   }
   __syncthreads();
-  for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
-    const int j = base + threadIdx.x;
-    int q = -1;
-    if (j < n) {
+  const int lane = threadIdx.x & 31;
+  const int n_groups = (n + 31) >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
+    const int j = grp * 32 + lane;
+    const bool live = j < n;
+    int q = 0, pix = 0, cnt = 1;
+    bool first = false, last = false;
+    float v[PFN_C];
+#pragma unroll
+    for (int c = 0; c < PFN_C; ++c) v[c] = 0.f;
+    if (live) {
       const float4 r = __ldg(rec + j);
       q = rec_q(r);
-      const int s0 = pil_start[q], s1 = pil_start[q + 1], pix = pil_pix[q];
+      const float4 h0 = __ldg(pil_hdr + 3 * (size_t)q), h1 = __ldg(pil_hdr + 3 * (size_t)q + 1),
+                   h2 = __ldg(pil_hdr + 3 * (size_t)q + 2);
+      const int s0 = __float_as_int(h0.x);
+      cnt = __float_as_int(h0.y);
+      pix = __float_as_int(h0.z);
+      first = j == s0;
+      last = j + 1 == s0 + cnt;
       float fe[PFN_K];
-      decorate(r.x, r.y, r.z, pil_mean[3 * (size_t)q], pil_mean[3 * (size_t)q + 1], pil_mean[3 * (size_t)q + 2],
-               pil_coor[3 * (size_t)q], pil_coor[3 * (size_t)q + 1], pil_coor[3 * (size_t)q + 2], G, fe);
+      decorate_hdr(r, h1, h2, fe);
       float2 y2[PFN_C / 2];
 #pragma unroll
       for (int c = 0; c < PFN_C / 2; ++c) y2[c] = make_float2(0.f, 0.f);
@@ -240,55 +277,83 @@ __global__ void __launch_bounds__(256) k_pfn_points(const int* __restrict__ coun
           y2[c4 / 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), fk, y2[c4 / 2 + 1]);
         }
       }
-      const float* ab = sAB + (size_t)(pix / HW) * 2 * PFN_C;
+      const float* ab = sAB + (size_t)__float_as_int(h0.w) * 2 * PFN_C;
       unsigned m = 0u;
 #pragma unroll
-      for (int c = 0; c < PFN_C / 2; ++c) {
-        const float2 a = *reinterpret_cast<const float2*>(ab + 2 * c), b = *reinterpret_cast<const float2*>(ab + PFN_C + 2 * c);
-        const float2 v = __ffma2_rn(y2[c], a, b);
-        m |= (v.x > 0.f ? 1u : 0u) << (2 * c);
-        m |= (v.y > 0.f ? 1u : 0u) << (2 * c + 1);
-        T[threadIdx.x][2 * c] = fmaxf(v.x, 0.f);
-        T[threadIdx.x][2 * c + 1] = fmaxf(v.y, 0.f);
+      for (int c4 = 0; c4 < PFN_C; c4 += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(ab + c4), b = *reinterpret_cast<const float4*>(ab + PFN_C + c4);
+        const float2 v0 = __ffma2_rn(y2[c4 / 2], make_float2(a.x, a.y), make_float2(b.x, b.y));
+        const float2 v1 = __ffma2_rn(y2[c4 / 2 + 1], make_float2(a.z, a.w), make_float2(b.z, b.w));
+        v[c4] = fmaxf(v0.x, 0.f); v[c4 + 1] = fmaxf(v0.y, 0.f); v[c4 + 2] = fmaxf(v1.x, 0.f); v[c4 + 3] = fmaxf(v1.y, 0.f);
+        // relu(x) > 0  <=>  x > 0; the bits of a non-negative float are a positive int exactly when it is > 0
+        m |= ((unsigned)(-__float_as_int(v[c4])) >> 31) << c4;
+        m |= ((unsigned)(-__float_as_int(v[c4 + 1])) >> 31) << (c4 + 1);
+        m |= ((unsigned)(-__float_as_int(v[c4 + 2])) >> 31) << (c4 + 2);
+        m |= ((unsigned)(-__float_as_int(v[c4 + 3])) >> 31) << (c4 + 3);
       }
       pt_mask[j] = m;
-      PX[threadIdx.x] = pix;
-      CN[threadIdx.x] = s1 - s0;
-      FL[threadIdx.x] = (unsigned char)((j == s0 ? 1 : 0) | (j + 1 == s1 ? 2 : 0));
     }
-    Q[threadIdx.x] = q;
-    __syncthreads();
-    {
-      const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-      const size_t G0 = ((size_t)(base >> 5) + g) * 2 * PFN_C;  // this group's two partial rows
-      float acc = 0.f;
-      bool started = false;   // the running segment began inside this group
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const int pt = g * 32 + i;
-        const int qq = Q[pt];
-        if (qq < 0) break;                     // past the end of the point list (warp-uniform)
-        const int fl = FL[pt];
-        if (fl & 1) { acc = 0.f; started = true; }
-        acc += T[pt][c];
-        if (fl & 2) {                          // the pillar ends here
-          if (started) store_pillar<BF16>(__fdiv_rn(acc, (float)CN[pt]), qq, PX[pt], c, pil_feats, image);
-          else part[G0 + c] = acc;             // leading segment of a pillar that began in an earlier group
-          acc = 0.f;
-        } else if (i == 31) {                  // the pillar continues into the next group
-          part[G0 + (started ? PFN_C : 0) + c] = acc;
-        }
+    const unsigned firstmask = __ballot_sync(0xffffffffu, first), lastmask = __ballot_sync(0xffffffffu, last);
+    const int nvalid = min(32, n - grp * 32);
+    // segmented inclusive scan over the lanes; a segment starts at lane 0 (possibly the tail of an earlier group's
+    // pillar) and at every first point of a pillar
+    const unsigned starts = firstmask | 1u;
+    const int seg_start = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));
+    const int dist = lane - seg_start;
+    const unsigned far = __ballot_sync(0xffffffffu, dist >= 4);
+#pragma unroll
+    for (int c = 0; c < PFN_C; ++c) {
+      float x = v[c], t;
+      t = __shfl_up_sync(0xffffffffu, x, 1); if (dist >= 1) x += t;
+      t = __shfl_up_sync(0xffffffffu, x, 2); if (dist >= 2) x += t;
+      v[c] = x;
+    }
+    if (far) {   // some segment of this group is longer than 4 points (warp-uniform)
+#pragma unroll
+      for (int c = 0; c < PFN_C; ++c) {
+        float x = v[c], t;
+        t = __shfl_up_sync(0xffffffffu, x, 4); if (dist >= 4) x += t;
+        t = __shfl_up_sync(0xffffffffu, x, 8); if (dist >= 8) x += t;
+        t = __shfl_up_sync(0xffffffffu, x, 16); if (dist >= 16) x += t;
+        v[c] = x;
       }
     }
-    __syncthreads();
+    const bool begins = (firstmask >> seg_start) & 1u;   // the segment this lane closes began inside this group
+    float* prow = part + (size_t)grp * 2 * PFN_C;
+    if (live && last) {
+      if (begins) {
+        const float inv = __frcp_rn((float)cnt);
+#pragma unroll
+        for (int c = 0; c < PFN_C; ++c) v[c] *= inv;
+        if (pil_feats) store_row32(pil_feats + (size_t)q * PFN_C, v);
+        if (BF16) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(image) + (size_t)pix * PFN_C);
+#pragma unroll
+          for (int c8 = 0; c8 < PFN_C; c8 += 8) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[c8], v[c8 + 1]), p1 = __floats2bfloat162_rn(v[c8 + 2], v[c8 + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[c8 + 4], v[c8 + 5]), p3 = __floats2bfloat162_rn(v[c8 + 6], v[c8 + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<unsigned*>(&p0); u.y = *reinterpret_cast<unsigned*>(&p1);
+            u.z = *reinterpret_cast<unsigned*>(&p2); u.w = *reinterpret_cast<unsigned*>(&p3);
+            dst[c8 / 8] = u;
+          }
+        } else {
+          store_row32(reinterpret_cast<float*>(image) + (size_t)pix * PFN_C, v);
+        }
+      } else {
+        store_row32(prow, v);            // leading segment of a pillar that began in an earlier group
+      }
+    } else if (live && lane == nvalid - 1) {
+      store_row32(prow + (begins ? PFN_C : 0), v);   // the pillar continues into the next group
+    }
   }
 }
 
 // warp per group boundary: the group in which a straddling pillar BEGINS adds up that pillar's partial sums
 template <bool BF16>
 __global__ void __launch_bounds__(256) k_pfn_straddlers(const int* __restrict__ counts, int F,
-                                                        const float4* __restrict__ rec, const int* __restrict__ pil_pix,
-                                                        const int* __restrict__ pil_start, const float* __restrict__ part,
+                                                        const float4* __restrict__ rec, const float4* __restrict__ pil_hdr,
+                                                        const float* __restrict__ part,
                                                         float* __restrict__ pil_feats, void* __restrict__ image) {
   const int n = counts[2 * F + F];
   const int c = threadIdx.x & 31;
@@ -298,12 +363,13 @@ __global__ void __launch_bounds__(256) k_pfn_straddlers(const int* __restrict__ 
     const int jl = 32 * g + 31;
     if (jl >= n) break;                        // a partial last group has nothing after it
     const int q = rec_q(__ldg(rec + jl));
-    const int s0 = pil_start[q], s1 = pil_start[q + 1];
+    const float4 h0 = __ldg(pil_hdr + 3 * (size_t)q);
+    const int s0 = __float_as_int(h0.x), cnt = __float_as_int(h0.y), s1 = s0 + cnt;
     if (s1 <= jl + 1 || s0 < 32 * g) continue; // ends here, or began earlier (then an earlier group owns it)
     float tot = part[((size_t)g * 2 + 1) * PFN_C + c];
     const int g_last = (s1 - 1) >> 5;
     for (int g2 = g + 1; g2 <= g_last; ++g2) tot += part[(size_t)g2 * 2 * PFN_C + c];
-    store_pillar<BF16>(__fdiv_rn(tot, (float)(s1 - s0)), q, pil_pix[q], c, pil_feats, image);
+    store_pillar<BF16>(tot * __frcp_rn((float)cnt), q, __float_as_int(h0.z), c, pil_feats, image);
   }
 }
 
@@ -314,49 +380,96 @@ __global__ void __launch_bounds__(256) k_pfn_straddlers(const int* __restrict__ 
 //   sum_p xhat f_k = rstd (sum_j W_cj S2[j,k] - mean S1[k])          (S1, S2 = the forward's feature moments)
 // so  A2 = sum gy^ xhat = rstd (W_c . T_c - mean A1),  grad_gamma = A2,  grad_beta = A1  and
 //   grad_W[c,k] = a_c (T[c][k] - (A1/N) S1[k] - (A2/N) sum_p xhat f_k)      (training; eval: a_c T[c][k]).
-// grid (X, F): warp per pillar, lane = channel; the points come as broadcast 16-byte CSR records plus the ReLU mask
-// word the forward saved (no recomputation of the linear layer).  bwd_acc layout [F][32][10] (double): A1 | T[9].
+// grid (X, F): a warp owns 32 consecutive CSR positions of frame f.  Phase 1, lane = point: coalesced loads of the
+// point records, the ReLU mask words the forward saved and the pillar headers into a shared slab.  Then the image
+// gradient rows of the (at most 32) pillars the group touches are fetched, all loads in flight together -- the kernel
+// is latency-bound, not bandwidth-bound.  Phase 2, lane = channel: per pillar segment the masked sums of (1, x, y, z),
+// expanded once per segment.  Everything is linear in the segment sums, so pillars that straddle groups need no
+// special handling.  bwd_acc layout [F][32][10] (double): A1 | T[9].
+struct BwdSlab {
+  float4 pt[32];        // x, y, z, mask bits
+  float4 h1[32], h2[32];// per segment: mean xyz, centre x | centre y, centre z, count, -
+  float g[32][PFN_C + 1];
+};
+
 template <bool BF16>
-__global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F, PfnGeom G,
+__global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F,
                                                  const float4* __restrict__ rec, const unsigned* __restrict__ pt_mask,
-                                                 const int* __restrict__ pil_coor, const int* __restrict__ pil_pix,
-                                                 const int* __restrict__ pil_start, const float* __restrict__ pil_mean,
+                                                 const float4* __restrict__ pil_hdr,
                                                  const void* __restrict__ grad_image, double* __restrict__ bwd_acc) {
-  __shared__ float red[8][PFN_C][PFN_K + 2];
+  __shared__ BwdSlab slabs[8];
+  static_assert(sizeof(BwdSlab) * 8 >= sizeof(float) * 8 * PFN_C * (PFN_K + 2), "the block reduction reuses the slabs");
+  float (*red)[PFN_C][PFN_K + 2] = reinterpret_cast<float (*)[PFN_C][PFN_K + 2]>(slabs);
   const int f = blockIdx.y;
-  const int q0 = counts[3 * F + 1 + f], q1 = counts[3 * F + 1 + f + 1];
+  const int p0 = counts[2 * F + f], p1 = counts[2 * F + f + 1];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  BwdSlab& S = slabs[wib];
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  float acc[PFN_K], a1 = 0.f;
+  float acc[PFN_K + 1];   // A1 | T[9] of channel `lane`
 #pragma unroll
-  for (int k = 0; k < PFN_K; ++k) acc[k] = 0.f;
-  for (int q = q0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); q < q1; q += warps) {
-    const int s0 = pil_start[q], s1 = pil_start[q + 1];
-    const int pix = pil_pix[q];
-    float g = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad_image)[(size_t)pix * PFN_C + lane])
-                   : reinterpret_cast<const float*>(grad_image)[(size_t)pix * PFN_C + lane];
-    g = __fdiv_rn(g, (float)(s1 - s0));  // mean backward: grad / count (scatter_points_cuda_kernel.cuh:134-137)
-    const float mx = pil_mean[3 * (size_t)q], my = pil_mean[3 * (size_t)q + 1], mz = pil_mean[3 * (size_t)q + 2];
-    const int cz = pil_coor[3 * (size_t)q], cy = pil_coor[3 * (size_t)q + 1], cx = pil_coor[3 * (size_t)q + 2];
-    // within a pillar f[p,k] = xyz[p, k%3] - off[k]: accumulate the masked sums of (1, x, y, z) and expand once
-    float u0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
-#pragma unroll 2
-    for (int j = s0; j < s1; ++j) {
+  for (int k = 0; k < PFN_K + 1; ++k) acc[k] = 0.f;
+  const int n_groups = (p1 - p0 + 31) >> 5;
+  for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
+    const int j = p0 + grp * 32 + lane;
+    const bool live = j < p1;
+    int q = -1, pix = 0;
+    float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f), h2 = h1;
+    if (live) {
       const float4 r = __ldg(rec + j);
-      const unsigned m = __ldg(pt_mask + j);
-      if ((m >> lane) & 1u) { u0 += 1.f; ux += r.x; uy += r.y; uz += r.z; }  // ReLU mask
+      q = rec_q(r);
+      S.pt[lane] = make_float4(r.x, r.y, r.z, __uint_as_float(__ldg(pt_mask + j)));
     }
-    // offsets of the three decoration groups: raw (0), cluster mean, pillar centre
-    const float ox = __fadd_rn(__fmul_rn((float)cx, G.vx), G.ox), oy = __fadd_rn(__fmul_rn((float)cy, G.vy), G.oy),
-                oz = __fadd_rn(__fmul_rn((float)cz, G.vz), G.oz);
-    a1 = fmaf(g, u0, a1);
-    acc[0] = fmaf(g, ux, acc[0]); acc[1] = fmaf(g, uy, acc[1]); acc[2] = fmaf(g, uz, acc[2]);
-    acc[3] = fmaf(g, ux - mx * u0, acc[3]); acc[4] = fmaf(g, uy - my * u0, acc[4]); acc[5] = fmaf(g, uz - mz * u0, acc[5]);
-    acc[6] = fmaf(g, ux - ox * u0, acc[6]); acc[7] = fmaf(g, uy - oy * u0, acc[7]); acc[8] = fmaf(g, uz - oz * u0, acc[8]);
+    const int qprev = __shfl_up_sync(0xffffffffu, q, 1);
+    const bool start = live && (lane == 0 || q != qprev);
+    const unsigned startmask = __ballot_sync(0xffffffffu, start);
+    const int nvalid = min(32, p1 - (p0 + grp * 32));
+    const int slot = __popc(startmask & ((1u << lane) - 1u));
+    if (start) {
+      const float4 h0 = __ldg(pil_hdr + 3 * (size_t)q);
+      h1 = __ldg(pil_hdr + 3 * (size_t)q + 1); h2 = __ldg(pil_hdr + 3 * (size_t)q + 2);
+      pix = __float_as_int(h0.z);
+      h2.z = (float)__float_as_int(h0.y);   // count
+      S.h1[slot] = h1; S.h2[slot] = h2;
+    }
+    const int nseg = __popc(startmask);
+    // image-gradient rows of the group's pillars: lane = channel, one row per segment, all loads issued together
+    {
+      unsigned sm_ = startmask;
+      for (int s = 0; s < nseg; ++s) {
+        const int src = __ffs(sm_) - 1;
+        sm_ &= sm_ - 1;
+        const int px = __shfl_sync(0xffffffffu, pix, src);
+        const size_t o = (size_t)px * PFN_C + lane;
+        S.g[s][lane] = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad_image)[o])
+                            : reinterpret_cast<const float*>(grad_image)[o];
+      }
+    }
+    __syncwarp();
+    // phase 2: lane = channel
+    unsigned rest = startmask;
+    for (int s = 0; s < nseg; ++s) {
+      const int a = __ffs(rest) - 1;
+      rest &= rest - 1;
+      const int e = rest ? __ffs(rest) - 1 : nvalid;   // one past the segment's last point
+      float u0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
+      for (int i = a; i < e; ++i) {
+        const float4 r = S.pt[i];
+        if ((__float_as_uint(r.w) >> lane) & 1u) { u0 += 1.f; ux += r.x; uy += r.y; uz += r.z; }  // ReLU mask
+      }
+      const float4 m = S.h1[s], c2 = S.h2[s];
+      // mean backward: grad / count (scatter_points_cuda_kernel.cuh:134-137)
+      const float g = __fdiv_rn(S.g[s][lane], c2.z);
+      // offsets of the three decoration groups: raw (0), cluster mean (m.xyz), pillar centre (m.w, c2.x, c2.y)
+      acc[0] = fmaf(g, u0, acc[0]);
+      acc[1] = fmaf(g, ux, acc[1]); acc[2] = fmaf(g, uy, acc[2]); acc[3] = fmaf(g, uz, acc[3]);
+      acc[4] = fmaf(g, ux - m.x * u0, acc[4]); acc[5] = fmaf(g, uy - m.y * u0, acc[5]); acc[6] = fmaf(g, uz - m.z * u0, acc[6]);
+      acc[7] = fmaf(g, ux - m.w * u0, acc[7]); acc[8] = fmaf(g, uy - c2.x * u0, acc[8]); acc[9] = fmaf(g, uz - c2.y * u0, acc[9]);
+    }
+    __syncwarp();
   }
-  red[wib][lane][0] = a1;
+  __syncthreads();   // every warp is done with its slab
 #pragma unroll
-  for (int k = 0; k < PFN_K; ++k) red[wib][lane][1 + k] = acc[k];
+  for (int k = 0; k < PFN_K + 1; ++k) red[wib][lane][k] = acc[k];
   __syncthreads();
   for (int i = threadIdx.x; i < PFN_C * (PFN_K + 1); i += blockDim.x) {
     const int c = i / (PFN_K + 1), k = i % (PFN_K + 1);
@@ -372,21 +485,21 @@ __device__ __forceinline__ int tri_index(int j, int k) {  // position of S2[j][k
   return PFN_K + j * PFN_K - (j * (j - 1)) / 2 + (k - j);
 }
 
-__global__ void __launch_bounds__(1024) k_pfn_bwd_finalize(const int* __restrict__ counts, int F, int training,
+__global__ void __launch_bounds__(512) k_pfn_bwd_finalize(const int* __restrict__ counts, int F, int training,
                                                            const double* __restrict__ bwd_acc,
                                                            const double* __restrict__ mom,
                                                            const float* __restrict__ bn_params,
                                                            const float* __restrict__ weight,
                                                            float* __restrict__ grad_weight, float* __restrict__ grad_gamma,
                                                            float* __restrict__ grad_beta) {
-  __shared__ double sred[32][PFN_C + 1];
+  __shared__ double sred[16][PFN_C + 1];
   const int c = threadIdx.x & 31, slot = threadIdx.x >> 5;
   double w[PFN_K], out[PFN_K + 2];  // gw[9] | gg | gb
 #pragma unroll
   for (int k = 0; k < PFN_K; ++k) w[k] = (double)weight[c * PFN_K + k];
 #pragma unroll
   for (int k = 0; k < PFN_K + 2; ++k) out[k] = 0.0;
-  for (int f = slot; f < F; f += 32) {
+  for (int f = slot; f < F; f += 16) {
     const int n = counts[f];
     if (n <= 0) continue;
     const double* A = bwd_acc + ((size_t)f * PFN_C + c) * (PFN_K + 1);
@@ -421,13 +534,26 @@ __global__ void __launch_bounds__(1024) k_pfn_bwd_finalize(const int* __restrict
     __syncthreads();
     if (slot == 0) {
       double s = 0.0;
-      for (int i = 0; i < 32; ++i) s += sred[i][c];
+      for (int i = 0; i < 16; ++i) s += sred[i][c];
       if (k < PFN_K) grad_weight[c * PFN_K + k] += (float)s;
       else if (k == PFN_K) grad_gamma[c] += (float)s;
       else grad_beta[c] += (float)s;
     }
     __syncthreads();
   }
+}
+
+// Dense zero fill with ONE small block per SM (16-byte stores, grid-stride): enough store traffic to saturate HBM while
+// leaving almost all warp slots free, so that it can run under other kernels on a second stream (a library memset /
+// fill launches enough blocks to occupy every SM until it is done).
+__global__ void __launch_bounds__(256) k_zero_fill(uint4* __restrict__ p, size_t n16, unsigned char* __restrict__ tail,
+                                                   int ntail) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) { p[i] = z; p[i + stride] = z; p[i + 2 * stride] = z; p[i + 3 * stride] = z; }
+  for (; i < n16; i += stride) p[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
 }
 
 static PfnGeom make_geom(const dfb_pfn_args* a) {
@@ -441,11 +567,22 @@ static PfnGeom make_geom(const dfb_pfn_args* a) {
 
 using namespace dfb;
 
+extern "C" int dfb_zero_fill(void* ptr, long long bytes, int blocks_per_sm, void* stream_) {
+  if (bytes < 0 || ((uintptr_t)ptr & 15)) { set_error("dfb_zero_fill: pointer must be 16-byte aligned"); return DFB_ERR_ARG; }
+  if (bytes == 0) return DFB_OK;
+  const size_t n16 = (size_t)bytes / 16;
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  k_zero_fill<<<sm_count() * blocks_per_sm, 256, 0, (cudaStream_t)stream_>>>((uint4*)ptr, n16, (unsigned char*)ptr + n16 * 16,
+                                                                            (int)(bytes - (long long)n16 * 16));
+  add_launches(1);
+  return check_launch("dfb_zero_fill");
+}
+
 extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (!a || a->F <= 0 || a->H <= 0 || a->W <= 0) { set_error("dfb_pfn_forward: bad sizes"); return DFB_ERR_ARG; }
   if (a->F > 256) { set_error("dfb_pfn_forward: at most 256 frames per call"); return DFB_ERR_UNSUPPORTED; }
-  if (!a->csr_rec || !a->pt_mask || !a->partials) { set_error("dfb_pfn_forward: csr_rec / pt_mask / partials missing"); return DFB_ERR_ARG; }
+  if (!a->csr_rec || !a->pt_mask || !a->partials || !a->pil_hdr) { set_error("dfb_pfn_forward: csr_rec / pt_mask / partials / pil_hdr missing"); return DFB_ERR_ARG; }
   const int F = a->F, HW = a->H * a->W;
   const PfnGeom G = make_geom(a);
   const int sms = sm_count();
@@ -453,15 +590,19 @@ extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
   const size_t img_bytes = (size_t)F * HW * PFN_C * (a->image_bf16 ? 2 : 4);
   // the dense zero canvas (PointPillarsScatter, encoder.py:135-139).  A caller that zero-fills the image itself on
   // another stream (to overlap the fill with the index kernels) passes the event that marks its completion.
-  if (!a->image_ready_event) cudaMemsetAsync(a->image, 0, img_bytes, st);
+  if (!a->image_ready_event) {
+    const size_t n16 = img_bytes / 16;   // F*H*W*32 elements: always a multiple of 16 bytes
+    k_zero_fill<<<sms * 2, 256, 0, st>>>((uint4*)a->image, n16, (unsigned char*)a->image + n16 * 16, (int)(img_bytes - n16 * 16));
+  }
   cudaMemsetAsync(a->stats, 0, sizeof(double) * (size_t)F * PFN_MOM_PITCH, st);
-  k_pillar_mean<<<sms * 8, 256, 0, st>>>(a->counts, F, rec, a->pil_start, a->pil_mean);
+  float4* hdr = (float4*)a->pil_hdr;
+  k_pillar_mean<<<sms * 8, 256, 0, st>>>(a->counts, F, HW, G, rec, a->pil_start, a->pil_pix, a->pil_coor, a->pil_mean, hdr);
   int launches = 4;
   if (a->training) {
     int bx = (sms * 4 + F - 1) / F;
     if (bx < 1) bx = 1;
     dim3 g(bx, F);
-    k_pfn_moments<<<g, 256, 0, st>>>(a->counts, F, G, rec, a->pil_coor, a->pil_mean, a->stats);
+    k_pfn_moments<<<g, 256, 0, st>>>(a->counts, F, rec, hdr, a->stats);
     ++launches;
   }
   k_bn_finalize<<<1, 1024, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum, a->stats, a->weight, a->gamma, a->beta,
@@ -475,13 +616,13 @@ extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
     configured = true;
   }
   if (a->image_bf16) {
-    k_pfn_points<true><<<sms * 4, 256, dyn, st>>>(a->counts, F, HW, G, rec, a->pil_coor, a->pil_pix, a->pil_start, a->pil_mean,
-                                                  a->weight, a->bn_params, a->pt_mask, a->partials, a->pil_feats, a->image);
-    k_pfn_straddlers<true><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, a->pil_pix, a->pil_start, a->partials, a->pil_feats, a->image);
+    k_pfn_points<true><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->weight, a->bn_params, a->pt_mask, a->partials,
+                                                  a->pil_feats, a->image);
+    k_pfn_straddlers<true><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
   } else {
-    k_pfn_points<false><<<sms * 4, 256, dyn, st>>>(a->counts, F, HW, G, rec, a->pil_coor, a->pil_pix, a->pil_start, a->pil_mean,
-                                                   a->weight, a->bn_params, a->pt_mask, a->partials, a->pil_feats, a->image);
-    k_pfn_straddlers<false><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, a->pil_pix, a->pil_start, a->partials, a->pil_feats, a->image);
+    k_pfn_points<false><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->weight, a->bn_params, a->pt_mask, a->partials,
+                                                   a->pil_feats, a->image);
+    k_pfn_straddlers<false><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
   }
   add_launches(launches);
   return check_launch("dfb_pfn_forward");
@@ -491,22 +632,19 @@ extern "C" int dfb_pfn_backward(const dfb_pfn_bwd_args* b, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (!b) { set_error("dfb_pfn_backward: null args"); return DFB_ERR_ARG; }
   const dfb_pfn_args* a = &b->fwd;
-  if (!a->csr_rec || !a->pt_mask) { set_error("dfb_pfn_backward: csr_rec / pt_mask missing"); return DFB_ERR_ARG; }
+  if (!a->csr_rec || !a->pt_mask || !a->pil_hdr) { set_error("dfb_pfn_backward: csr_rec / pt_mask / pil_hdr missing"); return DFB_ERR_ARG; }
   const int F = a->F;
-  const PfnGeom G = make_geom(a);
   const int sms = sm_count();
   const float4* rec = (const float4*)a->csr_rec;
   cudaMemsetAsync(b->bwd_stats, 0, sizeof(double) * (size_t)F * PFN_C * (PFN_K + 1), st);
-  int bx = (sms * 8 + F - 1) / F;
+  int bx = (sms * 4 + F - 1) / F;
   if (bx < 1) bx = 1;
   dim3 g(bx, F);
   if (a->image_bf16)
-    k_pfn_bwd<true><<<g, 256, 0, st>>>(a->counts, F, G, rec, a->pt_mask, a->pil_coor, a->pil_pix, a->pil_start, a->pil_mean,
-                                       b->grad_image, b->bwd_stats);
+    k_pfn_bwd<true><<<g, 256, 0, st>>>(a->counts, F, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
   else
-    k_pfn_bwd<false><<<g, 256, 0, st>>>(a->counts, F, G, rec, a->pt_mask, a->pil_coor, a->pil_pix, a->pil_start, a->pil_mean,
-                                        b->grad_image, b->bwd_stats);
-  k_pfn_bwd_finalize<<<1, 1024, 0, st>>>(a->counts, F, a->training, b->bwd_stats, a->stats, a->bn_params, a->weight,
+    k_pfn_bwd<false><<<g, 256, 0, st>>>(a->counts, F, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
+  k_pfn_bwd_finalize<<<1, 512, 0, st>>>(a->counts, F, a->training, b->bwd_stats, a->stats, a->bn_params, a->weight,
                                          b->grad_weight, b->grad_gamma, b->grad_beta);
   add_launches(2);
   return check_launch("dfb_pfn_backward");

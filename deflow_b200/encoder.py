@@ -150,16 +150,6 @@ class PointPillarsScatter(nn.Module):
         return torch.cat(out, dim=0)
 
 
-_SIDE = {}
-
-
-def _side_stream(device) -> "torch.cuda.Stream":
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=device)
-    return _SIDE[key]
-
-
 class DynamicEmbedder(nn.Module):
     """OSF/src/models/basic/encoder.py:602-631."""
 
@@ -174,23 +164,13 @@ class DynamicEmbedder(nn.Module):
 
     def embed(self, points: torch.Tensor, image_dtype=torch.float32):
         """points f32[F,Nmax,3] NaN-padded -> (NHWC pseudo-images [F,H,W,32], PillarIndex)."""
-        # The dense zero canvas (PointPillarsScatter) is pure HBM write bandwidth, the index kernels are latency / atomics
-        # bound: fill the canvas on a side stream while the index runs; the first kernel that writes image rows waits
-        # for the fill (event).
-        H, W = int(self.pseudo_image_dims[0]), int(self.pseudo_image_dims[1])
-        main = torch.cuda.current_stream(points.device)
-        image = torch.empty((points.shape[0], H, W, 32), dtype=image_dtype, device=points.device)
-        side = _side_stream(points.device)
-        side.wait_stream(main)              # the allocator may hand out memory whose last use is still queued on `main`
-        with torch.cuda.stream(side):
-            image.zero_()
-            ready = torch.cuda.Event()
-            ready.record(side)
         idx = self.voxelizer.index(points)
         gx, gy, _ = idx.grid
-        if [gy, gx] != [H, W]:
+        if [gy, gx] != [int(self.pseudo_image_dims[0]), int(self.pseudo_image_dims[1])]:
             raise RuntimeError(f"pseudo_image_dims {self.pseudo_image_dims} do not match the voxel grid {(gy, gx)}")
-        image, _, _ = self.feature_net.forward_fused(idx, image_dtype, want_feats=False, image=image, image_ready=ready)
+        # (Measured on B200: zero-filling the canvas on a second stream UNDER the index kernels makes the pair slower than
+        # running them back to back -- the fill saturates HBM and the latency-bound index kernels stall behind it.)
+        image, _, _ = self.feature_net.forward_fused(idx, image_dtype, want_feats=False)
         return image, idx
 
     def forward(self, points: torch.Tensor) -> Tuple[torch.Tensor, List[dict]]:

@@ -157,7 +157,7 @@ def ego_warp(pc0: torch.Tensor, pose0: Optional[torch.Tensor], pose1: Optional[t
 # Fused pillar feature net
 # ----------------------------------------------------------------------------------------------
 def _pfn_args(idx: PillarIndex, H, W, training, center_off, eps, momentum, weight, gamma, beta, rm, rv, pil_mean,
-              stats, bn_params, pil_feats, image, pt_mask, partials=None, image_ready=None) -> PfnArgs:
+              stats, bn_params, pil_feats, image, pt_mask, pil_hdr, partials=None, image_ready=None) -> PfnArgs:
     a = PfnArgs()
     a.F, a.H, a.W, a.training = idx.F, H, W, int(training)
     a.voxel_size = _f3(idx.voxel_size)
@@ -174,6 +174,7 @@ def _pfn_args(idx: PillarIndex, H, W, training, center_off, eps, momentum, weigh
     a.image_bf16 = int(image.dtype == torch.bfloat16)
     a.pil_cap = idx.pil_cap
     a.csr_rec, a.pt_mask, a.partials = idx.csr_rec.data_ptr(), pt_mask.data_ptr(), _ptr(partials)
+    a.pil_hdr = pil_hdr.data_ptr()
     a.image_ready_event = None if image_ready is None else image_ready.cuda_event
     return a
 
@@ -196,15 +197,17 @@ class _PillarFeatureNet(torch.autograd.Function):
         pil_feats = torch.empty((idx.pil_cap, 32), dtype=torch.float32, device=dev) if want_feats else None
         pt_mask = torch.empty(idx.cap, dtype=torch.int32, device=dev)
         partials = torch.empty((idx.cap // 32 + 1, 2, 32), dtype=torch.float32, device=dev)
+        pil_hdr = torch.empty((idx.pil_cap, 12), dtype=torch.float32, device=dev)
+        ctx.set_materialize_grads(False)   # no zero-filled gradients for the non-differentiable pillar outputs
         if image is None:
             image = torch.empty((idx.F, H, W, 32), dtype=image_dtype, device=dev)
         else:
             assert tuple(image.shape) == (idx.F, H, W, 32) and image.dtype == image_dtype and image.is_contiguous()
         a = _pfn_args(idx, H, W, training, center_off, eps, momentum, w, g, b, running_mean, running_var, pil_mean,
-                      stats, bn_params, pil_feats, image, pt_mask, partials, image_ready)
+                      stats, bn_params, pil_feats, image, pt_mask, pil_hdr, partials, image_ready)
         check(_lib.lib().dfb_pfn_forward(C.byref(a), _stream(weight)), "pfn_forward")
         ctx.idx, ctx.cfg = idx, (H, W, training, eps, momentum, center_off)
-        ctx.save_for_backward(w, g, b, pil_mean, stats, bn_params, pt_mask)
+        ctx.save_for_backward(w, g, b, pil_mean, stats, bn_params, pt_mask, pil_hdr)
         if pil_feats is None:
             pil_feats = pil_mean.new_empty(0)
         ctx.mark_non_differentiable(pil_feats, pil_mean)
@@ -212,15 +215,17 @@ class _PillarFeatureNet(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_image, _g1, _g2):
-        w, g, b, pil_mean, stats, bn_params, pt_mask = ctx.saved_tensors
+        w, g, b, pil_mean, stats, bn_params, pt_mask, pil_hdr = ctx.saved_tensors
         idx = ctx.idx
         H, W, training, eps, momentum, center_off = ctx.cfg
+        if grad_image is None:
+            return (None,) * 14
         grad_image = grad_image.contiguous()
         dev = w.device
         ba = PfnBwdArgs()
         # `image` is not touched by the backward kernels; pass the gradient buffer to carry the dtype flag
         ba.fwd = _pfn_args(idx, H, W, training, center_off, eps, momentum, w, g, b, None, None, pil_mean, stats,
-                           bn_params, None, grad_image, pt_mask)
+                           bn_params, None, grad_image, pt_mask, pil_hdr)
         gw = torch.zeros_like(w)
         gg = torch.zeros_like(g)
         gb = torch.zeros_like(b)

@@ -158,10 +158,15 @@ typedef struct {
   const float* csr_rec;   /* [cap,4] from dfb_pillar_index: (x, y, z, pillar id) in CSR order */
   unsigned* pt_mask;      /* out [cap]: the 32 ReLU decisions of every point (CSR order), read by the backward */
   float* partials;        /* workspace [(cap/32 + 1), 2, 32] fp32: partial sums of pillars that straddle 32-point groups */
+  float* pil_hdr;         /* out [pil_cap,12]: per pillar (first CSR position, count, pixel, frame | mean xyz, centre x | centre yz)
+                             written by the forward, read by every later pass and the backward */
   void* image_ready_event;/* optional cudaEvent_t: the caller zero-fills `image` on another stream; the first kernel that
                              writes the image waits for this event and the call does not memset the image itself */
 } dfb_pfn_args;
 int dfb_pfn_forward(const dfb_pfn_args* args, void* stream);
+/* Dense zero fill (the PointPillarsScatter canvas) with blocks_per_sm small blocks per SM, meant to run on a second
+ * stream under other kernels; ptr 16-byte aligned. */
+int dfb_zero_fill(void* ptr, long long bytes, int blocks_per_sm, void* stream);
 
 typedef struct {
   dfb_pfn_args fwd;         /* same buffers as the forward call */
