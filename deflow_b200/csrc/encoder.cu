@@ -387,10 +387,21 @@ __global__ void __launch_bounds__(256) k_pfn_straddlers(const int* __restrict__ 
 // expanded once per segment.  Everything is linear in the segment sums, so pillars that straddle groups need no
 // special handling.  bwd_acc layout [F][32][10] (double): A1 | T[9].
 struct BwdSlab {
-  float4 pt[32];        // x, y, z, mask bits
-  float4 h1[32], h2[32];// per segment: mean xyz, centre x | centre y, centre z, count, -
-  float g[32][PFN_C + 1];
+  float4 pt[32];        // x, y, z of the group's points
+  float4 h1[32], h2[32];// per segment: mean xyz, centre x | centre y, centre z
+  float g[32][PFN_C + 1];  // per segment: image-gradient row / point count
 };
+
+// transpose the 32 x 32 bit matrix held one row per lane (5 butterfly exchanges): lane c ends up with bit r = row r's bit c
+__device__ __forceinline__ unsigned transpose_bits(unsigned x, int lane) {
+#pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) {
+    const unsigned m0 = k == 16 ? 0x0000ffffu : k == 8 ? 0x00ff00ffu : k == 4 ? 0x0f0f0f0fu : k == 2 ? 0x33333333u : 0x55555555u;
+    const unsigned o = __shfl_xor_sync(0xffffffffu, x, k);
+    x = (lane & k) ? ((x & ~m0) | ((o >> k) & m0)) : ((x & m0) | ((o << k) & ~m0));
+  }
+  return x;
+}
 
 template <bool BF16>
 __global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F,
@@ -413,23 +424,21 @@ __global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts,
     const int j = p0 + grp * 32 + lane;
     const bool live = j < p1;
     int q = -1, pix = 0;
-    float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f), h2 = h1;
-    if (live) {
-      const float4 r = __ldg(rec + j);
-      q = rec_q(r);
-      S.pt[lane] = make_float4(r.x, r.y, r.z, __uint_as_float(__ldg(pt_mask + j)));
-    }
+    unsigned mrow = 0u;
+    float inv_cnt = 0.f;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) { r = __ldg(rec + j); q = rec_q(r); mrow = __ldg(pt_mask + j); }
+    S.pt[lane] = r;
     const int qprev = __shfl_up_sync(0xffffffffu, q, 1);
     const bool start = live && (lane == 0 || q != qprev);
     const unsigned startmask = __ballot_sync(0xffffffffu, start);
-    const int nvalid = min(32, p1 - (p0 + grp * 32));
     const int slot = __popc(startmask & ((1u << lane) - 1u));
     if (start) {
       const float4 h0 = __ldg(pil_hdr + 3 * (size_t)q);
-      h1 = __ldg(pil_hdr + 3 * (size_t)q + 1); h2 = __ldg(pil_hdr + 3 * (size_t)q + 2);
+      S.h1[slot] = __ldg(pil_hdr + 3 * (size_t)q + 1);
+      S.h2[slot] = __ldg(pil_hdr + 3 * (size_t)q + 2);
       pix = __float_as_int(h0.z);
-      h2.z = (float)__float_as_int(h0.y);   // count
-      S.h1[slot] = h1; S.h2[slot] = h2;
+      inv_cnt = __frcp_rn((float)__float_as_int(h0.y));   // mean backward: grad / count (scatter_points_cuda_kernel.cuh:134-137)
     }
     const int nseg = __popc(startmask);
     // image-gradient rows of the group's pillars: lane = channel, one row per segment, all loads issued together
@@ -439,32 +448,40 @@ __global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts,
         const int src = __ffs(sm_) - 1;
         sm_ &= sm_ - 1;
         const int px = __shfl_sync(0xffffffffu, pix, src);
+        const float ic = __shfl_sync(0xffffffffu, inv_cnt, src);
         const size_t o = (size_t)px * PFN_C + lane;
-        S.g[s][lane] = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad_image)[o])
-                            : reinterpret_cast<const float*>(grad_image)[o];
+        const float g = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad_image)[o])
+                             : reinterpret_cast<const float*>(grad_image)[o];
+        S.g[s][lane] = g * ic;
       }
     }
+    const unsigned col = transpose_bits(mrow, lane);   // bit i = ReLU decision of point i for channel `lane`
     __syncwarp();
-    // phase 2: lane = channel
-    unsigned rest = startmask;
-    for (int s = 0; s < nseg; ++s) {
-      const int a = __ffs(rest) - 1;
-      rest &= rest - 1;
-      const int e = rest ? __ffs(rest) - 1 : nvalid;   // one past the segment's last point
-      float u0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
-      for (int i = a; i < e; ++i) {
-        const float4 r = S.pt[i];
-        if ((__float_as_uint(r.w) >> lane) & 1u) { u0 += 1.f; ux += r.x; uy += r.y; uz += r.z; }  // ReLU mask
-      }
+    // lane = channel: masked sums of (1, x, y, z) over each pillar segment, expanded once per segment
+    float u0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
+    int s = -1;
+    auto flush = [&]() {
       const float4 m = S.h1[s], c2 = S.h2[s];
-      // mean backward: grad / count (scatter_points_cuda_kernel.cuh:134-137)
-      const float g = __fdiv_rn(S.g[s][lane], c2.z);
+      const float g = S.g[s][lane];
       // offsets of the three decoration groups: raw (0), cluster mean (m.xyz), pillar centre (m.w, c2.x, c2.y)
       acc[0] = fmaf(g, u0, acc[0]);
       acc[1] = fmaf(g, ux, acc[1]); acc[2] = fmaf(g, uy, acc[2]); acc[3] = fmaf(g, uz, acc[3]);
-      acc[4] = fmaf(g, ux - m.x * u0, acc[4]); acc[5] = fmaf(g, uy - m.y * u0, acc[5]); acc[6] = fmaf(g, uz - m.z * u0, acc[6]);
-      acc[7] = fmaf(g, ux - m.w * u0, acc[7]); acc[8] = fmaf(g, uy - c2.x * u0, acc[8]); acc[9] = fmaf(g, uz - c2.y * u0, acc[9]);
+      acc[4] = fmaf(g, fmaf(-m.x, u0, ux), acc[4]); acc[5] = fmaf(g, fmaf(-m.y, u0, uy), acc[5]);
+      acc[6] = fmaf(g, fmaf(-m.z, u0, uz), acc[6]);
+      acc[7] = fmaf(g, fmaf(-m.w, u0, ux), acc[7]); acc[8] = fmaf(g, fmaf(-c2.x, u0, uy), acc[8]);
+      acc[9] = fmaf(g, fmaf(-c2.y, u0, uz), acc[9]);
+      u0 = 0.f; ux = 0.f; uy = 0.f; uz = 0.f;
+    };
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((startmask >> i) & 1u) {   // warp-uniform
+        if (s >= 0) flush();
+        ++s;
+      }
+      const float4 pt = S.pt[i];
+      if ((col >> i) & 1u) { u0 += 1.f; ux += pt.x; uy += pt.y; uz += pt.z; }
     }
+    if (s >= 0) flush();
     __syncwarp();
   }
   __syncthreads();   // every warp is done with its slab
@@ -599,7 +616,7 @@ extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
   k_pillar_mean<<<sms * 8, 256, 0, st>>>(a->counts, F, HW, G, rec, a->pil_start, a->pil_pix, a->pil_coor, a->pil_mean, hdr);
   int launches = 4;
   if (a->training) {
-    int bx = (sms * 4 + F - 1) / F;
+    int bx = (sms * 3) / F;   // 80 registers -> 3 resident blocks per SM: one wave, no tail
     if (bx < 1) bx = 1;
     dim3 g(bx, F);
     k_pfn_moments<<<g, 256, 0, st>>>(a->counts, F, rec, hdr, a->stats);
@@ -637,7 +654,7 @@ extern "C" int dfb_pfn_backward(const dfb_pfn_bwd_args* b, void* stream_) {
   const int sms = sm_count();
   const float4* rec = (const float4*)a->csr_rec;
   cudaMemsetAsync(b->bwd_stats, 0, sizeof(double) * (size_t)F * PFN_C * (PFN_K + 1), st);
-  int bx = (sms * 4 + F - 1) / F;
+  int bx = (sms * 4) / F;   // 46 KB of shared memory / 64 registers -> 4 resident blocks per SM: one wave, no tail
   if (bx < 1) bx = 1;
   dim3 g(bx, F);
   if (a->image_bf16)
