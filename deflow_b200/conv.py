@@ -127,6 +127,7 @@ def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize
     gx = torch.empty((n, H, W, cin), dtype=out_dtype, device=gy.device)
     stats = torch.zeros((2, cin), dtype=torch.float64, device=gy.device) if colsum else None
     a = _args(1, n, H, W, ksize, stride, [gy], [cin], cout, w_dgrad, None, gx, stats, cin_total, cin_off, xs_lo=gy_lo)
+    a.stats_sum_only = int(colsum)
     kc = 64 if cout % 64 == 0 else 32
     name = f"k_conv_igemm_halo<{cin}>" if _halo(ksize, stride, [cout]) else f"k_conv_igemm<{cin},{kc}>"
     with _timed(name, 2.0 * n * gy.shape[1] * gy.shape[2] * cout * cin * ksize * ksize, gy):

@@ -64,6 +64,7 @@ struct KStep {
 struct IgemmMaps {
   CUtensorMap a[MAX_AMAPS];
   CUtensorMap b;
+  CUtensorMap out;   // bf16 output as [ch, x, y, n] with box [32, 8, 4, 1], SWIZZLE_64B (epilogue TMA stores)
 };
 
 struct IgemmParams {
@@ -77,6 +78,7 @@ struct IgemmParams {
   int sy, sx, oy, ox;
   const float* bias;   // [N] or null
   double* stats;       // [2][N] running sum / sum of squares over all output elements, or null
+  int stats_sum_only;  // only the sums are wanted (bias gradient from a data-gradient launch)
   // halo variant (3x3 stride 1): steps[] holds one entry per 64-channel chunk (wk = K offset of tap 0)
   int halo_pitch;      // pixels per halo row in shared memory (10 or 16)
   int halo_flip;       // data gradient: tap t reads halo offset (2 - t/3, 2 - t%3)
@@ -86,28 +88,32 @@ struct IgemmParams {
   KStep steps[MAX_STEPS];
 };
 
-template <int N>
-__device__ __forceinline__ void colsum_butterfly(float (&v)[32], int lane) {
-  // after the 5 exchange rounds lane L holds in v[0] the sum over the 32 lanes of column L
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const bool up = (lane & s) != 0;
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-}
+constexpr int EPI_STAGE_BYTES = 2048;                 // per epilogue warp: 32 pixels x 32 channels bf16 / 32 x 16 fp32
+constexpr int EPI_SMEM = 4 * EPI_STAGE_BYTES;
 
-// Epilogue shared by the implicit-GEMM kernels: 4 warps = 128 TMEM lanes = the 16 x 8 pixels of a tile.
+// Epilogue shared by the implicit-GEMM kernels: 4 warps = 128 TMEM lanes = the 16 x 8 pixels of a tile; warp q owns
+// tile rows 4q .. 4q+3 (32 pixels, lane = pixel).  Per block of 32 channels:
+//   * bias from shared memory;
+//   * BatchNorm statistics: the warp's 32 x 32 fp32 block goes through a 2 KB XOR-swizzled slab in two halves of 16
+//     columns and is summed column-wise (lane = column x row parity) -- conflict-free both ways, ~1/2 the
+//     instructions of a shuffle butterfly;
+//   * bf16 output: each lane writes its 64-byte row into the same 2 KB region with the 64-byte TMA swizzle and one
+//     lane issues a TMA store of the [32 ch x 8 x 4] box -- fully coalesced, clipped at the image border by the
+//     hardware.  (A lane-per-pixel st.global touches 32 different 128-byte lines per instruction.)
+//   * fp32 output (parity mode): direct stores.
 template <int N>
-__device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, uint32_t tmem_base, uint64_t* acc_full,
-                                               uint64_t* acc_empty, float* s_stats, int warp, int lane) {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+__device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUtensorMap* out_map, uint32_t tmem_base,
+                                               uint64_t* acc_full, uint64_t* acc_empty, float* s_stats,
+                                               const float* s_bias, uint8_t* stage_all, int warp, int lane) {
+  const int q = warp & 3;  // TMEM lane quarter this warp may access
   const int m = q * 32 + lane;
   const int r = m >> 3, c = m & 7;
+  uint8_t* stg = stage_all + q * EPI_STAGE_BYTES;
+  float* slab = reinterpret_cast<float*>(stg);
+  const int sw16 = (lane >> 1) & 15;        // slab column swizzle of this lane's row
+  const int sw4 = (lane >> 1) & 3;          // 64-byte TMA swizzle of this lane's row
+  const int rcol = lane & 15, rpar = lane >> 4;
+  bool store_pending = false;
   int acc = 0;
   uint32_t acc_phase = 0;
   for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
@@ -124,37 +130,61 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, uint32_t tm
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + col, v);
       if (P.bias) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += __ldg(P.bias + col + i);
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col + i);
+          v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+        }
       }
-      if (valid) {
-        if (P.out_fp32) {
+      if (store_pending) {            // the previous TMA store must have read the region before it is rewritten
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        store_pending = false;
+      }
+      if (P.stats) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) slab[lane * 16 + (i ^ sw16)] = valid ? v[h * 16 + i] : 0.f;
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {       // rows 2i + rpar of column rcol
+            const float t = slab[(2 * i + rpar) * 16 + (rcol ^ i)];
+            s1 += t;
+            s2 = fmaf(t, t, s2);
+          }
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (lane < 16) {
+            atomicAdd(&s_stats[col + h * 16 + lane], s1);
+            if (!P.stats_sum_only) atomicAdd(&s_stats[N + col + h * 16 + lane], s2);
+          }
+          __syncwarp();
+        }
+      }
+      if (P.out_fp32) {
+        if (valid) {
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off + col);
 #pragma unroll
           for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off + col);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<unsigned*>(&p0); u.y = *reinterpret_cast<unsigned*>(&p1);
-            u.z = *reinterpret_cast<unsigned*>(&p2); u.w = *reinterpret_cast<unsigned*>(&p3);
-            dst[i] = u;
-          }
         }
-      }
-      if (P.stats) {
-        float sq[32];
+      } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (!valid) v[i] = 0.f;
-          sq[i] = v[i] * v[i];
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<unsigned*>(&p0); u.y = *reinterpret_cast<unsigned*>(&p1);
+          u.z = *reinterpret_cast<unsigned*>(&p2); u.w = *reinterpret_cast<unsigned*>(&p3);
+          *reinterpret_cast<uint4*>(stg + lane * 64 + ((i ^ sw4) << 4)) = u;
         }
-        colsum_butterfly<N>(v, lane);
-        colsum_butterfly<N>(sq, lane);
-        atomicAdd(&s_stats[col + lane], v[0]);
-        atomicAdd(&s_stats[N + col + lane], sq[0]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(out_map, stg, col, tx * TILE_W, ty * TILE_H + 4 * q, n);
+          tma_store_commit();
+        }
+        store_pending = true;
       }
     }
     tc_fence_before();
@@ -163,6 +193,7 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, uint32_t tm
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
   }
+  if (lane == 0) tma_store_wait_all();
 }
 
 template <int N, int KC>
@@ -173,7 +204,7 @@ struct IgemmCfg {
   static constexpr int BUDGET = 200 * 1024;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * N * 4 * 2;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_SMEM + 1024 /*alignment slack*/ + 256 /*barriers*/ + 3 * N * 4 + 64;
   static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
   static constexpr int SWIZZLE = KC * 2;             // bytes per pixel row: 128 or 64
   static constexpr int LAYOUT = KC == 64 ? 2 : 4;    // UMMA layout type
@@ -187,13 +218,15 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;  // [STAGES][A | B], every tile 1024-byte aligned (A_BYTES, B_BYTES are multiples of 1024)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;   // 1024-aligned (stage sizes are multiples of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_SMEM);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
   uint64_t* acc_full = bars + 2 * Cfg::STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);  // [2][N]
+  float* s_stats = reinterpret_cast<float*>(epi_stage + EPI_SMEM + 256);  // [2][N]
+  float* s_bias = s_stats + 2 * N;                                         // [N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -206,6 +239,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -260,14 +294,14 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
       }
     }
   } else {
-    igemm_epilogue<N>(P, tmem_base, acc_full, acc_empty, s_stats, warp, lane);
+    igemm_epilogue<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (P.stats) {
-    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) atomicAdd(&P.stats[i], (double)s_stats[i]);
+    for (int i = threadIdx.x; i < (P.stats_sum_only ? N : 2 * N); i += blockDim.x) atomicAdd(&P.stats[i], (double)s_stats[i]);
   }
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
@@ -285,10 +319,10 @@ struct HaloCfg {
   static constexpr int HALO_BYTES = 23 * 1024;                     // 18 x 10 pixels x 128 B = 23040, 1024-aligned
   static constexpr int W_BYTES = N * 128;                          // one tap x one 64-channel chunk
   static constexpr int HALO_STAGES = 3;
-  static constexpr int W_STAGES_RAW = (225 * 1024 - 2048 - 2 * N * 4 - HALO_STAGES * HALO_BYTES) / W_BYTES;
+  static constexpr int W_STAGES_RAW = (225 * 1024 - 2048 - 3 * N * 4 - EPI_SMEM - HALO_STAGES * HALO_BYTES) / W_BYTES;
   static constexpr int W_STAGES = W_STAGES_RAW > 18 ? 18 : W_STAGES_RAW;
   static constexpr int TILE_BYTES = HALO_STAGES * HALO_BYTES + W_STAGES * W_BYTES;
-  static constexpr int SMEM = TILE_BYTES + 1024 + 512 + 2 * N * 4;
+  static constexpr int SMEM = TILE_BYTES + EPI_SMEM + 1024 + 512 + 3 * N * 4;
   static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
 };
 
@@ -300,7 +334,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* halos = smem;
   uint8_t* wts = smem + Cfg::HALO_STAGES * Cfg::HALO_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILE_BYTES);
+  uint8_t* epi_stage = smem + Cfg::TILE_BYTES;              // 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_SMEM);
   uint64_t* h_full = bars;                                  // [HALO_STAGES]
   uint64_t* h_empty = h_full + Cfg::HALO_STAGES;            // [HALO_STAGES]
   uint64_t* w_full = h_empty + Cfg::HALO_STAGES;            // [W_STAGES]
@@ -308,7 +343,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
   uint64_t* acc_full = w_empty + Cfg::W_STAGES;             // [2]
   uint64_t* acc_empty = acc_full + 2;                       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_stats = reinterpret_cast<float*>(smem + Cfg::TILE_BYTES + 512);
+  float* s_stats = reinterpret_cast<float*>(epi_stage + EPI_SMEM + 512);
+  float* s_bias = s_stats + 2 * N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t halo_tx = 18u * (uint32_t)P.halo_pitch * 128u;
 
@@ -322,6 +358,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -354,9 +391,24 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // The issue loop is on the critical path of the small-N tiles (an N = 64 MMA takes ~70 cycles).  The whole warp
+      // runs the loop (warp-uniform control flow -> uniform registers), one elected lane issues; descriptors are
+      // (lo, hi) register pairs whose hi words never change: per MMA one 32-bit add per operand.
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, N, 0, 0);
-      const uint32_t sbo = (uint32_t)P.halo_pitch * 128u;
+      const uint64_t a_proto = make_smem_desc(0, 16, (uint32_t)P.halo_pitch * 128u, 2, 0);
+      const uint64_t b_proto = make_smem_desc(0, 16, 1024, 2);
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_proto | ((smem_u32(halos) & 0x3FFFFu) >> 4);
+      const uint32_t b_lo0 = (uint32_t)b_proto | ((smem_u32(wts) & 0x3FFFFu) >> 4);
+      uint32_t tap_off[9];   // start of tap t inside the halo box, in 16-byte units
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int ty3 = t / 3, tx3 = t - 3 * ty3;
+        const int hy = P.halo_flip ? 2 - ty3 : ty3, hx = P.halo_flip ? 2 - tx3 : tx3;
+        tap_off[t] = (uint32_t)(hy * P.halo_pitch + hx) * 8u;
+      }
+      const bool resident = P.w_resident != 0;
       int hs = 0, ws = 0, acc = 0;
       uint32_t hph = 0, wph = 0, acc_phase = 0;
       bool first_tile = true;
@@ -364,49 +416,62 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * N;
-        if (P.w_resident) ws = 0;
+        uint32_t accum = 0u;
+        if (resident) ws = 0;
         for (int s = 0; s < P.nsteps; ++s) {
           mbar_wait(&h_full[hs], hph);
           tc_fence_after();
-          const uint32_t h_addr = smem_u32(halos + hs * Cfg::HALO_BYTES);
-          for (int t = 0; t < 9; ++t) {
-            if (!P.w_resident || first_tile) { mbar_wait(&w_full[ws], wph); tc_fence_after(); }
-            const int ty3 = t / 3, tx3 = t - 3 * ty3;
-            const int hy = P.halo_flip ? 2 - ty3 : ty3, hx = P.halo_flip ? 2 - tx3 : tx3;
-            const uint32_t a_addr = h_addr + (uint32_t)(hy * P.halo_pitch + hx) * 128u;
-            const uint32_t boff = P.dbg_base_offset ? ((a_addr >> 7) & 7u) : 0u;
-            const uint64_t adesc = make_smem_desc(a_addr, 16, sbo, 2, boff);
-            const uint64_t bdesc = make_smem_desc(smem_u32(wts + ws * Cfg::W_BYTES), 16, 1024, 2);
+          const uint32_t ah = a_lo0 + (uint32_t)hs * (uint32_t)(Cfg::HALO_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (s | t | k) != 0);
-            if (!P.w_resident) umma_commit(&w_empty[ws]);
+          for (int t = 0; t < 9; ++t) {
+            if (!resident || first_tile) { mbar_wait(&w_full[ws], wph); tc_fence_after(); }
+            const uint32_t a_lo = ah + tap_off[t];
+            const uint32_t b_lo = b_lo0 + (uint32_t)ws * (uint32_t)(Cfg::W_BYTES >> 4);
+            umma_bf16_lohi_warp(d, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+            umma_bf16_lohi_warp(d, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+            umma_bf16_lohi_warp(d, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+            umma_bf16_lohi_warp(d, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+            accum = 1u;
+            if (!resident) umma_commit_warp(&w_empty[ws]);
             if (++ws == Cfg::W_STAGES) { ws = 0; wph ^= 1; }
           }
-          umma_commit(&h_empty[hs]);
+          umma_commit_warp(&h_empty[hs]);
           if (++hs == Cfg::HALO_STAGES) { hs = 0; hph ^= 1; }
         }
-        umma_commit(&acc_full[acc]);
+        umma_commit_warp(&acc_full[acc]);
         first_tile = false;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
-    igemm_epilogue<N>(P, tmem_base, acc_full, acc_empty, s_stats, warp, lane);
+    igemm_epilogue<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (P.stats) {
-    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) atomicAdd(&P.stats[i], (double)s_stats[i]);
+    for (int i = threadIdx.x; i < (P.stats_sum_only ? N : 2 * N); i += blockDim.x) atomicAdd(&P.stats[i], (double)s_stats[i]);
   }
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// Output tensor map of a launch: element (n, y, x, ch) of the tile space lives at
+// out + n*img + (y*sy+oy)*row + (x*sx+ox)*pix + ch  (bf16) -> dims [ch, x, y, n], box [32, 8, 4, 1], SWIZZLE_64B.
+static int build_out_map(IgemmMaps& maps, const IgemmParams& P, int N) {
+  if (P.out_fp32) return DFB_OK;
+  const uint64_t dims[4] = {(uint64_t)N, (uint64_t)P.Wt, (uint64_t)P.Ht, (uint64_t)P.n_img};
+  const uint64_t str[3] = {(uint64_t)P.out_pix * P.sx * 2, (uint64_t)P.out_row * P.sy * 2, (uint64_t)P.out_img * 2};
+  const uint32_t box[4] = {32, TILE_W, 4, 1};
+  const char* base = (const char*)P.out + ((size_t)P.oy * P.out_row + (size_t)P.ox * P.out_pix) * 2;
+  return make_tensor_map_bf16(&maps.out, base, 4, dims, str, box, 64);
+}
+
 template <int N>
-static int launch_igemm_halo(const IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
+static int launch_igemm_halo(IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
   using Cfg = HaloCfg<N>;
+  if (int rc = build_out_map(maps, P, N)) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_igemm_halo<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -421,7 +486,7 @@ static int launch_igemm_halo(const IgemmMaps& maps, IgemmParams& P, cudaStream_t
   return check_launch("conv_igemm_halo");
 }
 
-static int dispatch_igemm_halo(int N, const IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
+static int dispatch_igemm_halo(int N, IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
   if (N == 32) return launch_igemm_halo<32>(maps, P, st);
   if (N == 64) return launch_igemm_halo<64>(maps, P, st);
   if (N == 128) return launch_igemm_halo<128>(maps, P, st);
@@ -488,8 +553,9 @@ __global__ void __launch_bounds__(256) k_split_bf16x2(const float4* __restrict__
 }
 
 template <int N, int KC>
-static int launch_igemm(const IgemmMaps& maps, const IgemmParams& P, cudaStream_t st) {
+static int launch_igemm(IgemmMaps& maps, const IgemmParams& P, cudaStream_t st) {
   using Cfg = IgemmCfg<N, KC>;
+  if (int rc = build_out_map(maps, P, N)) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_igemm<N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -503,7 +569,7 @@ static int launch_igemm(const IgemmMaps& maps, const IgemmParams& P, cudaStream_
   return check_launch("conv_igemm");
 }
 
-static int dispatch_igemm(int N, int KC, const IgemmMaps& maps, const IgemmParams& P, cudaStream_t st) {
+static int dispatch_igemm(int N, int KC, IgemmMaps& maps, const IgemmParams& P, cudaStream_t st) {
 #define DFB_CASE(n, kc) if (N == n && KC == kc) return launch_igemm<n, kc>(maps, P, st)
   DFB_CASE(32, 64); DFB_CASE(64, 64); DFB_CASE(128, 64); DFB_CASE(256, 64);
   DFB_CASE(32, 32); DFB_CASE(64, 32); DFB_CASE(128, 32); DFB_CASE(256, 32);
@@ -564,6 +630,7 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
   P.out_fp32 = a->y_fp32;
   P.bias = a->bias;
   P.stats = a->stats;
+  P.stats_sum_only = a->stats_sum_only;
   int N, KC, rc, nsteps = 0;
   // split-precision ("bf16x3") mode: every operand is a (hi, lo) bf16 pair, x = hi + lo to ~16 significant bits; the
   // K loop runs hi*hi + hi*lo + lo*hi into the same fp32 accumulator.  lo tensor maps live at index + 4, the lo half of

@@ -228,6 +228,7 @@ typedef struct {
   double* stats;         /* [2][cout] or NULL */
   const void* x_lo[2];   /* split-precision mode: the lo halves of the sources (x[] are the hi halves) */
   int split3;            /* 1: operands are (hi, lo) bf16 pairs, weights packed with split3, K loop = hi*hi + hi*lo + lo*hi */
+  int stats_sum_only;    /* 1: only stats[0][*] (the per-channel sums) is wanted, e.g. a bias gradient from a data-gradient launch */
 } dfb_conv_args;
 int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, int split3, void* w_fwd, void* w_dgrad,
                           void* stream);
