@@ -46,7 +46,8 @@ class PfnArgs(C.Structure):
                 ("running_var", C.c_void_p), ("pil_mean", C.c_void_p), ("stats", C.c_void_p),
                 ("bn_params", C.c_void_p), ("pil_feats", C.c_void_p), ("image", C.c_void_p),
                 ("image_bf16", C.c_int), ("pil_cap", C.c_longlong), ("csr_rec", C.c_void_p), ("pt_mask", C.c_void_p),
-                ("partials", C.c_void_p), ("pil_hdr", C.c_void_p), ("image_ready_event", C.c_void_p)]
+                ("partials", C.c_void_p), ("pil_hdr", C.c_void_p), ("image_ready_event", C.c_void_p),
+                ("range_min", C.c_float * 3)]
 
 
 class PfnBwdArgs(C.Structure):

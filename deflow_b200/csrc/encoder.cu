@@ -45,42 +45,61 @@ __device__ __forceinline__ int rec_q(const float4& r) { return __float_as_int(r.
 //   h[0] = (first CSR position, point count, pixel index, frame)   (ints)
 //   h[1] = (mean x, mean y, mean z, centre x)                       h[2] = (centre y, centre z, -, -)
 // with centre = c * voxel + (voxel / 2 + range_min), rounded exactly like encoder.py:452-457.
+// Four lanes per pillar (median pillar: 4 points), two pillars per lane group and iteration with every first-round
+// load of both issued before the first use -- the pass is latency-bound, not bandwidth-bound.  The four lanes split the
+// header stores between them.
 __global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ counts, int F, int HW, PfnGeom G,
                                                      const float4* __restrict__ rec,
                                                      const int* __restrict__ pil_start, const int* __restrict__ pil_pix,
                                                      const int* __restrict__ pil_coor, float* __restrict__ pil_mean,
                                                      float4* __restrict__ pil_hdr) {
   const int M = counts[3 * F + 1 + F];
-  const int sub = threadIdx.x & 7;
-  const int groups = (gridDim.x * blockDim.x) >> 3;
-  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; q < ((M + 3) & ~3); q += groups) {
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    int s0 = 0, s1 = 0;
-    if (q < M) { s0 = pil_start[q]; s1 = pil_start[q + 1]; }
-    for (int j = s0 + sub; j < s1; j += 8) {
-      const float4 r = __ldg(rec + j);
-      sx += r.x; sy += r.y; sz += r.z;
+  const int Mr = (M + 7) & ~7;                    // all 8 lane groups of a warp run the same number of iterations
+  const int sub = threadIdx.x & 3;
+  const int groups = (gridDim.x * blockDim.x) >> 2;
+  constexpr int U = 2;
+  for (int q0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; q0 < Mr; q0 += U * groups) {
+    int s0[U], s1[U], pix[U], cz[U], cy[U], cx[U];
+    float4 r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u * groups;
+      s0[u] = 0; s1[u] = 0; pix[u] = 0; cz[u] = cy[u] = cx[u] = 0;
+      if (q < M) {
+        s0[u] = pil_start[q]; s1[u] = pil_start[q + 1];
+        pix[u] = pil_pix[q];
+        cz[u] = pil_coor[3 * (size_t)q]; cy[u] = pil_coor[3 * (size_t)q + 1]; cx[u] = pil_coor[3 * (size_t)q + 2];
+      }
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      sx += __shfl_xor_sync(0xffffffffu, sx, o);
-      sy += __shfl_xor_sync(0xffffffffu, sy, o);
-      sz += __shfl_xor_sync(0xffffffffu, sz, o);
-    }
-    if (sub == 0 && q < M) {
-      const float n = (float)(s1 - s0);  // reduced_feats /= count.to(float) (scatter_points_cuda.cu:59-60)
-      const float mx = __fdiv_rn(sx, n), my = __fdiv_rn(sy, n), mz = __fdiv_rn(sz, n);
-      pil_mean[3 * (size_t)q] = mx;
-      pil_mean[3 * (size_t)q + 1] = my;
-      pil_mean[3 * (size_t)q + 2] = mz;
-      const int pix = pil_pix[q];
-      const int cz = pil_coor[3 * (size_t)q], cy = pil_coor[3 * (size_t)q + 1], cx = pil_coor[3 * (size_t)q + 2];
-      const float ox = __fadd_rn(__fmul_rn((float)cx, G.vx), G.ox), oy = __fadd_rn(__fmul_rn((float)cy, G.vy), G.oy),
-                  oz = __fadd_rn(__fmul_rn((float)cz, G.vz), G.oz);
-      float4* h = pil_hdr + 3 * (size_t)q;
-      h[0] = make_float4(__int_as_float(s0), __int_as_float(s1 - s0), __int_as_float(pix), __int_as_float(pix / HW));
-      h[1] = make_float4(mx, my, mz, ox);
-      h[2] = make_float4(oy, oz, 0.f, 0.f);
+    for (int u = 0; u < U; ++u)
+      r[u] = s0[u] + sub < s1[u] ? __ldg(rec + s0[u] + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u * groups;
+      float sx = r[u].x, sy = r[u].y, sz = r[u].z;
+      for (int j = s0[u] + sub + 4; j < s1[u]; j += 4) {
+        const float4 t = __ldg(rec + j);
+        sx += t.x; sy += t.y; sz += t.z;
+      }
+#pragma unroll
+      for (int o = 2; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+      }
+      if (q < M) {
+        const float n = (float)(s1[u] - s0[u]);  // reduced_feats /= count.to(float) (scatter_points_cuda.cu:59-60)
+        const float mx = __fdiv_rn(sx, n), my = __fdiv_rn(sy, n), mz = __fdiv_rn(sz, n);
+        const float ox = __fadd_rn(__fmul_rn((float)cx[u], G.vx), G.ox), oy = __fadd_rn(__fmul_rn((float)cy[u], G.vy), G.oy),
+                    oz = __fadd_rn(__fmul_rn((float)cz[u], G.vz), G.oz);
+        float4* h = pil_hdr + 3 * (size_t)q;
+        if (sub == 0) h[0] = make_float4(__int_as_float(s0[u]), __int_as_float(s1[u] - s0[u]), __int_as_float(pix[u]),
+                                         __int_as_float(pix[u] / HW));
+        else if (sub == 1) h[1] = make_float4(mx, my, mz, ox);
+        else if (sub == 2) h[2] = make_float4(oy, oz, 0.f, 0.f);
+        else { pil_mean[3 * (size_t)q] = mx; pil_mean[3 * (size_t)q + 1] = my; pil_mean[3 * (size_t)q + 2] = mz; }
+      }
     }
   }
 }
@@ -227,13 +246,13 @@ __device__ __forceinline__ void store_row32(float* __restrict__ dst, const float
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256, 3) k_pfn_points(const int* __restrict__ counts, int F,
+__global__ void __launch_bounds__(256, 4) k_pfn_points(const int* __restrict__ counts, int F,
                                                        const float4* __restrict__ rec, const float4* __restrict__ pil_hdr,
                                                        const float* __restrict__ weight, const float* __restrict__ bn_params,
                                                        unsigned* __restrict__ pt_mask, float* __restrict__ part,
                                                        float* __restrict__ pil_feats, void* __restrict__ image) {
   __shared__ __align__(16) float Wp[PFN_K][PFN_C];          // Wp[k][c]
-  extern __shared__ __align__(16) float sAB[];              // [F][2][32] scale / shift per frame
+  extern __shared__ __align__(16) float sAB[];              // [F][2][32] scale / shift per frame | 8 x [32][33] tiles
   const int n = counts[2 * F + F];
   for (int i = threadIdx.x; i < PFN_C * PFN_K; i += blockDim.x) Wp[i % PFN_K][i / PFN_K] = weight[i];
   for (int i = threadIdx.x; i < F * 2 * PFN_C; i += blockDim.x) {
@@ -242,6 +261,7 @@ __global__ void __launch_bounds__(256, 3) k_pfn_points(const int* __restrict__ c
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  float* T = sAB + (size_t)F * 2 * PFN_C + (threadIdx.x >> 5) * (32 * 33);   // this warp's [point][channel] tile
   const int n_groups = (n + 31) >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
@@ -249,9 +269,6 @@ __global__ void __launch_bounds__(256, 3) k_pfn_points(const int* __restrict__ c
     const bool live = j < n;
     int q = 0, pix = 0, cnt = 1;
     bool first = false, last = false;
-    float v[PFN_C];
-#pragma unroll
-    for (int c = 0; c < PFN_C; ++c) v[c] = 0.f;
     if (live) {
       const float4 r = __ldg(rec + j);
       q = rec_q(r);
@@ -284,68 +301,48 @@ __global__ void __launch_bounds__(256, 3) k_pfn_points(const int* __restrict__ c
         const float4 a = *reinterpret_cast<const float4*>(ab + c4), b = *reinterpret_cast<const float4*>(ab + PFN_C + c4);
         const float2 v0 = __ffma2_rn(y2[c4 / 2], make_float2(a.x, a.y), make_float2(b.x, b.y));
         const float2 v1 = __ffma2_rn(y2[c4 / 2 + 1], make_float2(a.z, a.w), make_float2(b.z, b.w));
-        v[c4] = fmaxf(v0.x, 0.f); v[c4 + 1] = fmaxf(v0.y, 0.f); v[c4 + 2] = fmaxf(v1.x, 0.f); v[c4 + 3] = fmaxf(v1.y, 0.f);
+        const float r0 = fmaxf(v0.x, 0.f), r1 = fmaxf(v0.y, 0.f), r2 = fmaxf(v1.x, 0.f), r3 = fmaxf(v1.y, 0.f);
         // relu(x) > 0  <=>  x > 0; the bits of a non-negative float are a positive int exactly when it is > 0
-        m |= ((unsigned)(-__float_as_int(v[c4])) >> 31) << c4;
-        m |= ((unsigned)(-__float_as_int(v[c4 + 1])) >> 31) << (c4 + 1);
-        m |= ((unsigned)(-__float_as_int(v[c4 + 2])) >> 31) << (c4 + 2);
-        m |= ((unsigned)(-__float_as_int(v[c4 + 3])) >> 31) << (c4 + 3);
+        m |= ((unsigned)(-__float_as_int(r0)) >> 31) << c4;
+        m |= ((unsigned)(-__float_as_int(r1)) >> 31) << (c4 + 1);
+        m |= ((unsigned)(-__float_as_int(r2)) >> 31) << (c4 + 2);
+        m |= ((unsigned)(-__float_as_int(r3)) >> 31) << (c4 + 3);
+        // transpose through the tile: bank (33 * lane + c) % 32 = (lane + c) % 32, conflict-free both ways
+        T[lane * 33 + c4] = r0; T[lane * 33 + c4 + 1] = r1; T[lane * 33 + c4 + 2] = r2; T[lane * 33 + c4 + 3] = r3;
       }
       pt_mask[j] = m;
     }
     const unsigned firstmask = __ballot_sync(0xffffffffu, first), lastmask = __ballot_sync(0xffffffffu, last);
     const int nvalid = min(32, n - grp * 32);
-    // segmented inclusive scan over the lanes; a segment starts at lane 0 (possibly the tail of an earlier group's
-    // pillar) and at every first point of a pillar
-    const unsigned starts = firstmask | 1u;
-    const int seg_start = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));
-    const int dist = lane - seg_start;
-    const unsigned far = __ballot_sync(0xffffffffu, dist >= 4);
-#pragma unroll
-    for (int c = 0; c < PFN_C; ++c) {
-      float x = v[c], t;
-      t = __shfl_up_sync(0xffffffffu, x, 1); if (dist >= 1) x += t;
-      t = __shfl_up_sync(0xffffffffu, x, 2); if (dist >= 2) x += t;
-      v[c] = x;
-    }
-    if (far) {   // some segment of this group is longer than 4 points (warp-uniform)
-#pragma unroll
-      for (int c = 0; c < PFN_C; ++c) {
-        float x = v[c], t;
-        t = __shfl_up_sync(0xffffffffu, x, 4); if (dist >= 4) x += t;
-        t = __shfl_up_sync(0xffffffffu, x, 8); if (dist >= 8) x += t;
-        t = __shfl_up_sync(0xffffffffu, x, 16); if (dist >= 16) x += t;
-        v[c] = x;
-      }
-    }
-    const bool begins = (firstmask >> seg_start) & 1u;   // the segment this lane closes began inside this group
+    __syncwarp();
+    // lane = channel: walk the group's points in CSR order; a pillar that begins AND ends inside the group is finished
+    // on the spot (mean, voxel feature row, NHWC image row: one coalesced 64 / 128-byte row per pillar)
     float* prow = part + (size_t)grp * 2 * PFN_C;
-    if (live && last) {
-      if (begins) {
-        const float inv = __frcp_rn((float)cnt);
+    float acc = 0.f;
+    bool began = false;
 #pragma unroll
-        for (int c = 0; c < PFN_C; ++c) v[c] *= inv;
-        if (pil_feats) store_row32(pil_feats + (size_t)q * PFN_C, v);
-        if (BF16) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(image) + (size_t)pix * PFN_C);
-#pragma unroll
-          for (int c8 = 0; c8 < PFN_C; c8 += 8) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[c8], v[c8 + 1]), p1 = __floats2bfloat162_rn(v[c8 + 2], v[c8 + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[c8 + 4], v[c8 + 5]), p3 = __floats2bfloat162_rn(v[c8 + 6], v[c8 + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<unsigned*>(&p0); u.y = *reinterpret_cast<unsigned*>(&p1);
-            u.z = *reinterpret_cast<unsigned*>(&p2); u.w = *reinterpret_cast<unsigned*>(&p3);
-            dst[c8 / 8] = u;
+    for (int i = 0; i < 32; ++i) {
+      if (i < nvalid) {                       // warp-uniform
+        if ((firstmask >> i) & 1u) { acc = 0.f; began = true; }
+        acc += T[i * 33 + lane];
+        if ((lastmask >> i) & 1u) {
+          if (began) {
+            const int cnt_i = __shfl_sync(0xffffffffu, cnt, i), pix_i = __shfl_sync(0xffffffffu, pix, i);
+            const float val = acc * __frcp_rn((float)cnt_i);
+            if (pil_feats) pil_feats[(size_t)__shfl_sync(0xffffffffu, q, i) * PFN_C + lane] = val;
+            if (BF16) reinterpret_cast<__nv_bfloat16*>(image)[(size_t)pix_i * PFN_C + lane] = __float2bfloat16_rn(val);
+            else reinterpret_cast<float*>(image)[(size_t)pix_i * PFN_C + lane] = val;
+          } else {
+            prow[lane] = acc;                 // leading segment of a pillar that began in an earlier group
           }
-        } else {
-          store_row32(reinterpret_cast<float*>(image) + (size_t)pix * PFN_C, v);
+          began = false;
+          acc = 0.f;
+        } else if (i == nvalid - 1) {
+          prow[(began ? PFN_C : 0) + lane] = acc;   // the pillar continues into the next group
         }
-      } else {
-        store_row32(prow, v);            // leading segment of a pillar that began in an earlier group
       }
-    } else if (live && lane == nvalid - 1) {
-      store_row32(prow + (begins ? PFN_C : 0), v);   // the pillar continues into the next group
     }
+    __syncwarp();                             // the tile is rewritten by the next group
   }
 }
 
@@ -386,10 +383,18 @@ __global__ void __launch_bounds__(256) k_pfn_straddlers(const int* __restrict__ 
 // is latency-bound, not bandwidth-bound.  Phase 2, lane = channel: per pillar segment the masked sums of (1, x, y, z),
 // expanded once per segment.  Everything is linear in the segment sums, so pillars that straddle groups need no
 // special handling.  bwd_acc layout [F][32][10] (double): A1 | T[9].
+struct BwdGeom {       // pixel of a point, recomputed from its coordinates exactly as the index pass did
+  float lox, loy, vx, vy;
+  int W, HW;
+};
+
+template <bool BF16>
 struct BwdSlab {
+  static constexpr int ROW_BYTES = BF16 ? 64 : 128;
   float4 pt[32];        // x, y, z of the group's points
   float4 h1[32], h2[32];// per segment: mean xyz, centre x | centre y, centre z
-  float g[32][PFN_C + 1];  // per segment: image-gradient row / point count
+  float ic[32];         // per segment: 1 / point count
+  __align__(16) unsigned char g[32][ROW_BYTES];   // per segment: image-gradient row, raw (cp.async destination)
 };
 
 // transpose the 32 x 32 bit matrix held one row per lane (5 butterfly exchanges): lane c ends up with bit r = row r's bit c
@@ -403,66 +408,86 @@ __device__ __forceinline__ unsigned transpose_bits(unsigned x, int lane) {
   return x;
 }
 
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Latency plan per group of 32 CSR positions: the point records and ReLU mask words of the NEXT group are already in
+// registers (prefetched during the previous compute phase); the pillar headers (segment starts only) and the image
+// gradient rows are fetched TOGETHER -- the row address comes from the point itself (its pixel is recomputed from xyz),
+// not from the header -- and the rows go straight to shared memory with cp.async (16 bytes per lane, 8 / 4 rows per
+// instruction), so no load result is waited for before the next load is issued.
 template <bool BF16>
-__global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F,
+__global__ void __launch_bounds__(256) k_pfn_bwd(const int* __restrict__ counts, int F, BwdGeom Gm,
                                                  const float4* __restrict__ rec, const unsigned* __restrict__ pt_mask,
                                                  const float4* __restrict__ pil_hdr,
                                                  const void* __restrict__ grad_image, double* __restrict__ bwd_acc) {
-  __shared__ BwdSlab slabs[8];
-  static_assert(sizeof(BwdSlab) * 8 >= sizeof(float) * 8 * PFN_C * (PFN_K + 2), "the block reduction reuses the slabs");
+  using Slab = BwdSlab<BF16>;
+  __shared__ Slab slabs[8];
+  static_assert(sizeof(Slab) * 8 >= sizeof(float) * 8 * PFN_C * (PFN_K + 2), "the block reduction reuses the slabs");
   float (*red)[PFN_C][PFN_K + 2] = reinterpret_cast<float (*)[PFN_C][PFN_K + 2]>(slabs);
   const int f = blockIdx.y;
   const int p0 = counts[2 * F + f], p1 = counts[2 * F + f + 1];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  BwdSlab& S = slabs[wib];
+  Slab& S = slabs[wib];
   const int warps = (gridDim.x * blockDim.x) >> 5;
   float acc[PFN_K + 1];   // A1 | T[9] of channel `lane`
 #pragma unroll
   for (int k = 0; k < PFN_K + 1; ++k) acc[k] = 0.f;
   const int n_groups = (p1 - p0 + 31) >> 5;
-  for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
+  constexpr int LPR = Slab::ROW_BYTES / 16;   // lanes per row
+  constexpr int RPI = 32 / LPR;               // rows per cp.async instruction
+  int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned mrow = 0u;
+  if (grp < n_groups && p0 + grp * 32 + lane < p1) { r = __ldg(rec + p0 + grp * 32 + lane); mrow = __ldg(pt_mask + p0 + grp * 32 + lane); }
+  for (; grp < n_groups; grp += warps) {
     const int j = p0 + grp * 32 + lane;
     const bool live = j < p1;
-    int q = -1, pix = 0;
-    unsigned mrow = 0u;
-    float inv_cnt = 0.f;
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) { r = __ldg(rec + j); q = rec_q(r); mrow = __ldg(pt_mask + j); }
+    const int q = live ? rec_q(r) : -1;
     S.pt[lane] = r;
     const int qprev = __shfl_up_sync(0xffffffffu, q, 1);
     const bool start = live && (lane == 0 || q != qprev);
     const unsigned startmask = __ballot_sync(0xffffffffu, start);
     const int slot = __popc(startmask & ((1u << lane) - 1u));
-    if (start) {
-      const float4 h0 = __ldg(pil_hdr + 3 * (size_t)q);
-      S.h1[slot] = __ldg(pil_hdr + 3 * (size_t)q + 1);
-      S.h2[slot] = __ldg(pil_hdr + 3 * (size_t)q + 2);
-      pix = __float_as_int(h0.z);
-      inv_cnt = __frcp_rn((float)__float_as_int(h0.y));   // mean backward: grad / count (scatter_points_cuda_kernel.cuh:134-137)
-    }
     const int nseg = __popc(startmask);
-    // image-gradient rows of the group's pillars: lane = channel, one row per segment, all loads issued together
-    {
-      unsigned sm_ = startmask;
-      for (int s = 0; s < nseg; ++s) {
-        const int src = __ffs(sm_) - 1;
-        sm_ &= sm_ - 1;
-        const int px = __shfl_sync(0xffffffffu, pix, src);
-        const float ic = __shfl_sync(0xffffffffu, inv_cnt, src);
-        const size_t o = (size_t)px * PFN_C + lane;
-        const float g = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad_image)[o])
-                             : reinterpret_cast<const float*>(grad_image)[o];
-        S.g[s][lane] = g * ic;
-      }
+    // pixel of the point = f*H*W + cy*W + cx with the index pass's own voxel formula (the point is known to be in range)
+    const int pix = f * Gm.HW + voxel_coord(r.y, Gm.loy, Gm.vy) * Gm.W + voxel_coord(r.x, Gm.lox, Gm.vx);
+    if (start) {
+      const float4* h = pil_hdr + 3 * (size_t)q;
+      const float4 h0 = __ldg(h);
+      S.h1[slot] = __ldg(h + 1);
+      S.h2[slot] = __ldg(h + 2);
+      S.ic[slot] = __frcp_rn((float)__float_as_int(h0.y));   // mean backward: grad / count (scatter_points_cuda_kernel.cuh:134-137)
     }
+    // image-gradient rows of the group's segments -> shared memory, asynchronously
+    for (int s0 = 0; s0 < nseg; s0 += RPI) {
+      const int s = s0 + lane / LPR;
+      // lane of the s-th set bit of startmask
+      const int src = s < nseg ? __fns(startmask, 0, s + 1) : 0;
+      const int px = __shfl_sync(0xffffffffu, pix, src);
+      if (s < nseg)
+        cp_async16(&S.g[s][(lane % LPR) * 16],
+                   reinterpret_cast<const unsigned char*>(grad_image) + (size_t)px * Slab::ROW_BYTES + (lane % LPR) * 16);
+    }
+    // prefetch the next group's records while this one is processed
     const unsigned col = transpose_bits(mrow, lane);   // bit i = ReLU decision of point i for channel `lane`
+    {
+      const int jn = j + warps * 32;
+      r = make_float4(0.f, 0.f, 0.f, 0.f); mrow = 0u;
+      if (grp + warps < n_groups && jn < p1) { r = __ldg(rec + jn); mrow = __ldg(pt_mask + jn); }
+    }
+    cp_async_wait_all();
     __syncwarp();
     // lane = channel: masked sums of (1, x, y, z) over each pillar segment, expanded once per segment
     float u0 = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
     int s = -1;
     auto flush = [&]() {
       const float4 m = S.h1[s], c2 = S.h2[s];
-      const float g = S.g[s][lane];
+      const float graw = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(S.g[s])[lane])
+                              : reinterpret_cast<const float*>(S.g[s])[lane];
+      const float g = graw * S.ic[s];
       // offsets of the three decoration groups: raw (0), cluster mean (m.xyz), pillar centre (m.w, c2.x, c2.y)
       acc[0] = fmaf(g, u0, acc[0]);
       acc[1] = fmaf(g, ux, acc[1]); acc[2] = fmaf(g, uy, acc[2]); acc[3] = fmaf(g, uz, acc[3]);
@@ -625,19 +650,23 @@ extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
   k_bn_finalize<<<1, 1024, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum, a->stats, a->weight, a->gamma, a->beta,
                                     a->running_mean, a->running_var, a->bn_params);
   if (a->image_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)a->image_ready_event, 0);
-  const int dyn = F * 2 * PFN_C * (int)sizeof(float);
+  const int tile_bytes = 8 * 32 * 33 * (int)sizeof(float);
+  const int dyn = F * 2 * PFN_C * (int)sizeof(float) + tile_bytes;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_pfn_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
-    cudaFuncSetAttribute(k_pfn_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
+    cudaFuncSetAttribute(k_pfn_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float) + tile_bytes);
+    cudaFuncSetAttribute(k_pfn_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float) + tile_bytes);
     configured = true;
   }
+  // resident CTAs per SM: 4 by registers, fewer when many frames make the scale/shift table large
+  int per_sm = (220 * 1024) / (dyn + 2048);
+  per_sm = per_sm > 4 ? 4 : per_sm < 1 ? 1 : per_sm;
   if (a->image_bf16) {
-    k_pfn_points<true><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->weight, a->bn_params, a->pt_mask, a->partials,
+    k_pfn_points<true><<<sms * per_sm, 256, dyn, st>>>(a->counts, F, rec, hdr, a->weight, a->bn_params, a->pt_mask, a->partials,
                                                   a->pil_feats, a->image);
     k_pfn_straddlers<true><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
   } else {
-    k_pfn_points<false><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->weight, a->bn_params, a->pt_mask, a->partials,
+    k_pfn_points<false><<<sms * per_sm, 256, dyn, st>>>(a->counts, F, rec, hdr, a->weight, a->bn_params, a->pt_mask, a->partials,
                                                    a->pil_feats, a->image);
     k_pfn_straddlers<false><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
   }
@@ -654,13 +683,18 @@ extern "C" int dfb_pfn_backward(const dfb_pfn_bwd_args* b, void* stream_) {
   const int sms = sm_count();
   const float4* rec = (const float4*)a->csr_rec;
   cudaMemsetAsync(b->bwd_stats, 0, sizeof(double) * (size_t)F * PFN_C * (PFN_K + 1), st);
-  int bx = (sms * 4) / F;   // 46 KB of shared memory / 64 registers -> 4 resident blocks per SM: one wave, no tail
+  if (((uintptr_t)b->grad_image & 15)) { set_error("dfb_pfn_backward: grad_image must be 16-byte aligned"); return DFB_ERR_ARG; }
+  BwdGeom Gm;
+  Gm.lox = a->range_min[0]; Gm.loy = a->range_min[1]; Gm.vx = a->voxel_size[0]; Gm.vy = a->voxel_size[1];
+  Gm.W = a->W; Gm.HW = a->H * a->W;
+  // 30 KB of shared memory / 48 registers (bf16) -> 5 resident blocks per SM, 46 KB / 64 registers (fp32) -> 4: one wave
+  int bx = (sms * (a->image_bf16 ? 5 : 4)) / F;
   if (bx < 1) bx = 1;
   dim3 g(bx, F);
   if (a->image_bf16)
-    k_pfn_bwd<true><<<g, 256, 0, st>>>(a->counts, F, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
+    k_pfn_bwd<true><<<g, 256, 0, st>>>(a->counts, F, Gm, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
   else
-    k_pfn_bwd<false><<<g, 256, 0, st>>>(a->counts, F, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
+    k_pfn_bwd<false><<<g, 256, 0, st>>>(a->counts, F, Gm, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
   k_pfn_bwd_finalize<<<1, 512, 0, st>>>(a->counts, F, a->training, b->bwd_stats, a->stats, a->bn_params, a->weight,
                                          b->grad_weight, b->grad_gamma, b->grad_beta);
   add_launches(2);

@@ -20,33 +20,46 @@ constexpr int IDX_BLOCK = 256;
 constexpr int IDX_ITEMS = 4;
 constexpr int IDX_CHUNK = IDX_BLOCK * IDX_ITEMS;  // points per block
 
-// ---------------------------------------------------------------- K1: keys + occupancy bitmap
+// ---------------------------------------------------------------- K1: occupancy bitmap + valid counts
+// All twelve loads of a thread's four points are issued before the first use (the kernel is latency-bound: what
+// matters is bytes in flight).  No per-point key array: K3 recomputes the voxel of a point from its coordinates.
+__device__ __forceinline__ int point_key(float x, float y, float z, const VoxelParams& P) {
+  // NaN rows are dropped before voxelisation (encoder.py:576-577)
+  if (isnan(x) || isnan(y) || isnan(z)) return -1;
+  int cx, cy, cz;
+  if (voxel_coords(x, y, z, P, cx, cy, cz) != 0) return -1;
+  return (cz * P.gy + cy) * P.gx + cx;
+}
+
 __global__ void __launch_bounds__(IDX_BLOCK) k_mark_points(const float* __restrict__ pts, int Nmax, int stride,
                                                           VoxelParams P, int Wd, int nblk,
-                                                          int* __restrict__ keys, unsigned* __restrict__ bitmap,
-                                                          int* __restrict__ blk_cnt) {
+                                                          unsigned* __restrict__ bitmap, int* __restrict__ blk_cnt) {
+  __shared__ int s_total;
   const int f = blockIdx.y, blk = blockIdx.x;
   const float* p = pts + (size_t)f * Nmax * stride;
-  int total = 0;
+  if (threadIdx.x == 0) s_total = 0;
+  float x[IDX_ITEMS], y[IDX_ITEMS], z[IDX_ITEMS];
+  const float qnan = __int_as_float(0x7fc00000);
 #pragma unroll
   for (int j = 0; j < IDX_ITEMS; ++j) {
     const int i = blk * IDX_CHUNK + j * IDX_BLOCK + threadIdx.x;
-    int key = -1;
-    if (i < Nmax) {
-      const float x = p[(size_t)i * stride], y = p[(size_t)i * stride + 1], z = p[(size_t)i * stride + 2];
-      // NaN rows are dropped before voxelisation (encoder.py:576-577)
-      if (!(isnan(x) || isnan(y) || isnan(z))) {
-        int cx, cy, cz;
-        if (voxel_coords(x, y, z, P, cx, cy, cz) == 0) {
-          key = (cz * P.gy + cy) * P.gx + cx;
-          atomicOr(&bitmap[(size_t)f * Wd + (key >> 5)], 1u << (key & 31));
-        }
-      }
-      keys[(size_t)f * Nmax + i] = key;
-    }
-    total += __syncthreads_count(key >= 0);
+    x[j] = y[j] = z[j] = qnan;
+    if (i < Nmax) { x[j] = p[(size_t)i * stride]; y[j] = p[(size_t)i * stride + 1]; z[j] = p[(size_t)i * stride + 2]; }
   }
-  if (threadIdx.x == 0) blk_cnt[f * nblk + blk] = total;
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < IDX_ITEMS; ++j) {
+    const int key = point_key(x[j], y[j], z[j], P);
+    if (key >= 0) {
+      atomicOr(&bitmap[(size_t)f * Wd + (key >> 5)], 1u << (key & 31));
+      ++cnt;
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_total, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) blk_cnt[f * nblk + blk] = s_total;
 }
 
 // ---------------------------------------------------------------- K2: bitmap popcount scan (two levels, one launch)
@@ -121,56 +134,92 @@ __global__ void __launch_bounds__(1024) k_bitmap_scan(const unsigned* __restrict
 }
 
 // ---------------------------------------------------------------- K3: stable compaction + rank + slot
+// A thread owns FOUR CONSECUTIVE points of the block's 1024-point chunk, so one block scan of the per-thread valid
+// counts gives the stable (original-order) destination of every point.  The chunk is staged through shared memory
+// with fully coalesced scalar loads (12 in flight per thread) when the rows are packed xyz; the rank gathers, the
+// counting-sort atomics and the stores of a thread's four points are independent of each other.
 __global__ void __launch_bounds__(IDX_BLOCK) k_compact(
-    const float* __restrict__ pts, const int* __restrict__ keys, int Nmax, int stride, VoxelParams P, int Wd,
+    const float* __restrict__ pts, int Nmax, int stride, VoxelParams P, int Wd,
     int nblk, int F, int HW, const unsigned* __restrict__ bitmap, const int* __restrict__ word_rank,
     const int* __restrict__ seg_base, int S, const int* __restrict__ blk_off, const int* __restrict__ counts, float* __restrict__ pt_xyz,
     int* __restrict__ pt_coor, long long* __restrict__ pt_idx, float* __restrict__ pt_offs,
     int* __restrict__ pt_pillar, int* __restrict__ pt_slot, int* __restrict__ pil_cnt, int* __restrict__ pil_coor,
     int* __restrict__ pil_pix) {
   __shared__ int sm[33];
+  __shared__ __align__(16) float stage[IDX_CHUNK * 3];
   const int f = blockIdx.y, blk = blockIdx.x;
   const float* p = pts + (size_t)f * Nmax * stride;
+  const int i0 = blk * IDX_CHUNK + IDX_ITEMS * threadIdx.x;   // first of this thread's four points
+  float x[IDX_ITEMS], y[IDX_ITEMS], z[IDX_ITEMS];
+  const float qnan = __int_as_float(0x7fc00000);
+  if (stride == 3) {
+    const float* src = p + (size_t)blk * IDX_CHUNK * 3;
+    const int nfl = min(IDX_CHUNK, Nmax - blk * IDX_CHUNK) * 3;
+#pragma unroll
+    for (int k = 0; k < 3 * IDX_ITEMS; ++k) {
+      const int e = k * IDX_BLOCK + threadIdx.x;
+      stage[e] = e < nfl ? src[e] : qnan;
+    }
+    __syncthreads();
+    const float4* q4 = reinterpret_cast<const float4*>(stage) + 3 * threadIdx.x;
+    const float4 a = q4[0], b = q4[1], c = q4[2];
+    x[0] = a.x; y[0] = a.y; z[0] = a.z; x[1] = a.w; y[1] = b.x; z[1] = b.y;
+    x[2] = b.z; y[2] = b.w; z[2] = c.x; x[3] = c.y; y[3] = c.z; z[3] = c.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < IDX_ITEMS; ++k) {
+      const int i = i0 + k;
+      x[k] = y[k] = z[k] = qnan;
+      if (i < Nmax) { x[k] = p[(size_t)i * stride]; y[k] = p[(size_t)i * stride + 1]; z[k] = p[(size_t)i * stride + 2]; }
+    }
+  }
+  int key[IDX_ITEMS], cnt = 0;
+#pragma unroll
+  for (int k = 0; k < IDX_ITEMS; ++k) { key[k] = point_key(x[k], y[k], z[k], P); cnt += key[k] >= 0; }
+  int tot;
+  const int ex = block_excl_scan<IDX_BLOCK>(cnt, sm, tot);
+  if (cnt == 0) return;
   const int pt_base = counts[2 * F + f] + blk_off[f * nblk + blk];
   const int pil_base = counts[3 * F + 1 + f];
-  int carry = 0;
   const float hx = P.vx / 2, hy = P.vy / 2, hz = P.vz / 2;  // voxel_size / 2 (encoder.py:519)
-#pragma unroll 1
-  for (int j = 0; j < IDX_ITEMS; ++j) {
-    const int i = blk * IDX_CHUNK + j * IDX_BLOCK + threadIdx.x;
-    const int key = i < Nmax ? keys[(size_t)f * Nmax + i] : -1;
-    int tot;
-    const int ex = block_excl_scan<IDX_BLOCK>(key >= 0 ? 1 : 0, sm, tot);
-    if (key >= 0) {
-      const int dst = pt_base + carry + ex;
-      const float x = p[(size_t)i * stride], y = p[(size_t)i * stride + 1], z = p[(size_t)i * stride + 2];
-      const int cx = key % P.gx, t = key / P.gx, cy = t % P.gy, cz = t / P.gy;
-      pt_xyz[3 * (size_t)dst] = x;
-      pt_xyz[3 * (size_t)dst + 1] = y;
-      pt_xyz[3 * (size_t)dst + 2] = z;
-      pt_coor[3 * (size_t)dst] = cz;
-      pt_coor[3 * (size_t)dst + 1] = cy;
-      pt_coor[3 * (size_t)dst + 2] = cx;
-      pt_idx[dst] = i;
-      // point_offsets = p - ((c * vs + min) + vs / 2), every step rounded to fp32 (encoder.py:516-523)
-      pt_offs[3 * (size_t)dst] = __fsub_rn(x, __fadd_rn(__fadd_rn(__fmul_rn((float)cx, P.vx), P.lox), hx));
-      pt_offs[3 * (size_t)dst + 1] = __fsub_rn(y, __fadd_rn(__fadd_rn(__fmul_rn((float)cy, P.vy), P.loy), hy));
-      pt_offs[3 * (size_t)dst + 2] = __fsub_rn(z, __fadd_rn(__fadd_rn(__fmul_rn((float)cz, P.vz), P.loz), hz));
-      const unsigned word = bitmap[(size_t)f * Wd + (key >> 5)];
-      const int rank = seg_base[f * S + (key >> 15)] + word_rank[(size_t)f * Wd + (key >> 5)] +
-                       __popc(word & ((1u << (key & 31)) - 1u));
-      const int q = pil_base + rank;
-      pt_pillar[dst] = q;
-      const int slot = atomicAdd(&pil_cnt[q], 1);
-      pt_slot[dst] = slot;
-      if (slot == 0) {  // exactly one point per pillar sees slot 0
-        pil_coor[3 * (size_t)q] = cz;
-        pil_coor[3 * (size_t)q + 1] = cy;
-        pil_coor[3 * (size_t)q + 2] = cx;
-        pil_pix[q] = f * HW + cy * P.gx + cx;  // PointPillarsScatter: y * nx + x (encoder.py:141)
-      }
+  // rank of the point's cell among the occupied cells of the frame = the reference's voxel id
+  int q[IDX_ITEMS], slot[IDX_ITEMS];
+#pragma unroll
+  for (int k = 0; k < IDX_ITEMS; ++k) {
+    q[k] = -1;
+    if (key[k] >= 0) {
+      const unsigned word = bitmap[(size_t)f * Wd + (key[k] >> 5)];
+      q[k] = pil_base + seg_base[f * S + (key[k] >> 15)] + word_rank[(size_t)f * Wd + (key[k] >> 5)] +
+             __popc(word & ((1u << (key[k] & 31)) - 1u));
     }
-    carry += tot;
+  }
+#pragma unroll
+  for (int k = 0; k < IDX_ITEMS; ++k) slot[k] = q[k] >= 0 ? atomicAdd(&pil_cnt[q[k]], 1) : 0;
+  int dst = pt_base + ex;
+#pragma unroll
+  for (int k = 0; k < IDX_ITEMS; ++k) {
+    if (key[k] < 0) continue;
+    const int cx = key[k] % P.gx, t = key[k] / P.gx, cy = t % P.gy, cz = t / P.gy;
+    pt_xyz[3 * (size_t)dst] = x[k];
+    pt_xyz[3 * (size_t)dst + 1] = y[k];
+    pt_xyz[3 * (size_t)dst + 2] = z[k];
+    pt_coor[3 * (size_t)dst] = cz;
+    pt_coor[3 * (size_t)dst + 1] = cy;
+    pt_coor[3 * (size_t)dst + 2] = cx;
+    pt_idx[dst] = i0 + k;
+    // point_offsets = p - ((c * vs + min) + vs / 2), every step rounded to fp32 (encoder.py:516-523)
+    pt_offs[3 * (size_t)dst] = __fsub_rn(x[k], __fadd_rn(__fadd_rn(__fmul_rn((float)cx, P.vx), P.lox), hx));
+    pt_offs[3 * (size_t)dst + 1] = __fsub_rn(y[k], __fadd_rn(__fadd_rn(__fmul_rn((float)cy, P.vy), P.loy), hy));
+    pt_offs[3 * (size_t)dst + 2] = __fsub_rn(z[k], __fadd_rn(__fadd_rn(__fmul_rn((float)cz, P.vz), P.loz), hz));
+    pt_pillar[dst] = q[k];
+    pt_slot[dst] = slot[k];
+    if (slot[k] == 0) {  // exactly one point per pillar sees slot 0
+      pil_coor[3 * (size_t)q[k]] = cz;
+      pil_coor[3 * (size_t)q[k] + 1] = cy;
+      pil_coor[3 * (size_t)q[k] + 2] = cx;
+      pil_pix[q[k]] = f * HW + cy * P.gx + cx;  // PointPillarsScatter: y * nx + x (encoder.py:141)
+    }
+    ++dst;
   }
 }
 
@@ -228,11 +277,29 @@ __global__ void __launch_bounds__(256) k_fill_csr(const int* __restrict__ counts
   const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int q = t0; q < M; q += stride) pil_start[q] = pil_loc[q] + blk_base[q / PSCAN_ITEMS];
   if (t0 == 0) pil_start[M] = n;
-  for (int p = t0; p < n; p += stride) {
-    const int q = pt_pillar[p];
-    const int j = pil_loc[q] + blk_base[q / PSCAN_ITEMS] + pt_slot[p];
-    sorted_pt[j] = p;
-    csr_rec[j] = make_float4(pt_xyz[3 * (size_t)p], pt_xyz[3 * (size_t)p + 1], pt_xyz[3 * (size_t)p + 2], __int_as_float(q));
+  // four points per thread and iteration, every load of the four issued before the first dependent gather
+  constexpr int U = 4;
+  for (int p0 = t0; p0 < n; p0 += U * stride) {
+    int q[U], sl[U];
+    float x[U], y[U], z[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * stride;
+      q[u] = -1;
+      if (p < n) {
+        q[u] = pt_pillar[p]; sl[u] = pt_slot[p];
+        x[u] = pt_xyz[3 * (size_t)p]; y[u] = pt_xyz[3 * (size_t)p + 1]; z[u] = pt_xyz[3 * (size_t)p + 2];
+      }
+    }
+    int j[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) j[u] = q[u] >= 0 ? pil_loc[q[u]] + blk_base[q[u] / PSCAN_ITEMS] + sl[u] : -1;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j[u] < 0) continue;
+      sorted_pt[j[u]] = p0 + u * stride;
+      csr_rec[j[u]] = make_float4(x[u], y[u], z[u], __int_as_float(q[u]));
+    }
   }
 }
 
@@ -306,7 +373,7 @@ extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
   }
   if (a->Nmax > 0) {
     dim3 g((unsigned)nblk_, F);
-    k_mark_points<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, a->keys, a->bitmap, a->blk_cnt);
+    k_mark_points<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, a->bitmap, a->blk_cnt);
   }
   {
     dim3 g(S, F);
@@ -315,7 +382,7 @@ extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
   }
   if (a->Nmax > 0) {
     dim3 g((unsigned)nblk_, F);
-    k_compact<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->keys, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
+    k_compact<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
                                        a->word_rank, seg_base, S, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
                                        a->pt_offs, a->pt_pillar, a->pt_slot, a->pil_cnt, a->pil_coor, a->pil_pix);
   }

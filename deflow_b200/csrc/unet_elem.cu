@@ -6,6 +6,7 @@
 // momentum 0.1) -> GELU), BilinearDecoder (OpenSceneFlow/src/models/basic/unet.py:8-18:
 // F.interpolate(scale_factor=2, mode="bilinear", align_corners=False)).
 #include "common.cuh"
+#include "stream_pipe.cuh"
 #include "../../include/deflow_b200.h"
 
 namespace dfb {
@@ -325,6 +326,350 @@ __global__ void __launch_bounds__(256) k_upsample2x_bwd(const void* __restrict__
   }
 }
 
+// ================================================================ bf16 streaming variants (perf mode)
+// The same three BatchNorm/GELU passes and the per-channel sum for bf16 tensors, restructured for B200:
+//   * inputs arrive through the bulk-async ring of stream_pipe.cuh (bytes in flight independent of the ALU phase);
+//   * the arithmetic is packed fp32x2 (FFMA2 / FMUL2 / FADD2: two channels per instruction), the per-channel
+//     parameters of the thread's fixed channel octet live in registers, bf16 <-> fp32 is a shift / one cvt per pair.
+// ~13 issue slots + 2 MUFU per element instead of ~30 + 2: the passes become HBM-bound instead of issue-bound.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 bf2_to_f2(unsigned w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ unsigned f2_to_bf2(float2 v) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<const unsigned*>(&p);
+}
+
+// cdf = Phi(z), pdf = phi(z) for two channels (same Abramowitz & Stegun 7.1.26 form as gelu_parts; signs of the
+// polynomial folded into its coefficients, exp through ex2 with the 1/2 and log2(e) folded into one constant)
+__device__ __forceinline__ void gelu_parts2(float2 z, float2& cdf, float2& pdf) {
+  const float2 e2 = __fmul2_rn(__fmul2_rn(z, z), f2(-0.72134752044448170368f));   // -z^2/2 * log2(e)
+  const float2 e = make_float2(ex2_approx(e2.x), ex2_approx(e2.y));                // exp(-z^2/2)
+  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+  const float2 den = __ffma2_rn(az, f2(0.3275911f * 0.70710678118654752f), f2(1.0f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 q = __ffma2_rn(t, f2(-1.061405429f), f2(1.453152027f));
+  q = __ffma2_rn(t, q, f2(-1.421413741f));
+  q = __ffma2_rn(t, q, f2(0.284496736f));
+  q = __ffma2_rn(t, q, f2(-0.254829592f));
+  q = __fmul2_rn(q, t);                                                            // -P(t)
+  const float2 ea = __ffma2_rn(q, e, f2(1.0f));                                    // erf(|z|/sqrt2)
+  const float2 es = make_float2(copysignf(ea.x, z.x), copysignf(ea.y, z.y));
+  cdf = __ffma2_rn(es, f2(0.5f), f2(0.5f));
+  pdf = __fmul2_rn(e, f2(0.3989422804014327f));
+}
+
+// per-thread parameter octet: 4 float2 per array
+__device__ __forceinline__ void ld_oct(const float* p, float2 (&d)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[i] = make_float2(p[2 * i], p[2 * i + 1]);
+}
+
+constexpr int SP_STAGES = 4;
+
+// y = GELU(a*x + b)
+__global__ void __launch_bounds__(sp::THREADS, 4) k_bn_gelu_apply_s(const void* __restrict__ x, const float* __restrict__ bn,
+                                                                   int C, long long n_vec, uint4* __restrict__ y) {
+  extern __shared__ __align__(128) uint8_t sp_smem[];
+  sp::Ring<1, SP_STAGES> ring(sp_smem);
+  ring.init();
+  if (threadIdx.x >= sp::CONSUMERS) {
+    if (threadIdx.x == sp::CONSUMERS) { const void* const in[1] = {x}; ring.produce(in, n_vec); }
+    return;
+  }
+  const int c0 = (threadIdx.x % (C >> 3)) << 3;
+  float2 a[4], b[4];
+  ld_oct(bn + c0, a); ld_oct(bn + C + c0, b);
+  const long long n_chunks = (n_vec + sp::CHUNK_VEC - 1) / sp::CHUNK_VEC;
+  int it = 0;
+  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++it) {
+    ring.wait_full(it);
+    const uint4* sx = ring.slot(it % SP_STAGES, 0);
+    const uint4 u0 = sx[threadIdx.x], u1 = sx[threadIdx.x + 256];
+    ring.release(it);
+    const long long e = ch * sp::CHUNK_VEC + threadIdx.x;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const uint4 u = v ? u1 : u0;
+      const unsigned w[4] = {u.x, u.y, u.z, u.w};
+      unsigned o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 z = __ffma2_rn(bf2_to_f2(w[i]), a[i], b[i]);
+        float2 cdf, pdf;
+        gelu_parts2(z, cdf, pdf);
+        o[i] = f2_to_bf2(__fmul2_rn(z, cdf));
+      }
+      if (e + 256 * v < n_vec) y[e + 256 * v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// Backward pass 1: red[0][c] = sum g1, red[1][c] = sum g1 * xhat, with g1 = gy * GELU'(a*x + b)
+__global__ void __launch_bounds__(sp::THREADS, 2) k_bn_gelu_bwd_reduce_s(const void* __restrict__ x, const void* __restrict__ gy,
+                                                                        const float* __restrict__ bn, int C, long long n_vec,
+                                                                        double* __restrict__ red) {
+  extern __shared__ __align__(128) uint8_t sp_smem[];
+  __shared__ float acc1[256], acc2[256];
+  sp::Ring<2, SP_STAGES> ring(sp_smem);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { acc1[i] = 0.f; acc2[i] = 0.f; }
+  ring.init();
+  if (threadIdx.x >= sp::CONSUMERS) {
+    if (threadIdx.x == sp::CONSUMERS) { const void* const in[2] = {x, gy}; ring.produce(in, n_vec); }
+  } else {
+    const int c0 = (threadIdx.x % (C >> 3)) << 3;
+    float2 a[4], b[4], rs[4], nmr[4], s1[4], s2[4];
+    ld_oct(bn + c0, a); ld_oct(bn + C + c0, b); ld_oct(bn + 3 * C + c0, rs);
+    {
+      float2 mu[4];
+      ld_oct(bn + 2 * C + c0, mu);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { nmr[i] = make_float2(-mu[i].x * rs[i].x, -mu[i].y * rs[i].y); s1[i] = f2(0.f); s2[i] = f2(0.f); }
+    }
+    const long long n_chunks = (n_vec + sp::CHUNK_VEC - 1) / sp::CHUNK_VEC;
+    int it = 0;
+    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++it) {
+      ring.wait_full(it);
+      const uint4* sx = ring.slot(it % SP_STAGES, 0);
+      const uint4* sg = ring.slot(it % SP_STAGES, 1);
+      const bool two = ch * sp::CHUNK_VEC + threadIdx.x + 256 < n_vec, one = ch * sp::CHUNK_VEC + threadIdx.x < n_vec;
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      // a partial last chunk leaves stale bytes behind the copied range: read those vectors as zeros
+      const uint4 x0 = one ? sx[threadIdx.x] : z4, x1 = two ? sx[threadIdx.x + 256] : z4;
+      const uint4 g0 = one ? sg[threadIdx.x] : z4, g1v = two ? sg[threadIdx.x + 256] : z4;
+      ring.release(it);
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const uint4 ux = v ? x1 : x0, ug = v ? g1v : g0;
+        const unsigned wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 xf = bf2_to_f2(wx[i]);
+          const float2 z = __ffma2_rn(xf, a[i], b[i]);
+          float2 cdf, pdf;
+          gelu_parts2(z, cdf, pdf);
+          const float2 g1 = __fmul2_rn(bf2_to_f2(wg[i]), __ffma2_rn(z, pdf, cdf));
+          s1[i] = __fadd2_rn(s1[i], g1);
+          s2[i] = __ffma2_rn(g1, __ffma2_rn(xf, rs[i], nmr[i]), s2[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(&acc1[c0 + 2 * i], s1[i].x); atomicAdd(&acc1[c0 + 2 * i + 1], s1[i].y);
+      atomicAdd(&acc2[c0 + 2 * i], s2[i].x); atomicAdd(&acc2[c0 + 2 * i + 1], s2[i].y);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&red[i], (double)acc1[i]);
+    atomicAdd(&red[C + i], (double)acc2[i]);
+  }
+}
+
+// Backward pass 2: gx = a * (g1 - m1 - xhat*m2) (training) or a * g1 (eval), as a*g1 + (c1*x + c0) with
+// c1 = -a*m2*rstd, c0 = -a*(m1 - m2*mean*rstd)
+__global__ void __launch_bounds__(sp::THREADS, 2) k_bn_gelu_bwd_apply_s(const void* __restrict__ x, const void* __restrict__ gy,
+                                                                       const float* __restrict__ bn, const double* __restrict__ red,
+                                                                       double count, int training, int C, long long n_vec,
+                                                                       uint4* __restrict__ gx) {
+  extern __shared__ __align__(128) uint8_t sp_smem[];
+  sp::Ring<2, SP_STAGES> ring(sp_smem);
+  ring.init();
+  if (threadIdx.x >= sp::CONSUMERS) {
+    if (threadIdx.x == sp::CONSUMERS) { const void* const in[2] = {x, gy}; ring.produce(in, n_vec); }
+    return;
+  }
+  const int c0 = (threadIdx.x % (C >> 3)) << 3;
+  float2 a[4], b[4], k0[4], k1[4];
+  ld_oct(bn + c0, a); ld_oct(bn + C + c0, b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v0[2], v1[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + 2 * i + h;
+      const float m1 = training ? (float)(red[c] / count) : 0.f, m2 = training ? (float)(red[C + c] / count) : 0.f;
+      const float ac = bn[c], mu = bn[2 * C + c], r = bn[3 * C + c];
+      v1[h] = -ac * m2 * r;
+      v0[h] = -ac * (m1 - m2 * mu * r);
+    }
+    k0[i] = make_float2(v0[0], v0[1]); k1[i] = make_float2(v1[0], v1[1]);
+  }
+  const long long n_chunks = (n_vec + sp::CHUNK_VEC - 1) / sp::CHUNK_VEC;
+  int it = 0;
+  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++it) {
+    ring.wait_full(it);
+    const uint4* sx = ring.slot(it % SP_STAGES, 0);
+    const uint4* sg = ring.slot(it % SP_STAGES, 1);
+    const uint4 x0 = sx[threadIdx.x], x1 = sx[threadIdx.x + 256];
+    const uint4 g0 = sg[threadIdx.x], g1v = sg[threadIdx.x + 256];
+    ring.release(it);
+    const long long e = ch * sp::CHUNK_VEC + threadIdx.x;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const uint4 ux = v ? x1 : x0, ug = v ? g1v : g0;
+      const unsigned wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+      unsigned o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 xf = bf2_to_f2(wx[i]);
+        const float2 z = __ffma2_rn(xf, a[i], b[i]);
+        float2 cdf, pdf;
+        gelu_parts2(z, cdf, pdf);
+        const float2 g1 = __fmul2_rn(bf2_to_f2(wg[i]), __ffma2_rn(z, pdf, cdf));
+        o[i] = f2_to_bf2(__ffma2_rn(a[i], g1, __ffma2_rn(k1[i], xf, k0[i])));
+      }
+      if (e + 256 * v < n_vec) gx[e + 256 * v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// out[c] += sum over pixels (bias gradients of the un-normalised decoder convolutions and of the GRU gates)
+__global__ void __launch_bounds__(sp::THREADS, 4) k_channel_sum_s(const void* __restrict__ g, int C, long long n_vec,
+                                                                 float* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t sp_smem[];
+  __shared__ float acc[256];
+  sp::Ring<1, SP_STAGES> ring(sp_smem);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) acc[i] = 0.f;
+  ring.init();
+  if (threadIdx.x >= sp::CONSUMERS) {
+    if (threadIdx.x == sp::CONSUMERS) { const void* const in[1] = {g}; ring.produce(in, n_vec); }
+  } else {
+    const int c0 = (threadIdx.x % (C >> 3)) << 3;
+    float2 s[4] = {f2(0.f), f2(0.f), f2(0.f), f2(0.f)};
+    const long long n_chunks = (n_vec + sp::CHUNK_VEC - 1) / sp::CHUNK_VEC;
+    int it = 0;
+    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++it) {
+      ring.wait_full(it);
+      const uint4* sg = ring.slot(it % SP_STAGES, 0);
+      const long long e = ch * sp::CHUNK_VEC + threadIdx.x;
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 u0 = e < n_vec ? sg[threadIdx.x] : z4, u1 = e + 256 < n_vec ? sg[threadIdx.x + 256] : z4;
+      ring.release(it);
+      s[0] = __fadd2_rn(s[0], __fadd2_rn(bf2_to_f2(u0.x), bf2_to_f2(u1.x)));
+      s[1] = __fadd2_rn(s[1], __fadd2_rn(bf2_to_f2(u0.y), bf2_to_f2(u1.y)));
+      s[2] = __fadd2_rn(s[2], __fadd2_rn(bf2_to_f2(u0.z), bf2_to_f2(u1.z)));
+      s[3] = __fadd2_rn(s[3], __fadd2_rn(bf2_to_f2(u0.w), bf2_to_f2(u1.w)));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { atomicAdd(&acc[c0 + 2 * i], s[i].x); atomicAdd(&acc[c0 + 2 * i + 1], s[i].y); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], acc[i]);
+}
+
+// ---------------------------------------------------------------- bilinear x2, bf16 streaming variants
+// Forward: a thread owns one INPUT pixel octet and writes the 2x2 output quad it centres: 9 loads (mostly L1 hits,
+// the 3x3 neighbourhoods of adjacent threads overlap) for 4 stores, 32-bit index arithmetic, packed fp32x2 lerps.
+// Same rounding order as the generic kernel: x-lerp (0.75 centre + 0.25 neighbour) then y-lerp.
+__device__ __forceinline__ void unpack4(const uint4& u, float2 (&f)[4]) {
+  f[0] = bf2_to_f2(u.x); f[1] = bf2_to_f2(u.y); f[2] = bf2_to_f2(u.z); f[3] = bf2_to_f2(u.w);
+}
+__device__ __forceinline__ uint4 pack4(const float2 (&f)[4]) {
+  return make_uint4(f2_to_bf2(f[0]), f2_to_bf2(f[1]), f2_to_bf2(f[2]), f2_to_bf2(f[3]));
+}
+__device__ __forceinline__ void lerp4(const float2 (&c)[4], const float2 (&nb)[4], float2 (&o)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = __ffma2_rn(c[i], f2(0.75f), __fmul2_rn(nb[i], f2(0.25f)));
+}
+
+__global__ void __launch_bounds__(256) k_upsample2x_q(const uint4* __restrict__ in, int n, int h, int w, int vshift,
+                                                      uint4* __restrict__ out) {
+  const int vpp = 1 << vshift;
+  const unsigned total = (unsigned)n * h * w * vpp;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int v = e & (vpp - 1);
+    unsigned p = e >> vshift;
+    const int ix = p % w; p /= w;
+    const int iy = p % h;
+    const int b = p / h;
+    const int xm = max(ix - 1, 0), xp = min(ix + 1, w - 1);
+    const int ym = max(iy - 1, 0), yp = min(iy + 1, h - 1);
+    const uint4* base = in + (((size_t)b * h * w) << vshift) + v;
+    float2 L[3][4], R[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int y = r == 0 ? ym : r == 1 ? iy : yp;
+      const uint4* row = base + (((size_t)y * w) << vshift);
+      float2 c[4], l[4], rr[4];
+      unpack4(__ldg(row + ((size_t)ix << vshift)), c);
+      unpack4(__ldg(row + ((size_t)xm << vshift)), l);
+      unpack4(__ldg(row + ((size_t)xp << vshift)), rr);
+      lerp4(c, l, L[r]);
+      lerp4(c, rr, R[r]);
+    }
+    float2 o[4];
+    uint4* ob = out + ((((size_t)b * 2 * h + 2 * iy) * 2 * w + 2 * ix) << vshift) + v;
+    const size_t orow = ((size_t)2 * w) << vshift;
+    lerp4(L[1], L[0], o); ob[0] = pack4(o);
+    lerp4(R[1], R[0], o); ob[vpp] = pack4(o);
+    lerp4(L[1], L[2], o); ob[orow] = pack4(o);
+    lerp4(R[1], R[2], o); ob[orow + vpp] = pack4(o);
+  }
+}
+
+// Backward: gin[iy][ix] = sum over the 4x4 output window 2i-1 .. 2i+2 of wy*wx*gout (weights 0.25/0.75/0.75/0.25 inside,
+// folded at the edges by up_w); rows combined horizontally first.
+__global__ void __launch_bounds__(256) k_upsample2x_bwd_q(const uint4* __restrict__ gout, int n, int h, int w, int vshift,
+                                                          uint4* __restrict__ gin) {
+  const int vpp = 1 << vshift;
+  const unsigned total = (unsigned)n * h * w * vpp;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int v = e & (vpp - 1);
+    unsigned p = e >> vshift;
+    const int ix = p % w; p /= w;
+    const int iy = p % h;
+    const int b = p / h;
+    float wx[4], wy[4];
+    int ox[4], oy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = 2 * ix - 1 + j, y = 2 * iy - 1 + j;
+      ox[j] = min(max(x, 0), 2 * w - 1); oy[j] = min(max(y, 0), 2 * h - 1);
+      wx[j] = (x < 0 || x >= 2 * w) ? 0.f : up_w(ix, x, w);
+      wy[j] = (y < 0 || y >= 2 * h) ? 0.f : up_w(iy, y, h);
+    }
+    const uint4* base = gout + (((size_t)b * 4 * h * w) << vshift) + v;
+    float2 acc[4] = {f2(0.f), f2(0.f), f2(0.f), f2(0.f)};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint4* row = base + (((size_t)oy[r] * 2 * w) << vshift);
+      float2 t[4] = {f2(0.f), f2(0.f), f2(0.f), f2(0.f)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 g[4];
+        unpack4(__ldg(row + ((size_t)ox[j] << vshift)), g);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = __ffma2_rn(g[i], f2(wx[j]), t[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = __ffma2_rn(t[i], f2(wy[r]), acc[i]);
+    }
+    gin[e] = pack4(acc);
+  }
+}
+
+// one wave: CTAs per SM from the occupancy calculator (cached per kernel), never more CTAs than chunks
+template <class K>
+static int stream_grid(K kernel, int smem, long long n_vec, int* cache) {
+  if (*cache == 0) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, sp::THREADS, smem);
+    *cache = per_sm > 0 ? per_sm : 1;
+  }
+  long long g = (long long)sm_count() * *cache;
+  const long long n_chunks = (n_vec + sp::CHUNK_VEC - 1) / sp::CHUNK_VEC;
+  if (g > n_chunks) g = n_chunks;
+  return (int)(g < 1 ? 1 : g);
+}
+
+static bool stream_ok(int C, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr) {
+  return C % 8 == 0 && C <= 256 && 256 % (C >> 3) == 0 && !(((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15);
+}
+
 static int grid_for_elems(long long work, int block, int mult = 16) {
   long long b = (work + block - 1) / block;
   const long long cap = (long long)sm_count() * mult;
@@ -350,6 +695,14 @@ extern "C" int dfb_bn2d_finalize(const double* stats, double count, int C, int t
 extern "C" int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, int f32, void* stream_) {
   if (C % 8 || C > 256) { set_error("dfb_bn_gelu_apply: C must be a multiple of 8 and <= 256"); return DFB_ERR_ARG; }
   const long long n_vec = n_pix * (C >> 3);
+  if (!f32 && stream_ok(C, x, y)) {
+    static int occ = 0;
+    constexpr int smem = sp::Ring<1, SP_STAGES>::BYTES;
+    const int g = stream_grid(k_bn_gelu_apply_s, smem, n_vec, &occ);
+    k_bn_gelu_apply_s<<<g, sp::THREADS, smem, (cudaStream_t)stream_>>>(x, bn, C, n_vec, (uint4*)y);
+    add_launches(1);
+    return check_launch("dfb_bn_gelu_apply");
+  }
   const int g = grid_for_elems(n_vec, 1024, 12);
   if (f32) k_bn_gelu_apply<true><<<g, 256, 0, (cudaStream_t)stream_>>>(x, bn, C, n_vec, y);
   else k_bn_gelu_apply<false><<<g, 256, 0, (cudaStream_t)stream_>>>(x, bn, C, n_vec, y);
@@ -365,7 +718,14 @@ extern "C" int dfb_bn_gelu_backward(const void* x, const void* gy, const float* 
   cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st);
   const long long n_vec = n_pix * (C >> 3);
   const int g = grid_for_elems(n_vec, 512, 8);
-  if (f32) {
+  if (!f32 && stream_ok(C, x, gy, gx)) {
+    static int occ_r = 0, occ_a = 0;
+    constexpr int smem = sp::Ring<2, SP_STAGES>::BYTES;
+    const int gr = stream_grid(k_bn_gelu_bwd_reduce_s, smem, n_vec, &occ_r);
+    const int ga = stream_grid(k_bn_gelu_bwd_apply_s, smem, n_vec, &occ_a);
+    k_bn_gelu_bwd_reduce_s<<<gr, sp::THREADS, smem, st>>>(x, gy, bn, C, n_vec, red);
+    k_bn_gelu_bwd_apply_s<<<ga, sp::THREADS, smem, st>>>(x, gy, bn, red, (double)n_pix, training, C, n_vec, (uint4*)gx);
+  } else if (f32) {
     k_bn_gelu_bwd_reduce<true><<<g, 256, 0, st>>>(x, gy, bn, C, n_vec, red);
     k_bn_gelu_bwd_apply<true><<<g, 256, 0, st>>>(x, gy, bn, red, (double)n_pix, training, C, n_vec, gx);
   } else {
@@ -381,6 +741,15 @@ extern "C" int dfb_bn_gelu_backward(const void* x, const void* gy, const float* 
 // an fp32 tensor in parity mode)
 extern "C" int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, double* stats2, int f32, void* stream_) {
   if (C % 8 || C > 256 || 256 % (C >> 3)) { set_error("dfb_channel_sum: unsupported channel count %d", C); return DFB_ERR_ARG; }
+  if (!f32 && !stats2 && out && stream_ok(C, g)) {
+    static int occ = 0;
+    constexpr int smem = sp::Ring<1, SP_STAGES>::BYTES;
+    const long long n_vec = n_pix * (C >> 3);
+    const int gr = stream_grid(k_channel_sum_s, smem, n_vec, &occ);
+    k_channel_sum_s<<<gr, sp::THREADS, smem, (cudaStream_t)stream_>>>(g, C, n_vec, out);
+    add_launches(1);
+    return check_launch("dfb_channel_sum");
+  }
   const int prows = 256 / (C >> 3);
   const int gr = grid_for_elems(n_pix, prows, 8);
   if (f32) k_channel_sum<true><<<gr, 256, 0, (cudaStream_t)stream_>>>(g, C, n_pix, out, stats2);
@@ -393,6 +762,16 @@ extern "C" int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* 
   if (C % 8) { set_error("dfb_upsample2x: C must be a multiple of 8"); return DFB_ERR_ARG; }
   const long long vec_in = (long long)n * h * w * (C >> 3);
   cudaStream_t st = (cudaStream_t)stream_;
+  const int vpp = C >> 3;
+  if (!f32 && (vpp & (vpp - 1)) == 0 && vec_in * 4 < (1ll << 31) && !(((uintptr_t)in | (uintptr_t)out) & 15)) {
+    int vshift = 0;
+    while ((1 << vshift) < vpp) ++vshift;
+    const int g = grid_for_elems(vec_in, 256, 8);
+    if (!backward) k_upsample2x_q<<<g, 256, 0, st>>>((const uint4*)in, n, h, w, vshift, (uint4*)out);
+    else k_upsample2x_bwd_q<<<g, 256, 0, st>>>((const uint4*)in, n, h, w, vshift, (uint4*)out);
+    add_launches(1);
+    return check_launch("dfb_upsample2x");
+  }
   if (!backward) {
     const int g = grid_for_elems(vec_in * 4, 256);
     if (f32) k_upsample2x<true><<<g, 256, 0, st>>>(in, n, h, w, C, out);

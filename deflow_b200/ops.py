@@ -109,7 +109,6 @@ def pillar_index(points: torch.Tensor, voxel_size, pc_range) -> PillarIndex:
     idx.pil_start = torch.empty(pil_cap + 1, **i32)
     idx.sorted_pt = torch.empty(cap, **i32)
     idx.csr_rec = torch.empty((cap, 4), dtype=torch.float32, device=dev)
-    keys = torch.empty(cap, **i32)
     nw, nb = max(F * words.value, 1), max(F * max(blocks.value, 1), 1)
     # everything that must start at zero lives in ONE allocation (one memset): bitmap | pil_cnt | blk_cnt | tickets
     zero = torch.empty(nw + pil_cap + nb + 4, **i32)
@@ -120,7 +119,7 @@ def pillar_index(points: torch.Tensor, voxel_size, pc_range) -> PillarIndex:
     a = IndexArgs()
     a.F, a.Nmax, a.pt_stride, a.pil_cap = F, Nmax, S, pil_cap
     a.voxel_size, a.range = vs, rg
-    a.pts, a.keys, a.bitmap, a.word_rank = points.data_ptr(), keys.data_ptr(), bitmap.data_ptr(), word_rank.data_ptr()
+    a.pts, a.keys, a.bitmap, a.word_rank = points.data_ptr(), None, bitmap.data_ptr(), word_rank.data_ptr()
     a.blk_cnt, a.pt_slot, a.counts = blk.data_ptr(), slot.data_ptr(), idx.counts.data_ptr()
     a.pt_xyz, a.pt_coor, a.pt_idx, a.pt_offs = (idx.pt_xyz.data_ptr(), idx.pt_coor.data_ptr(), idx.pt_idx.data_ptr(),
                                                 idx.pt_offs.data_ptr())
@@ -162,6 +161,7 @@ def _pfn_args(idx: PillarIndex, H, W, training, center_off, eps, momentum, weigh
     a.F, a.H, a.W, a.training = idx.F, H, W, int(training)
     a.voxel_size = _f3(idx.voxel_size)
     a.center_off = _f3(center_off)
+    a.range_min = _f3(idx.pc_range[:3])
     a.eps, a.momentum = eps, momentum
     a.counts, a.pt_xyz, a.pt_coor, a.pt_pillar = (idx.counts.data_ptr(), idx.pt_xyz.data_ptr(), idx.pt_coor.data_ptr(),
                                                   idx.pt_pillar.data_ptr())

@@ -86,7 +86,7 @@ typedef struct {
   float voxel_size[3];
   float range[6];
   const float* pts;
-  int* keys;         /* [F*Nmax] */
+  int* keys;         /* unused since r01 (the compaction pass recomputes voxels); may be NULL */
   unsigned* bitmap;  /* [F*words] */
   int* word_rank;    /* [F*words] */
   int* blk_cnt;      /* [F*blocks] */
@@ -162,6 +162,7 @@ typedef struct {
                              written by the forward, read by every later pass and the backward */
   void* image_ready_event;/* optional cudaEvent_t: the caller zero-fills `image` on another stream; the first kernel that
                              writes the image waits for this event and the call does not memset the image itself */
+  float range_min[3];     /* point_cloud_range[0:3] (x, y, z minimum), fp32: the backward recomputes a point's pixel from it */
 } dfb_pfn_args;
 int dfb_pfn_forward(const dfb_pfn_args* args, void* stream);
 /* Dense zero fill (the PointPillarsScatter canvas) with blocks_per_sm small blocks per SM, meant to run on a second

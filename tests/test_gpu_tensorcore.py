@@ -144,6 +144,49 @@ def test_upsample_and_channel_sum():
     assert _rel(s, g.float().sum((0, 1, 2))) <= 1e-5
 
 
+@pytest.mark.parametrize("n,H,W,C", [(1, 23, 15, 64), (4, 160, 128, 64), (3, 37, 29, 256), (4, 320, 256, 32), (1, 2, 5, 128)])
+def test_streaming_bn_gelu_ragged_and_ring_wrap(n, H, W, C):
+    """The bulk-async streaming passes (csrc/stream_pipe.cuh): partial last chunks, more chunks per CTA than ring
+    stages, single-chunk tensors -- against torch fp32 on the same bf16 inputs."""
+    torch.manual_seed(n * 1000 + C)
+    x = (torch.randn(n, H, W, C, device=DEV) * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    beta = (0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.gelu(F.batch_norm(xr, None, None, gamma, beta, True, 0.1, 1e-5))
+    xf = x.float()
+    stats = torch.stack([xf.double().sum((0, 1, 2)), xf.double().square().sum((0, 1, 2))])
+    bn = conv.bn2d_finalize(stats, n * H * W, True, 1e-5, 0.1, gamma.detach(), beta.detach(), None, None)
+    y = conv.bn_gelu_apply(x, bn)
+    assert float((y.float() - ref.permute(0, 2, 3, 1)).abs().max()) <= 2 ** -7 * max(1.0, float(ref.abs().max()))
+    gy = torch.randn(n, H, W, C, device=DEV).to(torch.bfloat16)
+    ref.backward(gy.float().permute(0, 3, 1, 2))
+    gg, gb, gbias = (torch.zeros(C, device=DEV) for _ in range(3))
+    gx = conv.bn_gelu_backward(x, gy, bn, True, gg, gb, gbias)
+    rgx = xr.grad.permute(0, 2, 3, 1)
+    assert float((gx.float() - rgx).abs().max()) <= 2 ** -7 * max(1.0, float(rgx.abs().max()))
+    tol = 2e-4 if n * H * W > 16 else 2e-2   # tiny batches: the statistics themselves are ill-conditioned
+    assert _rel(gg, gamma.grad) <= tol and _rel(gb, beta.grad) <= tol
+    s = conv.channel_sum(gy)
+    assert _rel(s, gy.float().sum((0, 1, 2))) <= 1e-5
+
+
+@pytest.mark.parametrize("n,h,w,C", [(2, 12, 20, 64), (1, 1, 1, 32), (3, 5, 7, 256), (2, 64, 64, 128)])
+def test_upsample_quad_kernels(n, h, w, C):
+    torch.manual_seed(h * w + C)
+    x = torch.randn(n, h, w, C, device=DEV).to(torch.bfloat16)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    y = conv.upsample2x(x)
+    assert y.shape == (n, 2 * h, 2 * w, C)
+    assert float((y.float() - ref.permute(0, 2, 3, 1)).abs().max()) <= 2 ** -7 * float(ref.abs().max())
+    g = torch.randn(n, 2 * h, 2 * w, C, device=DEV).to(torch.bfloat16)
+    ref.backward(g.float().permute(0, 3, 1, 2))
+    gx = conv.upsample2x(g, backward=True)
+    rg = xr.grad.permute(0, 2, 3, 1)
+    assert float((gx.float() - rg).abs().max()) <= 2 ** -7 * float(rg.abs().max())
+
+
 def test_unet_tensor_core_path_vs_fp32_library():
     """Whole backbone, forward + backward: bf16 tensor-core path against the strict-fp32 path (same weights)."""
     torch.manual_seed(0)
