@@ -305,9 +305,7 @@ class _ConvBnGelu(torch.autograd.Function):
         x, raw, bn, wd = ctx.saved_tensors
         stride, training, wshape = ctx.cfg
         cout, cin = wshape[0], wshape[1]
-        gg = torch.zeros(cout, dtype=torch.float32, device=x.device)
-        gbeta = torch.zeros_like(gg)
-        gbias = torch.zeros_like(gg)
+        gg, gbeta, gbias = torch.zeros((3, cout), dtype=torch.float32, device=x.device).unbind(0)   # one fill
         graw = bn_gelu_backward(raw, gact.contiguous(), bn, training, gg, gbeta, gbias)
         gw = conv2d_wgrad([x], graw, 3, stride)
         gx = conv2d_dgrad(graw, wd, x.shape[1], x.shape[2], cin, cin, 0, 3, stride) if ctx.needs_input_grad[0] else None

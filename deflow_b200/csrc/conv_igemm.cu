@@ -922,29 +922,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);  // both operands MN-major
-      int stage = 0;
-      uint32_t phase = 0;
-      bool first = true;
-      for (int tile = t_begin; tile < t_end; ++tile) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-        // MN-major SWIZZLE_128B: 64-element MN groups LBO apart, 8-row K groups SBO = 1024 bytes apart
-        const uint64_t adesc = make_smem_desc(a_addr, WG_PIX * 128, 1024, 2);
-        const uint64_t bdesc = make_smem_desc(b_addr, WG_PIX * 128, 1024, 2);
+    // whole-warp issue loop, (lo, hi) descriptor halves -- see k_conv_wgrad_halo
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);  // both operands MN-major
+    // MN-major SWIZZLE_128B: 64-element MN groups LBO apart, 8-row K groups SBO = 1024 bytes apart
+    const uint32_t d_hi = (uint32_t)(make_smem_desc(0, 0, 1024, 2) >> 32);
+    const uint32_t lbo = (uint32_t)((WG_PIX * 128) >> 4) << 16;
+    const uint32_t a_lo0 = ((smem_u32(smem) & 0x3FFFFu) >> 4) + lbo;
+    const uint32_t b_lo0 = a_lo0 + (uint32_t)(Cfg::A_BYTES >> 4);
+    int stage = 0;
+    uint32_t phase = 0, accum = 0u;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t soff = (uint32_t)stage * (uint32_t)(Cfg::STAGE_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < WG_PIX / 16; ++k) {  // 16 pixels = 2 K groups = 2048 bytes per UMMA
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, !first);
-          first = false;
-        }
-        umma_commit(&empty[stage]);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-      }
-      umma_commit(acc_full);
+      for (int k = 0; k < WG_PIX / 16; ++k)   // 16 pixels = 2 K groups = 2048 bytes per UMMA
+        umma_bf16_lohi_warp(tmem_base, a_lo0 + soff + (uint32_t)(k * 128), d_hi, b_lo0 + soff + (uint32_t)(k * 128), d_hi, idesc,
+                            accum | (uint32_t)(k > 0));
+      accum = 1u;
+      umma_commit_warp(&empty[stage]);
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
+    umma_commit_warp(acc_full);
   } else if (t_end > t_begin) {
     const int q = warp & 3;
     const int m = q * 32 + lane;            // accumulator row: group (m >> 6), channel (m & 63) of that group
@@ -1049,31 +1048,43 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_halo(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      bool first = true;
-      for (int tile = t_begin; tile < t_end; ++tile) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + WH_HALO_BYTES;
-        const uint64_t bdesc = make_smem_desc(b_addr, WG_PIX * 128, 1024, 2);
-        for (int pr = 0; pr < it.npairs; ++pr) {
-          const int o1 = (it.t1[pr] / 3) * 10 + it.t1[pr] % 3, o2 = (it.t2[pr] / 3) * 10 + it.t2[pr] % 3;
-          // two 64-channel M groups = two taps, (o2 - o1) pixel rows apart; 8-pixel K groups one halo row (1280 B) apart
-          const uint64_t adesc = make_smem_desc(a_addr + o1 * 128, (uint32_t)(o2 - o1) * 128u, 1280, 2);
+    // Whole-warp issue loop (warp-uniform control flow, one elected lane issues) with (lo, hi) descriptor halves: only
+    // the start-address field of the low word changes from MMA to MMA.  Under `if (lane == 0)` the loop cost ~30 SASS
+    // instructions per MMA on one thread (ncu r01: tensor pipe active 14 %) -- more than the 64-128 cycles an MMA takes.
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+    const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 0, 1280, 2) >> 32), b_hi = (uint32_t)(make_smem_desc(0, 0, 1024, 2) >> 32);
+    const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+    // per tap pair: start (o1 pixel rows into the box) | leading byte offset ((o2 - o1) pixel rows), in 16-byte units
+    uint32_t pair_lo[Cfg::MAX_PAIRS];
 #pragma unroll
-          for (int k = 0; k < WG_PIX / 16; ++k)  // 16 pixels = 2 patch rows: A advances 2 halo rows, B 16 tile rows
-            umma_bf16(tmem_base + pr * N, adesc + (uint64_t)(k * 160), bdesc + (uint64_t)(k * 128), idesc, !(first && k == 0));
-        }
-        first = false;
-        umma_commit(&empty[stage]);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-      }
-      umma_commit(acc_full);
+    for (int pr = 0; pr < Cfg::MAX_PAIRS; ++pr) {
+      const int t1 = pr < it.npairs ? it.t1[pr] : 0, t2 = pr < it.npairs ? it.t2[pr] : 1;
+      const int o1 = (t1 / 3) * 10 + t1 % 3, o2 = (t2 / 3) * 10 + t2 % 3;
+      pair_lo[pr] = smem_lo + (uint32_t)o1 * 8u + (((uint32_t)(o2 - o1) * 8u) << 16);
     }
+    const uint32_t b_lo0 = smem_lo + (uint32_t)(WH_HALO_BYTES >> 4) + ((uint32_t)((WG_PIX * 128) >> 4) << 16);
+    const int npairs = it.npairs;
+    int stage = 0;
+    uint32_t phase = 0, accum = 0u;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t soff = (uint32_t)stage * (uint32_t)(Cfg::STAGE_BYTES >> 4);
+#pragma unroll
+      for (int pr = 0; pr < Cfg::MAX_PAIRS; ++pr) {
+        if (pr < npairs) {
+          // two 64-channel M groups = two taps; 16 pixels = 2 patch rows: A advances 2 halo rows (160 units), B 128 units
+#pragma unroll
+          for (int k = 0; k < WG_PIX / 16; ++k)
+            umma_bf16_lohi_warp(tmem_base + pr * N, pair_lo[pr] + soff + (uint32_t)(k * 160), a_hi,
+                                b_lo0 + soff + (uint32_t)(k * 128), b_hi, idesc, accum | (uint32_t)(k > 0));
+        }
+      }
+      accum = 1u;
+      umma_commit_warp(&empty[stage]);
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+    umma_commit_warp(acc_full);
   } else if (t_end > t_begin) {
     const int q = warp & 3;
     const int m = q * 32 + lane;

@@ -74,17 +74,21 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
   for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < M0; q += warps) {
     const int s0 = pil_start[q], s1 = pil_start[q + 1];
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    int j = s0;
-    for (; j + 1 < s1; j += 2) {  // two rows in flight
-      const int p0 = sorted_pt[j], p1 = sorted_pt[j + 1];
-      const float4 v0 = load4<IN_BF>(grad_h0, (size_t)p0 * 128 + lane * 4);
-      const float4 v1 = load4<IN_BF>(grad_h0, (size_t)p1 * 128 + lane * 4);
-      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
-      b.x += v1.x; b.y += v1.y; b.z += v1.z; b.w += v1.w;
-    }
-    if (j < s1) {
-      const float4 v0 = load4<IN_BF>(grad_h0, (size_t)sorted_pt[j] * 128 + lane * 4);
-      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+    // up to eight rows in flight (all indices first, then all rows): the median pillar is done in one round, and the
+    // heavy tail (hundreds of points in one pillar) is not a chain of dependent round trips
+    for (int j = s0; j < s1; j += 8) {
+      int pt[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pt[k] = j + k < s1 ? sorted_pt[j + k] : -1;
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] = pt[k] >= 0 ? load4<IN_BF>(grad_h0, (size_t)pt[k] * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
+        b.x += v[k + 1].x; b.y += v[k + 1].y; b.z += v[k + 1].z; b.w += v[k + 1].w;
+      }
     }
     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     const int pix = pil_pix[q];

@@ -14,12 +14,15 @@
 //   straddlers   (pillars that cross a 32-point group boundary)
 // Backward: one pillar-centric pass over the saved ReLU masks + a finalize block.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/deflow_b200.h"
 
 namespace dfb {
 
 constexpr int PFN_C = 32;
 constexpr int PFN_K = 9;
+
+__constant__ float c_pfn_w[PFN_C * PFN_K];   // Linear(9,32,bias=False) weight [c][k] of the running forward (k_pfn_points)
 
 struct PfnGeom {
   float vx, vy, vz;
@@ -71,22 +74,45 @@ __global__ void __launch_bounds__(256) k_pillar_mean(const int* __restrict__ cou
         cz[u] = pil_coor[3 * (size_t)q]; cy[u] = pil_coor[3 * (size_t)q + 1]; cx[u] = pil_coor[3 * (size_t)q + 2];
       }
     }
+    // pillars with more than 64 points (the heavy tail: up to ~750 on real sweeps) are summed by the whole warp below;
+    // left to a 4-lane group they would set the duration of the kernel
+    bool heavy[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) heavy[u] = s1[u] - s0[u] > 64;
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      r[u] = s0[u] + sub < s1[u] ? __ldg(rec + s0[u] + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+      r[u] = (!heavy[u] && s0[u] + sub < s1[u]) ? __ldg(rec + s0[u] + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int q = q0 + u * groups;
       float sx = r[u].x, sy = r[u].y, sz = r[u].z;
-      for (int j = s0[u] + sub + 4; j < s1[u]; j += 4) {
-        const float4 t = __ldg(rec + j);
-        sx += t.x; sy += t.y; sz += t.z;
+      if (!heavy[u]) {
+        for (int j = s0[u] + sub + 4; j < s1[u]; j += 4) {
+          const float4 t = __ldg(rec + j);
+          sx += t.x; sy += t.y; sz += t.z;
+        }
       }
 #pragma unroll
       for (int o = 2; o > 0; o >>= 1) {
         sx += __shfl_xor_sync(0xffffffffu, sx, o);
         sy += __shfl_xor_sync(0xffffffffu, sy, o);
         sz += __shfl_xor_sync(0xffffffffu, sz, o);
+      }
+      unsigned hm = __ballot_sync(0xffffffffu, heavy[u] && sub == 0);
+      while (hm) {                                   // warp-uniform
+        const int src = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const int hs0 = __shfl_sync(0xffffffffu, s0[u], src), hs1 = __shfl_sync(0xffffffffu, s1[u], src);
+        float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+        const int lane = threadIdx.x & 31;
+        int j = hs0 + lane;
+        for (; j + 32 < hs1; j += 64) {
+          const float4 t0 = __ldg(rec + j), t1 = __ldg(rec + j + 32);
+          ax += t0.x; ay += t0.y; az += t0.z; bx += t1.x; by += t1.y; bz += t1.z;
+        }
+        if (j < hs1) { const float4 t0 = __ldg(rec + j); ax += t0.x; ay += t0.y; az += t0.z; }
+        ax = warp_sum(ax + bx); ay = warp_sum(ay + by); az = warp_sum(az + bz);
+        if ((lane & ~3) == src) { sx = ax; sy = ay; sz = az; }
       }
       if (q < M) {
         const float n = (float)(s1[u] - s0[u]);  // reduced_feats /= count.to(float) (scatter_points_cuda.cu:59-60)
@@ -246,22 +272,19 @@ __device__ __forceinline__ void store_row32(float* __restrict__ dst, const float
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256, 4) k_pfn_points(const int* __restrict__ counts, int F,
+__global__ void __launch_bounds__(256, 3) k_pfn_points(const int* __restrict__ counts, int F,
                                                        const float4* __restrict__ rec, const float4* __restrict__ pil_hdr,
-                                                       const float* __restrict__ weight, const float* __restrict__ bn_params,
+                                                       const float* __restrict__ bn_params,
                                                        unsigned* __restrict__ pt_mask, float* __restrict__ part,
                                                        float* __restrict__ pil_feats, void* __restrict__ image) {
-  __shared__ __align__(16) float Wp[PFN_K][PFN_C];          // Wp[k][c]
-  extern __shared__ __align__(16) float sAB[];              // [F][2][32] scale / shift per frame | 8 x [32][33] tiles
+  extern __shared__ __align__(16) float sAB[];              // [F][2][32] scale / shift per frame
   const int n = counts[2 * F + F];
-  for (int i = threadIdx.x; i < PFN_C * PFN_K; i += blockDim.x) Wp[i % PFN_K][i / PFN_K] = weight[i];
   for (int i = threadIdx.x; i < F * 2 * PFN_C; i += blockDim.x) {
     const int f = i / (2 * PFN_C), r = i % (2 * PFN_C);
     sAB[i] = bn_params[(size_t)f * 4 * PFN_C + r];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  float* T = sAB + (size_t)F * 2 * PFN_C + (threadIdx.x >> 5) * (32 * 33);   // this warp's [point][channel] tile
   const int n_groups = (n + 31) >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
@@ -269,6 +292,9 @@ __global__ void __launch_bounds__(256, 4) k_pfn_points(const int* __restrict__ c
     const bool live = j < n;
     int q = 0, pix = 0, cnt = 1;
     bool first = false, last = false;
+    float v[PFN_C];
+#pragma unroll
+    for (int c = 0; c < PFN_C; ++c) v[c] = 0.f;
     if (live) {
       const float4 r = __ldg(rec + j);
       q = rec_q(r);
@@ -281,18 +307,17 @@ __global__ void __launch_bounds__(256, 4) k_pfn_points(const int* __restrict__ c
       last = j + 1 == s0 + cnt;
       float fe[PFN_K];
       decorate_hdr(r, h1, h2, fe);
+      // weights are FFMA constant-bank operands (c_pfn_w[c][k], the torch layout): no load instructions at all
       float2 y2[PFN_C / 2];
 #pragma unroll
-      for (int c = 0; c < PFN_C / 2; ++c) y2[c] = make_float2(0.f, 0.f);
+      for (int c = 0; c < PFN_C / 2; ++c) {
+        float y0 = 0.f, y1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < PFN_K; ++k) {
-        const float2 fk = make_float2(fe[k], fe[k]);
-#pragma unroll
-        for (int c4 = 0; c4 < PFN_C; c4 += 4) {
-          const float4 w = *reinterpret_cast<const float4*>(&Wp[k][c4]);
-          y2[c4 / 2] = __ffma2_rn(make_float2(w.x, w.y), fk, y2[c4 / 2]);
-          y2[c4 / 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), fk, y2[c4 / 2 + 1]);
+        for (int k = 0; k < PFN_K; ++k) {
+          y0 = fmaf(fe[k], c_pfn_w[(2 * c) * PFN_K + k], y0);
+          y1 = fmaf(fe[k], c_pfn_w[(2 * c + 1) * PFN_K + k], y1);
         }
+        y2[c] = make_float2(y0, y1);
       }
       const float* ab = sAB + (size_t)__float_as_int(h0.w) * 2 * PFN_C;
       unsigned m = 0u;
@@ -301,48 +326,68 @@ __global__ void __launch_bounds__(256, 4) k_pfn_points(const int* __restrict__ c
         const float4 a = *reinterpret_cast<const float4*>(ab + c4), b = *reinterpret_cast<const float4*>(ab + PFN_C + c4);
         const float2 v0 = __ffma2_rn(y2[c4 / 2], make_float2(a.x, a.y), make_float2(b.x, b.y));
         const float2 v1 = __ffma2_rn(y2[c4 / 2 + 1], make_float2(a.z, a.w), make_float2(b.z, b.w));
-        const float r0 = fmaxf(v0.x, 0.f), r1 = fmaxf(v0.y, 0.f), r2 = fmaxf(v1.x, 0.f), r3 = fmaxf(v1.y, 0.f);
+        v[c4] = fmaxf(v0.x, 0.f); v[c4 + 1] = fmaxf(v0.y, 0.f); v[c4 + 2] = fmaxf(v1.x, 0.f); v[c4 + 3] = fmaxf(v1.y, 0.f);
         // relu(x) > 0  <=>  x > 0; the bits of a non-negative float are a positive int exactly when it is > 0
-        m |= ((unsigned)(-__float_as_int(r0)) >> 31) << c4;
-        m |= ((unsigned)(-__float_as_int(r1)) >> 31) << (c4 + 1);
-        m |= ((unsigned)(-__float_as_int(r2)) >> 31) << (c4 + 2);
-        m |= ((unsigned)(-__float_as_int(r3)) >> 31) << (c4 + 3);
-        // transpose through the tile: bank (33 * lane + c) % 32 = (lane + c) % 32, conflict-free both ways
-        T[lane * 33 + c4] = r0; T[lane * 33 + c4 + 1] = r1; T[lane * 33 + c4 + 2] = r2; T[lane * 33 + c4 + 3] = r3;
+        m |= ((unsigned)(-__float_as_int(v[c4])) >> 31) << c4;
+        m |= ((unsigned)(-__float_as_int(v[c4 + 1])) >> 31) << (c4 + 1);
+        m |= ((unsigned)(-__float_as_int(v[c4 + 2])) >> 31) << (c4 + 2);
+        m |= ((unsigned)(-__float_as_int(v[c4 + 3])) >> 31) << (c4 + 3);
       }
       pt_mask[j] = m;
     }
     const unsigned firstmask = __ballot_sync(0xffffffffu, first), lastmask = __ballot_sync(0xffffffffu, last);
     const int nvalid = min(32, n - grp * 32);
-    __syncwarp();
-    // lane = channel: walk the group's points in CSR order; a pillar that begins AND ends inside the group is finished
-    // on the spot (mean, voxel feature row, NHWC image row: one coalesced 64 / 128-byte row per pillar)
-    float* prow = part + (size_t)grp * 2 * PFN_C;
-    float acc = 0.f;
-    bool began = false;
+    // segmented inclusive scan over the lanes; a segment starts at lane 0 (possibly the tail of an earlier group's
+    // pillar) and at every first point of a pillar
+    const unsigned starts = firstmask | 1u;
+    const int seg_start = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));
+    const int dist = lane - seg_start;
+    const unsigned far = __ballot_sync(0xffffffffu, dist >= 4);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < nvalid) {                       // warp-uniform
-        if ((firstmask >> i) & 1u) { acc = 0.f; began = true; }
-        acc += T[i * 33 + lane];
-        if ((lastmask >> i) & 1u) {
-          if (began) {
-            const int cnt_i = __shfl_sync(0xffffffffu, cnt, i), pix_i = __shfl_sync(0xffffffffu, pix, i);
-            const float val = acc * __frcp_rn((float)cnt_i);
-            if (pil_feats) pil_feats[(size_t)__shfl_sync(0xffffffffu, q, i) * PFN_C + lane] = val;
-            if (BF16) reinterpret_cast<__nv_bfloat16*>(image)[(size_t)pix_i * PFN_C + lane] = __float2bfloat16_rn(val);
-            else reinterpret_cast<float*>(image)[(size_t)pix_i * PFN_C + lane] = val;
-          } else {
-            prow[lane] = acc;                 // leading segment of a pillar that began in an earlier group
-          }
-          began = false;
-          acc = 0.f;
-        } else if (i == nvalid - 1) {
-          prow[(began ? PFN_C : 0) + lane] = acc;   // the pillar continues into the next group
-        }
+    for (int c = 0; c < PFN_C; ++c) {
+      float x = v[c], t;
+      t = __shfl_up_sync(0xffffffffu, x, 1); if (dist >= 1) x += t;
+      t = __shfl_up_sync(0xffffffffu, x, 2); if (dist >= 2) x += t;
+      v[c] = x;
+    }
+    if (far) {   // some segment of this group is longer than 4 points (warp-uniform)
+#pragma unroll
+      for (int c = 0; c < PFN_C; ++c) {
+        float x = v[c], t;
+        t = __shfl_up_sync(0xffffffffu, x, 4); if (dist >= 4) x += t;
+        t = __shfl_up_sync(0xffffffffu, x, 8); if (dist >= 8) x += t;
+        t = __shfl_up_sync(0xffffffffu, x, 16); if (dist >= 16) x += t;
+        v[c] = x;
       }
     }
-    __syncwarp();                             // the tile is rewritten by the next group
+    const bool begins = (firstmask >> seg_start) & 1u;   // the segment this lane closes began inside this group
+    float* prow = part + (size_t)grp * 2 * PFN_C;
+    if (live && last) {
+      if (begins) {
+        const float inv = __frcp_rn((float)cnt);
+#pragma unroll
+        for (int c = 0; c < PFN_C; ++c) v[c] *= inv;
+        if (pil_feats) store_row32(pil_feats + (size_t)q * PFN_C, v);
+        if (BF16) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(image) + (size_t)pix * PFN_C);
+#pragma unroll
+          for (int c8 = 0; c8 < PFN_C; c8 += 8) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[c8], v[c8 + 1]), p1 = __floats2bfloat162_rn(v[c8 + 2], v[c8 + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[c8 + 4], v[c8 + 5]), p3 = __floats2bfloat162_rn(v[c8 + 6], v[c8 + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<unsigned*>(&p0); u.y = *reinterpret_cast<unsigned*>(&p1);
+            u.z = *reinterpret_cast<unsigned*>(&p2); u.w = *reinterpret_cast<unsigned*>(&p3);
+            dst[c8 / 8] = u;
+          }
+        } else {
+          store_row32(reinterpret_cast<float*>(image) + (size_t)pix * PFN_C, v);
+        }
+      } else {
+        store_row32(prow, v);            // leading segment of a pillar that began in an earlier group
+      }
+    } else if (live && lane == nvalid - 1) {
+      store_row32(prow + (begins ? PFN_C : 0), v);   // the pillar continues into the next group
+    }
   }
 }
 
@@ -650,26 +695,25 @@ extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
   k_bn_finalize<<<1, 1024, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum, a->stats, a->weight, a->gamma, a->beta,
                                     a->running_mean, a->running_var, a->bn_params);
   if (a->image_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)a->image_ready_event, 0);
-  const int tile_bytes = 8 * 32 * 33 * (int)sizeof(float);
-  const int dyn = F * 2 * PFN_C * (int)sizeof(float) + tile_bytes;
+  const int dyn = F * 2 * PFN_C * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_pfn_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float) + tile_bytes);
-    cudaFuncSetAttribute(k_pfn_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float) + tile_bytes);
+    cudaFuncSetAttribute(k_pfn_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
+    cudaFuncSetAttribute(k_pfn_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
     configured = true;
   }
-  // resident CTAs per SM: 4 by registers, fewer when many frames make the scale/shift table large
-  int per_sm = (220 * 1024) / (dyn + 2048);
-  per_sm = per_sm > 4 ? 4 : per_sm < 1 ? 1 : per_sm;
-  if (a->image_bf16) {
-    k_pfn_points<true><<<sms * per_sm, 256, dyn, st>>>(a->counts, F, rec, hdr, a->weight, a->bn_params, a->pt_mask, a->partials,
+  // Linear(9,32) weights -> constant bank (device-to-device, stream-ordered): the point pass reads them as FFMA
+  // constant operands instead of 72 shared-memory broadcast loads per point (ncu: the pass was LSU-bound).  One
+  // constant copy per device: concurrent forwards of DIFFERENT feature nets must not run on different streams.
+  cudaMemcpyToSymbolAsync(c_pfn_w, a->weight, sizeof(float) * PFN_C * PFN_K, 0, cudaMemcpyDeviceToDevice, st);
+  if (a->image_bf16)
+    k_pfn_points<true><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->bn_params, a->pt_mask, a->partials,
                                                   a->pil_feats, a->image);
-    k_pfn_straddlers<true><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
-  } else {
-    k_pfn_points<false><<<sms * per_sm, 256, dyn, st>>>(a->counts, F, rec, hdr, a->weight, a->bn_params, a->pt_mask, a->partials,
+  else
+    k_pfn_points<false><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->bn_params, a->pt_mask, a->partials,
                                                    a->pil_feats, a->image);
-    k_pfn_straddlers<false><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
-  }
+  if (a->image_bf16) k_pfn_straddlers<true><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
+  else k_pfn_straddlers<false><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
   add_launches(launches);
   return check_launch("dfb_pfn_forward");
 }

@@ -12,6 +12,7 @@
 // reference's boolean indexing produces.  A counting sort (one integer atomic per point) builds a
 // CSR list of the points of every pillar so that all later reductions are atomic-free segment sums.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/deflow_b200.h"
 
 namespace dfb {
@@ -31,27 +32,61 @@ __device__ __forceinline__ int point_key(float x, float y, float z, const VoxelP
   return (cz * P.gy + cy) * P.gx + cx;
 }
 
+// The block's 1024 x (x, y, z) rows through shared memory: fully coalesced global loads (one sector fetched once; the
+// strided per-point loads re-fetched every sector ~3x from L2, ncu r01), then conflict-free stride-3 shared reads.
+// Thread t receives points t, t + 256, t + 512, t + 768 of the chunk; rows past Nmax read as NaN (= dropped).
+__device__ __forceinline__ void load_chunk(const float* __restrict__ p, int Nmax, int stride, int blk, float* stage,
+                                           float (&x)[IDX_ITEMS], float (&y)[IDX_ITEMS], float (&z)[IDX_ITEMS]) {
+  const float qnan = __int_as_float(0x7fc00000);
+  if (stride == 3) {
+    const float* src = p + (size_t)blk * IDX_CHUNK * 3;
+    const int nfl = min(IDX_CHUNK, Nmax - blk * IDX_CHUNK) * 3;
+    if (nfl == IDX_CHUNK * 3 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        reinterpret_cast<float4*>(stage)[k * IDX_BLOCK + threadIdx.x] = __ldg(reinterpret_cast<const float4*>(src) + k * IDX_BLOCK + threadIdx.x);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3 * IDX_ITEMS; ++k) {
+        const int e = k * IDX_BLOCK + threadIdx.x;
+        stage[e] = e < nfl ? src[e] : qnan;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < IDX_ITEMS; ++j) {
+      const int e = 3 * (j * IDX_BLOCK + threadIdx.x);
+      x[j] = stage[e]; y[j] = stage[e + 1]; z[j] = stage[e + 2];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < IDX_ITEMS; ++j) {
+      const int i = blk * IDX_CHUNK + j * IDX_BLOCK + threadIdx.x;
+      x[j] = y[j] = z[j] = qnan;
+      if (i < Nmax) { x[j] = p[(size_t)i * stride]; y[j] = p[(size_t)i * stride + 1]; z[j] = p[(size_t)i * stride + 2]; }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(IDX_BLOCK) k_mark_points(const float* __restrict__ pts, int Nmax, int stride,
-                                                          VoxelParams P, int Wd, int nblk,
+                                                          VoxelParams P, int Wd, int nblk, int precheck,
                                                           unsigned* __restrict__ bitmap, int* __restrict__ blk_cnt) {
   __shared__ int s_total;
+  __shared__ __align__(16) float stage[IDX_CHUNK * 3];
   const int f = blockIdx.y, blk = blockIdx.x;
   const float* p = pts + (size_t)f * Nmax * stride;
   if (threadIdx.x == 0) s_total = 0;
   float x[IDX_ITEMS], y[IDX_ITEMS], z[IDX_ITEMS];
-  const float qnan = __int_as_float(0x7fc00000);
-#pragma unroll
-  for (int j = 0; j < IDX_ITEMS; ++j) {
-    const int i = blk * IDX_CHUNK + j * IDX_BLOCK + threadIdx.x;
-    x[j] = y[j] = z[j] = qnan;
-    if (i < Nmax) { x[j] = p[(size_t)i * stride]; y[j] = p[(size_t)i * stride + 1]; z[j] = p[(size_t)i * stride + 2]; }
-  }
+  load_chunk(p, Nmax, stride, blk, stage, x, y, z);
   int cnt = 0;
 #pragma unroll
   for (int j = 0; j < IDX_ITEMS; ++j) {
     const int key = point_key(x[j], y[j], z[j], P);
     if (key >= 0) {
-      atomicOr(&bitmap[(size_t)f * Wd + (key >> 5)], 1u << (key & 31));
+      // a pillar holds ~4 points: most of them find the bit already set (a stale read only costs a redundant atomic)
+      unsigned* wp = &bitmap[(size_t)f * Wd + (key >> 5)];
+      const unsigned bit = 1u << (key & 31);
+      if (!precheck || !(__ldcg(wp) & bit)) atomicOr(wp, bit);
       ++cnt;
     }
   }
@@ -134,10 +169,10 @@ __global__ void __launch_bounds__(1024) k_bitmap_scan(const unsigned* __restrict
 }
 
 // ---------------------------------------------------------------- K3: stable compaction + rank + slot
-// A thread owns FOUR CONSECUTIVE points of the block's 1024-point chunk, so one block scan of the per-thread valid
-// counts gives the stable (original-order) destination of every point.  The chunk is staged through shared memory
-// with fully coalesced scalar loads (12 in flight per thread) when the rows are packed xyz; the rank gathers, the
-// counting-sort atomics and the stores of a thread's four points are independent of each other.
+// Thread t owns points t, t + 256, t + 512, t + 768 of the block's 1024-point chunk (consecutive lanes = consecutive
+// points, so the compacted rows a warp stores are contiguous).  All twelve coordinate loads are issued up front, the
+// four stable destinations come from four ballots + one shared-memory table of per-(item, warp) totals (one barrier
+// instead of twelve), and the rank gathers, counting-sort atomics and stores of the four points are independent.
 __global__ void __launch_bounds__(IDX_BLOCK) k_compact(
     const float* __restrict__ pts, int Nmax, int stride, VoxelParams P, int Wd,
     int nblk, int F, int HW, const unsigned* __restrict__ bitmap, const int* __restrict__ word_rank,
@@ -145,81 +180,146 @@ __global__ void __launch_bounds__(IDX_BLOCK) k_compact(
     int* __restrict__ pt_coor, long long* __restrict__ pt_idx, float* __restrict__ pt_offs,
     int* __restrict__ pt_pillar, int* __restrict__ pt_slot, int* __restrict__ pil_cnt, int* __restrict__ pil_coor,
     int* __restrict__ pil_pix) {
-  __shared__ int sm[33];
+  constexpr int NW = IDX_BLOCK / 32;
+  __shared__ int wtot[IDX_ITEMS][NW];
   __shared__ __align__(16) float stage[IDX_CHUNK * 3];
   const int f = blockIdx.y, blk = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const float* p = pts + (size_t)f * Nmax * stride;
-  const int i0 = blk * IDX_CHUNK + IDX_ITEMS * threadIdx.x;   // first of this thread's four points
   float x[IDX_ITEMS], y[IDX_ITEMS], z[IDX_ITEMS];
-  const float qnan = __int_as_float(0x7fc00000);
-  if (stride == 3) {
-    const float* src = p + (size_t)blk * IDX_CHUNK * 3;
-    const int nfl = min(IDX_CHUNK, Nmax - blk * IDX_CHUNK) * 3;
+  load_chunk(p, Nmax, stride, blk, stage, x, y, z);
+  __syncthreads();                       // every thread has its rows: the staging buffer becomes the store transposer
+  float* wst = stage + w * 96;           // 32 rows x 3 words per warp
+  int key[IDX_ITEMS];
+  unsigned bal[IDX_ITEMS];
 #pragma unroll
-    for (int k = 0; k < 3 * IDX_ITEMS; ++k) {
-      const int e = k * IDX_BLOCK + threadIdx.x;
-      stage[e] = e < nfl ? src[e] : qnan;
-    }
-    __syncthreads();
-    const float4* q4 = reinterpret_cast<const float4*>(stage) + 3 * threadIdx.x;
-    const float4 a = q4[0], b = q4[1], c = q4[2];
-    x[0] = a.x; y[0] = a.y; z[0] = a.z; x[1] = a.w; y[1] = b.x; z[1] = b.y;
-    x[2] = b.z; y[2] = b.w; z[2] = c.x; x[3] = c.y; y[3] = c.z; z[3] = c.w;
-  } else {
-#pragma unroll
-    for (int k = 0; k < IDX_ITEMS; ++k) {
-      const int i = i0 + k;
-      x[k] = y[k] = z[k] = qnan;
-      if (i < Nmax) { x[k] = p[(size_t)i * stride]; y[k] = p[(size_t)i * stride + 1]; z[k] = p[(size_t)i * stride + 2]; }
-    }
+  for (int j = 0; j < IDX_ITEMS; ++j) {
+    key[j] = point_key(x[j], y[j], z[j], P);
+    bal[j] = __ballot_sync(0xffffffffu, key[j] >= 0);
+    if (lane == 0) wtot[j][w] = __popc(bal[j]);
   }
-  int key[IDX_ITEMS], cnt = 0;
-#pragma unroll
-  for (int k = 0; k < IDX_ITEMS; ++k) { key[k] = point_key(x[k], y[k], z[k], P); cnt += key[k] >= 0; }
-  int tot;
-  const int ex = block_excl_scan<IDX_BLOCK>(cnt, sm, tot);
-  if (cnt == 0) return;
+  __syncthreads();
   const int pt_base = counts[2 * F + f] + blk_off[f * nblk + blk];
   const int pil_base = counts[3 * F + 1 + f];
+  int dst[IDX_ITEMS];
+  {
+    int run = pt_base;
+#pragma unroll
+    for (int j = 0; j < IDX_ITEMS; ++j) {
+      int before = 0, tot = 0;
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) { const int t = wtot[j][ww]; before += ww < w ? t : 0; tot += t; }
+      dst[j] = run + before + __popc(bal[j] & ((1u << lane) - 1u));
+      run += tot;
+    }
+  }
   const float hx = P.vx / 2, hy = P.vy / 2, hz = P.vz / 2;  // voxel_size / 2 (encoder.py:519)
   // rank of the point's cell among the occupied cells of the frame = the reference's voxel id
   int q[IDX_ITEMS], slot[IDX_ITEMS];
 #pragma unroll
-  for (int k = 0; k < IDX_ITEMS; ++k) {
-    q[k] = -1;
-    if (key[k] >= 0) {
-      const unsigned word = bitmap[(size_t)f * Wd + (key[k] >> 5)];
-      q[k] = pil_base + seg_base[f * S + (key[k] >> 15)] + word_rank[(size_t)f * Wd + (key[k] >> 5)] +
-             __popc(word & ((1u << (key[k] & 31)) - 1u));
+  for (int j = 0; j < IDX_ITEMS; ++j) {
+    q[j] = -1;
+    if (key[j] >= 0) {
+      const unsigned word = bitmap[(size_t)f * Wd + (key[j] >> 5)];
+      q[j] = pil_base + seg_base[f * S + (key[j] >> 15)] + word_rank[(size_t)f * Wd + (key[j] >> 5)] +
+             __popc(word & ((1u << (key[j] & 31)) - 1u));
     }
   }
 #pragma unroll
-  for (int k = 0; k < IDX_ITEMS; ++k) slot[k] = q[k] >= 0 ? atomicAdd(&pil_cnt[q[k]], 1) : 0;
-  int dst = pt_base + ex;
+  for (int j = 0; j < IDX_ITEMS; ++j) slot[j] = q[j] >= 0 ? atomicAdd(&pil_cnt[q[j]], 1) : 0;
+  // the compacted rows of a warp-item are contiguous in the outputs: transpose each 3-word row array through 96 words of
+  // shared memory so that a store instruction writes 128 contiguous bytes (the direct 12-byte-stride stores wrote every
+  // sector three times: 3.1x L1->L2 write traffic, ncu r01)
 #pragma unroll
-  for (int k = 0; k < IDX_ITEMS; ++k) {
-    if (key[k] < 0) continue;
-    const int cx = key[k] % P.gx, t = key[k] / P.gx, cy = t % P.gy, cz = t / P.gy;
-    pt_xyz[3 * (size_t)dst] = x[k];
-    pt_xyz[3 * (size_t)dst + 1] = y[k];
-    pt_xyz[3 * (size_t)dst + 2] = z[k];
-    pt_coor[3 * (size_t)dst] = cz;
-    pt_coor[3 * (size_t)dst + 1] = cy;
-    pt_coor[3 * (size_t)dst + 2] = cx;
-    pt_idx[dst] = i0 + k;
-    // point_offsets = p - ((c * vs + min) + vs / 2), every step rounded to fp32 (encoder.py:516-523)
-    pt_offs[3 * (size_t)dst] = __fsub_rn(x[k], __fadd_rn(__fadd_rn(__fmul_rn((float)cx, P.vx), P.lox), hx));
-    pt_offs[3 * (size_t)dst + 1] = __fsub_rn(y[k], __fadd_rn(__fadd_rn(__fmul_rn((float)cy, P.vy), P.loy), hy));
-    pt_offs[3 * (size_t)dst + 2] = __fsub_rn(z[k], __fadd_rn(__fadd_rn(__fmul_rn((float)cz, P.vz), P.loz), hz));
-    pt_pillar[dst] = q[k];
-    pt_slot[dst] = slot[k];
-    if (slot[k] == 0) {  // exactly one point per pillar sees slot 0
-      pil_coor[3 * (size_t)q[k]] = cz;
-      pil_coor[3 * (size_t)q[k] + 1] = cy;
-      pil_coor[3 * (size_t)q[k] + 2] = cx;
-      pil_pix[q[k]] = f * HW + cy * P.gx + cx;  // PointPillarsScatter: y * nx + x (encoder.py:141)
+  for (int j = 0; j < IDX_ITEMS; ++j) {
+    const bool ok = key[j] >= 0;
+    const int nrow = __popc(bal[j]), r = __popc(bal[j] & ((1u << lane) - 1u));
+    const int d = dst[j];
+    const int d0 = __shfl_sync(0xffffffffu, d - r, 0);       // destination of the warp-item's first valid row
+    const int kk = ok ? key[j] : 0;
+    const int cx = kk % P.gx, t = kk / P.gx, cy = t % P.gy, cz = t / P.gy;
+    if (ok) { wst[3 * r] = x[j]; wst[3 * r + 1] = y[j]; wst[3 * r + 2] = z[j]; }
+    __syncwarp();
+    for (int e = lane; e < 3 * nrow; e += 32) pt_xyz[3 * (size_t)d0 + e] = wst[e];
+    __syncwarp();
+    if (ok) { wst[3 * r] = __int_as_float(cz); wst[3 * r + 1] = __int_as_float(cy); wst[3 * r + 2] = __int_as_float(cx); }
+    __syncwarp();
+    for (int e = lane; e < 3 * nrow; e += 32) pt_coor[3 * (size_t)d0 + e] = __float_as_int(wst[e]);
+    __syncwarp();
+    if (ok) {
+      // point_offsets = p - ((c * vs + min) + vs / 2), every step rounded to fp32 (encoder.py:516-523)
+      wst[3 * r] = __fsub_rn(x[j], __fadd_rn(__fadd_rn(__fmul_rn((float)cx, P.vx), P.lox), hx));
+      wst[3 * r + 1] = __fsub_rn(y[j], __fadd_rn(__fadd_rn(__fmul_rn((float)cy, P.vy), P.loy), hy));
+      wst[3 * r + 2] = __fsub_rn(z[j], __fadd_rn(__fadd_rn(__fmul_rn((float)cz, P.vz), P.loz), hz));
     }
-    ++dst;
+    __syncwarp();
+    for (int e = lane; e < 3 * nrow; e += 32) pt_offs[3 * (size_t)d0 + e] = wst[e];
+    __syncwarp();
+    if (!ok) continue;
+    pt_idx[d] = blk * IDX_CHUNK + j * IDX_BLOCK + threadIdx.x;
+    pt_pillar[d] = q[j];
+    pt_slot[d] = slot[j];
+    if (slot[j] == 0) {  // exactly one point per pillar sees slot 0
+      pil_coor[3 * (size_t)q[j]] = cz;
+      pil_coor[3 * (size_t)q[j] + 1] = cy;
+      pil_coor[3 * (size_t)q[j] + 2] = cx;
+      pil_pix[q[j]] = f * HW + cy * P.gx + cx;  // PointPillarsScatter: y * nx + x (encoder.py:141)
+    }
+  }
+}
+
+// Variant (DFB_COMPACT=loop): one block scan per item, everything of an item finished before the next is touched.
+__global__ void __launch_bounds__(IDX_BLOCK) k_compact_loop(
+    const float* __restrict__ pts, int Nmax, int stride, VoxelParams P, int Wd,
+    int nblk, int F, int HW, const unsigned* __restrict__ bitmap, const int* __restrict__ word_rank,
+    const int* __restrict__ seg_base, int S, const int* __restrict__ blk_off, const int* __restrict__ counts, float* __restrict__ pt_xyz,
+    int* __restrict__ pt_coor, long long* __restrict__ pt_idx, float* __restrict__ pt_offs,
+    int* __restrict__ pt_pillar, int* __restrict__ pt_slot, int* __restrict__ pil_cnt, int* __restrict__ pil_coor,
+    int* __restrict__ pil_pix) {
+  __shared__ int sm[33];
+  const int f = blockIdx.y, blk = blockIdx.x;
+  const float* p = pts + (size_t)f * Nmax * stride;
+  const int pt_base = counts[2 * F + f] + blk_off[f * nblk + blk];
+  const int pil_base = counts[3 * F + 1 + f];
+  int carry = 0;
+  const float hx = P.vx / 2, hy = P.vy / 2, hz = P.vz / 2;
+  const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll 1
+  for (int j = 0; j < IDX_ITEMS; ++j) {
+    const int i = blk * IDX_CHUNK + j * IDX_BLOCK + threadIdx.x;
+    float x = qnan, y = qnan, z = qnan;
+    if (i < Nmax) { x = p[(size_t)i * stride]; y = p[(size_t)i * stride + 1]; z = p[(size_t)i * stride + 2]; }
+    const int key = point_key(x, y, z, P);
+    int tot;
+    const int ex = block_excl_scan<IDX_BLOCK>(key >= 0 ? 1 : 0, sm, tot);
+    if (key >= 0) {
+      const int dst = pt_base + carry + ex;
+      const int cx = key % P.gx, t = key / P.gx, cy = t % P.gy, cz = t / P.gy;
+      pt_xyz[3 * (size_t)dst] = x;
+      pt_xyz[3 * (size_t)dst + 1] = y;
+      pt_xyz[3 * (size_t)dst + 2] = z;
+      pt_coor[3 * (size_t)dst] = cz;
+      pt_coor[3 * (size_t)dst + 1] = cy;
+      pt_coor[3 * (size_t)dst + 2] = cx;
+      pt_idx[dst] = i;
+      pt_offs[3 * (size_t)dst] = __fsub_rn(x, __fadd_rn(__fadd_rn(__fmul_rn((float)cx, P.vx), P.lox), hx));
+      pt_offs[3 * (size_t)dst + 1] = __fsub_rn(y, __fadd_rn(__fadd_rn(__fmul_rn((float)cy, P.vy), P.loy), hy));
+      pt_offs[3 * (size_t)dst + 2] = __fsub_rn(z, __fadd_rn(__fadd_rn(__fmul_rn((float)cz, P.vz), P.loz), hz));
+      const unsigned word = bitmap[(size_t)f * Wd + (key >> 5)];
+      const int rank = seg_base[f * S + (key >> 15)] + word_rank[(size_t)f * Wd + (key >> 5)] +
+                       __popc(word & ((1u << (key & 31)) - 1u));
+      const int q = pil_base + rank;
+      pt_pillar[dst] = q;
+      const int slot = atomicAdd(&pil_cnt[q], 1);
+      pt_slot[dst] = slot;
+      if (slot == 0) {
+        pil_coor[3 * (size_t)q] = cz;
+        pil_coor[3 * (size_t)q + 1] = cy;
+        pil_coor[3 * (size_t)q + 2] = cx;
+        pil_pix[q] = f * HW + cy * P.gx + cx;
+      }
+    }
+    carry += tot;
   }
 }
 
@@ -267,6 +367,7 @@ __global__ void __launch_bounds__(1024) k_pillar_scan(const int* __restrict__ pi
 // pil_start (final) for every pillar; for every point its CSR position j = pil_start[q] + slot:
 //   sorted_pt[j] = p   and   csr_rec[j] = (x, y, z, q)   -- the 16-byte record every later pass over the points of a
 // pillar reads sequentially (no p -> xyz -> q double indirection in the feature-net kernels).
+template <int U>
 __global__ void __launch_bounds__(256) k_fill_csr(const int* __restrict__ counts, int F, int total_cap,
                                                   const int* __restrict__ pt_pillar, const int* __restrict__ pt_slot,
                                                   const float* __restrict__ pt_xyz, const int* __restrict__ pil_loc,
@@ -278,7 +379,6 @@ __global__ void __launch_bounds__(256) k_fill_csr(const int* __restrict__ counts
   for (int q = t0; q < M; q += stride) pil_start[q] = pil_loc[q] + blk_base[q / PSCAN_ITEMS];
   if (t0 == 0) pil_start[M] = n;
   // four points per thread and iteration, every load of the four issued before the first dependent gather
-  constexpr int U = 4;
   for (int p0 = t0; p0 < n; p0 += U * stride) {
     int q[U], sl[U];
     float x[U], y[U], z[U];
@@ -301,6 +401,12 @@ __global__ void __launch_bounds__(256) k_fill_csr(const int* __restrict__ counts
       csr_rec[j[u]] = make_float4(x[u], y[u], z[u], __int_as_float(q[u]));
     }
   }
+}
+
+// tuning switches (diagnostic): integer environment variable, read on every call (cheap next to a launch sequence)
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 VoxelParams make_voxel_params(const float* vs, const float* rng) {
@@ -373,7 +479,7 @@ extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
   }
   if (a->Nmax > 0) {
     dim3 g((unsigned)nblk_, F);
-    k_mark_points<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, a->bitmap, a->blk_cnt);
+    k_mark_points<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, env_flag("DFB_MARK_PRECHECK", 1), a->bitmap, a->blk_cnt);
   }
   {
     dim3 g(S, F);
@@ -382,9 +488,14 @@ extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
   }
   if (a->Nmax > 0) {
     dim3 g((unsigned)nblk_, F);
-    k_compact<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
-                                       a->word_rank, seg_base, S, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
-                                       a->pt_offs, a->pt_pillar, a->pt_slot, a->pil_cnt, a->pil_coor, a->pil_pix);
+    if (env_flag("DFB_COMPACT_LOOP", 0))
+      k_compact_loop<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
+                                              a->word_rank, seg_base, S, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
+                                              a->pt_offs, a->pt_pillar, a->pt_slot, a->pil_cnt, a->pil_coor, a->pil_pix);
+    else
+      k_compact<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
+                                         a->word_rank, seg_base, S, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
+                                         a->pt_offs, a->pt_pillar, a->pt_slot, a->pil_cnt, a->pil_coor, a->pil_pix);
   }
   k_pillar_scan<<<nb, 1024, 0, st>>>(a->pil_cnt, a->counts, F, pil_loc, blk_tot, blk_base, a->tickets + 1);
   {
@@ -393,8 +504,15 @@ extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
     int maxb = sm_count() * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    k_fill_csr<<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pt_xyz, pil_loc, blk_base,
-                                       a->pil_start, a->sorted_pt, (float4*)a->csr_rec);
+    if (env_flag("DFB_FILL_U", 1) >= 4)
+      k_fill_csr<4><<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pt_xyz, pil_loc, blk_base,
+                                            a->pil_start, a->sorted_pt, (float4*)a->csr_rec);
+    else if (env_flag("DFB_FILL_U", 1) == 2)
+      k_fill_csr<2><<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pt_xyz, pil_loc, blk_base,
+                                            a->pil_start, a->sorted_pt, (float4*)a->csr_rec);
+    else
+      k_fill_csr<1><<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pt_xyz, pil_loc, blk_base,
+                                            a->pil_start, a->sorted_pt, (float4*)a->csr_rec);
   }
   add_launches(a->Nmax > 0 ? 5 : 3);
   return check_launch("dfb_pillar_index");

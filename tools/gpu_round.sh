@@ -1,13 +1,17 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, bench line, scatter microbench, ncu launch list.  Outputs under gpurun_out/.
-set -x
+# One GPU-box visit: parity tests, microbenchmarks, bench line, scatter microbench (+ ncu launch list).  Outputs under gpurun_out/.
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
-tail -c 3000 gpurun_out/bench.log
-timeout 300 python bench.py --scatter-only > gpurun_out/scatter.log 2> gpurun_out/scatter.err; echo "scatter rc=$?"
+T="timeout -s KILL"
+$T 300 python -m pytest tests/test_gpu_tensorcore.py -x -q -k "streaming or upsample or bn_gelu" > gpurun_out/pytest_new.log 2>&1; echo "pytest_new rc=$?"
+tail -4 gpurun_out/pytest_new.log
+$T 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
+$T 300 python tools/elem_bench.py > gpurun_out/elem_bench.log 2>&1; echo "elem rc=$?"; cat gpurun_out/elem_bench.log
+$T 300 python bench.py --scatter-only > gpurun_out/scatter.log 2> gpurun_out/scatter.err; echo "scatter rc=$?"
 cat gpurun_out/scatter.log
-DFB_PROFILE=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+$T 600 python bench.py --no-scatter > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
+head -c 1500 gpurun_out/bench.log
+$T 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+  --log-file gpurun_out/scatter_launches.csv python bench.py --scatter-only --steps 1 > gpurun_out/scatter_ncu.log 2>&1; echo "ncu scatter rc=$?"
+DFB_PROFILE=1 $T 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-scatter --no-e2e > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
