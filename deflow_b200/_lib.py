@@ -31,7 +31,7 @@ class IndexArgs(C.Structure):
                 ("pil_cnt", C.c_void_p), ("pil_coor", C.c_void_p), ("pil_pix", C.c_void_p),
                 ("pil_start", C.c_void_p), ("sorted_pt", C.c_void_p), ("csr_rec", C.c_void_p),
                 ("scan_ws", C.c_void_p), ("tickets", C.c_void_p), ("zero_base", C.c_void_p),
-                ("zero_bytes", C.c_longlong)]
+                ("zero_bytes", C.c_longlong), ("occ", C.c_void_p)]
 
 
 class PfnArgs(C.Structure):
@@ -120,6 +120,7 @@ def _declare(lib):
         "dfb_pfn_forward": [C.POINTER(PfnArgs), vp],
         "dfb_pfn_backward": [C.POINTER(PfnBwdArgs), vp],
         "dfb_zero_fill": [vp, i64, i32, vp],
+        "dfb_clear_rows": [vp, i32, vp, vp, i32, i64, vp],
         "dfb_decoder_gather": [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, i32, vp],
         "dfb_decoder_gather_backward": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
         "dfb_flow_loss": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
@@ -156,7 +157,7 @@ def _declare(lib):
 
 EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size", "dfb_dynamic_voxelize_forward",
            "dfb_scatter_index", "dfb_scatter_reduce", "dfb_dynamic_point_to_voxel_backward", "dfb_index_workspace",
-           "dfb_index_scan_workspace", "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_zero_fill", "dfb_decoder_gather",
+           "dfb_index_scan_workspace", "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_zero_fill", "dfb_clear_rows", "dfb_decoder_gather",
            "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_split_bf16x2", "dfb_conv2d", "dfb_conv2d_wgrad",
            "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",

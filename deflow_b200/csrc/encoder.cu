@@ -643,6 +643,18 @@ __global__ void __launch_bounds__(256) k_zero_fill(uint4* __restrict__ p, size_t
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
 }
 
+// rows of 16-byte vectors: row r = pix[r], v16 vectors each
+__global__ void __launch_bounds__(256) k_clear_rows(uint4* __restrict__ image, int v16, const int* __restrict__ pix,
+                                                    const int* __restrict__ counts, int count_index, long long cap) {
+  const long long n = min((long long)counts[count_index], cap);
+  const long long total = n * v16;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / v16;
+    image[(size_t)__ldg(pix + r) * v16 + (e - r * v16)] = z;
+  }
+}
+
 static PfnGeom make_geom(const dfb_pfn_args* a) {
   PfnGeom G;
   G.vx = a->voxel_size[0]; G.vy = a->voxel_size[1]; G.vz = a->voxel_size[2];
@@ -663,6 +675,17 @@ extern "C" int dfb_zero_fill(void* ptr, long long bytes, int blocks_per_sm, void
                                                                             (int)(bytes - (long long)n16 * 16));
   add_launches(1);
   return check_launch("dfb_zero_fill");
+}
+
+extern "C" int dfb_clear_rows(void* image, int row_bytes, const int* pix, const int* counts, int count_index, long long cap,
+                              void* stream_) {
+  if (!image || !pix || !counts || row_bytes <= 0 || row_bytes % 16 || ((uintptr_t)image & 15)) {
+    set_error("dfb_clear_rows: rows must be 16-byte multiples of a 16-byte aligned image"); return DFB_ERR_ARG;
+  }
+  if (cap <= 0) return DFB_OK;
+  k_clear_rows<<<sm_count() * 8, 256, 0, (cudaStream_t)stream_>>>((uint4*)image, row_bytes / 16, pix, counts, count_index, cap);
+  add_launches(1);
+  return check_launch("dfb_clear_rows");
 }
 
 extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {

@@ -89,6 +89,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
 
   if (warp == 8) {
     // ------------------------------------------------------------------ control: weights once, then MMA issue
+    // The whole warp runs this code (warp-uniform control flow keeps descriptors and loop state in uniform registers);
+    // lane 0 alone issues TMA, one elected lane issues the MMAs.  Under `if (lane == 0)` every tcgen05.mma cost ~30 SASS
+    // instructions on one thread -- more than the MMA itself takes.
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, 3 * 32768 + 3 * 16384 + 3 * 4096);
       for (int c = 0; c < 3; ++c) {
@@ -96,41 +99,47 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
         tma_load_2d(smem + GF_WQ + c * 16384, &maps.wq, bar_w, c * 64, 0);
         tma_load_2d(smem + GF_W1 + c * 4096, &maps.w1, bar_w, c * 64, 0);
       }
-      mbar_wait(bar_w, 0);
-      uint32_t use_a = 0;
-      const uint32_t a_h = smem_u32(smem + GF_AH), a_x = smem_u32(smem + GF_AX);
-      // slot >= 0: the A_H tile holds bf16(h) entering iteration `slot` (or the final state): save it for the backward
-      auto gemm = [&](uint32_t w_base, uint32_t w_chunk_bytes, int N, uint32_t dcol, int row0, int slot, bool save_x) {
-        mbar_wait(bar_a, use_a & 1); ++use_a;
-        tc_fence_after();
-        const bool st = P.save && slot >= 0;
-        if (st) {
-          tma_store_3d(&maps.h, smem + GF_AH, 0, row0, slot);
-          tma_store_3d(&maps.h, smem + GF_AH + 16384, 64, row0, slot);
-          if (save_x) tma_store_3d(&maps.x, smem + GF_AX, 0, row0, 0);
-          tma_store_commit();
-        }
-        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const uint64_t ad = make_smem_desc(c < 2 ? a_h + c * 16384 : a_x, 16, 1024, 2);
-          const uint64_t bd = make_smem_desc(w_base + c * w_chunk_bytes, 16, 1024, 2);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + dcol, ad + 2 * k, bd + 2 * k, idesc, (c | k) != 0);
-        }
-        if (st) tma_store_wait_read();  // the workers overwrite the tile after the commit below
-        umma_commit(bar_d);
-      };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = tile * 128;
-        for (int it = 0; it < P.iters; ++it) {
-          gemm(smem_u32(smem + GF_WZR), 32768, 256, 0, row0, it, it == 0);   // z | r pre-activations -> columns 0..255
-          gemm(smem_u32(smem + GF_WQ), 16384, 128, 256, row0, -1, false);    // q pre-activation      -> columns 256..383
-        }
-        gemm(smem_u32(smem + GF_W1), 4096, 32, 384, row0, P.iters, P.iters == 0);  // MLP hidden layer -> columns 384..415
-      }
-      tma_store_wait_all();
     }
+    __syncwarp();
+    mbar_wait(bar_w, 0);
+    uint32_t use_a = 0;
+    // K-major SWIZZLE_128B descriptors as (lo, hi) halves: lo = start >> 4 | LBO(16 B) << 16, hi constant
+    const uint32_t d_hi = (uint32_t)(make_smem_desc(0, 16, 1024, 2) >> 32);
+    const uint32_t lo0 = (uint32_t)make_smem_desc(0, 16, 1024, 2);
+    const uint32_t a_h = lo0 | ((smem_u32(smem + GF_AH) & 0x3FFFFu) >> 4), a_x = lo0 | ((smem_u32(smem + GF_AX) & 0x3FFFFu) >> 4);
+    // slot >= 0: the A_H tile holds bf16(h) entering iteration `slot` (or the final state): save it for the backward
+    auto gemm = [&](uint32_t w_off, uint32_t w_chunk_bytes, uint32_t idesc, uint32_t dcol, int row0, int slot, bool save_x) {
+      mbar_wait(bar_a, use_a & 1); ++use_a;
+      tc_fence_after();
+      const bool st = P.save && slot >= 0;
+      if (st && lane == 0) {
+        tma_store_3d(&maps.h, smem + GF_AH, 0, row0, slot);
+        tma_store_3d(&maps.h, smem + GF_AH + 16384, 64, row0, slot);
+        if (save_x) tma_store_3d(&maps.x, smem + GF_AX, 0, row0, 0);
+        tma_store_commit();
+      }
+      const uint32_t w_lo = lo0 | ((smem_u32(smem + w_off) & 0x3FFFFu) >> 4);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uint32_t ad = c < 2 ? a_h + (uint32_t)c * (16384u >> 4) : a_x;
+        const uint32_t bd = w_lo + (uint32_t)c * (w_chunk_bytes >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi_warp(tmem + dcol, ad + 2 * k, d_hi, bd + 2 * k, d_hi, idesc, (uint32_t)((c | k) != 0));
+      }
+      if (st && lane == 0) tma_store_wait_read();  // the workers overwrite the tile after the commit below
+      __syncwarp();
+      umma_commit_warp(bar_d);
+    };
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int row0 = tile * 128;
+      for (int it = 0; it < P.iters; ++it) {
+        gemm(GF_WZR, 32768, make_idesc_bf16(128, 256, 0, 0), 0, row0, it, it == 0);   // z | r pre-activations -> columns 0..255
+        gemm(GF_WQ, 16384, make_idesc_bf16(128, 128, 0, 0), 256, row0, -1, false);    // q pre-activation      -> columns 256..383
+      }
+      gemm(GF_W1, 4096, make_idesc_bf16(128, 32, 0, 0), 384, row0, P.iters, P.iters == 0);  // MLP hidden layer -> columns 384..415
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ workers
     const int q = warp & 3, half = warp >> 2;
@@ -401,83 +410,100 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
   constexpr uint32_t C_ZR = 0, C_Q = 256, C_DX = 448;
 
   if (warp == 8) {
+    // whole-warp control flow, lane 0 issues TMA, one elected lane issues the MMAs (see k_gru_fused_fwd)
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, 3 * 32768 + 3 * 16384);
       for (int c = 0; c < 3; ++c) {
         tma_load_2d(smem + GB_WZR + c * 32768, &maps.wzr, bar_w, c * 64, 0);
         tma_load_2d(smem + GB_WQ + c * 16384, &maps.wq, bar_w, c * 64, 0);
       }
-      mbar_wait(bar_w, 0);
-      uint32_t use_a = 0, use_d = 0, use_h = 0;
-      uint8_t* sp = smem + GB_P; uint8_t* sq = smem + GB_Q; uint8_t* sx = smem + GB_X;
-      const uint32_t t_p = smem_u32(sp), t_q = smem_u32(sq), t_x = smem_u32(sx);
-      const uint32_t wzr = smem_u32(smem + GB_WZR), wq = smem_u32(smem + GB_WQ);
-      auto wait_a = [&]() { mbar_wait(bar_a, use_a & 1); ++use_a; tc_fence_after(); };
-      auto commit_d = [&]() { umma_commit(bar_d); ++use_d; };
-      auto gemm_fwd = [&](uint32_t w_base, uint32_t w_chunk, int N, uint32_t dcol) {
-        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    }
+    __syncwarp();
+    mbar_wait(bar_w, 0);
+    uint32_t use_a = 0, use_d = 0, use_h = 0;
+    uint8_t* sp = smem + GB_P; uint8_t* sq = smem + GB_Q; uint8_t* sx = smem + GB_X;
+    const uint32_t t_p = smem_u32(sp), t_q = smem_u32(sq), t_x = smem_u32(sx);
+    const uint32_t wzr = smem_u32(smem + GB_WZR), wq = smem_u32(smem + GB_WQ);
+    auto lo_of = [](uint32_t addr, uint32_t lbo_bytes) { return ((addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); };
+    const uint32_t d_hi = (uint32_t)(make_smem_desc(0, 16, 1024, 2) >> 32);   // SBO 1024, SWIZZLE_128B: shared by all operands
+    auto wait_a = [&]() { mbar_wait(bar_a, use_a & 1); ++use_a; tc_fence_after(); };
+    auto commit_d = [&]() { umma_commit_warp(bar_d); ++use_d; };
+    auto gemm_fwd = [&](uint32_t w_base, uint32_t w_chunk, uint32_t idesc, uint32_t dcol) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const uint64_t ad = make_smem_desc(c < 2 ? t_p + c * 16384 : t_x, 16, 1024, 2);
-          const uint64_t bd = make_smem_desc(w_base + c * w_chunk, 16, 1024, 2);
+      for (int c = 0; c < 3; ++c) {
+        const uint32_t ad = lo_of(c < 2 ? t_p + c * 16384 : t_x, 16);
+        const uint32_t bd = lo_of(w_base + c * w_chunk, 16);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + dcol, ad + 2 * k, bd + 2 * k, idesc, (c | k) != 0);
-        }
-      };
-      // D[128, N'] (+)= G[128, 128] (A tile pair, K-major) x W[rows row0..row0+127][columns of chunks c0..]: the weight
-      // tiles are read MN-major (transposed view): K' = weight rows, N' = weight columns.
-      auto gemm_dgrad = [&](uint32_t a_tile, uint32_t w_base, uint32_t w_chunk, int row0, int c0, int N, uint32_t dcol,
-                            bool accumulate) {
-        const uint32_t idesc = make_idesc_bf16(128, N, 0, 1);
-        const uint32_t b0 = w_base + c0 * w_chunk + row0 * 128;
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi_warp(tmem + dcol, ad + 2 * k, d_hi, bd + 2 * k, d_hi, idesc, (uint32_t)((c | k) != 0));
+      }
+    };
+    // D[128, N'] (+)= G[128, 128] (A tile pair, K-major) x W[rows row0..row0+127][columns of chunks c0..]: the weight
+    // tiles are read MN-major (transposed view): K' = weight rows, N' = weight columns.
+    auto gemm_dgrad = [&](uint32_t a_tile, uint32_t w_base, uint32_t w_chunk, int row0, int c0, uint32_t idesc, uint32_t dcol,
+                          bool accumulate) {
+      const uint32_t b0 = w_base + c0 * w_chunk + row0 * 128;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint64_t ad = make_smem_desc(a_tile + (i >> 2) * 16384, 16, 1024, 2) + 2 * (i & 3);
-          const uint64_t bd = make_smem_desc(b0 + i * 2048, w_chunk, 1024, 2);
-          umma_bf16(tmem + dcol, ad, bd, idesc, accumulate || i != 0);
-        }
-      };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = tile * 128;
-        for (int it = P.iters - 1; it >= 0; --it) {
-          const bool first = it == P.iters - 1;
-          // P (and X on the first iteration) are free: the previous G4 was waited for below
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t ad = lo_of(a_tile + (i >> 2) * 16384, 16) + 2 * (i & 3);
+        const uint32_t bd = lo_of(b0 + i * 2048, w_chunk);
+        umma_bf16_lohi_warp(tmem + dcol, ad, d_hi, bd, d_hi, idesc, (uint32_t)(accumulate || i != 0));
+      }
+    };
+    constexpr uint32_t I_F256 = make_idesc_bf16(128, 256, 0, 0), I_F128 = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t I_D128 = make_idesc_bf16(128, 128, 0, 1), I_D64 = make_idesc_bf16(128, 64, 0, 1);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int row0 = tile * 128;
+      for (int it = P.iters - 1; it >= 0; --it) {
+        const bool first = it == P.iters - 1;
+        // P (and X on the first iteration) are free: the previous G4 was waited for below
+        if (lane == 0) {
           mbar_arrive_expect_tx(bar_h, 32768 + (first ? 16384 : 0));
           tma_load_3d(sp, &maps.h, bar_h, 0, row0, it);
           tma_load_3d(sp + 16384, &maps.h, bar_h, 64, row0, it);
           if (first) tma_load_3d(sx, &maps.x, bar_h, 0, row0, 0);
-          mbar_wait(bar_h, use_h & 1); ++use_h;
-          wait_a();  // workers are done with the TMEM contents of the previous stage
-          gemm_fwd(wzr, 32768, 256, C_ZR);
-          commit_d();
-          wait_a();  // P = r * h_t
+        }
+        __syncwarp();
+        mbar_wait(bar_h, use_h & 1); ++use_h;
+        wait_a();  // workers are done with the TMEM contents of the previous stage
+        gemm_fwd(wzr, 32768, I_F256, C_ZR);
+        commit_d();
+        wait_a();  // P = r * h_t
+        if (lane == 0) {
           tma_store_3d(&maps.rh, sp, 0, row0, it); tma_store_3d(&maps.rh, sp + 16384, 64, row0, it);
           tma_store_commit();
-          gemm_fwd(wq, 16384, 128, C_Q);
-          tma_store_wait_read();
-          commit_d();
-          wait_a();  // P = dq_pre, Q = dz_pre
+        }
+        gemm_fwd(wq, 16384, I_F128, C_Q);
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        commit_d();
+        wait_a();  // P = dq_pre, Q = dz_pre
+        if (lane == 0) {
           tma_store_3d(&maps.dq, sp, 0, row0, it); tma_store_3d(&maps.dq, sp + 16384, 64, row0, it);
           tma_store_3d(&maps.dzr, sq, 0, row0, it); tma_store_3d(&maps.dzr, sq + 16384, 64, row0, it);
           tma_store_commit();
-          gemm_dgrad(t_p, wq, 16384, 0, 0, 128, C_Q, false);        // d_rh  = dq Wq[:, 0:128]
-          gemm_dgrad(t_p, wq, 16384, 0, 2, 64, C_DX, !first);       // d_x  += dq Wq[:, 128:192]
-          gemm_dgrad(t_q, wzr, 32768, 0, 0, 128, C_ZR, false);      // d_h   = dz Wz[:, 0:128]
-          gemm_dgrad(t_q, wzr, 32768, 0, 2, 64, C_DX, true);        // d_x  += dz Wz[:, 128:192]
-          tma_store_wait_read();
-          commit_d();
-          wait_a();  // P = dr_pre
+        }
+        gemm_dgrad(t_p, wq, 16384, 0, 0, I_D128, C_Q, false);        // d_rh  = dq Wq[:, 0:128]
+        gemm_dgrad(t_p, wq, 16384, 0, 2, I_D64, C_DX, !first);       // d_x  += dq Wq[:, 128:192]
+        gemm_dgrad(t_q, wzr, 32768, 0, 0, I_D128, C_ZR, false);      // d_h   = dz Wz[:, 0:128]
+        gemm_dgrad(t_q, wzr, 32768, 0, 2, I_D64, C_DX, true);        // d_x  += dz Wz[:, 128:192]
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        commit_d();
+        wait_a();  // P = dr_pre
+        if (lane == 0) {
           tma_store_3d(&maps.dzr, sp, 128, row0, it); tma_store_3d(&maps.dzr, sp + 16384, 192, row0, it);
           tma_store_commit();
-          gemm_dgrad(t_p, wzr, 32768, 128, 0, 128, C_ZR, true);     // d_h  += dr Wr[:, 0:128]
-          gemm_dgrad(t_p, wzr, 32768, 128, 2, 64, C_DX, true);      // d_x  += dr Wr[:, 128:192]
-          tma_store_wait_read();
-          commit_d();
-          mbar_wait(bar_d, (use_d - 1) & 1);  // G4 has finished reading P before the next h_t lands in it
         }
+        gemm_dgrad(t_p, wzr, 32768, 128, 0, I_D128, C_ZR, true);     // d_h  += dr Wr[:, 0:128]
+        gemm_dgrad(t_p, wzr, 32768, 128, 2, I_D64, C_DX, true);      // d_x  += dr Wr[:, 128:192]
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        commit_d();
+        mbar_wait(bar_d, (use_d - 1) & 1);  // G4 has finished reading P before the next h_t lands in it
       }
-      tma_store_wait_all();
     }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
   } else {
     const int q = warp & 3, half = warp >> 2;
     const int m = q * 32 + lane;

@@ -110,9 +110,12 @@ def pillar_index(points: torch.Tensor, voxel_size, pc_range) -> PillarIndex:
     idx.sorted_pt = torch.empty(cap, **i32)
     idx.csr_rec = torch.empty((cap, 4), dtype=torch.float32, device=dev)
     nw, nb = max(F * words.value, 1), max(F * max(blocks.value, 1), 1)
-    # everything that must start at zero lives in ONE allocation (one memset): bitmap | pil_cnt | blk_cnt | tickets
-    zero = torch.empty(nw + pil_cap + nb + 4, **i32)
-    bitmap, idx.pil_cnt, blk, tickets = zero[:nw], zero[nw:nw + pil_cap], zero[nw + pil_cap:nw + pil_cap + nb], zero[-4:]
+    # everything that must start at zero lives in ONE allocation (one memset): occ bytes | pil_cnt | blk_cnt | tickets.
+    # occ = occupancy byte map (32 bytes per bitmap word); the bitmap itself is written by the scan kernel.
+    zero = torch.empty(8 * nw + pil_cap + nb + 4, **i32)
+    occ = zero[:8 * nw]
+    idx.pil_cnt, blk, tickets = zero[8 * nw:8 * nw + pil_cap], zero[8 * nw + pil_cap:8 * nw + pil_cap + nb], zero[-4:]
+    bitmap = torch.empty(nw, **i32)
     word_rank = torch.empty(nw, **i32)
     scan_ws = torch.empty(max(int(lib.dfb_index_scan_workspace(F, words.value, pil_cap)), 1), **i32)
     slot = torch.empty(cap, **i32)
@@ -128,6 +131,7 @@ def pillar_index(points: torch.Tensor, voxel_size, pc_range) -> PillarIndex:
     a.pil_start, a.sorted_pt, a.csr_rec = idx.pil_start.data_ptr(), idx.sorted_pt.data_ptr(), idx.csr_rec.data_ptr()
     a.scan_ws, a.tickets = scan_ws.data_ptr(), tickets.data_ptr()
     a.zero_base, a.zero_bytes = zero.data_ptr(), zero.numel() * 4
+    a.occ = occ.data_ptr()
     check(lib.dfb_pillar_index(C.byref(a), _stream(points)), "pillar_index")
     idx._keep = (points,)
     return idx
@@ -203,6 +207,7 @@ class _PillarFeatureNet(torch.autograd.Function):
             image = torch.empty((idx.F, H, W, 32), dtype=image_dtype, device=dev)
         else:
             assert tuple(image.shape) == (idx.F, H, W, 32) and image.dtype == image_dtype and image.is_contiguous()
+            image = image.detach()   # a new tensor object on the same storage: the output is not the input itself
         a = _pfn_args(idx, H, W, training, center_off, eps, momentum, w, g, b, running_mean, running_var, pil_mean,
                       stats, bn_params, pil_feats, image, pt_mask, pil_hdr, partials, image_ready)
         check(_lib.lib().dfb_pfn_forward(C.byref(a), _stream(weight)), "pfn_forward")
@@ -235,6 +240,16 @@ class _PillarFeatureNet(torch.autograd.Function):
         ba.bwd_stats, ba.grad_accum = bwd_stats.data_ptr(), None
         check(_lib.lib().dfb_pfn_backward(C.byref(ba), _stream(w)), "pfn_backward")
         return (gw, gg, gb) + (None,) * 11
+
+
+def clear_rows(image: torch.Tensor, pix: torch.Tensor, counts: torch.Tensor, count_index: int):
+    """Zero the rows image.view(-1, C)[pix[:counts[count_index]]] (the pillars a previous forward wrote into a reused
+    pseudo-image) instead of zero-filling the whole canvas."""
+    _need_cuda(image, "clear_rows")
+    assert image.is_contiguous() and pix.dtype == torch.int32 and counts.dtype == torch.int32
+    row_bytes = image.shape[-1] * image.element_size()
+    check(_lib.lib().dfb_clear_rows(image.data_ptr(), row_bytes, pix.data_ptr(), counts.data_ptr(), count_index,
+                                    pix.numel(), _stream(image)), "clear_rows")
 
 
 def pillar_feature_net(weight, gamma, beta, idx, running_mean, running_var, training, eps, momentum, center_off,

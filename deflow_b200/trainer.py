@@ -20,6 +20,11 @@ class TrainStep:
         self.loss_fn = loss_fn
         self.clip = gradient_clip_val
         self.grads = dd.GradAverager(model.parameters())
+        # one forward + backward per call: the pseudo-image of a step is dead before the next step's embed(), so the
+        # embedder may keep its canvas and clear only the previous step's pillar rows (encoder.DynamicEmbedder.reuse_canvas)
+        emb = getattr(model, "embedder", None)
+        if emb is not None and hasattr(emb, "reuse_canvas"):
+            emb.reuse_canvas = True
         self.opt = torch.optim.Adam(self.grads.params, lr=lr, fused=self.grads.flat.is_cuda)  # trainer.py:173-175
 
     def __call__(self, batch) -> torch.Tensor:

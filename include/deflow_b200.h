@@ -107,6 +107,8 @@ typedef struct {
   unsigned* tickets; /* workspace [2], zeroed inside */
   void* zero_base;   /* optional: when bitmap | pil_cnt | blk_cnt | tickets are carved from ONE allocation, its base ... */
   long long zero_bytes; /* ... and size, so that a single memset clears them (NULL: four memsets) */
+  unsigned char* occ;   /* optional occupancy BYTE map [F * 32 * bitmap words] (part of zero_base, or zeroed inside): points mark
+                           their cell with a plain byte store instead of an atomicOr on the bitmap; the scan packs it to bits */
 } dfb_index_args;
 
 int dfb_index_workspace(int F, int Nmax, const float* voxel_size, const float* range,
@@ -168,6 +170,10 @@ int dfb_pfn_forward(const dfb_pfn_args* args, void* stream);
 /* Dense zero fill (the PointPillarsScatter canvas) with blocks_per_sm small blocks per SM, meant to run on a second
  * stream under other kernels; ptr 16-byte aligned. */
 int dfb_zero_fill(void* ptr, long long bytes, int blocks_per_sm, void* stream);
+/* Sparse clear of a pseudo-image that is reused from call to call: zero the row_bytes-byte rows pix[0 .. n) with
+ * n = min(counts[count_index], cap) -- the pillars the PREVIOUS forward wrote (its pil_pix / counts) -- instead of
+ * zero-filling the whole dense canvas again (PointPillarsScatter's zeros() + index_put, encoder.py:135-141). */
+int dfb_clear_rows(void* image, int row_bytes, const int* pix, const int* counts, int count_index, long long cap, void* stream);
 
 typedef struct {
   dfb_pfn_args fwd;         /* same buffers as the forward call */

@@ -420,3 +420,25 @@ def test_full_size_properties_config2_shape():
     feats = torch.randn((n1, 32), device=DEV)
     sf = ops.dynamic_point_to_voxel_forward(feats, coors1, "sum")[0]
     np.testing.assert_allclose(sf.double().sum(0).cpu().numpy(), feats.double().sum(0).cpu().numpy(), rtol=1e-6, atol=1e-3)
+
+
+def test_reused_canvas_matches_fresh_canvas():
+    """DynamicEmbedder.reuse_canvas: the persistent pseudo-image with a sparse clear of the previous call's pillar rows
+    equals a freshly zero-filled canvas, call after call, for changing inputs (PointPillarsScatter zero canvas,
+    OSF/src/models/basic/encoder.py:135-141)."""
+    import deflow_b200 as d
+    from deflow_b200 import synth
+    vs, rg = [0.2, 0.2, 6], [-51.2, -51.2, -3, 51.2, 51.2, 3]
+    torch.manual_seed(3)
+    emb = d.DynamicEmbedder(vs, [512, 512], rg, 32).to("cuda").eval()
+    ref = d.DynamicEmbedder(vs, [512, 512], rg, 32).to("cuda").eval()
+    ref.load_state_dict(emb.state_dict())
+    emb.reuse_canvas = True
+    for seed, n in [(1, 3000), (2, 5000), (3, 10), (4, 4000)]:
+        b = synth.make_batch(2, n, seed=seed)
+        pts = torch.cat([b["pc0"], b["pc1"]], 0).cuda()
+        with torch.no_grad():
+            got, idx = emb.embed(pts, torch.bfloat16)
+            want, _ = ref.embed(pts, torch.bfloat16)
+        assert torch.equal(got, want)
+        assert int((got.float().abs().sum(-1) > 0).sum()) <= idx.pil_off(idx.F)
