@@ -101,7 +101,10 @@ constexpr int EPI_SMEM = 4 * EPI_STAGE_BYTES;
 //     lane issues a TMA store of the [32 ch x 8 x 4] box -- fully coalesced, clipped at the image border by the
 //     hardware.  (A lane-per-pixel st.global touches 32 different 128-byte lines per instruction.)
 //   * fp32 output (parity mode): direct stores.
-template <int N>
+// PAIR (k_conv_igemm_halo_pair): the N = 128 accumulator columns are two 64-channel halves; lane (r, c) holds output
+// pixel (2r, c) of a 32 x 8 tile in columns 0..63 and pixel (2r + 1, c) in columns 64..127.  The output tensor map is
+// then 5-D [ch, x, row parity, row / 2, n] and a store box is [32 ch, 8, 1, 4, 1].
+template <int N, bool PAIR = false>
 __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUtensorMap* out_map, uint32_t tmem_base,
                                                uint64_t* acc_full, uint64_t* acc_empty, float* s_stats,
                                                const float* s_bias, uint8_t* stage_all, int warp, int lane) {
@@ -118,20 +121,24 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
   uint32_t acc_phase = 0;
   for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
     const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
-    const int y = ty * TILE_H + r, x = tx * TILE_W + c;
-    const bool valid = y < P.Ht && x < P.Wt;
-    const long long off = (long long)n * P.out_img + (long long)(y * P.sy + P.oy) * P.out_row +
-                          (long long)(x * P.sx + P.ox) * P.out_pix;
+    const int y0 = PAIR ? ty * 2 * TILE_H + 2 * r : ty * TILE_H + r, x = tx * TILE_W + c;
+    const long long off0 = (long long)n * P.out_img + (long long)(y0 * P.sy + P.oy) * P.out_row +
+                           (long long)(x * P.sx + P.ox) * P.out_pix;
     mbar_wait(&acc_full[acc], acc_phase);
     tc_fence_after();
 #pragma unroll 1
     for (int col = 0; col < N; col += 32) {
+      const int half = PAIR ? col / (N / 2) : 0;       // output row parity of this column block
+      const int ch0 = PAIR ? col % (N / 2) : col;      // first output channel of this column block
+      const int y = y0 + half;
+      const bool valid = y < P.Ht && x < P.Wt;
+      const long long off = off0 + (long long)half * P.out_row;
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + col, v);
       if (P.bias) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col + i);
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch0 + i);
           v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
         }
       }
@@ -156,15 +163,15 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
           s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
           s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
           if (lane < 16) {
-            atomicAdd(&s_stats[col + h * 16 + lane], s1);
-            if (!P.stats_sum_only) atomicAdd(&s_stats[N + col + h * 16 + lane], s2);
+            atomicAdd(&s_stats[ch0 + h * 16 + lane], s1);
+            if (!P.stats_sum_only) atomicAdd(&s_stats[(PAIR ? N / 2 : N) + ch0 + h * 16 + lane], s2);
           }
           __syncwarp();
         }
       }
       if (P.out_fp32) {
         if (valid) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off + col);
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off + ch0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
@@ -181,7 +188,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(out_map, stg, col, tx * TILE_W, ty * TILE_H + 4 * q, n);
+          if (PAIR) tma_store_5d(out_map, stg, ch0, tx * TILE_W, half, ty * TILE_H + 4 * q, n);
+          else tma_store_4d(out_map, stg, col, tx * TILE_W, ty * TILE_H + 4 * q, n);
           tma_store_commit();
         }
         store_pending = true;
@@ -457,6 +465,202 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-pair halo variant for 64 output channels.  An M = 128 x N = 64 MMA is bound by the A-operand fetch from shared
+// memory (~70 cycles for 32 cycles of math, tools/mma_chain_bench.cu), so the N = 64 layers ran at half the tensor
+// rate.  Here one MMA produces TWO output rows: the 128 A rows are the 16 EVEN rows x 8 columns of a 32 x 8 pixel tile
+// (8-pixel groups 2 halo rows apart), the accumulator has 128 columns = [output row 2r | output row 2r + 1] x 64
+// channels, and the B operand of halo row offset hy is [W(ky = hy) | W(ky = hy - 1)] -- two taps that sit next to each
+// other in shared memory, one N = 128 operand.  hy = 0 and hy = 3 touch only one of the two output rows (N = 64 MMAs
+// into one half of the accumulator).  Per 64-channel chunk and kx: 2 x N=128 + 2 x N=64 MMA groups instead of 6 x N=64
+// for the same 256 pixels.  Weight slot p of a kx triple holds ky = 2 - p (forward) or ky = p (data gradient, flipped
+// taps), so that hy = 1 reads slots (1, 2), hy = 2 slots (0, 1), hy = 0 slot 2 and hy = 3 slot 0 in both directions.
+struct HaloPairCfg {
+  static constexpr int N = 64;                                     // output channels
+  static constexpr int ROWS = 2 * TILE_H + 2;                      // 34 halo rows
+  static constexpr int HALO_BYTES = 43 * 1024;                     // 34 x 10 pixels x 128 B = 43520, 1024-aligned
+  static constexpr int W_BYTES = N * 128;                          // one tap x one 64-channel chunk
+  static constexpr int HALO_STAGES = 2;
+  static constexpr int W_STAGES = 15;                              // five kx triples
+  static constexpr int TILE_BYTES = HALO_STAGES * HALO_BYTES + W_STAGES * W_BYTES;
+  static constexpr int SMEM = TILE_BYTES + EPI_SMEM + 1024 + 512 + 3 * N * 4;
+  static constexpr int TMEM_COLS = 4 * N;                          // two accumulators of 2 x 64 columns
+};
+
+__global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo_pair(const __grid_constant__ IgemmMaps maps,
+                                                                           const __grid_constant__ IgemmParams P) {
+  using Cfg = HaloPairCfg;
+  constexpr int N = Cfg::N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* halos = smem;
+  uint8_t* wts = smem + Cfg::HALO_STAGES * Cfg::HALO_BYTES;
+  uint8_t* epi_stage = smem + Cfg::TILE_BYTES;              // 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_SMEM);
+  uint64_t* h_full = bars;                                  // [HALO_STAGES]
+  uint64_t* h_empty = h_full + Cfg::HALO_STAGES;            // [HALO_STAGES]
+  uint64_t* w_full = h_empty + Cfg::HALO_STAGES;            // [W_STAGES]
+  uint64_t* w_empty = w_full + Cfg::W_STAGES;               // [W_STAGES]
+  uint64_t* acc_full = w_empty + Cfg::W_STAGES;             // [2]
+  uint64_t* acc_empty = acc_full + 2;                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(epi_stage + EPI_SMEM + 512);
+  float* s_bias = s_stats + 2 * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t halo_tx = (uint32_t)Cfg::ROWS * (uint32_t)P.halo_pitch * 128u;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < MAX_AMAPS; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < Cfg::HALO_STAGES; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); }
+    for (int i = 0; i < Cfg::W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int hs = 0, ws = 0;
+      uint32_t hph = 0, wph = 0;
+      bool first_tile = true;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
+        const int x0 = tx * TILE_W - 1, y0 = ty * 2 * TILE_H - 1;
+        for (int s = 0; s < P.nsteps; ++s) {
+          const KStep st = P.steps[s];
+          mbar_wait(&h_empty[hs], hph ^ 1);
+          mbar_arrive_expect_tx(&h_full[hs], halo_tx);
+          tma_load_4d(halos + hs * Cfg::HALO_BYTES, &maps.a[st.map], &h_full[hs], st.c0, x0, y0, n);
+          if (++hs == Cfg::HALO_STAGES) { hs = 0; hph ^= 1; }
+          if (!P.w_resident || first_tile) {
+            for (int hx = 0; hx < 3; ++hx) {
+              for (int p = 0; p < 3; ++p) {
+                const int ky = P.halo_flip ? p : 2 - p, kx = P.halo_flip ? 2 - hx : hx;
+                mbar_wait(&w_empty[ws], wph ^ 1);
+                mbar_arrive_expect_tx(&w_full[ws], Cfg::W_BYTES);
+                tma_load_2d(wts + ws * Cfg::W_BYTES, &maps.b, &w_full[ws], st.wk + (ky * 3 + kx) * P.tap_k_stride, 0);
+                if (++ws == Cfg::W_STAGES) { ws = 0; wph ^= 1; }
+              }
+            }
+          }
+        }
+        first_tile = false;
+      }
+    }
+  } else if (warp == 1) {
+    // whole-warp issue loop, (lo, hi) descriptors (see k_conv_igemm_halo)
+    constexpr uint32_t idesc128 = make_idesc_bf16(TILE_M, 2 * N, 0, 0), idesc64 = make_idesc_bf16(TILE_M, N, 0, 0);
+    const uint64_t a_proto = make_smem_desc(0, 16, 2u * (uint32_t)P.halo_pitch * 128u, 2, 0);   // 8-pixel groups two halo rows apart
+    const uint64_t b_proto = make_smem_desc(0, 16, 1024, 2);
+    const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+    const uint32_t a_lo0 = (uint32_t)a_proto | ((smem_u32(halos) & 0x3FFFFu) >> 4);
+    const uint32_t b_lo0 = (uint32_t)b_proto | ((smem_u32(wts) & 0x3FFFFu) >> 4);
+    const uint32_t row16 = (uint32_t)P.halo_pitch * 8u;      // one halo row in 16-byte units
+    constexpr uint32_t slot16 = (uint32_t)(Cfg::W_BYTES >> 4);
+    const bool resident = P.w_resident != 0;
+    int hs = 0, ws = 0, acc = 0;
+    uint32_t hph = 0, wph = 0, acc_phase = 0;
+    bool first_tile = true;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * 2 * N;
+      uint32_t accum = 0u;
+      if (resident) ws = 0;
+      for (int s = 0; s < P.nsteps; ++s) {
+        mbar_wait(&h_full[hs], hph);
+        tc_fence_after();
+        const uint32_t ah = a_lo0 + (uint32_t)hs * (uint32_t)(Cfg::HALO_BYTES >> 4);
+#pragma unroll
+        for (int hx = 0; hx < 3; ++hx) {
+          if (!resident || first_tile) {
+            mbar_wait(&w_full[ws], wph); mbar_wait(&w_full[ws + 1], wph); mbar_wait(&w_full[ws + 2], wph);
+            tc_fence_after();
+          }
+          const uint32_t b0 = b_lo0 + (uint32_t)ws * slot16;
+          const uint32_t a0 = ah + (uint32_t)hx * 8u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // hy = 1: rows (2r | 2r+1) <- taps in slots (1 | 2); the very first MMA overwrites
+            umma_bf16_lohi_warp(d, a0 + row16 + 2 * k, a_hi, b0 + slot16 + 2 * k, b_hi, idesc128, accum | (uint32_t)(k > 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // hy = 2: slots (0 | 1)
+            umma_bf16_lohi_warp(d, a0 + 2 * row16 + 2 * k, a_hi, b0 + 2 * k, b_hi, idesc128, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // hy = 0: even output rows only <- slot 2
+            umma_bf16_lohi_warp(d, a0 + 2 * k, a_hi, b0 + 2 * slot16 + 2 * k, b_hi, idesc64, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // hy = 3: odd output rows only <- slot 0
+            umma_bf16_lohi_warp(d + N, a0 + 3 * row16 + 2 * k, a_hi, b0 + 2 * k, b_hi, idesc64, 1u);
+          accum = 1u;
+          if (!resident) { umma_commit_warp(&w_empty[ws]); umma_commit_warp(&w_empty[ws + 1]); umma_commit_warp(&w_empty[ws + 2]); }
+          ws += 3;
+          if (ws == Cfg::W_STAGES) { ws = 0; wph ^= 1; }
+        }
+        umma_commit_warp(&h_empty[hs]);
+        if (++hs == Cfg::HALO_STAGES) { hs = 0; hph ^= 1; }
+      }
+      umma_commit_warp(&acc_full[acc]);
+      first_tile = false;
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    igemm_epilogue<2 * N, true>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (P.stats) {
+    for (int i = threadIdx.x; i < (P.stats_sum_only ? N : 2 * N); i += blockDim.x) atomicAdd(&P.stats[i], (double)s_stats[i]);
+  }
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// bf16 output of the row-pair kernel as [ch, x, row parity, row / 2, n], box [32, 8, 1, 4, 1], SWIZZLE_64B
+static int build_out_map_pair(IgemmMaps& maps, const IgemmParams& P, int N) {
+  const uint64_t dims[5] = {(uint64_t)N, (uint64_t)P.Wt, 2, (uint64_t)P.Ht / 2, (uint64_t)P.n_img};
+  const uint64_t str[4] = {(uint64_t)P.out_pix * 2, (uint64_t)P.out_row * 2, (uint64_t)P.out_row * 4, (uint64_t)P.out_img * 2};
+  const uint32_t box[5] = {32, TILE_W, 1, 4, 1};
+  return make_tensor_map_bf16(&maps.out, P.out, 5, dims, str, box, 64);
+}
+
+static int launch_igemm_halo_pair(IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
+  using Cfg = HaloPairCfg;
+  if (int rc = build_out_map_pair(maps, P, Cfg::N)) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_igemm_halo_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) { set_error("igemm_halo_pair: cannot reserve %d bytes of shared memory: %s", Cfg::SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    configured = true;
+  }
+  P.tiles_y = (P.Ht + 2 * TILE_H - 1) / (2 * TILE_H);
+  P.num_tiles = P.tiles_x * P.tiles_y * P.n_img;
+  P.w_resident = (9 * P.nsteps <= Cfg::W_STAGES) ? 1 : 0;
+  int grid = sm_count();
+  if (grid > P.num_tiles) grid = P.num_tiles;
+  k_conv_igemm_halo_pair<<<grid, IGEMM_THREADS, Cfg::SMEM, st>>>(maps, P);
+  add_launches(1);
+  return check_launch("conv_igemm_halo_pair");
+}
+
+// DFB_HALO_PAIR=0 keeps the 64-channel layers on k_conv_igemm_halo<64> (A/B comparisons); default = row-pair kernel
+static bool halo_pair_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DFB_HALO_PAIR");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode != 0;
+}
+
 // Output tensor map of a launch: element (n, y, x, ch) of the tile space lives at
 // out + n*img + (y*sy+oy)*row + (x*sx+ox)*pix + ch  (bf16) -> dims [ch, x, y, n], box [32, 8, 4, 1], SWIZZLE_64B.
 static int build_out_map(IgemmMaps& maps, const IgemmParams& P, int N) {
@@ -676,7 +880,8 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
       P.dbg_base_offset = 0;
       P.halo_flip = 0;
       P.tap_k_stride = cin_total;
-      const uint32_t hbox[4] = {64, (uint32_t)P.halo_pitch, 18, 1};
+      const bool pair = N == 64 && !P.out_fp32 && !S3 && Ho % 2 == 0 && halo_pair_enabled();
+      const uint32_t hbox[4] = {64, (uint32_t)P.halo_pitch, pair ? (uint32_t)HaloPairCfg::ROWS : 18u, 1};
       int coff = 0;
       for (int i = 0; i < a->n_src; ++i) {
         const uint64_t C = a->cin[i];
@@ -695,7 +900,7 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
       P.nsteps = nsteps;
       P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
       P.num_tiles = P.tiles_x * P.tiles_y * a->n;
-      return dispatch_igemm_halo(N, maps, P, st);
+      return pair ? launch_igemm_halo_pair(maps, P, st) : dispatch_igemm_halo(N, maps, P, st);
     }
     if (s == 1) {
       for (int i = 0; i < a->n_src; ++i) {
@@ -774,14 +979,15 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
       P.dbg_base_offset = 0;
       P.halo_flip = 1;                       // gx[y, x] = sum_t W[t]^T gy[y - dy_t, x - dx_t]
       P.tap_k_stride = cout;
-      const uint32_t hbox[4] = {64, (uint32_t)P.halo_pitch, 18, 1};
+      const bool pair = N == 64 && !P.out_fp32 && !S3 && H % 2 == 0 && halo_pair_enabled();
+      const uint32_t hbox[4] = {64, (uint32_t)P.halo_pitch, pair ? (uint32_t)HaloPairCfg::ROWS : 18u, 1};
       if ((rc = mk_a(0, a->x[0], dims, str, hbox, 128))) return rc;
       for (int c0 = 0; c0 < cout; c0 += 64) P.steps[nsteps++] = KStep{0, 0, 0, 0, (int16_t)c0, (int16_t)c0};
       if ((nsteps = expand3(nsteps, K_HI)) < 0) { set_error("dfb_conv2d: too many K steps"); return DFB_ERR_UNSUPPORTED; }
       P.nsteps = nsteps;
       P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
       P.num_tiles = P.tiles_x * P.tiles_y * a->n;
-      return dispatch_igemm_halo(N, maps, P, st);
+      return pair ? launch_igemm_halo_pair(maps, P, st) : dispatch_igemm_halo(N, maps, P, st);
     }
     if (s == 1) {
       // gx[y, x] = sum_t W[t]^T gy[y - dy_t, x - dx_t]

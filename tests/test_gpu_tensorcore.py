@@ -26,6 +26,9 @@ CASES = [
     ("3x3 128->256 s2", 1, 32, 32, [128], 256, 3, 2),
     ("1x1 cat(32,32)->64", 1, 32, 32, [32, 32], 64, 1, 1),
     ("3x3 64->64 many tiles", 3, 128, 128, [64], 64, 3, 1),
+    ("3x3 64->64 two row-pair tiles, ragged", 2, 40, 24, [64], 64, 3, 1),
+    ("3x3 cat(64,64)->64 tall", 1, 96, 16, [64, 64], 64, 3, 1),
+    ("3x3 64->64 odd height", 1, 17, 16, [64], 64, 3, 1),
 ]
 
 
