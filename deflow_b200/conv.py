@@ -38,6 +38,15 @@ def _halo(ksize, stride, cins):
     return ksize == 3 and stride == 1 and all(c % 64 == 0 for c in cins)
 
 
+def _halo_name(n_out, out_rows, out_dtype):
+    """Kernel a halo launch resolves to in dfb_conv2d (csrc/conv_igemm.cu): 64 output channels with bf16 output and an
+    even row count go to the row-pair kernel unless DFB_HALO_PAIR=0."""
+    import os
+    if n_out == 64 and out_dtype == torch.bfloat16 and out_rows % 2 == 0 and os.environ.get("DFB_HALO_PAIR", "1") != "0":
+        return "k_conv_igemm_halo_pair"
+    return f"k_conv_igemm_halo<{n_out}>"
+
+
 def _args(mode, n, H, W, ksize, stride, xs, cins, cout, w, bias=None, y=None, stats=None, cin_total=0, cin_off=0,
           xs_lo=None):
     a = ConvArgs()
@@ -107,7 +116,7 @@ def conv2d_forward(xs: Sequence[torch.Tensor], w_fwd, bias, cout, ksize, stride,
     cins = [x.shape[3] for x in xs]
     a = _args(0, n, H, W, ksize, stride, xs, cins, cout, w_fwd, bias, y, stats, xs_lo=xs_lo)
     kc = 64 if all(c % 64 == 0 for c in cins) else 32
-    name = f"k_conv_igemm_halo<{cout}>" if _halo(ksize, stride, cins) else f"k_conv_igemm<{cout},{kc}>"
+    name = _halo_name(cout, Ho, out_dtype) if _halo(ksize, stride, cins) else f"k_conv_igemm<{cout},{kc}>"
     with _timed(name, 2.0 * n * Ho * Wo * cout * sum(cins) * ksize * ksize, y):
         check(_lib.lib().dfb_conv2d(C.byref(a), _stream(y)), "conv2d forward")
     return y
@@ -129,7 +138,7 @@ def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize
     a = _args(1, n, H, W, ksize, stride, [gy], [cin], cout, w_dgrad, None, gx, stats, cin_total, cin_off, xs_lo=gy_lo)
     a.stats_sum_only = int(colsum)
     kc = 64 if cout % 64 == 0 else 32
-    name = f"k_conv_igemm_halo<{cin}>" if _halo(ksize, stride, [cout]) else f"k_conv_igemm<{cin},{kc}>"
+    name = _halo_name(cin, H, out_dtype) if _halo(ksize, stride, [cout]) else f"k_conv_igemm<{cin},{kc}>"
     with _timed(name, 2.0 * n * gy.shape[1] * gy.shape[2] * cout * cin * ksize * ksize, gy):
         check(_lib.lib().dfb_conv2d(C.byref(a), _stream(gy)), "conv2d dgrad")
     if colsum:

@@ -53,7 +53,12 @@ int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uin
 constexpr int TILE_H = 16, TILE_W = 8, TILE_M = TILE_H * TILE_W;  // 128 output pixels per tile
 constexpr int MAX_STEPS = 224;
 constexpr int MAX_AMAPS = 8;   // 4 sources / parity planes x (hi, lo) in split-precision mode
-constexpr int IGEMM_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..5 epilogue
+// warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..9 epilogue.  Eight epilogue warps: two per TMEM lane quarter, each
+// taking every other block of 32 accumulator columns.  With four (one per scheduler, ~300 dependent instructions per
+// column block) the epilogue of a 64-channel tile took longer than its MMAs (r01: 7 k cycles per 256 pixels measured
+// against 3.6 k cycles of MMA time) -- the layers with few K steps per tile were epilogue-bound, not tensor-bound.
+constexpr int EPI_WARPS = 8;
+constexpr int IGEMM_THREADS = 64 + 32 * EPI_WARPS;
 
 struct KStep {
   int8_t map, dy, dx, pad;  // source tensor map, pixel shift (in that source's pixel grid)
@@ -89,7 +94,7 @@ struct IgemmParams {
 };
 
 constexpr int EPI_STAGE_BYTES = 2048;                 // per epilogue warp: 32 pixels x 32 channels bf16 / 32 x 16 fp32
-constexpr int EPI_SMEM = 4 * EPI_STAGE_BYTES;
+constexpr int EPI_SMEM = EPI_WARPS * EPI_STAGE_BYTES;
 
 // Epilogue shared by the implicit-GEMM kernels: 4 warps = 128 TMEM lanes = the 16 x 8 pixels of a tile; warp q owns
 // tile rows 4q .. 4q+3 (32 pixels, lane = pixel).  Per block of 32 channels:
@@ -109,9 +114,10 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
                                                uint64_t* acc_full, uint64_t* acc_empty, float* s_stats,
                                                const float* s_bias, uint8_t* stage_all, int warp, int lane) {
   const int q = warp & 3;  // TMEM lane quarter this warp may access
+  const int cg = (warp - 2) >> 2;          // which of the EPI_WARPS / 4 interleaved column-block sets this warp takes
   const int m = q * 32 + lane;
   const int r = m >> 3, c = m & 7;
-  uint8_t* stg = stage_all + q * EPI_STAGE_BYTES;
+  uint8_t* stg = stage_all + (warp - 2) * EPI_STAGE_BYTES;
   float* slab = reinterpret_cast<float*>(stg);
   const int sw16 = (lane >> 1) & 15;        // slab column swizzle of this lane's row
   const int sw4 = (lane >> 1) & 3;          // 64-byte TMA swizzle of this lane's row
@@ -127,7 +133,7 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
     mbar_wait(&acc_full[acc], acc_phase);
     tc_fence_after();
 #pragma unroll 1
-    for (int col = 0; col < N; col += 32) {
+    for (int col = 32 * cg; col < N; col += 32 * (EPI_WARPS / 4)) {
       const int half = PAIR ? col / (N / 2) : 0;       // output row parity of this column block
       const int ch0 = PAIR ? col % (N / 2) : col;      // first output channel of this column block
       const int y = y0 + half;
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
     for (int i = 0; i < MAX_AMAPS; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&maps.b);
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -361,7 +367,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
     tma_prefetch_desc(&maps.b);
     for (int i = 0; i < Cfg::HALO_STAGES; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); }
     for (int i = 0; i < Cfg::W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo_pair(const
     tma_prefetch_desc(&maps.b);
     for (int i = 0; i < Cfg::HALO_STAGES; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); }
     for (int i = 0; i < Cfg::W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
