@@ -17,7 +17,15 @@
 namespace dfb {
 namespace tc {
 
-constexpr int GF_THREADS = 288;  // warps 0..7 workers, warp 8 control (TMA + MMA issue)
+// warps 0..15 workers, warp 16 control (TMA + MMA issue).  Sixteen worker warps = four per scheduler and per TMEM lane
+// quarter, each thread owning one point row x 32 of the 128 hidden channels: the gate stages are issue / MUFU / latency
+// bound (r01: tensor pipe active 16 %, ~14 k cycles per GRU iteration against 2.5 k cycles of MMA time), and with eight
+// warps (two per scheduler) there was nothing to hide the TMEM-load, MUFU and shared-memory latencies behind.
+constexpr int GW = 16;                    // worker warps
+constexpr int GPARTS = GW / 4;            // channel parts per point row
+constexpr int GCPT = 128 / GPARTS;        // hidden channels per thread (32)
+constexpr int GXPT = 64 / GPARTS;         // x channels per thread (16)
+constexpr int GF_THREADS = 32 * (GW + 1);
 constexpr int GF_WZR = 0;                         // 3 x [256 x 128 B]
 constexpr int GF_WQ = GF_WZR + 3 * 32768;         // 3 x [128 x 128 B]
 constexpr int GF_W1 = GF_WQ + 3 * 16384;          // 3 x [ 32 x 128 B]
@@ -71,10 +79,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
   const int num_tiles = (P.n_pad + 127) / 128;
 
   for (int i = threadIdx.x; i < GF_PAR_FLOATS - 5; i += blockDim.x) par[i] = P.par[i];
-  if (warp == 8) {
+  if (warp == GW) {
     if (lane == 0) {
       tma_prefetch_desc(&maps.wzr); tma_prefetch_desc(&maps.wq); tma_prefetch_desc(&maps.w1);
-      mbar_init(bar_w, 1); mbar_init(bar_a, 8); mbar_init(bar_d, 1);
+      mbar_init(bar_w, 1); mbar_init(bar_a, GW); mbar_init(bar_d, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -87,7 +95,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
   const float* bz = par; const float* br = par + 128; const float* bq = par + 256; const float* b1 = par + 384;
   const float* w2 = par + 416; const float* b2 = par + 512; const float* woff = par + 515; const float* boff = par + 707;
 
-  if (warp == 8) {
+  if (warp == GW) {
     // ------------------------------------------------------------------ control: weights once, then MMA issue
     // The whole warp runs this code (warp-uniform control flow keeps descriptors and loop state in uniform registers);
     // lane 0 alone issues TMA, one elected lane issues the MMAs.  Under `if (lane == 0)` every tcgen05.mma cost ~30 SASS
@@ -142,34 +150,37 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ workers
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;          // TMEM lane quarter (rows), channel part
     const int m = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint8_t* tile_h = smem + GF_AH + half * 16384;
+    constexpr int CH0_CHUNKS = GCPT / 8;               // 16-byte chunks of this thread's channels per row
+    const int ch0 = part * GCPT;                       // first hidden channel of this thread
+    uint8_t* tile_h = smem + GF_AH + (ch0 >> 6) * 16384;   // the 64-channel tile its channels live in ...
+    const int chunk0 = (ch0 & 63) >> 3;                    // ... starting at this 16-byte chunk of a row
     uint8_t* tile_x = smem + GF_AX;
     uint32_t use_d = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int p = tile * 128 + m;
       const bool valid = p < P.n;
       const bool inpad = p < P.n_pad;
-      // x = Woff o + boff: this thread's 32 of the 64 channels -> chunks half*4 .. half*4+3 of the X tile
+      // x = Woff o + boff: this thread's GXPT of the 64 channels
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
       if (valid) { o0 = P.offs[3 * (size_t)p]; o1 = P.offs[3 * (size_t)p + 1]; o2 = P.offs[3 * (size_t)p + 2]; }
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
+      for (int c8 = 0; c8 < GXPT / 8; ++c8) {
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int ch = half * 32 + c8 * 8 + i;
+          const int ch = part * GXPT + c8 * 8 + i;
           f[i] = valid ? fmaf(o2, woff[3 * ch + 2], fmaf(o1, woff[3 * ch + 1], fmaf(o0, woff[3 * ch], boff[ch]))) : 0.f;
         }
-        st_tile_chunk(tile_x, m, half * 4 + c8, f);
+        st_tile_chunk(tile_x, m, part * (GXPT / 8) + c8, f);
       }
-      float h[64];
+      float h[GCPT];
       if (valid) {
-        const uint4* src = reinterpret_cast<const uint4*>(P.h0 + (size_t)p * 128 + half * 64);
+        const uint4* src = reinterpret_cast<const uint4*>(P.h0 + (size_t)p * 128 + ch0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < CH0_CHUNKS; ++i) {
           const uint4 u = __ldg(src + i);
           const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -177,15 +188,15 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) h[i] = 0.f;
+        for (int i = 0; i < GCPT; ++i) h[i] = 0.f;
       }
-      auto publish_h = [&](int) {  // bf16(h) -> A tile (the control thread saves the tile by TMA when training)
+      auto publish_h = [&](int) {  // bf16(h) -> A tile (the control warp saves the tile by TMA when training)
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
+        for (int c8 = 0; c8 < CH0_CHUNKS; ++c8) {
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = valid ? h[c8 * 8 + i] : 0.f;
-          st_tile_chunk(tile_h, m, c8, f);
+          st_tile_chunk(tile_h, m, chunk0 + c8, f);
         }
       };
       auto signal_a = [&]() {
@@ -204,33 +215,33 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
         wait_d();
         // r = sigmoid(r_pre + br); A tile <- bf16(r * h)
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < GCPT / 32; ++cc) {
           float v[32];
-          tmem_ld32(tmem + lane_base + 128 + half * 64 + cc * 32, v);
+          tmem_ld32(tmem + lane_base + 128 + ch0 + cc * 32, v);
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = cc * 32 + c8 * 8 + i;
-              f[i] = fsigmoid(v[c8 * 8 + i] + br[half * 64 + j]) * h[j];
+              f[i] = fsigmoid(v[c8 * 8 + i] + br[ch0 + j]) * h[j];
             }
-            st_tile_chunk(tile_h, m, cc * 4 + c8, f);
+            st_tile_chunk(tile_h, m, chunk0 + cc * 4 + c8, f);
           }
         }
         signal_a();
         wait_d();
         // h = (1 - z) h + z tanh(q_pre + bq),  z = sigmoid(z_pre + bz)
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < GCPT / 32; ++cc) {
           float vz[32], vq[32];
-          tmem_ld32(tmem + lane_base + half * 64 + cc * 32, vz);
-          tmem_ld32(tmem + lane_base + 256 + half * 64 + cc * 32, vq);
+          tmem_ld32(tmem + lane_base + ch0 + cc * 32, vz);
+          tmem_ld32(tmem + lane_base + 256 + ch0 + cc * 32, vq);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int j = cc * 32 + i;
-            const float z = fsigmoid(vz[i] + bz[half * 64 + j]);
-            const float qq = ftanh(vq[i] + bq[half * 64 + j]);
+            const float z = fsigmoid(vz[i] + bz[ch0 + j]);
+            const float qq = ftanh(vq[i] + bq[ch0 + j]);
             h[j] = fmaf(z, qq - h[j], h[j]);
           }
         }
@@ -238,7 +249,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
       publish_h(P.iters);
       signal_a();
       wait_d();
-      if (half == 0) {  // 32 hidden units of the MLP head: this thread's row, all 32 columns
+      if (part == 0) {  // 32 hidden units of the MLP head: this thread's row, all 32 columns
         float v[32];
         tmem_ld32(tmem + lane_base + 384, v);
         float f0 = b2[0], f1 = b2[1], f2 = b2[2];
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == GW) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace tc
@@ -390,11 +401,11 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
   const int num_tiles = (P.n_pad + 127) / 128;
 
   for (int i = threadIdx.x; i < 384; i += blockDim.x) par[i] = P.par[i];
-  if (warp == 8) {
+  if (warp == GW) {
     if (lane == 0) {
       tma_prefetch_desc(&maps.wzr); tma_prefetch_desc(&maps.wq); tma_prefetch_desc(&maps.h); tma_prefetch_desc(&maps.x);
       tma_prefetch_desc(&maps.rh); tma_prefetch_desc(&maps.dq); tma_prefetch_desc(&maps.dzr);
-      mbar_init(bar_w, 1); mbar_init(bar_a, 8); mbar_init(bar_d, 1); mbar_init(bar_h, 1);
+      mbar_init(bar_w, 1); mbar_init(bar_a, GW); mbar_init(bar_d, 1); mbar_init(bar_h, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -409,7 +420,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
   // [448,512) d_x accumulator
   constexpr uint32_t C_ZR = 0, C_Q = 256, C_DX = 448;
 
-  if (warp == 8) {
+  if (warp == GW) {
     // whole-warp control flow, lane 0 issues TMA, one elected lane issues the MMAs (see k_gru_fused_fwd)
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, 3 * 32768 + 3 * 16384);
@@ -505,11 +516,14 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
     if (lane == 0) tma_store_wait_all();
     __syncwarp();
   } else {
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;          // TMEM lane quarter (rows), channel part (GCPT channels)
     const int m = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint8_t* tile_p = smem + GB_P + half * 16384;
-    uint8_t* tile_q = smem + GB_Q + half * 16384;
+    constexpr int NCH = GCPT / 8;                      // 16-byte chunks of this thread's channels per row
+    const int ch0 = part * GCPT;
+    const int chunk0 = (ch0 & 63) >> 3;
+    uint8_t* tile_p = smem + GB_P + (ch0 >> 6) * 16384;
+    uint8_t* tile_q = smem + GB_Q + (ch0 >> 6) * 16384;
     uint32_t use_d = 0, use_h = 0;
     auto signal_a = [&]() {
       tc_fence_before();
@@ -523,10 +537,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
       const bool valid = p < P.n;
       const bool inpad = p < P.n_pad;
       const size_t prow = inpad ? (size_t)p : 0;
-      float dh[64];
+      float dh[GCPT];
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        if (valid) ld_bf16x8(P.dh_in + prow * 128 + half * 64 + c8 * 8, &dh[c8 * 8]);
+      for (int c8 = 0; c8 < NCH; ++c8) {
+        if (valid) ld_bf16x8(P.dh_in + prow * 128 + ch0 + c8 * 8, &dh[c8 * 8]);
         else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) dh[c8 * 8 + i] = 0.f;
@@ -536,13 +550,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
         signal_a();  // TMEM of the previous stage has been read
         wait_d();    // z | r pre-activations
         mbar_wait(bar_h, use_h & 1); ++use_h;  // the h_t tile written by TMA is visible to this thread
-        uint4 hp[8];                            // this row's 64 channels of h_t, packed bf16
+        uint4 hp[NCH];                          // this row's GCPT channels of h_t, packed bf16
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) hp[c8] = *reinterpret_cast<const uint4*>(tile_p + m * 128 + ((c8 ^ (m & 7)) << 4));
+        for (int c8 = 0; c8 < NCH; ++c8) hp[c8] = *reinterpret_cast<const uint4*>(tile_p + m * 128 + (((chunk0 + c8) ^ (m & 7)) << 4));
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < GCPT / 32; ++cc) {
           float v[32];
-          tmem_ld32(tmem + lane_base + C_ZR + 128 + half * 64 + cc * 32, v);
+          tmem_ld32(tmem + lane_base + C_ZR + 128 + ch0 + cc * 32, v);
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             float f[8], hh[8];
@@ -550,18 +564,18 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = cc * 32 + c8 * 8 + i;
-              f[i] = valid ? fsigmoid(v[c8 * 8 + i] + br[half * 64 + j]) * hh[i] : 0.f;
+              f[i] = valid ? fsigmoid(v[c8 * 8 + i] + br[ch0 + j]) * hh[i] : 0.f;
             }
-            st_tile_chunk(tile_p, m, cc * 4 + c8, f);
+            st_tile_chunk(tile_p, m, chunk0 + cc * 4 + c8, f);
           }
         }
         signal_a();
         wait_d();  // q pre-activation
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < GCPT / 16; ++cc) {
           float vz[16], vq[16];
-          tmem_ld16(tmem + lane_base + C_ZR + half * 64 + cc * 16, vz);
-          tmem_ld16(tmem + lane_base + C_Q + half * 64 + cc * 16, vq);
+          tmem_ld16(tmem + lane_base + C_ZR + ch0 + cc * 16, vz);
+          tmem_ld16(tmem + lane_base + C_Q + ch0 + cc * 16, vq);
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
             float fq[8], fz[8], hh[8];
@@ -569,24 +583,24 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = cc * 16 + c8 * 8 + i;
-              const float z = fsigmoid(vz[c8 * 8 + i] + bz[half * 64 + j]);
-              const float qq = ftanh(vq[c8 * 8 + i] + bq[half * 64 + j]);
+              const float z = fsigmoid(vz[c8 * 8 + i] + bz[ch0 + j]);
+              const float qq = ftanh(vq[c8 * 8 + i] + bq[ch0 + j]);
               const float g = dh[j];
               fq[i] = g * z * (1.0f - qq * qq);
               fz[i] = g * (qq - hh[i]) * z * (1.0f - z);
               dh[j] = g * (1.0f - z);
             }
-            st_tile_chunk(tile_p, m, cc * 2 + c8, fq);
-            st_tile_chunk(tile_q, m, cc * 2 + c8, fz);
+            st_tile_chunk(tile_p, m, chunk0 + cc * 2 + c8, fq);
+            st_tile_chunk(tile_q, m, chunk0 + cc * 2 + c8, fz);
           }
         }
         signal_a();
         wait_d();  // d_rh in C_Q, partial d_h in C_ZR[0,128); r pre-activation still in C_ZR[128,256)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < GCPT / 16; ++cc) {
           float vr[16], vg[16];
-          tmem_ld16(tmem + lane_base + C_ZR + 128 + half * 64 + cc * 16, vr);
-          tmem_ld16(tmem + lane_base + C_Q + half * 64 + cc * 16, vg);
+          tmem_ld16(tmem + lane_base + C_ZR + 128 + ch0 + cc * 16, vr);
+          tmem_ld16(tmem + lane_base + C_Q + ch0 + cc * 16, vg);
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
             float f[8], hh[8];
@@ -594,20 +608,20 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = cc * 16 + c8 * 8 + i;
-              const float r = fsigmoid(vr[c8 * 8 + i] + br[half * 64 + j]);
+              const float r = fsigmoid(vr[c8 * 8 + i] + br[ch0 + j]);
               const float g = valid ? vg[c8 * 8 + i] : 0.f;
               f[i] = g * hh[i] * r * (1.0f - r);
               dh[j] = fmaf(g, r, dh[j]);
             }
-            st_tile_chunk(tile_p, m, cc * 2 + c8, f);
+            st_tile_chunk(tile_p, m, chunk0 + cc * 2 + c8, f);
           }
         }
         signal_a();
         wait_d();  // d_h complete in C_ZR[0,128)
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < GCPT / 32; ++cc) {
           float v[32];
-          tmem_ld32(tmem + lane_base + C_ZR + half * 64 + cc * 32, v);
+          tmem_ld32(tmem + lane_base + C_ZR + ch0 + cc * 32, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) dh[cc * 32 + i] += valid ? v[i] : 0.f;
         }
@@ -615,23 +629,23 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
       // outputs of the tile: dh0 (bf16) and d_x = TMEM accumulator + the head's contribution
       if (inpad) {
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) st_bf16x8(P.dh0 + prow * 128 + half * 64 + c8 * 8, &dh[c8 * 8]);
+        for (int c8 = 0; c8 < NCH; ++c8) st_bf16x8(P.dh0 + prow * 128 + ch0 + c8 * 8, &dh[c8 * 8]);
       }
       {
-        float v[32];
-        if (P.iters > 0) tmem_ld32(tmem + lane_base + C_DX + half * 32, v);
+        float v[GXPT];
+        if (P.iters > 0) tmem_ld16(tmem + lane_base + C_DX + part * GXPT, v);
         else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          for (int i = 0; i < GXPT; ++i) v[i] = 0.f;
         }
         if (inpad) {
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
+          for (int c8 = 0; c8 < GXPT / 8; ++c8) {
             float f[8];
-            ld_bf16x8(P.dx_in + prow * 64 + half * 32 + c8 * 8, f);
+            ld_bf16x8(P.dx_in + prow * 64 + part * GXPT + c8 * 8, f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = valid ? f[i] + v[c8 * 8 + i] : 0.f;
-            float4* dst = reinterpret_cast<float4*>(P.dx + prow * 64 + half * 32 + c8 * 8);
+            float4* dst = reinterpret_cast<float4*>(P.dx + prow * 64 + part * GXPT + c8 * 8);
             dst[0] = make_float4(f[0], f[1], f[2], f[3]);
             dst[1] = make_float4(f[4], f[5], f[6], f[7]);
           }
@@ -643,7 +657,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == GW) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace tc
