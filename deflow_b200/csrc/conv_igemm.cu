@@ -1190,7 +1190,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad(const __grid_const
 constexpr int WH_HALO_BYTES = 13 * 1024;  // 100 pixel rows x 128 B = 12800, 1024-aligned
 constexpr int WH_MAX_ITEMS = 32;
 
-struct WHItem { int8_t map, npairs, dup_first, pad1; int16_t c0, ci_glob; int8_t t1[5], t2[5]; int16_t pad2; };  // dup_first: the last pair's first tap repeats one already covered (odd tap count)
+struct WHItem { int8_t map, npairs, dup_first, pad1; int16_t c0, ci_glob; int8_t t1[5], t2[5]; int16_t pad2; int16_t blk0, nsplit; };  // dup_first: the last pair's first tap repeats one already covered (odd tap count); blk0 / nsplit: the CTAs of this item
 
 struct WgradHaloParams {
   int n_img, Ht, Wt, tiles_x, tiles_y, num_tiles;
@@ -1224,9 +1224,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_halo(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int item_id = blockIdx.x % P.n_items, split = blockIdx.x / P.n_items;
+  // CTAs are dealt to the work items in proportion to their MMA count (tap pairs): an item with one pair loads the same
+  // x box and gy tile per pixel tile as an item with four and would otherwise only wait on L2
+  int item_id = 0;
+  for (int i = 1; i < P.n_items; ++i) if ((int)blockIdx.x >= P.items[i].blk0) item_id = i;
   const WHItem it = P.items[item_id];
-  const int per = (P.num_tiles + P.splits - 1) / P.splits;
+  const int split = (int)blockIdx.x - it.blk0;
+  const int per = (P.num_tiles + it.nsplit - 1) / it.nsplit;
   const int t_begin = split * per, t_end = min(P.num_tiles, t_begin + per);
 
   if (warp == 0 && lane == 0) {
@@ -1333,7 +1337,7 @@ static int launch_wgrad_halo(const WgradMaps& maps, const WgradHaloParams& P, cu
     if (e != cudaSuccess) { set_error("wgrad_halo<%d>: cannot reserve %d bytes of shared memory: %s", N, Cfg::SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     configured = true;
   }
-  k_conv_wgrad_halo<N><<<P.n_items * P.splits, WG_THREADS, Cfg::SMEM, st>>>(maps, P);
+  k_conv_wgrad_halo<N><<<P.splits, WG_THREADS, Cfg::SMEM, st>>>(maps, P);   // P.splits = total CTAs
   add_launches(1);
   return check_launch("conv_wgrad_halo");
 }
@@ -1416,17 +1420,21 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
       const uint64_t str[3] = {C * 2, C * 2 * W, C * 2 * W * H};
       if ((rc = make_tensor_map_bf16(&maps.a[i], a->x[i], 4, dims, str, hbox, 128))) return rc;
       for (int c0 = 0; c0 < a->cin[i]; c0 += 64) {
-        int t = 0;
-        while (t < 9) {  // tap sets of up to max_pairs pairs
+        // nine taps = five tap pairs (the last one repeats tap 7); spread over ceil(5 / max_pairs) items as evenly as
+        // possible (N = 128: 3 + 2 pairs, not 4 + 1; N = 256: 2 + 2 + 1)
+        const int n_it = (5 + max_pairs - 1) / max_pairs;
+        int pr0 = 0;
+        for (int k = 0; k < n_it; ++k) {
           if (ni >= tc::WH_MAX_ITEMS) { set_error("dfb_conv2d_wgrad: too many work items"); return DFB_ERR_UNSUPPORTED; }
+          const int cnt = (5 - pr0 + (n_it - k) - 1) / (n_it - k);
           tc::WHItem& it = Q.items[ni++];
           it.map = (int8_t)i; it.c0 = (int16_t)c0; it.ci_glob = (int16_t)(coff + c0); it.npairs = 0; it.dup_first = 0;
-          while (t < 9 && it.npairs < max_pairs) {
-            if (t + 1 < 9) { it.t1[it.npairs] = (int8_t)t; it.t2[it.npairs] = (int8_t)(t + 1); }
-            else { it.t1[it.npairs] = (int8_t)(t - 1); it.t2[it.npairs] = (int8_t)t; it.dup_first = 1; }  // (7, 8), 7 dropped
+          for (int pr = pr0; pr < pr0 + cnt; ++pr) {
+            if (pr < 4) { it.t1[it.npairs] = (int8_t)(2 * pr); it.t2[it.npairs] = (int8_t)(2 * pr + 1); }
+            else { it.t1[it.npairs] = 7; it.t2[it.npairs] = 8; it.dup_first = 1; }  // (7, 8), 7 dropped
             ++it.npairs;
-            t += 2;
           }
+          pr0 += cnt;
         }
       }
       coff += a->cin[i];
@@ -1435,10 +1443,20 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
     Q.n_img = a->n; Q.Ht = Ho; Q.Wt = Wo;
     Q.tiles_x = (Wo + 7) / 8; Q.tiles_y = (Ho + 7) / 8;
     Q.num_tiles = Q.tiles_x * Q.tiles_y * a->n;
-    int splits = (2 * sm_count() + ni - 1) / ni;
-    if (splits > Q.num_tiles) splits = Q.num_tiles;
-    if (splits < 1) splits = 1;
-    Q.splits = splits;
+    {
+      int wsum = 0, blk = 0;
+      for (int k = 0; k < ni; ++k) wsum += Q.items[k].npairs;
+      const int target = 2 * sm_count();
+      for (int k = 0; k < ni; ++k) {
+        int ns = (target * Q.items[k].npairs + wsum / 2) / wsum;
+        if (ns > Q.num_tiles) ns = Q.num_tiles;
+        if (ns < 1) ns = 1;
+        Q.items[k].blk0 = (int16_t)blk;
+        Q.items[k].nsplit = (int16_t)ns;
+        blk += ns;
+      }
+      Q.splits = blk;   // total CTAs
+    }
     Q.cin_total = cin_total; Q.cout = a->cout; Q.wacc = wacc;
     const size_t total = (size_t)taps * a->cout * cin_total;
     cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
