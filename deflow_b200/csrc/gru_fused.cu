@@ -12,20 +12,15 @@
 // gate pre-activations back with tcgen05.ld for the sigmoid / tanh / lerp.  For the backward pass the kernel saves
 // bf16 copies of the state entering every iteration, the final state and the head pre-activation.
 #include "tc_common.cuh"
+#include <stdlib.h>
 #include "../../include/deflow_b200.h"
 
 namespace dfb {
 namespace tc {
 
-// warps 0..15 workers, warp 16 control (TMA + MMA issue).  Sixteen worker warps = four per scheduler and per TMEM lane
-// quarter, each thread owning one point row x 32 of the 128 hidden channels: the gate stages are issue / MUFU / latency
-// bound (r01: tensor pipe active 16 %, ~14 k cycles per GRU iteration against 2.5 k cycles of MMA time), and with eight
-// warps (two per scheduler) there was nothing to hide the TMEM-load, MUFU and shared-memory latencies behind.
-constexpr int GW = 16;                    // worker warps
-constexpr int GPARTS = GW / 4;            // channel parts per point row
-constexpr int GCPT = 128 / GPARTS;        // hidden channels per thread (32)
-constexpr int GXPT = 64 / GPARTS;         // x channels per thread (16)
-constexpr int GF_THREADS = 32 * (GW + 1);
+// Warps 0..GW-1 are workers, warp GW is the control warp (TMA + MMA issue).  GW = 8: thread = point row x 64 hidden
+// channels (168 registers); GW = 16: four warps per scheduler and TMEM lane quarter, thread = row x 32 channels (the CTA
+// is then allocated as 20 warps: 96 registers per thread).  Selected at launch (DFB_GRU_WARPS, see dfb_gru_fused_*).
 constexpr int GF_WZR = 0;                         // 3 x [256 x 128 B]
 constexpr int GF_WQ = GF_WZR + 3 * 32768;         // 3 x [128 x 128 B]
 constexpr int GF_W1 = GF_WQ + 3 * 16384;          // 3 x [ 32 x 128 B]
@@ -57,6 +52,31 @@ __device__ __forceinline__ float ftanh(float v) {
 }
 __device__ __forceinline__ float fsigmoid(float v) { return fmaf(0.5f, ftanh(0.5f * v), 0.5f); }
 
+// Packed fp32x2 forms (FADD2 / FMUL2 / FFMA2: two channels per instruction).  The gate stages were issue-bound (ncu r01:
+// ~2300 scalar instructions per thread and GRU iteration for 2.5 k cycles of MMA time), the MUFU count is unchanged.
+__device__ __forceinline__ float2 g2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 ftanh2(float2 v) { return make_float2(ftanh(v.x), ftanh(v.y)); }
+__device__ __forceinline__ float2 fsigmoid2(float2 v) { return __ffma2_rn(ftanh2(__fmul2_rn(v, g2(0.5f))), g2(0.5f), g2(0.5f)); }
+// shared-memory accesses with explicit state space (pointers derived from the aligned dynamic smem base are generic
+// to the compiler: LD.E / ST.E instead of LDS / STS)
+__device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+__device__ __forceinline__ uint32_t bf2_pack(float2 v) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ float2 bf2_unpack(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+// 8 consecutive channels (4 packed pairs) of row `row` -> chunk `chunk` of a [128 x 128 B] SWIZZLE_128B K-major tile
+__device__ __forceinline__ void st_tile_chunk2(uint32_t tile_saddr, int row, int chunk, const float2 (&f)[4]) {
+  sts_u4(tile_saddr + row * 128 + ((chunk ^ (row & 7)) << 4), make_uint4(bf2_pack(f[0]), bf2_pack(f[1]), bf2_pack(f[2]), bf2_pack(f[3])));
+}
+
 // store 8 consecutive channels (one 16-byte chunk) of row `row` into a [128 x 128 B] SWIZZLE_128B K-major tile
 __device__ __forceinline__ void st_tile_chunk(uint8_t* tile, int row, int chunk, const float* f) {
   uint4 u;
@@ -66,8 +86,12 @@ __device__ __forceinline__ void st_tile_chunk(uint8_t* tile, int row, int chunk,
   *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = u;
 }
 
-__global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_constant__ GruFusedMaps maps,
+template <int GW>
+__global__ void __launch_bounds__(32 * (GW + 1), 1) k_gru_fused_fwd(const __grid_constant__ GruFusedMaps maps,
                                                                  const __grid_constant__ GruFusedParams P) {
+  constexpr int GPARTS = GW / 4;       // channel parts per point row
+  constexpr int GCPT = 128 / GPARTS;   // hidden channels per thread
+  constexpr int GXPT = 64 / GPARTS;    // x channels per thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* par = reinterpret_cast<float*>(smem + GF_PAR);
@@ -158,6 +182,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
     uint8_t* tile_h = smem + GF_AH + (ch0 >> 6) * 16384;   // the 64-channel tile its channels live in ...
     const int chunk0 = (ch0 & 63) >> 3;                    // ... starting at this 16-byte chunk of a row
     uint8_t* tile_x = smem + GF_AX;
+    const uint32_t s_tile_h = smem_u32(tile_h), s_bz = smem_u32(bz), s_br = smem_u32(br), s_bq = smem_u32(bq);
     uint32_t use_d = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int p = tile * 128 + m;
@@ -220,13 +245,14 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
           tmem_ld32(tmem + lane_base + 128 + ch0 + cc * 32, v);
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
-            float f[8];
+            float2 f[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = cc * 32 + c8 * 8 + i;
-              f[i] = fsigmoid(v[c8 * 8 + i] + br[ch0 + j]) * h[j];
+            for (int i = 0; i < 4; ++i) {
+              const int j = cc * 32 + c8 * 8 + 2 * i;
+              const float2 pre = __fadd2_rn(make_float2(v[c8 * 8 + 2 * i], v[c8 * 8 + 2 * i + 1]), lds_f2(s_br + 4 * (ch0 + j)));
+              f[i] = __fmul2_rn(fsigmoid2(pre), make_float2(h[j], h[j + 1]));
             }
-            st_tile_chunk(tile_h, m, chunk0 + cc * 4 + c8, f);
+            st_tile_chunk2(s_tile_h, m, chunk0 + cc * 4 + c8, f);
           }
         }
         signal_a();
@@ -238,11 +264,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_fwd(const __grid_co
           tmem_ld32(tmem + lane_base + ch0 + cc * 32, vz);
           tmem_ld32(tmem + lane_base + 256 + ch0 + cc * 32, vq);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 32; i += 2) {
             const int j = cc * 32 + i;
-            const float z = fsigmoid(vz[i] + bz[ch0 + j]);
-            const float qq = ftanh(vq[i] + bq[ch0 + j]);
-            h[j] = fmaf(z, qq - h[j], h[j]);
+            const float2 z = fsigmoid2(__fadd2_rn(make_float2(vz[i], vz[i + 1]), lds_f2(s_bz + 4 * (ch0 + j))));
+            const float2 qq = ftanh2(__fadd2_rn(make_float2(vq[i], vq[i + 1]), lds_f2(s_bq + 4 * (ch0 + j))));
+            const float2 hj = make_float2(h[j], h[j + 1]);
+            const float2 hn = __ffma2_rn(z, __fadd2_rn(qq, make_float2(-hj.x, -hj.y)), hj);
+            h[j] = hn.x; h[j + 1] = hn.y;
           }
         }
       }
@@ -288,6 +316,16 @@ using namespace dfb::tc;
 
 static int make_rows_map(CUtensorMap* map, const void* base, int cols, int n_pad, int slabs);
 
+// worker warps per CTA of the fused GRU kernels: DFB_GRU_WARPS=8|16 (default 8)
+static int gru_worker_warps() {
+  static int w = 0;
+  if (!w) {
+    const char* e = getenv("DFB_GRU_WARPS");
+    w = (e && atoi(e) == 16) ? 16 : 8;
+  }
+  return w;
+}
+
 // wzr: bf16 [256][192] (Wz rows then Wr rows), wq: bf16 [128][192], w1: bf16 [32][192]; K order = [h(128), x(64)].
 extern "C" int dfb_gru_fused_forward(const void* h0, const float* offsets, const void* wzr, const void* wq,
                                      const void* w1, const float* par, int n, int n_pad, int iters, void* hsave,
@@ -320,14 +358,16 @@ extern "C" int dfb_gru_fused_forward(const void* h0, const float* offsets, const
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gru_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_gru_fused_fwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gru_fused_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
     if (e != cudaSuccess) { set_error("gru_fused: cannot reserve %d bytes of shared memory: %s", GF_SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     configured = true;
   }
   const int tiles = (n_pad + 127) / 128;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
-  k_gru_fused_fwd<<<grid, GF_THREADS, GF_SMEM, st>>>(maps, P);
+  if (gru_worker_warps() == 16) k_gru_fused_fwd<16><<<grid, 32 * 17, GF_SMEM, st>>>(maps, P);
+  else k_gru_fused_fwd<8><<<grid, 32 * 9, GF_SMEM, st>>>(maps, P);
   add_launches(1);
   return check_launch("dfb_gru_fused_forward");
 }
@@ -387,8 +427,12 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
 // All HBM traffic of the iteration loop goes through TMA: the control thread loads the h_t / x tiles straight into
 // the swizzled operand tiles and stores the rh / dq_pre / dzr_pre tiles from them (bulk async groups), so the 256
 // worker threads touch only TMEM, registers and shared memory inside the loop.
-__global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_constant__ GruBwdMaps maps,
+template <int GW>
+__global__ void __launch_bounds__(32 * (GW + 1), 1) k_gru_fused_bwd(const __grid_constant__ GruBwdMaps maps,
                                                                  const __grid_constant__ GruBwdParams P) {
+  constexpr int GPARTS = GW / 4;       // channel parts per point row
+  constexpr int GCPT = 128 / GPARTS;   // hidden channels per thread
+  constexpr int GXPT = 64 / GPARTS;    // x channels per thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* par = reinterpret_cast<float*>(smem + GB_PAR);
@@ -524,6 +568,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
     const int chunk0 = (ch0 & 63) >> 3;
     uint8_t* tile_p = smem + GB_P + (ch0 >> 6) * 16384;
     uint8_t* tile_q = smem + GB_Q + (ch0 >> 6) * 16384;
+    const uint32_t s_tile_p = smem_u32(tile_p), s_tile_q = smem_u32(tile_q);
+    const uint32_t s_bz = smem_u32(bz), s_br = smem_u32(br), s_bq = smem_u32(bq);
     uint32_t use_d = 0, use_h = 0;
     auto signal_a = [&]() {
       tc_fence_before();
@@ -537,6 +583,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
       const bool valid = p < P.n;
       const bool inpad = p < P.n_pad;
       const size_t prow = inpad ? (size_t)p : 0;
+      const float2 vmask = g2(valid ? 1.0f : 0.0f);
       float dh[GCPT];
 #pragma unroll
       for (int c8 = 0; c8 < NCH; ++c8) {
@@ -559,14 +606,16 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
           tmem_ld32(tmem + lane_base + C_ZR + 128 + ch0 + cc * 32, v);
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
-            float f[8], hh[8];
-            unpack_bf16x8(hp[cc * 4 + c8], hh);
+            const uint4 hw = hp[cc * 4 + c8];
+            const uint32_t hwv[4] = {hw.x, hw.y, hw.z, hw.w};
+            float2 f[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = cc * 32 + c8 * 8 + i;
-              f[i] = valid ? fsigmoid(v[c8 * 8 + i] + br[ch0 + j]) * hh[i] : 0.f;
+            for (int i = 0; i < 4; ++i) {
+              const int j = cc * 32 + c8 * 8 + 2 * i;
+              const float2 pre = __fadd2_rn(make_float2(v[c8 * 8 + 2 * i], v[c8 * 8 + 2 * i + 1]), lds_f2(s_br + 4 * (ch0 + j)));
+              f[i] = __fmul2_rn(__fmul2_rn(fsigmoid2(pre), bf2_unpack(hwv[i])), vmask);
             }
-            st_tile_chunk(tile_p, m, chunk0 + cc * 4 + c8, f);
+            st_tile_chunk2(s_tile_p, m, chunk0 + cc * 4 + c8, f);
           }
         }
         signal_a();
@@ -578,20 +627,25 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
           tmem_ld16(tmem + lane_base + C_Q + ch0 + cc * 16, vq);
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
-            float fq[8], fz[8], hh[8];
-            unpack_bf16x8(hp[cc * 2 + c8], hh);
+            const uint4 hw = hp[cc * 2 + c8];
+            const uint32_t hwv[4] = {hw.x, hw.y, hw.z, hw.w};
+            float2 fq[4], fz[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = cc * 16 + c8 * 8 + i;
-              const float z = fsigmoid(vz[c8 * 8 + i] + bz[ch0 + j]);
-              const float qq = ftanh(vq[c8 * 8 + i] + bq[ch0 + j]);
-              const float g = dh[j];
-              fq[i] = g * z * (1.0f - qq * qq);
-              fz[i] = g * (qq - hh[i]) * z * (1.0f - z);
-              dh[j] = g * (1.0f - z);
+            for (int i = 0; i < 4; ++i) {
+              const int j = cc * 16 + c8 * 8 + 2 * i;
+              const float2 z = fsigmoid2(__fadd2_rn(make_float2(vz[c8 * 8 + 2 * i], vz[c8 * 8 + 2 * i + 1]), lds_f2(s_bz + 4 * (ch0 + j))));
+              const float2 qq = ftanh2(__fadd2_rn(make_float2(vq[c8 * 8 + 2 * i], vq[c8 * 8 + 2 * i + 1]), lds_f2(s_bq + 4 * (ch0 + j))));
+              const float2 nhh = bf2_unpack(hwv[i] ^ 0x80008000u);          // -h_t
+              const float2 g = make_float2(dh[j], dh[j + 1]);
+              const float2 omz = __ffma2_rn(z, g2(-1.0f), g2(1.0f));         // 1 - z
+              const float2 gz = __fmul2_rn(g, z);
+              fq[i] = __fmul2_rn(gz, __ffma2_rn(qq, make_float2(-qq.x, -qq.y), g2(1.0f)));   // g z (1 - q^2)
+              fz[i] = __fmul2_rn(__fmul2_rn(gz, omz), __fadd2_rn(qq, nhh));                  // g (q - h) z (1 - z)
+              const float2 dn = __fmul2_rn(g, omz);
+              dh[j] = dn.x; dh[j + 1] = dn.y;
             }
-            st_tile_chunk(tile_p, m, chunk0 + cc * 2 + c8, fq);
-            st_tile_chunk(tile_q, m, chunk0 + cc * 2 + c8, fz);
+            st_tile_chunk2(s_tile_p, m, chunk0 + cc * 2 + c8, fq);
+            st_tile_chunk2(s_tile_q, m, chunk0 + cc * 2 + c8, fz);
           }
         }
         signal_a();
@@ -603,17 +657,19 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
           tmem_ld16(tmem + lane_base + C_Q + ch0 + cc * 16, vg);
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
-            float f[8], hh[8];
-            unpack_bf16x8(hp[cc * 2 + c8], hh);
+            const uint4 hw = hp[cc * 2 + c8];
+            const uint32_t hwv[4] = {hw.x, hw.y, hw.z, hw.w};
+            float2 f[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = cc * 16 + c8 * 8 + i;
-              const float r = fsigmoid(vr[c8 * 8 + i] + br[ch0 + j]);
-              const float g = valid ? vg[c8 * 8 + i] : 0.f;
-              f[i] = g * hh[i] * r * (1.0f - r);
-              dh[j] = fmaf(g, r, dh[j]);
+            for (int i = 0; i < 4; ++i) {
+              const int j = cc * 16 + c8 * 8 + 2 * i;
+              const float2 r = fsigmoid2(__fadd2_rn(make_float2(vr[c8 * 8 + 2 * i], vr[c8 * 8 + 2 * i + 1]), lds_f2(s_br + 4 * (ch0 + j))));
+              const float2 g = __fmul2_rn(make_float2(vg[c8 * 8 + 2 * i], vg[c8 * 8 + 2 * i + 1]), vmask);
+              const float2 gr = __fmul2_rn(g, r);
+              f[i] = __fmul2_rn(__fmul2_rn(gr, bf2_unpack(hwv[i])), __ffma2_rn(r, g2(-1.0f), g2(1.0f)));   // g h r (1 - r)
+              dh[j] += gr.x; dh[j + 1] += gr.y;
             }
-            st_tile_chunk(tile_p, m, chunk0 + cc * 2 + c8, f);
+            st_tile_chunk2(s_tile_p, m, chunk0 + cc * 2 + c8, f);
           }
         }
         signal_a();
@@ -633,7 +689,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) k_gru_fused_bwd(const __grid_co
       }
       {
         float v[GXPT];
-        if (P.iters > 0) tmem_ld16(tmem + lane_base + C_DX + part * GXPT, v);
+        if (P.iters > 0) {
+          if constexpr (GXPT == 32) tmem_ld32(tmem + lane_base + C_DX + part * GXPT, v);
+          else tmem_ld16(tmem + lane_base + C_DX + part * GXPT, v);
+        }
         else {
 #pragma unroll
           for (int i = 0; i < GXPT; ++i) v[i] = 0.f;
@@ -699,14 +758,16 @@ extern "C" int dfb_gru_fused_backward(const void* hsave, const void* xsave, cons
   P.dh0 = (__nv_bfloat16*)dh0; P.dx = dx;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gru_fused_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_gru_fused_bwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gru_fused_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM);
     if (e != cudaSuccess) { set_error("gru_fused_bwd: cannot reserve %d bytes of shared memory: %s", GB_SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     configured = true;
   }
   const int tiles = (n_pad + 127) / 128;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
-  k_gru_fused_bwd<<<grid, GF_THREADS, GB_SMEM, st>>>(maps, P);
+  if (gru_worker_warps() == 16) k_gru_fused_bwd<16><<<grid, 32 * 17, GB_SMEM, st>>>(maps, P);
+  else k_gru_fused_bwd<8><<<grid, 32 * 9, GB_SMEM, st>>>(maps, P);
   add_launches(1);
   return check_launch("dfb_gru_fused_backward");
 }
