@@ -316,14 +316,16 @@ using namespace dfb::tc;
 
 static int make_rows_map(CUtensorMap* map, const void* base, int cols, int n_pad, int slabs);
 
-// worker warps per CTA of the fused GRU kernels: DFB_GRU_WARPS=8|16 (default 8)
-static int gru_worker_warps() {
-  static int w = 0;
-  if (!w) {
+// worker warps per CTA of the fused GRU kernels: DFB_GRU_WARPS=8|16 forces both; default = what measured fastest on
+// B200 (r01): 8 for the forward (168 registers, no spills), 16 for the backward (its gate stages have more latency to hide)
+static int gru_worker_warps(bool backward) {
+  static int w = -1;
+  if (w < 0) {
     const char* e = getenv("DFB_GRU_WARPS");
-    w = (e && atoi(e) == 16) ? 16 : 8;
+    w = e ? atoi(e) : 0;
   }
-  return w;
+  if (w == 8 || w == 16) return w;
+  return backward ? 16 : 8;
 }
 
 // wzr: bf16 [256][192] (Wz rows then Wr rows), wq: bf16 [128][192], w1: bf16 [32][192]; K order = [h(128), x(64)].
@@ -366,7 +368,7 @@ extern "C" int dfb_gru_fused_forward(const void* h0, const float* offsets, const
   const int tiles = (n_pad + 127) / 128;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
-  if (gru_worker_warps() == 16) k_gru_fused_fwd<16><<<grid, 32 * 17, GF_SMEM, st>>>(maps, P);
+  if (gru_worker_warps(false) == 16) k_gru_fused_fwd<16><<<grid, 32 * 17, GF_SMEM, st>>>(maps, P);
   else k_gru_fused_fwd<8><<<grid, 32 * 9, GF_SMEM, st>>>(maps, P);
   add_launches(1);
   return check_launch("dfb_gru_fused_forward");
@@ -766,7 +768,7 @@ extern "C" int dfb_gru_fused_backward(const void* hsave, const void* xsave, cons
   const int tiles = (n_pad + 127) / 128;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
-  if (gru_worker_warps() == 16) k_gru_fused_bwd<16><<<grid, 32 * 17, GB_SMEM, st>>>(maps, P);
+  if (gru_worker_warps(true) == 16) k_gru_fused_bwd<16><<<grid, 32 * 17, GB_SMEM, st>>>(maps, P);
   else k_gru_fused_bwd<8><<<grid, 32 * 9, GB_SMEM, st>>>(maps, P);
   add_launches(1);
   return check_launch("dfb_gru_fused_backward");
