@@ -63,7 +63,8 @@ class ConvArgs(C.Structure):
                 ("stride", C.c_int), ("n_src", C.c_int), ("x", C.c_void_p * 2), ("cin", C.c_int * 2),
                 ("cin_total", C.c_int), ("cin_off", C.c_int), ("cout", C.c_int), ("w", C.c_void_p),
                 ("bias", C.c_void_p), ("y", C.c_void_p), ("y_fp32", C.c_int), ("stats", C.c_void_p),
-                ("x_lo", C.c_void_p * 2), ("split3", C.c_int), ("stats_sum_only", C.c_int)]
+                ("x_lo", C.c_void_p * 2), ("split3", C.c_int), ("stats_sum_only", C.c_int),
+                ("y2", C.c_void_p), ("cin2", C.c_int)]
 
 
 def sources():

@@ -34,6 +34,39 @@ class _timed:
             TIMING.append(self.rec)
 
 
+class _ZeroPool:
+    """Small zero-initialised accumulators (BatchNorm statistics, bias / affine gradients) carved from one zero-filled
+    chunk: a training step asks for ~200 of them, and one fill kernel per request is 200 tiny launches serialised
+    between the convolutions.  A chunk is handed out once and never recycled (its views keep it alive)."""
+    CHUNK = 1 << 20   # bytes
+
+    def __init__(self):
+        self.buf = {}
+
+    def take(self, shape, dtype, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = ((n * torch.empty((), dtype=dtype).element_size() + 255) // 256) * 256
+        if nbytes > self.CHUNK // 4:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        key = (device.type, device.index)
+        ent = self.buf.get(key)
+        if ent is None or ent[1] + nbytes > self.CHUNK:
+            ent = [torch.zeros(self.CHUNK, dtype=torch.uint8, device=device), 0]
+            self.buf[key] = ent
+        off = ent[1]
+        ent[1] += nbytes
+        return ent[0][off:off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
+
+
+_zeros = _ZeroPool()
+
+
+def zeros(shape, dtype, device):
+    return _zeros.take(tuple(shape) if not isinstance(shape, int) else (shape,), dtype, torch.device(device))
+
+
 def _halo(ksize, stride, cins):
     return ksize == 3 and stride == 1 and all(c % 64 == 0 for c in cins)
 
@@ -134,7 +167,7 @@ def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize
         gy, lo = split(gy)
         gy_lo, out_dtype = [lo], torch.float32
     gx = torch.empty((n, H, W, cin), dtype=out_dtype, device=gy.device)
-    stats = torch.zeros((2, cin), dtype=torch.float64, device=gy.device) if colsum else None
+    stats = zeros((2, cin), torch.float64, gy.device) if colsum else None
     a = _args(1, n, H, W, ksize, stride, [gy], [cin], cout, w_dgrad, None, gx, stats, cin_total, cin_off, xs_lo=gy_lo)
     a.stats_sum_only = int(colsum)
     kc = 64 if cout % 64 == 0 else 32
@@ -144,6 +177,25 @@ def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize
     if colsum:
         gx._dfb_colsum = stats[0]
     return gx
+
+
+def conv2d_dgrad_two(gy: torch.Tensor, w_dgrad, H, W, c0, c1, cin_total, ksize):
+    """1x1 stride-1 data gradient for BOTH sources of a concatenated input in one pass over gy:
+    -> (gx0 [n,H,W,c0], gx1 [n,H,W,c1]) bf16, each with its per-channel sum attached (``_dfb_colsum``)."""
+    assert gy.is_contiguous() and gy.dtype == torch.bfloat16 and ksize == 1
+    n, _, _, cout = gy.shape
+    gx0 = torch.empty((n, H, W, c0), dtype=torch.bfloat16, device=gy.device)
+    gx1 = torch.empty((n, H, W, c1), dtype=torch.bfloat16, device=gy.device)
+    stats = zeros((2, c0 + c1), torch.float64, gy.device)
+    a = _args(1, n, H, W, ksize, 1, [gy], [c0], cout, w_dgrad, None, gx0, stats, cin_total, 0)
+    a.stats_sum_only = 1
+    a.y2, a.cin2 = gx1.data_ptr(), c1
+    kc = 64 if cout % 64 == 0 else 32
+    with _timed(f"k_conv_igemm<{c0 + c1},{kc}>", 2.0 * n * H * W * cout * (c0 + c1), gy):
+        check(_lib.lib().dfb_conv2d(C.byref(a), _stream(gy)), "conv2d dgrad (two outputs)")
+    gx0._dfb_colsum = stats[0][:c0]
+    gx1._dfb_colsum = stats[0][c0:]
+    return gx0, gx1
 
 
 def bias_grad(gy: torch.Tensor) -> torch.Tensor:
@@ -213,7 +265,7 @@ def bn_gelu_backward(x, gy, bn, training, g_gamma, g_beta, g_bias):
 
 def channel_sum(g):
     Cn = g.shape[-1]
-    out = torch.zeros(Cn, dtype=torch.float32, device=g.device)
+    out = zeros((Cn,), torch.float32, g.device)
     check(_lib.lib().dfb_channel_sum(g.data_ptr(), Cn, g.numel() // Cn, out.data_ptr(), None,
                                      int(g.dtype == torch.float32), _stream(g)), "channel_sum")
     return out
@@ -280,6 +332,10 @@ class _Conv(torch.autograd.Function):
         ct = ctx.wshape[1]
         gw = conv2d_wgrad(xs, gy, k, 1)
         gxs, off = [None, None], 0
+        if (len(xs) == 2 and k == 1 and all(ctx.need) and gy.dtype == torch.bfloat16
+                and xs[0].shape[3] % 32 == 0 and xs[1].shape[3] % 32 == 0 and ct in (32, 64, 128, 256)):
+            g0, g1 = conv2d_dgrad_two(gy, wd, xs[0].shape[1], xs[0].shape[2], xs[0].shape[3], xs[1].shape[3], ct, k)
+            return gw, gb, g0, g1
         for i, x in enumerate(xs):
             c = x.shape[3]
             if ctx.need[i]:
@@ -299,7 +355,7 @@ class _ConvBnGelu(torch.autograd.Function):
     def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, stride, training, eps, momentum):
         wf, wd = packed(w, x.dtype == torch.float32)
         cout = w.shape[0]
-        stats = torch.zeros((2, cout), dtype=torch.float64, device=x.device) if training else None
+        stats = zeros((2, cout), torch.float64, x.device) if training else None
         raw = conv2d_forward([x], wf, b.detach().float().contiguous(), cout, 3, stride, stats)
         count = raw.numel() // cout
         bn = bn2d_finalize(stats, count, training, eps, momentum, gamma.detach().float(), beta.detach().float(),
@@ -314,7 +370,7 @@ class _ConvBnGelu(torch.autograd.Function):
         x, raw, bn, wd = ctx.saved_tensors
         stride, training, wshape = ctx.cfg
         cout, cin = wshape[0], wshape[1]
-        gg, gbeta, gbias = torch.zeros((3, cout), dtype=torch.float32, device=x.device).unbind(0)   # one fill
+        gg, gbeta, gbias = zeros((3, cout), torch.float32, x.device).unbind(0)
         graw = bn_gelu_backward(raw, gact.contiguous(), bn, training, gg, gbeta, gbias)
         gw = conv2d_wgrad([x], graw, 3, stride)
         gx = conv2d_dgrad(graw, wd, x.shape[1], x.shape[2], cin, cin, 0, 3, stride) if ctx.needs_input_grad[0] else None
@@ -325,8 +381,26 @@ def conv_bn_gelu(x, conv_mod, bn_mod, training):
     out = _ConvBnGelu.apply(x, conv_mod.weight, conv_mod.bias, bn_mod.weight, bn_mod.bias, bn_mod.running_mean,
                             bn_mod.running_var, conv_mod.stride[0], training, bn_mod.eps, bn_mod.momentum)
     if training:
-        bn_mod.num_batches_tracked += 1
+        _pending_nbt.append(bn_mod.num_batches_tracked)
     return out
+
+
+# BatchNorm2d.num_batches_tracked += 1 for every call, applied in one foreach launch per forward (flush_batch_counters)
+_pending_nbt = []
+
+
+def flush_batch_counters():
+    if _pending_nbt:
+        uniq, counts = {}, {}
+        for t in _pending_nbt:
+            uniq[id(t)] = t
+            counts[id(t)] = counts.get(id(t), 0) + 1
+        by_count = {}
+        for k, t in uniq.items():
+            by_count.setdefault(counts[k], []).append(t)
+        for c, ts in by_count.items():
+            torch._foreach_add_(ts, c)
+        _pending_nbt.clear()
 
 
 class _Upsample2x(torch.autograd.Function):

@@ -70,6 +70,7 @@ struct IgemmMaps {
   CUtensorMap a[MAX_AMAPS];
   CUtensorMap b;
   CUtensorMap out;   // bf16 output as [ch, x, y, n] with box [32, 8, 4, 1], SWIZZLE_64B (epilogue TMA stores)
+  CUtensorMap out2;  // second output of a split data-gradient launch (accumulator columns >= split_col); follows `out`
 };
 
 struct IgemmParams {
@@ -84,6 +85,8 @@ struct IgemmParams {
   const float* bias;   // [N] or null
   double* stats;       // [2][N] running sum / sum of squares over all output elements, or null
   int stats_sum_only;  // only the sums are wanted (bias gradient from a data-gradient launch)
+  int split_col;       // > 0: accumulator columns >= split_col are the channels of a second output tensor (maps.out2)
+  void* out2;          // that tensor [n, Ht, Wt, N - split_col] bf16 (sx = sy = 1, no offsets)
   // halo variant (3x3 stride 1): steps[] holds one entry per 64-channel chunk (wk = K offset of tap 0)
   int halo_pitch;      // pixels per halo row in shared memory (10 or 16)
   int halo_flip;       // data gradient: tap t reads halo offset (2 - t/3, 2 - t%3)
@@ -135,7 +138,9 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
 #pragma unroll 1
     for (int col = 32 * cg; col < N; col += 32 * (EPI_WARPS / 4)) {
       const int half = PAIR ? col / (N / 2) : 0;       // output row parity of this column block
-      const int ch0 = PAIR ? col % (N / 2) : col;      // first output channel of this column block
+      const bool second = !PAIR && P.split_col > 0 && col >= P.split_col;   // second output tensor of a split launch
+      const int ch0 = PAIR ? col % (N / 2) : col;      // channel index for bias / statistics
+      const int oc0 = second ? col - P.split_col : ch0;  // first channel inside the output tensor
       const int y = y0 + half;
       const bool valid = y < P.Ht && x < P.Wt;
       const long long off = off0 + (long long)half * P.out_row;
@@ -195,7 +200,7 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
         __syncwarp();
         if (lane == 0) {
           if (PAIR) tma_store_5d(out_map, stg, ch0, tx * TILE_W, half, ty * TILE_H + 4 * q, n);
-          else tma_store_4d(out_map, stg, col, tx * TILE_W, ty * TILE_H + 4 * q, n);
+          else tma_store_4d(second ? out_map + 1 : out_map, stg, oc0, tx * TILE_W, ty * TILE_H + 4 * q, n);
           tma_store_commit();
         }
         store_pending = true;
@@ -671,11 +676,18 @@ static bool halo_pair_enabled() {
 // out + n*img + (y*sy+oy)*row + (x*sx+ox)*pix + ch  (bf16) -> dims [ch, x, y, n], box [32, 8, 4, 1], SWIZZLE_64B.
 static int build_out_map(IgemmMaps& maps, const IgemmParams& P, int N) {
   if (P.out_fp32) return DFB_OK;
-  const uint64_t dims[4] = {(uint64_t)N, (uint64_t)P.Wt, (uint64_t)P.Ht, (uint64_t)P.n_img};
+  const uint64_t dims[4] = {(uint64_t)(P.split_col > 0 ? P.split_col : N), (uint64_t)P.Wt, (uint64_t)P.Ht, (uint64_t)P.n_img};
   const uint64_t str[3] = {(uint64_t)P.out_pix * P.sx * 2, (uint64_t)P.out_row * P.sy * 2, (uint64_t)P.out_img * 2};
   const uint32_t box[4] = {32, TILE_W, 4, 1};
   const char* base = (const char*)P.out + ((size_t)P.oy * P.out_row + (size_t)P.ox * P.out_pix) * 2;
-  return make_tensor_map_bf16(&maps.out, base, 4, dims, str, box, 64);
+  if (int rc = make_tensor_map_bf16(&maps.out, base, 4, dims, str, box, 64)) return rc;
+  if (P.split_col > 0) {   // second output: the remaining N - split_col channels, densely packed NHWC
+    const uint64_t c2 = (uint64_t)(N - P.split_col);
+    const uint64_t d2[4] = {c2, (uint64_t)P.Wt, (uint64_t)P.Ht, (uint64_t)P.n_img};
+    const uint64_t s2[3] = {c2 * 2, c2 * 2 * P.Wt, c2 * 2 * P.Wt * P.Ht};
+    return make_tensor_map_bf16(&maps.out2, P.out2, 4, d2, s2, box, 64);
+  }
+  return DFB_OK;
 }
 
 template <int N>
@@ -961,7 +973,12 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
     // ---------------------------------------------------------------- data gradient
     // source = gy [n, Ho, Wo, cout]; output gx [n, H, W, cin_slice]; weights Wd[ci][tap*cout + co] (rows = all cin_total
     // channels; the slice starts at row cin_off).
-    const int cout = a->cout, cin = a->cin[0];
+    const int cout = a->cout;
+    const bool split_out = a->y2 != nullptr;
+    if (split_out && (k != 1 || s != 1 || a->y_fp32 || S3 || a->cin[0] % 32 || a->cin2 % 32 || a->cin2 <= 0)) {
+      set_error("dfb_conv2d dgrad: a second output needs a 1x1 stride-1 bf16 launch with 32-channel multiples"); return DFB_ERR_UNSUPPORTED;
+    }
+    const int cin = a->cin[0] + (split_out ? a->cin2 : 0);   // accumulator columns
     const int K_HI = taps * cout;
     N = cin;
     KC = cout % 64 == 0 ? 64 : 32;
@@ -976,7 +993,8 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
     const uint32_t bb[2] = {(uint32_t)KC, (uint32_t)N};
     const char* wbase = (const char*)a->w + (size_t)a->cin_off * taps * cout * 2 * (1 + S3);
     if ((rc = make_tensor_map_bf16(&maps.b, wbase, 2, bd, bs, bb, KC * 2))) return rc;
-    P.out_img = (long long)H * W * cin; P.out_row = (long long)W * cin; P.out_pix = cin;
+    P.out_img = (long long)H * W * a->cin[0]; P.out_row = (long long)W * a->cin[0]; P.out_pix = a->cin[0];
+    if (split_out) { P.split_col = a->cin[0]; P.out2 = a->y2; }
     if (s == 1 && k == 3 && KC == 64 && halo_mode() > 0) {
       const int hm = halo_mode();
       P.Ht = H; P.Wt = W; P.sy = P.sx = 1; P.oy = P.ox = 0;

@@ -103,7 +103,7 @@ class _Decoder(torch.autograd.Function):
         dev = dflow.device
         st = _stream(dflow)
         dflow = dflow.contiguous().float()
-        z32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+        z32 = lambda *s: tc.zeros(s, torch.float32, dev)  # noqa: E731
         dy1 = torch.empty((n_pad, 32), dtype=DT, device=dev)
         gw2, gb2 = z32(3, 32), z32(3)
         check(lib.dfb_head_out_backward(y1.data_ptr(), w2f.data_ptr(), dflow.data_ptr(), n, n_pad, dy1.data_ptr(),
@@ -201,7 +201,7 @@ class _FusedGRUDecoder(torch.autograd.Function):
         dev = dflow.device
         st = _stream(dflow)
         dflow = dflow.contiguous().float()
-        z32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+        z32 = lambda *s: tc.zeros(s, torch.float32, dev)  # noqa: E731
         # MLP head
         dy1 = torch.empty((n_pad, 32), dtype=BF, device=dev)
         gw2, gb2 = z32(3, 32), z32(3)

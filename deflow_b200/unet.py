@@ -114,6 +114,7 @@ class FastFlow3DUNet(nn.Module):
         s = up(self.decoder_step1, (r0, r1), (l0, l1))
         t = up(self.decoder_step2, (s,), (f0, f1))
         u = up(self.decoder_step3, (t,), (img0, img1))
+        tc.flush_batch_counters()
         return tc.conv_bias(self.decoder_step4.weight, self.decoder_step4.bias, u)
 
     # cuDNN strict-fp32 comparator (use_library = True): not a product path, kept for tests that compare the

@@ -236,6 +236,11 @@ typedef struct {
   const void* x_lo[2];   /* split-precision mode: the lo halves of the sources (x[] are the hi halves) */
   int split3;            /* 1: operands are (hi, lo) bf16 pairs, weights packed with split3, K loop = hi*hi + hi*lo + lo*hi */
   int stats_sum_only;    /* 1: only stats[0][*] (the per-channel sums) is wanted, e.g. a bias gradient from a data-gradient launch */
+  void* y2;              /* mode 1, 1x1 stride 1, bf16 only: second output.  The launch then covers the input channels
+                            [cin_off, cin_off + cin[0] + cin2): the first cin[0] go to y [n,H,W,cin[0]], the next cin2 to
+                            y2 [n,H,W,cin2] -- the two sources of a concatenated input get their gradients from ONE pass
+                            over grad_y */
+  int cin2;
 } dfb_conv_args;
 int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, int split3, void* w_fwd, void* w_dgrad,
                           void* stream);

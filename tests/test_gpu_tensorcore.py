@@ -70,6 +70,22 @@ def test_conv_forward_dgrad_wgrad(case):
     assert _rel(gw2, 2 * wr.grad) <= 5e-5
 
 
+@pytest.mark.parametrize("c0,c1,cout,H,W", [(32, 32, 64, 40, 24), (64, 64, 128, 16, 16), (128, 128, 256, 16, 8)])
+def test_conv_dgrad_two_outputs_equals_two_launches(c0, c1, cout, H, W):
+    """1x1 data gradient of a two-source convolution: one launch writing both outputs == one launch per source."""
+    torch.manual_seed(c0 + cout)
+    n, ct = 2, c0 + c1
+    w = torch.randn(cout, ct, 1, 1, device=DEV) / ct ** 0.5
+    _, wd = conv.pack_weights(w)
+    gy = torch.randn(n, H, W, cout, device=DEV).to(torch.bfloat16)
+    a0 = conv.conv2d_dgrad(gy, wd, H, W, c0, ct, 0, 1, 1, colsum=True)
+    a1 = conv.conv2d_dgrad(gy, wd, H, W, c1, ct, c0, 1, 1, colsum=True)
+    b0, b1 = conv.conv2d_dgrad_two(gy, wd, H, W, c0, c1, ct, 1)
+    assert torch.equal(a0, b0) and torch.equal(a1, b1)
+    assert _rel(b0._dfb_colsum.float(), a0._dfb_colsum.float()) <= 1e-6
+    assert _rel(b1._dfb_colsum.float(), a1._dfb_colsum.float()) <= 1e-6
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_split_precision_matches_fp32(case):
     """Parity mode: fp32 tensors, operands as (hi, lo) bf16 pairs, hi*hi + hi*lo + lo*hi on the tensor cores."""
