@@ -381,9 +381,13 @@ def run_native(args):
                           for k, v in fam.items()), key=lambda r: -r["ms_per_step"])
         if kernels:
             top = kernels[0]
-            # ncu --set full (profiles/r01_ncu_full_main_kernels.txt): a 64->64 3x3 launch at 512^2 x 16 reads 0.537 GB and
-            # writes 0.487 GB of DRAM = its input + output tensors once (algorithmic bytes 1.07 GB): no re-reads.
-            traffic = 1.02e9 if top["kernel"] == "k_conv_igemm_halo<64>" else None
+            # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this command
+            # (profiles/r01_traffic.json, written by tools/traffic_table.py: dram__bytes_read.sum + dram__bytes_write.sum,
+            # averaged over the captured launches of that kernel)
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get(top["kernel"], {}).get("dram_bytes_per_launch")
             roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": peaks["bf16_tflops_sustained"],
                     "unit": "TFLOP/s", "frac": top["frac_of_sustained_peak"], "traffic": traffic,
                     "avg_launch_ms": top["avg_launch_ms"], "share_of_step": top["ms_per_step"] / ms,
