@@ -50,3 +50,44 @@ def test_synthetic_batch_layout():
     m = ext.unique_pillars(info["voxel_coords"].numpy())[0].shape[0]
     n = info["points"].shape[0]
     assert 0.03 < m / n < 0.5 and n < int(ok.sum())
+
+
+def test_split_frames_backward_is_the_slicing_gradient():
+    """deflow._SplitFrames: same values and gradients as image[:B], image[B:] (one concatenation instead of two
+    zero-filled slice gradients and an add)."""
+    from deflow_b200.deflow import _SplitFrames
+    torch.manual_seed(0)
+    x = torch.randn(6, 4, 5, 3, requires_grad=True)
+    a, b = _SplitFrames.apply(x, 2)
+    assert torch.equal(a, x[:2]) and torch.equal(b, x[2:])
+    (a.square().sum() + (3 * b).sum()).backward()
+    xr = x.detach().clone().requires_grad_(True)
+    (xr[:2].square().sum() + (3 * xr[2:]).sum()).backward()
+    assert torch.equal(x.grad, xr.grad)
+    # one branch unused: its half of the gradient is zero
+    y = torch.randn(4, 2, requires_grad=True)
+    a, b = _SplitFrames.apply(y, 1)
+    a.sum().backward()
+    assert torch.equal(y.grad, torch.cat([torch.ones(1, 2), torch.zeros(3, 2)]))
+
+
+def test_zero_pool_hands_out_disjoint_zeroed_views():
+    from deflow_b200 import conv
+    ts = [conv.zeros(s, dt, "cpu") for s, dt in [((2, 64), torch.float64), ((3, 32), torch.float32), ((5,), torch.float32),
+                                                 ((2, 256), torch.float64), ((1 << 19,), torch.float32)]]
+    for i, t in enumerate(ts):
+        assert float(t.abs().sum()) == 0.0
+        t += i + 1                       # writing one view must not touch the others
+    for i, t in enumerate(ts):
+        assert float(t.min()) == float(t.max()) == i + 1
+    assert ts[0].dtype == torch.float64 and ts[0].shape == (2, 64) and ts[0].data_ptr() % 8 == 0
+
+
+def test_batch_counters_flush_once_per_forward():
+    from deflow_b200 import conv
+    a, b = torch.zeros((), dtype=torch.long), torch.zeros((), dtype=torch.long)
+    conv._pending_nbt.extend([a, b, a])   # an encoder BatchNorm is called twice per forward (pc0, pc1), a decoder-side one once
+    conv.flush_batch_counters()
+    assert int(a) == 2 and int(b) == 1 and not conv._pending_nbt
+    conv.flush_batch_counters()
+    assert int(a) == 2 and int(b) == 1
