@@ -288,61 +288,6 @@ __global__ void __launch_bounds__(IDX_BLOCK) k_compact(
   }
 }
 
-// Variant (DFB_COMPACT=loop): one block scan per item, everything of an item finished before the next is touched.
-__global__ void __launch_bounds__(IDX_BLOCK) k_compact_loop(
-    const float* __restrict__ pts, int Nmax, int stride, VoxelParams P, int Wd,
-    int nblk, int F, int HW, const unsigned* __restrict__ bitmap, const int* __restrict__ word_rank,
-    const int* __restrict__ seg_base, int S, const int* __restrict__ blk_off, const int* __restrict__ counts, float* __restrict__ pt_xyz,
-    int* __restrict__ pt_coor, long long* __restrict__ pt_idx, float* __restrict__ pt_offs,
-    int* __restrict__ pt_pillar, int* __restrict__ pt_slot, int* __restrict__ pil_cnt, int* __restrict__ pil_coor,
-    int* __restrict__ pil_pix) {
-  __shared__ int sm[33];
-  const int f = blockIdx.y, blk = blockIdx.x;
-  const float* p = pts + (size_t)f * Nmax * stride;
-  const int pt_base = counts[2 * F + f] + blk_off[f * nblk + blk];
-  const int pil_base = counts[3 * F + 1 + f];
-  int carry = 0;
-  const float hx = P.vx / 2, hy = P.vy / 2, hz = P.vz / 2;
-  const float qnan = __int_as_float(0x7fc00000);
-#pragma unroll 1
-  for (int j = 0; j < IDX_ITEMS; ++j) {
-    const int i = blk * IDX_CHUNK + j * IDX_BLOCK + threadIdx.x;
-    float x = qnan, y = qnan, z = qnan;
-    if (i < Nmax) { x = p[(size_t)i * stride]; y = p[(size_t)i * stride + 1]; z = p[(size_t)i * stride + 2]; }
-    const int key = point_key(x, y, z, P);
-    int tot;
-    const int ex = block_excl_scan<IDX_BLOCK>(key >= 0 ? 1 : 0, sm, tot);
-    if (key >= 0) {
-      const int dst = pt_base + carry + ex;
-      const int cx = key % P.gx, t = key / P.gx, cy = t % P.gy, cz = t / P.gy;
-      pt_xyz[3 * (size_t)dst] = x;
-      pt_xyz[3 * (size_t)dst + 1] = y;
-      pt_xyz[3 * (size_t)dst + 2] = z;
-      pt_coor[3 * (size_t)dst] = cz;
-      pt_coor[3 * (size_t)dst + 1] = cy;
-      pt_coor[3 * (size_t)dst + 2] = cx;
-      pt_idx[dst] = i;
-      pt_offs[3 * (size_t)dst] = __fsub_rn(x, __fadd_rn(__fadd_rn(__fmul_rn((float)cx, P.vx), P.lox), hx));
-      pt_offs[3 * (size_t)dst + 1] = __fsub_rn(y, __fadd_rn(__fadd_rn(__fmul_rn((float)cy, P.vy), P.loy), hy));
-      pt_offs[3 * (size_t)dst + 2] = __fsub_rn(z, __fadd_rn(__fadd_rn(__fmul_rn((float)cz, P.vz), P.loz), hz));
-      const unsigned word = bitmap[(size_t)f * Wd + (key >> 5)];
-      const int rank = seg_base[f * S + (key >> 15)] + word_rank[(size_t)f * Wd + (key >> 5)] +
-                       __popc(word & ((1u << (key & 31)) - 1u));
-      const int q = pil_base + rank;
-      pt_pillar[dst] = q;
-      const int slot = atomicAdd(&pil_cnt[q], 1);
-      pt_slot[dst] = slot;
-      if (slot == 0) {
-        pil_coor[3 * (size_t)q] = cz;
-        pil_coor[3 * (size_t)q + 1] = cy;
-        pil_coor[3 * (size_t)q + 2] = cx;
-        pil_pix[q] = f * HW + cy * P.gx + cx;
-      }
-    }
-    carry += tot;
-  }
-}
-
 // ---------------------------------------------------------------- K4: CSR offsets of the pillars
 // Points and pillars are both stored frame after frame, so pil_start is ONE global exclusive scan of pil_cnt.  Two
 // levels in one launch: block-local scans of 2048 pillars (-> pil_loc, block totals); the last block to finish scans
@@ -398,7 +343,7 @@ __global__ void __launch_bounds__(256) k_fill_csr(const int* __restrict__ counts
   const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int q = t0; q < M; q += stride) pil_start[q] = pil_loc[q] + blk_base[q / PSCAN_ITEMS];
   if (t0 == 0) pil_start[M] = n;
-  // four points per thread and iteration, every load of the four issued before the first dependent gather
+  // U points per thread and iteration, every load of the U issued before the first dependent gather
   for (int p0 = t0; p0 < n; p0 += U * stride) {
     int q[U], sl[U];
     float x[U], y[U], z[U];
@@ -421,12 +366,6 @@ __global__ void __launch_bounds__(256) k_fill_csr(const int* __restrict__ counts
       csr_rec[j[u]] = make_float4(x[u], y[u], z[u], __int_as_float(q[u]));
     }
   }
-}
-
-// tuning switches (diagnostic): integer environment variable, read on every call (cheap next to a launch sequence)
-static int env_flag(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
 }
 
 VoxelParams make_voxel_params(const float* vs, const float* rng) {
@@ -510,14 +449,9 @@ extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
   }
   if (a->Nmax > 0) {
     dim3 g((unsigned)nblk_, F);
-    if (env_flag("DFB_COMPACT_LOOP", 0))
-      k_compact_loop<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
-                                              a->word_rank, seg_base, S, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
-                                              a->pt_offs, a->pt_pillar, a->pt_slot, a->pil_cnt, a->pil_coor, a->pil_pix);
-    else
-      k_compact<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
-                                         a->word_rank, seg_base, S, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
-                                         a->pt_offs, a->pt_pillar, a->pt_slot, a->pil_cnt, a->pil_coor, a->pil_pix);
+    k_compact<<<g, IDX_BLOCK, 0, st>>>(a->pts, a->Nmax, a->pt_stride, P, Wd, nblk, F, P.gx * P.gy, a->bitmap,
+                                       a->word_rank, seg_base, S, a->blk_cnt, a->counts, a->pt_xyz, a->pt_coor, a->pt_idx,
+                                       a->pt_offs, a->pt_pillar, a->pt_slot, a->pil_cnt, a->pil_coor, a->pil_pix);
   }
   k_pillar_scan<<<nb, 1024, 0, st>>>(a->pil_cnt, a->counts, F, pil_loc, blk_tot, blk_base, a->tickets + 1);
   {
@@ -526,15 +460,10 @@ extern "C" int dfb_pillar_index(const dfb_index_args* a, void* stream_) {
     int maxb = sm_count() * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    if (env_flag("DFB_FILL_U", 1) >= 4)
-      k_fill_csr<4><<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pt_xyz, pil_loc, blk_base,
-                                            a->pil_start, a->sorted_pt, (float4*)a->csr_rec);
-    else if (env_flag("DFB_FILL_U", 1) == 2)
-      k_fill_csr<2><<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pt_xyz, pil_loc, blk_base,
-                                            a->pil_start, a->sorted_pt, (float4*)a->csr_rec);
-    else
-      k_fill_csr<1><<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pt_xyz, pil_loc, blk_base,
-                                            a->pil_start, a->sorted_pt, (float4*)a->csr_rec);
+    // one point per thread and iteration: two or four in flight measured SLOWER on B200 (r01 sweep: the random 16-byte
+    // CSR writes then spread over a wider window and more partially written sectors are evicted before they fill)
+    k_fill_csr<1><<<blocks, 256, 0, st>>>(a->counts, F, (int)cap, a->pt_pillar, a->pt_slot, a->pt_xyz, pil_loc, blk_base,
+                                          a->pil_start, a->sorted_pt, (float4*)a->csr_rec);
   }
   add_launches(a->Nmax > 0 ? 5 : 3);
   return check_launch("dfb_pillar_index");

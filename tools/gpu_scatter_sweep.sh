@@ -1,5 +1,7 @@
 #!/bin/bash
 # Scatter-path variant sweep (diagnostic env switches) + ncu captures.  Outputs under gpurun_out/.
+# Historical: run at commit 60d604d (results: profiles/r01_scatter_variant_sweep.txt); the DFB_COMPACT_LOOP / DFB_FILL_U /
+# DFB_MARK_PRECHECK / DFB_PFN_POINTS switches it sets selected variants that lost and have been removed since.
 mkdir -p gpurun_out
 T="timeout -s KILL"
 run() {  # name, env...
