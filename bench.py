@@ -279,10 +279,12 @@ def run_native(args):
         return float(ms) / steps, out
 
     n_warm = args.warmup if os.environ.get("DFB_PROFILE") else max(args.warmup, 3)  # profiling runs may warm up less
+    # the sampler starts BEFORE the warm-up: nvidia-smi's start-up takes a driver lock for tens of milliseconds, which
+    # must not land inside the timed region (it samples every 200 ms through warm-up and the timed steps, all under load)
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(n_warm):
         loss = step(resident)
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
     from deflow_b200 import conv as tcconv
     ms, loss = timed(lambda: step(resident), args.steps)
