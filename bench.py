@@ -403,7 +403,7 @@ def run_native(args):
                     "frac": whole / peaks["bf16_tflops_sustained"], "traffic": None,
                     "note": "whole-step algorithmic FLOPs / step time (fp32 parity mode: dense contractions in cuDNN/cuBLAS)"}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU baseline is timed at N = 1 only (rank 0 would stall the others)
             pts = args.cpu_points or args.points
             v, t, cores = cpu_reference_pairs_per_sec(pts, args.grid, args.decoder, args.loss, 6, 1)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
