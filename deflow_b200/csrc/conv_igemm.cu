@@ -1360,6 +1360,129 @@ static int launch_wgrad_halo(const WgradMaps& maps, const WgradHaloParams& P, cu
   return check_launch("conv_wgrad_halo");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-shift weight gradient for 3x3 stride-1 convolutions with 64 output channels (EXPERIMENTAL: built, not yet
+// validated on a GPU, off unless DFB_WGRAD_X=1).
+//   gW[(ky,kx)][co][ci] = sum_p gy[p, co] x[p + (ky-1, kx-1), ci] = sum_p' gy[p' - (ky-1, 0), co] x[p' + (0, kx-1), ci]
+// so the three kx taps are HORIZONTAL shifts of an x box ([8 rows x 10 cols] x 64 channels, taps stacked along M like
+// in k_conv_wgrad_halo) and the three ky taps are VERTICAL shifts of a gy box ([10 rows x 8 cols] x 64 channels)
+// stacked along N: N group g starts g box rows (1024 B) in = tap ky = 2 - g.  Per 16-pixel K slice: two M = 128 x
+// N = 192 MMAs (kx pairs (0,1) and (1,2), the repeated kx = 1 rows dropped) instead of five M = 128 x N = 64 ones,
+// which are bound by the A-operand fetch (70 cycles for 32 cycles of math) -- ~1.75x by the measured MMA times.
+// Out-of-range box rows / columns are zero-filled by TMA: exactly the padding (x) and the missing output pixels (gy).
+constexpr int WX_BOX_BYTES = 80 * 128;      // 80 pixel rows of 128 B (10 KB, 1024-aligned) for either box
+struct WgradXCfg {
+  static constexpr int STAGE_BYTES = 2 * WX_BOX_BYTES;
+  static constexpr int STAGES = 8;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;     // two accumulators of 192 columns
+};
+
+struct WgradXParams {
+  int n_img, Ht, Wt, tiles_x, tiles_y, num_tiles;
+  int n_items, splits;          // grid = n_items * splits
+  int cin_total, cout;
+  float* wacc;
+  int8_t map[8];                // per item: x tensor map
+  int16_t c0[8], ci_glob[8];    // per item: channel offset in the source / in the layer's cin_total
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad_x(const __grid_constant__ WgradMaps maps,
+                                                                const __grid_constant__ WgradXParams P) {
+  using Cfg = WgradXCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x % P.n_items, split = blockIdx.x / P.n_items;
+  const int per = (P.num_tiles + P.splits - 1) / P.splits;
+  const int t_begin = split * per, t_end = min(P.num_tiles, t_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < MAX_AMAPS; ++i) tma_prefetch_desc(&maps.a[i]);
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
+        const int x0 = tx * 8, y0 = ty * 8;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[stage], 2 * WX_BOX_BYTES);
+        tma_load_4d(a_dst, &maps.a[P.map[item]], &full[stage], P.c0[item], x0 - 1, y0, n);      // x: [8 rows][10 cols]
+        tma_load_4d(a_dst + WX_BOX_BYTES, &maps.a[MAX_AMAPS - 1], &full[stage], 0, x0, y0 - 1, n); // gy: [10 rows][8 cols]
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // whole-warp issue loop, (lo, hi) descriptor halves (see k_conv_wgrad_halo)
+    constexpr uint32_t idesc = make_idesc_bf16(128, 192, 1, 1);
+    const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 0, 1280, 2) >> 32);   // x: 8-pixel K groups one box row (10 px) apart
+    const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 0, 1024, 2) >> 32);   // gy: 8-pixel K groups one box row (8 px) apart
+    const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+    const uint32_t a_lo0 = smem_lo + ((128u >> 4) << 16);                                       // M groups: kx, kx + 1 (one pixel apart)
+    const uint32_t b_lo0 = smem_lo + (uint32_t)(WX_BOX_BYTES >> 4) + ((1024u >> 4) << 16);      // N groups: ky = 2, 1, 0 (one row apart)
+    int stage = 0;
+    uint32_t phase = 0, accum = 0u;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t soff = (uint32_t)stage * (uint32_t)(Cfg::STAGE_BYTES >> 4);
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {       // kx pairs (0, 1) and (1, 2)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)          // 16 pixels = 2 box rows: x advances 2 x 1280 B, gy 2 x 1024 B
+          umma_bf16_lohi_warp(tmem_base + pr * 192, a_lo0 + soff + (uint32_t)pr * 8u + (uint32_t)(k * 160), a_hi,
+                              b_lo0 + soff + (uint32_t)(k * 128), b_hi, idesc, accum | (uint32_t)(k > 0));
+      }
+      accum = 1u;
+      umma_commit_warp(&empty[stage]);
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+    umma_commit_warp(acc_full);
+  } else if (t_end > t_begin) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int ci = P.ci_glob[item] + (m & 63);
+    for (int pr = 0; pr < 2; ++pr) {
+      const int kx = pr + (m >> 6);
+      const bool live = ci < P.cin_total && !(pr == 1 && m < 64);   // kx = 1 was already covered by pair 0
+#pragma unroll 1
+      for (int col = 0; col < 192; col += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + pr * 192 + col, v);
+        const int ky = 2 - col / 64, co0 = col % 64;
+        float* dst = P.wacc + ((size_t)(ky * 3 + kx) * P.cout + co0) * P.cin_total + ci;
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)i * P.cin_total, v[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
 // wacc [taps][cout][cin] -> torch [cout][cin][taps]; accumulate = grad += (autograd accumulation)
 __global__ void __launch_bounds__(256) k_unpack_wgrad(const float* __restrict__ wacc, int cout, int cin, int taps,
                                                       float* __restrict__ gw, int accumulate) {
@@ -1426,6 +1549,54 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
   int ng = 0;
   if (s == 1 && k == 3 && halo_wgrad_enabled()) {
     // ---------------------------------------------------------------- halo variant
+    {
+      const char* ex = getenv("DFB_WGRAD_X");   // experimental cross-shift kernel (k_conv_wgrad_x), 64 output channels only
+      int n_chunks = 0;
+      for (int i = 0; i < a->n_src; ++i) n_chunks += (a->cin[i] + 63) / 64;
+      if (ex && atoi(ex) == 1 && a->cout == 64 && n_chunks <= 8) {
+        tc::WgradXParams X;
+        memset(&X, 0, sizeof(X));
+        const uint32_t xbox[4] = {64, 10, 8, 1}, gbox[4] = {64, 8, 10, 1};
+        int ni = 0, coff = 0;
+        for (int i = 0; i < a->n_src; ++i) {
+          const uint64_t C = a->cin[i];
+          const uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)a->n};
+          const uint64_t str[3] = {C * 2, C * 2 * W, C * 2 * W * H};
+          if ((rc = make_tensor_map_bf16(&maps.a[i], a->x[i], 4, dims, str, xbox, 128))) return rc;
+          for (int c0 = 0; c0 < a->cin[i]; c0 += 64) { X.map[ni] = (int8_t)i; X.c0[ni] = (int16_t)c0; X.ci_glob[ni] = (int16_t)(coff + c0); ++ni; }
+          coff += a->cin[i];
+        }
+        {
+          const uint64_t C = a->cout;
+          const uint64_t dims[4] = {C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)a->n};
+          const uint64_t str[3] = {C * 2, C * 2 * Wo, C * 2 * Wo * Ho};
+          if ((rc = make_tensor_map_bf16(&maps.a[tc::MAX_AMAPS - 1], a->y, 4, dims, str, gbox, 128))) return rc;
+        }
+        X.n_items = ni;
+        X.n_img = a->n; X.Ht = Ho; X.Wt = Wo;
+        X.tiles_x = (Wo + 7) / 8; X.tiles_y = (Ho + 7) / 8;
+        X.num_tiles = X.tiles_x * X.tiles_y * a->n;
+        int splits = (2 * sm_count() + ni - 1) / ni;
+        if (splits > X.num_tiles) splits = X.num_tiles;
+        if (splits < 1) splits = 1;
+        X.splits = splits;
+        X.cin_total = cin_total; X.cout = a->cout; X.wacc = wacc;
+        const size_t total = (size_t)taps * a->cout * cin_total;
+        cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
+        static bool configured = false;
+        if (!configured) {
+          cudaError_t e = cudaFuncSetAttribute(tc::k_conv_wgrad_x, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WgradXCfg::SMEM);
+          if (e != cudaSuccess) { set_error("wgrad_x: cannot reserve shared memory: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+          configured = true;
+        }
+        tc::k_conv_wgrad_x<<<ni * splits, tc::WG_THREADS, tc::WgradXCfg::SMEM, st>>>(maps, X);
+        long long blocks = ((long long)total + 255) / 256;
+        if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+        tc::k_unpack_wgrad<<<(int)blocks, 256, 0, st>>>(wacc, a->cout, cin_total, taps, grad_w, accumulate);
+        add_launches(2);
+        return check_launch("dfb_conv2d_wgrad (cross-shift)");
+      }
+    }
     tc::WgradHaloParams Q;
     memset(&Q, 0, sizeof(Q));
     const uint32_t hbox[4] = {64, 10, 10, 1};
