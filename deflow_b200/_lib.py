@@ -67,6 +67,12 @@ class ConvArgs(C.Structure):
                 ("y2", C.c_void_p), ("cin2", C.c_int)]
 
 
+class PackDesc(C.Structure):
+    """dfb_pack_desc"""
+    _fields_ = [("w", C.c_void_p), ("w_fwd", C.c_void_p), ("w_dgrad", C.c_void_p), ("first", C.c_longlong),
+                ("cout", C.c_int), ("cin", C.c_int), ("ksize", C.c_int), ("pad_", C.c_int)]
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -126,6 +132,7 @@ def _declare(lib):
         "dfb_decoder_gather_backward": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
         "dfb_flow_loss": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
         "dfb_conv_pack_weights": [vp, i32, i32, i32, i32, vp, vp, vp],
+        "dfb_conv_pack_weights_multi": [vp, i32, i64, i32, vp],
         "dfb_split_bf16x2": [vp, i64, vp, vp, vp],
         "dfb_conv2d": [C.POINTER(ConvArgs), vp],
         "dfb_conv2d_wgrad": [C.POINTER(ConvArgs), vp, vp, i32, vp],
@@ -159,7 +166,7 @@ def _declare(lib):
 EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size", "dfb_dynamic_voxelize_forward",
            "dfb_scatter_index", "dfb_scatter_reduce", "dfb_dynamic_point_to_voxel_backward", "dfb_index_workspace",
            "dfb_index_scan_workspace", "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_zero_fill", "dfb_clear_rows", "dfb_decoder_gather",
-           "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_split_bf16x2", "dfb_conv2d", "dfb_conv2d_wgrad",
+           "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_conv_pack_weights_multi", "dfb_split_bf16x2", "dfb_conv2d", "dfb_conv2d_wgrad",
            "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",
            "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",

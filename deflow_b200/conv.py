@@ -1,6 +1,6 @@
 """Host side of the tensor-core convolution kernels (deflow_b200/csrc/conv_igemm.cu): NHWC bf16 activations,
 weights kept in the reference's torch layout [Cout, Cin, k, k] fp32 (state_dict contract) and re-packed to
-bf16 GEMM operands on the device every step.  OSF = /root/reference/OpenSceneFlow (unet.py:49-68)."""
+bf16 GEMM operands on the device at the start of EVERY forward (WeightBank: one launch for all layers, no cache).  OSF = /root/reference/OpenSceneFlow (unet.py:49-68)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -175,7 +175,7 @@ def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize
     with _timed(name, 2.0 * n * gy.shape[1] * gy.shape[2] * cout * cin * ksize * ksize, gy):
         check(_lib.lib().dfb_conv2d(C.byref(a), _stream(gy)), "conv2d dgrad")
     if colsum:
-        gx._dfb_colsum = stats[0]
+        gx._dfb_colsum = (stats[0], gx._version)
     return gx
 
 
@@ -193,16 +193,18 @@ def conv2d_dgrad_two(gy: torch.Tensor, w_dgrad, H, W, c0, c1, cin_total, ksize):
     kc = 64 if cout % 64 == 0 else 32
     with _timed(f"k_conv_igemm<{c0 + c1},{kc}>", 2.0 * n * H * W * cout * (c0 + c1), gy):
         check(_lib.lib().dfb_conv2d(C.byref(a), _stream(gy)), "conv2d dgrad (two outputs)")
-    gx0._dfb_colsum = stats[0][:c0]
-    gx1._dfb_colsum = stats[0][c0:]
+    gx0._dfb_colsum = (stats[0][:c0], gx0._version)
+    gx1._dfb_colsum = (stats[0][c0:], gx1._version)
     return gx0, gx1
 
 
 def bias_grad(gy: torch.Tensor) -> torch.Tensor:
     """sum over pixels of gy: taken from the producing data-gradient kernel's epilogue when available."""
     cs = getattr(gy, "_dfb_colsum", None)
-    if cs is not None and cs.shape[0] == gy.shape[-1]:
-        return cs.float()
+    # valid only while gy is the very tensor the data-gradient kernel wrote: autograd accumulating a second consumer's
+    # gradient into it in place bumps its version, and then the sums are recomputed
+    if cs is not None and cs[1] == gy._version and cs[0].shape[0] == gy.shape[-1]:
+        return cs[0].float()
     return channel_sum(gy)
 
 
@@ -286,21 +288,93 @@ def upsample2x(x, backward=False):
 # ----------------------------------------------------------------------------------------------
 # autograd wiring
 # ----------------------------------------------------------------------------------------------
+class WeightBank:
+    """bf16 GEMM operands of every convolution weight of a module tree, re-packed from the fp32 masters by ONE kernel
+    launch at the start of every forward (``refresh``).  Nothing is cached across forwards: an optimizer step is
+    invisible to autograd's version counters (``torch.optim.Adam(fused=True)`` does not bump ``_version``, neither does
+    ``param.data.copy_``), so any cache keyed on the parameter goes stale -- which froze the UNet at its step-1
+    weights in round 1.  The packed buffers persist (same storage every step); the device descriptor table is rebuilt
+    only when a parameter's storage moves (``.to(device)``, ``load_state_dict`` with assign)."""
+
+    def __init__(self, weights: Sequence[torch.Tensor]):
+        self.weights = list(weights)
+        assert 0 < len(self.weights) <= 64
+        self._key = None
+        self._table = {}
+        self._bufs = {}
+
+    def _build(self, split3: bool):
+        dev = self.weights[0].device
+        m = 2 if split3 else 1
+        n_el = [w.numel() for w in self.weights]
+        bufs = []
+        descs = (_lib.PackDesc * len(self.weights))()
+        first = 0
+        for i, w in enumerate(self.weights):
+            cout, cin, k, _ = w.shape
+            assert w.dtype == torch.float32 and w.is_contiguous() and w.device == dev
+            wf = torch.empty((cout, m * k * k * cin), dtype=torch.bfloat16, device=dev)
+            wd = torch.empty((cin, m * k * k * cout), dtype=torch.bfloat16, device=dev)
+            bufs.append((wf, wd))
+            d = descs[i]
+            d.w, d.w_fwd, d.w_dgrad, d.first = w.data_ptr(), wf.data_ptr(), wd.data_ptr(), first
+            d.cout, d.cin, d.ksize = cout, cin, k
+            first += n_el[i]
+        host = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).clone()
+        self._table[split3] = (host.to(dev), first)
+        self._bufs[split3] = bufs
+
+    def refresh(self, split3: bool):
+        """Pack every weight now (one launch) and hang (token, w_fwd, w_dgrad) on its parameter for ``packed``;
+        returns the token of this refresh."""
+        key = tuple((w.data_ptr(), w.device) for w in self.weights)
+        if key != self._key:
+            self._key, self._table, self._bufs = key, {}, {}
+        if split3 not in self._table:
+            self._build(split3)
+        table, total = self._table[split3]
+        w0 = self.weights[0]
+        check(_lib.lib().dfb_conv_pack_weights_multi(table.data_ptr(), len(self.weights), total, int(split3), _stream(w0)),
+              "pack_weights_multi")
+        WeightBank._tokens += 1
+        token = WeightBank._tokens
+        name = "_dfb_packed3" if split3 else "_dfb_packed"
+        for w, pair in zip(self.weights, self._bufs[split3]):
+            setattr(w, name, (token, pair[0], pair[1]))
+        return token
+
+    _tokens = 0
+
+
+# tokens of the refreshes whose forward is running: packed() serves only operands packed by one of them
+_live_tokens: List[int] = []
+
+
+class bank_scope:
+    """``with bank_scope(bank, split3):`` -- refresh the bank and let ``packed`` serve its operands inside the block."""
+
+    def __init__(self, bank: WeightBank, split3: bool):
+        self.bank, self.split3 = bank, split3
+
+    def __enter__(self):
+        _live_tokens.append(self.bank.refresh(self.split3))
+
+    def __exit__(self, *a):
+        _live_tokens.pop()
+
+
 def packed(w: torch.Tensor, split3: bool = False):
-    """bf16 GEMM operands of a weight, re-packed only when the parameter changed (optimizer step / load_state_dict).
-    The cache lives ON the parameter object (not in a table keyed by id(): a freed parameter's id, version and
-    data_ptr can all be reused by a new model's parameter)."""
-    name = "_dfb_packed3" if split3 else "_dfb_packed"
-    hit = getattr(w, name, None)
-    if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
-        return hit[2], hit[3]
-    wf, wd = pack_weights(w, True, split3)
-    setattr(w, name, (w._version, w.data_ptr(), wf, wd))
-    return wf, wd
+    """bf16 GEMM operands of a convolution weight.  Inside a ``bank_scope`` they are the ones the bank packed at the
+    start of THIS forward; anywhere else the weight is packed on the spot (never served from a cache: see WeightBank)."""
+    hit = getattr(w, "_dfb_packed3" if split3 else "_dfb_packed", None)
+    if hit is not None and hit[0] in _live_tokens:
+        return hit[1], hit[2]
+    return pack_weights(w, True, split3)
 
 
 def packed_raw(w4: torch.Tensor, split3: bool = False):
-    """Packed operands of a derived (non-parameter) weight tensor: cached on the tensor object itself."""
+    """Packed operands of a derived (non-parameter) weight tensor built inside one forward: cached on that tensor
+    object, which does not outlive the autograd graph of the call."""
     name = "_dfb_packed3" if split3 else "_dfb_packed"
     hit = getattr(w4, name, None)
     if hit is None:

@@ -759,6 +759,46 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
   }
 }
 
+// All convolution weights of a model in ONE launch (run at the start of every forward: the optimizer has just changed the
+// fp32 masters).  table[i].first = index of weight i's first element in the concatenated element space; a thread finds its
+// weight by binary search over the (<= 64 entry) table held in shared memory.
+__global__ void __launch_bounds__(256) k_pack_weights_multi(const dfb_pack_desc* __restrict__ table, int n_w, long long total,
+                                                            int split3) {
+  __shared__ dfb_pack_desc sd[64];
+  for (int i = threadIdx.x; i < n_w; i += blockDim.x) sd[i] = table[i];
+  __syncthreads();
+  const int m = split3 ? 2 : 1;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    int lo_i = 0, hi_i = n_w - 1;
+    while (lo_i < hi_i) {
+      const int mid = (lo_i + hi_i + 1) >> 1;
+      if (sd[mid].first <= g) lo_i = mid; else hi_i = mid - 1;
+    }
+    const dfb_pack_desc& d = sd[lo_i];
+    const long long e = g - d.first;
+    const int taps = d.ksize * d.ksize, Cin = d.cin, Cout = d.cout;
+    const int t = (int)(e % taps);
+    const int ci = (int)((e / taps) % Cin);
+    const int co = (int)(e / ((long long)taps * Cin));
+    const float f = d.w[e];
+    const __nv_bfloat16 v = __float2bfloat16_rn(f);
+    const __nv_bfloat16 l = __float2bfloat16_rn(f - __bfloat162float(v));
+    const long long kf = (long long)taps * Cin, kd = (long long)taps * Cout;
+    __nv_bfloat16* wf = (__nv_bfloat16*)d.w_fwd;
+    __nv_bfloat16* wd = (__nv_bfloat16*)d.w_dgrad;
+    if (wf) {
+      const long long o = (long long)co * kf * m + (long long)t * Cin + ci;
+      wf[o] = v;
+      if (split3) wf[o + kf] = l;
+    }
+    if (wd) {
+      const long long o = (long long)ci * kd * m + (long long)t * Cout + co;
+      wd[o] = v;
+      if (split3) wd[o + kd] = l;
+    }
+  }
+}
+
 // fp32 -> (hi, lo) bf16 pair with hi + lo = x to ~16 significant bits
 __global__ void __launch_bounds__(256) k_split_bf16x2(const float4* __restrict__ x, long long n4, uint2* __restrict__ hi,
                                                       uint2* __restrict__ lo) {
@@ -814,6 +854,19 @@ extern "C" int dfb_split_bf16x2(const float* x, long long n, void* hi, void* lo,
   k_split_bf16x2<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const float4*)x, n / 4, (uint2*)hi, (uint2*)lo);
   add_launches(1);
   return check_launch("dfb_split_bf16x2");
+}
+
+extern "C" int dfb_conv_pack_weights_multi(const dfb_pack_desc* table_dev, int n_weights, long long total_elems, int split3,
+                                           void* stream_) {
+  if (n_weights <= 0 || n_weights > 64 || total_elems <= 0 || !table_dev) {
+    set_error("dfb_conv_pack_weights_multi: 1..64 weights and a device table are required");
+    return DFB_ERR_ARG;
+  }
+  long long blocks = (total_elems + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  k_pack_weights_multi<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(table_dev, n_weights, total_elems, split3);
+  add_launches(1);
+  return check_launch("dfb_conv_pack_weights_multi");
 }
 
 extern "C" int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, int split3, void* w_fwd, void* w_dgrad,

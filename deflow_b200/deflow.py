@@ -79,6 +79,13 @@ class DeFlow(nn.Module):
     def __init__(self, voxel_size=[0.2, 0.2, 6], point_cloud_range=[-51.2, -51.2, -3, 51.2, 51.2, 3],
                  grid_feature_size=[512, 512], decoder_option="gru", num_iters=4, precision="fp32"):
         super().__init__()
+        # constructor arguments as the reference's hydra target spells them (OSF/conf/model/deflow.yaml:4-9,
+        # grid_feature_size added by ModelWrapper.__init__, OSF/src/trainer.py:42-55): goes into a checkpoint's
+        # ``hyper_parameters`` (trainer.TrainStep.state_dict), which OSF/eval.py:41-46 reads back
+        self.target_cfg = {"_target_": "src.models.DeFlow", "decoder_option": decoder_option, "num_iters": int(num_iters),
+                           "voxel_size": [float(v) for v in voxel_size],
+                           "point_cloud_range": [float(v) for v in point_cloud_range],
+                           "grid_feature_size": [int(v) for v in grid_feature_size]}
         self.embedder = DynamicEmbedder(voxel_size=voxel_size, pseudo_image_dims=grid_feature_size,
                                         point_cloud_range=point_cloud_range, feat_channels=32)
         self.backbone = FastFlow3DUNet()
@@ -174,3 +181,6 @@ class FastFlow3D(DeFlow):
                  grid_feature_size=[512, 512], precision="fp32"):
         super().__init__(voxel_size, point_cloud_range, grid_feature_size, decoder_option="linear",
                          precision=precision)
+        self.target_cfg = {"_target_": "src.models.FastFlow3D", "voxel_size": self.target_cfg["voxel_size"],
+                           "point_cloud_range": self.target_cfg["point_cloud_range"],
+                           "grid_feature_size": self.target_cfg["grid_feature_size"]}

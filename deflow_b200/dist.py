@@ -2,7 +2,8 @@
 
 The reference trains with Lightning DDP (OSF/train.py:125): bucketed NCCL all-reduce of 6 891 939 fp32 gradients
 (27.6 MB) overlapped with backward.  On an NVSwitch domain that message takes ~0.1 ms against a >40 ms step, so the
-path shards by frame pair with a single collective per step and no overlap machinery (DESIGN.md "multi-GPU").
+path shards by frame pair with at most two collectives per step: the head + UNet-decoder slice of the flat gradient
+buffer is averaged while the encoder backward still runs, the rest after it (DESIGN.md "multi-GPU").
 Works with any torch.distributed backend (nccl on the B200 box, gloo in the CPU tests)."""
 from __future__ import annotations
 
@@ -35,35 +36,93 @@ def broadcast_module(module: torch.nn.Module, src: int = 0):
     """Replicate parameters and buffers of rank `src` (DDP does this at construction)."""
     if world_size() == 1:
         return
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src)
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src)
+
+
+def _avg_inplace(t: torch.Tensor, async_op: bool = False):
+    """Mean over ranks: ReduceOp.AVG on NCCL (no separate divide pass); gloo has no AVG, so SUM + divide there."""
+    if dist.get_backend() == "nccl":
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+    work = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=False)
+    t.div_(dist.get_world_size())
+    return None if not async_op else work
 
 
 class GradAverager:
-    """Gradient mean across ranks with ONE collective on a flat fp32 buffer.
+    """Gradient mean across ranks on a flat fp32 buffer, in at most two collectives.
 
     ``zero()`` drops the ``.grad`` tensors (autograd then *assigns* each gradient instead of launching an add kernel
-    per parameter); ``average()`` packs them into the flat buffer (one multi-tensor copy), all-reduces it when there
-    is more than one rank, and re-points every ``.grad`` at its slice, so clipping and the optimizer work on views."""
+    per parameter); ``average()`` packs them into the flat buffer (one multi-tensor copy), averages it over the ranks
+    and re-points every ``.grad`` at its slice, so clipping and the optimizer work on views.
+
+    ``plan_early_slice(model)`` + ``arm_early_slice()`` (TrainStep, world size > 1): the parameters whose gradients the
+    backward finishes FIRST -- the flow head and the UNet decoder, the tail of ``model.parameters()`` -- form one
+    contiguous slice of the flat buffer; a post-accumulate hook on each of them counts down, and when the last one has
+    its gradient the slice is packed and its all-reduce is issued asynchronously (NCCL's own stream), overlapping the
+    encoder + pillar-feature-net backward that is still running.  ``average()`` then only has the head of the buffer
+    left."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.views, off = [], 0
+        self.views, self.offsets, off = [], [], 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            self.offsets.append(off)
             off += p.numel()
+        self.early_from = None      # index into self.params where the early slice starts
+        self._early_left = -1
+        self._early_work = None
+        self._early_done = False
+        self._hooks = []
         self.zero()
 
     def zero(self):
         for p in self.params:
             p.grad = None
 
-    def average(self):
+    # -------------------------------------------------------------------------------------- early slice
+    def plan_early_slice(self, model: torch.nn.Module, late_prefixes=("embedder.", "backbone.encoder_step")):
+        """Everything after the last parameter whose name starts with one of ``late_prefixes`` is 'early'."""
+        names = {id(p): n for n, p in model.named_parameters()}
+        last_late = -1
+        for i, p in enumerate(self.params):
+            if names.get(id(p), "").startswith(tuple(late_prefixes)):
+                last_late = i
+        self.early_from = last_late + 1
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        if self.early_from >= len(self.params):
+            self.early_from = None
+            return
+        for p in self.params[self.early_from:]:
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_early_grad))
+
+    def arm_early_slice(self):
+        if self.early_from is not None:
+            self._early_left = len(self.params) - self.early_from
+            self._early_work, self._early_done = None, False
+
+    def _on_early_grad(self, _p):
+        if self._early_left <= 0:
+            return
+        self._early_left -= 1
+        if self._early_left == 0 and world_size() > 1:
+            i0 = self.early_from
+            self._pack(range(i0, len(self.params)))
+            self._early_work = _avg_inplace(self.flat[self.offsets[i0]:], async_op=True)
+            self._early_done = True
+
+    # -------------------------------------------------------------------------------------- pack + average
+    def _pack(self, indices):
         src, dst = [], []
-        for p, v in zip(self.params, self.views):
+        for i in indices:
+            p, v = self.params[i], self.views[i]
             if p.grad is None:
                 v.zero_()
             elif p.grad.data_ptr() != v.data_ptr():
@@ -71,12 +130,22 @@ class GradAverager:
                 dst.append(v)
         if src:
             torch._foreach_copy_(dst, src)
+
+    def average(self):
+        early = self._early_done and self.early_from is not None
+        n_late = self.early_from if early else len(self.params)
+        self._pack(range(n_late))
         for p, v in zip(self.params, self.views):
             p.grad = v
-        w = world_size()
-        if w > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(w)
+        if world_size() > 1:
+            if early:
+                if n_late > 0:
+                    _avg_inplace(self.flat[:self.offsets[self.early_from]])
+                if self._early_work is not None:
+                    self._early_work.wait()
+            else:
+                _avg_inplace(self.flat)
+        self._early_left, self._early_work, self._early_done = -1, None, False
 
     @property
     def nbytes(self):

@@ -90,7 +90,20 @@ class FastFlow3DUNet(nn.Module):
     #   bf16 images  -> perf mode: bf16 operands, fp32 accumulation;
     #   fp32 images  -> parity mode: every operand is a (hi, lo) bf16 pair and the K loop runs hi*hi + hi*lo + lo*hi
     #                   ("bf16x3": ~16 significant bits per operand, fp32 accumulation and fp32 activations in HBM).
+    def _weight_bank(self):
+        from . import conv as tc
+        bank = self.__dict__.get("_dfb_bank")
+        if bank is None:
+            bank = tc.WeightBank([m.weight for m in self.modules() if isinstance(m, nn.Conv2d)])
+            self.__dict__["_dfb_bank"] = bank
+        return bank
+
     def _forward_tensor_core(self, img0, img1):
+        from . import conv as tc
+        with tc.bank_scope(self._weight_bank(), img0.dtype == torch.float32):
+            return self._forward_packed(img0, img1)
+
+    def _forward_packed(self, img0, img1):
         from . import conv as tc
 
         def encoder(x):

@@ -244,6 +244,19 @@ typedef struct {
 } dfb_conv_args;
 int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, int split3, void* w_fwd, void* w_dgrad,
                           void* stream);
+/* Every convolution weight of a model in ONE launch (the training step re-packs after each optimizer update:
+ * the fp32 masters in torch layout are the state_dict contract, REF/src/models/basic/unet.py:49-68).  table_dev: device
+ * array of n_weights (<= 64) descriptors, `first` = running element offset (exclusive prefix sum of cout*cin*k*k);
+ * total_elems = sum of all element counts. */
+typedef struct dfb_pack_desc {
+  const float* w;        /* [cout,cin,k,k] fp32 */
+  void* w_fwd;           /* bf16 [cout][(split3?2:1)*k*k*cin] or NULL */
+  void* w_dgrad;         /* bf16 [cin][(split3?2:1)*k*k*cout] or NULL */
+  long long first;
+  int cout, cin, ksize, pad_;
+} dfb_pack_desc;
+int dfb_conv_pack_weights_multi(const dfb_pack_desc* table_dev, int n_weights, long long total_elems, int split3,
+                                void* stream);
 /* fp32 x[n] -> hi = bf16(x), lo = bf16(x - hi): the operand pairs of the split-precision ("bf16x3") parity mode */
 int dfb_split_bf16x2(const float* x, long long n, void* hi, void* lo, void* stream);
 int dfb_conv2d(const dfb_conv_args* args, void* stream);

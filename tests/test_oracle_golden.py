@@ -55,3 +55,34 @@ def test_config1_20k_and_real_sweep():
         fx, batch, cfg, state, buffers, res = _run(name, False)
         assert np.array_equal(res["pc0_valid_point_idxes"][0].numpy(), fx["pc0_idx_0"])
         np.testing.assert_allclose(res["flow"][0].detach().numpy(), fx["flow_0"], atol=5e-5)
+
+
+@pytest.mark.parametrize("name,tol", [("train4_small_gru_lr2e-5", 2e-5), ("train3_small_gru_lr2e-4", 3e-4)])
+def test_training_trajectory_matches_reference(name, tol):
+    """K Adam steps of the oracle (clip 5.0) against the trajectory the reference modules produced
+    (make_golden.run_train_case; OSF/src/trainer.py:94-175).  The lr 2e-4 trajectory overshoots and amplifies
+    arithmetic noise (1 vs 8 threads of the reference itself: 2e-5), hence its wider tolerance."""
+    tz = np.load(f"{__import__('helpers').GOLDEN}/{name}.npz")
+    fx, batch, cfg = load_fixture(str(tz["fixture"]))
+    state = orc.random_state(int(tz["seed_state"]), str(tz["decoder"]))
+    params = [v for k, v in state.items() if v.is_floating_point() and "running" not in k]
+    for v in params:
+        v.requires_grad_(True)
+    buffers = {k: v.clone() for k, v in state.items() if "running" in k}
+    opt = torch.optim.Adam(params, lr=float(tz["lr"]))
+    losses = []
+    for _ in range(int(tz["steps"])):
+        opt.zero_grad(set_to_none=True)
+        res = orc.deflow_forward(batch, state, cfg["voxel_size"], cfg["range"], cfg["grid"], cfg["decoder"], 4,
+                                 training=True, buffers=buffers)
+        loss = orc.training_step_loss(batch, res, str(tz["loss_name"]))
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, float(tz["clip"]))
+        opt.step()
+        losses.append(float(loss))
+    np.testing.assert_allclose(losses, tz["losses"], rtol=tol)
+    for k in tz.files:
+        if k.startswith("weight::"):
+            w0 = orc.random_state(int(tz["seed_state"]), str(tz["decoder"]))[k[8:]].numpy()
+            d_ref, d = tz[k] - w0, state[k[8:]].detach().numpy() - w0
+            assert np.linalg.norm(d - d_ref) <= 50 * tol * np.linalg.norm(d_ref), k
