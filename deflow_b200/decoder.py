@@ -12,7 +12,6 @@ from typing import List
 
 import torch
 from torch import nn
-import torch.nn.functional as F
 
 from . import ops
 
@@ -27,22 +26,14 @@ class ConvGRU(nn.Module):
         self.convq = nn.Conv1d(input_dim + hidden_dim, hidden_dim, 1)
 
     def forward(self, h, x):
-        """Reference layout: h[N,128,1], x[N,64,1]."""
-        return self.step(h.squeeze(-1), x.squeeze(-1)).unsqueeze(-1)
-
-    def step(self, h, x):
-        """Row layout: h[N,128], x[N,64] (a k=1 Conv1d is a matmul with weight[:, :, 0])."""
-        hx = torch.cat([h, x], dim=1)
-        z = torch.sigmoid(F.linear(hx, self.convz.weight[:, :, 0], self.convz.bias))
-        r = torch.sigmoid(F.linear(hx, self.convr.weight[:, :, 0], self.convr.bias))
-        q = torch.tanh(F.linear(torch.cat([r * h, x], dim=1), self.convq.weight[:, :, 0], self.convq.bias))
-        return (1 - z) * h + z * q
+        """Reference layout: h[N,128,1], x[N,64,1] -> h'[N,128,1] (decoder.py:184-193): one GRU iteration on the
+        tensor-core gate GEMMs + gate kernels, split-precision ("bf16x3") fp32 arithmetic, with its own backward.
+        (ConvGRUDecoder runs all iterations inside one fused launch sequence instead of calling this.)"""
+        from . import gru
+        return gru.gru_step(h.squeeze(-1), x.squeeze(-1), self).unsqueeze(-1)
 
 
 class _GatherDecoder(nn.Module):
-    def _gather(self, before_nhwc, after_nhwc, idx: ops.PillarIndex, B: int, n_rows: int):
-        return ops.decoder_gather(before_nhwc, after_nhwc, idx, B, n_rows, torch.float32)
-
     def _forward_tensor_core(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets, iters):
         """bf16 perf mode: gather -> (GRU iterations) -> MLP head on the tensor cores (deflow_b200/gru.py)."""
         from . import gru
@@ -82,19 +73,11 @@ class ConvGRUDecoder(_GatherDecoder):
                                      nn.Linear(pseudoimage_channels // 2, 3))
         self.num_iters = num_iters
         self.compute_dtype = torch.float32
-        self.use_library = False   # True: cuBLAS fp32 comparator (tests only)
 
     def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
         """All pc0 points of the batch at once -> flow [n_rows, 3]."""
         offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
-        if not self.use_library:
-            return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, self.num_iters)
-        h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(self.compute_dtype == torch.bfloat16)):
-            x = self.offset_encoder(offsets)
-            for _ in range(self.num_iters):
-                h = self.gru.step(h.float(), x.float())
-            return self.decoder(torch.cat([h, x.float()], dim=1)).float()
+        return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, self.num_iters)
 
 
 class LinearDecoder(_GatherDecoder):
@@ -105,16 +88,10 @@ class LinearDecoder(_GatherDecoder):
         self.offset_encoder = nn.Linear(3, 128)
         self.decoder = nn.Sequential(nn.Linear(pseudoimage_channels * 4, 32), nn.GELU(), nn.Linear(32, 3))
         self.compute_dtype = torch.float32
-        self.use_library = False
 
     def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
         offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
-        if not self.use_library:
-            return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, 0)
-        h = self._gather(img_nhwc, unet_nhwc, idx, B, n_rows)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(self.compute_dtype == torch.bfloat16)):
-            x = self.offset_encoder(offsets)
-            return self.decoder(torch.cat([h, x.float()], dim=1)).float()
+        return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, 0)
 
 
 def _index_from_infos(infos, H, W) -> ops.PillarIndex:

@@ -102,15 +102,13 @@ class DeFlow(nn.Module):
     def set_precision(self, precision: str):
         """'fp32' = parity mode: fp32 tensors everywhere, the dense contractions on the tensor cores with split-precision
         ("bf16x3") operands; 'bf16' = perf mode (bf16 operands and activations, fp32 accumulation / statistics /
-        voxelisation) -- SURVEY.md section 8(d).  'fp32_library' routes the dense contractions through cuDNN / cuBLAS
-        fp32: a comparator for tests, not a product path."""
-        if precision not in ("fp32", "bf16", "fp32_library"):
-            raise ValueError("precision must be 'fp32', 'bf16' or 'fp32_library'")
+        voxelisation) -- SURVEY.md section 8(d).  Both run on the same tcgen05 kernels; there is no library backend."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
         self.precision = precision
         dt = torch.bfloat16 if precision == "bf16" else torch.float32
         for m in (self.backbone, self.head):
             m.compute_dtype = dt
-            m.use_library = precision == "fp32_library"
         return self
 
     def load_from_checkpoint(self, ckpt_path):

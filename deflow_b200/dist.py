@@ -162,3 +162,13 @@ def max_over_ranks(value: float, device) -> float:
 def barrier():
     if world_size() > 1:
         dist.barrier()
+
+
+def enable_sync_bn(model: torch.nn.Module):
+    """BatchNorm batch statistics over ALL ranks (the reference's default ``sync_bn: true``, OSF/conf/config.yaml:23,
+    OSF/train.py:128 -> torch.nn.SyncBatchNorm): sets ``sync_group`` on the modules whose kernels exchange their
+    statistics (conv.conv_bn_gelu, ops.pillar_feature_net)."""
+    model.sync_bn = world_size() > 1
+    for m in model.modules():
+        if hasattr(m, "compute_dtype") or hasattr(m, "fused_ok"):
+            m.sync_bn = model.sync_bn

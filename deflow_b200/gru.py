@@ -162,6 +162,75 @@ def decode(h0, offsets, n, head, iters, parity=False):
                           head.decoder[0].weight, head.decoder[0].bias, head.decoder[2].weight, head.decoder[2].bias)
 
 
+class _GRUStep(torch.autograd.Function):
+    """ONE ConvGRU iteration h, x -> h' (decoder.py:184-193) in fp32 parity arithmetic: the gate GEMMs are 1x1
+    split-precision tensor-core convolutions over the row list, the gate math is csrc/gru_elem.cu.  Serves the
+    reference-signature ``ConvGRU.forward``; the decoders run all iterations through _Decoder / the fused kernels."""
+
+    @staticmethod
+    def forward(ctx, h, x, wz, bz, wr, br, wq, bq):
+        lib = _lib.lib()
+        if not h.is_cuda:
+            raise RuntimeError("deflow_b200.ConvGRU runs on CUDA (sm_100a) only; there is no CPU path")
+        if h.shape[1] != 128 or x.shape[1] not in (32, 64, 128):
+            raise RuntimeError("ConvGRU: the tensor-core path covers hidden_dim 128 and input_dim 32 / 64 / 128")
+        n = h.shape[0]
+        n_pad = max((n + 7) // 8 * 8, 8)
+        dev, st = h.device, _stream(h)
+        f = lambda t: t.detach().float().contiguous()  # noqa: E731
+        hp = torch.zeros((n_pad, 128), dtype=torch.float32, device=dev)
+        xp = torch.zeros((n_pad, x.shape[1]), dtype=torch.float32, device=dev)
+        hp[:n].copy_(h.detach())
+        xp[:n].copy_(x.detach())
+        cin = 128 + x.shape[1]
+        wzr4 = torch.cat([f(wz)[:, :, 0], f(wr)[:, :, 0]], 0).reshape(256, cin, 1, 1).contiguous()
+        wq4 = f(wq).reshape(128, cin, 1, 1)
+        zr = _conv([hp, xp], wzr4, torch.cat([f(bz), f(br)]), 256)
+        rh = torch.empty_like(hp)
+        check(lib.dfb_gru_rh(zr.data_ptr(), hp.data_ptr(), n, n_pad, rh.data_ptr(), 1, st), "gru_rh")
+        q = _conv([rh, xp], wq4, f(bq), 128)
+        h_new = torch.empty_like(hp)
+        check(lib.dfb_gru_update(zr.data_ptr(), q.data_ptr(), hp.data_ptr(), n, n_pad, h_new.data_ptr(), None, 1, st),
+              "gru_update")
+        ctx.saved = (hp, xp, zr, rh, q, wzr4, wq4)
+        ctx.meta = (n, n_pad, x.shape[1])
+        return h_new[:n]
+
+    @staticmethod
+    def backward(ctx, dh_out):
+        lib = _lib.lib()
+        hp, xp, zr, rh, q, wzr4, wq4 = ctx.saved
+        n, n_pad, cx = ctx.meta
+        dev, st = dh_out.device, _stream(dh_out)
+        dh = torch.zeros((n_pad, 128), dtype=torch.float32, device=dev)
+        dh[:n].copy_(dh_out)
+        dq = torch.empty((n_pad, 128), dtype=torch.float32, device=dev)
+        dzr = torch.empty((n_pad, 256), dtype=torch.float32, device=dev)
+        dh_acc = torch.empty_like(dh)
+        check(lib.dfb_gru_bwd1(zr.data_ptr(), q.data_ptr(), hp.data_ptr(), dh.data_ptr(), n, n_pad, dq.data_ptr(),
+                               dzr.data_ptr(), dh_acc.data_ptr(), 1, st), "gru_bwd1")
+        gwq = _wgrad([rh, xp], dq)
+        gbq = tc.channel_sum(dq)
+        d_rh = _dgrad(dq, wq4, 0, 128)
+        d_xq = _dgrad(dq, wq4, 128, 128 + cx)
+        check(lib.dfb_gru_bwd2(zr.data_ptr(), hp.data_ptr(), d_rh.data_ptr(), n, n_pad, dzr.data_ptr(), dh_acc.data_ptr(),
+                               1, st), "gru_bwd2")
+        gwzr = _wgrad([hp, xp], dzr)
+        gbzr = tc.channel_sum(dzr)
+        d_h2 = _dgrad(dzr, wzr4, 0, 128)
+        d_xzr = _dgrad(dzr, wzr4, 128, 128 + cx)
+        check(lib.dfb_acc_bf16(dh_acc.data_ptr(), d_h2.data_ptr(), None, dh_acc.numel(), 1, st), "acc")
+        dx = torch.zeros((n_pad, cx), dtype=torch.float32, device=dev)
+        check(lib.dfb_acc_bf16(dx.data_ptr(), d_xq.data_ptr(), d_xzr.data_ptr(), dx.numel(), 1, st), "acc")
+        return (dh_acc[:n], dx[:n], gwzr[:128, :, 0], gbzr[:128], gwzr[128:, :, 0], gbzr[128:], gwq[:, :, 0], gbq)
+
+
+def gru_step(h, x, gru_mod):
+    """h[N,128], x[N,Cx] fp32 -> h'[N,128] (one iteration of ``gru_mod``: a decoder.ConvGRU)."""
+    return _GRUStep.apply(h.float(), x.float(), gru_mod.convz.weight, gru_mod.convz.bias, gru_mod.convr.weight,
+                          gru_mod.convr.bias, gru_mod.convq.weight, gru_mod.convq.bias)
+
+
 class _FusedGRUDecoder(torch.autograd.Function):
     """ConvGRUDecoder on the persistent fused kernels (csrc/gru_fused.cu): h0 bf16 [n_pad,128], offsets [n,3] -> flow."""
 
@@ -186,9 +255,10 @@ class _FusedGRUDecoder(torch.autograd.Function):
         y1 = torch.empty((n_pad, 32), dtype=BF, device=dev) if train else None
         flow = torch.empty((n, 3), dtype=torch.float32, device=dev)
         P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
-        check(lib.dfb_gru_fused_forward(h0.data_ptr(), offsets.data_ptr(), wzr_b.data_ptr(), wq_b.data_ptr(),
-                                        w1_b.data_ptr(), par.data_ptr(), n, n_pad, iters, P(hsave), P(xsave), P(y1),
-                                        flow.data_ptr(), st), "gru_fused_forward")
+        with tc._timed("k_gru_fused_fwd", 602688.0 * n * iters / 4, h0):
+            check(lib.dfb_gru_fused_forward(h0.data_ptr(), offsets.data_ptr(), wzr_b.data_ptr(), wq_b.data_ptr(),
+                                            w1_b.data_ptr(), par.data_ptr(), n, n_pad, iters, P(hsave), P(xsave), P(y1),
+                                            flow.data_ptr(), st), "gru_fused_forward")
         ctx.saved = (hsave, xsave, y1, offsets, wzr_b, wq_b, w1f, w2f, par)
         ctx.meta = (n, n_pad, iters)
         return flow
@@ -218,10 +288,13 @@ class _FusedGRUDecoder(torch.autograd.Function):
         dzr = torch.empty((iters, n_pad, 256), dtype=BF, device=dev)
         dh0 = torch.empty((n_pad, 128), dtype=BF, device=dev)
         dx = torch.empty((n_pad, 64), dtype=torch.float32, device=dev)
-        check(lib.dfb_gru_fused_backward(hsave.data_ptr(), xsave.data_ptr(), d_h.data_ptr(), d_x.data_ptr(),
-                                         wzr_b.data_ptr(), wq_b.data_ptr(), par.data_ptr(), n, n_pad, iters,
-                                         rh.data_ptr(), dq.data_ptr(), dzr.data_ptr(), dh0.data_ptr(), dx.data_ptr(), st),
-              "gru_fused_backward")
+        # algorithmic FLOPs of the launch: the data-gradient GEMMs of the GRU iterations (147 456 FLOP / point / iteration,
+        # SURVEY 8a row a10); the gate recomputation it also does is not counted
+        with tc._timed("k_gru_fused_bwd", 147456.0 * n * iters, dflow):
+            check(lib.dfb_gru_fused_backward(hsave.data_ptr(), xsave.data_ptr(), d_h.data_ptr(), d_x.data_ptr(),
+                                             wzr_b.data_ptr(), wq_b.data_ptr(), par.data_ptr(), n, n_pad, iters,
+                                             rh.data_ptr(), dq.data_ptr(), dzr.data_ptr(), dh0.data_ptr(), dx.data_ptr(), st),
+                  "gru_fused_backward")
         gwq = gwzr = None
         for t in range(iters):
             gwq = _wgrad([rh[t], xsave], dq[t], gwq)

@@ -8,11 +8,18 @@ from __future__ import annotations
 
 import torch
 from torch import nn
-import torch.nn.functional as F
+
+
+def _to_nhwc(x: torch.Tensor, dtype) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("deflow_b200 modules run on CUDA (sm_100a) only; there is no CPU path")
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
 
 
 class ConvWithNorms(nn.Module):
-    """Conv2d(k, stride, pad) -> BatchNorm2d -> GELU (exact erf)  (basic/__init__.py:61-79)."""
+    """Conv2d(k, stride, pad) -> BatchNorm2d -> GELU (exact erf)  (basic/__init__.py:61-79), NCHW in / NCHW out like the
+    reference; computed by the tcgen05 convolution + BN/GELU kernels (deflow_b200/conv.py) on an NHWC copy.  fp32 input
+    -> split-precision ("bf16x3") parity arithmetic, bf16 input -> bf16 operands."""
 
     def __init__(self, in_num_channels: int, out_num_channels: int, kernel_size: int, stride: int, padding: int):
         super().__init__()
@@ -21,21 +28,31 @@ class ConvWithNorms(nn.Module):
         self.nonlinearity = nn.GELU()
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = self.conv(x)
-        if y.shape[2] == 1 and y.shape[3] == 1:  # basic/__init__.py:73-76
-            return self.nonlinearity(y)
-        return self.nonlinearity(self.batchnorm(y))
+        from . import conv as tc
+        if self.conv.kernel_size != (3, 3) or self.conv.padding != (1, 1):
+            raise RuntimeError("ConvWithNorms: the tensor-core path covers the 3x3 / pad 1 layers of FastFlow3DUNet")
+        if (x.shape[2] - 1) // self.conv.stride[0] + 1 == 1 and (x.shape[3] - 1) // self.conv.stride[1] + 1 == 1:
+            raise RuntimeError("ConvWithNorms: 1x1 outputs skip BatchNorm in the reference (basic/__init__.py:73-76); "
+                               "that branch never triggers on the DeFlow path and is not built")
+        dt = torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32
+        y = tc.conv_bn_gelu(_to_nhwc(x, dt), self.conv, self.batchnorm, self.training)
+        tc.flush_batch_counters()
+        return y.permute(0, 3, 1, 2)
 
 
 class BilinearDecoder(nn.Module):
-    """unet.py:8-18."""
+    """unet.py:8-18 (scale factor 2, bilinear, align_corners=False)."""
 
     def __init__(self, scale_factor: int):
         super().__init__()
         self.scale_factor = scale_factor
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return F.interpolate(x, scale_factor=self.scale_factor, mode="bilinear", align_corners=False)
+        from . import conv as tc
+        if self.scale_factor != 2:
+            raise RuntimeError("BilinearDecoder: the kernel covers scale_factor=2 (every use in FastFlow3DUNet)")
+        dt = torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32
+        return tc.upsample_bilinear2x(_to_nhwc(x, dt)).permute(0, 3, 1, 2)
 
 
 class UpsampleSkip(nn.Module):
@@ -48,10 +65,19 @@ class UpsampleSkip(nn.Module):
         self.u4_u5 = nn.Sequential(nn.Conv2d(2 * latent_channels, out_channels, 3, 1, 1),
                                    nn.Conv2d(out_channels, out_channels, 3, 1, 1))
 
+    def forward_nhwc(self, a, b):
+        """a, b: tuples of 1-2 NHWC tensors (a channel concatenation is passed as its parts and never materialised)."""
+        from . import conv as tc
+        c1 = self.u1_u2[0]
+        u1 = tc.conv_bias(c1.weight, c1.bias, *a)
+        u2 = tc.upsample_bilinear2x(u1)
+        u3 = tc.conv_bias(self.u3.weight, self.u3.bias, *b)
+        u4 = tc.conv_bias(self.u4_u5[0].weight, self.u4_u5[0].bias, u2, u3)
+        return tc.conv_bias(self.u4_u5[1].weight, self.u4_u5[1].bias, u4)
+
     def forward(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-        u2 = self.u1_u2(a)
-        u3 = self.u3(b)
-        return self.u4_u5(torch.cat([u2, u3], dim=1))
+        dt = torch.bfloat16 if a.dtype == torch.bfloat16 else torch.float32
+        return self.forward_nhwc((_to_nhwc(a, dt),), (_to_nhwc(b, dt),)).permute(0, 3, 1, 2)
 
 
 class FastFlow3DUNet(nn.Module):
@@ -67,22 +93,14 @@ class FastFlow3DUNet(nn.Module):
         self.decoder_step3 = UpsampleSkip(128, 64, 64)
         self.decoder_step4 = nn.Conv2d(64, 64, 3, 1, 1)
         self.compute_dtype = torch.float32
-        self.use_library = False   # True: cuDNN fp32 comparator (tests only); False: the tcgen05 kernels in both modes
 
     def forward(self, pc0_B: torch.Tensor, pc1_B: torch.Tensor) -> torch.Tensor:
         """Reference signature: [B,32,H,W] x2 -> [B,64,H,W] (any memory format; channels-last is the fast one)."""
-        if not self.use_library:
-            out = self.forward_nhwc(pc0_B.permute(0, 2, 3, 1).contiguous().to(self.compute_dtype),
-                                    pc1_B.permute(0, 2, 3, 1).contiguous().to(self.compute_dtype))
-            return out.permute(0, 3, 1, 2)
-        return self._forward_library(pc0_B, pc1_B)
+        return self.forward_nhwc(_to_nhwc(pc0_B, self.compute_dtype), _to_nhwc(pc1_B, self.compute_dtype)).permute(0, 3, 1, 2)
 
     def forward_nhwc(self, img0: torch.Tensor, img1: torch.Tensor) -> torch.Tensor:
         """NHWC [B,H,W,32] x2 -> NHWC [B,H,W,64]."""
-        if not self.use_library:
-            return self._forward_tensor_core(img0.contiguous(), img1.contiguous())
-        out = self._forward_library(img0.permute(0, 3, 1, 2), img1.permute(0, 3, 1, 2))
-        return out.permute(0, 2, 3, 1).contiguous()
+        return self._forward_tensor_core(img0.contiguous(), img1.contiguous())
 
     # Every convolution is a tcgen05 implicit GEMM (csrc/conv_igemm.cu); BatchNorm statistics come from the convolution
     # epilogue; BN+GELU, bilinear x2 and their backward are HBM-bound passes (csrc/unet_elem.cu).  Channel
@@ -114,40 +132,10 @@ class FastFlow3DUNet(nn.Module):
                 outs.append(x)
             return outs
 
-        def up(block, a, b):
-            c1 = block.u1_u2[0]
-            u1 = tc.conv_bias(c1.weight, c1.bias, *a)
-            u2 = tc.upsample_bilinear2x(u1)
-            u3 = tc.conv_bias(block.u3.weight, block.u3.bias, *b)
-            u4 = tc.conv_bias(block.u4_u5[0].weight, block.u4_u5[0].bias, u2, u3)
-            return tc.conv_bias(block.u4_u5[1].weight, block.u4_u5[1].bias, u4)
-
         f0, l0, r0 = encoder(img0)
         f1, l1, r1 = encoder(img1)
-        s = up(self.decoder_step1, (r0, r1), (l0, l1))
-        t = up(self.decoder_step2, (s,), (f0, f1))
-        u = up(self.decoder_step3, (t,), (img0, img1))
+        s = self.decoder_step1.forward_nhwc((r0, r1), (l0, l1))
+        t = self.decoder_step2.forward_nhwc((s,), (f0, f1))
+        u = self.decoder_step3.forward_nhwc((t,), (img0, img1))
         tc.flush_batch_counters()
         return tc.conv_bias(self.decoder_step4.weight, self.decoder_step4.bias, u)
-
-    # cuDNN strict-fp32 comparator (use_library = True): not a product path, kept for tests that compare the
-    # split-precision tensor-core path with a library implementation of the same arithmetic.
-    def _forward_library(self, pc0_B, pc1_B):
-        dt = self.compute_dtype
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dt == torch.bfloat16)), \
-                torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            pc0_F = self.encoder_step_1(pc0_B)
-            pc0_L = self.encoder_step_2(pc0_F)
-            pc0_R = self.encoder_step_3(pc0_L)
-            pc1_F = self.encoder_step_1(pc1_B)
-            pc1_L = self.encoder_step_2(pc1_F)
-            pc1_R = self.encoder_step_3(pc1_L)
-            Rstar = torch.cat([pc0_R, pc1_R], dim=1)
-            Lstar = torch.cat([pc0_L, pc1_L], dim=1)
-            Fstar = torch.cat([pc0_F, pc1_F], dim=1)
-            Bstar = torch.cat([pc0_B, pc1_B], dim=1)
-            S = self.decoder_step1(Rstar, Lstar)
-            T = self.decoder_step2(S, Fstar)
-            U = self.decoder_step3(T, Bstar)
-            V = self.decoder_step4(U)
-        return V

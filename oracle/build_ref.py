@@ -27,8 +27,49 @@ def build(verbose=False):
     return os.path.join(OUT, "mmcv_ref_ext.so")
 
 
+# Python modules of the reference that the on-GPU checker / bar-to-beat need (oracle/ref_modules.py): staged verbatim into
+# the git-ignored oracle/_ref/osf so that they travel to the GPU box next to mmcv_ref_ext.so.
+PY_ROOT = "/root/reference/OpenSceneFlow"
+PY_FILES = ["src/__init__.py", "src/models/__init__.py", "src/models/deflow.py", "src/models/fastflow3d.py",
+            "src/models/flow4d.py", "src/models/ssf.py",
+            "src/models/basic/__init__.py", "src/models/basic/encoder.py", "src/models/basic/decoder.py",
+            "src/models/basic/unet.py", "src/models/basic/flow4d_module.py", "src/models/basic/ssf_module.py",
+            "src/lossfuncs.py", "src/utils/mics.py", "src/utils/eval_metric.py", "src/utils/av2_eval.py", "src/trainer.py",
+            "src/dataset.py",
+            "assets/__init__.py", "assets/cuda/__init__.py", "assets/cuda/mmcv/__init__.py",
+            "assets/cuda/mmcv/scatter_points.py", "assets/cuda/mmcv/voxelize.py",
+            "assets/cuda/chamfer3D/__init__.py", "assets/cuda/chamfer3D/chamfer3D_cuda.cpp",
+            "assets/cuda/chamfer3D/chamfer3D.cu", "assets/cuda/chamfer3D/setup.py",
+            "assets/tests/test_pc0.npy", "assets/tests/test_pc1.npy"]
+
+
+def stage():
+    """Copy PY_FILES into oracle/_ref/osf (outputs only under oracle/_ref; nothing enters the repo's history)."""
+    import shutil
+    if not os.path.isdir(PY_ROOT):
+        return None
+    dst_root = os.path.join(OUT, "osf")
+    n = 0
+    for rel in PY_FILES:
+        src = os.path.join(PY_ROOT, rel)
+        dst = os.path.join(dst_root, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if os.path.exists(src):
+            shutil.copyfile(src, dst)
+            n += 1
+        elif rel.endswith("__init__.py"):
+            open(dst, "a").close()   # namespace marker the reference tree does not have
+    return dst_root, n
+
+
+_loaded = None
+
+
 def load_ref():
     """Import the prebuilt module (no compilation, no /root/reference access)."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
     path = os.path.join(OUT, "mmcv_ref_ext.so")
     if not os.path.exists(path):
         return None
@@ -37,8 +78,10 @@ def load_ref():
     spec = importlib.util.spec_from_file_location("mmcv_ref_ext", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    _loaded = mod
     return mod
 
 
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv))
+    print(stage())

@@ -21,10 +21,8 @@ outputs, loss values and a few gradient tensors.
 """
 from __future__ import annotations
 
-import ast
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -34,74 +32,14 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OSF = "/root/reference/OpenSceneFlow"
 sys.path.insert(0, ROOT)
 
-from oracle import mmcv_ext_oracle as ext_np  # noqa: E402
 from oracle import deflow_oracle as orc  # noqa: E402
 from deflow_b200 import synth  # noqa: E402
 
 
-# ----------------------------------------------------------------------------- stubs
-class _Timing:
-    def __getitem__(self, i):
-        return self
-
-    def start(self, *a, **k):
-        return None
-
-    def stop(self, *a, **k):
-        return None
-
-    def print(self, *a, **k):
-        return None
-
-
-def install_stubs():
-    dz = types.ModuleType("dztimer")
-    dz.Timing = _Timing
-    sys.modules["dztimer"] = dz
-
-    e = types.ModuleType("mmcv._ext")
-
-    def dynamic_voxelize_forward(points, voxel_size, coors_range, coors, NDim=3):
-        out = ext_np.dynamic_voxelize_forward(points.detach().numpy(), voxel_size.numpy(), coors_range.numpy(),
-                                              coors.numpy())
-        coors.copy_(torch.from_numpy(out))
-
-    def dynamic_point_to_voxel_forward(feats, coors, reduce_type):
-        r = ext_np.dynamic_point_to_voxel_forward(feats.detach().numpy(), coors.numpy(), reduce_type)
-        return [torch.from_numpy(np.ascontiguousarray(x)) for x in r]
-
-    def dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats, reduced_feats, coors_idx,
-                                        reduce_count, reduce_type):
-        g = ext_np.dynamic_point_to_voxel_backward(grad_reduced_feats.numpy(), feats.detach().numpy(),
-                                                   reduced_feats.detach().numpy(), coors_idx.numpy(),
-                                                   reduce_count.numpy(), reduce_type)
-        grad_feats.copy_(torch.from_numpy(g))
-
-    def hard_voxelize_forward(*a, **k):
-        raise RuntimeError("hard_voxelize_forward is not on the DeFlow path")
-
-    e.dynamic_voxelize_forward = dynamic_voxelize_forward
-    e.dynamic_point_to_voxel_forward = dynamic_point_to_voxel_forward
-    e.dynamic_point_to_voxel_backward = dynamic_point_to_voxel_backward
-    e.hard_voxelize_forward = hard_voxelize_forward
-    pkg = types.ModuleType("mmcv")
-    pkg._ext = e
-    sys.modules["mmcv"] = pkg
-    sys.modules["mmcv._ext"] = e
-
-
+# ----------------------------------------------------------------------------- the reference (stubs: oracle/ref_modules.py)
 def load_reference():
-    install_stubs()
-    sys.path.insert(0, OSF)
-    from src.models.deflow import DeFlow  # noqa
-    from src.models.fastflow3d import FastFlow3D  # noqa
-    src = open(os.path.join(OSF, "src/lossfuncs.py")).read()
-    tree = ast.parse(src)
-    ns = {"torch": torch}
-    for node in tree.body:
-        if isinstance(node, ast.FunctionDef) and node.name in ("deflowLoss", "ff3dLoss", "zeroflowLoss"):
-            exec(compile(ast.Module([node], []), "lossfuncs.py", "exec"), ns)
-    return DeFlow, FastFlow3D, ns
+    from oracle import ref_modules
+    return ref_modules.load_reference(ext="numpy")
 
 
 # ----------------------------------------------------------------------------- cases

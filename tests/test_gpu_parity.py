@@ -395,6 +395,49 @@ def test_reference_signature_modules():
         assert float((flows[0].cpu() - o).abs().max()) <= 2e-4
 
 
+def test_benchmark_shape_parity_forward_backward_all_gradients_vs_oracle():
+    """The benchmarked shape (BASELINE configs[1]: 80 000 points / frame, 512 x 512 pillars), B = 2, parity mode:
+    forward, loss and the gradient of EVERY parameter -- all 29 convolution weights, the GRU gate weights, the PFN --
+    against the CPU oracle on the same inputs.  Flow bound: north_star 1e-3 abs."""
+    B, n = 2, 80000
+    batch = synth.make_batch(B, n, seed=5)
+    state = orc.random_state(31, "gru")
+    for k, v in state.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    buffers = {k: v.clone() for k, v in state.items() if "running" in k}
+    torch.set_num_threads(max(torch.get_num_threads(), __import__("os").cpu_count() or 1))
+    ref = orc.deflow_forward(batch, state, VS, RG, (512, 512), "gru", 4, training=True, buffers=buffers)
+    ref_loss = orc.training_step_loss(batch, ref, "deflowLoss")
+    ref_loss.backward()
+
+    m = d.DeFlow(VS, RG, [512, 512], "gru", 4, precision="fp32")
+    m.load_state_dict({k: v.detach() for k, v in orc.random_state(31, "gru").items()}, strict=True)
+    m = m.to(DEV).train()
+    gb = batch_to(batch, DEV)
+    res = m(gb)
+    loss = d.training_step_loss(gb, res, "deflowLoss")
+    loss.backward()
+    worst = 0.0
+    for b in range(B):
+        assert np.array_equal(res["pc0_valid_point_idxes"][b].cpu().numpy(), ref["pc0_valid_point_idxes"][b].numpy())
+        assert np.array_equal(res["pc1_valid_point_idxes"][b].cpu().numpy(), ref["pc1_valid_point_idxes"][b].numpy())
+        worst = max(worst, float((res["flow"][b].detach().cpu() - ref["flow"][b].detach()).abs().max()))
+    assert worst <= 1e-3, f"flow error {worst}"
+    assert abs(float(loss) - float(ref_loss)) <= 2e-4 * max(1.0, abs(float(ref_loss)))
+    bad = []
+    for k, p in m.named_parameters():
+        g, r = p.grad.detach().cpu().double(), state[k].grad.double()
+        # norm-relative; the floor covers convolution biases in front of a BatchNorm, whose exact gradient is 0
+        if float((g - r).norm()) > 2e-3 * float(r.norm()) + 2e-4 * max(1.0, float(r.abs().max())):
+            bad.append((k, float((g - r).norm()), float(r.norm())))
+    assert not bad, bad
+    sd = m.state_dict()
+    for k in buffers:
+        if "num_batches" not in k:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), buffers[k].numpy(), rtol=2e-4, atol=2e-5, err_msg=k)
+
+
 # ----------------------------------------------------------------------------- full-size properties
 def test_full_size_properties_config2_shape():
     """BASELINE configs[1] shape (80k points / frame, 512x512), a few frames: size-independent invariants."""

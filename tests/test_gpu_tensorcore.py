@@ -232,15 +232,14 @@ def test_unet_tensor_core_path_vs_fp32_library():
     b = (torch.randn(2, 64, 64, 32, device=DEV) * (torch.rand(2, 64, 64, 1, device=DEV) < 0.1)).to(torch.bfloat16)
     g = torch.randn(2, 64, 64, 64, device=DEV)
     net.compute_dtype = torch.float32
-    net.use_library = True          # cuDNN strict-fp32 comparator
+    import library_ref                   # cuDNN strict-fp32 comparator on the same parameters (tests/library_ref.py)
     a32, b32 = a.float().requires_grad_(True), b.float().requires_grad_(True)
-    ref = net.forward_nhwc(a32, b32)
+    ref = library_ref.unet_forward(net, a32.permute(0, 3, 1, 2), b32.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
     ref.backward(g)
     ref_grads = {k: p.grad.clone() for k, p in net.named_parameters()}
     ga32 = a32.grad.clone()
     net.zero_grad()
     # parity mode: fp32 tensors, split-precision (bf16x3) tensor-core convolutions -- must agree with cuDNN fp32 closely
-    net.use_library = False
     a3, b3 = a.float().requires_grad_(True), b.float().requires_grad_(True)
     out3 = net.forward_nhwc(a3, b3)
     out3.backward(g)
@@ -291,33 +290,42 @@ def test_model_bf16_mode_reports_flow_error():
         assert e.max() <= 0.15 and e.mean() <= 0.01
 
 
-@pytest.mark.parametrize("kind", ["gru", "linear"])
-def test_decoder_tensor_core_path_vs_fp32(kind):
-    """ConvGRUDecoder / LinearDecoder: bf16 tensor-core path (hand-written backward) against the fp32 torch path."""
+def _decoder_inputs(B, H, W, n_per_frame, seed):
     from deflow_b200 import ops, synth
-    torch.manual_seed(3)
-    B, H, W = 2, 64, 64
     rg = [-6.4, -6.4, -3, 6.4, 6.4, 3]
-    pts = synth.make_batch(2 * B, 1500, seed=31)["pc0"].clone()
+    pts = synth.make_batch(2 * B, n_per_frame, seed=seed)["pc0"].clone()
     pts[..., :2] /= 8.0
     idx = ops.pillar_index(pts.half().float().to(DEV), [0.2, 0.2, 6], rg)
-    n0 = idx.pt_off(B)
-    head = (d.ConvGRUDecoder(num_iters=4) if kind == "gru" else d.LinearDecoder()).to(DEV)
-    head.apply(d.weights_init)
     img = (torch.randn(2 * B, H, W, 32, device=DEV) * 0.5).to(torch.bfloat16)
     unet = (torch.randn(B, H, W, 64, device=DEV) * 0.5).to(torch.bfloat16)
+    return idx, idx.pt_off(B), img, unet
+
+
+@pytest.mark.parametrize("kind", ["gru", "linear"])
+def test_decoder_tensor_core_path_vs_fp32(kind):
+    """ConvGRUDecoder / LinearDecoder: parity mode and bf16 tensor-core path (hand-written backward) against cuBLAS fp32
+    (tests/library_ref.py, same parameters)."""
+    import library_ref
+    from deflow_b200 import ops
+    torch.manual_seed(3)
+    B, H, W = 2, 64, 64
+    idx, n0, img, unet = _decoder_inputs(B, H, W, 1500, 31)
+    head = (d.ConvGRUDecoder(num_iters=4) if kind == "gru" else d.LinearDecoder()).to(DEV)
+    head.apply(d.weights_init)
     gflow = torch.randn(n0, 3, device=DEV)
     res = {}
     for mode in ("library", "fp32", "bf16"):
         head.zero_grad()
         head.compute_dtype = torch.bfloat16 if mode == "bf16" else torch.float32
-        head.use_library = mode == "library"
         i2 = (img.clone() if mode == "bf16" else img.float()).requires_grad_(True)
         u2 = (unet.clone() if mode == "bf16" else unet.float()).requires_grad_(True)
-        flow = head.forward_flat(i2, u2, idx, B, n0)
+        if mode == "library":
+            h0 = ops.decoder_gather(i2, u2, idx, B, n0, torch.float32)
+            flow = library_ref.decoder_forward(head, h0, idx.pt_offs[:n0])
+        else:
+            flow = head.forward_flat(i2, u2, idx, B, n0)
         flow.backward(gflow)
         res[mode] = (flow.detach(), i2.grad.float(), u2.grad.float(), {k: p.grad.clone() for k, p in head.named_parameters()})
-    head.use_library = False
     f32, f16, f3 = res["library"], res["bf16"], res["fp32"]
     # parity mode (split-precision GEMMs, fp32 gate tensors) against cuBLAS fp32
     e3 = float((f3[0] - f32[0]).abs().max())
@@ -333,6 +341,78 @@ def test_decoder_tensor_core_path_vs_fp32(kind):
     for k, g in f32[3].items():
         r = _rel(f16[3][k], g)
         assert r <= 0.1, (k, r)
+
+
+@pytest.mark.parametrize("n_per_frame,seed", [(1500, 31), (777, 5), (61, 9), (4099, 2)])
+def test_fused_gru_kernels_vs_fp32_on_the_same_rounded_operands(n_per_frame, seed):
+    """The persistent fused GRU kernels (csrc/gru_fused.cu, 14 % of the step) against an fp32 cuBLAS evaluation of the
+    SAME arithmetic: bf16-rounded weights, and a bf16 round trip wherever the kernel rounds a GEMM operand (hidden state,
+    x, r*h) -- what remains is accumulation order, tanh.approx and the bf16 rounding of the backward's dq / dzr operands.
+    Ragged point counts (not multiples of the 128-point tile, fewer points than one tile); every weight gradient and the
+    gradient of the gathered pillar vectors.  Bound 2^-7 relative (like the convolution kernels' own test)."""
+    import library_ref
+    from deflow_b200 import gru, ops
+    torch.manual_seed(seed)
+    B, H, W = 2, 64, 64
+    idx, n0, img, unet = _decoder_inputs(B, H, W, n_per_frame, seed)
+    assert n0 % 128 != 0
+    head = d.ConvGRUDecoder(num_iters=4).to(DEV)
+    head.apply(d.weights_init)
+    with torch.no_grad():    # non-trivial biases; weights exactly representable in bf16 so that both sides see the same operands
+        for p in head.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+        for m in (head.gru.convz, head.gru.convr, head.gru.convq, head.decoder[0]):
+            m.weight.copy_(m.weight.to(torch.bfloat16).float())
+    gflow = torch.randn(n0, 3, device=DEV)
+    n_pad = max((n0 + 7) // 8 * 8, 8)
+    h0b = ops.decoder_gather(img, unet, idx, B, n0, torch.bfloat16, n_pad).detach()
+    offs = idx.pt_offs[:n0]
+    # fused kernels
+    head.zero_grad()
+    ha = h0b.clone().requires_grad_(True)
+    fa = gru.decode_fused(ha, offs, n0, head)
+    fa.backward(gflow)
+    ga = {k: p.grad.clone() for k, p in head.named_parameters()}
+    # fp32 comparator on the same rounded operands
+    head.zero_grad()
+    hb = h0b[:n0].float().requires_grad_(True)
+    fb = library_ref.decoder_forward(head, hb, offs, rnd=library_ref.round_bf16)
+    fb.backward(gflow)
+    tol = 2.0 ** -7
+    scale = float(fb.abs().max())
+    e = float((fa - fb.detach()).abs().max())
+    print(f"fused GRU n={n0}: flow abs max err {e:.3g} (|flow| max {scale:.3g}); rel {e / scale:.3g}")
+    assert e <= tol * max(scale, 1.0)
+    assert _rel(ha.grad[:n0].float(), hb.grad) <= tol, _rel(ha.grad[:n0].float(), hb.grad)
+    assert float(ha.grad[n0:].float().abs().max() if n_pad > n0 else 0.0) == 0.0     # padding rows get no gradient
+    for k, p in head.named_parameters():
+        r = _rel(ga[k], p.grad)
+        assert r <= tol, (k, r)
+
+
+def test_conv_gru_module_reference_signature():
+    """ConvGRU.forward(h[N,128,1], x[N,64,1]) (decoder.py:184-193) on the product kernels, forward and backward, against
+    cuBLAS fp32 on the same parameters."""
+    import library_ref
+    torch.manual_seed(1)
+    g = d.ConvGRU(64, 128).to(DEV)
+    for n in (333, 8):
+        h = torch.randn(n, 128, 1, device=DEV, requires_grad=True)
+        x = torch.randn(n, 64, 1, device=DEV, requires_grad=True)
+        go = torch.randn(n, 128, 1, device=DEV)
+        g.zero_grad()
+        out = g(h, x)
+        out.backward(go)
+        got = (out.detach(), h.grad.clone(), x.grad.clone(), {k: p.grad.clone() for k, p in g.named_parameters()})
+        g.zero_grad(); h.grad = None; x.grad = None
+        ref = library_ref.gru_step(g, h[:, :, 0], x[:, :, 0])
+        ref.backward(go[:, :, 0])
+        assert out.shape == (n, 128, 1)
+        assert float((got[0][:, :, 0] - ref.detach()).abs().max()) <= 1e-4
+        assert _rel(got[1], h.grad) <= 1e-3 and _rel(got[2], x.grad) <= 1e-3
+        for k, p in g.named_parameters():
+            assert _rel(got[3][k], p.grad) <= 2e-3, k
 
 
 def test_model_bf16_eval_mode_and_ego_motion_key():
