@@ -151,6 +151,7 @@ def _declare(lib):
         "dfb_acc_bf16": [vp, vp, vp, i64, i32, vp],
         "dfb_head_out": [vp, vp, vp, i32, vp, i32, vp],
         "dfb_head_out_backward": [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp],
+        "dfb_collate_pad": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "dfb_gru_fused_forward": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
         "dfb_gru_fused_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     }
@@ -160,6 +161,8 @@ def _declare(lib):
         fn.argtypes = args
     lib.dfb_index_scan_workspace.restype = i64
     lib.dfb_index_scan_workspace.argtypes = [i32, i64, i64]
+    lib.dfb_collate_workspace.restype = i64
+    lib.dfb_collate_workspace.argtypes = [i32, i32]
     return sig
 
 
@@ -170,7 +173,7 @@ EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size",
            "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",
            "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",
-           "dfb_gru_fused_forward", "dfb_gru_fused_backward"]
+           "dfb_gru_fused_forward", "dfb_gru_fused_backward", "dfb_collate_workspace", "dfb_collate_pad"]
 
 
 def lib():

@@ -230,6 +230,9 @@ def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, gr
     a = _args(0, n, H, W, ksize, stride, xs, cins, cout, None, None, gy, None)
     ncol = max(cout, 64)
     name = f"k_conv_wgrad_halo<{ncol}>" if (ksize == 3 and stride == 1) else f"k_conv_wgrad<{ncol}>"
+    if ksize == 3 and stride == 1 and cout == 64 and sum((c + 63) // 64 for c in cins) <= 8 \
+            and __import__("os").environ.get("DFB_WGRAD_X", "1") != "0":
+        name = "k_conv_wgrad_x"      # cross-shift kernel for 64 output channels (dfb_conv2d_wgrad)
     with _timed(name, 2.0 * n * gy.shape[1] * gy.shape[2] * cout * ct * ksize * ksize, gy):
         check(_lib.lib().dfb_conv2d_wgrad(C.byref(a), wacc.data_ptr(), grad_w.data_ptr(), int(acc), _stream(gy)), "conv2d wgrad")
     return grad_w

@@ -330,6 +330,20 @@ int dfb_gru_fused_backward(const void* hsave, const void* xsave, const void* dh_
                            const void* wq, const float* par, int n, int n_pad, int iters, void* rh, void* dq, void* dzr,
                            void* dh0, float* dx, void* stream);
 
+/* ------------------------------------------------------------------ input feed
+ * Device-side collate_fn_pad (REF/src/dataset.py:22-74; the single-sample strip of ModelWrapper.run_model_wo_ground_data,
+ * REF/src/trainer.py:268-282): the raw samples of one frame slot arrive concatenated -- pts f32[total,3], ground u8[total]
+ * (1 = ground point, dropped), offs i32[B+1] (device) -- and leave as the padded batch the model consumes:
+ * pts_out f32[B,Nmax,3] = pc[~gm] in original order, NaN rows after the kept points; optional per-point payloads that follow
+ * the same mask (flow f32[total,3], valid u8, cls u8) -> zero-padded [B,Nmax,...] (pad_sequence default).  keep_counts
+ * i32[B] = kept points per sample.  workspace: dfb_collate_workspace(B, max_points_per_sample) ints; its last int is set
+ * to 1 if a sample kept more than Nmax points (the surplus is dropped). */
+long long dfb_collate_workspace(int B, int max_points_per_sample);
+int dfb_collate_pad(const float* pts, const unsigned char* ground, const int* offs, int B, int max_points_per_sample,
+                    int Nmax, const float* flow, const unsigned char* valid, const unsigned char* cls, float* pts_out,
+                    float* flow_out, unsigned char* valid_out, unsigned char* cls_out, int* keep_counts, int* workspace,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

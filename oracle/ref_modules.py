@@ -151,3 +151,35 @@ def load_weights_init():
     import torch.nn as nn
     import torch.nn.init as init
     return extract_functions("src/utils/mics.py", ("weights_init",), {"nn": nn, "init": init})["weights_init"]
+
+
+def load_eval_metric():
+    """The reference's src/utils/eval_metric.py + av2_eval.py, imported unmodified.  ``av2`` (av2==0.2.1, OSF/environment.yaml:35)
+    is not installed: stub modules carry the one thing the metric code takes from it, the AnnotationCategories enum (order
+    restated in oracle/eval_oracle.py from the published av2-api source), plus placeholders for names it only imports."""
+    import enum
+    from . import eval_oracle
+    r = root()
+    if r is None:
+        raise RuntimeError("reference modules not found")
+    cats = enum.Enum("AnnotationCategories", {k: k for k in eval_oracle.ANNOTATION_CATEGORIES}, type=str)
+    mods = {"av2": {}, "av2.datasets": {}, "av2.datasets.sensor": {}, "av2.datasets.sensor.constants": {"AnnotationCategories": cats},
+            "av2.geometry": {}, "av2.geometry.geometry": {}, "av2.geometry.se3": {"SE3": object},
+            "av2.utils": {}, "av2.utils.typing": {"NDArrayFloat": np.ndarray, "NDArrayBool": np.ndarray, "NDArrayInt": np.ndarray},
+            "av2.utils.io": {"read_feather": None}}
+    for name, attrs in mods.items():
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+    for name in mods:                      # parent.child attributes (import av2.geometry.geometry as ...)
+        if "." in name:
+            parent, child = name.rsplit(".", 1)
+            setattr(sys.modules[parent], child, sys.modules[name])
+    if not hasattr(np, "NaN"):             # the reference targets numpy < 2 (eval_metric.py:133 uses np.NaN)
+        np.NaN = np.nan
+    _purge()
+    if r not in sys.path:
+        sys.path.insert(0, r)
+    import src.utils.eval_metric as em  # noqa
+    return em
