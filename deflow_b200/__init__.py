@@ -6,3 +6,4 @@ from .decoder import ConvGRU, ConvGRUDecoder, LinearDecoder  # noqa: F401
 from .unet import FastFlow3DUNet  # noqa: F401
 from .mmcv_ext import DynamicScatter, Voxelization, dynamic_scatter, voxelization  # noqa: F401
 from .lossfuncs import deflowLoss, ff3dLoss, training_step_loss  # noqa: F401
+from . import eval_metric, feed  # noqa: F401,E402

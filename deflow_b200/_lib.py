@@ -73,6 +73,12 @@ class PackDesc(C.Structure):
                 ("cout", C.c_int), ("cin", C.c_int), ("ksize", C.c_int), ("pad_", C.c_int)]
 
 
+class EvalTables(C.Structure):
+    """dfb_eval_tables"""
+    _fields_ = [("fg_bg", C.c_ubyte * 256), ("meta", C.c_ubyte * 256), ("speed_splits", C.c_double * 52),
+                ("dist_splits", C.c_double * 6), ("n_speed", C.c_int), ("n_dist", C.c_int)]
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -151,6 +157,7 @@ def _declare(lib):
         "dfb_acc_bf16": [vp, vp, vp, i64, i32, vp],
         "dfb_head_out": [vp, vp, vp, i32, vp, i32, vp],
         "dfb_head_out_backward": [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp],
+        "dfb_eval_accumulate": [vp, vp, vp, i32, vp, vp, vp, i64, C.POINTER(EvalTables), vp, vp],
         "dfb_collate_pad": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "dfb_gru_fused_forward": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
         "dfb_gru_fused_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
@@ -173,7 +180,8 @@ EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size",
            "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",
            "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",
-           "dfb_gru_fused_forward", "dfb_gru_fused_backward", "dfb_collate_workspace", "dfb_collate_pad"]
+           "dfb_gru_fused_forward", "dfb_gru_fused_backward", "dfb_collate_workspace", "dfb_collate_pad",
+           "dfb_eval_accumulate"]
 
 
 def lib():

@@ -344,6 +344,29 @@ int dfb_collate_pad(const float* pts, const unsigned char* ground, const int* of
                     float* flow_out, unsigned char* valid_out, unsigned char* cls_out, int* keep_counts, int* workspace,
                     void* stream);
 
+/* ------------------------------------------------------------------ evaluation metrics on the device
+ * One pass over the points of a validation frame accumulates (+=) everything the reference's three per-frame metric
+ * functions reduce on the host: evaluate_leaderboard / evaluate_leaderboard_v2 / evaluate_ssf
+ * (REF/src/utils/eval_metric.py:28-106 -> REF/src/utils/av2_eval.py:460-553, 839-870, 872-915).
+ * est_flow = final flow (pose flow + estimate), rigid_flow = pose flow, gt_flow: f32[n,3]; pc0: f32 rows of pc_stride floats
+ * (xyz first); is_valid, cls: u8[n].  acc: double[DFB_EVAL_ACC_DOUBLES], layout in csrc/eval_metric.cu:
+ * [0,8) three-way subset counts, [8,16) their EPE sums, [16,19) TP FP FN, [19,784) bucketed [5 classes][51 speed
+ * buckets][count, sum error, sum speed], [784,814) range-wise [5 ranges][static, dynamic][count, sum error, sum distance].
+ * tables (host struct, passed by value to the kernel): class id -> {0 background, 1 foreground, 255 neither}
+ * (av2_eval.py:217-229), class id -> bucketed meta class row {0..4, 255} (av2_eval.py:47-75, row order of
+ * eval_metric.py:262), the speed bucket edges (np.linspace(0, 2, 51) + inf, av2_eval.py:848) and range edges (:892). */
+#define DFB_EVAL_ACC_DOUBLES 814
+typedef struct dfb_eval_tables {
+  unsigned char fg_bg[256];
+  unsigned char meta[256];
+  double speed_splits[52];
+  double dist_splits[6];
+  int n_speed, n_dist;
+} dfb_eval_tables;
+int dfb_eval_accumulate(const float* est_flow, const float* rigid_flow, const float* pc0, int pc_stride,
+                        const float* gt_flow, const unsigned char* is_valid, const unsigned char* cls, long long n,
+                        const dfb_eval_tables* tables, double* acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
