@@ -47,14 +47,14 @@ class PfnArgs(C.Structure):
                 ("bn_params", C.c_void_p), ("pil_feats", C.c_void_p), ("image", C.c_void_p),
                 ("image_bf16", C.c_int), ("pil_cap", C.c_longlong), ("csr_rec", C.c_void_p), ("pt_mask", C.c_void_p),
                 ("partials", C.c_void_p), ("pil_hdr", C.c_void_p), ("image_ready_event", C.c_void_p),
-                ("range_min", C.c_float * 3)]
+                ("range_min", C.c_float * 3), ("phase", C.c_int), ("sync_stats", C.c_void_p), ("sync_counts", C.c_void_p)]
 
 
 class PfnBwdArgs(C.Structure):
     """dfb_pfn_bwd_args"""
     _fields_ = [("fwd", PfnArgs), ("grad_image", C.c_void_p), ("grad_weight", C.c_void_p),
                 ("grad_gamma", C.c_void_p), ("grad_beta", C.c_void_p), ("bwd_stats", C.c_void_p),
-                ("grad_accum", C.c_void_p)]
+                ("grad_accum", C.c_void_p), ("phase", C.c_int), ("sync_bwd_stats", C.c_void_p)]
 
 
 class ConvArgs(C.Structure):
@@ -145,6 +145,7 @@ def _declare(lib):
         "dfb_bn2d_finalize": [vp, C.c_double, i32, i32, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp],
         "dfb_bn_gelu_apply": [vp, vp, i32, i64, vp, i32, vp],
         "dfb_bn_gelu_backward": [vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, i32, vp],
+        "dfb_bn_gelu_backward_phase": [vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, i32, i32, C.c_double, vp],
         "dfb_channel_sum": [vp, i32, i64, vp, vp, i32, vp],
         "dfb_upsample2x": [vp, i32, i32, i32, i32, vp, i32, i32, vp],
         "dfb_offset_encode": [vp, vp, vp, i32, i32, i32, vp, i32, vp],
@@ -181,7 +182,7 @@ EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",
            "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",
            "dfb_gru_fused_forward", "dfb_gru_fused_backward", "dfb_collate_workspace", "dfb_collate_pad",
-           "dfb_eval_accumulate"]
+           "dfb_eval_accumulate", "dfb_bn_gelu_backward_phase"]
 
 
 def lib():

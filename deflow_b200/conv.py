@@ -258,13 +258,21 @@ def bn_gelu_apply(x, bn):
     return y
 
 
-def bn_gelu_backward(x, gy, bn, training, g_gamma, g_beta, g_bias):
+def bn_gelu_backward(x, gy, bn, training, g_gamma, g_beta, g_bias, sync=None):
     Cn = x.shape[-1]
     gx = torch.empty_like(x)
     red = torch.empty(2 * Cn, dtype=torch.float64, device=x.device)
-    check(_lib.lib().dfb_bn_gelu_backward(x.data_ptr(), gy.data_ptr(), bn.data_ptr(), Cn, x.numel() // Cn, int(training),
-                                          red.data_ptr(), gx.data_ptr(), g_gamma.data_ptr(), g_beta.data_ptr(),
-                                          _ptr(g_bias), int(x.dtype == torch.float32), _stream(x)), "bn_gelu_backward")
+    args = (x.data_ptr(), gy.data_ptr(), bn.data_ptr(), Cn, x.numel() // Cn, int(training), red.data_ptr(), gx.data_ptr(),
+            g_gamma.data_ptr(), g_beta.data_ptr(), _ptr(g_bias), int(x.dtype == torch.float32))
+    if sync is None or not training:
+        check(_lib.lib().dfb_bn_gelu_backward(*args, _stream(x)), "bn_gelu_backward")
+        return gx
+    # SyncBatchNorm: this rank's two per-channel sums (and the affine gradients from them, which stay local), their sum
+    # over the ranks, then the data gradient with the pooled sums and the pooled pixel count
+    check(_lib.lib().dfb_bn_gelu_backward_phase(*args, 1, 0.0, _stream(x)), "bn_gelu_backward (reduce)")
+    sync.all_reduce_sum(red)
+    check(_lib.lib().dfb_bn_gelu_backward_phase(*args, 2, float(x.numel() // Cn) * sync.world, _stream(x)),
+          "bn_gelu_backward (apply)")
     return gx
 
 
@@ -429,12 +437,21 @@ class _ConvBnGelu(torch.autograd.Function):
     """ConvWithNorms (OSF/src/models/basic/__init__.py:61-79): Conv2d(3, stride, 1) -> BatchNorm2d -> GELU."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, stride, training, eps, momentum):
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, stride, training, eps, momentum, sync=None):
         wf, wd = packed(w, x.dtype == torch.float32)
         cout = w.shape[0]
-        stats = zeros((2, cout), torch.float64, x.device) if training else None
+        sync = sync if training else None
+        stats = (torch.zeros((2, cout), dtype=torch.float64, device=x.device) if sync is not None
+                 else zeros((2, cout), torch.float64, x.device)) if training else None
         raw = conv2d_forward([x], wf, b.detach().float().contiguous(), cout, 3, stride, stats)
         count = raw.numel() // cout
+        if sync is not None:
+            # SyncBatchNorm (OSF/train.py:128): per-channel sum / sum of squares from the convolution epilogue, summed over
+            # the ranks (one small collective per layer call); every rank runs the same B x H x W, so the pooled count is
+            # world x count
+            sync.all_reduce_sum(stats)
+            count = count * sync.world
+        ctx.sync = sync
         bn = bn2d_finalize(stats, count, training, eps, momentum, gamma.detach().float(), beta.detach().float(),
                            running_mean, running_var)
         act = bn_gelu_apply(raw, bn)
@@ -448,15 +465,16 @@ class _ConvBnGelu(torch.autograd.Function):
         stride, training, wshape = ctx.cfg
         cout, cin = wshape[0], wshape[1]
         gg, gbeta, gbias = zeros((3, cout), torch.float32, x.device).unbind(0)
-        graw = bn_gelu_backward(raw, gact.contiguous(), bn, training, gg, gbeta, gbias)
+        graw = bn_gelu_backward(raw, gact.contiguous(), bn, training, gg, gbeta, gbias, ctx.sync)
         gw = conv2d_wgrad([x], graw, 3, stride)
         gx = conv2d_dgrad(graw, wd, x.shape[1], x.shape[2], cin, cin, 0, 3, stride) if ctx.needs_input_grad[0] else None
-        return gx, gw, gbias, gg, gbeta, None, None, None, None, None, None
+        return gx, gw, gbias, gg, gbeta, None, None, None, None, None, None, None
 
 
 def conv_bn_gelu(x, conv_mod, bn_mod, training):
     out = _ConvBnGelu.apply(x, conv_mod.weight, conv_mod.bias, bn_mod.weight, bn_mod.bias, bn_mod.running_mean,
-                            bn_mod.running_var, conv_mod.stride[0], training, bn_mod.eps, bn_mod.momentum)
+                            bn_mod.running_var, conv_mod.stride[0], training, bn_mod.eps, bn_mod.momentum,
+                            getattr(bn_mod, "dfb_sync", None))
     if training:
         _pending_nbt.append(bn_mod.num_batches_tracked)
     return out

@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(1024) k_bn_finalize(const int* __restrict__ co
                                                       float momentum, const double* __restrict__ mom,
                                                       const float* __restrict__ weight, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, float* __restrict__ running_mean,
-                                                      float* __restrict__ running_var, float* __restrict__ bn_params) {
+                                                      float* __restrict__ running_var, float* __restrict__ bn_params,
+                                                      const int* __restrict__ sync_counts) {
   __shared__ float s_mean[32][PFN_C], s_unb[32][PFN_C];
   __shared__ int s_n[32];
   const int c = threadIdx.x & 31, slot = threadIdx.x >> 5;
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(1024) k_bn_finalize(const int* __restrict__ co
   for (int f0 = 0; f0 < F; f0 += 32) {
     const int f = f0 + slot;
     if (f < F) {
-      const int n = counts[f];
+      // SyncBatchNorm: `mom` then holds the moments summed over all ranks and sync_counts the pooled point counts
+      const int n = sync_counts ? sync_counts[f] : counts[f];
       float mean = rm0, var = rv0;
       float unb = 0.f;
       if (training && n > 0) {
@@ -578,7 +580,13 @@ __global__ void __launch_bounds__(512) k_pfn_bwd_finalize(const int* __restrict_
                                                            const float* __restrict__ bn_params,
                                                            const float* __restrict__ weight,
                                                            float* __restrict__ grad_weight, float* __restrict__ grad_gamma,
-                                                           float* __restrict__ grad_beta) {
+                                                           float* __restrict__ grad_beta,
+                                                           const double* __restrict__ sync_bwd_acc,
+                                                           const int* __restrict__ sync_counts) {
+  // SyncBatchNorm (sync_* given): bwd_acc / mom / counts are THIS rank's sums, sync_bwd_acc / sync_counts the sums over
+  // all ranks.  grad_gamma, grad_beta and grad_W stay local sums over this rank's points (the data-parallel gradient
+  // mean follows), but the two batch means inside the BatchNorm backward are the pooled ones:
+  //   grad_W[c,k] = a_c (T_loc[c][k] - (A1_glob/N_glob) S1_loc[k] - (A2_glob/N_glob) sum_{p local} xhat f_k)
   __shared__ double sred[16][PFN_C + 1];
   const int c = threadIdx.x & 31, slot = threadIdx.x >> 5;
   double w[PFN_K], out[PFN_K + 2];  // gw[9] | gg | gb
@@ -587,8 +595,8 @@ __global__ void __launch_bounds__(512) k_pfn_bwd_finalize(const int* __restrict_
 #pragma unroll
   for (int k = 0; k < PFN_K + 2; ++k) out[k] = 0.0;
   for (int f = slot; f < F; f += 16) {
-    const int n = counts[f];
-    if (n <= 0) continue;
+    if (counts[f] <= 0) continue;
+    const int n = sync_counts ? sync_counts[f] : counts[f];
     const double* A = bwd_acc + ((size_t)f * PFN_C + c) * (PFN_K + 1);
     const float* bp = bn_params + (size_t)f * 4 * PFN_C;
     const double a = bp[c], mu = bp[2 * PFN_C + c], rstd = bp[3 * PFN_C + c];
@@ -601,7 +609,16 @@ __global__ void __launch_bounds__(512) k_pfn_bwd_finalize(const int* __restrict_
     out[PFN_K + 1] += A1;
     if (training) {
       const double* m = mom + (size_t)f * PFN_MOM_PITCH;  // S1[9] | S2 upper triangle
-      const double m1 = A1 / n, m2 = A2 / n;
+      double A1g = A1, A2g = A2;
+      if (sync_bwd_acc) {
+        const double* Ag = sync_bwd_acc + ((size_t)f * PFN_C + c) * (PFN_K + 1);
+        double wtg = 0.0;
+#pragma unroll
+        for (int k = 0; k < PFN_K; ++k) wtg += w[k] * Ag[1 + k];
+        A1g = Ag[0];
+        A2g = rstd * (wtg - mu * A1g);
+      }
+      const double m1 = A1g / n, m2 = A2g / n;
 #pragma unroll
       for (int k = 0; k < PFN_K; ++k) {
         double ws2 = 0.0;
@@ -688,82 +705,105 @@ extern "C" int dfb_clear_rows(void* image, int row_bytes, const int* pix, const 
   return check_launch("dfb_clear_rows");
 }
 
+// a->phase: 0 = everything; 1 = up to the per-frame feature moments (a->stats); 2 = from the BatchNorm finalisation on.
+// SyncBatchNorm callers run phase 1, sum a->stats and the per-frame counts over the ranks (into a->sync_stats /
+// a->sync_counts) and run phase 2; a->stats keeps THIS rank's moments for the backward.
 extern "C" int dfb_pfn_forward(const dfb_pfn_args* a, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (!a || a->F <= 0 || a->H <= 0 || a->W <= 0) { set_error("dfb_pfn_forward: bad sizes"); return DFB_ERR_ARG; }
   if (a->F > 256) { set_error("dfb_pfn_forward: at most 256 frames per call"); return DFB_ERR_UNSUPPORTED; }
   if (!a->csr_rec || !a->pt_mask || !a->partials || !a->pil_hdr) { set_error("dfb_pfn_forward: csr_rec / pt_mask / partials / pil_hdr missing"); return DFB_ERR_ARG; }
+  if (a->phase < 0 || a->phase > 2) { set_error("dfb_pfn_forward: phase must be 0, 1 or 2"); return DFB_ERR_ARG; }
   const int F = a->F, HW = a->H * a->W;
   const PfnGeom G = make_geom(a);
   const int sms = sm_count();
   const float4* rec = (const float4*)a->csr_rec;
-  const size_t img_bytes = (size_t)F * HW * PFN_C * (a->image_bf16 ? 2 : 4);
-  // the dense zero canvas (PointPillarsScatter, encoder.py:135-139).  A caller that zero-fills the image itself on
-  // another stream (to overlap the fill with the index kernels) passes the event that marks its completion.
-  if (!a->image_ready_event) {
-    const size_t n16 = img_bytes / 16;   // F*H*W*32 elements: always a multiple of 16 bytes
-    k_zero_fill<<<sms * 2, 256, 0, st>>>((uint4*)a->image, n16, (unsigned char*)a->image + n16 * 16, (int)(img_bytes - n16 * 16));
-  }
-  cudaMemsetAsync(a->stats, 0, sizeof(double) * (size_t)F * PFN_MOM_PITCH, st);
   float4* hdr = (float4*)a->pil_hdr;
-  k_pillar_mean<<<sms * 8, 256, 0, st>>>(a->counts, F, HW, G, rec, a->pil_start, a->pil_pix, a->pil_coor, a->pil_mean, hdr);
-  int launches = 4;
-  if (a->training) {
-    int bx = (sms * 3) / F;   // 80 registers -> 3 resident blocks per SM: one wave, no tail
-    if (bx < 1) bx = 1;
-    dim3 g(bx, F);
-    k_pfn_moments<<<g, 256, 0, st>>>(a->counts, F, rec, hdr, a->stats);
+  int launches = 0;
+  if (a->phase != 2) {
+    const size_t img_bytes = (size_t)F * HW * PFN_C * (a->image_bf16 ? 2 : 4);
+    // the dense zero canvas (PointPillarsScatter, encoder.py:135-139).  A caller that zero-fills the image itself on
+    // another stream (to overlap the fill with the index kernels) passes the event that marks its completion.
+    if (!a->image_ready_event) {
+      const size_t n16 = img_bytes / 16;   // F*H*W*32 elements: always a multiple of 16 bytes
+      k_zero_fill<<<sms * 2, 256, 0, st>>>((uint4*)a->image, n16, (unsigned char*)a->image + n16 * 16, (int)(img_bytes - n16 * 16));
+      ++launches;
+    }
+    cudaMemsetAsync(a->stats, 0, sizeof(double) * (size_t)F * PFN_MOM_PITCH, st);
+    k_pillar_mean<<<sms * 8, 256, 0, st>>>(a->counts, F, HW, G, rec, a->pil_start, a->pil_pix, a->pil_coor, a->pil_mean, hdr);
     ++launches;
+    if (a->training) {
+      int bx = (sms * 3) / F;   // 80 registers -> 3 resident blocks per SM: one wave, no tail
+      if (bx < 1) bx = 1;
+      dim3 g(bx, F);
+      k_pfn_moments<<<g, 256, 0, st>>>(a->counts, F, rec, hdr, a->stats);
+      ++launches;
+    }
   }
-  k_bn_finalize<<<1, 1024, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum, a->stats, a->weight, a->gamma, a->beta,
-                                    a->running_mean, a->running_var, a->bn_params);
-  if (a->image_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)a->image_ready_event, 0);
-  const int dyn = F * 2 * PFN_C * (int)sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_pfn_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
-    cudaFuncSetAttribute(k_pfn_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
-    configured = true;
+  if (a->phase != 1) {
+    k_bn_finalize<<<1, 1024, 0, st>>>(a->counts, F, a->training, a->eps, a->momentum,
+                                      a->sync_stats ? (const double*)a->sync_stats : (const double*)a->stats, a->weight, a->gamma,
+                                      a->beta, a->running_mean, a->running_var, a->bn_params, (const int*)a->sync_counts);
+    if (a->image_ready_event) cudaStreamWaitEvent(st, (cudaEvent_t)a->image_ready_event, 0);
+    const int dyn = F * 2 * PFN_C * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(k_pfn_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
+      cudaFuncSetAttribute(k_pfn_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 2 * PFN_C * (int)sizeof(float));
+      configured = true;
+    }
+    // Linear(9,32) weights -> constant bank (device-to-device, stream-ordered): the point pass reads them as FFMA
+    // constant operands instead of 72 shared-memory broadcast loads per point (ncu: the pass was LSU-bound).  One
+    // constant copy per device: concurrent forwards of DIFFERENT feature nets must not run on different streams.
+    cudaMemcpyToSymbolAsync(c_pfn_w, a->weight, sizeof(float) * PFN_C * PFN_K, 0, cudaMemcpyDeviceToDevice, st);
+    if (a->image_bf16)
+      k_pfn_points<true><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->bn_params, a->pt_mask, a->partials,
+                                                    a->pil_feats, a->image);
+    else
+      k_pfn_points<false><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->bn_params, a->pt_mask, a->partials,
+                                                     a->pil_feats, a->image);
+    if (a->image_bf16) k_pfn_straddlers<true><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
+    else k_pfn_straddlers<false><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
+    launches += 3;
   }
-  // Linear(9,32) weights -> constant bank (device-to-device, stream-ordered): the point pass reads them as FFMA
-  // constant operands instead of 72 shared-memory broadcast loads per point (ncu: the pass was LSU-bound).  One
-  // constant copy per device: concurrent forwards of DIFFERENT feature nets must not run on different streams.
-  cudaMemcpyToSymbolAsync(c_pfn_w, a->weight, sizeof(float) * PFN_C * PFN_K, 0, cudaMemcpyDeviceToDevice, st);
-  if (a->image_bf16)
-    k_pfn_points<true><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->bn_params, a->pt_mask, a->partials,
-                                                  a->pil_feats, a->image);
-  else
-    k_pfn_points<false><<<sms * 3, 256, dyn, st>>>(a->counts, F, rec, hdr, a->bn_params, a->pt_mask, a->partials,
-                                                   a->pil_feats, a->image);
-  if (a->image_bf16) k_pfn_straddlers<true><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
-  else k_pfn_straddlers<false><<<sms * 8, 256, 0, st>>>(a->counts, F, rec, hdr, a->partials, a->pil_feats, a->image);
   add_launches(launches);
   return check_launch("dfb_pfn_forward");
 }
 
+// b->phase: 0 = everything; 1 = the point pass only (b->bwd_stats = this rank's A1 | T sums); 2 = the finalisation only,
+// with b->sync_bwd_stats = those sums over all ranks (SyncBatchNorm; b->fwd.sync_counts = pooled counts).
 extern "C" int dfb_pfn_backward(const dfb_pfn_bwd_args* b, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (!b) { set_error("dfb_pfn_backward: null args"); return DFB_ERR_ARG; }
   const dfb_pfn_args* a = &b->fwd;
   if (!a->csr_rec || !a->pt_mask || !a->pil_hdr) { set_error("dfb_pfn_backward: csr_rec / pt_mask / pil_hdr missing"); return DFB_ERR_ARG; }
+  if (b->phase < 0 || b->phase > 2) { set_error("dfb_pfn_backward: phase must be 0, 1 or 2"); return DFB_ERR_ARG; }
   const int F = a->F;
   const int sms = sm_count();
   const float4* rec = (const float4*)a->csr_rec;
-  cudaMemsetAsync(b->bwd_stats, 0, sizeof(double) * (size_t)F * PFN_C * (PFN_K + 1), st);
-  if (((uintptr_t)b->grad_image & 15)) { set_error("dfb_pfn_backward: grad_image must be 16-byte aligned"); return DFB_ERR_ARG; }
-  BwdGeom Gm;
-  Gm.lox = a->range_min[0]; Gm.loy = a->range_min[1]; Gm.vx = a->voxel_size[0]; Gm.vy = a->voxel_size[1];
-  Gm.W = a->W; Gm.HW = a->H * a->W;
-  // 30 KB of shared memory / 48 registers (bf16) -> 5 resident blocks per SM, 46 KB / 64 registers (fp32) -> 4: one wave
-  int bx = (sms * (a->image_bf16 ? 5 : 4)) / F;
-  if (bx < 1) bx = 1;
-  dim3 g(bx, F);
-  if (a->image_bf16)
-    k_pfn_bwd<true><<<g, 256, 0, st>>>(a->counts, F, Gm, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
-  else
-    k_pfn_bwd<false><<<g, 256, 0, st>>>(a->counts, F, Gm, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
-  k_pfn_bwd_finalize<<<1, 512, 0, st>>>(a->counts, F, a->training, b->bwd_stats, a->stats, a->bn_params, a->weight,
-                                         b->grad_weight, b->grad_gamma, b->grad_beta);
-  add_launches(2);
+  int launches = 0;
+  if (b->phase != 2) {
+    cudaMemsetAsync(b->bwd_stats, 0, sizeof(double) * (size_t)F * PFN_C * (PFN_K + 1), st);
+    if (((uintptr_t)b->grad_image & 15)) { set_error("dfb_pfn_backward: grad_image must be 16-byte aligned"); return DFB_ERR_ARG; }
+    BwdGeom Gm;
+    Gm.lox = a->range_min[0]; Gm.loy = a->range_min[1]; Gm.vx = a->voxel_size[0]; Gm.vy = a->voxel_size[1];
+    Gm.W = a->W; Gm.HW = a->H * a->W;
+    // 30 KB of shared memory / 48 registers (bf16) -> 5 resident blocks per SM, 46 KB / 64 registers (fp32) -> 4: one wave
+    int bx = (sms * (a->image_bf16 ? 5 : 4)) / F;
+    if (bx < 1) bx = 1;
+    dim3 g(bx, F);
+    if (a->image_bf16)
+      k_pfn_bwd<true><<<g, 256, 0, st>>>(a->counts, F, Gm, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
+    else
+      k_pfn_bwd<false><<<g, 256, 0, st>>>(a->counts, F, Gm, rec, a->pt_mask, (const float4*)a->pil_hdr, b->grad_image, b->bwd_stats);
+    ++launches;
+  }
+  if (b->phase != 1) {
+    k_pfn_bwd_finalize<<<1, 512, 0, st>>>(a->counts, F, a->training, b->bwd_stats, a->stats, a->bn_params, a->weight,
+                                           b->grad_weight, b->grad_gamma, b->grad_beta, (const double*)b->sync_bwd_stats,
+                                           (const int*)a->sync_counts);
+    ++launches;
+  }
+  add_launches(launches);
   return check_launch("dfb_pfn_backward");
 }

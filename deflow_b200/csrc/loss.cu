@@ -1,12 +1,13 @@
-// deflowLoss / ff3dLoss with the trainer's ground-truth construction fused in, for all samples of a
+// deflowLoss / ff3dLoss / zeroflowLoss with the trainer's ground-truth construction fused in, for all samples of a
 // step, without host synchronisation.
 //
-// Reference: deflowLoss (OpenSceneFlow/src/lossfuncs.py:102-125), ff3dLoss (:148-157) and the loop of
+// Reference: deflowLoss (OpenSceneFlow/src/lossfuncs.py:102-125), zeroflowLoss (:128-145), ff3dLoss (:148-157) and the loop of
 // ModelWrapper.training_step (OpenSceneFlow/src/trainer.py:120-142):
 //   gt[p]  = flow[b][idx[p]] - pose_flow[b][idx[p]]
 //   deflow : speed = |gt| / 0.1; mean |est - gt| over the buckets speed < 0.4, 0.4 <= speed <= 1.0,
 //            speed > 1.0; empty buckets (NaN mean) are skipped; the per-sample losses are SUMMED.
 //   ff3d   : mean(|est - gt| * (0.1 + 0.9 * [class > 0])).
+//   zeroflow (kind 2): mean over the finite points of |est - gt| * clamp(1.8 * (|gt| * 10) - 0.8, 0.1, 1.0).
 // The reference launches three boolean-mask kernels and three isnan() host syncs per sample.
 #include "common.cuh"
 #include "../../include/deflow_b200.h"
@@ -50,6 +51,11 @@ __device__ __forceinline__ PointTerm point_term(int kind, int p, int b, const fl
     if (!finite3(gx, gy, gz) || !finite3(px, py, pz)) { t.bucket = -1; return t; }
     const float speed = __fdiv_rn(sqrtf(gx * gx + gy * gy + gz * gz), 0.1f);
     t.bucket = speed < 0.4f ? 0 : (speed <= 1.0f ? 1 : 2);
+  } else if (kind == 2) {
+    if (!finite3(gx, gy, gz) || !finite3(px, py, pz)) { t.bucket = -1; return t; }      // lossfuncs.py:131-134
+    const float speed = __fmul_rn(sqrtf(gx * gx + gy * gy + gz * gz), 10.0f);             // :138
+    t.w = fmaxf(0.1f, fminf(__fsub_rn(__fmul_rn(1.8f, speed), 0.8f), 1.0f));              // :140-142
+    t.bucket = 0;
   } else {
     t.bucket = 0;
     t.w = (classes && classes[src] > 0) ? 1.0f : 0.1f;  // 0.1 + 0.9 * [class > 0] (lossfuncs.py:154-156)
@@ -105,6 +111,8 @@ __global__ void k_loss_finalize(int kind, int B, const int* __restrict__ counts,
       if (w[3] > 0) l += (float)(w[0] / w[3]);
       if (w[4] > 0) l += (float)(w[1] / w[4]);
       total += l;
+    } else if (kind == 2) {
+      total += w[3] > 0 ? (float)(w[0] / w[3]) : __int_as_float(0x7fc00000);   // mean over the finite points
     } else {
       const int n = counts[b];
       total += n > 0 ? (float)(w[0] / (double)n) : __int_as_float(0x7fc00000);  // mean of empty = NaN
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(256) k_loss_grad(int kind, const float* __rest
     const PointTerm t = point_term(kind, p, b, est, flow_gt, pose_flow, classes, pt_idx, Nmax);
     float gx = 0.f, gy = 0.f, gz = 0.f;
     if (t.bucket >= 0 && t.err > 0.f) {  // d|v|/dv = v/|v|, 0 at v = 0 (torch vector_norm backward)
-      const double denom = kind == 0 ? ws[(size_t)b * LW + 3 + t.bucket] : (double)counts[b];
+      const double denom = kind != 1 ? ws[(size_t)b * LW + 3 + t.bucket] : (double)counts[b];
       const float s = t.w / ((float)denom * t.err);
       gx = t.ex * s; gy = t.ey * s; gz = t.ez * s;
     }
@@ -145,7 +153,7 @@ extern "C" int dfb_flow_loss(int kind, const float* est, const float* flow_gt, c
                              const unsigned char* classes, const long long* pt_idx, const int* counts, int F, int B,
                              int Nmax, double* bucket_ws, float* loss, float* grad_est, int n_cap, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  if (kind < 0 || kind > 1) { set_error("dfb_flow_loss: unknown loss kind %d", kind); return DFB_ERR_ARG; }
+  if (kind < 0 || kind > 2) { set_error("dfb_flow_loss: unknown loss kind %d (0 deflowLoss, 1 ff3dLoss, 2 zeroflowLoss)", kind); return DFB_ERR_ARG; }
   if (B <= 0 || F < B) { set_error("dfb_flow_loss: bad sizes"); return DFB_ERR_ARG; }
   cudaMemsetAsync(bucket_ws, 0, sizeof(double) * (size_t)B * LW, st);
   int bx = (sm_count() * 4 + B - 1) / B;

@@ -710,31 +710,51 @@ extern "C" int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long lon
   return check_launch("dfb_bn_gelu_apply");
 }
 
-extern "C" int dfb_bn_gelu_backward(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
-                                    double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, int f32,
-                                    void* stream_) {
+// phase 0: everything.  SyncBatchNorm callers split the call around their all-reduce of `red`:
+//   phase 1: red[2][C] = this rank's sums (sum g1, sum g1 * xhat) and the parameter gradients from them (local sums, as
+//            torch.nn.SyncBatchNorm leaves them to the data-parallel gradient mean);
+//   phase 2: gx from `red` (now summed over all ranks) and count_total = pixels per channel over all ranks.
+static int bn_gelu_backward_impl(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
+                                 double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, int f32, int phase,
+                                 double count_total, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (C % 8 || C > 256 || 256 % (C >> 3)) { set_error("dfb_bn_gelu_backward: unsupported channel count %d", C); return DFB_ERR_ARG; }
-  cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st);
+  if (phase < 0 || phase > 2) { set_error("dfb_bn_gelu_backward: phase must be 0, 1 or 2"); return DFB_ERR_ARG; }
+  const bool do_reduce = phase != 2, do_apply = phase != 1;
+  if (do_reduce) cudaMemsetAsync(red, 0, sizeof(double) * 2 * C, st);
   const long long n_vec = n_pix * (C >> 3);
   const int g = grid_for_elems(n_vec, 512, 8);
+  const double cnt = phase == 2 ? count_total : (double)n_pix;
+  int launches = 0;
   if (!f32 && stream_ok(C, x, gy, gx)) {
     static int occ_r = 0, occ_a = 0;
     constexpr int smem = sp::Ring<2, SP_STAGES>::BYTES;
     const int gr = stream_grid(k_bn_gelu_bwd_reduce_s, smem, n_vec, &occ_r);
     const int ga = stream_grid(k_bn_gelu_bwd_apply_s, smem, n_vec, &occ_a);
-    k_bn_gelu_bwd_reduce_s<<<gr, sp::THREADS, smem, st>>>(x, gy, bn, C, n_vec, red);
-    k_bn_gelu_bwd_apply_s<<<ga, sp::THREADS, smem, st>>>(x, gy, bn, red, (double)n_pix, training, C, n_vec, (uint4*)gx);
+    if (do_reduce) { k_bn_gelu_bwd_reduce_s<<<gr, sp::THREADS, smem, st>>>(x, gy, bn, C, n_vec, red); ++launches; }
+    if (do_apply) { k_bn_gelu_bwd_apply_s<<<ga, sp::THREADS, smem, st>>>(x, gy, bn, red, cnt, training, C, n_vec, (uint4*)gx); ++launches; }
   } else if (f32) {
-    k_bn_gelu_bwd_reduce<true><<<g, 256, 0, st>>>(x, gy, bn, C, n_vec, red);
-    k_bn_gelu_bwd_apply<true><<<g, 256, 0, st>>>(x, gy, bn, red, (double)n_pix, training, C, n_vec, gx);
+    if (do_reduce) { k_bn_gelu_bwd_reduce<true><<<g, 256, 0, st>>>(x, gy, bn, C, n_vec, red); ++launches; }
+    if (do_apply) { k_bn_gelu_bwd_apply<true><<<g, 256, 0, st>>>(x, gy, bn, red, cnt, training, C, n_vec, gx); ++launches; }
   } else {
-    k_bn_gelu_bwd_reduce<false><<<g, 256, 0, st>>>(x, gy, bn, C, n_vec, red);
-    k_bn_gelu_bwd_apply<false><<<g, 256, 0, st>>>(x, gy, bn, red, (double)n_pix, training, C, n_vec, gx);
+    if (do_reduce) { k_bn_gelu_bwd_reduce<false><<<g, 256, 0, st>>>(x, gy, bn, C, n_vec, red); ++launches; }
+    if (do_apply) { k_bn_gelu_bwd_apply<false><<<g, 256, 0, st>>>(x, gy, bn, red, cnt, training, C, n_vec, gx); ++launches; }
   }
-  k_bn_param_grads<<<(C + 127) / 128, 128, 0, st>>>(red, bn, C, training, g_gamma, g_beta, g_bias);
-  add_launches(3);
+  if (do_reduce) { k_bn_param_grads<<<(C + 127) / 128, 128, 0, st>>>(red, bn, C, training, g_gamma, g_beta, g_bias); ++launches; }
+  add_launches(launches);
   return check_launch("dfb_bn_gelu_backward");
+}
+
+extern "C" int dfb_bn_gelu_backward(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
+                                    double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, int f32,
+                                    void* stream_) {
+  return bn_gelu_backward_impl(x, gy, bn, C, n_pix, training, red, gx, g_gamma, g_beta, g_bias, f32, 0, 0.0, stream_);
+}
+
+extern "C" int dfb_bn_gelu_backward_phase(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
+                                          double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, int f32,
+                                          int phase, double count_total, void* stream_) {
+  return bn_gelu_backward_impl(x, gy, bn, C, n_pix, training, red, gx, g_gamma, g_beta, g_bias, f32, phase, count_total, stream_);
 }
 
 // out[c] += sum over pixels (may be NULL); stats2 (may be NULL): [2][C] += sum, sum of squares (BatchNorm statistics of

@@ -164,11 +164,42 @@ def barrier():
         dist.barrier()
 
 
-def enable_sync_bn(model: torch.nn.Module):
-    """BatchNorm batch statistics over ALL ranks (the reference's default ``sync_bn: true``, OSF/conf/config.yaml:23,
-    OSF/train.py:128 -> torch.nn.SyncBatchNorm): sets ``sync_group`` on the modules whose kernels exchange their
-    statistics (conv.conv_bn_gelu, ops.pillar_feature_net)."""
-    model.sync_bn = world_size() > 1
+class StatSync:
+    """Sums small statistics tensors over the ranks of the default process group (SyncBatchNorm exchange)."""
+
+    def __init__(self):
+        self.world = world_size()
+        self.calls = 0
+        self.bytes = 0
+
+    def all_reduce_sum(self, t: torch.Tensor):
+        self.calls += 1
+        self.bytes += t.numel() * t.element_size()
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+
+def enable_sync_bn(model: torch.nn.Module, sync=None):
+    """BatchNorm batch statistics over ALL ranks -- the reference's default ``sync_bn: true`` (OSF/conf/config.yaml:23,
+    OSF/train.py:128: Lightning converts every BatchNorm to torch.nn.SyncBatchNorm).  Marks every BatchNorm module of the
+    model; the kernels behind them (conv.conv_bn_gelu for the 16 encoder BatchNorm2d, ops.pillar_feature_net for the
+    pillar feature net's BatchNorm1d) then exchange their statistics through ``sync``: forward = per-channel sum /
+    sum of squares (BatchNorm2d) or the 54 feature moments + point counts of all 2B frames (BatchNorm1d); backward = the
+    two per-channel sums of the BatchNorm backward.  Parameter gradients stay local sums and are averaged with all the
+    other gradients.  ``sync=None`` -> a StatSync over the default process group (no-op exchange at world size 1).
+    Returns the sync object (``.calls`` / ``.bytes`` count the exchanges)."""
+    sync = sync if sync is not None else StatSync()
+    n = 0
     for m in model.modules():
-        if hasattr(m, "compute_dtype") or hasattr(m, "fused_ok"):
-            m.sync_bn = model.sync_bn
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.dfb_sync = sync
+            n += 1
+    model.dfb_sync = sync
+    return sync
+
+
+def disable_sync_bn(model: torch.nn.Module):
+    for m in model.modules():
+        if hasattr(m, "dfb_sync"):
+            del m.dfb_sync

@@ -87,7 +87,7 @@ class DynamicPillarFeatureNet(nn.Module):
         training = self.training or not bn.track_running_stats
         out = ops.pillar_feature_net(lin.weight, bn.weight, bn.bias, idx, bn.running_mean, bn.running_var, training,
                                      bn.eps, bn.momentum, (self.x_offset, self.y_offset, self.z_offset), image_dtype,
-                                     want_feats, image, image_ready)
+                                     want_feats, image, image_ready, getattr(bn, "dfb_sync", None))
         if training and bn.track_running_stats:
             bn.num_batches_tracked += idx.F  # one BatchNorm1d call per sample-frame in the reference
         return out

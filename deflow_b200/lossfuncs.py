@@ -38,6 +38,11 @@ def ff3dLoss(res_dict):
     return _single(res_dict, "ff3dLoss")
 
 
+def zeroflowLoss(res_dict):
+    """OSF/src/lossfuncs.py:128-145 (FastFlow3DDistillationLoss of ZeroFlow)."""
+    return _single(res_dict, "zeroflowLoss")
+
+
 def training_step_loss(batch, res, loss_fn: str = "deflowLoss") -> torch.Tensor:
     """Sum over the batch of loss_fn({'est_flow': res.flow[b], 'gt_flow': flow[b][idx] - pose_flow[b][idx],
     'gt_classes': classes[b][idx]})  (OSF/src/trainer.py:120-142)."""

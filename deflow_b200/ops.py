@@ -160,7 +160,8 @@ def ego_warp(pc0: torch.Tensor, pose0: Optional[torch.Tensor], pose1: Optional[t
 # Fused pillar feature net
 # ----------------------------------------------------------------------------------------------
 def _pfn_args(idx: PillarIndex, H, W, training, center_off, eps, momentum, weight, gamma, beta, rm, rv, pil_mean,
-              stats, bn_params, pil_feats, image, pt_mask, pil_hdr, partials=None, image_ready=None) -> PfnArgs:
+              stats, bn_params, pil_feats, image, pt_mask, pil_hdr, partials=None, image_ready=None, phase=0,
+              sync_stats=None, sync_counts=None) -> PfnArgs:
     a = PfnArgs()
     a.F, a.H, a.W, a.training = idx.F, H, W, int(training)
     a.voxel_size = _f3(idx.voxel_size)
@@ -180,6 +181,7 @@ def _pfn_args(idx: PillarIndex, H, W, training, center_off, eps, momentum, weigh
     a.csr_rec, a.pt_mask, a.partials = idx.csr_rec.data_ptr(), pt_mask.data_ptr(), _ptr(partials)
     a.pil_hdr = pil_hdr.data_ptr()
     a.image_ready_event = None if image_ready is None else image_ready.cuda_event
+    a.phase, a.sync_stats, a.sync_counts = phase, _ptr(sync_stats), _ptr(sync_counts)
     return a
 
 
@@ -189,7 +191,7 @@ class _PillarFeatureNet(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, weight, gamma, beta, idx: PillarIndex, running_mean, running_var, training, eps, momentum,
-                center_off, image_dtype, want_feats, image, image_ready):
+                center_off, image_dtype, want_feats, image, image_ready, sync=None):
         _need_cuda(weight, "pillar_feature_net")
         gx, gy, gz = idx.grid
         H, W = gy, gx
@@ -208,10 +210,29 @@ class _PillarFeatureNet(torch.autograd.Function):
         else:
             assert tuple(image.shape) == (idx.F, H, W, 32) and image.dtype == image_dtype and image.is_contiguous()
             image = image.detach()   # a new tensor object on the same storage: the output is not the input itself
-        a = _pfn_args(idx, H, W, training, center_off, eps, momentum, w, g, b, running_mean, running_var, pil_mean,
-                      stats, bn_params, pil_feats, image, pt_mask, pil_hdr, partials, image_ready)
-        check(_lib.lib().dfb_pfn_forward(C.byref(a), _stream(weight)), "pfn_forward")
+        sync = sync if (sync is not None and training) else None
+        sync_counts = None
+        if sync is None:
+            a = _pfn_args(idx, H, W, training, center_off, eps, momentum, w, g, b, running_mean, running_var, pil_mean,
+                          stats, bn_params, pil_feats, image, pt_mask, pil_hdr, partials, image_ready)
+            check(_lib.lib().dfb_pfn_forward(C.byref(a), _stream(weight)), "pfn_forward")
+        else:
+            # SyncBatchNorm (OSF/train.py:128): the BatchNorm1d call of sample-frame f pools the points of frame f of
+            # EVERY rank.  Phase 1 leaves this rank's feature moments in `stats`; they and the per-frame point counts
+            # are summed over the ranks (two small collectives for all 2B frames); phase 2 normalises with the pooled ones.
+            a = _pfn_args(idx, H, W, training, center_off, eps, momentum, w, g, b, running_mean, running_var, pil_mean,
+                          stats, bn_params, pil_feats, image, pt_mask, pil_hdr, partials, image_ready, phase=1)
+            check(_lib.lib().dfb_pfn_forward(C.byref(a), _stream(weight)), "pfn_forward (moments)")
+            sync_stats = stats.clone()
+            sync_counts = idx.counts[:idx.F].clone()
+            sync.all_reduce_sum(sync_stats)
+            sync.all_reduce_sum(sync_counts)
+            a = _pfn_args(idx, H, W, training, center_off, eps, momentum, w, g, b, running_mean, running_var, pil_mean,
+                          stats, bn_params, pil_feats, image, pt_mask, pil_hdr, partials, image_ready, phase=2,
+                          sync_stats=sync_stats, sync_counts=sync_counts)
+            check(_lib.lib().dfb_pfn_forward(C.byref(a), _stream(weight)), "pfn_forward (normalise)")
         ctx.idx, ctx.cfg = idx, (H, W, training, eps, momentum, center_off)
+        ctx.sync, ctx.sync_counts = sync, sync_counts
         ctx.save_for_backward(w, g, b, pil_mean, stats, bn_params, pt_mask, pil_hdr)
         if pil_feats is None:
             pil_feats = pil_mean.new_empty(0)
@@ -224,7 +245,7 @@ class _PillarFeatureNet(torch.autograd.Function):
         idx = ctx.idx
         H, W, training, eps, momentum, center_off = ctx.cfg
         if grad_image is None:
-            return (None,) * 14
+            return (None,) * 15
         grad_image = grad_image.contiguous()
         dev = w.device
         ba = PfnBwdArgs()
@@ -238,8 +259,17 @@ class _PillarFeatureNet(torch.autograd.Function):
         ba.grad_image, ba.grad_weight, ba.grad_gamma, ba.grad_beta = (grad_image.data_ptr(), gw.data_ptr(),
                                                                      gg.data_ptr(), gb.data_ptr())
         ba.bwd_stats, ba.grad_accum = bwd_stats.data_ptr(), None
-        check(_lib.lib().dfb_pfn_backward(C.byref(ba), _stream(w)), "pfn_backward")
-        return (gw, gg, gb) + (None,) * 11
+        if ctx.sync is None:
+            check(_lib.lib().dfb_pfn_backward(C.byref(ba), _stream(w)), "pfn_backward")
+        else:
+            ba.phase = 1
+            check(_lib.lib().dfb_pfn_backward(C.byref(ba), _stream(w)), "pfn_backward (point pass)")
+            pooled = bwd_stats.clone()
+            ctx.sync.all_reduce_sum(pooled)
+            ba.phase, ba.sync_bwd_stats = 2, pooled.data_ptr()
+            ba.fwd.sync_counts = ctx.sync_counts.data_ptr()
+            check(_lib.lib().dfb_pfn_backward(C.byref(ba), _stream(w)), "pfn_backward (finalise)")
+        return (gw, gg, gb) + (None,) * 12
 
 
 def clear_rows(image: torch.Tensor, pix: torch.Tensor, counts: torch.Tensor, count_index: int):
@@ -253,12 +283,12 @@ def clear_rows(image: torch.Tensor, pix: torch.Tensor, counts: torch.Tensor, cou
 
 
 def pillar_feature_net(weight, gamma, beta, idx, running_mean, running_var, training, eps, momentum, center_off,
-                       image_dtype=torch.float32, want_feats=True, image=None, image_ready=None):
+                       image_dtype=torch.float32, want_feats=True, image=None, image_ready=None, sync=None):
     """image / image_ready: an image buffer the caller is zero-filling on another stream, and the torch.cuda.Event that
     marks the end of that fill (DynamicEmbedder.embed overlaps it with the index kernels); default: allocated and
     zero-filled here."""
     return _PillarFeatureNet.apply(weight, gamma, beta, idx, running_mean, running_var, training, eps, momentum,
-                                   center_off, image_dtype, want_feats, image, image_ready)
+                                   center_off, image_dtype, want_feats, image, image_ready, sync)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -308,7 +338,7 @@ def decoder_gather(img, unet, idx, B, n_rows, out_dtype=torch.float32, n_alloc=N
 # ----------------------------------------------------------------------------------------------
 # Losses
 # ----------------------------------------------------------------------------------------------
-LOSS_KINDS = {"deflowLoss": 0, "ff3dLoss": 1}
+LOSS_KINDS = {"deflowLoss": 0, "ff3dLoss": 1, "zeroflowLoss": 2}
 
 
 class _FlowLoss(torch.autograd.Function):

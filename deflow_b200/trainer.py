@@ -34,8 +34,7 @@ class TrainStep:
             # the backward produces the decoder and UNet-decoder gradients first and the shared encoder's last: the first
             # slice of the flat buffer is all-reduced on a side stream while the encoder backward still runs
             self.grads.plan_early_slice(model)
-        if self.sync_bn:
-            dd.enable_sync_bn(model)
+        self.stat_sync = dd.enable_sync_bn(model) if self.sync_bn else None
 
     def __call__(self, batch) -> torch.Tensor:
         self.grads.zero()

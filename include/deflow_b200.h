@@ -165,6 +165,13 @@ typedef struct {
   void* image_ready_event;/* optional cudaEvent_t: the caller zero-fills `image` on another stream; the first kernel that
                              writes the image waits for this event and the call does not memset the image itself */
   float range_min[3];     /* point_cloud_range[0:3] (x, y, z minimum), fp32: the backward recomputes a point's pixel from it */
+  /* SyncBatchNorm (REF/conf/config.yaml:23 sync_bn, REF/train.py:128): the call can run in two phases around the caller's
+   * all-reduce.  phase 0 = everything (default); 1 = up to the per-frame moments in `stats`; 2 = from the BatchNorm
+   * finalisation on, normalising with sync_stats [F,64] (the moments summed over all ranks) and sync_counts [F] (pooled
+   * point counts) when given.  `stats` keeps this rank's moments (the backward needs them). */
+  int phase;
+  const double* sync_stats;
+  const int* sync_counts;
 } dfb_pfn_args;
 int dfb_pfn_forward(const dfb_pfn_args* args, void* stream);
 /* Dense zero fill (the PointPillarsScatter canvas) with blocks_per_sm small blocks per SM, meant to run on a second
@@ -183,6 +190,8 @@ typedef struct {
   float* grad_beta;         /* [32]    accumulated (+=) */
   double* bwd_stats;        /* workspace [F,32,10] doubles: per frame and channel A1 | T[9] (zeroed inside) */
   double* grad_accum;       /* unused (kept for ABI stability) */
+  int phase;                /* 0 = everything; 1 = point pass only (bwd_stats); 2 = finalisation only */
+  const double* sync_bwd_stats; /* phase 2 under SyncBatchNorm: bwd_stats summed over all ranks (fwd.sync_counts = pooled counts) */
 } dfb_pfn_bwd_args;
 int dfb_pfn_backward(const dfb_pfn_bwd_args* args, void* stream);
 
@@ -281,6 +290,12 @@ int dfb_bn2d_finalize(const double* stats, double count, int C, int training, fl
 int dfb_bn_gelu_apply(const void* x, const float* bn, int C, long long n_pix, void* y, int f32, void* stream);
 int dfb_bn_gelu_backward(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
                          double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, int f32, void* stream);
+/* The same in two phases around a caller's all-reduce (SyncBatchNorm, REF/train.py:128): phase 1 = `red` [2][C] from this
+ * rank's pixels + the parameter gradients (local sums); phase 2 = gx from `red` summed over all ranks, count_total = pixels
+ * per channel over all ranks.  phase 0 = dfb_bn_gelu_backward. */
+int dfb_bn_gelu_backward_phase(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
+                               double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, int f32, int phase,
+                               double count_total, void* stream);
 int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, double* stats2, int f32, void* stream);
 int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int backward, int f32, void* stream);
 

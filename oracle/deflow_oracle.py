@@ -105,16 +105,51 @@ def pillars_to_image(voxel_feats, voxel_coors, ny, nx):
     return canvas.view(1, voxel_feats.shape[1], ny, nx)
 
 
-def embed(points_b, state, grid, voxel_size, pc_range, training, buffers):
-    """DynamicEmbedder.forward (encoder.py:618-631)."""
-    infos, imgs = [], []
-    for b in range(points_b.shape[0]):
-        info = voxelize_frame(points_b[b], voxel_size, pc_range)
-        vf, vc, _, _, _ = pillar_feature_net(info["points"], info["voxel_coords"], state,
-                                             voxel_size=voxel_size, pc_range=pc_range,
-                                             training=training, buffers=buffers)
-        imgs.append(pillars_to_image(vf, vc, grid[0], grid[1]))
-        infos.append(info)
+def embed(points_b, state, grid, voxel_size, pc_range, training, buffers, sync_world=1):
+    """DynamicEmbedder.forward (encoder.py:618-631).
+
+    sync_world = R > 1 restates the reference's default ``sync_bn: true`` (OSF/conf/config.yaml:23, OSF/train.py:128 ->
+    torch.nn.SyncBatchNorm) for a batch that holds the samples of R ranks, rank-major: the BatchNorm1d call of local
+    sample b pools the points of sample b of EVERY rank, i.e. it equals one batch_norm over their concatenation."""
+    nb = points_b.shape[0]
+    if sync_world <= 1 or not training:
+        infos, imgs = [], []
+        for b in range(nb):
+            info = voxelize_frame(points_b[b], voxel_size, pc_range)
+            vf, vc, _, _, _ = pillar_feature_net(info["points"], info["voxel_coords"], state,
+                                                 voxel_size=voxel_size, pc_range=pc_range,
+                                                 training=training, buffers=buffers)
+            imgs.append(pillars_to_image(vf, vc, grid[0], grid[1]))
+            infos.append(info)
+        return torch.cat(imgs, dim=0), infos
+    assert nb % sync_world == 0
+    B = nb // sync_world
+    vx, vy, vz = voxel_size
+    offs = (vx / 2 + pc_range[0], vy / 2 + pc_range[1], vz / 2 + pc_range[2])
+    infos = [voxelize_frame(points_b[b], voxel_size, pc_range) for b in range(nb)]
+    imgs = [None] * nb
+    w = state["embedder.feature_net.pfn_layers.0.0.weight"]
+    bn = "embedder.feature_net.pfn_layers.0.1."
+    for b in range(B):                          # local sample index: the same call on every rank
+        members = [b + r * B for r in range(sync_world)]
+        lins, maps = [], []
+        for m in members:
+            pts, coors = infos[m]["points"], infos[m]["voxel_coords"]
+            vcoors, cmap, count = ext.unique_pillars(coors.numpy())
+            vcoors, cmap, count = torch.from_numpy(vcoors), torch.from_numpy(cmap), torch.from_numpy(count)
+            mean = scatter_mean(pts, cmap, count)[cmap.long()]
+            centre = torch.stack([coors[:, 2].to(pts.dtype) * vx + offs[0], coors[:, 1].to(pts.dtype) * vy + offs[1],
+                                  coors[:, 0].to(pts.dtype) * vz + offs[2]], 1)
+            lins.append(torch.cat([pts, pts[:, :3] - mean[:, :3], pts[:, :3] - centre], -1) @ w.T)
+            maps.append((vcoors, cmap, count))
+        rm = buffers[bn + "running_mean"] if buffers is not None else None
+        rv = buffers[bn + "running_var"] if buffers is not None else None
+        pooled = F.batch_norm(torch.cat(lins, 0), rm, rv, state[bn + "weight"], state[bn + "bias"], True, 0.01, 1e-3)
+        o = 0
+        for m, lin, (vcoors, cmap, count) in zip(members, lins, maps):
+            pf = F.relu(pooled[o:o + lin.shape[0]])
+            o += lin.shape[0]
+            imgs[m] = pillars_to_image(scatter_mean(pf, cmap, count), vcoors, grid[0], grid[1])
     return torch.cat(imgs, dim=0), infos
 
 
@@ -206,8 +241,10 @@ def linear_decoder_single(before, after, offsets, voxel_coords, state):
 # ----------------------------------------------------------------------------- model
 def deflow_forward(batch: Dict, state: Dict[str, torch.Tensor], voxel_size=DEFAULT_VOXEL_SIZE,
                    pc_range=DEFAULT_RANGE, grid=(512, 512), decoder="gru", num_iters=4,
-                   training=True, buffers=None, return_internals=False) -> Dict:
-    """DeFlow.forward (OSF/src/models/deflow.py:49-114) / FastFlow3D.forward (fastflow3d.py:74-103)."""
+                   training=True, buffers=None, return_internals=False, sync_world=1) -> Dict:
+    """DeFlow.forward (OSF/src/models/deflow.py:49-114) / FastFlow3D.forward (fastflow3d.py:74-103).
+    sync_world = R: the batch holds the samples of R data-parallel ranks (rank-major) trained with SyncBatchNorm: BatchNorm2d
+    over the whole batch IS the pooled statistic; the per-sample BatchNorm1d calls are pooled across ranks (see embed)."""
     bsz = len(batch["pose0"])
     pose_flows, pc0s = [], []
     for b in range(bsz):
@@ -219,8 +256,8 @@ def deflow_forward(batch: Dict, state: Dict[str, torch.Tensor], voxel_size=DEFAU
         pose_flows.append(pf)
         pc0s.append(warped)
     pc0s = torch.stack(pc0s, 0)
-    img0, info0 = embed(pc0s, state, grid, voxel_size, pc_range, training, buffers)
-    img1, info1 = embed(batch["pc1"], state, grid, voxel_size, pc_range, training, buffers)
+    img0, info0 = embed(pc0s, state, grid, voxel_size, pc_range, training, buffers, sync_world)
+    img1, info1 = embed(batch["pc1"], state, grid, voxel_size, pc_range, training, buffers, sync_world)
     feat = unet(img0, img1, state, training, buffers)
     before = torch.cat([img0, img1], dim=1)
     flows = []
@@ -267,6 +304,17 @@ def ff3d_loss(est_flow, gt_flow, classes) -> torch.Tensor:
     return (err * ((classes > 0).float() * 0.9 + 0.1)).mean()
 
 
+def zeroflow_loss(est_flow, gt_flow) -> torch.Tensor:
+    """zeroflowLoss (OSF/src/lossfuncs.py:128-145)."""
+    ok = ~gt_flow.isnan() & ~est_flow.isnan() & ~gt_flow.isinf() & ~est_flow.isinf()
+    pred = est_flow[ok].reshape(-1, 3)
+    gt = gt_flow[ok].reshape(-1, 3)
+    err = torch.linalg.vector_norm(pred - gt, dim=-1)
+    speed = torch.linalg.vector_norm(gt, dim=-1) * 10.0
+    scale = torch.max(torch.ones_like(speed) * 0.1, torch.min(1.8 * speed - 0.8, torch.ones_like(speed)))
+    return (err * scale).mean()
+
+
 def training_step_loss(batch, res, loss="deflowLoss") -> torch.Tensor:
     """The arithmetic of ModelWrapper.training_step (OSF/src/trainer.py:116-152):
     gt = flow[idx] - pose_flow[idx]; per-sample losses are SUMMED over the batch."""
@@ -276,6 +324,8 @@ def training_step_loss(batch, res, loss="deflowLoss") -> torch.Tensor:
         gt = batch["flow"][b][idx] - res["pose_flow"][b][idx]
         if loss == "deflowLoss":
             total = total + deflow_loss(res["flow"][b], gt)
+        elif loss == "zeroflowLoss":
+            total = total + zeroflow_loss(res["flow"][b], gt)
         else:
             total = total + ff3d_loss(res["flow"][b], gt, batch["flow_category_indices"][b][idx])
     return total

@@ -285,7 +285,7 @@ def test_ego_warp_matches_oracle():
         np.testing.assert_allclose(pf[b].cpu().numpy(), ref_pf.numpy(), rtol=0, atol=1e-5, equal_nan=True)
 
 
-@pytest.mark.parametrize("name", ["deflowLoss", "ff3dLoss"])
+@pytest.mark.parametrize("name", ["deflowLoss", "ff3dLoss", "zeroflowLoss"])
 def test_loss_single_sample_api(name):
     gen = torch.Generator().manual_seed(4)
     n = 5000
@@ -296,11 +296,15 @@ def test_loss_single_sample_api(name):
     if name == "deflowLoss":
         gt[11] = float("nan")
         ref = orc.deflow_loss(est, gt)
+    elif name == "zeroflowLoss":
+        gt[11] = float("nan")
+        gt[12] = float("inf")
+        ref = orc.zeroflow_loss(est, gt)
     else:
         ref = orc.ff3d_loss(est, gt, cls)
     ref.backward()
     e2 = est.detach().to(DEV).requires_grad_(True)
-    fn = d.deflowLoss if name == "deflowLoss" else d.ff3dLoss
+    fn = {"deflowLoss": d.deflowLoss, "ff3dLoss": d.ff3dLoss, "zeroflowLoss": d.zeroflowLoss}[name]
     out = fn({"est_flow": e2, "gt_flow": gt.to(DEV), "gt_classes": cls.to(DEV)})["loss"]
     out.backward()
     assert abs(float(out) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))

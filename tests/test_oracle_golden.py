@@ -86,3 +86,23 @@ def test_training_trajectory_matches_reference(name, tol):
             w0 = orc.random_state(int(tz["seed_state"]), str(tz["decoder"]))[k[8:]].numpy()
             d_ref, d = tz[k] - w0, state[k[8:]].detach().numpy() - w0
             assert np.linalg.norm(d - d_ref) <= 50 * tol * np.linalg.norm(d_ref), k
+
+
+def test_loss_restatements_equal_reference_functions():
+    """deflowLoss / zeroflowLoss / ff3dLoss restatements against the reference's own functions (AST-extracted from
+    OSF/src/lossfuncs.py:102-157)."""
+    from oracle import ref_modules
+    if ref_modules.root() is None:
+        pytest.skip("reference sources not available")
+    ns = ref_modules.extract_functions("src/lossfuncs.py", ("deflowLoss", "ff3dLoss", "zeroflowLoss"))
+    g = torch.Generator().manual_seed(0)
+    n = 4000
+    gt = torch.randn(n, 3, generator=g) * torch.tensor([0.0, 0.03, 0.3])[torch.randint(0, 3, (n, 1), generator=g)]
+    est = gt + 0.05 * torch.randn(n, 3, generator=g)
+    gt[5] = float("nan")
+    cls = torch.randint(0, 3, (n,), generator=g).to(torch.uint8)
+    assert float(ns["deflowLoss"]({"est_flow": est, "gt_flow": gt})["loss"]) == pytest.approx(float(orc.deflow_loss(est, gt)), rel=1e-6)
+    assert float(ns["zeroflowLoss"]({"est_flow": est, "gt_flow": gt})["loss"]) == pytest.approx(float(orc.zeroflow_loss(est, gt)), rel=1e-6)
+    gt[5] = 0.0
+    assert float(ns["ff3dLoss"]({"est_flow": est, "gt_flow": gt, "gt_classes": cls})["loss"]) == pytest.approx(
+        float(orc.ff3d_loss(est, gt, cls)), rel=1e-6)
