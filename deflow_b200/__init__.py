@@ -5,5 +5,5 @@ from .encoder import DynamicEmbedder, DynamicPillarFeatureNet, DynamicVoxelizer,
 from .decoder import ConvGRU, ConvGRUDecoder, LinearDecoder  # noqa: F401
 from .unet import FastFlow3DUNet  # noqa: F401
 from .mmcv_ext import DynamicScatter, Voxelization, dynamic_scatter, voxelization  # noqa: F401
-from .lossfuncs import deflowLoss, ff3dLoss, zeroflowLoss, training_step_loss  # noqa: F401
-from . import eval_metric, feed  # noqa: F401,E402
+from .lossfuncs import deflowLoss, ff3dLoss, seflowLoss, zeroflowLoss, training_step_loss  # noqa: F401
+from . import chamfer3D, eval_metric, feed  # noqa: F401,E402

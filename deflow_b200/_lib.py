@@ -159,6 +159,8 @@ def _declare(lib):
         "dfb_head_out": [vp, vp, vp, i32, vp, i32, vp],
         "dfb_head_out_backward": [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp],
         "dfb_eval_accumulate": [vp, vp, vp, i32, vp, vp, vp, i64, C.POINTER(EvalTables), vp, vp],
+        "dfb_chamfer_forward": [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp],
+        "dfb_chamfer_backward": [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp],
         "dfb_collate_pad": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "dfb_gru_fused_forward": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
         "dfb_gru_fused_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
@@ -182,7 +184,8 @@ EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",
            "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",
            "dfb_gru_fused_forward", "dfb_gru_fused_backward", "dfb_collate_workspace", "dfb_collate_pad",
-           "dfb_eval_accumulate", "dfb_bn_gelu_backward_phase"]
+           "dfb_eval_accumulate", "dfb_bn_gelu_backward_phase",
+           "dfb_chamfer_forward", "dfb_chamfer_backward"]
 
 
 def lib():

@@ -105,6 +105,10 @@ class DeviceCollator:
             out["valid"] = torch.empty((B, Nmax), dtype=torch.uint8, device=dev)
             out["cls"] = torch.empty((B, Nmax), dtype=torch.uint8, device=dev)
         counts = torch.empty(B, dtype=torch.int32, device=dev)
+        if Nmax == 0 or total == 0:          # nothing survives the ground mask: an all-padding batch of width 0
+            counts.zero_()
+            out["counts"], out["keep_host"] = counts, keep
+            return out
         ws = torch.empty(int(lib.dfb_collate_workspace(B, max_n)), dtype=torch.int32, device=dev)
         P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         check(lib.dfb_collate_pad(pts.data_ptr(), gm.data_ptr(), offs.data_ptr(), B, max_n, Nmax, P(f), P(v), P(c),

@@ -382,6 +382,16 @@ int dfb_eval_accumulate(const float* est_flow, const float* rigid_flow, const fl
                         const float* gt_flow, const unsigned char* is_valid, const unsigned char* cls, long long n,
                         const dfb_eval_tables* tables, double* acc, void* stream);
 
+/* ------------------------------------------------------------------ chamfer nearest neighbours (seflowLoss)
+ * chamfer3D.forward / .backward (REF/assets/cuda/chamfer3D/chamfer3D_cuda.cpp, kernels chamfer3D.cu:33-124), used by
+ * seflowLoss (REF/src/lossfuncs.py:22-100).  pc0 f32[n0,3], pc1 f32[n1,3]; dist0[i] = min_j |pc0[i]-pc1[j]|^2 (squared),
+ * idx0[i] = the lowest j attaining it (1e20 / -1 for an empty target); dist1 / idx1 the other way round.
+ * workspace: n0 + n1 64-bit words.  backward: grad_pc0 / grad_pc1 f32[n,3] are zeroed inside, then receive both directions. */
+int dfb_chamfer_forward(const float* pc0, int n0, const float* pc1, int n1, float* dist0, float* dist1, int* idx0, int* idx1,
+                        unsigned long long* workspace, void* stream);
+int dfb_chamfer_backward(const float* pc0, int n0, const float* pc1, int n1, const int* idx0, const int* idx1,
+                         const float* grad_dist0, const float* grad_dist1, float* grad_pc0, float* grad_pc1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

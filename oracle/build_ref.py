@@ -62,7 +62,41 @@ def stage():
     return dst_root, n
 
 
+def build_chamfer(verbose=False):
+    """The reference's chamfer3D extension (assets/cuda/chamfer3D/{chamfer3D.cu, chamfer3D_cuda.cpp}; its setup.py lists
+    exactly these two files) -> oracle/_ref/chamfer3D_ref.so, the on-GPU checker of csrc/chamfer.cu."""
+    src = "/root/reference/OpenSceneFlow/assets/cuda/chamfer3D"
+    if not os.path.isdir(src):
+        return None
+    out = os.path.join(OUT, "chamfer")
+    os.makedirs(out, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    from torch.utils.cpp_extension import load
+    load(name="chamfer3D_ref", sources=[os.path.join(src, "chamfer3D_cuda.cpp"), os.path.join(src, "chamfer3D.cu")],
+         build_directory=out, verbose=verbose, is_python_module=False)
+    import shutil
+    shutil.copyfile(os.path.join(out, "chamfer3D_ref.so"), os.path.join(OUT, "chamfer3D_ref.so"))
+    return os.path.join(OUT, "chamfer3D_ref.so")
+
+
+def load_chamfer_ref():
+    global _loaded_chamfer
+    if _loaded_chamfer is not None:
+        return _loaded_chamfer
+    path = os.path.join(OUT, "chamfer3D_ref.so")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    import torch  # noqa: F401
+    spec = importlib.util.spec_from_file_location("chamfer3D_ref", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _loaded_chamfer = mod
+    return mod
+
+
 _loaded = None
+_loaded_chamfer = None
 
 
 def load_ref():
@@ -84,4 +118,5 @@ def load_ref():
 
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv))
+    print(build_chamfer(verbose="-v" in sys.argv))
     print(stage())

@@ -58,9 +58,9 @@ def test_training_trajectory_matches_reference_modules(name, tol_loss, tol_delta
     for k in tz.files:
         if k.startswith("weight::"):
             w0 = init[k[8:]].cpu().numpy()
-            d_ref, d = tz[k] - w0, sd[k[8:]].cpu().numpy() - w0
+            d_ref, d_got = tz[k] - w0, sd[k[8:]].cpu().numpy() - w0
             assert np.linalg.norm(d_ref) > 0
-            assert np.linalg.norm(d - d_ref) <= tol_delta * np.linalg.norm(d_ref), k
+            assert np.linalg.norm(d_got - d_ref) <= tol_delta * np.linalg.norm(d_ref), k
             # the verdict's criterion: weights after the last step within 1e-4 relative
             assert np.linalg.norm(sd[k[8:]].cpu().numpy() - tz[k]) <= 1e-4 * np.linalg.norm(tz[k]) * (1 if "lr2e-5" in name else 10), k
         if k.startswith("buf::"):   # running statistics after K updates (measured on B200: 1.4e-5 / 8e-5 abs on values ~0.05)

@@ -106,3 +106,25 @@ def test_loss_restatements_equal_reference_functions():
     gt[5] = 0.0
     assert float(ns["ff3dLoss"]({"est_flow": est, "gt_flow": gt, "gt_classes": cls})["loss"]) == pytest.approx(
         float(orc.ff3d_loss(est, gt, cls)), rel=1e-6)
+
+
+def test_seflow_loss_restatement_equals_reference_function():
+    """seflowLoss (OSF/src/lossfuncs.py:22-100): the reference's own function (AST-extracted, its MyCUDAChamferDis bound to the
+    CPU stand-in of the chamfer op) against oracle/seflow_oracle.seflow_loss, values and gradient."""
+    from oracle import ref_modules, seflow_oracle as so
+    if ref_modules.root() is None:
+        pytest.skip("reference sources not available")
+    ns = ref_modules.extract_functions("src/lossfuncs.py", ("seflowLoss",),
+                                       {"MyCUDAChamferDis": so.ChamferStandIn(), "TRUNCATED_DIST": 4})
+    for n0, n1, seed in ((3000, 2800, 1), (900, 1000, 2), (400, 300, 3)):      # the last has no dynamic cluster (<= 256 points)
+        sc = so.make_scene(n0, n1, seed)
+        e1 = sc["est_flow"].clone().requires_grad_(True)
+        e2 = sc["est_flow"].clone().requires_grad_(True)
+        ref = ns["seflowLoss"]({**sc, "est_flow": e1})
+        got = so.seflow_loss({**sc, "est_flow": e2})
+        assert set(ref) == set(got)
+        for k in ref:
+            assert float(ref[k]) == pytest.approx(float(got[k]), rel=1e-6, abs=1e-7), k
+        sum(ref.values()).backward()
+        sum(got.values()).backward()
+        np.testing.assert_allclose(e2.grad.numpy(), e1.grad.numpy(), rtol=1e-5, atol=1e-8)
