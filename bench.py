@@ -540,6 +540,11 @@ def run_native(args):
                 "config": workload_config(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "scatter": scatter, "stages_ms": stages, "loss": float(loss),
                 "flow_err": flow_err, "ms_per_step_regions": regions, "lr": 2e-6,
+                "sync_bn_exchange": ({"collectives_per_step": step.stat_sync.calls / max(step.global_step, 1),
+                                      "bytes_per_step": step.stat_sync.bytes / max(step.global_step, 1)}
+                                     if step.stat_sync is not None else None),
+                "grad_allreduce": {"bytes": step.grads.nbytes, "op": "AVG", "early_slice_params": (
+                    len(step.grads.params) - step.grads.early_from if step.grads.early_from is not None else 0)},
                 "timed_seconds": sum(regions) * args.steps * 1e-3}
     if world > 1:
         dist.barrier()

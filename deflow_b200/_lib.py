@@ -161,6 +161,7 @@ def _declare(lib):
         "dfb_eval_accumulate": [vp, vp, vp, i32, vp, vp, vp, i64, C.POINTER(EvalTables), vp, vp],
         "dfb_chamfer_forward": [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp],
         "dfb_chamfer_backward": [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp],
+        "dfb_hard_voxelize_assign": [vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp],
         "dfb_collate_pad": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "dfb_gru_fused_forward": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
         "dfb_gru_fused_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
@@ -171,6 +172,8 @@ def _declare(lib):
         fn.argtypes = args
     lib.dfb_index_scan_workspace.restype = i64
     lib.dfb_index_scan_workspace.argtypes = [i32, i64, i64]
+    lib.dfb_hard_voxelize_workspace.restype = i64
+    lib.dfb_hard_voxelize_workspace.argtypes = [i32]
     lib.dfb_collate_workspace.restype = i64
     lib.dfb_collate_workspace.argtypes = [i32, i32]
     return sig
@@ -185,7 +188,7 @@ EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size",
            "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",
            "dfb_gru_fused_forward", "dfb_gru_fused_backward", "dfb_collate_workspace", "dfb_collate_pad",
            "dfb_eval_accumulate", "dfb_bn_gelu_backward_phase",
-           "dfb_chamfer_forward", "dfb_chamfer_backward"]
+           "dfb_chamfer_forward", "dfb_chamfer_backward", "dfb_hard_voxelize_workspace", "dfb_hard_voxelize_assign"]
 
 
 def lib():

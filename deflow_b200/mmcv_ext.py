@@ -92,7 +92,7 @@ class DynamicScatter(nn.Module):
 
 
 class _Voxelization(Function):
-    """Dynamic branch of OSF/assets/cuda/mmcv/voxelize.py:22-112 (max_points == -1 or max_voxels == -1)."""
+    """OSF/assets/cuda/mmcv/voxelize.py:22-112: dynamic branch (max_points == -1 or max_voxels == -1) and hard branch."""
 
     @staticmethod
     def forward(ctx, points, voxel_size, coors_range, max_points=35, max_voxels=20000, deterministic=True):
@@ -101,7 +101,16 @@ class _Voxelization(Function):
             _ext.dynamic_voxelize_forward(points, torch.tensor(voxel_size, dtype=torch.float),
                                           torch.tensor(coors_range, dtype=torch.float), coors, NDim=3)
             return coors
-        return _ext.hard_voxelize_forward(points, voxel_size, coors_range, max_points, max_voxels, deterministic)
+        # voxelize.py:86-111
+        voxels = points.new_zeros(size=(max_voxels, max_points, points.size(1)))
+        coors = points.new_zeros(size=(max_voxels, 3), dtype=torch.int)
+        num_points_per_voxel = points.new_zeros(size=(max_voxels,), dtype=torch.int)
+        voxel_num = torch.zeros(size=(), dtype=torch.long)
+        _ext.hard_voxelize_forward(points, torch.tensor(voxel_size, dtype=torch.float),
+                                   torch.tensor(coors_range, dtype=torch.float), voxels, coors, num_points_per_voxel,
+                                   voxel_num, max_points=max_points, max_voxels=max_voxels, NDim=3,
+                                   deterministic=deterministic)
+        return voxels[:voxel_num], coors[:voxel_num], num_points_per_voxel[:voxel_num]
 
 
 voxelization = _Voxelization.apply

@@ -396,6 +396,32 @@ def dynamic_voxelize_forward(points, voxel_size, coors_range, coors, NDim=3):
                                                   coors.data_ptr(), _stream(points)), "dynamic_voxelize_forward")
 
 
+def _scatter_index(coors, extent=None):
+    """Unique voxels of int32 coordinate rows (any row with a negative component is invalid): dfb_scatter_index.
+    -> point2voxel_map[n], voxel_coors[n,3] (first M rows valid, sorted), counts[n], pil_start[n+1], sorted_pt[n], counts6."""
+    n = coors.shape[0]
+    dev = coors.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    if extent is None:
+        # exclusive coordinate bound: one small reduction + host read, like the reference's own
+        # .item() sync after unique_dim (scatter_points_cuda.cu:29)
+        ext = (coors.max(dim=0).values + 1).clamp_(min=1).tolist()
+    else:
+        ext = [int(e) for e in extent]
+    extent_c = (C.c_int * 3)(*ext)
+    cells = ext[0] * ext[1] * ext[2]
+    words = (cells + 31) // 32
+    bitmap, word_rank = torch.empty(words, **i32), torch.empty(words, **i32)
+    blk, slot = torch.empty((n + 1023) // 1024, **i32), torch.empty(n, **i32)
+    cmap, vcoors, vcount = torch.empty(n, **i32), torch.empty((n, 3), **i32), torch.empty(n, **i32)
+    pil_start, sorted_pt, counts6 = torch.empty(n + 1, **i32), torch.empty(n, **i32), torch.empty(6, **i32)
+    check(_lib.lib().dfb_scatter_index(coors.data_ptr(), n, extent_c, bitmap.data_ptr(), word_rank.data_ptr(), blk.data_ptr(),
+                                       slot.data_ptr(), cmap.data_ptr(), vcoors.data_ptr(), vcount.data_ptr(),
+                                       pil_start.data_ptr(), sorted_pt.data_ptr(), counts6.data_ptr(), _stream(coors)),
+          "scatter_index")
+    return cmap, vcoors, vcount, pil_start, sorted_pt, counts6
+
+
 def dynamic_point_to_voxel_forward(feats, coors, reduce_type):
     """mmcv._ext.dynamic_point_to_voxel_forward (OSF/assets/cuda/mmcv/scatter_points_cuda.cu:9-66)
     -> [voxel_feats, voxel_coors, point2voxel_map, voxel_points_count]."""
@@ -409,21 +435,9 @@ def dynamic_point_to_voxel_forward(feats, coors, reduce_type):
     i32 = dict(dtype=torch.int32, device=dev)
     if n == 0:  # scatter_points_cuda.cu:15-18
         return [feats.clone(), coors.clone(), torch.empty(0, **i32), torch.empty(0, **i32)]
-    # exclusive coordinate bound: one small reduction + host read, like the reference's own
-    # .item() sync after unique_dim (scatter_points_cuda.cu:29)
-    ext = (coors.max(dim=0).values + 1).clamp_(min=1).tolist()
-    extent = (C.c_int * 3)(*ext)
-    cells = ext[0] * ext[1] * ext[2]
-    words = (cells + 31) // 32
-    bitmap, word_rank = torch.empty(words, **i32), torch.empty(words, **i32)
-    blk, slot = torch.empty((n + 1023) // 1024, **i32), torch.empty(n, **i32)
-    cmap, vcoors, vcount = torch.empty(n, **i32), torch.empty((n, 3), **i32), torch.empty(n, **i32)
-    pil_start, sorted_pt, counts6 = torch.empty(n + 1, **i32), torch.empty(n, **i32), torch.empty(6, **i32)
+    cmap, vcoors, vcount, pil_start, sorted_pt, counts6 = _scatter_index(coors)
     lib = _lib.lib()
     st = _stream(feats)
-    check(lib.dfb_scatter_index(coors.data_ptr(), n, extent, bitmap.data_ptr(), word_rank.data_ptr(), blk.data_ptr(),
-                                slot.data_ptr(), cmap.data_ptr(), vcoors.data_ptr(), vcount.data_ptr(),
-                                pil_start.data_ptr(), sorted_pt.data_ptr(), counts6.data_ptr(), st), "scatter_index")
     out = torch.empty((n, c), dtype=torch.float32, device=dev)
     check(lib.dfb_scatter_reduce(feats.data_ptr(), n, c, pil_start.data_ptr(), sorted_pt.data_ptr(),
                                  counts6[1:].data_ptr(), n, REDUCE[reduce_type], out.data_ptr(), st), "scatter_reduce")
@@ -450,7 +464,36 @@ def dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats, reduc
         n, m, c, REDUCE[reduce_type], _ptr(ws), _stream(grad_feats)), "dynamic_point_to_voxel_backward")
 
 
-def hard_voxelize_forward(*args, **kwargs):
-    """Exists by name because OSF/assets/cuda/mmcv/voxelize.py:17-18 asserts it at import; no model on
-    the DeFlow path calls it (HardVoxelizer is unused -- SURVEY.md section 2.1 row 3)."""
-    raise RuntimeError("hard_voxelize_forward is outside the DeFlow hot path and is not implemented in deflow_b200")
+def hard_voxelize_forward(points, voxel_size, coors_range, voxels, coors, num_points_per_voxel, voxel_num, max_points,
+                          max_voxels, NDim=3, deterministic=True):
+    """mmcv._ext.hard_voxelize_forward (OSF/assets/cuda/mmcv/voxelization.cpp:36-60, voxelization_cuda.cu:8-148): fills the
+    caller's pre-zeroed ``voxels [max_voxels,max_points,F]``, ``coors [max_voxels,3]``, ``num_points_per_voxel [max_voxels]``
+    and sets ``voxel_num`` (a 0-d int64 tensor, voxelize.py:94).  Voxels are numbered in order of first appearance and keep
+    their first ``max_points`` points -- the reference's deterministic result (``deterministic=False`` may return any valid
+    assignment there; the deterministic one is returned here too)."""
+    _need_cuda(points, "hard_voxelize_forward")
+    if NDim != 3:
+        raise RuntimeError("hard_voxelize_forward: NDim must be 3")
+    points = points.contiguous()
+    assert points.dtype == torch.float32 and voxels.is_contiguous() and coors.is_contiguous() and coors.dtype == torch.int32
+    assert num_points_per_voxel.dtype == torch.int32 and num_points_per_voxel.is_contiguous()
+    n, c = points.shape
+    if n == 0:
+        voxel_num.fill_(0)
+        return
+    dev = points.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    vs_t = torch.as_tensor(voxel_size, dtype=torch.float32)
+    rg_t = torch.as_tensor(coors_range, dtype=torch.float32)
+    tmp = torch.zeros((n, 3), **i32)
+    dynamic_voxelize_forward(points, vs_t, rg_t, tmp, 3)
+    gx, gy, gz = grid_size(vs_t.tolist(), rg_t.tolist())
+    cmap, _, _, pil_start, sorted_pt, _ = _scatter_index(tmp, (gz, gy, gx))
+    lib = _lib.lib()
+    ws = torch.empty(int(lib.dfb_hard_voxelize_workspace(n)), **i32)
+    vnum = torch.zeros(1, **i32)
+    check(lib.dfb_hard_voxelize_assign(points.data_ptr(), n, c, tmp.data_ptr(), cmap.data_ptr(), pil_start.data_ptr(),
+                                       sorted_pt.data_ptr(), int(max_points), int(max_voxels), voxels.data_ptr(),
+                                       coors.data_ptr(), num_points_per_voxel.data_ptr(), vnum.data_ptr(), ws.data_ptr(),
+                                       _stream(points)), "hard_voxelize_assign")
+    voxel_num.fill_(int(vnum.item()))      # the reference returns the count to the host as well (voxelization_cuda.cu:144-147)

@@ -392,6 +392,19 @@ int dfb_chamfer_forward(const float* pc0, int n0, const float* pc1, int n1, floa
 int dfb_chamfer_backward(const float* pc0, int n0, const float* pc1, int n1, const int* idx0, const int* idx1,
                          const float* grad_dist0, const float* grad_dist1, float* grad_pc0, float* grad_pc1, void* stream);
 
+/* ------------------------------------------------------------------ hard voxelisation
+ * hard_voxelize_forward(points, voxel_size, coors_range, voxels, coors, num_points_per_voxel, voxel_num, max_points,
+ * max_voxels, NDim=3, deterministic) (REF/assets/cuda/mmcv/voxelization.cpp:36-60, voxelization_cuda.cu:8-148): three calls
+ *   1. dfb_dynamic_voxelize_forward -> coors i32[n,3];   2. dfb_scatter_index on them -> point2voxel_map, pil_start, sorted_pt;
+ *   3. dfb_hard_voxelize_assign: voxels f32[max_voxels,max_points,num_features], voxel_coors i32[max_voxels,3] and
+ *      num_points_per_voxel i32[max_voxels] (all pre-zeroed by the caller, as voxelize.py:88-93 does), voxel_num i32[1]
+ *      (device).  Voxels are numbered in order of first appearance; a voxel keeps its first max_points points.
+ * workspace: dfb_hard_voxelize_workspace(n) ints. */
+long long dfb_hard_voxelize_workspace(int n);
+int dfb_hard_voxelize_assign(const float* points, int n, int num_features, const int* coors, const int* point2voxel_map,
+                             const int* pil_start, const int* sorted_pt, int max_points, int max_voxels, float* voxels,
+                             int* voxel_coors, int* num_points_per_voxel, int* voxel_num, int* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,3 +157,35 @@ def dynamic_point_to_voxel_backward(grad_reduced: np.ndarray, feats: np.ndarray,
         mm, cc = np.nonzero(src < n)
         grad[src[mm, cc], cc] = grad_reduced[mm, cc]
     return grad
+
+
+def hard_voxelize_forward(points, voxel_size, coors_range, max_points, max_voxels):
+    """HardVoxelizeForwardCUDAKernelLauncher, deterministic (voxelization_cuda.cu:8-148; kernels
+    voxelization_cuda_kernel.cuh:52-170): voxels are numbered in order of first appearance (determin_voxel_num), a voxel
+    keeps its first max_points points (point_to_voxelidx_kernel), voxels beyond max_voxels are dropped.
+    -> voxels f32[M,max_points,F], coors i32[M,3], num_points_per_voxel i32[M]."""
+    points = np.ascontiguousarray(points, np.float32)
+    n, f = points.shape
+    tmp = dynamic_voxelize_forward(points, voxel_size, coors_range, np.zeros((n, 3), np.int32))
+    voxels = np.zeros((max_voxels, max_points, f), np.float32)
+    coors = np.zeros((max_voxels, 3), np.int32)
+    num = np.zeros((max_voxels,), np.int32)
+    seen = {}            # coordinate -> [voxel id or -1, points seen so far]
+    voxel_num = 0
+    for i in range(n):
+        if tmp[i, 0] == -1:
+            continue
+        key = (int(tmp[i, 0]), int(tmp[i, 1]), int(tmp[i, 2]))
+        ent = seen.get(key)
+        if ent is None:
+            vid = voxel_num if voxel_num < max_voxels else -1
+            if vid >= 0:
+                voxel_num += 1
+                coors[vid] = tmp[i]
+            ent = seen[key] = [vid, 0]
+        rank = ent[1]
+        ent[1] += 1
+        if rank < max_points and ent[0] >= 0:
+            voxels[ent[0], rank] = points[i]
+            num[ent[0]] += 1
+    return voxels[:voxel_num], coors[:voxel_num], num[:voxel_num]

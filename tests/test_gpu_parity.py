@@ -152,6 +152,42 @@ def test_pillar_index_bit_exact(F, n, vs, rg):
     assert np.array_equal(pil[srt], np.repeat(np.arange(m_tot), np.diff(start)))
 
 
+def test_three_d_voxels_flow4d_configuration():
+    """the second consumer of the encoder -- Flow4D voxelises in 3-D (voxel 0.2 m cubes, z in [-3.2, 3.2]: 32
+    layers, OSF/src/models/basic/flow4d_module.py:31-115) with the same DynamicVoxelizer / DynamicPillarFeatureNet classes.
+    Index integers bit-exact against the oracle; per-voxel features of the per-sample call within fp32 tolerance."""
+    vs3, rg3 = [0.2, 0.2, 0.2], [-12.8, -12.8, -3.2, 12.8, 12.8, 3.2]
+    rng = np.random.default_rng(77)
+    F, n = 2, 6000
+    pts = rng.normal(size=(F, n, 3)).astype(np.float32) * np.array([6.0, 6.0, 1.5], np.float32)
+    pts[0, n - 50:] = np.nan
+    tp = torch.from_numpy(pts)
+    idx = ops.pillar_index(tp.to(DEV), vs3, rg3)
+    assert idx.grid == (128, 128, 32)
+    for f in range(F):
+        info = orc.voxelize_frame(tp[f], vs3, rg3)
+        vc, cmap, cnt = ext.unique_pillars(info["voxel_coords"].numpy())
+        a, b, q0, q1 = idx.pt_off(f), idx.pt_off(f + 1), idx.pil_off(f), idx.pil_off(f + 1)
+        assert int(info["voxel_coords"][:, 0].max()) > 0                           # several z layers are occupied
+        assert torch.equal(idx.pt_coor[a:b].cpu(), info["voxel_coords"]) and torch.equal(idx.pt_idx[a:b].cpu(), info["point_idxes"])
+        assert np.array_equal(idx.pil_coor[q0:q1].cpu().numpy(), vc) and np.array_equal(idx.pil_cnt[q0:q1].cpu().numpy(), cnt)
+        assert np.array_equal(idx.pt_pillar[a:b].cpu().numpy() - q0, cmap)
+        assert torch.equal(idx.pt_offs[a:b].cpu(), info["point_offsets"])
+    # per-sample feature net with 16 output channels, as Flow4D configures it
+    torch.manual_seed(2)
+    net = d.DynamicPillarFeatureNet(3, vs3, rg3, feat_channels=(16,), mode="avg").to(DEV).train()
+    state = {"embedder.feature_net." + k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    info = d.DynamicVoxelizer(vs3, rg3)(tp[1:2].to(DEV))[0]
+    vf, vcoors, pf = net(info["points"], info["voxel_coords"])
+    o = orc.voxelize_frame(tp[1], vs3, rg3)
+    buffers = {k: v.clone() for k, v in state.items() if "running" in k}
+    rvf, rvc, rpf, _, _ = orc.pillar_feature_net(o["points"], o["voxel_coords"], state, voxel_size=vs3, pc_range=rg3,
+                                                 training=True, buffers=buffers)
+    assert torch.equal(vcoors.cpu(), rvc)
+    np.testing.assert_allclose(vf.detach().cpu().numpy(), rvf.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(pf.detach().cpu().numpy(), rpf.numpy(), rtol=1e-4, atol=2e-5)
+
+
 def test_pillar_index_empty_frames():
     pts = torch.full((2, 16, 3), float("nan"))
     pts[1, :4] = torch.tensor([[0.0, 0, 0], [0.01, 0.01, 0], [200.0, 0, 0], [5.0, 5.0, 0.5]])

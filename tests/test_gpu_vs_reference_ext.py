@@ -75,3 +75,34 @@ def test_batched_pillar_index_equals_reference_kernels_on_synthetic_av2(ref):
         assert torch.equal(idx.pt_coor[a:b], coors) and torch.equal(idx.pt_xyz[a:b], pv)
         assert torch.equal(idx.pil_coor[q0:q1], vc) and torch.equal(idx.pil_cnt[q0:q1], cnt)
         assert torch.equal(idx.pt_pillar[a:b] - q0, cmap)
+
+
+@pytest.mark.parametrize("n,max_points,max_voxels,seed", [(30000, 10, 20000, 1), (30000, 3, 500, 2), (5000, 35, 20000, 3), (1, 5, 5, 4)])
+def test_hard_voxelize_equals_reference_kernel_and_oracle(ref, n, max_points, max_voxels, seed):
+    """hard_voxelize_forward (voxelization_cuda.cu:8-148): bit-exact against the reference's own kernels (deterministic path)
+    and the numpy oracle -- voxel order of first appearance, per-voxel point order, max_points / max_voxels truncation."""
+    from oracle import mmcv_ext_oracle as ext
+    vs, rg = [0.4, 0.4, 6], [-20.0, -20.0, -3, 20.0, 20.0, 3]
+    rng = np.random.default_rng(seed)
+    pts = np.concatenate([rng.normal(size=(n, 3)).astype(np.float32) * np.array([9, 9, 1.5], np.float32),
+                          rng.random(size=(n, 1)).astype(np.float32)], 1)        # xyz + intensity
+    tp = torch.from_numpy(pts).to(DEV)
+    out = {}
+    for name, fn in (("ref", ref.hard_voxelize_forward), ("dfb", ops.hard_voxelize_forward)):
+        voxels = torch.zeros((max_voxels, max_points, 4), device=DEV)
+        coors = torch.zeros((max_voxels, 3), dtype=torch.int32, device=DEV)
+        npv = torch.zeros((max_voxels,), dtype=torch.int32, device=DEV)
+        vnum = torch.zeros((), dtype=torch.long)
+        fn(tp, torch.tensor(vs, dtype=torch.float32), torch.tensor(rg, dtype=torch.float32), voxels, coors, npv, vnum,
+           max_points, max_voxels, 3, True)
+        m = int(vnum)
+        out[name] = (voxels[:m].cpu(), coors[:m].cpu(), npv[:m].cpu())
+    ov, oc, on = ext.hard_voxelize_forward(pts, vs, rg, max_points, max_voxels)
+    for a, b in zip(out["dfb"], out["ref"]):
+        assert torch.equal(a, b)
+    assert np.array_equal(out["dfb"][0].numpy(), ov) and np.array_equal(out["dfb"][1].numpy(), oc)
+    assert np.array_equal(out["dfb"][2].numpy(), on)
+    # the module surface (voxelize.py:115-189)
+    import deflow_b200 as d
+    v, c, k = d.Voxelization(vs, rg, max_points, max_voxels)(tp)
+    assert torch.equal(v.cpu(), out["ref"][0]) and torch.equal(c.cpu(), out["ref"][1]) and torch.equal(k.cpu(), out["ref"][2])
