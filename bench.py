@@ -399,7 +399,8 @@ def run_native(args):
 
     # stage breakdown (one extra step with events; not part of `value`)
     stages = {}
-    if rank == 0:
+    # (with SyncBatchNorm every forward / backward contains collectives, so the extra step has to run on all ranks)
+    if rank == 0 or args.sync_bn:
         evs = {}
         orig = {}
 
@@ -463,10 +464,12 @@ def run_native(args):
     # north-star 1e-3 bound against the oracle: tests/test_gpu_parity.py) on the bench batch, same weights, train-mode
     # BatchNorm -- SURVEY 8d: "the measured flow error printed beside every perf-mode number"
     flow_err = None
-    if rank == 0 and not args.no_flow_err and not os.environ.get("DFB_PROFILE"):
+    if (rank == 0 or args.sync_bn) and not args.no_flow_err and not os.environ.get("DFB_PROFILE"):
         try:
             par = d.DeFlow(vs, RG, [args.grid, args.grid], args.decoder, 4, precision="fp32").to(dev).train()
             par.load_state_dict(model.state_dict())
+            if args.sync_bn:
+                dd.enable_sync_bn(par, step.stat_sync)
             with torch.no_grad():
                 fa = model(resident)["_dfb"]["flow_flat"].float()
                 fb = par(resident)["_dfb"]["flow_flat"].float()
