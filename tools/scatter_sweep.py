@@ -62,9 +62,13 @@ def main():
              f"{'pts/frame':>9s} | {'fused ms':>8s} {'GB/s 8d':>8s} {'frac':>5s} {'GB/s -canvas':>12s} {'frac':>5s} {'M/N':>5s} | "
              f"{'ext C=3 ms':>10s} {'GB/s':>6s} | {'ext C=32 ms':>11s} {'GB/s':>6s}"]
     rows = []
+    bench.scatter_microbench(dev, peaks, n=100000, grid=1024, iters=3)     # global warm-up (allocator, function attributes)
+    ext_path(dev, 100000, 32, iters=2)
     for n in (25000, 50000, 100000, 200000, 400000):
-        sc = bench.scatter_microbench(dev, peaks, n=n, grid=1024, iters=5)
+        bench.scatter_microbench(dev, peaks, n=n, grid=1024, iters=2)      # per-size warm-up: buffers of this size exist
+        sc = bench.scatter_microbench(dev, peaks, n=n, grid=1024, iters=8)
         ms = sum(sc["ms"].values())
+        ext_path(dev, n, 3, iters=1)
         m3, b3 = ext_path(dev, n, 3)
         m32, b32 = ext_path(dev, n, 32)
         rows.append({"n": n, "fused": sc, "ext_c3_ms": m3, "ext_c3_gbs": b3 / m3 / 1e6, "ext_c32_ms": m32, "ext_c32_gbs": b32 / m32 / 1e6})
