@@ -179,22 +179,23 @@ def conv2d_dgrad(gy: torch.Tensor, w_dgrad, H, W, cin, cin_total, cin_off, ksize
     return gx
 
 
-def conv2d_dgrad_two(gy: torch.Tensor, w_dgrad, H, W, c0, c1, cin_total, ksize):
+def conv2d_dgrad_two(gy: torch.Tensor, w_dgrad, H, W, c0, c1, cin_total, ksize, colsum: bool = True):
     """1x1 stride-1 data gradient for BOTH sources of a concatenated input in one pass over gy:
-    -> (gx0 [n,H,W,c0], gx1 [n,H,W,c1]) bf16, each with its per-channel sum attached (``_dfb_colsum``)."""
+    -> (gx0 [n,H,W,c0], gx1 [n,H,W,c1]) bf16; with ``colsum`` each carries its per-channel sum (``_dfb_colsum``)."""
     assert gy.is_contiguous() and gy.dtype == torch.bfloat16 and ksize == 1
     n, _, _, cout = gy.shape
     gx0 = torch.empty((n, H, W, c0), dtype=torch.bfloat16, device=gy.device)
     gx1 = torch.empty((n, H, W, c1), dtype=torch.bfloat16, device=gy.device)
-    stats = zeros((2, c0 + c1), torch.float64, gy.device)
+    stats = zeros((2, c0 + c1), torch.float64, gy.device) if colsum else None
     a = _args(1, n, H, W, ksize, 1, [gy], [c0], cout, w_dgrad, None, gx0, stats, cin_total, 0)
-    a.stats_sum_only = 1
+    a.stats_sum_only = int(colsum)
     a.y2, a.cin2 = gx1.data_ptr(), c1
     kc = 64 if cout % 64 == 0 else 32
     with _timed(f"k_conv_igemm<{c0 + c1},{kc}>", 2.0 * n * H * W * cout * (c0 + c1), gy):
         check(_lib.lib().dfb_conv2d(C.byref(a), _stream(gy)), "conv2d dgrad (two outputs)")
-    gx0._dfb_colsum = (stats[0][:c0], gx0._version)
-    gx1._dfb_colsum = (stats[0][c0:], gx1._version)
+    if colsum:
+        gx0._dfb_colsum = (stats[0][:c0], gx0._version)
+        gx1._dfb_colsum = (stats[0][c0:], gx1._version)
     return gx0, gx1
 
 
@@ -403,28 +404,37 @@ class _Conv(torch.autograd.Function):
         k = w.shape[2]
         wf, wd = packed(w, x0.dtype == torch.float32)
         y = conv2d_forward(xs, wf, b.detach().float().contiguous(), w.shape[0], k, 1)
-        ctx.save_for_backward(wd, *xs)
+        ctx.save_for_backward(wd, w, *xs)
         ctx.k, ctx.wshape = k, tuple(w.shape)
         ctx.need = (ctx.needs_input_grad[2], x1 is not None and ctx.needs_input_grad[3])
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        wd, *xs = ctx.saved_tensors
+        wd, w, *xs = ctx.saved_tensors
         gb = bias_grad(gy)       # before .contiguous(): the attribute lives on the tensor the producer returned
         gy = gy.contiguous()
         k = ctx.k
         ct = ctx.wshape[1]
         gw = conv2d_wgrad(xs, gy, k, 1)
         gxs, off = [None, None], 0
+        # Per-channel sums of the data gradient = the bias gradient of the convolution that produced this input.  3x3: from
+        # the epilogue of the (MMA-bound) halo kernel, where they are nearly free.  1x1: the epilogue is what bounds these
+        # HBM-bound launches and the column sums doubled it (B200: 0.077 -> 0.140 ms for dec2.u1), while for a 1x1 stride-1
+        # convolution they follow exactly from sum_p gx[p, ci] = sum_co W[co, ci] * sum_p gy[p, co] = (W^T gb)[ci].
+        mv = (w.detach().reshape(w.shape[0], ct).float().t() @ gb.float()) if k == 1 else None
         if (len(xs) == 2 and k == 1 and all(ctx.need) and gy.dtype == torch.bfloat16
                 and xs[0].shape[3] % 32 == 0 and xs[1].shape[3] % 32 == 0 and ct in (32, 64, 128, 256)):
-            g0, g1 = conv2d_dgrad_two(gy, wd, xs[0].shape[1], xs[0].shape[2], xs[0].shape[3], xs[1].shape[3], ct, k)
+            c0 = xs[0].shape[3]
+            g0, g1 = conv2d_dgrad_two(gy, wd, xs[0].shape[1], xs[0].shape[2], c0, xs[1].shape[3], ct, k, colsum=False)
+            g0._dfb_colsum, g1._dfb_colsum = (mv[:c0], g0._version), (mv[c0:], g1._version)
             return gw, gb, g0, g1
         for i, x in enumerate(xs):
             c = x.shape[3]
             if ctx.need[i]:
-                gxs[i] = conv2d_dgrad(gy, wd, x.shape[1], x.shape[2], c, ct, off, k, 1, colsum=True)
+                gxs[i] = conv2d_dgrad(gy, wd, x.shape[1], x.shape[2], c, ct, off, k, 1, colsum=(k != 1))
+                if k == 1:
+                    gxs[i]._dfb_colsum = (mv[off:off + c], gxs[i]._version)
             off += c
         return gw, gb, gxs[0], gxs[1]
 
@@ -505,7 +515,13 @@ class _Upsample2x(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return upsample2x(g.contiguous(), backward=True)
+        cs = getattr(g, "_dfb_colsum", None)
+        out = upsample2x(g.contiguous(), backward=True)
+        # every output pixel of the bilinear x2 spreads weights that sum to 1 (edge replication included), so the adjoint
+        # preserves per-channel sums exactly: the bias-gradient sums ride through to the 1x1 convolution in front
+        if cs is not None and cs[1] == g._version:
+            out._dfb_colsum = (cs[0], out._version)
+        return out
 
 
 def upsample_bilinear2x(x):

@@ -11,7 +11,8 @@
 // float4 (one broadcast LDS.128 per target), every thread scans it for TWO queries, and the partial minima meet in one
 // 64-bit atomicMin per query on the key (distance bits << 32 | index): non-negative floats order like their bit patterns,
 // so the minimum key is the smallest distance and, among equal distances, the smallest index -- the reference's
-// tie-break.  Distance arithmetic is pinned to the reference's contraction: fma(dz,dz, fma(dy,dy, dx*dx)).
+// tie-break.  Distance arithmetic is pinned to what nvcc makes of the reference's expression (checked in its SASS: FMUL on
+// dy, then FFMA with dx, then FFMA with dz): fma(dz,dz, fma(dx,dx, dy*dy)).
 #include "common.cuh"
 #include "../../include/deflow_b200.h"
 
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chamfer_nn(const float* __restri
 #pragma unroll
       for (int k = 0; k < CH_Q; ++k) {
         const float dx = __fsub_rn(t.x, qx[k]), dy = __fsub_rn(t.y, qy[k]), dz = __fsub_rn(t.z, qz[k]);
-        const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+        const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
         if (d < best[k]) { best[k] = d; best_i[k] = base + j; }
       }
     }

@@ -1,8 +1,8 @@
 """CPU restatement of the chamfer nearest-neighbour op and of seflowLoss.  TEST INFRASTRUCTURE ONLY (oracle/__init__.py).
 
 * ``chamfer_forward`` -- NmDistanceKernel (OpenSceneFlow/assets/cuda/chamfer3D/chamfer3D.cu:33-74): squared distance
-  d = (x1-x0)^2 + (y1-y0)^2 + (z1-z0)^2 in fp32 as nvcc contracts it (fma(dz,dz, fma(dy,dy, dx*dx)), emulated through
-  float64), strict `<` scan = lowest index among equal distances, (1e20, -1) for an empty target.  Pinned on the GPU against
+  d = (x1-x0)^2 + (y1-y0)^2 + (z1-z0)^2 in fp32 as nvcc contracts it (fma(dz,dz, fma(dx,dx, dy*dy)) -- read off the SASS of
+  that expression -- emulated through float64), strict `<` scan = lowest index among equal distances, (1e20, -1) for an empty target.  Pinned on the GPU against
   the reference's own compiled extension (oracle/_ref/chamfer3D_ref.so, tests/test_gpu_chamfer.py).
 * ``ChamferStandIn`` -- the object ``MyCUDAChamferDis`` of OSF/src/lossfuncs.py:14-16, differentiable on the CPU
   (gradient = NmDistanceGradKernel, chamfer3D.cu:92-114).
@@ -26,8 +26,8 @@ def _nn(q, t, chunk=2048):
         dx = (t32[None, :, 0] - qq[:, None, 0]).astype(np.float32)
         dy = (t32[None, :, 1] - qq[:, None, 1]).astype(np.float32)
         dz = (t32[None, :, 2] - qq[:, None, 2]).astype(np.float32)
-        d = (dx * dx).astype(np.float32)
-        d = (dy.astype(np.float64) * dy.astype(np.float64) + d.astype(np.float64)).astype(np.float32)
+        d = (dy * dy).astype(np.float32)
+        d = (dx.astype(np.float64) * dx.astype(np.float64) + d.astype(np.float64)).astype(np.float32)
         d = (dz.astype(np.float64) * dz.astype(np.float64) + d.astype(np.float64)).astype(np.float32)
         i = np.argmin(d, axis=1)                       # first minimum = lowest index
         dist[a:a + chunk] = d[np.arange(d.shape[0]), i]
