@@ -48,50 +48,51 @@ TRUNCATED_DIST = 4   # OSF/src/lossfuncs.py:19
 
 def seflowLoss(res_dict, timer=None):
     """Self-supervised SeFlow loss (OSF/src/lossfuncs.py:22-100): chamfer, dynamic chamfer, static-flow and cluster terms.
-    The nearest-neighbour searches -- the native op of this loss (chamfer3D.cu) -- run on csrc/chamfer.cu; the per-cluster
-    bookkeeping is the reference's torch-level glue (data-dependent label loop), kept as it is there."""
+
+    The nearest-neighbour searches -- the native op of this loss (chamfer3D.cu) -- run on csrc/chamfer.cu.  The cluster term
+    (Eq. 8-11; a Python loop over the labels with an argsort, a nonzero and three boolean-index kernels per cluster in the
+    reference, lossfuncs.py:63-86) is evaluated for all clusters at once with segment reductions: per cluster the point with
+    the largest nearest-neighbour distance whose neighbour in pc1 is dynamic (amax over the cluster, then the lowest point
+    index attaining it), its displacement as the cluster's rigid flow, and the mean deviation of the estimated flow from it
+    over all points of clusters that have such a point."""
     from .chamfer3D import nnChamferDis
     cham = nnChamferDis()
-    pc0_label, pc1_label = res_dict["pc0_labels"], res_dict["pc1_labels"]
-    pc0, pc1, est_flow = res_dict["pc0"], res_dict["pc1"], res_dict["est_flow"]
-    pseudo_pc1from0 = pc0 + est_flow
-    unique_labels = torch.unique(pc0_label)
-    pc0_dynamic = pc0[pc0_label > 0]
-    pc1_dynamic = pc1[pc1_label > 0]
-    have_dynamic_cluster = (pc0_dynamic.shape[0] > 256) & (pc1_dynamic.shape[0] > 256)
-    est_dist0, est_dist1, _, _ = cham.disid_res(pseudo_pc1from0, pc1)
-    raw_dist0, raw_dist1, raw_idx0, _ = cham.disid_res(pc0, pc1)
-    chamfer_dis = torch.mean(est_dist0[est_dist0 <= TRUNCATED_DIST]) + torch.mean(est_dist1[est_dist1 <= TRUNCATED_DIST])
-    dynamic_chamfer_dis = torch.tensor(0.0, device=est_flow.device)
-    if have_dynamic_cluster:
-        dynamic_chamfer_dis = dynamic_chamfer_dis + cham(pseudo_pc1from0[pc0_label > 0], pc1_dynamic, truncate_dist=TRUNCATED_DIST)
-    static_cluster_loss = torch.tensor(0.0, device=est_flow.device)
-    moved_cluster_loss = torch.tensor(0.0, device=est_flow.device)
-    moved_cluster_norms = []
-    raw_idx0 = raw_idx0.long()
-    for label in unique_labels:
-        mask = pc0_label == label
-        if label == 0:
-            static_cluster_loss = static_cluster_loss + torch.linalg.vector_norm(est_flow[mask, :], dim=-1).mean()   # Eq. 6
-        elif label > 0 and have_dynamic_cluster:
-            cluster_id_flow = est_flow[mask, :]
-            cluster_nnd = raw_dist0[mask]
-            if cluster_nnd.shape[0] <= 0:
-                continue
-            sorted_idxs = torch.argsort(cluster_nnd, descending=True)                                                # Eq. 8
-            nearby_label = pc1_label[raw_idx0[mask][sorted_idxs]]
-            non_zero_valid_indices = torch.nonzero(nearby_label > 0)
-            if non_zero_valid_indices.shape[0] <= 0:
-                continue
-            max_idx = sorted_idxs[non_zero_valid_indices.squeeze(1)[0]]
-            max_flow = pc1[raw_idx0[mask][max_idx]] - pc0[mask][max_idx]                                             # Eq. 9
-            moved_cluster_norms.append(torch.linalg.vector_norm(cluster_id_flow - max_flow, dim=-1))                 # Eq. 10
-    if moved_cluster_norms:
-        moved_cluster_loss = torch.cat(moved_cluster_norms).mean()                                                   # Eq. 11
-    elif have_dynamic_cluster:
-        moved_cluster_loss = torch.mean(raw_dist0[raw_dist0 <= TRUNCATED_DIST]) + torch.mean(raw_dist1[raw_dist1 <= TRUNCATED_DIST])
-    return {"chamfer_dis": chamfer_dis, "dynamic_chamfer_dis": dynamic_chamfer_dis,
-            "static_flow_loss": static_cluster_loss, "cluster_based_pc0pc1": moved_cluster_loss}
+    l0, l1 = res_dict["pc0_labels"].long(), res_dict["pc1_labels"].long()
+    pc0, pc1, est = res_dict["pc0"], res_dict["pc1"], res_dict["est_flow"]
+    dev = est.device
+    zero = torch.zeros((), device=dev)
+    warped = pc0 + est
+    dyn0, dyn1 = l0 > 0, l1 > 0
+    have_dyn = int(dyn0.sum()) > 256 and int(dyn1.sum()) > 256          # lossfuncs.py:35-38 (one host read)
+    e0, e1, _, _ = cham.disid_res(warped, pc1)
+    r0, r1, nn0, _ = cham.disid_res(pc0, pc1)
+    out = {"chamfer_dis": e0[e0 <= TRUNCATED_DIST].mean() + e1[e1 <= TRUNCATED_DIST].mean()}
+    out["dynamic_chamfer_dis"] = zero + cham(warped[dyn0], pc1[dyn1], truncate_dist=TRUNCATED_DIST) if have_dyn else zero
+    # Eq. 6: static points should not move (a NaN mean when there is no static point, as in the reference)
+    static = ~dyn0 & (l0 == 0)
+    out["static_flow_loss"] = zero + torch.linalg.vector_norm(est[static], dim=-1).mean() if bool((l0 == 0).any()) else zero
+    moved = zero
+    if have_dyn:
+        nn0 = nn0.long()
+        labels, seg = torch.unique(l0, return_inverse=True)             # seg[p] = cluster slot of point p
+        K = labels.shape[0]
+        cand = dyn0 & (l1[nn0] > 0)                                     # the neighbour in pc1 is dynamic too (Eq. 8)
+        key = torch.where(cand, r0.detach(), torch.full_like(r0, -1.0))
+        best = torch.full((K,), -1.0, device=dev).scatter_reduce(0, seg, key, "amax", include_self=True)
+        hit = cand & (key == best[seg])
+        n = l0.shape[0]
+        pick = torch.full((K,), n, device=dev, dtype=torch.long).scatter_reduce(
+            0, seg, torch.where(hit, torch.arange(n, device=dev), torch.full((n,), n, device=dev)), "amin", include_self=True)
+        has = pick < n                                                  # clusters with a usable point
+        safe = pick.clamp(max=n - 1)
+        rigid = pc1[nn0[safe]] - pc0[safe]                              # Eq. 9: that point's displacement, per cluster
+        use = has[seg] & dyn0
+        if bool(use.any()):
+            moved = torch.linalg.vector_norm(est[use] - rigid[seg[use]].detach(), dim=-1).mean()      # Eq. 10-11
+        else:
+            moved = r0[r0 <= TRUNCATED_DIST].mean() + r1[r1 <= TRUNCATED_DIST].mean()                 # lossfuncs.py:90-91
+    out["cluster_based_pc0pc1"] = moved
+    return out
 
 
 def training_step_loss(batch, res, loss_fn: str = "deflowLoss") -> torch.Tensor:
