@@ -9,6 +9,7 @@ SUMMED over the batch, backward, gradient mean across ranks, clip-by-norm 5.0 (O
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -29,7 +30,9 @@ class TrainStep:
         self.opt = torch.optim.Adam(self.grads.params, lr=lr, fused=self.grads.flat.is_cuda)  # trainer.py:173-175
         self.global_step = 0
         self.epoch = 0
-        self.overlap = overlap_allreduce and dd.world_size() > 1 and self.grads.flat.is_cuda
+        # DFB_ALLREDUCE_OVERLAP=0: one collective after the backward (A/B switch)
+        self.overlap = (overlap_allreduce and dd.world_size() > 1 and self.grads.flat.is_cuda
+                        and os.environ.get("DFB_ALLREDUCE_OVERLAP", "1") != "0")
         if self.overlap:
             # the backward produces the decoder and UNet-decoder gradients first and the shared encoder's last: the first
             # slice of the flat buffer is all-reduced on a side stream while the encoder backward still runs
