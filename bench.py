@@ -546,7 +546,7 @@ def run_native(args):
                 "sync_bn_exchange": ({"collectives_per_step": step.stat_sync.calls / max(step.global_step, 1),
                                       "bytes_per_step": step.stat_sync.bytes / max(step.global_step, 1)}
                                      if step.stat_sync is not None else None),
-                "grad_allreduce": {"bytes": step.grads.nbytes, "op": "AVG", "early_slice_params": (
+                "grad_allreduce": {"bytes": step.grads.nbytes, "op": "AVG", "overlapped_early_slice_params": (
                     len(step.grads.params) - step.grads.early_from if step.grads.early_from is not None else 0)},
                 "timed_seconds": sum(regions) * args.steps * 1e-3}
     if world > 1:

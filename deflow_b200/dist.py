@@ -2,8 +2,8 @@
 
 The reference trains with Lightning DDP (OSF/train.py:125): bucketed NCCL all-reduce of 6 891 939 fp32 gradients
 (27.6 MB) overlapped with backward.  On an NVSwitch domain that message takes ~0.1 ms against a >40 ms step, so the
-path shards by frame pair with at most two collectives per step: the head + UNet-decoder slice of the flat gradient
-buffer is averaged while the encoder backward still runs, the rest after it (DESIGN.md "multi-GPU").
+path shards by frame pair with one collective per step (ReduceOp.AVG on the flat buffer); an overlapped two-slice variant is
+opt-in and measured slower on NVSwitch (DESIGN.md "multi-GPU").
 Works with any torch.distributed backend (nccl on the B200 box, gloo in the CPU tests)."""
 from __future__ import annotations
 

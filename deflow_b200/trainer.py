@@ -20,7 +20,7 @@ from .lossfuncs import training_step_loss
 
 class TrainStep:
     def __init__(self, model: torch.nn.Module, lr: float = 2e-4, loss_fn: str = "deflowLoss",
-                 gradient_clip_val: float = 5.0, sync_bn: bool = False, overlap_allreduce: bool = True):
+                 gradient_clip_val: float = 5.0, sync_bn: bool = False, overlap_allreduce: bool = False):
         self.model = model
         self.loss_fn = loss_fn
         self.lr = lr
@@ -30,12 +30,15 @@ class TrainStep:
         self.opt = torch.optim.Adam(self.grads.params, lr=lr, fused=self.grads.flat.is_cuda)  # trainer.py:173-175
         self.global_step = 0
         self.epoch = 0
-        # DFB_ALLREDUCE_OVERLAP=0: one collective after the backward (A/B switch)
-        self.overlap = (overlap_allreduce and dd.world_size() > 1 and self.grads.flat.is_cuda
-                        and os.environ.get("DFB_ALLREDUCE_OVERLAP", "1") != "0")
+        # Gradient mean: ONE ReduceOp.AVG collective on the flat buffer after the backward (default).  Opt-in
+        # (overlap_allreduce=True or DFB_ALLREDUCE_OVERLAP=1): the head + UNet-decoder slice is all-reduced from a hook while
+        # the encoder backward still runs.  Measured on 2 x B200 (profiles/r02_allreduce_overlap_ab.txt): 32.02-32.10 ms
+        # with the overlap against 31.96-31.98 ms without (N = 1 on the same box: 31.83 ms) -- the 27.6 MB all-reduce costs
+        # ~0.13 ms on NVSwitch, and the NCCL kernel that overlaps the backward takes SMs away from persistent kernels
+        # that are sized one CTA per SM, so overlapping loses slightly more than it hides.
+        want = overlap_allreduce or os.environ.get("DFB_ALLREDUCE_OVERLAP", "0") == "1"
+        self.overlap = want and dd.world_size() > 1 and self.grads.flat.is_cuda
         if self.overlap:
-            # the backward produces the decoder and UNet-decoder gradients first and the shared encoder's last: the first
-            # slice of the flat buffer is all-reduced on a side stream while the encoder backward still runs
             self.grads.plan_early_slice(model)
         self.stat_sync = dd.enable_sync_bn(model) if self.sync_bn else None
 
