@@ -162,6 +162,7 @@ def _declare(lib):
         "dfb_chamfer_forward": [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp],
         "dfb_chamfer_backward": [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp],
         "dfb_hard_voxelize_assign": [vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp],
+        "dfb_conv3x3_dgrad_colsum": [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp],
         "dfb_collate_pad": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "dfb_gru_fused_forward": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
         "dfb_gru_fused_backward": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
@@ -188,7 +189,8 @@ EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size",
            "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",
            "dfb_gru_fused_forward", "dfb_gru_fused_backward", "dfb_collate_workspace", "dfb_collate_pad",
            "dfb_eval_accumulate", "dfb_bn_gelu_backward_phase",
-           "dfb_chamfer_forward", "dfb_chamfer_backward", "dfb_hard_voxelize_workspace", "dfb_hard_voxelize_assign"]
+           "dfb_chamfer_forward", "dfb_chamfer_backward", "dfb_hard_voxelize_workspace", "dfb_hard_voxelize_assign",
+           "dfb_conv3x3_dgrad_colsum"]
 
 
 def lib():

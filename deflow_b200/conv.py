@@ -199,6 +199,23 @@ def conv2d_dgrad_two(gy: torch.Tensor, w_dgrad, H, W, c0, c1, cin_total, ksize, 
     return gx0, gx1
 
 
+_BORDER_COLSUM = __import__("os").environ.get("DFB_BORDER_COLSUM", "1") != "0"   # A/B switch
+
+
+def conv3x3_dgrad_colsum(gy: torch.Tensor, gy_total: torch.Tensor, w: torch.Tensor, cin_off: int, cin: int) -> torch.Tensor:
+    """sum over pixels of the 3x3 / stride 1 data gradient for the input channels [cin_off, cin_off + cin), from gy's border
+    rows / columns, its total per-channel sum and the fp32 weights -- the data gradient itself is not read."""
+    n, H, W, cout = gy.shape
+    wf = w.detach().float().contiguous()
+    tot = gy_total.detach().float().contiguous()
+    ws = torch.empty(8 * cout, dtype=torch.float32, device=gy.device)
+    out = torch.empty(cin, dtype=torch.float32, device=gy.device)
+    check(_lib.lib().dfb_conv3x3_dgrad_colsum(gy.data_ptr(), int(gy.dtype == torch.float32), n, H, W, cout, tot.data_ptr(),
+                                              wf.data_ptr(), wf.shape[1], cin_off, cin, ws.data_ptr(), out.data_ptr(),
+                                              _stream(gy)), "conv3x3_dgrad_colsum")
+    return out
+
+
 def bias_grad(gy: torch.Tensor) -> torch.Tensor:
     """sum over pixels of gy: taken from the producing data-gradient kernel's epilogue when available."""
     cs = getattr(gy, "_dfb_colsum", None)
@@ -423,6 +440,9 @@ class _Conv(torch.autograd.Function):
         # HBM-bound launches and the column sums doubled it (B200: 0.077 -> 0.140 ms for dec2.u1), while for a 1x1 stride-1
         # convolution they follow exactly from sum_p gx[p, ci] = sum_co W[co, ci] * sum_p gy[p, co] = (W^T gb)[ci].
         mv = (w.detach().reshape(w.shape[0], ct).float().t() @ gb.float()) if k == 1 else None
+        # 3x3 with 64 input channels per source (the row-pair kernel, whose epilogue is its limit: +50 % with the sums):
+        # from the border rows / columns of gy and W instead (dfb_conv3x3_dgrad_colsum); wider layers keep the epilogue sums
+        borders = k == 3 and _BORDER_COLSUM and all(x.shape[3] == 64 for x in xs)
         if (len(xs) == 2 and k == 1 and all(ctx.need) and gy.dtype == torch.bfloat16
                 and xs[0].shape[3] % 32 == 0 and xs[1].shape[3] % 32 == 0 and ct in (32, 64, 128, 256)):
             c0 = xs[0].shape[3]
@@ -432,9 +452,11 @@ class _Conv(torch.autograd.Function):
         for i, x in enumerate(xs):
             c = x.shape[3]
             if ctx.need[i]:
-                gxs[i] = conv2d_dgrad(gy, wd, x.shape[1], x.shape[2], c, ct, off, k, 1, colsum=(k != 1))
+                gxs[i] = conv2d_dgrad(gy, wd, x.shape[1], x.shape[2], c, ct, off, k, 1, colsum=(k != 1 and not borders))
                 if k == 1:
                     gxs[i]._dfb_colsum = (mv[off:off + c], gxs[i]._version)
+                elif borders:
+                    gxs[i]._dfb_colsum = (conv3x3_dgrad_colsum(gy, gb, w, off, c), gxs[i]._version)
             off += c
         return gw, gb, gxs[0], gxs[1]
 

@@ -804,3 +804,127 @@ extern "C" int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* 
   add_launches(1);
   return check_launch("dfb_upsample2x");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Per-channel sums of a 3x3 / stride 1 / pad 1 data gradient WITHOUT touching the data gradient: the bias gradient of the
+// convolution that produced this layer's input (UpsampleSkip, OpenSceneFlow/src/models/basic/unet.py:25-37: conv -> conv with
+// bias and nothing in between).  gx[p] = sum_taps W_tap^T gy[p - off_tap] with gy zero outside the image, hence
+//   sum_p gx[p, ci] = sum_{ky,kx} sum_co W[co, ci, ky, kx] * S_{ky,kx}[co],
+//   S_{ky,kx} = T - [ky == 0] top row - [ky == 2] bottom row - [kx == 0] left column - [kx == 2] right column + corner,
+// where T = sum of gy over all pixels (this layer's own bias gradient, already known) and the border terms are sums of gy
+// over one image row / column / corner pixel (summed over the batch).  Taking these sums in the epilogue of the 64-channel
+// row-pair data-gradient kernel cost +50 % of that launch (B200: 0.235 -> 0.355 ms at 512^2); the border sums read
+// 2(H + W) pixels per image.
+namespace dfb {
+
+// out [8][C] (+=): top row, bottom row, left column, right column, corners TL, TR, BL, BR
+template <bool F32>
+__global__ void __launch_bounds__(256) k_border_sums(const void* __restrict__ gy, int n, int H, int W, int C, float* __restrict__ out) {
+  extern __shared__ float s_acc[];    // [8][C]
+  for (int i = threadIdx.x; i < 8 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int per_img = 2 * W + 2 * H;
+  const long long total = (long long)n * per_img;
+  const int lanes_per_pix = C;                       // thread = (pixel slot, channel)
+  const int pix_per_iter = blockDim.x / lanes_per_pix > 0 ? blockDim.x / lanes_per_pix : 1;
+  const int c = threadIdx.x % lanes_per_pix, slot = threadIdx.x / lanes_per_pix;
+  if (slot < pix_per_iter) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long b = (long long)blockIdx.x * pix_per_iter + slot; b < total; b += (long long)gridDim.x * pix_per_iter) {
+      const int img = (int)(b / per_img);
+      int r = (int)(b % per_img);
+      int kind, y, x;
+      if (r < W) { kind = 0; y = 0; x = r; }
+      else if (r < 2 * W) { kind = 1; y = H - 1; x = r - W; }
+      else if (r < 2 * W + H) { kind = 2; y = r - 2 * W; x = 0; }
+      else { kind = 3; y = r - 2 * W - H; x = W - 1; }
+      const size_t off = (((size_t)img * H + y) * W + x) * C + c;
+      const float v = F32 ? reinterpret_cast<const float*>(gy)[off] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gy)[off]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += (kind == k) ? v : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (acc[k] != 0.f) atomicAdd(&s_acc[k * C + c], acc[k]);
+  }
+  // corners: block 0, thread = channel (looped), summed over the batch
+  if (blockIdx.x == 0) {
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int img = 0; img < n; ++img) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int y = (k & 2) ? H - 1 : 0, x = (k & 1) ? W - 1 : 0;
+          const size_t off = (((size_t)img * H + y) * W + x) * C + ch;
+          t[k] += F32 ? reinterpret_cast<const float*>(gy)[off] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gy)[off]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_acc[(4 + k) * C + ch] += t[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * C; i += blockDim.x) {
+    if (s_acc[i] != 0.f) atomicAdd(out + i, s_acc[i]);
+  }
+}
+
+// colsum[ci] = sum_taps sum_co W[co, cin_off + ci, ky, kx] * S_tap[co]; one block per ci
+__global__ void __launch_bounds__(128) k_colsum_from_borders(const float* __restrict__ border, const float* __restrict__ total,
+                                                             const float* __restrict__ w, int cout, int cin_total, int cin_off,
+                                                             float* __restrict__ colsum) {
+  const int ci = blockIdx.x;
+  double acc = 0.0;
+  for (int co = threadIdx.x; co < cout; co += blockDim.x) {
+    const float T = total[co];
+    const float top = border[co], bot = border[cout + co], lef = border[2 * cout + co], rig = border[3 * cout + co];
+    const float tl = border[4 * cout + co], tr = border[5 * cout + co], bl = border[6 * cout + co], br = border[7 * cout + co];
+    const float* wp = w + ((size_t)co * cin_total + cin_off + ci) * 9;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        double s = T;
+        if (ky == 0) s -= top;
+        if (ky == 2) s -= bot;
+        if (kx == 0) s -= lef;
+        if (kx == 2) s -= rig;
+        if (ky == 0 && kx == 0) s += tl;
+        if (ky == 0 && kx == 2) s += tr;
+        if (ky == 2 && kx == 0) s += bl;
+        if (ky == 2 && kx == 2) s += br;
+        acc += (double)wp[ky * 3 + kx] * s;
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ double red[4];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) colsum[ci] = (float)(red[0] + red[1] + red[2] + red[3]);
+}
+
+}  // namespace dfb
+
+extern "C" int dfb_conv3x3_dgrad_colsum(const void* gy, int f32, int n, int H, int W, int cout, const float* gy_total,
+                                        const float* w, int cin_total, int cin_off, int cin, float* border_ws,
+                                        float* colsum, void* stream_) {
+  using namespace dfb;
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n <= 0 || H <= 0 || W <= 0 || cout <= 0 || cout > 1024 || cin <= 0 || cin_off < 0 || cin_off + cin > cin_total) {
+    set_error("dfb_conv3x3_dgrad_colsum: bad sizes");
+    return DFB_ERR_ARG;
+  }
+  cudaMemsetAsync(border_ws, 0, sizeof(float) * 8 * (size_t)cout, st);
+  const long long border_px = (long long)n * (2 * W + 2 * H);
+  const int ppi = 256 / cout > 0 ? 256 / cout : 1;
+  long long blocks = (border_px + ppi * 8 - 1) / (ppi * 8);
+  if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+  if (blocks < 1) blocks = 1;
+  const int threads = cout > 256 ? 1024 : 256;
+  const size_t smem = sizeof(float) * 8 * (size_t)cout;
+  if (f32) k_border_sums<true><<<(int)blocks, threads, smem, st>>>(gy, n, H, W, cout, border_ws);
+  else k_border_sums<false><<<(int)blocks, threads, smem, st>>>(gy, n, H, W, cout, border_ws);
+  k_colsum_from_borders<<<cin, 128, 0, st>>>(border_ws, gy_total, w, cout, cin_total, cin_off, colsum);
+  add_launches(2);
+  return check_launch("dfb_conv3x3_dgrad_colsum");
+}

@@ -296,6 +296,12 @@ int dfb_bn_gelu_backward(const void* x, const void* gy, const float* bn, int C, 
 int dfb_bn_gelu_backward_phase(const void* x, const void* gy, const float* bn, int C, long long n_pix, int training,
                                double* red, void* gx, float* g_gamma, float* g_beta, float* g_bias, int f32, int phase,
                                double count_total, void* stream);
+/* Per-channel sums of the data gradient of a 3x3 / stride 1 / pad 1 convolution WITHOUT reading that gradient -- the bias
+ * gradient of the producer convolution (REF/src/models/basic/unet.py:25-37): from gy [n,H,W,cout] only its border rows /
+ * columns are read, gy_total f32[cout] = sum of gy over all pixels, w f32 torch layout [cout,cin_total,3,3]; colsum f32[cin]
+ * for the input channels [cin_off, cin_off + cin).  border_ws: f32[8*cout] scratch. */
+int dfb_conv3x3_dgrad_colsum(const void* gy, int f32, int n, int H, int W, int cout, const float* gy_total, const float* w,
+                             int cin_total, int cin_off, int cin, float* border_ws, float* colsum, void* stream);
 int dfb_channel_sum(const void* g, int C, long long n_pix, float* out, double* stats2, int f32, void* stream);
 int dfb_upsample2x(const void* in, int n, int h, int w, int C, void* out, int backward, int f32, void* stream);
 

@@ -89,6 +89,29 @@ def test_conv_dgrad_two_outputs_equals_two_launches(c0, c1, cout, H, W):
     assert _rel(conv.bias_grad(b0), conv.channel_sum(b0)) == 0.0
 
 
+@pytest.mark.parametrize("n,H,W,cout,cins,f32", [(2, 32, 32, 64, [64], False), (3, 20, 12, 64, [64, 64], False), (1, 1, 7, 128, [64], True),
+                                                 (2, 9, 1, 64, [64], False), (1, 64, 48, 256, [128, 128], True)])
+def test_conv3x3_dgrad_colsum_from_border_sums(n, H, W, cout, cins, f32):
+    """Per-channel sums of a 3x3 / stride 1 / pad 1 data gradient from gy's border rows / columns, its total and the weights
+    (dfb_conv3x3_dgrad_colsum) against the sums of the actual fp32 data gradient."""
+    torch.manual_seed(H * 7 + W)
+    ct = sum(cins)
+    w = (torch.randn(cout, ct, 3, 3, device=DEV) / (ct * 9) ** 0.5)
+    gy = torch.randn(n, H, W, cout, device=DEV)
+    if not f32:
+        gy = gy.to(torch.bfloat16)
+    x = torch.zeros(n, ct, H, W, device=DEV, requires_grad=True)
+    F.conv2d(x, w, None, 1, 1).backward(gy.float().permute(0, 3, 1, 2))
+    want = x.grad.double().sum((0, 2, 3))
+    tot = gy.float().sum((0, 1, 2))
+    off = 0
+    for c in cins:
+        got = conv.conv3x3_dgrad_colsum(gy.contiguous(), tot, w, off, c)
+        ref = want[off:off + c]
+        assert float((got.double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), (off, c)
+        off += c
+
+
 @pytest.mark.parametrize("n,H,W,cins", [(2, 32, 32, [64]), (1, 20, 12, [64]), (1, 96, 16, [64, 64])])
 @pytest.mark.parametrize("variant", ["1", "0"])
 def test_wgrad_cross_shift_variant(monkeypatch, n, H, W, cins, variant):

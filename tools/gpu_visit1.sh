@@ -7,7 +7,6 @@ T="timeout -s KILL"
 $T 1500 python -m pytest tests -m gpu -q -rf --durations=8 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 tail -45 gpurun_out/pytest_gpu.log
 $T 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
-bash tools/gpu_next.sh
 $T 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
 python - <<'PY'
 import json
