@@ -136,6 +136,8 @@ def _declare(lib):
         "dfb_clear_rows": [vp, i32, vp, vp, i32, i64, vp],
         "dfb_decoder_gather": [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, i32, vp],
         "dfb_decoder_gather_backward": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
+        "dfb_decoder_gather_backward_split": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "dfb_add_cat2": [vp, vp, vp, vp, i64, i32, vp, vp],
         "dfb_flow_loss": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
         "dfb_conv_pack_weights": [vp, i32, i32, i32, i32, vp, vp, vp],
         "dfb_conv_pack_weights_multi": [vp, i32, i64, i32, vp],
@@ -190,7 +192,7 @@ EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size",
            "dfb_gru_fused_forward", "dfb_gru_fused_backward", "dfb_collate_workspace", "dfb_collate_pad",
            "dfb_eval_accumulate", "dfb_bn_gelu_backward_phase",
            "dfb_chamfer_forward", "dfb_chamfer_backward", "dfb_hard_voxelize_workspace", "dfb_hard_voxelize_assign",
-           "dfb_conv3x3_dgrad_colsum"]
+           "dfb_conv3x3_dgrad_colsum", "dfb_decoder_gather_backward_split", "dfb_add_cat2"]
 
 
 def lib():

@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
                                                             const int* __restrict__ pil_start,
                                                             const int* __restrict__ sorted_pt,
                                                             void* __restrict__ grad_img, void* __restrict__ grad_unet,
-                                                            int pil_cap) {
+                                                            int pil_cap, int img_accumulate) {
+  // grad_img == NULL: only the UNet rows; grad_unet == NULL: only the image rows; img_accumulate: the image rows are ADDED to
+  // an existing dense gradient (every (frame, pixel) row belongs to exactly one pillar: plain read-modify-write)
   const int M0 = min(counts[3 * F + 1 + B], pil_cap);  // pillars of the pc0 frames
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -83,7 +85,8 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
       float4 v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        v[k] = pt[k] >= 0 ? load4<IN_BF>(grad_h0, (size_t)pt[k] * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[k] = (pt[k] >= 0 && (lane < 16 ? grad_img != nullptr : grad_unet != nullptr))
+                   ? load4<IN_BF>(grad_h0, (size_t)pt[k] * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 8; k += 2) {
         a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
@@ -92,9 +95,18 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
     }
     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     const int pix = pil_pix[q];
-    if (lane < 8) store4<OUT_BF>(grad_img, (size_t)pix * 32 + lane * 4, a);
-    else if (lane < 16) store4<OUT_BF>(grad_img, ((size_t)pix + (size_t)B * HW) * 32 + (lane - 8) * 4, a);
-    else store4<OUT_BF>(grad_unet, (size_t)pix * 64 + (lane - 16) * 4, a);
+    if (lane < 16) {
+      if (grad_img) {
+        const size_t e = lane < 8 ? (size_t)pix * 32 + lane * 4 : ((size_t)pix + (size_t)B * HW) * 32 + (lane - 8) * 4;
+        if (img_accumulate) {
+          const float4 o = load4<OUT_BF>(grad_img, e);
+          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+        }
+        store4<OUT_BF>(grad_img, e, a);
+      }
+    } else if (grad_unet) {
+      store4<OUT_BF>(grad_unet, (size_t)pix * 64 + (lane - 16) * 4, a);
+    }
   }
 }
 
@@ -120,26 +132,89 @@ extern "C" int dfb_decoder_gather(const void* img, const void* unet, int in_bf16
   return check_launch("dfb_decoder_gather");
 }
 
-extern "C" int dfb_decoder_gather_backward(const void* grad_h0, int grad_bf16, int B, int H, int W,
-                                           const int* counts, int F, const int* pil_pix, const int* pil_start,
-                                           const int* sorted_pt, void* grad_img, void* grad_unet, int out_bf16,
-                                           int pil_cap, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
+static int gather_backward_impl(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
+                                const int* pil_pix, const int* pil_start, const int* sorted_pt, void* grad_img,
+                                void* grad_unet, int out_bf16, int pil_cap, int img_accumulate, cudaStream_t st) {
   if (B <= 0 || F < B || H <= 0 || W <= 0) { set_error("dfb_decoder_gather_backward: bad sizes"); return DFB_ERR_ARG; }
   const size_t HW = (size_t)H * W, es = out_bf16 ? 2 : 4;
   // dense gradients: zero everywhere except the pc0 pillars (index_put_ accumulate into zeros)
-  cudaMemsetAsync(grad_img, 0, (size_t)2 * B * HW * 32 * es, st);
-  cudaMemsetAsync(grad_unet, 0, (size_t)B * HW * 64 * es, st);
+  if (grad_img && !img_accumulate) cudaMemsetAsync(grad_img, 0, (size_t)2 * B * HW * 32 * es, st);
+  if (grad_unet) cudaMemsetAsync(grad_unet, 0, (size_t)B * HW * 64 * es, st);
   if (pil_cap > 0) {
     long long blocks = ((long long)pil_cap * 32 + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     const int g = (int)blocks;
-    if (grad_bf16 && out_bf16) k_decoder_gather_bwd<true, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap);
-    else if (grad_bf16) k_decoder_gather_bwd<true, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap);
-    else if (out_bf16) k_decoder_gather_bwd<false, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap);
-    else k_decoder_gather_bwd<false, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap);
+    if (grad_bf16 && out_bf16) k_decoder_gather_bwd<true, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_accumulate);
+    else if (grad_bf16) k_decoder_gather_bwd<true, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_accumulate);
+    else if (out_bf16) k_decoder_gather_bwd<false, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_accumulate);
+    else k_decoder_gather_bwd<false, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_accumulate);
     add_launches(1);
   }
   return check_launch("dfb_decoder_gather_backward");
+}
+
+extern "C" int dfb_decoder_gather_backward(const void* grad_h0, int grad_bf16, int B, int H, int W,
+                                           const int* counts, int F, const int* pil_pix, const int* pil_start,
+                                           const int* sorted_pt, void* grad_img, void* grad_unet, int out_bf16,
+                                           int pil_cap, void* stream_) {
+  if (!grad_img || !grad_unet) { set_error("dfb_decoder_gather_backward: both outputs are required (see dfb_decoder_gather_backward_split)"); return DFB_ERR_ARG; }
+  return gather_backward_impl(grad_h0, grad_bf16, B, H, W, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, out_bf16,
+                              pil_cap, 0, (cudaStream_t)stream_);
+}
+
+extern "C" int dfb_decoder_gather_backward_split(const void* grad_h0, int grad_bf16, int B, int H, int W,
+                                                 const int* counts, int F, const int* pil_pix, const int* pil_start,
+                                                 const int* sorted_pt, void* grad_img, void* grad_unet, int out_bf16,
+                                                 int pil_cap, int img_accumulate, void* stream_) {
+  if (!grad_img && !grad_unet) { set_error("dfb_decoder_gather_backward_split: no output"); return DFB_ERR_ARG; }
+  return gather_backward_impl(grad_h0, grad_bf16, B, H, W, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, out_bf16,
+                              pil_cap, img_accumulate, (cudaStream_t)stream_);
+}
+
+// out[0 : n) = a0 + b0, out[n : 2n) = a1 + b1 (16-byte vectors): the gradient of the pseudo-image from its two consumers per
+// frame half (first encoder convolution, last skip convolution), concatenated -- one pass instead of two additions and a
+// concatenation.  b0 / b1 may be NULL (a consumer without gradient).
+template <bool BF>
+__global__ void __launch_bounds__(256) k_add_cat2(const uint4* __restrict__ a0, const uint4* __restrict__ b0,
+                                                  const uint4* __restrict__ a1, const uint4* __restrict__ b1, long long n16,
+                                                  uint4* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n16; i += (long long)gridDim.x * blockDim.x) {
+    const bool hi = i >= n16;
+    const long long j = hi ? i - n16 : i;
+    const uint4* a = hi ? a1 : a0;
+    const uint4* b = hi ? b1 : b0;
+    uint4 x = a[j];
+    if (b) {
+      const uint4 y = b[j];
+      if (BF) {
+        __nv_bfloat162* xp = reinterpret_cast<__nv_bfloat162*>(&x);
+        const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 p = __bfloat1622float2(xp[k]), q = __bfloat1622float2(yp[k]);
+          xp[k] = __floats2bfloat162_rn(p.x + q.x, p.y + q.y);
+        }
+      } else {
+        float* xp = reinterpret_cast<float*>(&x);
+        const float* yp = reinterpret_cast<const float*>(&y);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xp[k] += yp[k];
+      }
+    }
+    out[i] = x;
+  }
+}
+
+extern "C" int dfb_add_cat2(const void* a0, const void* b0, const void* a1, const void* b1, long long bytes_per_half, int bf16,
+                            void* out, void* stream_) {
+  if (!a0 || !a1 || !out || bytes_per_half <= 0 || bytes_per_half % 16) { set_error("dfb_add_cat2: bad arguments"); return DFB_ERR_ARG; }
+  if ((b0 == nullptr) != (b1 == nullptr)) { set_error("dfb_add_cat2: both or neither of the second addends"); return DFB_ERR_ARG; }
+  const long long n16 = bytes_per_half / 16;
+  long long blocks = (2 * n16 + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  if (bf16) k_add_cat2<true><<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const uint4*)a0, (const uint4*)b0, (const uint4*)a1, (const uint4*)b1, n16, (uint4*)out);
+  else k_add_cat2<false><<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const uint4*)a0, (const uint4*)b0, (const uint4*)a1, (const uint4*)b1, n16, (uint4*)out);
+  add_launches(1);
+  return check_launch("dfb_add_cat2");
 }

@@ -34,19 +34,19 @@ class ConvGRU(nn.Module):
 
 
 class _GatherDecoder(nn.Module):
-    def _forward_tensor_core(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets, iters):
+    def _forward_tensor_core(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets, iters, sink=None):
         """bf16 perf mode: gather -> (GRU iterations) -> MLP head on the tensor cores (deflow_b200/gru.py)."""
         from . import gru
         n_pad = max((n_rows + 7) // 8 * 8, 8)
         if self.compute_dtype == torch.float32:
             # parity mode: fp32 gate tensors, split-precision ("bf16x3") tensor-core GEMMs
-            h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.float32, n_pad)
+            h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.float32, n_pad, sink)
             return gru.decode(h0, offsets, n_rows, self, iters, parity=True)
         if iters > 0 and os.environ.get("DFB_GRU", "fused") == "fused":
             # persistent fused kernels (csrc/gru_fused.cu); DFB_GRU=unfused selects the GEMM + elementwise launches
-            h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.bfloat16, n_pad)
+            h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.bfloat16, n_pad, sink)
             return gru.decode_fused(h0, offsets, n_rows, self)
-        h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.float32, n_pad)
+        h0 = ops.decoder_gather(img_nhwc, unet_nhwc, idx, B, n_rows, torch.float32, n_pad, sink)
         return gru.decode(h0, offsets, n_rows, self, iters)
 
     def forward(self, before_pseudoimages, after_pseudoimages, voxelizer_infos) -> List[torch.Tensor]:
@@ -74,10 +74,10 @@ class ConvGRUDecoder(_GatherDecoder):
         self.num_iters = num_iters
         self.compute_dtype = torch.float32
 
-    def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
+    def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None, sink=None):
         """All pc0 points of the batch at once -> flow [n_rows, 3]."""
         offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
-        return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, self.num_iters)
+        return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, self.num_iters, sink)
 
 
 class LinearDecoder(_GatherDecoder):
@@ -89,9 +89,9 @@ class LinearDecoder(_GatherDecoder):
         self.decoder = nn.Sequential(nn.Linear(pseudoimage_channels * 4, 32), nn.GELU(), nn.Linear(32, 3))
         self.compute_dtype = torch.float32
 
-    def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None):
+    def forward_flat(self, img_nhwc, unet_nhwc, idx, B, n_rows, offsets=None, sink=None):
         offsets = idx.pt_offs[:n_rows] if offsets is None else offsets
-        return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, 0)
+        return self._forward_tensor_core(img_nhwc, unet_nhwc, idx, B, n_rows, offsets, 0, sink)
 
 
 def _index_from_infos(infos, H, W) -> ops.PillarIndex:

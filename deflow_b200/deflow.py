@@ -4,6 +4,7 @@ OSF/src/models/fastflow3d.py:42-103): same constructor, same ``forward(batch) ->
 """
 from __future__ import annotations
 
+import os
 import time
 from typing import Dict
 
@@ -53,26 +54,44 @@ def weights_init(m):
 
 
 class _SplitFrames(torch.autograd.Function):
-    """image [2B,H,W,C] -> (image[:B], image[B:]) with ONE concatenation as its backward.  Plain slicing makes autograd
-    zero-fill two full-size gradient tensors, copy a half into each and add them (about 3 GB of HBM traffic per step at
-    512^2 x 32 frames); here the two half gradients are written once, side by side."""
+    """image [2B,H,W,C] -> (image[:B], image[B:]) twice: one pair for the encoder, one for the last skip convolution -- the
+    two consumers of each frame half -- so that the backward receives their gradients SEPARATELY and builds the gradient of
+    the whole image in one pass: out = cat(g_enc0 + g_skip0, g_enc1 + g_skip1) (ops.add_cat2), then the rows of the decoder
+    gather's gradient that belong to the image are added in place (``sink``, see ops._DecoderGather.backward).  Plain
+    slicing + autograd made this two dense additions, a zero-filled dense gather gradient, a concatenation and a third dense
+    addition (about 5 GB of HBM traffic per step at 512^2 x 32 frames)."""
 
     @staticmethod
-    def forward(ctx, image, B):
+    def forward(ctx, image, B, sink):
         ctx.meta = (B, image.shape, image.dtype, image.device)
+        ctx.sink = sink
         base = image.detach()            # same storage, no autograd view relation to the input
-        return base[:B], base[B:]
+        return base[:B], base[B:], base[:B], base[B:]
 
     @staticmethod
-    def backward(ctx, g0, g1):
+    def backward(ctx, ga0, ga1, gb0, gb1):
         B, shape, dtype, device = ctx.meta
-        if g0 is None and g1 is None:
-            return None, None
-        if g0 is None:
-            g0 = torch.zeros((B,) + tuple(shape[1:]), dtype=dtype, device=device)
-        if g1 is None:
-            g1 = torch.zeros((shape[0] - B,) + tuple(shape[1:]), dtype=dtype, device=device)
-        return torch.cat([g0, g1], 0), None
+        half = (B,) + tuple(shape[1:])
+        pend = ctx.sink.pop("gather", None) if ctx.sink is not None else None
+        if ga0 is None and ga1 is None and gb0 is None and gb1 is None and pend is None:
+            return None, None, None
+        z = lambda: torch.zeros(half, dtype=dtype, device=device)  # noqa: E731
+        if ga0 is None and gb0 is not None:
+            ga0, gb0 = gb0, None
+        if ga1 is None and gb1 is not None:
+            ga1, gb1 = gb1, None
+        ga0 = z() if ga0 is None else ga0.contiguous()
+        ga1 = z() if ga1 is None else ga1.contiguous()
+        if (gb0 is None) != (gb1 is None):
+            gb0 = z() if gb0 is None else gb0
+            gb1 = z() if gb1 is None else gb1
+        if gb0 is not None:
+            gb0, gb1 = gb0.contiguous(), gb1.contiguous()
+        out = ops.add_cat2(ga0, gb0, ga1, gb1)
+        if pend is not None:
+            grad_h0, idx, Bp, H, W = pend
+            ops.gather_backward_split(grad_h0, idx, Bp, H, W, out, None, out.dtype, True)
+        return out, None, None
 
 
 class DeFlow(nn.Module):
@@ -148,13 +167,17 @@ class DeFlow(nn.Module):
         self.timer[1].stop()
 
         self.timer[2].start("Encoder")
-        img0, img1 = _SplitFrames.apply(image, B)
-        unet_out = self.backbone.forward_nhwc(img0, img1)
+        # the pseudo-image has three consumers (encoder, last skip convolution, decoder gather): their gradients meet in
+        # _SplitFrames.backward (DFB_IMG_GRAD_FUSE=0: the gather returns its own dense gradient and autograd adds it)
+        fuse = torch.is_grad_enabled() and image.requires_grad and os.environ.get("DFB_IMG_GRAD_FUSE", "1") != "0"
+        sink = {} if fuse else None
+        img0, img1, img0s, img1s = _SplitFrames.apply(image, B, sink)
+        unet_out = self.backbone.forward_nhwc(img0, img1, skip_imgs=(img0s, img1s))
         self.timer[2].stop()
 
         self.timer[3].start("Decoder")
         n0 = idx.pt_off(B)  # the one host sync of the forward
-        flow_flat = self.head.forward_flat(image, unet_out, idx, B, n0)
+        flow_flat = self.head.forward_flat(image, unet_out, idx, B, n0, sink=sink)
         self.timer[3].stop()
 
         infos = [idx.frame_info(f) for f in range(2 * B)]

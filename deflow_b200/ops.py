@@ -298,8 +298,9 @@ class _DecoderGather(torch.autograd.Function):
     """h0[p] = [img0[y,x], img1[y,x], unet[y,x]] for every pc0 point (OSF/src/models/basic/decoder.py:215-225)."""
 
     @staticmethod
-    def forward(ctx, img, unet, idx: PillarIndex, B, n_rows, out_dtype, n_alloc):
+    def forward(ctx, img, unet, idx: PillarIndex, B, n_rows, out_dtype, n_alloc, sink=None):
         _need_cuda(img, "decoder_gather")
+        ctx.sink = sink
         assert img.is_contiguous() and unet.is_contiguous() and img.dtype == unet.dtype
         F, H, W, c = img.shape
         assert c == 32 and F == 2 * B and tuple(unet.shape) == (B, H, W, 64)
@@ -321,18 +322,44 @@ class _DecoderGather(torch.autograd.Function):
         B, H, W, dt = ctx.meta
         grad_h0 = grad_h0.contiguous()
         assert grad_h0.dtype in (torch.float32, torch.bfloat16)
-        g_img = torch.empty((2 * B, H, W, 32), dtype=dt, device=grad_h0.device)
         g_unet = torch.empty((B, H, W, 64), dtype=dt, device=grad_h0.device)
+        if ctx.sink is not None:
+            # Deferred image part (deflow._SplitFrames.backward): only the UNet gradient is produced now; the rows that belong
+            # to the pseudo-image are added into its gradient once the other consumers of the image have written theirs --
+            # no dense zero-filled [2B,H,W,32] tensor, no dense addition.
+            gather_backward_split(grad_h0, idx, B, H, W, None, g_unet, dt, False)
+            ctx.sink["gather"] = (grad_h0, idx, B, H, W)
+            return None, g_unet, None, None, None, None, None, None
+        g_img = torch.empty((2 * B, H, W, 32), dtype=dt, device=grad_h0.device)
         check(_lib.lib().dfb_decoder_gather_backward(grad_h0.data_ptr(), int(grad_h0.dtype == torch.bfloat16), B, H, W,
                                                      idx.counts.data_ptr(), idx.F, idx.pil_pix.data_ptr(),
                                                      idx.pil_start.data_ptr(), idx.sorted_pt.data_ptr(),
                                                      g_img.data_ptr(), g_unet.data_ptr(), int(dt == torch.bfloat16),
                                                      idx.pil_cap, _stream(grad_h0)), "decoder_gather_backward")
-        return g_img, g_unet, None, None, None, None, None
+        return g_img, g_unet, None, None, None, None, None, None
 
 
-def decoder_gather(img, unet, idx, B, n_rows, out_dtype=torch.float32, n_alloc=None):
-    return _DecoderGather.apply(img, unet, idx, B, n_rows, out_dtype, n_alloc)
+def gather_backward_split(grad_h0, idx, B, H, W, g_img, g_unet, dt, accumulate):
+    """dfb_decoder_gather_backward_split: either output may be None; accumulate = add the image rows into g_img."""
+    check(_lib.lib().dfb_decoder_gather_backward_split(
+        grad_h0.data_ptr(), int(grad_h0.dtype == torch.bfloat16), B, H, W, idx.counts.data_ptr(), idx.F,
+        idx.pil_pix.data_ptr(), idx.pil_start.data_ptr(), idx.sorted_pt.data_ptr(), _ptr(g_img), _ptr(g_unet),
+        int(dt == torch.bfloat16), idx.pil_cap, int(accumulate), _stream(grad_h0)), "decoder_gather_backward_split")
+
+
+def add_cat2(a0, b0, a1, b1):
+    """cat([a0 + b0, a1 + b1], 0) in one pass (b0 = b1 = None: plain concatenation)."""
+    _need_cuda(a0, "add_cat2")
+    for t in (a0, a1, b0, b1):
+        assert t is None or (t.is_contiguous() and t.shape == a0.shape and t.dtype == a0.dtype)
+    out = torch.empty((2 * a0.shape[0],) + tuple(a0.shape[1:]), dtype=a0.dtype, device=a0.device)
+    check(_lib.lib().dfb_add_cat2(a0.data_ptr(), _ptr(b0), a1.data_ptr(), _ptr(b1), a0.numel() * a0.element_size(),
+                                  int(a0.dtype == torch.bfloat16), out.data_ptr(), _stream(a0)), "add_cat2")
+    return out
+
+
+def decoder_gather(img, unet, idx, B, n_rows, out_dtype=torch.float32, n_alloc=None, sink=None):
+    return _DecoderGather.apply(img, unet, idx, B, n_rows, out_dtype, n_alloc, sink)
 
 
 # ----------------------------------------------------------------------------------------------

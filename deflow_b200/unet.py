@@ -98,9 +98,12 @@ class FastFlow3DUNet(nn.Module):
         """Reference signature: [B,32,H,W] x2 -> [B,64,H,W] (any memory format; channels-last is the fast one)."""
         return self.forward_nhwc(_to_nhwc(pc0_B, self.compute_dtype), _to_nhwc(pc1_B, self.compute_dtype)).permute(0, 3, 1, 2)
 
-    def forward_nhwc(self, img0: torch.Tensor, img1: torch.Tensor) -> torch.Tensor:
-        """NHWC [B,H,W,32] x2 -> NHWC [B,H,W,64]."""
-        return self._forward_tensor_core(img0.contiguous(), img1.contiguous())
+    def forward_nhwc(self, img0: torch.Tensor, img1: torch.Tensor, skip_imgs=None) -> torch.Tensor:
+        """NHWC [B,H,W,32] x2 -> NHWC [B,H,W,64].  skip_imgs: optional aliases of (img0, img1) for the last skip connection
+        (DeFlow.forward hands over separate autograd edges so that the two gradients of an image arrive separately)."""
+        if skip_imgs is not None:
+            skip_imgs = (skip_imgs[0].contiguous(), skip_imgs[1].contiguous())
+        return self._forward_tensor_core(img0.contiguous(), img1.contiguous(), skip_imgs)
 
     # Every convolution is a tcgen05 implicit GEMM (csrc/conv_igemm.cu); BatchNorm statistics come from the convolution
     # epilogue; BN+GELU, bilinear x2 and their backward are HBM-bound passes (csrc/unet_elem.cu).  Channel
@@ -116,12 +119,12 @@ class FastFlow3DUNet(nn.Module):
             self.__dict__["_dfb_bank"] = bank
         return bank
 
-    def _forward_tensor_core(self, img0, img1):
+    def _forward_tensor_core(self, img0, img1, skip_imgs=None):
         from . import conv as tc
         with tc.bank_scope(self._weight_bank(), img0.dtype == torch.float32):
-            return self._forward_packed(img0, img1)
+            return self._forward_packed(img0, img1, skip_imgs)
 
-    def _forward_packed(self, img0, img1):
+    def _forward_packed(self, img0, img1, skip_imgs=None):
         from . import conv as tc
 
         def encoder(x):
@@ -136,6 +139,6 @@ class FastFlow3DUNet(nn.Module):
         f1, l1, r1 = encoder(img1)
         s = self.decoder_step1.forward_nhwc((r0, r1), (l0, l1))
         t = self.decoder_step2.forward_nhwc((s,), (f0, f1))
-        u = self.decoder_step3.forward_nhwc((t,), (img0, img1))
+        u = self.decoder_step3.forward_nhwc((t,), skip_imgs if skip_imgs is not None else (img0, img1))
         tc.flush_batch_counters()
         return tc.conv_bias(self.decoder_step4.weight, self.decoder_step4.bias, u)

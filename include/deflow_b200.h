@@ -206,6 +206,17 @@ int dfb_decoder_gather(const void* img, const void* unet, int in_bf16, int B, in
 int dfb_decoder_gather_backward(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
                                 const int* pil_pix, const int* pil_start, const int* sorted_pt, void* grad_img,
                                 void* grad_unet, int out_bf16, int pil_cap, void* stream);
+/* The same with either output optional: grad_img == NULL -> only the UNet gradient (dense); grad_unet == NULL -> only the
+ * image rows, and with img_accumulate they are ADDED to an existing dense image gradient instead of being written into a
+ * zero-filled one (the image part of the gather's backward is then applied after the other consumers of the pseudo-image
+ * have produced their gradients: no dense zero-fill, no dense addition). */
+int dfb_decoder_gather_backward_split(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
+                                      const int* pil_pix, const int* pil_start, const int* sorted_pt, void* grad_img,
+                                      void* grad_unet, int out_bf16, int pil_cap, int img_accumulate, void* stream);
+/* out[0:half) = a0 + b0, out[half:2*half) = a1 + b1 (elementwise, bf16 or fp32; b0 = b1 = NULL: plain concatenation): the
+ * gradient of the pseudo-image [2B,H,W,32] from the two consumers of each frame half in one pass. */
+int dfb_add_cat2(const void* a0, const void* b0, const void* a1, const void* b1, long long bytes_per_half, int bf16, void* out,
+                 void* stream);
 
 /* ------------------------------------------------------------------ losses
  * deflowLoss / ff3dLoss with the trainer's gt construction fused in

@@ -529,3 +529,42 @@ def test_reused_canvas_matches_fresh_canvas():
             want, _ = ref.embed(pts, torch.bfloat16)
         assert torch.equal(got, want)
         assert int((got.float().abs().sum(-1) > 0).sum()) <= idx.pil_off(idx.F)
+
+
+def test_split_frames_backward_is_the_slicing_gradient():
+    """deflow._SplitFrames hands every frame half to two consumers (encoder, last skip convolution) on separate autograd
+    edges; its backward = the gradient of plain slicing with both consumers added, in one pass (ops.add_cat2)."""
+    from deflow_b200.deflow import _SplitFrames
+    torch.manual_seed(0)
+    for dt in (torch.float32, torch.bfloat16):
+        x = torch.randn(6, 4, 5, 32, device=DEV).to(dt).requires_grad_(True)
+        a0, a1, b0, b1 = _SplitFrames.apply(x, 3, None)
+        assert torch.equal(a0, x[:3]) and torch.equal(a1, x[3:]) and torch.equal(b0, x[:3]) and torch.equal(b1, x[3:])
+        w = torch.randn(3, 4, 5, 32, device=DEV).to(dt)
+        ((a0 * w).sum() + (2 * a1 * w).sum() + (3 * b0 * w).sum() + (5 * b1 * w).sum()).backward()
+        want = torch.cat([(w.float() + 3 * w.float()), (2 * w.float() + 5 * w.float())], 0)
+        tol = 0 if dt == torch.float32 else 2e-2
+        assert float((x.grad.float() - want).abs().max()) <= tol * float(want.abs().max())
+    # one consumer only, and one half unused
+    y = torch.randn(4, 2, 2, 32, device=DEV, requires_grad=True)
+    a0, a1, b0, b1 = _SplitFrames.apply(y, 2, None)
+    a0.sum().backward()
+    assert torch.equal(y.grad, torch.cat([torch.ones(2, 2, 2, 32), torch.zeros(2, 2, 2, 32)]).to(DEV))
+
+
+def test_fused_image_gradient_path_equals_autograd_accumulation(monkeypatch):
+    """The pseudo-image's three gradients (encoder, last skip convolution, decoder gather) met in _SplitFrames.backward
+    (deferred gather rows added in place) against the plain autograd accumulation (DFB_IMG_GRAD_FUSE=0): same parameter
+    gradients of the pillar feature net, which is all that lies upstream of the image."""
+    fx, batch, cfg = load_fixture("deflow_small_gru")
+    gb = batch_to(batch, DEV)
+    grads = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("DFB_IMG_GRAD_FUSE", fuse)
+        m = _model_for(cfg)
+        res = m(gb)
+        d.training_step_loss(gb, res, cfg["loss"]).backward()
+        grads[fuse] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    for k in grads["1"]:
+        a, b = grads["1"][k], grads["0"][k]
+        assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max())), k

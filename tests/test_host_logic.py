@@ -52,25 +52,6 @@ def test_synthetic_batch_layout():
     assert 0.03 < m / n < 0.5 and n < int(ok.sum())
 
 
-def test_split_frames_backward_is_the_slicing_gradient():
-    """deflow._SplitFrames: same values and gradients as image[:B], image[B:] (one concatenation instead of two
-    zero-filled slice gradients and an add)."""
-    from deflow_b200.deflow import _SplitFrames
-    torch.manual_seed(0)
-    x = torch.randn(6, 4, 5, 3, requires_grad=True)
-    a, b = _SplitFrames.apply(x, 2)
-    assert torch.equal(a, x[:2]) and torch.equal(b, x[2:])
-    (a.square().sum() + (3 * b).sum()).backward()
-    xr = x.detach().clone().requires_grad_(True)
-    (xr[:2].square().sum() + (3 * xr[2:]).sum()).backward()
-    assert torch.equal(x.grad, xr.grad)
-    # one branch unused: its half of the gradient is zero
-    y = torch.randn(4, 2, requires_grad=True)
-    a, b = _SplitFrames.apply(y, 1)
-    a.sum().backward()
-    assert torch.equal(y.grad, torch.cat([torch.ones(1, 2), torch.zeros(3, 2)]))
-
-
 def test_zero_pool_hands_out_disjoint_zeroed_views():
     from deflow_b200 import conv
     ts = [conv.zeros(s, dt, "cpu") for s, dt in [((2, 64), torch.float64), ((3, 32), torch.float32), ((5,), torch.float32),
