@@ -79,6 +79,12 @@ class EvalTables(C.Structure):
                 ("dist_splits", C.c_double * 6), ("n_speed", C.c_int), ("n_dist", C.c_int)]
 
 
+class UnpackDesc(C.Structure):
+    """dfb_unpack_desc"""
+    _fields_ = [("wacc", C.c_void_p), ("grad", C.c_void_p), ("first", C.c_longlong),
+                ("cout", C.c_int), ("cin", C.c_int), ("ksize", C.c_int), ("accumulate", C.c_int)]
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -136,11 +142,13 @@ def _declare(lib):
         "dfb_clear_rows": [vp, i32, vp, vp, i32, i64, vp],
         "dfb_decoder_gather": [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, i32, vp],
         "dfb_decoder_gather_backward": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
-        "dfb_decoder_gather_backward_split": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "dfb_decoder_gather_backward_rows": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
+        "dfb_gather_img_rows_add": [vp, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp],
         "dfb_add_cat2": [vp, vp, vp, vp, i64, i32, vp, vp],
         "dfb_flow_loss": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],
         "dfb_conv_pack_weights": [vp, i32, i32, i32, i32, vp, vp, vp],
         "dfb_conv_pack_weights_multi": [vp, i32, i64, i32, vp],
+        "dfb_wgrad_unpack_multi": [vp, i32, i64, vp],
         "dfb_split_bf16x2": [vp, i64, vp, vp, vp],
         "dfb_conv2d": [C.POINTER(ConvArgs), vp],
         "dfb_conv2d_wgrad": [C.POINTER(ConvArgs), vp, vp, i32, vp],
@@ -185,14 +193,14 @@ def _declare(lib):
 EXPORTS = ["dfb_last_error", "dfb_version", "dfb_launch_count", "dfb_grid_size", "dfb_dynamic_voxelize_forward",
            "dfb_scatter_index", "dfb_scatter_reduce", "dfb_dynamic_point_to_voxel_backward", "dfb_index_workspace",
            "dfb_index_scan_workspace", "dfb_pillar_index", "dfb_ego_warp", "dfb_pfn_forward", "dfb_pfn_backward", "dfb_zero_fill", "dfb_clear_rows", "dfb_decoder_gather",
-           "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_conv_pack_weights_multi", "dfb_split_bf16x2", "dfb_conv2d", "dfb_conv2d_wgrad",
+           "dfb_decoder_gather_backward", "dfb_flow_loss", "dfb_conv_pack_weights", "dfb_conv_pack_weights_multi", "dfb_wgrad_unpack_multi", "dfb_split_bf16x2", "dfb_conv2d", "dfb_conv2d_wgrad",
            "dfb_bn2d_finalize", "dfb_bn_gelu_apply", "dfb_bn_gelu_backward", "dfb_channel_sum", "dfb_upsample2x",
            "dfb_offset_encode", "dfb_offset_encode_backward", "dfb_to_bf16_pad", "dfb_gru_rh", "dfb_gru_update",
            "dfb_gru_bwd1", "dfb_gru_bwd2", "dfb_acc_bf16", "dfb_head_out", "dfb_head_out_backward",
            "dfb_gru_fused_forward", "dfb_gru_fused_backward", "dfb_collate_workspace", "dfb_collate_pad",
            "dfb_eval_accumulate", "dfb_bn_gelu_backward_phase",
            "dfb_chamfer_forward", "dfb_chamfer_backward", "dfb_hard_voxelize_workspace", "dfb_hard_voxelize_assign",
-           "dfb_conv3x3_dgrad_colsum", "dfb_decoder_gather_backward_split", "dfb_add_cat2"]
+           "dfb_conv3x3_dgrad_colsum", "dfb_decoder_gather_backward_rows", "dfb_gather_img_rows_add", "dfb_add_cat2"]
 
 
 def lib():

@@ -226,25 +226,33 @@ def bias_grad(gy: torch.Tensor) -> torch.Tensor:
     return channel_sum(gy)
 
 
-def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, grad_w: Optional[torch.Tensor] = None):
-    """-> grad_w fp32 in torch layout [cout, sum(c_i), k, k]."""
+def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, grad_w: Optional[torch.Tensor] = None,
+                 wacc_slot: Optional[torch.Tensor] = None):
+    """-> grad_w fp32 in torch layout [cout, sum(c_i), k, k].  wacc_slot: a [k*k, cout, cin] fp32 accumulator of a
+    WeightBank with deferred gradients -- the result is ADDED there and nothing is returned (the bank unpacks all of its
+    weight gradients with one launch at the end of the backward pass)."""
     if gy.dtype == torch.float32:
         # split precision: x_hi*gy_hi + x_hi*gy_lo + x_lo*gy_hi accumulated into the same fp32 gradient
         pairs = [split(x) for x in xs]
         gh, gl = split(gy)
         hi, lo = [p[0] for p in pairs], [p[1] for p in pairs]
-        grad_w = conv2d_wgrad(hi, gh, ksize, stride, grad_w)
-        grad_w = conv2d_wgrad(hi, gl, ksize, stride, grad_w)
-        return conv2d_wgrad(lo, gh, ksize, stride, grad_w)
+        grad_w = conv2d_wgrad(hi, gh, ksize, stride, grad_w, wacc_slot)
+        grad_w = conv2d_wgrad(hi, gl, ksize, stride, grad_w, wacc_slot)
+        return conv2d_wgrad(lo, gh, ksize, stride, grad_w, wacc_slot)
     n, H, W, _ = xs[0].shape
     cout = gy.shape[3]
     cins = [x.shape[3] for x in xs]
     ct = sum(cins)
     assert gy.is_contiguous() and gy.dtype == torch.bfloat16
-    wacc = torch.empty((ksize * ksize, cout, ct), dtype=torch.float32, device=gy.device)
-    acc = grad_w is not None
-    if grad_w is None:
-        grad_w = torch.empty((cout, ct, ksize, ksize), dtype=torch.float32, device=gy.device)
+    deferred = wacc_slot is not None
+    if deferred:
+        assert tuple(wacc_slot.shape) == (ksize * ksize, cout, ct) and wacc_slot.is_contiguous()
+        wacc, acc, grad_w = wacc_slot, 2, None        # bit 1: keep the accumulator's contents; no unpack
+    else:
+        wacc = torch.empty((ksize * ksize, cout, ct), dtype=torch.float32, device=gy.device)
+        acc = int(grad_w is not None)
+        if grad_w is None:
+            grad_w = torch.empty((cout, ct, ksize, ksize), dtype=torch.float32, device=gy.device)
     a = _args(0, n, H, W, ksize, stride, xs, cins, cout, None, None, gy, None)
     ncol = max(cout, 64)
     name = f"k_conv_wgrad_halo<{ncol}>" if (ksize == 3 and stride == 1) else f"k_conv_wgrad<{ncol}>"
@@ -252,7 +260,7 @@ def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, gr
             and __import__("os").environ.get("DFB_WGRAD_X", "1") != "0":
         name = "k_conv_wgrad_x"      # cross-shift kernel for 64 output channels (dfb_conv2d_wgrad)
     with _timed(name, 2.0 * n * gy.shape[1] * gy.shape[2] * cout * ct * ksize * ksize, gy):
-        check(_lib.lib().dfb_conv2d_wgrad(C.byref(a), wacc.data_ptr(), grad_w.data_ptr(), int(acc), _stream(gy)), "conv2d wgrad")
+        check(_lib.lib().dfb_conv2d_wgrad(C.byref(a), wacc.data_ptr(), _ptr(grad_w), int(acc), _stream(gy)), "conv2d wgrad")
     return grad_w
 
 
@@ -331,6 +339,10 @@ class WeightBank:
         self._key = None
         self._table = {}
         self._bufs = {}
+        self._index = {id(w): i for i, w in enumerate(self.weights)}
+        self.defer_grads, self.grad_targets = False, None
+        self._grad_key, self._bw_active = None, False
+        self._unpack_key, self._unpack_table = None, None
 
     def _build(self, split3: bool):
         dev = self.weights[0].device
@@ -353,6 +365,92 @@ class WeightBank:
         self._table[split3] = (host.to(dev), first)
         self._bufs[split3] = bufs
 
+    # ------------------------------------------------------------------ deferred weight gradients
+    # With ``defer_grads`` (set by trainer.TrainStep) the weight-gradient kernels of the bank's convolutions leave their
+    # results in ONE persistent fp32 accumulator ([tap][cout][cin] per weight, zeroed once per backward pass): the two calls
+    # of a shared encoder weight and the three products of the split-precision mode sum there in place, the autograd
+    # Functions return no weight gradient, and a callback queued on the autograd engine unpacks ALL gradients to the torch
+    # layout with one launch when the backward pass ends -- straight into ``grad_targets`` (the views of the trainer's
+    # flat gradient buffer) when given.  Replaces 54 unpack launches, 54 memsets and the 64 additions autograd performs
+    # for the shared encoder weights per step.  Off by default: callers that use torch.autograd.grad() or gradient hooks
+    # on these weights need the per-launch gradients.
+    def enable_deferred_grads(self, grad_targets=None):
+        self.defer_grads = True
+        self.grad_targets = grad_targets      # {id(weight): fp32 tensor [cout,cin,k,k]} or None
+        self._grad_key = None
+
+    def _build_grad(self):
+        dev = self.weights[0].device
+        total = sum(w.numel() for w in self.weights)
+        self._acc = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._acc_views, off = [], 0
+        for w in self.weights:
+            cout, cin, k, _ = w.shape
+            self._acc_views.append(self._acc[off:off + w.numel()].view(k * k, cout, cin))
+            off += w.numel()
+        self._grad_total = total
+
+    def wgrad_slot(self, w):
+        """The accumulator of weight ``w`` for this backward pass (None: not a deferred weight).  The first request of a
+        backward pass zeroes the accumulator and queues the unpack on the autograd engine."""
+        if not getattr(self, "defer_grads", False):
+            return None
+        i = self._index.get(id(w))
+        if i is None:
+            return None
+        key = tuple(x.data_ptr() for x in self.weights)
+        if self._grad_key != key:
+            self._build_grad()
+            self._grad_key, self._unpack_key = key, None
+        if not self._bw_active:
+            self._acc.zero_()
+            self._bw_active = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._finish_backward)
+        return self._acc_views[i]
+
+    def _finish_backward(self):
+        self._bw_active = False
+        dev = self.weights[0].device
+        plan, flat = [], None
+        for w in self.weights:
+            tgt = self.grad_targets.get(id(w)) if self.grad_targets else None
+            accumulate = 0
+            if tgt is None:
+                if w.grad is not None:
+                    tgt, accumulate = w.grad, 1
+                else:
+                    if flat is None:
+                        flat = torch.empty(self._grad_total, dtype=torch.float32, device=dev)
+                        off = 0
+                    tgt = None      # filled below from `flat`
+            elif w.grad is not None and w.grad.data_ptr() == tgt.data_ptr():
+                accumulate = 1                      # a second backward into the same buffer (gradient accumulation)
+            plan.append([w, tgt, accumulate])
+        first = 0
+        for ent in plan:
+            if ent[1] is None:
+                ent[1] = flat[first:first + ent[0].numel()].view_as(ent[0])
+            first += ent[0].numel()
+        # the device descriptor table is rebuilt (one small H2D copy) only when a target pointer or flag changes: in a
+        # training loop it is the same every step, and nothing here synchronises the host with the device
+        key = tuple((t.data_ptr(), a) for _, t, a in plan)
+        if key != self._unpack_key:
+            descs = (_lib.UnpackDesc * len(plan))()
+            off = 0
+            for i, (w, tgt, accumulate) in enumerate(plan):
+                cout, cin, k, _ = w.shape
+                d = descs[i]
+                d.wacc, d.grad, d.first = self._acc_views[i].data_ptr(), tgt.data_ptr(), off
+                d.cout, d.cin, d.ksize, d.accumulate = cout, cin, k, accumulate
+                off += w.numel()
+            self._unpack_table = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).clone().to(dev)
+            self._unpack_key = key
+        check(_lib.lib().dfb_wgrad_unpack_multi(self._unpack_table.data_ptr(), len(plan), first, _stream(self.weights[0])),
+              "wgrad_unpack_multi")
+        for w, tgt, _ in plan:
+            if w.grad is None or w.grad.data_ptr() != tgt.data_ptr():
+                w.grad = tgt
+
     def refresh(self, split3: bool):
         """Pack every weight now (one launch) and hang (token, w_fwd, w_dgrad) on its parameter for ``packed``;
         returns the token of this refresh."""
@@ -370,6 +468,7 @@ class WeightBank:
         name = "_dfb_packed3" if split3 else "_dfb_packed"
         for w, pair in zip(self.weights, self._bufs[split3]):
             setattr(w, name, (token, pair[0], pair[1]))
+            w._dfb_bank = self
         return token
 
     _tokens = 0
@@ -412,6 +511,12 @@ def packed_raw(w4: torch.Tensor, split3: bool = False):
     return hit
 
 
+def _wgrad_slot(w):
+    """Deferred-gradient accumulator of a bank weight (None: return the gradient through autograd as usual)."""
+    bank = getattr(w, "_dfb_bank", None)
+    return bank.wgrad_slot(w) if bank is not None else None
+
+
 class _Conv(torch.autograd.Function):
     """Conv2d(k, stride 1, pad k//2, bias) over 1-2 channel-concatenated NHWC bf16 sources."""
 
@@ -433,7 +538,8 @@ class _Conv(torch.autograd.Function):
         gy = gy.contiguous()
         k = ctx.k
         ct = ctx.wshape[1]
-        gw = conv2d_wgrad(xs, gy, k, 1)
+        slot = _wgrad_slot(w)
+        gw = conv2d_wgrad(xs, gy, k, 1, None, slot)
         gxs, off = [None, None], 0
         # Per-channel sums of the data gradient = the bias gradient of the convolution that produced this input.  3x3: from
         # the epilogue of the (MMA-bound) halo kernel, where they are nearly free.  1x1: the epilogue is what bounds these
@@ -487,18 +593,18 @@ class _ConvBnGelu(torch.autograd.Function):
         bn = bn2d_finalize(stats, count, training, eps, momentum, gamma.detach().float(), beta.detach().float(),
                            running_mean, running_var)
         act = bn_gelu_apply(raw, bn)
-        ctx.save_for_backward(x, raw, bn, wd)
+        ctx.save_for_backward(x, raw, bn, wd, w)
         ctx.cfg = (stride, training, tuple(w.shape))
         return act
 
     @staticmethod
     def backward(ctx, gact):
-        x, raw, bn, wd = ctx.saved_tensors
+        x, raw, bn, wd, w = ctx.saved_tensors
         stride, training, wshape = ctx.cfg
         cout, cin = wshape[0], wshape[1]
         gg, gbeta, gbias = zeros((3, cout), torch.float32, x.device).unbind(0)
         graw = bn_gelu_backward(raw, gact.contiguous(), bn, training, gg, gbeta, gbias, ctx.sync)
-        gw = conv2d_wgrad([x], graw, 3, stride)
+        gw = conv2d_wgrad([x], graw, 3, stride, None, _wgrad_slot(w))
         gx = conv2d_dgrad(graw, wd, x.shape[1], x.shape[2], cin, cin, 0, 3, stride) if ctx.needs_input_grad[0] else None
         return gx, gw, gbias, gg, gbeta, None, None, None, None, None, None, None
 

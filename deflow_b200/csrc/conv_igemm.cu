@@ -1580,7 +1580,11 @@ static bool halo_wgrad_enabled() {
 // wacc: fp32 workspace [taps][cout][cin_total] (zeroed here); grad_w: torch layout fp32 [cout][cin_total][k][k].
 extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad_w, int accumulate, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  if (!a || !wacc || !grad_w) { set_error("dfb_conv2d_wgrad: null args"); return DFB_ERR_ARG; }
+  if (!a || !wacc) { set_error("dfb_conv2d_wgrad: null args"); return DFB_ERR_ARG; }
+  // accumulate bit 1: wacc already holds partial sums (a shared weight's other call, or the caller zeroed it): no memset;
+  // grad_w == NULL: leave the result in wacc ([tap][cout][cin]) for dfb_wgrad_unpack_multi
+  const bool keep_wacc = (accumulate & 2) != 0;
+  accumulate &= 1;
   const int k = a->ksize, s = a->stride, taps = k * k;
   if ((k != 1 && k != 3) || (s != 1 && s != 2) || a->n_src < 1 || a->n_src > 2) { set_error("dfb_conv2d_wgrad: bad conv geometry"); return DFB_ERR_ARG; }
   if (a->cout != 32 && a->cout != 64 && a->cout != 128 && a->cout != 256) { set_error("dfb_conv2d_wgrad: cout must be 32, 64, 128 or 256"); return DFB_ERR_UNSUPPORTED; }
@@ -1636,7 +1640,7 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
         X.splits = splits;
         X.cin_total = cin_total; X.cout = a->cout; X.wacc = wacc;
         const size_t total = (size_t)taps * a->cout * cin_total;
-        cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
+        if (!keep_wacc) cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
         static bool configured = false;
         if (!configured) {
           cudaError_t e = cudaFuncSetAttribute(tc::k_conv_wgrad_x, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WgradXCfg::SMEM);
@@ -1644,10 +1648,13 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
           configured = true;
         }
         tc::k_conv_wgrad_x<<<ni * splits, tc::WG_THREADS, tc::WgradXCfg::SMEM, st>>>(maps, X);
-        long long blocks = ((long long)total + 255) / 256;
-        if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-        tc::k_unpack_wgrad<<<(int)blocks, 256, 0, st>>>(wacc, a->cout, cin_total, taps, grad_w, accumulate);
-        add_launches(2);
+        add_launches(1);
+        if (grad_w) {
+          long long blocks = ((long long)total + 255) / 256;
+          if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+          tc::k_unpack_wgrad<<<(int)blocks, 256, 0, st>>>(wacc, a->cout, cin_total, taps, grad_w, accumulate);
+          add_launches(1);
+        }
         return check_launch("dfb_conv2d_wgrad (cross-shift)");
       }
     }
@@ -1702,15 +1709,17 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
     }
     Q.cin_total = cin_total; Q.cout = a->cout; Q.wacc = wacc;
     const size_t total = (size_t)taps * a->cout * cin_total;
-    cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
+    if (!keep_wacc) cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
     if (ncol == 64) rc = tc::launch_wgrad_halo<64>(maps, Q, st);
     else if (ncol == 128) rc = tc::launch_wgrad_halo<128>(maps, Q, st);
     else rc = tc::launch_wgrad_halo<256>(maps, Q, st);
     if (rc) return rc;
-    long long blocks = ((long long)total + 255) / 256;
-    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    tc::k_unpack_wgrad<<<(int)blocks, 256, 0, st>>>(wacc, a->cout, cin_total, taps, grad_w, accumulate);
-    add_launches(1);
+    if (grad_w) {
+      long long blocks = ((long long)total + 255) / 256;
+      if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+      tc::k_unpack_wgrad<<<(int)blocks, 256, 0, st>>>(wacc, a->cout, cin_total, taps, grad_w, accumulate);
+      add_launches(1);
+    }
     return check_launch("dfb_conv2d_wgrad");
   }
   if (s == 1) {
@@ -1761,14 +1770,55 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
   P.cout = a->cout;
   P.wacc = wacc;
   const size_t total = (size_t)taps * a->cout * cin_total;
-  cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
+  if (!keep_wacc) cudaMemsetAsync(wacc, 0, total * sizeof(float), st);
   if (a->cout <= 64) rc = tc::launch_wgrad<64>(maps, P, st);
   else if (a->cout == 128) rc = tc::launch_wgrad<128>(maps, P, st);
   else rc = tc::launch_wgrad<256>(maps, P, st);
   if (rc) return rc;
-  long long blocks = ((long long)total + 255) / 256;
-  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  tc::k_unpack_wgrad<<<(int)blocks, 256, 0, st>>>(wacc, a->cout, cin_total, taps, grad_w, accumulate);
-  add_launches(1);
+  if (grad_w) {
+    long long blocks = ((long long)total + 255) / 256;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    tc::k_unpack_wgrad<<<(int)blocks, 256, 0, st>>>(wacc, a->cout, cin_total, taps, grad_w, accumulate);
+    add_launches(1);
+  }
   return check_launch("dfb_conv2d_wgrad");
+}
+
+// Every weight gradient of a model from its [tap][cout][cin] accumulator to the torch layout [cout][cin][tap] in ONE launch
+// (the counterpart of dfb_conv_pack_weights_multi): table[i].first = running element offset, as there.
+namespace dfb {
+namespace tc {
+__global__ void __launch_bounds__(256) k_unpack_wgrad_multi(const dfb_unpack_desc* __restrict__ table, int n_w, long long total) {
+  __shared__ dfb_unpack_desc sd[64];
+  for (int i = threadIdx.x; i < n_w; i += blockDim.x) sd[i] = table[i];
+  __syncthreads();
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_w - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (sd[mid].first <= g) lo = mid; else hi = mid - 1;
+    }
+    const dfb_unpack_desc& d = sd[lo];
+    const long long e = g - d.first;
+    const int taps = d.ksize * d.ksize;
+    const int t = (int)(e % taps);
+    const int ci = (int)((e / taps) % d.cin);
+    const int co = (int)(e / ((long long)taps * d.cin));
+    const float v = d.wacc[((size_t)t * d.cout + co) * d.cin + ci];
+    d.grad[e] = d.accumulate ? d.grad[e] + v : v;
+  }
+}
+}  // namespace tc
+}  // namespace dfb
+
+extern "C" int dfb_wgrad_unpack_multi(const dfb_unpack_desc* table_dev, int n_weights, long long total_elems, void* stream_) {
+  if (n_weights <= 0 || n_weights > 64 || total_elems <= 0 || !table_dev) {
+    set_error("dfb_wgrad_unpack_multi: 1..64 weights and a device table are required");
+    return DFB_ERR_ARG;
+  }
+  long long blocks = (total_elems + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  dfb::tc::k_unpack_wgrad_multi<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(table_dev, n_weights, total_elems);
+  add_launches(1);
+  return check_launch("dfb_wgrad_unpack_multi");
 }

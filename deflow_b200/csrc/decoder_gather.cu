@@ -67,9 +67,10 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
                                                             const int* __restrict__ pil_start,
                                                             const int* __restrict__ sorted_pt,
                                                             void* __restrict__ grad_img, void* __restrict__ grad_unet,
-                                                            int pil_cap, int img_accumulate) {
-  // grad_img == NULL: only the UNet rows; grad_unet == NULL: only the image rows; img_accumulate: the image rows are ADDED to
-  // an existing dense gradient (every (frame, pixel) row belongs to exactly one pillar: plain read-modify-write)
+                                                            int pil_cap, float* __restrict__ img_rows) {
+  // img_rows != NULL (then grad_img == NULL): the 64 image channels of every pc0 pillar's sum go to the compact fp32 buffer
+  // img_rows[q][64] instead of a dense zero-filled image gradient; k_gather_img_rows_add adds them into the image gradient
+  // later, once the other consumers of the pseudo-image have written theirs.
   const int M0 = min(counts[3 * F + 1 + B], pil_cap);  // pillars of the pc0 frames
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -85,8 +86,7 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
       float4 v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        v[k] = (pt[k] >= 0 && (lane < 16 ? grad_img != nullptr : grad_unet != nullptr))
-                   ? load4<IN_BF>(grad_h0, (size_t)pt[k] * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[k] = pt[k] >= 0 ? load4<IN_BF>(grad_h0, (size_t)pt[k] * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 8; k += 2) {
         a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
@@ -96,17 +96,32 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     const int pix = pil_pix[q];
     if (lane < 16) {
-      if (grad_img) {
-        const size_t e = lane < 8 ? (size_t)pix * 32 + lane * 4 : ((size_t)pix + (size_t)B * HW) * 32 + (lane - 8) * 4;
-        if (img_accumulate) {
-          const float4 o = load4<OUT_BF>(grad_img, e);
-          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
-        }
-        store4<OUT_BF>(grad_img, e, a);
-      }
-    } else if (grad_unet) {
+      if (img_rows) *reinterpret_cast<float4*>(img_rows + (size_t)q * 64 + lane * 4) = a;
+      else if (lane < 8) store4<OUT_BF>(grad_img, (size_t)pix * 32 + lane * 4, a);
+      else store4<OUT_BF>(grad_img, ((size_t)pix + (size_t)B * HW) * 32 + (lane - 8) * 4, a);
+    } else {
       store4<OUT_BF>(grad_unet, (size_t)pix * 64 + (lane - 16) * 4, a);
     }
+  }
+}
+
+// grad_img[b, pix, :] += img_rows[q][0:32], grad_img[B + b, pix, :] += img_rows[q][32:64] for every pc0 pillar q: every
+// (frame, pixel) row belongs to exactly one pillar, so this is a plain read-modify-write of two 32-channel rows per pillar.
+template <bool OUT_BF>
+__global__ void __launch_bounds__(256) k_gather_img_rows_add(const float* __restrict__ img_rows, int B, int HW,
+                                                             const int* __restrict__ counts, int F,
+                                                             const int* __restrict__ pil_pix, void* __restrict__ grad_img,
+                                                             int pil_cap) {
+  const int M0 = min(counts[3 * F + 1 + B], pil_cap);
+  const long long total = (long long)M0 * 16;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(t >> 4), l = (int)(t & 15);
+    const int pix = pil_pix[q];
+    float4 a = *reinterpret_cast<const float4*>(img_rows + (size_t)q * 64 + l * 4);
+    const size_t e = l < 8 ? (size_t)pix * 32 + l * 4 : ((size_t)pix + (size_t)B * HW) * 32 + (l - 8) * 4;
+    const float4 o = load4<OUT_BF>(grad_img, e);
+    a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    store4<OUT_BF>(grad_img, e, a);
   }
 }
 
@@ -134,21 +149,21 @@ extern "C" int dfb_decoder_gather(const void* img, const void* unet, int in_bf16
 
 static int gather_backward_impl(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
                                 const int* pil_pix, const int* pil_start, const int* sorted_pt, void* grad_img,
-                                void* grad_unet, int out_bf16, int pil_cap, int img_accumulate, cudaStream_t st) {
+                                void* grad_unet, int out_bf16, int pil_cap, float* img_rows, cudaStream_t st) {
   if (B <= 0 || F < B || H <= 0 || W <= 0) { set_error("dfb_decoder_gather_backward: bad sizes"); return DFB_ERR_ARG; }
   const size_t HW = (size_t)H * W, es = out_bf16 ? 2 : 4;
   // dense gradients: zero everywhere except the pc0 pillars (index_put_ accumulate into zeros)
-  if (grad_img && !img_accumulate) cudaMemsetAsync(grad_img, 0, (size_t)2 * B * HW * 32 * es, st);
-  if (grad_unet) cudaMemsetAsync(grad_unet, 0, (size_t)B * HW * 64 * es, st);
+  if (grad_img) cudaMemsetAsync(grad_img, 0, (size_t)2 * B * HW * 32 * es, st);
+  cudaMemsetAsync(grad_unet, 0, (size_t)B * HW * 64 * es, st);
   if (pil_cap > 0) {
     long long blocks = ((long long)pil_cap * 32 + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     const int g = (int)blocks;
-    if (grad_bf16 && out_bf16) k_decoder_gather_bwd<true, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_accumulate);
-    else if (grad_bf16) k_decoder_gather_bwd<true, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_accumulate);
-    else if (out_bf16) k_decoder_gather_bwd<false, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_accumulate);
-    else k_decoder_gather_bwd<false, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_accumulate);
+    if (grad_bf16 && out_bf16) k_decoder_gather_bwd<true, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows);
+    else if (grad_bf16) k_decoder_gather_bwd<true, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows);
+    else if (out_bf16) k_decoder_gather_bwd<false, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows);
+    else k_decoder_gather_bwd<false, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows);
     add_launches(1);
   }
   return check_launch("dfb_decoder_gather_backward");
@@ -158,18 +173,30 @@ extern "C" int dfb_decoder_gather_backward(const void* grad_h0, int grad_bf16, i
                                            const int* counts, int F, const int* pil_pix, const int* pil_start,
                                            const int* sorted_pt, void* grad_img, void* grad_unet, int out_bf16,
                                            int pil_cap, void* stream_) {
-  if (!grad_img || !grad_unet) { set_error("dfb_decoder_gather_backward: both outputs are required (see dfb_decoder_gather_backward_split)"); return DFB_ERR_ARG; }
+  if (!grad_img || !grad_unet) { set_error("dfb_decoder_gather_backward: both outputs are required (see dfb_decoder_gather_backward_rows)"); return DFB_ERR_ARG; }
   return gather_backward_impl(grad_h0, grad_bf16, B, H, W, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, out_bf16,
-                              pil_cap, 0, (cudaStream_t)stream_);
+                              pil_cap, nullptr, (cudaStream_t)stream_);
 }
 
-extern "C" int dfb_decoder_gather_backward_split(const void* grad_h0, int grad_bf16, int B, int H, int W,
-                                                 const int* counts, int F, const int* pil_pix, const int* pil_start,
-                                                 const int* sorted_pt, void* grad_img, void* grad_unet, int out_bf16,
-                                                 int pil_cap, int img_accumulate, void* stream_) {
-  if (!grad_img && !grad_unet) { set_error("dfb_decoder_gather_backward_split: no output"); return DFB_ERR_ARG; }
-  return gather_backward_impl(grad_h0, grad_bf16, B, H, W, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, out_bf16,
-                              pil_cap, img_accumulate, (cudaStream_t)stream_);
+extern "C" int dfb_decoder_gather_backward_rows(const void* grad_h0, int grad_bf16, int B, int H, int W,
+                                                const int* counts, int F, const int* pil_pix, const int* pil_start,
+                                                const int* sorted_pt, float* img_rows, void* grad_unet, int out_bf16,
+                                                int pil_cap, void* stream_) {
+  if (!img_rows || !grad_unet) { set_error("dfb_decoder_gather_backward_rows: img_rows and grad_unet are required"); return DFB_ERR_ARG; }
+  return gather_backward_impl(grad_h0, grad_bf16, B, H, W, counts, F, pil_pix, pil_start, sorted_pt, nullptr, grad_unet, out_bf16,
+                              pil_cap, img_rows, (cudaStream_t)stream_);
+}
+
+extern "C" int dfb_gather_img_rows_add(const float* img_rows, int B, int H, int W, const int* counts, int F, const int* pil_pix,
+                                       void* grad_img, int out_bf16, int pil_cap, void* stream_) {
+  if (!img_rows || !grad_img || B <= 0 || F < B) { set_error("dfb_gather_img_rows_add: bad arguments"); return DFB_ERR_ARG; }
+  if (pil_cap <= 0) return DFB_OK;
+  long long blocks = ((long long)pil_cap * 16 + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  if (out_bf16) k_gather_img_rows_add<true><<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(img_rows, B, H * W, counts, F, pil_pix, grad_img, pil_cap);
+  else k_gather_img_rows_add<false><<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(img_rows, B, H * W, counts, F, pil_pix, grad_img, pil_cap);
+  add_launches(1);
+  return check_launch("dfb_gather_img_rows_add");
 }
 
 // out[0 : n) = a0 + b0, out[n : 2n) = a1 + b1 (16-byte vectors): the gradient of the pseudo-image from its two consumers per

@@ -89,8 +89,8 @@ class _SplitFrames(torch.autograd.Function):
             gb0, gb1 = gb0.contiguous(), gb1.contiguous()
         out = ops.add_cat2(ga0, gb0, ga1, gb1)
         if pend is not None:
-            grad_h0, idx, Bp, H, W = pend
-            ops.gather_backward_split(grad_h0, idx, Bp, H, W, out, None, out.dtype, True)
+            rows, idx, Bp, H, W = pend
+            ops.gather_img_rows_add(rows, idx, Bp, H, W, out)
         return out, None, None
 
 

@@ -327,8 +327,12 @@ class _DecoderGather(torch.autograd.Function):
             # Deferred image part (deflow._SplitFrames.backward): only the UNet gradient is produced now; the rows that belong
             # to the pseudo-image are added into its gradient once the other consumers of the image have written theirs --
             # no dense zero-filled [2B,H,W,32] tensor, no dense addition.
-            gather_backward_split(grad_h0, idx, B, H, W, None, g_unet, dt, False)
-            ctx.sink["gather"] = (grad_h0, idx, B, H, W)
+            rows = torch.empty((idx.pil_cap, 64), dtype=torch.float32, device=grad_h0.device)
+            check(_lib.lib().dfb_decoder_gather_backward_rows(
+                grad_h0.data_ptr(), int(grad_h0.dtype == torch.bfloat16), B, H, W, idx.counts.data_ptr(), idx.F,
+                idx.pil_pix.data_ptr(), idx.pil_start.data_ptr(), idx.sorted_pt.data_ptr(), rows.data_ptr(), g_unet.data_ptr(),
+                int(dt == torch.bfloat16), idx.pil_cap, _stream(grad_h0)), "decoder_gather_backward_rows")
+            ctx.sink["gather"] = (rows, idx, B, H, W)
             return None, g_unet, None, None, None, None, None, None
         g_img = torch.empty((2 * B, H, W, 32), dtype=dt, device=grad_h0.device)
         check(_lib.lib().dfb_decoder_gather_backward(grad_h0.data_ptr(), int(grad_h0.dtype == torch.bfloat16), B, H, W,
@@ -339,12 +343,11 @@ class _DecoderGather(torch.autograd.Function):
         return g_img, g_unet, None, None, None, None, None, None
 
 
-def gather_backward_split(grad_h0, idx, B, H, W, g_img, g_unet, dt, accumulate):
-    """dfb_decoder_gather_backward_split: either output may be None; accumulate = add the image rows into g_img."""
-    check(_lib.lib().dfb_decoder_gather_backward_split(
-        grad_h0.data_ptr(), int(grad_h0.dtype == torch.bfloat16), B, H, W, idx.counts.data_ptr(), idx.F,
-        idx.pil_pix.data_ptr(), idx.pil_start.data_ptr(), idx.sorted_pt.data_ptr(), _ptr(g_img), _ptr(g_unet),
-        int(dt == torch.bfloat16), idx.pil_cap, int(accumulate), _stream(grad_h0)), "decoder_gather_backward_split")
+def gather_img_rows_add(rows, idx, B, H, W, g_img):
+    """dfb_gather_img_rows_add: g_img[2B,H,W,32] += the deferred image rows of the decoder gather's backward."""
+    check(_lib.lib().dfb_gather_img_rows_add(rows.data_ptr(), B, H, W, idx.counts.data_ptr(), idx.F, idx.pil_pix.data_ptr(),
+                                             g_img.data_ptr(), int(g_img.dtype == torch.bfloat16), idx.pil_cap,
+                                             _stream(g_img)), "gather_img_rows_add")
 
 
 def add_cat2(a0, b0, a1, b1):

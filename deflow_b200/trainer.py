@@ -41,6 +41,14 @@ class TrainStep:
         if self.overlap:
             self.grads.plan_early_slice(model)
         self.stat_sync = dd.enable_sync_bn(model) if self.sync_bn else None
+        # the UNet's weight gradients are unpacked once per step straight into the flat gradient buffer (conv.WeightBank);
+        # not with the overlapped all-reduce, whose hooks wait for per-parameter gradients
+        bb = getattr(model, "backbone", None)
+        if (bb is not None and hasattr(bb, "_weight_bank") and self.grads.flat.is_cuda and not self.overlap
+                and os.environ.get("DFB_DEFER_WGRAD", "1") != "0"):
+            views = {id(p): v for p, v in zip(self.grads.params, self.grads.views)}
+            bank = bb._weight_bank()
+            bank.enable_deferred_grads({id(w): views[id(w)] for w in bank.weights if id(w) in views})
 
     def __call__(self, batch) -> torch.Tensor:
         self.grads.zero()

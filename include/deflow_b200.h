@@ -206,13 +206,15 @@ int dfb_decoder_gather(const void* img, const void* unet, int in_bf16, int B, in
 int dfb_decoder_gather_backward(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
                                 const int* pil_pix, const int* pil_start, const int* sorted_pt, void* grad_img,
                                 void* grad_unet, int out_bf16, int pil_cap, void* stream);
-/* The same with either output optional: grad_img == NULL -> only the UNet gradient (dense); grad_unet == NULL -> only the
- * image rows, and with img_accumulate they are ADDED to an existing dense image gradient instead of being written into a
- * zero-filled one (the image part of the gather's backward is then applied after the other consumers of the pseudo-image
- * have produced their gradients: no dense zero-fill, no dense addition). */
-int dfb_decoder_gather_backward_split(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
-                                      const int* pil_pix, const int* pil_start, const int* sorted_pt, void* grad_img,
-                                      void* grad_unet, int out_bf16, int pil_cap, int img_accumulate, void* stream);
+/* The same with the image part deferred: the 64 image channels of every pc0 pillar's gradient sum go to the compact buffer
+ * img_rows f32[pil_cap][64] instead of a dense zero-filled image gradient (grad_unet stays dense); dfb_gather_img_rows_add adds
+ * them into the image gradient [2B,H,W,32] in place once the other consumers of the pseudo-image have produced theirs:
+ * no dense zero-fill, no dense addition. */
+int dfb_decoder_gather_backward_rows(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
+                                     const int* pil_pix, const int* pil_start, const int* sorted_pt, float* img_rows,
+                                     void* grad_unet, int out_bf16, int pil_cap, void* stream);
+int dfb_gather_img_rows_add(const float* img_rows, int B, int H, int W, const int* counts, int F, const int* pil_pix,
+                            void* grad_img, int out_bf16, int pil_cap, void* stream);
 /* out[0:half) = a0 + b0, out[half:2*half) = a1 + b1 (elementwise, bf16 or fp32; b0 = b1 = NULL: plain concatenation): the
  * gradient of the pseudo-image [2B,H,W,32] from the two consumers of each frame half in one pass. */
 int dfb_add_cat2(const void* a0, const void* b0, const void* a1, const void* b1, long long bytes_per_half, int bf16, void* out,
@@ -277,6 +279,16 @@ typedef struct dfb_pack_desc {
 } dfb_pack_desc;
 int dfb_conv_pack_weights_multi(const dfb_pack_desc* table_dev, int n_weights, long long total_elems, int split3,
                                 void* stream);
+/* The way back for the gradients: every weight gradient of a model from its [tap][cout][cin] accumulator (dfb_conv2d_wgrad
+ * with grad_w == NULL leaves it there; accumulate bit 1 = do not zero the accumulator first, so the two calls of a shared
+ * encoder weight and the three products of the split-precision mode sum in place) to the torch layout, in ONE launch. */
+typedef struct dfb_unpack_desc {
+  const float* wacc;     /* [k*k][cout][cin] fp32 */
+  float* grad;           /* [cout,cin,k,k] fp32 */
+  long long first;
+  int cout, cin, ksize, accumulate;   /* accumulate: grad += instead of grad = */
+} dfb_unpack_desc;
+int dfb_wgrad_unpack_multi(const dfb_unpack_desc* table_dev, int n_weights, long long total_elems, void* stream);
 /* fp32 x[n] -> hi = bf16(x), lo = bf16(x - hi): the operand pairs of the split-precision ("bf16x3") parity mode */
 int dfb_split_bf16x2(const float* x, long long n, void* hi, void* lo, void* stream);
 int dfb_conv2d(const dfb_conv_args* args, void* stream);

@@ -475,3 +475,31 @@ def test_fastflow3d_class_linear_decoder_fp32_parity():
         assert float(np.abs(res["flow"][b].detach().cpu().numpy() - fx[f"flow_{b}"]).max()) <= 2e-4
     loss = d.training_step_loss(gb, res, "ff3dLoss")
     assert abs(float(loss) - float(fx["loss_total"])) <= 2e-4 * max(1.0, abs(float(fx["loss_total"])))
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_deferred_weight_gradients_equal_per_launch_gradients(dt):
+    """conv.WeightBank.enable_deferred_grads (what TrainStep turns on): all weight gradients of the UNet left in one
+    accumulator and unpacked by ONE launch from an autograd-engine callback at the end of the backward -- equal to the
+    gradients returned launch by launch through autograd, for shared encoder weights, both precision modes, and a second
+    backward that accumulates."""
+    torch.manual_seed(5)
+    net = d.FastFlow3DUNet().to(DEV).train()
+    net.apply(d.weights_init)
+    net.compute_dtype = dt
+    a = (torch.randn(2, 64, 64, 32, device=DEV) * (torch.rand(2, 64, 64, 1, device=DEV) < 0.2)).to(dt)
+    b = (torch.randn(2, 64, 64, 32, device=DEV) * (torch.rand(2, 64, 64, 1, device=DEV) < 0.2)).to(dt)
+    g = torch.randn(2, 64, 64, 64, device=DEV).to(dt)
+    net.forward_nhwc(a, b).backward(g)
+    ref = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad(set_to_none=True)
+    net._weight_bank().enable_deferred_grads(None)
+    net.forward_nhwc(a, b).backward(g)
+    tol = 2e-2 if dt == torch.bfloat16 else 1e-4      # unordered fp32 atomics over bf16 products / split-precision sums
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        assert _rel(p.grad, ref[k]) <= tol, (k, _rel(p.grad, ref[k]))
+    net.forward_nhwc(a, b).backward(g)               # accumulates into the existing .grad tensors
+    for k, p in net.named_parameters():
+        if k.endswith("conv.weight") or (k.endswith(".weight") and p.dim() == 4):
+            assert _rel(p.grad, 2 * ref[k]) <= tol, k
