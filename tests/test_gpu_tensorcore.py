@@ -493,13 +493,20 @@ def test_deferred_weight_gradients_equal_per_launch_gradients(dt):
     net.forward_nhwc(a, b).backward(g)
     ref = {k: p.grad.clone() for k, p in net.named_parameters()}
     net.zero_grad(set_to_none=True)
+    net.forward_nhwc(a, b).backward(g)               # the same once more: run-to-run noise of the per-launch path itself
+    noise = max(_rel(p.grad, ref[k]) for k, p in net.named_parameters())
+    net.zero_grad(set_to_none=True)
     net._weight_bank().enable_deferred_grads(None)
     net.forward_nhwc(a, b).backward(g)
-    tol = 2e-2 if dt == torch.bfloat16 else 1e-4      # unordered fp32 atomics over bf16 products / split-precision sums
+    # the split-precision mode pins the mechanism (1e-4); with bf16 operands the backward is not reproducible run to run
+    # (bf16 rounding of the BatchNorm-backward output flips with the unordered statistics sums), so the bound is the
+    # measured noise of the per-launch path
+    tol = 1e-4 if dt == torch.float32 else max(3 * noise, 2e-3)
+    print(f"deferred weight gradients {dt}: run-to-run noise of the per-launch path {noise:.2e}")
     for k, p in net.named_parameters():
         assert p.grad is not None, k
-        assert _rel(p.grad, ref[k]) <= tol, (k, _rel(p.grad, ref[k]))
+        assert _rel(p.grad, ref[k]) <= tol, (k, _rel(p.grad, ref[k]), noise)
     net.forward_nhwc(a, b).backward(g)               # accumulates into the existing .grad tensors
     for k, p in net.named_parameters():
-        if k.endswith("conv.weight") or (k.endswith(".weight") and p.dim() == 4):
-            assert _rel(p.grad, 2 * ref[k]) <= tol, k
+        if p.dim() == 4:
+            assert _rel(p.grad, 2 * ref[k]) <= tol, (k, _rel(p.grad, 2 * ref[k]))
