@@ -1567,6 +1567,17 @@ static int launch_wgrad(const WgradMaps& maps, const WgradParams& P, cudaStream_
 }  // namespace tc
 }  // namespace dfb
 
+// CTAs per weight-gradient launch = wgrad_cta_target() (default 2 per SM; DFB_WGRAD_CTAS_X10 = tenths of CTAs per SM, A/B sweeps)
+static int wgrad_cta_target() {
+  static int x10 = -1;
+  if (x10 < 0) {
+    const char* e = getenv("DFB_WGRAD_CTAS_X10");
+    x10 = e ? atoi(e) : 20;
+    if (x10 < 5 || x10 > 80) x10 = 20;
+  }
+  return (x10 * dfb::sm_count() + 5) / 10;
+}
+
 static bool halo_wgrad_enabled() {
   static int mode = -1;
   if (mode < 0) {
@@ -1634,7 +1645,7 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
         X.n_img = a->n; X.Ht = Ho; X.Wt = Wo;
         X.tiles_x = (Wo + 7) / 8; X.tiles_y = (Ho + 7) / 8;
         X.num_tiles = X.tiles_x * X.tiles_y * a->n;
-        int splits = (2 * sm_count() + ni - 1) / ni;
+        int splits = (wgrad_cta_target() + ni - 1) / ni;
         if (splits > X.num_tiles) splits = X.num_tiles;
         if (splits < 1) splits = 1;
         X.splits = splits;
@@ -1696,7 +1707,7 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
     {
       int wsum = 0, blk = 0;
       for (int k = 0; k < ni; ++k) wsum += Q.items[k].npairs;
-      const int target = 2 * sm_count();
+      const int target = wgrad_cta_target();
       for (int k = 0; k < ni; ++k) {
         int ns = (target * Q.items[k].npairs + wsum / 2) / wsum;
         if (ns > Q.num_tiles) ns = Q.num_tiles;
@@ -1762,7 +1773,7 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
   P.n_img = a->n; P.Ht = Ho; P.Wt = Wo;
   P.tiles_x = (Wo + 7) / 8; P.tiles_y = (Ho + 7) / 8;
   P.num_tiles = P.tiles_x * P.tiles_y * a->n;
-  int splits = (2 * sm_count() + P.n_pairs - 1) / P.n_pairs;
+  int splits = (wgrad_cta_target() + P.n_pairs - 1) / P.n_pairs;
   if (splits > P.num_tiles) splits = P.num_tiles;
   if (splits < 1) splits = 1;
   P.splits = splits;
