@@ -23,7 +23,8 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CANDIDATES = ["/root/reference/OpenSceneFlow", os.path.join(HERE, "_ref", "osf")]
+# the staged copy first: what runs on the GPU box (where /root/reference does not exist) is then also what runs here
+CANDIDATES = [os.path.join(HERE, "_ref", "osf"), "/root/reference/OpenSceneFlow"]
 
 
 def root():
