@@ -1567,13 +1567,16 @@ static int launch_wgrad(const WgradMaps& maps, const WgradParams& P, cudaStream_
 }  // namespace tc
 }  // namespace dfb
 
-// CTAs per weight-gradient launch = wgrad_cta_target() (default 2 per SM; DFB_WGRAD_CTAS_X10 = tenths of CTAs per SM, A/B sweeps)
+// CTAs per weight-gradient launch = wgrad_cta_target(): ONE per SM.  These kernels hold one CTA per SM (shared memory), so a
+// larger split-K only serialises in waves and multiplies the red.global.add traffic: measured on B200 (r02 visit 12, whole
+// step) 30.22 ms at 1 CTA / SM against 31.16 / 30.72 / 30.94 / 31.36 ms at 1.5 / 2 / 3 / 4.  DFB_WGRAD_CTAS_X10 = tenths of
+// CTAs per SM for sweeps.
 static int wgrad_cta_target() {
   static int x10 = -1;
   if (x10 < 0) {
     const char* e = getenv("DFB_WGRAD_CTAS_X10");
-    x10 = e ? atoi(e) : 20;
-    if (x10 < 5 || x10 > 80) x10 = 20;
+    x10 = e ? atoi(e) : 10;
+    if (x10 < 5 || x10 > 80) x10 = 10;
   }
   return (x10 * dfb::sm_count() + 5) / 10;
 }
@@ -1645,7 +1648,7 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
         X.n_img = a->n; X.Ht = Ho; X.Wt = Wo;
         X.tiles_x = (Wo + 7) / 8; X.tiles_y = (Ho + 7) / 8;
         X.num_tiles = X.tiles_x * X.tiles_y * a->n;
-        int splits = (wgrad_cta_target() + ni - 1) / ni;
+        int splits = wgrad_cta_target() / ni;        // floor: never more CTAs than the target (a single wave at the default)
         if (splits > X.num_tiles) splits = X.num_tiles;
         if (splits < 1) splits = 1;
         X.splits = splits;
@@ -1708,13 +1711,26 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
       int wsum = 0, blk = 0;
       for (int k = 0; k < ni; ++k) wsum += Q.items[k].npairs;
       const int target = wgrad_cta_target();
+      int nsv[tc::WH_MAX_ITEMS];
       for (int k = 0; k < ni; ++k) {
         int ns = (target * Q.items[k].npairs + wsum / 2) / wsum;
         if (ns > Q.num_tiles) ns = Q.num_tiles;
         if (ns < 1) ns = 1;
-        Q.items[k].blk0 = (int16_t)blk;
-        Q.items[k].nsplit = (int16_t)ns;
+        nsv[k] = ns;
         blk += ns;
+      }
+      // rounding must not push the launch past the target (one CTA per SM: a second, nearly empty wave costs a whole wave)
+      while (blk > target) {
+        int big = 0;
+        for (int k = 1; k < ni; ++k) if (nsv[k] > nsv[big]) big = k;
+        if (nsv[big] <= 1) break;
+        --nsv[big]; --blk;
+      }
+      blk = 0;
+      for (int k = 0; k < ni; ++k) {
+        Q.items[k].blk0 = (int16_t)blk;
+        Q.items[k].nsplit = (int16_t)nsv[k];
+        blk += nsv[k];
       }
       Q.splits = blk;   // total CTAs
     }
@@ -1773,7 +1789,7 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
   P.n_img = a->n; P.Ht = Ho; P.Wt = Wo;
   P.tiles_x = (Wo + 7) / 8; P.tiles_y = (Ho + 7) / 8;
   P.num_tiles = P.tiles_x * P.tiles_y * a->n;
-  int splits = (wgrad_cta_target() + P.n_pairs - 1) / P.n_pairs;
+  int splits = wgrad_cta_target() / P.n_pairs;   // floor: a single wave at the default target of one CTA per SM
   if (splits > P.num_tiles) splits = P.num_tiles;
   if (splits < 1) splits = 1;
   P.splits = splits;
