@@ -64,7 +64,7 @@ class ConvArgs(C.Structure):
                 ("cin_total", C.c_int), ("cin_off", C.c_int), ("cout", C.c_int), ("w", C.c_void_p),
                 ("bias", C.c_void_p), ("y", C.c_void_p), ("y_fp32", C.c_int), ("stats", C.c_void_p),
                 ("x_lo", C.c_void_p * 2), ("split3", C.c_int), ("stats_sum_only", C.c_int),
-                ("y2", C.c_void_p), ("cin2", C.c_int)]
+                ("y2", C.c_void_p), ("cin2", C.c_int), ("grad_bias", C.c_void_p)]
 
 
 class PackDesc(C.Structure):

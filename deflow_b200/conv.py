@@ -227,11 +227,14 @@ def bias_grad(gy: torch.Tensor) -> torch.Tensor:
 
 
 def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, grad_w: Optional[torch.Tensor] = None,
-                 wacc_slot: Optional[torch.Tensor] = None):
+                 wacc_slot: Optional[torch.Tensor] = None, grad_bias: Optional[torch.Tensor] = None):
     """-> grad_w fp32 in torch layout [cout, sum(c_i), k, k].  wacc_slot: a [k*k, cout, cin] fp32 accumulator of a
     WeightBank with deferred gradients -- the result is ADDED there and nothing is returned (the bank unpacks all of its
-    weight gradients with one launch at the end of the backward pass)."""
+    weight gradients with one launch at the end of the backward pass).  grad_bias: fp32 [cout], += the per-channel sums
+    of gy from the same launch (1x1 layers with an odd number of 64-channel input groups: the gate / head matrices of the
+    point decoder, 128 + 64 inputs)."""
     if gy.dtype == torch.float32:
+        assert grad_bias is None
         # split precision: x_hi*gy_hi + x_hi*gy_lo + x_lo*gy_hi accumulated into the same fp32 gradient
         pairs = [split(x) for x in xs]
         gh, gl = split(gy)
@@ -254,6 +257,9 @@ def conv2d_wgrad(xs: Sequence[torch.Tensor], gy: torch.Tensor, ksize, stride, gr
         if grad_w is None:
             grad_w = torch.empty((cout, ct, ksize, ksize), dtype=torch.float32, device=gy.device)
     a = _args(0, n, H, W, ksize, stride, xs, cins, cout, None, None, gy, None)
+    if grad_bias is not None:
+        assert grad_bias.dtype == torch.float32 and grad_bias.numel() == cout and grad_bias.is_contiguous()
+        a.grad_bias = grad_bias.data_ptr()
     ncol = max(cout, 64)
     name = f"k_conv_wgrad_halo<{ncol}>" if (ksize == 3 and stride == 1) else f"k_conv_wgrad<{ncol}>"
     if ksize == 3 and stride == 1 and cout == 64 and sum((c + 63) // 64 for c in cins) <= 8 \

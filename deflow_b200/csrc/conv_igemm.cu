@@ -71,6 +71,7 @@ struct IgemmMaps {
   CUtensorMap b;
   CUtensorMap out;   // bf16 output as [ch, x, y, n] with box [32, 8, 4, 1], SWIZZLE_64B (epilogue TMA stores)
   CUtensorMap out2;  // second output of a split data-gradient launch (accumulator columns >= split_col); follows `out`
+  CUtensorMap out3, out4;  // parity-merged stride-2 data gradient: out, out2, out3, out4 = the four parity planes of gx
 };
 
 struct IgemmParams {
@@ -93,6 +94,14 @@ struct IgemmParams {
   int tap_k_stride;    // K distance between consecutive taps in the packed weights
   int w_resident;      // all 9 * nsteps weight tiles fit the ring: load them once
   int dbg_base_offset; // descriptor base-offset field = (start >> 7) & 7 (experiment switch)
+  // parity-merged stride-2 data gradient (k_conv_igemm only): work item = (region tile, parity plane of gx); the K steps
+  // of plane p are steps[seg[p] .. seg[p+1]), its output map is (&maps.out)[p]; num_tiles counts items (4 x region tiles)
+  int par_mode;
+  int16_t seg[5];
+  // k_conv_igemm only.  wide: the epilogue stores 64-channel (128-byte) rows, box [64, 8, 4, 1] SWIZZLE_128B, half as
+  // many TMA requests per tile.  b_resident: all nsteps weight tiles are loaded ONCE into the tail of the stage ring
+  // (the ring keeps ring_stages stages and moves A tiles only) instead of once per tile and K step.
+  int wide, b_resident, ring_stages;
   KStep steps[MAX_STEPS];
 };
 
@@ -112,6 +121,18 @@ constexpr int EPI_SMEM = EPI_WARPS * EPI_STAGE_BYTES;
 // PAIR (k_conv_igemm_halo_pair): the N = 128 accumulator columns are two 64-channel halves; lane (r, c) holds output
 // pixel (2r, c) of a 32 x 8 tile in columns 0..63 and pixel (2r + 1, c) in columns 64..127.  The output tensor map is
 // then 5-D [ch, x, row parity, row / 2, n] and a store box is [32 ch, 8, 1, 4, 1].
+// Parity-merged launches: item w = blockIdx.x + i * gridDim.x covers region tile w / 4 and parity plane ((w & 3) + i) & 3.
+// The grid is a multiple of 4, so the four items of a region share i: their planes are a permutation of 0..3 (every
+// (region, plane) exactly once), four neighbouring CTAs work on the four planes of one region at the same time (their
+// interleaved 64-byte stores meet in L2 and leave as full lines, gy is fetched from DRAM once), and every CTA cycles
+// through the planes, whose K loops differ in length (1, 2, 2, 4 taps of a 3x3 kernel).
+__device__ __forceinline__ int par_decode(const IgemmParams& P, int& tile) {
+  if (!P.par_mode) return 0;
+  const int par = ((tile & 3) + tile / (int)gridDim.x) & 3;
+  tile >>= 2;
+  return par;
+}
+
 template <int N, bool PAIR = false>
 __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUtensorMap* out_map, uint32_t tmem_base,
                                                uint64_t* acc_full, uint64_t* acc_empty, float* s_stats,
@@ -128,7 +149,9 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
   bool store_pending = false;
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+  for (int item = blockIdx.x; item < P.num_tiles; item += gridDim.x) {
+    int tile = item;
+    const int par = PAIR ? 0 : par_decode(P, tile);
     const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
     const int y0 = PAIR ? ty * 2 * TILE_H + 2 * r : ty * TILE_H + r, x = tx * TILE_W + c;
     const long long off0 = (long long)n * P.out_img + (long long)(y0 * P.sy + P.oy) * P.out_row +
@@ -200,11 +223,117 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
         __syncwarp();
         if (lane == 0) {
           if (PAIR) tma_store_5d(out_map, stg, ch0, tx * TILE_W, half, ty * TILE_H + 4 * q, n);
-          else tma_store_4d(second ? out_map + 1 : out_map, stg, oc0, tx * TILE_W, ty * TILE_H + 4 * q, n);
+          else tma_store_4d(second ? out_map + 1 : out_map + par, stg, oc0, tx * TILE_W, ty * TILE_H + 4 * q, n);
           tma_store_commit();
         }
         store_pending = true;
       }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+  if (lane == 0) tma_store_wait_all();
+}
+
+// The same epilogue with 64-channel stores (k_conv_igemm, N a multiple of 64, bf16 output).  Measured on the general
+// kernels (r02 launch lists): a tile costs ~3.5-4 cycles per TMA request -- one request per box row, 64-byte rows cost what
+// 128-byte rows cost -- so the layers with one or two K steps per tile were bound by the NUMBER of requests, and half of
+// those were the 32-channel store rows.  A warp takes 64 accumulator columns (two tcgen05.ld), takes the statistics of
+// both halves through the slab first (it aliases the staging tile), then writes its 32 pixel rows of 128 bytes with the
+// 128-byte swizzle and issues ONE store of the [64 ch x 8 x 4] box.
+constexpr int EPI_STAGE_BYTES_WIDE = 4096;
+constexpr int EPI_SMEM_WIDE = EPI_WARPS * EPI_STAGE_BYTES_WIDE;
+
+template <int N, bool PAIR = false>
+__device__ __forceinline__ void igemm_epilogue_wide(const IgemmParams& P, const CUtensorMap* out_map, uint32_t tmem_base,
+                                                    uint64_t* acc_full, uint64_t* acc_empty, float* s_stats,
+                                                    const float* s_bias, uint8_t* stage_all, int warp, int lane) {
+  const int q = warp & 3;
+  const int cg = (warp - 2) >> 2;
+  const int m = q * 32 + lane;
+  const int r = m >> 3, c = m & 7;
+  uint8_t* stg = stage_all + (warp - 2) * EPI_STAGE_BYTES_WIDE;
+  float* slab = reinterpret_cast<float*>(stg);
+  const int sw16 = (lane >> 1) & 15;
+  const int sw8 = lane & 7;                 // 128-byte TMA swizzle of this lane's row
+  const int rcol = lane & 15, rpar = lane >> 4;
+  bool store_pending = false;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int item = blockIdx.x; item < P.num_tiles; item += gridDim.x) {
+    int tile = item;
+    const int par = PAIR ? 0 : par_decode(P, tile);
+    const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
+    const int y0 = PAIR ? ty * 2 * TILE_H + 2 * r : ty * TILE_H + r, x = tx * TILE_W + c;
+    mbar_wait(&acc_full[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int col = 64 * cg; col < N; col += 64 * (EPI_WARPS / 4)) {
+      // PAIR: N = 128 accumulator columns = two output rows x 64 channels; a 64-column block is one row parity
+      const int half = PAIR ? col / 64 : 0;
+      const int ch0 = PAIR ? 0 : col;                    // channel index for bias / statistics
+      const bool second = !PAIR && P.split_col > 0 && col >= P.split_col;
+      const int oc0 = second ? col - P.split_col : ch0;
+      const bool valid = y0 + half < P.Ht && x < P.Wt;
+      uint32_t pk[32];                     // the row's 64 channels as packed bf16 pairs
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {     // one tcgen05.ld of 32 columns at a time: 32 fp32 + 16 packed registers live
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + col + 32 * hh, v);
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch0 + 32 * hh + i);
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        }
+        if (hh == 0 && store_pending) {    // the previous TMA store must have read the tile before the slab reuses it
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          store_pending = false;
+        }
+        if (P.stats) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) slab[lane * 16 + (i ^ sw16)] = valid ? v[h * 16 + i] : 0.f;
+            __syncwarp();
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float t = slab[(2 * i + rpar) * 16 + (rcol ^ i)];
+              s1 += t;
+              s2 = fmaf(t, t, s2);
+            }
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+            if (lane < 16) {
+              atomicAdd(&s_stats[ch0 + 32 * hh + h * 16 + lane], s1);
+              if (!P.stats_sum_only) atomicAdd(&s_stats[(PAIR ? N / 2 : N) + ch0 + 32 * hh + h * 16 + lane], s2);
+            }
+            __syncwarp();
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          pk[16 * hh + i] = *reinterpret_cast<const unsigned*>(&p2);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((i ^ sw8) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) tma_store_5d(out_map, stg, 0, tx * TILE_W, half, ty * TILE_H + 4 * q, n);
+        else tma_store_4d(second ? out_map + 1 : out_map + par, stg, oc0, tx * TILE_W, ty * TILE_H + 4 * q, n);
+        tma_store_commit();
+      }
+      store_pending = true;
     }
     tc_fence_before();
     __syncwarp();
@@ -220,10 +349,10 @@ struct IgemmCfg {
   static constexpr int A_BYTES = TILE_M * KC * 2;
   static constexpr int B_BYTES = N * KC * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int BUDGET = 190 * 1024;          // operand tiles: a ring of [A | B] stages, or (b_resident) A ring + all B tiles
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_SMEM + 1024 /*alignment slack*/ + 256 /*barriers*/ + 3 * N * 4 + 64;
+  static constexpr int SMEM = BUDGET + EPI_SMEM_WIDE + 1024 /*alignment slack*/ + 256 /*barriers*/ + 3 * N * 4 + 64;
   static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
   static constexpr int SWIZZLE = KC * 2;             // bytes per pixel row: 128 or 64
   static constexpr int LAYOUT = KC == 64 ? 2 : 4;    // UMMA layout type
@@ -237,15 +366,20 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;  // [STAGES][A | B], every tile 1024-byte aligned (A_BYTES, B_BYTES are multiples of 1024)
-  uint8_t* epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;   // 1024-aligned (stage sizes are multiples of 1024)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_SMEM);
+  uint8_t* epi_stage = smem + Cfg::BUDGET;   // 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_SMEM_WIDE);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
   uint64_t* acc_full = bars + 2 * Cfg::STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_stats = reinterpret_cast<float*>(epi_stage + EPI_SMEM + 256);  // [2][N]
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // resident weights have landed
+  float* s_stats = reinterpret_cast<float*>(epi_stage + EPI_SMEM_WIDE + 256);  // [2][N]
   float* s_bias = s_stats + 2 * N;                                         // [N]
+  // b_resident: the ring holds A tiles only (ring_stages of them), the nsteps weight tiles sit behind it
+  const int ring = P.b_resident ? P.ring_stages : Cfg::STAGES;
+  const int ring_stride = P.b_resident ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
+  uint8_t* b_res = tiles + ring * Cfg::A_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -254,6 +388,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
     tma_prefetch_desc(&maps.b);
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -269,18 +404,25 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      if (P.b_resident) {
+        mbar_arrive_expect_tx(b_full, (uint32_t)(P.nsteps * Cfg::B_BYTES));
+        for (int s = 0; s < P.nsteps; ++s) tma_load_2d(b_res + s * Cfg::B_BYTES, &maps.b, b_full, P.steps[s].wk, 0);
+      }
+      for (int item = blockIdx.x; item < P.num_tiles; item += gridDim.x) {
+        int tile = item;
+        const int par = par_decode(P, tile);
+        const int s0 = P.par_mode ? P.seg[par] : 0, s1 = P.par_mode ? P.seg[par + 1] : P.nsteps;
         const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
         const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-        for (int s = 0; s < P.nsteps; ++s) {
+        for (int s = s0; s < s1; ++s) {
           const KStep st = P.steps[s];
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* a_dst = tiles + stage * Cfg::STAGE_BYTES;
+          uint8_t* a_dst = tiles + stage * ring_stride;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[stage], P.b_resident ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
           tma_load_4d(a_dst, &maps.a[st.map], &full[stage], st.c0, x0 + st.dx, y0 + st.dy, n);
-          tma_load_2d(b_dst, &maps.b, &full[stage], st.wk, 0);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (!P.b_resident) tma_load_2d(b_dst, &maps.b, &full[stage], st.wk, 0);
+          if (++stage == ring) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -290,22 +432,29 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, N, 0, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      if (P.b_resident) {
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+      }
+      for (int item = blockIdx.x; item < P.num_tiles; item += gridDim.x) {
+        int tile = item;
+        const int par = par_decode(P, tile);
+        const int s0 = P.par_mode ? P.seg[par] : 0, s1 = P.par_mode ? P.seg[par + 1] : P.nsteps;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * N;
-        for (int s = 0; s < P.nsteps; ++s) {
+        for (int s = s0; s < s1; ++s) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint32_t a_addr = smem_u32(tiles + stage * ring_stride);
+          const uint32_t b_addr = P.b_resident ? smem_u32(b_res + s * Cfg::B_BYTES) : a_addr + Cfg::A_BYTES;
           const uint64_t adesc = make_smem_desc(a_addr, 16, Cfg::SBO, Cfg::LAYOUT);
           const uint64_t bdesc = make_smem_desc(b_addr, 16, Cfg::SBO, Cfg::LAYOUT);
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k)  // +32 bytes (2 x 16 B) along K per UMMA_K = 16 bf16
-            umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+            umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, ((s - s0) | k) != 0);
           umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == ring) { stage = 0; phase ^= 1; }
         }
         umma_commit(&acc_full[acc]);
         acc ^= 1;
@@ -313,7 +462,12 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
       }
     }
   } else {
-    igemm_epilogue<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+    if constexpr (N % 64 == 0) {
+      if (P.wide) igemm_epilogue_wide<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+      else igemm_epilogue<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+    } else {
+      igemm_epilogue<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+    }
   }
 
   tc_fence_before();
@@ -486,28 +640,35 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
 // into one half of the accumulator).  Per 64-channel chunk and kx: 2 x N=128 + 2 x N=64 MMA groups instead of 6 x N=64
 // for the same 256 pixels.  Weight slot p of a kx triple holds ky = 2 - p (forward) or ky = p (data gradient, flipped
 // taps), so that hy = 1 reads slots (1, 2), hy = 2 slots (0, 1), hy = 0 slot 2 and hy = 3 slot 0 in both directions.
-struct HaloPairCfg {
+// WIDE: 64-channel epilogue stores (igemm_epilogue_wide: one 128-byte row per output pixel instead of two 64-byte ones);
+// the 16 KB of extra staging come out of the weight ring (four kx triples instead of five; the nine taps of a
+// single-chunk layer still stay resident).
+template <bool WIDE>
+struct HaloPairCfgT {
   static constexpr int N = 64;                                     // output channels
   static constexpr int ROWS = 2 * TILE_H + 2;                      // 34 halo rows
   static constexpr int HALO_BYTES = 43 * 1024;                     // 34 x 10 pixels x 128 B = 43520, 1024-aligned
   static constexpr int W_BYTES = N * 128;                          // one tap x one 64-channel chunk
   static constexpr int HALO_STAGES = 2;
-  static constexpr int W_STAGES = 15;                              // five kx triples
+  static constexpr int W_STAGES = WIDE ? 12 : 15;                  // kx triples
+  static constexpr int EPI_BYTES = WIDE ? EPI_SMEM_WIDE : EPI_SMEM;
   static constexpr int TILE_BYTES = HALO_STAGES * HALO_BYTES + W_STAGES * W_BYTES;
-  static constexpr int SMEM = TILE_BYTES + EPI_SMEM + 1024 + 512 + 3 * N * 4;
+  static constexpr int SMEM = TILE_BYTES + EPI_BYTES + 1024 + 512 + 3 * N * 4;
   static constexpr int TMEM_COLS = 4 * N;                          // two accumulators of 2 x 64 columns
 };
+using HaloPairCfg = HaloPairCfgT<false>;
 
+template <bool WIDE>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo_pair(const __grid_constant__ IgemmMaps maps,
                                                                            const __grid_constant__ IgemmParams P) {
-  using Cfg = HaloPairCfg;
+  using Cfg = HaloPairCfgT<WIDE>;
   constexpr int N = Cfg::N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* halos = smem;
   uint8_t* wts = smem + Cfg::HALO_STAGES * Cfg::HALO_BYTES;
   uint8_t* epi_stage = smem + Cfg::TILE_BYTES;              // 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_SMEM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_BYTES);
   uint64_t* h_full = bars;                                  // [HALO_STAGES]
   uint64_t* h_empty = h_full + Cfg::HALO_STAGES;            // [HALO_STAGES]
   uint64_t* w_full = h_empty + Cfg::HALO_STAGES;            // [W_STAGES]
@@ -515,7 +676,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo_pair(const
   uint64_t* acc_full = w_empty + Cfg::W_STAGES;             // [2]
   uint64_t* acc_empty = acc_full + 2;                       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_stats = reinterpret_cast<float*>(epi_stage + EPI_SMEM + 512);
+  float* s_stats = reinterpret_cast<float*>(epi_stage + Cfg::EPI_BYTES + 512);
   float* s_bias = s_stats + 2 * N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t halo_tx = (uint32_t)Cfg::ROWS * (uint32_t)P.halo_pitch * 128u;
@@ -623,7 +784,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo_pair(const
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    igemm_epilogue<2 * N, true>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+    if constexpr (WIDE) igemm_epilogue_wide<2 * N, true>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+    else igemm_epilogue<2 * N, true>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
   }
 
   tc_fence_before();
@@ -635,20 +797,21 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo_pair(const
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// bf16 output of the row-pair kernel as [ch, x, row parity, row / 2, n], box [32, 8, 1, 4, 1], SWIZZLE_64B
-static int build_out_map_pair(IgemmMaps& maps, const IgemmParams& P, int N) {
+// bf16 output of the row-pair kernel as [ch, x, row parity, row / 2, n], box [32 (wide: 64), 8, 1, 4, 1], SWIZZLE_64B (128B)
+static int build_out_map_pair(IgemmMaps& maps, const IgemmParams& P, int N, bool wide) {
   const uint64_t dims[5] = {(uint64_t)N, (uint64_t)P.Wt, 2, (uint64_t)P.Ht / 2, (uint64_t)P.n_img};
   const uint64_t str[4] = {(uint64_t)P.out_pix * 2, (uint64_t)P.out_row * 2, (uint64_t)P.out_row * 4, (uint64_t)P.out_img * 2};
-  const uint32_t box[5] = {32, TILE_W, 1, 4, 1};
-  return make_tensor_map_bf16(&maps.out, P.out, 5, dims, str, box, 64);
+  const uint32_t box[5] = {wide ? 64u : 32u, TILE_W, 1, 4, 1};
+  return make_tensor_map_bf16(&maps.out, P.out, 5, dims, str, box, wide ? 128 : 64);
 }
 
-static int launch_igemm_halo_pair(IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
-  using Cfg = HaloPairCfg;
-  if (int rc = build_out_map_pair(maps, P, Cfg::N)) return rc;
+template <bool WIDE>
+static int launch_igemm_halo_pair_t(IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
+  using Cfg = HaloPairCfgT<WIDE>;
+  if (int rc = build_out_map_pair(maps, P, Cfg::N, WIDE)) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_igemm_halo_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_igemm_halo_pair<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) { set_error("igemm_halo_pair: cannot reserve %d bytes of shared memory: %s", Cfg::SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     configured = true;
   }
@@ -657,9 +820,16 @@ static int launch_igemm_halo_pair(IgemmMaps& maps, IgemmParams& P, cudaStream_t 
   P.w_resident = (9 * P.nsteps <= Cfg::W_STAGES) ? 1 : 0;
   int grid = sm_count();
   if (grid > P.num_tiles) grid = P.num_tiles;
-  k_conv_igemm_halo_pair<<<grid, IGEMM_THREADS, Cfg::SMEM, st>>>(maps, P);
+  k_conv_igemm_halo_pair<WIDE><<<grid, IGEMM_THREADS, Cfg::SMEM, st>>>(maps, P);
   add_launches(1);
   return check_launch("conv_igemm_halo_pair");
+}
+
+// DFB_PAIR_WIDE=1: 64-channel epilogue stores in the row-pair kernel (read per call; A/B)
+static int launch_igemm_halo_pair(IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
+  const char* e = getenv("DFB_PAIR_WIDE");
+  if (e && atoi(e) != 0) return launch_igemm_halo_pair_t<true>(maps, P, st);
+  return launch_igemm_halo_pair_t<false>(maps, P, st);
 }
 
 // DFB_HALO_PAIR=0 keeps the 64-channel layers on k_conv_igemm_halo<64> (A/B comparisons); default = row-pair kernel
@@ -672,20 +842,32 @@ static bool halo_pair_enabled() {
   return mode != 0;
 }
 
+// k_conv_igemm A/B switches (read per call; tests toggle them): DFB_EPI_WIDE=0 -> 32-channel epilogue stores,
+// DFB_IGEMM_B_RESIDENT=0 -> weight tiles re-loaded with every A tile.
+static bool env_on(const char* name) {
+  const char* e = getenv(name);
+  return !(e && atoi(e) == 0);
+}
+static bool igemm_wide(const IgemmParams& P, int N) {
+  return !P.out_fp32 && N % 64 == 0 && P.split_col % 64 == 0 && P.halo_pitch == 0 && env_on("DFB_EPI_WIDE");
+}
+static bool igemm_resident_enabled() { return env_on("DFB_IGEMM_B_RESIDENT"); }
+
 // Output tensor map of a launch: element (n, y, x, ch) of the tile space lives at
 // out + n*img + (y*sy+oy)*row + (x*sx+ox)*pix + ch  (bf16) -> dims [ch, x, y, n], box [32, 8, 4, 1], SWIZZLE_64B.
 static int build_out_map(IgemmMaps& maps, const IgemmParams& P, int N) {
   if (P.out_fp32) return DFB_OK;
   const uint64_t dims[4] = {(uint64_t)(P.split_col > 0 ? P.split_col : N), (uint64_t)P.Wt, (uint64_t)P.Ht, (uint64_t)P.n_img};
   const uint64_t str[3] = {(uint64_t)P.out_pix * P.sx * 2, (uint64_t)P.out_row * P.sy * 2, (uint64_t)P.out_img * 2};
-  const uint32_t box[4] = {32, TILE_W, 4, 1};
+  const uint32_t box[4] = {P.wide ? 64u : 32u, TILE_W, 4, 1};
+  const int swz = P.wide ? 128 : 64;
   const char* base = (const char*)P.out + ((size_t)P.oy * P.out_row + (size_t)P.ox * P.out_pix) * 2;
-  if (int rc = make_tensor_map_bf16(&maps.out, base, 4, dims, str, box, 64)) return rc;
+  if (int rc = make_tensor_map_bf16(&maps.out, base, 4, dims, str, box, swz)) return rc;
   if (P.split_col > 0) {   // second output: the remaining N - split_col channels, densely packed NHWC
     const uint64_t c2 = (uint64_t)(N - P.split_col);
     const uint64_t d2[4] = {c2, (uint64_t)P.Wt, (uint64_t)P.Ht, (uint64_t)P.n_img};
     const uint64_t s2[3] = {c2 * 2, c2 * 2 * P.Wt, c2 * 2 * P.Wt * P.Ht};
-    return make_tensor_map_bf16(&maps.out2, P.out2, 4, d2, s2, box, 64);
+    return make_tensor_map_bf16(&maps.out2, P.out2, 4, d2, s2, box, swz);
   }
   return DFB_OK;
 }
@@ -721,6 +903,12 @@ static int dispatch_igemm_halo(int N, IgemmMaps& maps, IgemmParams& P, cudaStrea
 // Measured on B200 (tools/diag_conv.py): descriptors that start at a 128-byte (non-1024-byte) boundary read the
 // TMA-written swizzle correctly with the base-offset field left at 0, for both 1280- and 2048-byte group strides;
 // setting base-offset = (start >> 7) & 7 gives wrong results -- the swizzle XOR is taken from the absolute address.
+// DFB_DGRAD_PAR_MERGE=0: the stride-2 data gradient as four launches, one per parity plane (A/B); default = one launch.
+static bool par_merge_enabled() {
+  const char* e = getenv("DFB_DGRAD_PAR_MERGE");   // read per call (six launches per step): tests toggle it
+  return !(e && atoi(e) == 0);
+}
+
 static int halo_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -817,7 +1005,19 @@ __global__ void __launch_bounds__(256) k_split_bf16x2(const float4* __restrict__
 template <int N, int KC>
 static int launch_igemm(IgemmMaps& maps, const IgemmParams& P, cudaStream_t st) {
   using Cfg = IgemmCfg<N, KC>;
-  if (int rc = build_out_map(maps, P, N)) return rc;
+  IgemmParams Q = P;
+  Q.wide = igemm_wide(Q, N) ? 1 : 0;
+  if (!Q.par_mode) {   // (parity-merged launches come with their four output maps built)
+    if (int rc = build_out_map(maps, Q, N)) return rc;
+  }
+  Q.b_resident = 0;
+  Q.ring_stages = Cfg::STAGES;
+  if (!Q.out_fp32 && igemm_resident_enabled()) {
+    // weights once per CTA instead of once per tile and K step, when they leave room for >= 3 A tiles in the ring
+    const int res = Q.nsteps * Cfg::B_BYTES;
+    const int ring = (Cfg::BUDGET - res) / Cfg::A_BYTES;
+    if (res < Cfg::BUDGET && ring >= 3) { Q.b_resident = 1; Q.ring_stages = ring > Cfg::STAGES ? Cfg::STAGES : ring; }
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_igemm<N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -826,7 +1026,8 @@ static int launch_igemm(IgemmMaps& maps, const IgemmParams& P, cudaStream_t st) 
   }
   int grid = sm_count();
   if (grid > P.num_tiles) grid = P.num_tiles;
-  k_conv_igemm<N, KC><<<grid, IGEMM_THREADS, Cfg::SMEM, st>>>(maps, P);
+  if (Q.par_mode) grid &= ~3;   // par_decode: the four parity planes of a region must share the iteration index
+  k_conv_igemm<N, KC><<<grid, IGEMM_THREADS, Cfg::SMEM, st>>>(maps, Q);
   add_launches(1);
   return check_launch("conv_igemm");
 }
@@ -1083,6 +1284,40 @@ extern "C" int dfb_conv2d(const dfb_conv_args* a, void* stream_) {
     // stride 2: input row i = 2a + py receives from output rows o with 2o + ky - 1 = i:
     //   py = 0: ky = 1, o = a;      py = 1: ky = 0, o = a + 1  and  ky = 2, o = a.   One launch per parity plane.
     if (H % 2 || W % 2) { set_error("dfb_conv2d dgrad: stride-2 needs even H, W"); return DFB_ERR_UNSUPPORTED; }
+    if (k == 3 && !S3 && !a->y_fp32 && par_merge_enabled()) {
+      // all four parity planes in ONE launch (par_decode): gy is read from DRAM once instead of four times and the
+      // interleaved planes of gx are written while their lines are still in L2
+      nsteps = 0;
+      P.Ht = H / 2; P.Wt = W / 2; P.sy = P.sx = 2;
+      P.wide = igemm_wide(P, N) ? 1 : 0;
+      CUtensorMap* outs[4] = {&maps.out, &maps.out2, &maps.out3, &maps.out4};
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const int p = py * 2 + px;
+          P.seg[p] = (int16_t)nsteps;
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+              if (((ky + 1) & 1) != py || ((kx + 1) & 1) != px) continue;
+              const int dy = ky == 0 ? 1 : 0, dx = kx == 0 ? 1 : 0;
+              const int t = ky * 3 + kx;
+              for (int c0 = 0; c0 < cout; c0 += KC) {
+                if (nsteps >= MAX_STEPS) { set_error("dfb_conv2d: too many K steps"); return DFB_ERR_UNSUPPORTED; }
+                P.steps[nsteps++] = KStep{0, (int8_t)dy, (int8_t)dx, 0, (int16_t)c0, (int16_t)(t * cout + c0)};
+              }
+            }
+          P.oy = py; P.ox = px;
+          IgemmMaps tmp;
+          if ((rc = build_out_map(tmp, P, N))) return rc;
+          *outs[p] = tmp.out;
+        }
+      P.seg[4] = (int16_t)nsteps;
+      P.oy = P.ox = 0;
+      P.nsteps = nsteps;
+      P.par_mode = 1;
+      P.tiles_x = (P.Wt + TILE_W - 1) / TILE_W; P.tiles_y = (P.Ht + TILE_H - 1) / TILE_H;
+      P.num_tiles = 4 * P.tiles_x * P.tiles_y * a->n;
+      return dispatch_igemm(N, KC, maps, P, st);
+    }
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
         nsteps = 0;
@@ -1138,6 +1373,7 @@ struct WgradParams {
   int n_pairs, splits;                              // grid = n_pairs * splits
   int n_groups, cin_total, cout;
   float* wacc;                                      // [taps][cout][cin_total] fp32, += by red.add
+  float* grad_bias;                                 // [cout] fp32 += sum over pixels of gy, or NULL (odd group counts only)
   WGroup groups[MAX_GROUPS];
 };
 
@@ -1169,6 +1405,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad(const __grid_const
   const int g0 = pair * 2, g1 = g0 + 1 < P.n_groups ? g0 + 1 : -1;
   const int per = (P.num_tiles + P.splits - 1) / P.splits;
   const int t_begin = split * per, t_end = min(P.num_tiles, t_begin + per);
+  // Bias gradient for free: an odd group count leaves the second 64 rows of the last pair's M = 128 operand unused.
+  // Filled with ones (once, in every stage; the producer then loads only the first half), those accumulator rows
+  // become sum over pixels of 1 * gy[pixel, co] -- the per-channel sums of gy, i.e. the bias gradient of the layer.
+  const bool ones_half = P.grad_bias != nullptr && g1 < 0;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < MAX_AMAPS; ++i) tma_prefetch_desc(&maps.a[i]);
@@ -1178,6 +1418,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad(const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (ones_half) {
+    const uint4 one8 = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);   // eight bf16 1.0
+    for (int i = threadIdx.x; i < Cfg::STAGES * (WG_PIX * 128 / 16); i += blockDim.x) {
+      const int stage = i / (WG_PIX * 128 / 16), o = i % (WG_PIX * 128 / 16);
+      *reinterpret_cast<uint4*>(smem + stage * Cfg::STAGE_BYTES + WG_PIX * 128 + o * 16) = one8;
+    }
+    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1195,10 +1443,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad(const __grid_const
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-        mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+        mbar_arrive_expect_tx(&full[stage], ones_half ? Cfg::STAGE_BYTES - WG_PIX * 128 : Cfg::STAGE_BYTES);
         tma_load_4d(a_dst, &maps.a[ga.map], &full[stage], ga.c0, x0 + ga.dx, y0 + ga.dy, n);
         // an odd group count leaves the second half of the last pair unused: load the same box, discard the rows
-        tma_load_4d(a_dst + WG_PIX * 128, &maps.a[gb.map], &full[stage], gb.c0, x0 + gb.dx, y0 + gb.dy, n);
+        // (or keep the ones written at kernel start: the bias-gradient rows)
+        if (!ones_half) tma_load_4d(a_dst + WG_PIX * 128, &maps.a[gb.map], &full[stage], gb.c0, x0 + gb.dx, y0 + gb.dy, n);
 #pragma unroll
         for (int j = 0; j < N / 64; ++j) tma_load_4d(b_dst + j * WG_PIX * 128, &maps.b, &full[stage], j * 64, x0, y0, n);
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -1243,6 +1492,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_conv_wgrad(const __grid_const
       if (live) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)(col + i) * P.cin_total, v[i]);  // lanes = consecutive ci
+      }
+      if (ones_half && m == 64) {   // every row 64..127 holds the same per-channel sums of gy: one of them reports
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(P.grad_bias + col + i, v[i]);
       }
     }
   }
@@ -1619,6 +1872,7 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
     if ((rc = make_tensor_map_bf16(&maps.b, a->y, 4, dims, str, box, 128))) return rc;
   }
   int ng = 0;
+  if (a->grad_bias && (k != 1 || s != 1)) { set_error("dfb_conv2d_wgrad: grad_bias is served for 1x1 stride-1 layers only"); return DFB_ERR_UNSUPPORTED; }
   if (s == 1 && k == 3 && halo_wgrad_enabled()) {
     // ---------------------------------------------------------------- halo variant
     {
@@ -1786,6 +2040,10 @@ extern "C" int dfb_conv2d_wgrad(const dfb_conv_args* a, float* wacc, float* grad
   }
   P.n_groups = ng;
   P.n_pairs = (ng + 1) / 2;
+  if (a->grad_bias) {
+    if (ng % 2 == 0 || a->cout < 32) { set_error("dfb_conv2d_wgrad: grad_bias needs an odd number of 64-channel input groups (got %d)", ng); return DFB_ERR_UNSUPPORTED; }
+    P.grad_bias = a->grad_bias;
+  }
   P.n_img = a->n; P.Ht = Ho; P.Wt = Wo;
   P.tiles_x = (Wo + 7) / 8; P.tiles_y = (Ho + 7) / 8;
   P.num_tiles = P.tiles_x * P.tiles_y * a->n;

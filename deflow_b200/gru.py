@@ -7,6 +7,7 @@ Reference: ConvGRUDecoder.forward_single / LinearDecoder.forward_single (OSF/src
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -36,8 +37,14 @@ def _dgrad(gy, w4, lo, hi):
     return tc.conv2d_dgrad(_img(gy), wd, n_pad // 8, 8, hi - lo, w4.shape[1], lo, 1, 1).view(n_pad, hi - lo)
 
 
-def _wgrad(srcs, gy, acc=None):
-    return tc.conv2d_wgrad([_img(s) for s in srcs], _img(gy), 1, 1, acc)
+def _wgrad(srcs, gy, acc=None, gbias=None):
+    return tc.conv2d_wgrad([_img(s) for s in srcs], _img(gy), 1, 1, acc, grad_bias=gbias)
+
+
+# The bias gradients of the gate / head matrices ride in the weight-gradient launches (idle accumulator rows of the
+# 128 + 64-channel input, csrc/conv_igemm.cu k_conv_wgrad `ones_half`) instead of separate passes over dq / dzr / dy1
+# (k_channel_sum_s, 0.57 ms per step at config 2).  DFB_WGRAD_BIAS=0 restores the separate passes (A/B).
+_WGRAD_BIAS = os.environ.get("DFB_WGRAD_BIAS", "1") != "0"
 
 
 class _Decoder(torch.autograd.Function):
@@ -278,8 +285,11 @@ class _FusedGRUDecoder(torch.autograd.Function):
         check(lib.dfb_head_out_backward(y1.data_ptr(), w2f.data_ptr(), dflow.data_ptr(), n, n_pad, dy1.data_ptr(),
                                         gw2.data_ptr(), gb2.data_ptr(), 0, st), "head_out_backward")
         w14 = w1f.reshape(32, 192, 1, 1)
-        gw1 = _wgrad([hsave[iters], xsave], dy1)
-        gb1 = tc.channel_sum(dy1)
+        fold = _WGRAD_BIAS
+        gb1 = z32(32) if fold else None
+        gw1 = _wgrad([hsave[iters], xsave], dy1, None, gb1)
+        if not fold:
+            gb1 = tc.channel_sum(dy1)
         d_h = _dgrad(dy1, w14, 0, 128)
         d_x = _dgrad(dy1, w14, 128, 192)
         # GRU iterations
@@ -296,11 +306,13 @@ class _FusedGRUDecoder(torch.autograd.Function):
                                              rh.data_ptr(), dq.data_ptr(), dzr.data_ptr(), dh0.data_ptr(), dx.data_ptr(), st),
                   "gru_fused_backward")
         gwq = gwzr = None
+        gbq, gbzr = (z32(128), z32(256)) if fold else (None, None)
         for t in range(iters):
-            gwq = _wgrad([rh[t], xsave], dq[t], gwq)
-            gwzr = _wgrad([hsave[t], xsave], dzr[t], gwzr)
-        gbq = tc.channel_sum(dq.view(-1, 128))
-        gbzr = tc.channel_sum(dzr.view(-1, 256))
+            gwq = _wgrad([rh[t], xsave], dq[t], gwq, gbq)
+            gwzr = _wgrad([hsave[t], xsave], dzr[t], gwzr, gbzr)
+        if not fold:
+            gbq = tc.channel_sum(dq.view(-1, 128))
+            gbzr = tc.channel_sum(dzr.view(-1, 256))
         gw_off, gb_off = z32(64, 3), z32(64)
         check(lib.dfb_offset_encode_backward(dx.data_ptr(), offsets.data_ptr(), n, 64, gw_off.data_ptr(),
                                              gb_off.data_ptr(), st), "offset_encode_backward")

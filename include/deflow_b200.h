@@ -263,6 +263,9 @@ typedef struct {
                             y2 [n,H,W,cin2] -- the two sources of a concatenated input get their gradients from ONE pass
                             over grad_y */
   int cin2;
+  float* grad_bias;      /* dfb_conv2d_wgrad, 1x1 stride 1 with an odd number of 64-channel input groups only: [cout] fp32
+                            += sum over pixels of grad_y (the layer's bias gradient, from otherwise idle accumulator rows
+                            of the same launch); NULL = not wanted */
 } dfb_conv_args;
 int dfb_conv_pack_weights(const float* w, int cout, int cin, int ksize, int split3, void* w_fwd, void* w_dgrad,
                           void* stream);

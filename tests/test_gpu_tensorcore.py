@@ -129,6 +129,145 @@ def test_wgrad_cross_shift_variant(monkeypatch, n, H, W, cins, variant):
     assert _rel(gw, wr.grad) <= 5e-5
 
 
+@pytest.mark.parametrize("rows,cout,cins", [(1024, 128, [128, 64]), (104, 256, [128, 64]), (8, 32, [128, 64]), (4104, 64, [64]),
+                                            (520, 128, [64, 128])])
+def test_wgrad_bias_gradient_from_idle_accumulator_rows(rows, cout, cins):
+    """dfb_conv_args.grad_bias: the per-channel sums of gy from the weight-gradient launch of a 1x1 layer with an odd number
+    of 64-channel input groups (the gate / head matrices of the point decoder), accumulated over calls like the weight
+    gradient; equal to a plain column sum of the same bf16 values; the weight gradient itself is unchanged."""
+    torch.manual_seed(rows + cout)
+    xs = [torch.randn(1, rows // 8, 8, c, device=DEV).to(torch.bfloat16) for c in cins]
+    gys = [torch.randn(1, rows // 8, 8, cout, device=DEV).to(torch.bfloat16) for _ in range(2)]
+    gb = torch.zeros(cout, device=DEV)
+    gw = None
+    for gy in gys:
+        gw = conv.conv2d_wgrad(xs, gy, 1, 1, gw, grad_bias=gb)
+    ref_b = sum(g.double().sum((0, 1, 2)) for g in gys)
+    xcat = torch.cat([x.double() for x in xs], 3).reshape(rows, -1)
+    ref_w = sum(g.double().reshape(rows, cout).t() @ xcat for g in gys)
+    assert float((gb.double() - ref_b).abs().max()) <= 1e-5 * max(1.0, float(ref_b.abs().max()))
+    assert _rel(gw[:, :, 0, 0].double(), ref_w) <= 5e-5
+    plain = None
+    for gy in gys:
+        plain = conv.conv2d_wgrad(xs, gy, 1, 1, plain)
+    assert _rel(gw, plain) <= 1e-6
+
+
+def test_wgrad_bias_gradient_refuses_even_group_counts():
+    xs = [torch.zeros(1, 8, 8, 128, device=DEV, dtype=torch.bfloat16)]
+    gy = torch.zeros(1, 8, 8, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="odd number"):
+        conv.conv2d_wgrad(xs, gy, 1, 1, grad_bias=torch.zeros(64, device=DEV))
+    xs3 = [torch.zeros(1, 8, 8, 64, device=DEV, dtype=torch.bfloat16)]
+    with pytest.raises(RuntimeError, match="1x1"):
+        conv.conv2d_wgrad(xs3, gy, 3, 1, grad_bias=torch.zeros(64, device=DEV))
+
+
+@pytest.mark.parametrize("n,H,W,cin,cout", [(2, 64, 64, 32, 64), (3, 40, 24, 64, 128), (1, 32, 48, 128, 256), (1, 2, 2, 64, 128)])
+@pytest.mark.parametrize("merge", ["1", "0"])
+def test_stride2_dgrad_one_launch_for_the_four_parity_planes(monkeypatch, n, H, W, cin, cout, merge):
+    """Data gradient of the 3x3 stride-2 encoder convolutions: one launch over (region, parity plane) items (default) and
+    the four per-plane launches (DFB_DGRAD_PAR_MERGE=0) against autograd on the same bf16-rounded operands; the
+    per-channel sums taken in the epilogue (the producer's bias gradient) ride along in both."""
+    monkeypatch.setenv("DFB_DGRAD_PAR_MERGE", merge)
+    torch.manual_seed(H * W + cin)
+    w = (torch.randn(cout, cin, 3, 3, device=DEV) / (cin * 9) ** 0.5).to(torch.bfloat16).float()
+    x = torch.zeros(n, cin, H, W, device=DEV, requires_grad=True)
+    y = F.conv2d(x, w, None, stride=2, padding=1)
+    gy = torch.randn_like(y.permute(0, 2, 3, 1)).to(torch.bfloat16).contiguous()
+    y.backward(gy.float().permute(0, 3, 1, 2))
+    ref = x.grad.permute(0, 2, 3, 1)
+    _, wd = conv.pack_weights(w)
+    before = d._lib.launch_count()
+    gx = conv.conv2d_dgrad(gy, wd, H, W, cin, cin, 0, 3, 2, colsum=True)
+    assert d._lib.launch_count() - before == (1 if merge == "1" else 4)
+    scale = max(1e-6, float(ref.abs().max()))
+    assert float((gx.float() - ref).abs().max()) / scale <= 2 ** -7
+    cs = conv.bias_grad(gx)
+    ref_cs = ref.double().sum((0, 1, 2))
+    assert float((cs.double() - ref_cs).abs().max()) <= 2e-2 * max(1.0, float(ref_cs.abs().max()))
+
+
+GENERAL_CASES = [("1x1 128->64 many tiles", 2, 160, 128, [128], 64, 1, 1), ("1x1 cat(256,256)->256", 1, 16, 16, [256, 256], 256, 1, 1),
+                 ("1x1 32->64", 1, 40, 24, [32], 64, 1, 1), ("3x3 32->64 s2", 2, 64, 64, [32], 64, 3, 2),
+                 ("3x3 64->128 s2 many tiles", 2, 256, 192, [64], 128, 3, 2), ("1x1 cat(128,128)->128", 1, 24, 40, [128, 128], 128, 1, 1)]
+
+
+@pytest.mark.parametrize("case", GENERAL_CASES, ids=[c[0] for c in GENERAL_CASES])
+def test_general_kernel_store_width_and_weight_residency_variants(monkeypatch, case):
+    """k_conv_igemm: 64-channel epilogue stores + weights resident in shared memory (default) produce the very same
+    tensors as 32-channel stores + weights re-loaded per tile (DFB_EPI_WIDE=0, DFB_IGEMM_B_RESIDENT=0): the MMA order
+    is the same, only the data movement differs.  Forward (with BatchNorm statistics) and data gradient."""
+    name, n, H, W, cins, cout, k, st = case
+    torch.manual_seed(len(name))
+    xs = [torch.randn(n, H, W, c, device=DEV).to(torch.bfloat16) for c in cins]
+    ct = sum(cins)
+    w = torch.randn(cout, ct, k, k, device=DEV) / (ct * k * k) ** 0.5
+    b = torch.randn(cout, device=DEV)
+    wf, wd = conv.pack_weights(w)
+    Ho, Wo = conv.out_size(H, W, k, st)
+    gy = torch.randn(n, Ho, Wo, cout, device=DEV).to(torch.bfloat16)
+
+    def run():
+        stats = torch.zeros(2, cout, dtype=torch.float64, device=DEV)
+        y = conv.conv2d_forward(xs, wf, b, cout, k, st, stats)
+        gxs, off = [], 0
+        for c in cins:
+            gxs.append(conv.conv2d_dgrad(gy, wd, H, W, c, ct, off, k, st, colsum=True))
+            off += c
+        return y, stats, gxs
+
+    y1, s1, g1 = run()
+    xcat = torch.cat([x.float() for x in xs], 3).permute(0, 3, 1, 2)
+    ref = F.conv2d(xcat, w.to(torch.bfloat16).float(), b, stride=st, padding=k // 2).permute(0, 2, 3, 1)
+    assert _rel(y1.float(), ref) <= 2 ** -8
+    for wide, res in (("0", "0"), ("1", "0"), ("0", "1")):
+        monkeypatch.setenv("DFB_EPI_WIDE", wide)
+        monkeypatch.setenv("DFB_IGEMM_B_RESIDENT", res)
+        y0, s0, g0 = run()
+        assert torch.equal(y0, y1)
+        assert _rel(s0, s1) <= 1e-6
+        for a, bb in zip(g0, g1):
+            assert torch.equal(a, bb)
+            assert _rel(conv.bias_grad(a), conv.bias_grad(bb)) <= 1e-5
+
+
+PAIR_CASES = [(2, 32, 32, [64]), (3, 128, 128, [64]), (2, 40, 24, [64]), (1, 96, 16, [64, 64]), (1, 18, 16, [64])]
+
+
+@pytest.mark.parametrize("n,H,W,cins", PAIR_CASES)
+def test_row_pair_kernel_wide_store_variant(monkeypatch, n, H, W, cins):
+    """k_conv_igemm_halo_pair with 64-channel epilogue stores (DFB_PAIR_WIDE=1, weight ring of four kx triples) against
+    the 32-channel variant: identical outputs for the forward (with statistics) and the data gradient."""
+    torch.manual_seed(H + W)
+    xs = [torch.randn(n, H, W, c, device=DEV).to(torch.bfloat16) for c in cins]
+    ct = sum(cins)
+    w = torch.randn(64, ct, 3, 3, device=DEV) / (ct * 9) ** 0.5
+    b = torch.randn(64, device=DEV)
+    wf, wd = conv.pack_weights(w)
+    gy = torch.randn(n, H, W, 64, device=DEV).to(torch.bfloat16)
+
+    def run():
+        stats = torch.zeros(2, 64, dtype=torch.float64, device=DEV)
+        y = conv.conv2d_forward(xs, wf, b, 64, 3, 1, stats)
+        gxs, off = [], 0
+        for c in cins:
+            gxs.append(conv.conv2d_dgrad(gy, wd, H, W, c, ct, off, 3, 1))
+            off += c
+        return y, stats, gxs
+
+    y0, s0, g0 = run()
+    monkeypatch.setenv("DFB_PAIR_WIDE", "1")
+    y1, s1, g1 = run()
+    xcat = torch.cat([x.float() for x in xs], 3).permute(0, 3, 1, 2)
+    ref = F.conv2d(xcat, w.to(torch.bfloat16).float(), b, stride=1, padding=1).permute(0, 2, 3, 1)
+    assert _rel(y1.float(), ref) <= 2 ** -8
+    assert torch.equal(y0, y1)
+    assert _rel(s0, s1) <= 1e-6
+    for a, bb in zip(g0, g1):
+        assert torch.equal(a, bb)
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_split_precision_matches_fp32(case):
     """Parity mode: fp32 tensors, operands as (hi, lo) bf16 pairs, hi*hi + hi*lo + lo*hi on the tensor cores."""
