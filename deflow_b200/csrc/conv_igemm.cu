@@ -797,6 +797,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo_pair(const
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+static bool env_on(const char* name) {
+  const char* e = getenv(name);
+  return !(e && atoi(e) == 0);
+}
+
 // bf16 output of the row-pair kernel as [ch, x, row parity, row / 2, n], box [32 (wide: 64), 8, 1, 4, 1], SWIZZLE_64B (128B)
 static int build_out_map_pair(IgemmMaps& maps, const IgemmParams& P, int N, bool wide) {
   const uint64_t dims[5] = {(uint64_t)N, (uint64_t)P.Wt, 2, (uint64_t)P.Ht / 2, (uint64_t)P.n_img};
@@ -825,10 +830,10 @@ static int launch_igemm_halo_pair_t(IgemmMaps& maps, IgemmParams& P, cudaStream_
   return check_launch("conv_igemm_halo_pair");
 }
 
-// DFB_PAIR_WIDE=1: 64-channel epilogue stores in the row-pair kernel (read per call; A/B)
+// 64-channel epilogue stores in the row-pair kernel: 3.02 -> 2.95 ms per step over its 19 launches
+// (profiles/r02_tma_requests_ab.txt); DFB_PAIR_WIDE=0 -> 32-channel stores and a weight ring of five kx triples (A/B)
 static int launch_igemm_halo_pair(IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
-  const char* e = getenv("DFB_PAIR_WIDE");
-  if (e && atoi(e) != 0) return launch_igemm_halo_pair_t<true>(maps, P, st);
+  if (env_on("DFB_PAIR_WIDE")) return launch_igemm_halo_pair_t<true>(maps, P, st);
   return launch_igemm_halo_pair_t<false>(maps, P, st);
 }
 
@@ -844,10 +849,6 @@ static bool halo_pair_enabled() {
 
 // k_conv_igemm A/B switches (read per call; tests toggle them): DFB_EPI_WIDE=0 -> 32-channel epilogue stores,
 // DFB_IGEMM_B_RESIDENT=0 -> weight tiles re-loaded with every A tile.
-static bool env_on(const char* name) {
-  const char* e = getenv(name);
-  return !(e && atoi(e) == 0);
-}
 static bool igemm_wide(const IgemmParams& P, int N) {
   return !P.out_fp32 && N % 64 == 0 && P.split_col % 64 == 0 && P.halo_pitch == 0 && env_on("DFB_EPI_WIDE");
 }

@@ -237,8 +237,8 @@ PAIR_CASES = [(2, 32, 32, [64]), (3, 128, 128, [64]), (2, 40, 24, [64]), (1, 96,
 
 @pytest.mark.parametrize("n,H,W,cins", PAIR_CASES)
 def test_row_pair_kernel_wide_store_variant(monkeypatch, n, H, W, cins):
-    """k_conv_igemm_halo_pair with 64-channel epilogue stores (DFB_PAIR_WIDE=1, weight ring of four kx triples) against
-    the 32-channel variant: identical outputs for the forward (with statistics) and the data gradient."""
+    """k_conv_igemm_halo_pair with 64-channel epilogue stores (default; weight ring of four kx triples) against
+    the 32-channel variant (DFB_PAIR_WIDE=0): identical outputs for the forward (with statistics) and the data gradient."""
     torch.manual_seed(H + W)
     xs = [torch.randn(n, H, W, c, device=DEV).to(torch.bfloat16) for c in cins]
     ct = sum(cins)
@@ -256,6 +256,7 @@ def test_row_pair_kernel_wide_store_variant(monkeypatch, n, H, W, cins):
             off += c
         return y, stats, gxs
 
+    monkeypatch.setenv("DFB_PAIR_WIDE", "0")
     y0, s0, g0 = run()
     monkeypatch.setenv("DFB_PAIR_WIDE", "1")
     y1, s1, g1 = run()
