@@ -101,7 +101,8 @@ struct IgemmParams {
   // k_conv_igemm only.  wide: the epilogue stores 64-channel (128-byte) rows, box [64, 8, 4, 1] SWIZZLE_128B, half as
   // many TMA requests per tile.  b_resident: all nsteps weight tiles are loaded ONCE into the tail of the stage ring
   // (the ring keeps ring_stages stages and moves A tiles only) instead of once per tile and K step.
-  int wide, b_resident, ring_stages;
+  // alt: the two groups of four epilogue warps take alternate tiles (igemm_epilogue_alt; bf16 output only)
+  int wide, b_resident, ring_stages, alt;
   KStep steps[MAX_STEPS];
 };
 
@@ -344,6 +345,136 @@ __device__ __forceinline__ void igemm_epilogue_wide(const IgemmParams& P, const 
   if (lane == 0) tma_store_wait_all();
 }
 
+// Incremental tile decode for the persistent loops: tile index t0, t0 + stride, ... -> (tx, ty, n) without the three
+// integer divisions per tile (ncu r02: ~90 of the ~130 instructions a single-thread producer spent per tile, at ~8
+// cycles per dependent instruction, when a tile has one or two K steps).
+struct TileIter {
+  int tx, ty, n, dx, dy, dn, tiles_x, tiles_y;
+  __device__ __forceinline__ void init(int t0, int stride, int tiles_x_, int tiles_y_) {
+    tiles_x = tiles_x_; tiles_y = tiles_y_;
+    tx = t0 % tiles_x; int r = t0 / tiles_x; ty = r % tiles_y; n = r / tiles_y;
+    dx = stride % tiles_x; r = stride / tiles_x; dy = r % tiles_y; dn = r / tiles_y;
+  }
+  __device__ __forceinline__ void next() {
+    tx += dx;
+    int cy = dy;
+    if (tx >= tiles_x) { tx -= tiles_x; ++cy; }
+    ty += cy;
+    n += dn;
+    if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+  }
+};
+
+// One block of 32 * NH accumulator columns for this warp's 32 pixel rows: bias, BatchNorm statistics through the slab
+// (it aliases the staging tile, so statistics come first), bf16 rows of NH * 64 bytes with the matching TMA swizzle.
+// The caller issues the TMA store.  NH = 1: 32 channels, SWIZZLE_64B; NH = 2: 64 channels, SWIZZLE_128B.
+template <int NH>
+__device__ __forceinline__ void epi_block(const IgemmParams& P, uint32_t taddr, const float* bias_blk, float* sum_blk,
+                                          float* sq_blk, bool valid, uint8_t* stg, int lane, bool& store_pending) {
+  float* slab = reinterpret_cast<float*>(stg);
+  const int sw16 = (lane >> 1) & 15;
+  const int rcol = lane & 15, rpar = lane >> 4;
+  uint32_t pk[16 * NH];
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) {
+    float v[32];
+    tmem_ld32(taddr + 32 * hh, v);
+    if (P.bias) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_blk + 32 * hh + i);
+        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+      }
+    }
+    if (hh == 0 && store_pending) {    // the previous TMA store must have read the tile before it is rewritten
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+      store_pending = false;
+    }
+    if (P.stats) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) slab[lane * 16 + (i ^ sw16)] = valid ? v[h * 16 + i] : 0.f;
+        __syncwarp();
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float t = slab[(2 * i + rpar) * 16 + (rcol ^ i)];
+          s1 += t;
+          s2 = fmaf(t, t, s2);
+        }
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+        if (lane < 16) {
+          atomicAdd(&sum_blk[32 * hh + h * 16 + lane], s1);
+          if (!P.stats_sum_only) atomicAdd(&sq_blk[32 * hh + h * 16 + lane], s2);
+        }
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      pk[16 * hh + i] = *reinterpret_cast<const unsigned*>(&p2);
+    }
+  }
+  const int sw = NH == 2 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+  for (int i = 0; i < 4 * NH; ++i)
+    *reinterpret_cast<uint4*>(stg + lane * (64 * NH) + ((i ^ sw) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+  fence_proxy_async();
+  __syncwarp();
+}
+
+// Epilogue of the general kernel (k_conv_igemm, bf16 output): the two groups of four epilogue warps take ALTERNATE
+// tiles (group g owns accumulator g), each warp all column blocks of its 32 pixel rows.  With one or two K steps per
+// tile the kernel is bound by per-tile latency chains, not by bytes or MMAs (ncu r02: 30 % issue slots busy, every warp
+// 8 cycles per instruction, epilogue warps ~350 instructions per tile): two tiles in the epilogue at a time, no
+// divisions in the tile decode, and (WIDE) half as many TMA stores.
+template <int N, bool WIDE>
+__device__ __forceinline__ void igemm_epilogue_alt(const IgemmParams& P, const CUtensorMap* out_map, uint32_t tmem_base,
+                                                   uint64_t* acc_full, uint64_t* acc_empty, float* s_stats,
+                                                   const float* s_bias, uint8_t* stage_all, int warp, int lane) {
+  constexpr int NH = WIDE ? 2 : 1, BW = 32 * NH;
+  const int q = warp & 3;
+  const int grp = (warp - 2) >> 2;
+  const int m = q * 32 + lane;
+  const int r = m >> 3, c = m & 7;
+  uint8_t* stg = stage_all + (warp - 2) * EPI_STAGE_BYTES_WIDE;
+  const int G = (int)gridDim.x;
+  const int item0 = (int)blockIdx.x + grp * G;
+  TileIter ti;
+  ti.init(P.par_mode ? item0 >> 2 : item0, P.par_mode ? G >> 1 : 2 * G, P.tiles_x, P.tiles_y);
+  bool store_pending = false;
+  uint32_t acc_phase = 0;
+  int it = grp;                                   // iteration index of the CTA's item sequence
+  for (int item = item0; item < P.num_tiles; item += 2 * G, it += 2, ti.next()) {
+    const int par = P.par_mode ? (((int)blockIdx.x & 3) + it) & 3 : 0;   // par_decode without the division
+    const int y = ti.ty * TILE_H + r, x = ti.tx * TILE_W + c;
+    const bool valid = y < P.Ht && x < P.Wt;
+    mbar_wait(&acc_full[grp], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int col = 0; col < N; col += BW) {
+      const bool second = P.split_col > 0 && col >= P.split_col;
+      const int oc0 = second ? col - P.split_col : col;
+      epi_block<NH>(P, tmem_base + ((uint32_t)(q * 32) << 16) + grp * N + col, s_bias + col, s_stats + col, s_stats + N + col,
+                    valid, stg, lane, store_pending);
+      if (lane == 0) {
+        tma_store_4d(second ? out_map + 1 : out_map + par, stg, oc0, ti.tx * TILE_W, ti.ty * TILE_H + 4 * q, ti.n);
+        tma_store_commit();
+      }
+      store_pending = true;
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[grp]);
+    acc_phase ^= 1;
+  }
+  if (lane == 0) tma_store_wait_all();
+}
+
 template <int N, int KC>
 struct IgemmCfg {
   static constexpr int A_BYTES = TILE_M * KC * 2;
@@ -387,7 +518,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
     for (int i = 0; i < MAX_AMAPS; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&maps.b);
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
+    // alt: each accumulator is drained by ONE group of four epilogue warps (igemm_epilogue_alt)
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], P.alt ? EPI_WARPS / 2 : EPI_WARPS); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -399,6 +531,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const int G = (int)gridDim.x;
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -408,12 +541,13 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
         mbar_arrive_expect_tx(b_full, (uint32_t)(P.nsteps * Cfg::B_BYTES));
         for (int s = 0; s < P.nsteps; ++s) tma_load_2d(b_res + s * Cfg::B_BYTES, &maps.b, b_full, P.steps[s].wk, 0);
       }
-      for (int item = blockIdx.x; item < P.num_tiles; item += gridDim.x) {
-        int tile = item;
-        const int par = par_decode(P, tile);
+      TileIter ti;
+      ti.init(P.par_mode ? (int)blockIdx.x >> 2 : (int)blockIdx.x, P.par_mode ? G >> 2 : G, P.tiles_x, P.tiles_y);
+      int it = 0;
+      for (int item = blockIdx.x; item < P.num_tiles; item += G, ++it, ti.next()) {
+        const int par = P.par_mode ? (((int)blockIdx.x & 3) + it) & 3 : 0;   // = par_decode(item), without the division
         const int s0 = P.par_mode ? P.seg[par] : 0, s1 = P.par_mode ? P.seg[par + 1] : P.nsteps;
-        const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
-        const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+        const int x0 = ti.tx * TILE_W, y0 = ti.ty * TILE_H, n = ti.n;
         for (int s = s0; s < s1; ++s) {
           const KStep st = P.steps[s];
           mbar_wait(&empty[stage], phase ^ 1);
@@ -427,44 +561,50 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, N, 0, 0);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      if (P.b_resident) {
-        mbar_wait(b_full, 0);
+    // ------------------------------------------------------------ MMA issuer: the whole warp runs the loop (warp-uniform
+    // control flow, descriptors as (lo, hi) halves), one elected lane issues -- see k_conv_igemm_halo
+    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, N, 0, 0);
+    const uint64_t proto = make_smem_desc(0, 16, Cfg::SBO, Cfg::LAYOUT);
+    const uint32_t d_hi = (uint32_t)(proto >> 32);
+    const uint32_t lo0 = (uint32_t)proto | ((smem_u32(tiles) & 0x3FFFFu) >> 4);
+    const uint32_t b_res_lo = (uint32_t)proto | ((smem_u32(b_res) & 0x3FFFFu) >> 4);
+    const uint32_t stride16 = (uint32_t)ring_stride >> 4;
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    if (P.b_resident) {
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+    }
+    int it = 0;
+    for (int item = blockIdx.x; item < P.num_tiles; item += G, ++it) {
+      const int par = P.par_mode ? (((int)blockIdx.x & 3) + it) & 3 : 0;
+      const int s0 = P.par_mode ? P.seg[par] : 0, s1 = P.par_mode ? P.seg[par + 1] : P.nsteps;
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * N;
+      for (int s = s0; s < s1; ++s) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-      }
-      for (int item = blockIdx.x; item < P.num_tiles; item += gridDim.x) {
-        int tile = item;
-        const int par = par_decode(P, tile);
-        const int s0 = P.par_mode ? P.seg[par] : 0, s1 = P.par_mode ? P.seg[par + 1] : P.nsteps;
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + acc * N;
-        for (int s = s0; s < s1; ++s) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + stage * ring_stride);
-          const uint32_t b_addr = P.b_resident ? smem_u32(b_res + s * Cfg::B_BYTES) : a_addr + Cfg::A_BYTES;
-          const uint64_t adesc = make_smem_desc(a_addr, 16, Cfg::SBO, Cfg::LAYOUT);
-          const uint64_t bdesc = make_smem_desc(b_addr, 16, Cfg::SBO, Cfg::LAYOUT);
+        const uint32_t a_lo = lo0 + (uint32_t)stage * stride16;
+        const uint32_t b_lo = P.b_resident ? b_res_lo + (uint32_t)s * (uint32_t)(Cfg::B_BYTES >> 4) : a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k)  // +32 bytes (2 x 16 B) along K per UMMA_K = 16 bf16
-            umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, ((s - s0) | k) != 0);
-          umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
-          if (++stage == ring) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(&acc_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        for (int k = 0; k < KC / 16; ++k)  // +32 bytes (2 x 16 B) along K per UMMA_K = 16 bf16
+          umma_bf16_lohi_warp(d, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, (uint32_t)(((s - s0) | k) != 0));
+        umma_commit_warp(&empty[stage]);  // frees the smem stage once these MMAs have read it
+        if (++stage == ring) { stage = 0; phase ^= 1; }
       }
+      umma_commit_warp(&acc_full[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    if constexpr (N % 64 == 0) {
-      if (P.wide) igemm_epilogue_wide<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
-      else igemm_epilogue<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+    if (P.alt) {
+      if constexpr (N % 64 == 0) {
+        if (P.wide) igemm_epilogue_alt<N, true>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+        else igemm_epilogue_alt<N, false>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+      } else {
+        igemm_epilogue_alt<N, false>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+      }
     } else {
       igemm_epilogue<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
     }
@@ -847,10 +987,12 @@ static bool halo_pair_enabled() {
   return mode != 0;
 }
 
-// k_conv_igemm A/B switches (read per call; tests toggle them): DFB_EPI_WIDE=0 -> 32-channel epilogue stores,
-// DFB_IGEMM_B_RESIDENT=0 -> weight tiles re-loaded with every A tile.
+// k_conv_igemm A/B switches (read per call; tests toggle them): DFB_EPI_ALT=0 -> all eight epilogue warps on every tile
+// (and 32-channel stores), DFB_EPI_WIDE=0 -> 32-channel epilogue stores, DFB_IGEMM_B_RESIDENT=0 -> weight tiles re-loaded
+// with every A tile.
+static bool igemm_alt(const IgemmParams& P) { return !P.out_fp32 && P.halo_pitch == 0 && env_on("DFB_EPI_ALT"); }
 static bool igemm_wide(const IgemmParams& P, int N) {
-  return !P.out_fp32 && N % 64 == 0 && P.split_col % 64 == 0 && P.halo_pitch == 0 && env_on("DFB_EPI_WIDE");
+  return igemm_alt(P) && N % 64 == 0 && P.split_col % 64 == 0 && env_on("DFB_EPI_WIDE");
 }
 static bool igemm_resident_enabled() { return env_on("DFB_IGEMM_B_RESIDENT"); }
 
@@ -1007,6 +1149,7 @@ template <int N, int KC>
 static int launch_igemm(IgemmMaps& maps, const IgemmParams& P, cudaStream_t st) {
   using Cfg = IgemmCfg<N, KC>;
   IgemmParams Q = P;
+  Q.alt = igemm_alt(Q) ? 1 : 0;
   Q.wide = igemm_wide(Q, N) ? 1 : 0;
   if (!Q.par_mode) {   // (parity-merged launches come with their four output maps built)
     if (int rc = build_out_map(maps, Q, N)) return rc;

@@ -195,9 +195,10 @@ GENERAL_CASES = [("1x1 128->64 many tiles", 2, 160, 128, [128], 64, 1, 1), ("1x1
 
 @pytest.mark.parametrize("case", GENERAL_CASES, ids=[c[0] for c in GENERAL_CASES])
 def test_general_kernel_store_width_and_weight_residency_variants(monkeypatch, case):
-    """k_conv_igemm: 64-channel epilogue stores + weights resident in shared memory (default) produce the very same
-    tensors as 32-channel stores + weights re-loaded per tile (DFB_EPI_WIDE=0, DFB_IGEMM_B_RESIDENT=0): the MMA order
-    is the same, only the data movement differs.  Forward (with BatchNorm statistics) and data gradient."""
+    """k_conv_igemm: alternate-tile epilogue groups + 64-channel stores + weights resident in shared memory (default)
+    produce the very same tensors as all-warps-per-tile + 32-channel stores + weights re-loaded per tile (DFB_EPI_ALT=0,
+    DFB_EPI_WIDE=0, DFB_IGEMM_B_RESIDENT=0): the MMA order is the same, only the data movement differs.  Forward (with
+    BatchNorm statistics) and data gradient."""
     name, n, H, W, cins, cout, k, st = case
     torch.manual_seed(len(name))
     xs = [torch.randn(n, H, W, c, device=DEV).to(torch.bfloat16) for c in cins]
@@ -221,7 +222,8 @@ def test_general_kernel_store_width_and_weight_residency_variants(monkeypatch, c
     xcat = torch.cat([x.float() for x in xs], 3).permute(0, 3, 1, 2)
     ref = F.conv2d(xcat, w.to(torch.bfloat16).float(), b, stride=st, padding=k // 2).permute(0, 2, 3, 1)
     assert _rel(y1.float(), ref) <= 2 ** -8
-    for wide, res in (("0", "0"), ("1", "0"), ("0", "1")):
+    for alt, wide, res in (("0", "0", "0"), ("1", "1", "0"), ("1", "0", "1"), ("0", "1", "1")):
+        monkeypatch.setenv("DFB_EPI_ALT", alt)
         monkeypatch.setenv("DFB_EPI_WIDE", wide)
         monkeypatch.setenv("DFB_IGEMM_B_RESIDENT", res)
         y0, s0, g0 = run()
