@@ -4,12 +4,12 @@
 // ConvWithNorms in basic/__init__.py:61-79) -- cuDNN library calls on NCHW fp32/TF32 there.
 //
 // One kernel serves forward (stride 1 and 2, 1x1 and 3x3, channel-concatenated inputs) and data-gradient
-// (stride 1; stride 2 as four parity-plane launches): the host builds a table of K-steps, each step
+// (stride 1; stride 2 as one launch over the four parity planes of the result): the host builds a table of K-steps, each step
 // naming (source tensor map, pixel shift, channel chunk, weight K offset).  Per step the TMA producer
 // loads a [16 x 8 pixels] x KC-channel activation box (out-of-bounds = zero padding) and an [N x KC]
 // weight box; one thread issues KC/16 tcgen05.mma (M = 128 pixels, N = Cout) into a TMEM accumulator;
-// four epilogue warps read TMEM, add the bias, accumulate BatchNorm batch statistics (sum, sum of
-// squares per channel) and store bf16 NHWC.  Accumulators are double buffered in TMEM so the epilogue
+// eight epilogue warps read TMEM, add the bias, accumulate BatchNorm batch statistics (sum, sum of
+// squares per channel) and store bf16 NHWC through a swizzled staging tile and TMA.  Accumulators are double buffered in TMEM so the epilogue
 // of tile i overlaps the MMAs of tile i+1.  Persistent: one CTA per SM, static round-robin over tiles.
 #include "tc_common.cuh"
 #include "../../include/deflow_b200.h"

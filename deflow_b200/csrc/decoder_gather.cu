@@ -59,7 +59,47 @@ __global__ void __launch_bounds__(256) k_decoder_gather(const void* __restrict__
   }
 }
 
-// One warp per pc0 pillar: sum the 128-wide gradient rows of its points, write the three NHWC rows.
+// One warp per pc0 pillar: sum the 128-wide gradient rows of its points, write the three NHWC rows.  Pillar populations
+// are heavy-tailed (median 4, a few with hundreds to thousands of points), and a warp walking a 4000-point pillar alone
+// was the whole kernel's duration (0.6 ms at config 2 for 270 MB of rows): a block owns a contiguous range of pillars, its
+// warps take the light ones one each, and the heavy ones (> GB_HEAVY points) are summed by all eight warps together.
+constexpr int GB_HEAVY = 96;
+constexpr int GB_LIST = 64;
+
+template <bool IN_BF>
+__device__ __forceinline__ void gather_rows_sum(const void* __restrict__ grad_h0, const int* __restrict__ sorted_pt, int j0, int s1,
+                                                int stride, int lane, float4& a) {
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  // up to eight rows in flight (all indices first, then all rows)
+  for (int j = j0; j < s1; j += stride) {
+    int pt[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pt[k] = j + k < s1 ? sorted_pt[j + k] : -1;
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = pt[k] >= 0 ? load4<IN_BF>(grad_h0, (size_t)pt[k] * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
+      b.x += v[k + 1].x; b.y += v[k + 1].y; b.z += v[k + 1].z; b.w += v[k + 1].w;
+    }
+  }
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+
+template <bool OUT_BF>
+__device__ __forceinline__ void gather_rows_write(const float4& a, int q, int pix, int lane, int B, int HW, void* __restrict__ grad_img,
+                                                  void* __restrict__ grad_unet, float* __restrict__ img_rows) {
+  if (lane < 16) {
+    if (img_rows) *reinterpret_cast<float4*>(img_rows + (size_t)q * 64 + lane * 4) = a;
+    else if (lane < 8) store4<OUT_BF>(grad_img, (size_t)pix * 32 + lane * 4, a);
+    else store4<OUT_BF>(grad_img, ((size_t)pix + (size_t)B * HW) * 32 + (lane - 8) * 4, a);
+  } else {
+    store4<OUT_BF>(grad_unet, (size_t)pix * 64 + (lane - 16) * 4, a);
+  }
+}
+
 template <bool IN_BF, bool OUT_BF>
 __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restrict__ grad_h0, int B, int HW,
                                                             const int* __restrict__ counts, int F,
@@ -71,37 +111,45 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
   // img_rows != NULL (then grad_img == NULL): the 64 image channels of every pc0 pillar's sum go to the compact fp32 buffer
   // img_rows[q][64] instead of a dense zero-filled image gradient; k_gather_img_rows_add adds them into the image gradient
   // later, once the other consumers of the pseudo-image have written theirs.
+  __shared__ int heavy[GB_LIST];
+  __shared__ int n_heavy;
+  __shared__ float4 part[8][32];
   const int M0 = min(counts[3 * F + 1 + B], pil_cap);  // pillars of the pc0 frames
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < M0; q += warps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (M0 + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int qa = min(M0, (int)blockIdx.x * per), qb = min(M0, qa + per);
+  if (threadIdx.x == 0) n_heavy = 0;
+  __syncthreads();
+  for (int q = qa + warp; q < qb; q += 8) {
     const int s0 = pil_start[q], s1 = pil_start[q + 1];
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    // up to eight rows in flight (all indices first, then all rows): the median pillar is done in one round, and the
-    // heavy tail (hundreds of points in one pillar) is not a chain of dependent round trips
-    for (int j = s0; j < s1; j += 8) {
-      int pt[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) pt[k] = j + k < s1 ? sorted_pt[j + k] : -1;
-      float4 v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        v[k] = pt[k] >= 0 ? load4<IN_BF>(grad_h0, (size_t)pt[k] * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
-        b.x += v[k + 1].x; b.y += v[k + 1].y; b.z += v[k + 1].z; b.w += v[k + 1].w;
-      }
+    if (s1 - s0 > GB_HEAVY) {
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&n_heavy, 1);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (slot < GB_LIST) {
+        if (lane == 0) heavy[slot] = q;
+        continue;
+      }                                            // list full: this warp walks the pillar alone
     }
-    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-    const int pix = pil_pix[q];
-    if (lane < 16) {
-      if (img_rows) *reinterpret_cast<float4*>(img_rows + (size_t)q * 64 + lane * 4) = a;
-      else if (lane < 8) store4<OUT_BF>(grad_img, (size_t)pix * 32 + lane * 4, a);
-      else store4<OUT_BF>(grad_img, ((size_t)pix + (size_t)B * HW) * 32 + (lane - 8) * 4, a);
-    } else {
-      store4<OUT_BF>(grad_unet, (size_t)pix * 64 + (lane - 16) * 4, a);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_rows_sum<IN_BF>(grad_h0, sorted_pt, s0, s1, 8, lane, a);
+    gather_rows_write<OUT_BF>(a, q, pil_pix[q], lane, B, HW, grad_img, grad_unet, img_rows);
+  }
+  __syncthreads();
+  const int nh = min(n_heavy, GB_LIST);
+  for (int h = 0; h < nh; ++h) {
+    const int q = heavy[h];
+    const int s0 = pil_start[q], s1 = pil_start[q + 1];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_rows_sum<IN_BF>(grad_h0, sorted_pt, s0 + warp * 8, s1, 64, lane, a);   // warp w: rows s0 + 8w + 64i + [0, 8)
+    part[warp][lane] = a;
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { const float4 t = part[w][lane]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      gather_rows_write<OUT_BF>(a, q, pil_pix[q], lane, B, HW, grad_img, grad_unet, img_rows);
     }
+    __syncthreads();
   }
 }
 

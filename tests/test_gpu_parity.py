@@ -296,6 +296,47 @@ def test_decoder_gather_forward_backward(dtype):
     assert float((gu.float() - ru.float()).abs().max()) <= tol * max(1.0, float(ru.float().abs().max()))
 
 
+def test_decoder_gather_backward_heavy_pillars_shared_by_a_block():
+    """Pillar populations are heavy-tailed: pillars with more than 96 points are summed by the eight warps of a block
+    together (a list of up to 64 per block, the rest falls back to one warp each).  160 k single-point pillars + a run of
+    160 adjacent pillars with 100 points each (more heavy pillars than one block's list of 64 holds) + one pillar with 3000."""
+    B, H, W = 1, 512, 512
+    gen = torch.Generator().manual_seed(5)
+    cells = torch.randperm(H * W, generator=gen)[:160000]
+    cy, cx = cells // W, cells % W
+    keep = ~((cy == 300) & (cx >= 100) & (cx < 260)) & ~((cy == 17) & (cx == 33))
+    cy, cx = cy[keep], cx[keep]
+    run = torch.arange(100, 260).repeat_interleave(100)
+    ys = torch.cat([cy, torch.full((run.numel(),), 300), torch.full((3000,), 17)])
+    xs = torch.cat([cx, run, torch.full((3000,), 33)])
+    n = ys.numel()
+    perm = torch.randperm(n, generator=gen)
+    ys, xs = ys[perm], xs[perm]
+    jit = torch.rand(n, 2, generator=gen) * 0.1 + 0.05
+    pc0 = torch.stack([RG[0] + (xs + jit[:, 0] * 5) * VS[0], RG[1] + (ys + jit[:, 1] * 5) * VS[1], torch.zeros(n)], 1)
+    pc0 = pc0.half().float()            # coordinates stay inside their cell: offsets 0.25 .. 0.75 of a 0.2 m cell
+    pts = torch.stack([pc0, pc0])       # frames: pc0, pc1
+    idx = ops.pillar_index(pts.to(DEV), VS, RG)
+    n0 = idx.pt_off(B)
+    assert n0 == n
+    coor = idx.pt_coor[:n0].long()
+    cnt = torch.bincount(coor[:, 1] * W + coor[:, 2])
+    assert int(cnt.max()) == 3000 and int((cnt == 100).sum()) == 160
+    gdev = torch.Generator(device=DEV).manual_seed(3)
+    img = torch.randn((2 * B, H, W, 32), device=DEV, generator=gdev).requires_grad_(True)
+    unet = torch.randn((B, H, W, 64), device=DEV, generator=gdev).requires_grad_(True)
+    h0 = ops.decoder_gather(img, unet, idx, B, n0, torch.float32)
+    bidx = torch.zeros(n0, dtype=torch.long, device=DEV)
+    ref = torch.cat([img[bidx, coor[:, 1], coor[:, 2]], img[bidx + B, coor[:, 1], coor[:, 2]],
+                     unet[bidx, coor[:, 1], coor[:, 2]]], 1)
+    assert torch.equal(h0, ref.detach())
+    gh = torch.randn(h0.shape, device=DEV, generator=gdev)
+    gi, gu = torch.autograd.grad(h0, (img, unet), gh)
+    ri, ru = torch.autograd.grad(ref, (img, unet), gh)
+    assert float((gi - ri).abs().max()) <= 2e-5 * float(ri.abs().max())
+    assert float((gu - ru).abs().max()) <= 2e-5 * float(ru.abs().max())
+
+
 # ----------------------------------------------------------------------------- ego warp + losses
 def test_ego_warp_matches_oracle():
     B, N = 3, 1000
