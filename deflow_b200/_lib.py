@@ -142,7 +142,7 @@ def _declare(lib):
         "dfb_clear_rows": [vp, i32, vp, vp, i32, i64, vp],
         "dfb_decoder_gather": [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, i32, vp],
         "dfb_decoder_gather_backward": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
-        "dfb_decoder_gather_backward_rows": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
+        "dfb_decoder_gather_backward_rows": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp],
         "dfb_gather_img_rows_add": [vp, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp],
         "dfb_add_cat2": [vp, vp, vp, vp, i64, i32, vp, vp],
         "dfb_flow_loss": [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp],

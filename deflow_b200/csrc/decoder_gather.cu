@@ -107,7 +107,10 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
                                                             const int* __restrict__ pil_start,
                                                             const int* __restrict__ sorted_pt,
                                                             void* __restrict__ grad_img, void* __restrict__ grad_unet,
-                                                            int pil_cap, float* __restrict__ img_rows) {
+                                                            int pil_cap, float* __restrict__ img_rows,
+                                                            float* __restrict__ unet_colsum) {
+  // unet_colsum != NULL: f32[64] += the per-channel sums of grad_unet (= the bias gradient of the convolution that produced
+  // the UNet output) taken from the pillar sums at hand instead of a pass over the dense, mostly zero tensor.
   // img_rows != NULL (then grad_img == NULL): the 64 image channels of every pc0 pillar's sum go to the compact fp32 buffer
   // img_rows[q][64] instead of a dense zero-filled image gradient; k_gather_img_rows_add adds them into the image gradient
   // later, once the other consumers of the pseudo-image have written theirs.
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
   const int qa = min(M0, (int)blockIdx.x * per), qb = min(M0, qa + per);
   if (threadIdx.x == 0) n_heavy = 0;
   __syncthreads();
+  float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);   // lanes 16..31: running sum of this warp's UNet-channel rows
   for (int q = qa + warp; q < qb; q += 8) {
     const int s0 = pil_start[q], s1 = pil_start[q + 1];
     if (s1 - s0 > GB_HEAVY) {
@@ -134,6 +138,7 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     gather_rows_sum<IN_BF>(grad_h0, sorted_pt, s0, s1, 8, lane, a);
     gather_rows_write<OUT_BF>(a, q, pil_pix[q], lane, B, HW, grad_img, grad_unet, img_rows);
+    tot.x += a.x; tot.y += a.y; tot.z += a.z; tot.w += a.w;
   }
   __syncthreads();
   const int nh = min(n_heavy, GB_LIST);
@@ -148,8 +153,20 @@ __global__ void __launch_bounds__(256) k_decoder_gather_bwd(const void* __restri
 #pragma unroll
       for (int w = 1; w < 8; ++w) { const float4 t = part[w][lane]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
       gather_rows_write<OUT_BF>(a, q, pil_pix[q], lane, B, HW, grad_img, grad_unet, img_rows);
+      tot.x += a.x; tot.y += a.y; tot.z += a.z; tot.w += a.w;
     }
     __syncthreads();
+  }
+  if (unet_colsum) {   // block total of the 64 UNet channels -> one atomic per channel and block
+    part[warp][lane] = tot;
+    __syncthreads();
+    if (warp == 0 && lane >= 16) {
+      float4 t = part[0][lane];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { const float4 u = part[w][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+      float* dst = unet_colsum + (lane - 16) * 4;
+      if (qb > qa) { atomicAdd(dst, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w); }
+    }
   }
 }
 
@@ -197,7 +214,7 @@ extern "C" int dfb_decoder_gather(const void* img, const void* unet, int in_bf16
 
 static int gather_backward_impl(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
                                 const int* pil_pix, const int* pil_start, const int* sorted_pt, void* grad_img,
-                                void* grad_unet, int out_bf16, int pil_cap, float* img_rows, cudaStream_t st) {
+                                void* grad_unet, int out_bf16, int pil_cap, float* img_rows, float* unet_colsum, cudaStream_t st) {
   if (B <= 0 || F < B || H <= 0 || W <= 0) { set_error("dfb_decoder_gather_backward: bad sizes"); return DFB_ERR_ARG; }
   const size_t HW = (size_t)H * W, es = out_bf16 ? 2 : 4;
   // dense gradients: zero everywhere except the pc0 pillars (index_put_ accumulate into zeros)
@@ -208,10 +225,10 @@ static int gather_backward_impl(const void* grad_h0, int grad_bf16, int B, int H
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     const int g = (int)blocks;
-    if (grad_bf16 && out_bf16) k_decoder_gather_bwd<true, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows);
-    else if (grad_bf16) k_decoder_gather_bwd<true, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows);
-    else if (out_bf16) k_decoder_gather_bwd<false, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows);
-    else k_decoder_gather_bwd<false, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows);
+    if (grad_bf16 && out_bf16) k_decoder_gather_bwd<true, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows, unet_colsum);
+    else if (grad_bf16) k_decoder_gather_bwd<true, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows, unet_colsum);
+    else if (out_bf16) k_decoder_gather_bwd<false, true><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows, unet_colsum);
+    else k_decoder_gather_bwd<false, false><<<g, 256, 0, st>>>(grad_h0, B, (int)HW, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, pil_cap, img_rows, unet_colsum);
     add_launches(1);
   }
   return check_launch("dfb_decoder_gather_backward");
@@ -223,16 +240,16 @@ extern "C" int dfb_decoder_gather_backward(const void* grad_h0, int grad_bf16, i
                                            int pil_cap, void* stream_) {
   if (!grad_img || !grad_unet) { set_error("dfb_decoder_gather_backward: both outputs are required (see dfb_decoder_gather_backward_rows)"); return DFB_ERR_ARG; }
   return gather_backward_impl(grad_h0, grad_bf16, B, H, W, counts, F, pil_pix, pil_start, sorted_pt, grad_img, grad_unet, out_bf16,
-                              pil_cap, nullptr, (cudaStream_t)stream_);
+                              pil_cap, nullptr, nullptr, (cudaStream_t)stream_);
 }
 
 extern "C" int dfb_decoder_gather_backward_rows(const void* grad_h0, int grad_bf16, int B, int H, int W,
                                                 const int* counts, int F, const int* pil_pix, const int* pil_start,
                                                 const int* sorted_pt, float* img_rows, void* grad_unet, int out_bf16,
-                                                int pil_cap, void* stream_) {
+                                                int pil_cap, float* unet_colsum, void* stream_) {
   if (!img_rows || !grad_unet) { set_error("dfb_decoder_gather_backward_rows: img_rows and grad_unet are required"); return DFB_ERR_ARG; }
   return gather_backward_impl(grad_h0, grad_bf16, B, H, W, counts, F, pil_pix, pil_start, sorted_pt, nullptr, grad_unet, out_bf16,
-                              pil_cap, img_rows, (cudaStream_t)stream_);
+                              pil_cap, img_rows, unet_colsum, (cudaStream_t)stream_);
 }
 
 extern "C" int dfb_gather_img_rows_add(const float* img_rows, int B, int H, int W, const int* counts, int F, const int* pil_pix,

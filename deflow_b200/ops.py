@@ -328,10 +328,14 @@ class _DecoderGather(torch.autograd.Function):
             # to the pseudo-image are added into its gradient once the other consumers of the image have written theirs --
             # no dense zero-filled [2B,H,W,32] tensor, no dense addition.
             rows = torch.empty((idx.pil_cap, 64), dtype=torch.float32, device=grad_h0.device)
+            # per-channel sums of g_unet (the bias gradient of the UNet's last convolution) from the pillar sums, attached the
+            # way the data-gradient kernels attach theirs (conv.bias_grad): saves a pass over the dense 64-channel tensor
+            colsum = torch.zeros(64, dtype=torch.float32, device=grad_h0.device)
             check(_lib.lib().dfb_decoder_gather_backward_rows(
                 grad_h0.data_ptr(), int(grad_h0.dtype == torch.bfloat16), B, H, W, idx.counts.data_ptr(), idx.F,
                 idx.pil_pix.data_ptr(), idx.pil_start.data_ptr(), idx.sorted_pt.data_ptr(), rows.data_ptr(), g_unet.data_ptr(),
-                int(dt == torch.bfloat16), idx.pil_cap, _stream(grad_h0)), "decoder_gather_backward_rows")
+                int(dt == torch.bfloat16), idx.pil_cap, colsum.data_ptr(), _stream(grad_h0)), "decoder_gather_backward_rows")
+            g_unet._dfb_colsum = (colsum, g_unet._version)
             ctx.sink["gather"] = (rows, idx, B, H, W)
             return None, g_unet, None, None, None, None, None, None
         g_img = torch.empty((2 * B, H, W, 32), dtype=dt, device=grad_h0.device)

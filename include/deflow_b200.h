@@ -209,10 +209,11 @@ int dfb_decoder_gather_backward(const void* grad_h0, int grad_bf16, int B, int H
 /* The same with the image part deferred: the 64 image channels of every pc0 pillar's gradient sum go to the compact buffer
  * img_rows f32[pil_cap][64] instead of a dense zero-filled image gradient (grad_unet stays dense); dfb_gather_img_rows_add adds
  * them into the image gradient [2B,H,W,32] in place once the other consumers of the pseudo-image have produced theirs:
- * no dense zero-fill, no dense addition. */
+ * no dense zero-fill, no dense addition.  unet_colsum: NULL, or f32[64] += per-channel sums of grad_unet over all pixels (the
+ * bias gradient of the convolution that produced the UNet output, REF/src/models/basic/unet.py:100-103) from the pillar sums. */
 int dfb_decoder_gather_backward_rows(const void* grad_h0, int grad_bf16, int B, int H, int W, const int* counts, int F,
                                      const int* pil_pix, const int* pil_start, const int* sorted_pt, float* img_rows,
-                                     void* grad_unet, int out_bf16, int pil_cap, void* stream);
+                                     void* grad_unet, int out_bf16, int pil_cap, float* unet_colsum, void* stream);
 int dfb_gather_img_rows_add(const float* img_rows, int B, int H, int W, const int* counts, int F, const int* pil_pix,
                             void* grad_img, int out_bf16, int pil_cap, void* stream);
 /* out[0:half) = a0 + b0, out[half:2*half) = a1 + b1 (elementwise, bf16 or fp32; b0 = b1 = NULL: plain concatenation): the

@@ -335,6 +335,20 @@ def test_decoder_gather_backward_heavy_pillars_shared_by_a_block():
     ri, ru = torch.autograd.grad(ref, (img, unet), gh)
     assert float((gi - ri).abs().max()) <= 2e-5 * float(ri.abs().max())
     assert float((gu - ru).abs().max()) <= 2e-5 * float(ru.abs().max())
+    # deferred image rows (the training step's path): the image part arrives as compact rows, the UNet part carries its
+    # per-channel sums (the bias gradient of the UNet's last convolution) taken from the pillar sums
+    sink = {}
+    h1 = ops.decoder_gather(img, unet, idx, B, n0, torch.float32, None, sink)
+    (gu1,) = torch.autograd.grad(h1, (unet,), gh)
+    assert float((gu1 - ru).abs().max()) <= 2e-5 * float(ru.abs().max())
+    rows = sink["gather"][0]
+    gimg = torch.zeros_like(img)
+    ops.gather_img_rows_add(rows, idx, B, H, W, gimg)
+    assert float((gimg - ri).abs().max()) <= 2e-5 * float(ri.abs().max())
+    cs = getattr(gu1, "_dfb_colsum", None)
+    assert cs is not None and cs[1] == gu1._version
+    ref_cs = ru.double().sum((0, 1, 2))
+    assert float((cs[0].double() - ref_cs).abs().max()) <= 1e-4 * max(1.0, float(ref_cs.abs().max()))
 
 
 # ----------------------------------------------------------------------------- ego warp + losses
