@@ -29,19 +29,21 @@ LAYERS = [
 ]
 
 
-def timeit(fn, iters=6, warm=2):
+def timeit(fn, iters=11, warm=3):
+    """Median of `iters` timed launches (a mean lets one allocator / clock hiccup of a few ms into a 0.1 ms row)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    tot = 0.0
+    ts = []
     for _ in range(iters):
         flush.zero_()                                   # inputs out of L2 between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record()
         torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    return tot / iters
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
 
 
 def main():
@@ -84,7 +86,7 @@ def main():
         stats = torch.zeros((2, cout), dtype=torch.float64, device=dev) if name.startswith("enc") else None
         f = timeit(lambda: tc.conv2d_forward(xs, wf, bias, cout, k, stride, stats))
         if len(cins) == 2 and k == 1 and cin <= 256:
-            dg = timeit(lambda: tc.conv2d_dgrad_two(gy, wd, H, H, cins[0], cins[1], cin, k))
+            dg = timeit(lambda: tc.conv2d_dgrad_two(gy, wd, H, H, cins[0], cins[1], cin, k, colsum=False))   # as the step calls it
         else:
             def dgrad_all():
                 off = 0
@@ -102,7 +104,7 @@ def main():
         print(line, flush=True)
         rows.append(line)
     summ = (f"sum over one training step (count x (fwd + dgrad + wgrad)): cuDNN bf16 {tot['cb']:.2f} ms, cuDNN TF32 {tot['ct']:.2f} ms, "
-            f"tcgen05 {tot['us']:.2f} ms   [B={args.batch}, {args.grid}^2, L2 flushed between launches, cudnn.benchmark=True, "
+            f"tcgen05 {tot['us']:.2f} ms   [B={args.batch}, {args.grid}^2, median of 11 launches, L2 flushed between launches, cudnn.benchmark=True, "
             f"cuDNN {torch.backends.cudnn.version()}; cuDNN rows exclude the channel concatenation and BatchNorm statistics "
             f"that the tcgen05 rows include]")
     print(summ, flush=True)
