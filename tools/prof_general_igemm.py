@@ -26,6 +26,13 @@ cases = {
     "e1d": lambda: conv.conv2d_dgrad(gy_e1, wd_e1, 512, 512, 32, 32, 0, 3, 2),
     # enc1.1 forward: 3x3 64 -> 64 at 256^2 (row-pair kernel)
     "pair": lambda: conv.conv2d_forward([x64], wf_p, b64, 64, 3, 1),
+    # enc2.1 forward: 3x3 128 -> 128 at 128^2 (k_conv_igemm_halo<128>); enc3.1: 3x3 256 -> 256 at 64^2 (halo<256>)
+    "h128": lambda: conv.conv2d_forward([x128], wf_h128, b128, 128, 3, 1),
+    "h256": lambda: conv.conv2d_forward([x256], wf_h256, b256, 256, 3, 1),
+    # weight gradients of the same layers and of enc1.1 (k_conv_wgrad_halo<128>, <256>, k_conv_wgrad_x)
+    "wh128": lambda: conv.conv2d_wgrad([x128], gy128, 3, 1),
+    "wh256": lambda: conv.conv2d_wgrad([x256], gy256, 3, 1),
+    "wx": lambda: conv.conv2d_wgrad([x64], gy64, 3, 1),
 }
 x32 = bf(B, 512, 512, 32)
 b64 = torch.randn(64, device=DEV)
@@ -36,6 +43,11 @@ gy_e1 = bf(B, 256, 256, 64)
 _, wd_e1 = conv.pack_weights(torch.randn(64, 32, 3, 3, device=DEV) / 17)
 x64 = bf(B, 256, 256, 64)
 wf_p, _ = conv.pack_weights(torch.randn(64, 64, 3, 3, device=DEV) / 24)
+x128, gy128, b128 = bf(B, 128, 128, 128), bf(B, 128, 128, 128), torch.randn(128, device=DEV)
+x256, gy256, b256 = bf(B, 64, 64, 256), bf(B, 64, 64, 256), torch.randn(256, device=DEV)
+gy64 = bf(B, 256, 256, 64)
+wf_h128, _ = conv.pack_weights(torch.randn(128, 128, 3, 3, device=DEV) / 34)
+wf_h256, _ = conv.pack_weights(torch.randn(256, 256, 3, 3, device=DEV) / 48)
 
 which = sys.argv[1:] or list(cases)
 for rep in range(3):
