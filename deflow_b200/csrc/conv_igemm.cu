@@ -134,7 +134,9 @@ __device__ __forceinline__ int par_decode(const IgemmParams& P, int& tile) {
   return par;
 }
 
-template <int N, bool PAIR = false>
+// DUAL (k_conv_igemm_halo<N, true>): a work item is a PAIR of consecutive tiles (2 * item, 2 * item + 1) whose two
+// accumulators -- TMEM columns (2 * acc + which) * N -- complete together.
+template <int N, bool PAIR = false, bool DUAL = false>
 __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUtensorMap* out_map, uint32_t tmem_base,
                                                uint64_t* acc_full, uint64_t* acc_empty, float* s_stats,
                                                const float* s_bias, uint8_t* stage_all, int warp, int lane) {
@@ -150,15 +152,19 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
   bool store_pending = false;
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int item = blockIdx.x; item < P.num_tiles; item += gridDim.x) {
-    int tile = item;
-    const int par = PAIR ? 0 : par_decode(P, tile);
+  const int n_items = DUAL ? P.num_tiles / 2 : P.num_tiles;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    mbar_wait(&acc_full[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int which = 0; which < (DUAL ? 2 : 1); ++which) {
+    int tile = DUAL ? 2 * item + which : item;
+    const int par = (PAIR || DUAL) ? 0 : par_decode(P, tile);
     const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
     const int y0 = PAIR ? ty * 2 * TILE_H + 2 * r : ty * TILE_H + r, x = tx * TILE_W + c;
     const long long off0 = (long long)n * P.out_img + (long long)(y0 * P.sy + P.oy) * P.out_row +
                            (long long)(x * P.sx + P.ox) * P.out_pix;
-    mbar_wait(&acc_full[acc], acc_phase);
-    tc_fence_after();
+    const int acc_col = (DUAL ? 2 * acc + which : acc) * N;
 #pragma unroll 1
     for (int col = 32 * cg; col < N; col += 32 * (EPI_WARPS / 4)) {
       const int half = PAIR ? col / (N / 2) : 0;       // output row parity of this column block
@@ -169,7 +175,7 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
       const bool valid = y < P.Ht && x < P.Wt;
       const long long off = off0 + (long long)half * P.out_row;
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + col, v);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + col, v);
       if (P.bias) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -230,6 +236,7 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& P, const CUten
         store_pending = true;
       }
     }
+    }   // which
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -627,26 +634,32 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm(const __grid_co
 // is a function of the shared-memory address, so a descriptor that starts at a 128-byte (not 1024-byte) boundary
 // reads exactly what TMA wrote.  Activation traffic from L2 drops ~4-6x; weights stream through their own ring, or
 // stay resident for the whole kernel when all taps fit (64 -> 64 channels).
-template <int N>
+// DUAL: a work item is a pair of consecutive tiles that share every weight tile -- two halo boxes per stage, two
+// accumulators per buffer (4 N TMEM columns, N <= 128).  The 128 / 256-channel layers stream their weights per tile
+// (18 / 36 tiles of 16 / 32 KB for 128 pixels) and ran at 11 TB/s of L2 -> SM traffic (ncu l1tex__m_xbar2l1tex_read_bytes,
+// profiles/r02_ncu_tensor_pipe_final.txt: 698 MB per launch for 134 MB of activations), the fabric's limit, with the
+// tensor pipe 70 % active: M = 256 per weight tile halves that traffic.
+template <int N, bool DUAL = false>
 struct HaloCfg {
   static constexpr int HALO_BYTES = 23 * 1024;                     // 18 x 10 pixels x 128 B = 23040, 1024-aligned
+  static constexpr int SLOT_BYTES = (DUAL ? 2 : 1) * HALO_BYTES;   // one stage: the halo of every tile of the item
   static constexpr int W_BYTES = N * 128;                          // one tap x one 64-channel chunk
-  static constexpr int HALO_STAGES = 3;
-  static constexpr int W_STAGES_RAW = (225 * 1024 - 2048 - 3 * N * 4 - EPI_SMEM - HALO_STAGES * HALO_BYTES) / W_BYTES;
+  static constexpr int HALO_STAGES = DUAL ? 2 : 3;
+  static constexpr int W_STAGES_RAW = (225 * 1024 - 2048 - 3 * N * 4 - EPI_SMEM - HALO_STAGES * SLOT_BYTES) / W_BYTES;
   static constexpr int W_STAGES = W_STAGES_RAW > 18 ? 18 : W_STAGES_RAW;
-  static constexpr int TILE_BYTES = HALO_STAGES * HALO_BYTES + W_STAGES * W_BYTES;
+  static constexpr int TILE_BYTES = HALO_STAGES * SLOT_BYTES + W_STAGES * W_BYTES;
   static constexpr int SMEM = TILE_BYTES + EPI_SMEM + 1024 + 512 + 3 * N * 4;
-  static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+  static constexpr int TMEM_COLS = (DUAL ? 4 : 2) * N < 32 ? 32 : (DUAL ? 4 : 2) * N;
 };
 
-template <int N>
+template <int N, bool DUAL = false>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __grid_constant__ IgemmMaps maps,
                                                                       const __grid_constant__ IgemmParams P) {
-  using Cfg = HaloCfg<N>;
+  using Cfg = HaloCfg<N, DUAL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* halos = smem;
-  uint8_t* wts = smem + Cfg::HALO_STAGES * Cfg::HALO_BYTES;
+  uint8_t* wts = smem + Cfg::HALO_STAGES * Cfg::SLOT_BYTES;
   uint8_t* epi_stage = smem + Cfg::TILE_BYTES;              // 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_SMEM);
   uint64_t* h_full = bars;                                  // [HALO_STAGES]
@@ -682,14 +695,23 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
       int hs = 0, ws = 0;
       uint32_t hph = 0, wph = 0;
       bool first_tile = true;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const int n_items = DUAL ? P.num_tiles / 2 : P.num_tiles;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = DUAL ? 2 * item : item;
         const int tx = tile % P.tiles_x, t2 = tile / P.tiles_x, ty = t2 % P.tiles_y, n = t2 / P.tiles_y;
         const int x0 = tx * TILE_W - 1, y0 = ty * TILE_H - 1;
+        int x0b = 0, y0b = 0, nb = 0;             // DUAL: the second tile of the pair
+        if (DUAL) {
+          const int tb = tile + 1;
+          const int txb = tb % P.tiles_x, t2b = tb / P.tiles_x;
+          x0b = txb * TILE_W - 1; y0b = (t2b % P.tiles_y) * TILE_H - 1; nb = t2b / P.tiles_y;
+        }
         for (int s = 0; s < P.nsteps; ++s) {
           const KStep st = P.steps[s];
           mbar_wait(&h_empty[hs], hph ^ 1);
-          mbar_arrive_expect_tx(&h_full[hs], halo_tx);
-          tma_load_4d(halos + hs * Cfg::HALO_BYTES, &maps.a[st.map], &h_full[hs], st.c0, x0, y0, n);
+          mbar_arrive_expect_tx(&h_full[hs], (DUAL ? 2u : 1u) * halo_tx);
+          tma_load_4d(halos + hs * Cfg::SLOT_BYTES, &maps.a[st.map], &h_full[hs], st.c0, x0, y0, n);
+          if (DUAL) tma_load_4d(halos + hs * Cfg::SLOT_BYTES + Cfg::HALO_BYTES, &maps.a[st.map], &h_full[hs], st.c0, x0b, y0b, nb);
           if (++hs == Cfg::HALO_STAGES) { hs = 0; hph ^= 1; }
           if (!P.w_resident || first_tile) {
             for (int t = 0; t < 9; ++t) {
@@ -725,16 +747,17 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
       int hs = 0, ws = 0, acc = 0;
       uint32_t hph = 0, wph = 0, acc_phase = 0;
       bool first_tile = true;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const int n_items = DUAL ? P.num_tiles / 2 : P.num_tiles;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * N;
+        const uint32_t d = tmem_base + (DUAL ? 2 * acc : acc) * N;
         uint32_t accum = 0u;
         if (resident) ws = 0;
         for (int s = 0; s < P.nsteps; ++s) {
           mbar_wait(&h_full[hs], hph);
           tc_fence_after();
-          const uint32_t ah = a_lo0 + (uint32_t)hs * (uint32_t)(Cfg::HALO_BYTES >> 4);
+          const uint32_t ah = a_lo0 + (uint32_t)hs * (uint32_t)(Cfg::SLOT_BYTES >> 4);
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             if (!resident || first_tile) { mbar_wait(&w_full[ws], wph); tc_fence_after(); }
@@ -744,6 +767,13 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
             umma_bf16_lohi_warp(d, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
             umma_bf16_lohi_warp(d, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
             umma_bf16_lohi_warp(d, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+            if (DUAL) {   // the second tile of the pair against the same weight tile
+              const uint32_t a2 = a_lo + (uint32_t)(Cfg::HALO_BYTES >> 4);
+              umma_bf16_lohi_warp(d + N, a2, a_hi, b_lo, b_hi, idesc, accum);
+              umma_bf16_lohi_warp(d + N, a2 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+              umma_bf16_lohi_warp(d + N, a2 + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+              umma_bf16_lohi_warp(d + N, a2 + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+            }
             accum = 1u;
             if (!resident) umma_commit_warp(&w_empty[ws]);
             if (++ws == Cfg::W_STAGES) { ws = 0; wph ^= 1; }
@@ -758,7 +788,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) k_conv_igemm_halo(const __gr
       }
     }
   } else {
-    igemm_epilogue<N>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
+    igemm_epilogue<N, false, DUAL>(P, &maps.out, tmem_base, acc_full, acc_empty, s_stats, s_bias, epi_stage, warp, lane);
   }
 
   tc_fence_before();
@@ -1015,27 +1045,35 @@ static int build_out_map(IgemmMaps& maps, const IgemmParams& P, int N) {
   return DFB_OK;
 }
 
-template <int N>
+template <int N, bool DUAL = false>
 static int launch_igemm_halo(IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
-  using Cfg = HaloCfg<N>;
+  using Cfg = HaloCfg<N, DUAL>;
   if (int rc = build_out_map(maps, P, N)) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_igemm_halo<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_igemm_halo<N, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) { set_error("igemm_halo<%d>: cannot reserve %d bytes of shared memory: %s", N, Cfg::SMEM, cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     configured = true;
   }
   P.w_resident = (9 * P.nsteps <= Cfg::W_STAGES) ? 1 : 0;
+  const int items = DUAL ? P.num_tiles / 2 : P.num_tiles;
   int grid = sm_count();
-  if (grid > P.num_tiles) grid = P.num_tiles;
-  k_conv_igemm_halo<N><<<grid, IGEMM_THREADS, Cfg::SMEM, st>>>(maps, P);
+  if (grid > items) grid = items;
+  k_conv_igemm_halo<N, DUAL><<<grid, IGEMM_THREADS, Cfg::SMEM, st>>>(maps, P);
   add_launches(1);
   return check_launch("conv_igemm_halo");
+}
+
+static bool halo_dual_enabled() {
+  const char* e = getenv("DFB_HALO_DUAL");   // read per call: tests toggle it
+  return e && atoi(e) != 0;
 }
 
 static int dispatch_igemm_halo(int N, IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
   if (N == 32) return launch_igemm_halo<32>(maps, P, st);
   if (N == 64) return launch_igemm_halo<64>(maps, P, st);
+  // 128 output channels: pairs of tiles share every weight tile (HaloCfg DUAL); DFB_HALO_DUAL=0 -> one tile per item (A/B)
+  if (N == 128 && P.num_tiles % 2 == 0 && P.num_tiles >= 2 && halo_dual_enabled()) return launch_igemm_halo<128, true>(maps, P, st);
   if (N == 128) return launch_igemm_halo<128>(maps, P, st);
   if (N == 256) return launch_igemm_halo<256>(maps, P, st);
   set_error("conv_igemm_halo: unsupported N=%d", N);

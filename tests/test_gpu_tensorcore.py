@@ -271,6 +271,44 @@ def test_row_pair_kernel_wide_store_variant(monkeypatch, n, H, W, cins):
         assert torch.equal(a, bb)
 
 
+@pytest.mark.parametrize("n,H,W,cins", [(1, 32, 24, [128]), (2, 128, 128, [128]), (1, 64, 40, [128, 128]), (3, 16, 8, [128]), (1, 48, 56, [64])])
+def test_halo_kernel_dual_tile_variant(monkeypatch, n, H, W, cins):
+    """k_conv_igemm_halo<128, DUAL>: pairs of consecutive tiles share every weight tile (two halo boxes per stage, two
+    accumulators per buffer).  Same MMA order per tile, so outputs are identical to the one-tile-per-item kernel; forward
+    with BatchNorm statistics and data gradient; pairs that straddle tile rows (odd tiles_x) and images; an odd tile count
+    (3 x 16 x 8: 3 tiles) falls back to single tiles."""
+    torch.manual_seed(H * W)
+    xs = [torch.randn(n, H, W, c, device=DEV).to(torch.bfloat16) for c in cins]
+    ct = sum(cins)
+    w = torch.randn(128, ct, 3, 3, device=DEV) / (ct * 9) ** 0.5
+    b = torch.randn(128, device=DEV)
+    wf, wd = conv.pack_weights(w)
+    gy = torch.randn(n, H, W, 128, device=DEV).to(torch.bfloat16)
+
+    def run():
+        stats = torch.zeros(2, 128, dtype=torch.float64, device=DEV)
+        y = conv.conv2d_forward(xs, wf, b, 128, 3, 1, stats)
+        gxs, off = [], 0
+        for c in cins:
+            gxs.append(conv.conv2d_dgrad(gy, wd, H, W, c, ct, off, 3, 1, colsum=(c == 128)))
+            off += c
+        return y, stats, gxs
+
+    monkeypatch.setenv("DFB_HALO_DUAL", "0")
+    y0, s0, g0 = run()
+    monkeypatch.setenv("DFB_HALO_DUAL", "1")
+    y1, s1, g1 = run()
+    xcat = torch.cat([x.float() for x in xs], 3).permute(0, 3, 1, 2)
+    ref = F.conv2d(xcat, w.to(torch.bfloat16).float(), b, stride=1, padding=1).permute(0, 2, 3, 1)
+    assert _rel(y1.float(), ref) <= 2 ** -8
+    assert torch.equal(y0, y1)
+    assert _rel(s0, s1) <= 1e-6
+    for a, bb in zip(g0, g1):
+        assert torch.equal(a, bb)
+        if a.shape[-1] == 128:
+            assert _rel(conv.bias_grad(a), conv.bias_grad(bb)) <= 1e-5
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_split_precision_matches_fp32(case):
     """Parity mode: fp32 tensors, operands as (hi, lo) bf16 pairs, hi*hi + hi*lo + lo*hi on the tensor cores."""
