@@ -1064,10 +1064,10 @@ static int launch_igemm_halo(IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
   return check_launch("conv_igemm_halo");
 }
 
-static bool halo_dual_enabled() {
-  const char* e = getenv("DFB_HALO_DUAL");   // read per call: tests toggle it
-  return e && atoi(e) != 0;
-}
+// measured (profiles/r02_halo_dual_ab.txt): k_conv_igemm_halo<128> 2.82 -> 2.67 ms per step over its 25 launches, step
+// 28.4 -> 28.25 ms.  The rest of the gap to the tensor peak is shared-memory bandwidth: an M = 128 x N = 128 x K = 16 MMA reads
+// 8 KB of operands for 64 cycles of math (128 B per cycle, the limit) -- the remedy is cta_group::2 (half of B per CTA).
+static bool halo_dual_enabled() { return env_on("DFB_HALO_DUAL"); }   // read per call: tests toggle it
 
 static int dispatch_igemm_halo(int N, IgemmMaps& maps, IgemmParams& P, cudaStream_t st) {
   if (N == 32) return launch_igemm_halo<32>(maps, P, st);
