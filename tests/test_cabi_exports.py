@@ -58,3 +58,37 @@ def test_no_cpu_fallback():
         m(batch)
     with pytest.raises(RuntimeError):
         d.DynamicScatter([0.2, 0.2, 6], [-6.4, -6.4, -3, 6.4, 6.4, 3], True)(torch.zeros(4, 3), torch.zeros(4, 3, dtype=torch.int32))
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """Every struct of include/deflow_b200.h against its ctypes mirror in deflow_b200/_lib.py: total size and the offset of
+    every field, taken from the header by a C compiler (a field added on one side only would shift everything after it)."""
+    import shutil
+    import subprocess
+    from deflow_b200 import _lib
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    pairs = {"dfb_index_args": _lib.IndexArgs, "dfb_conv_args": _lib.ConvArgs, "dfb_pack_desc": _lib.PackDesc, "dfb_unpack_desc": _lib.UnpackDesc,
+             "dfb_pfn_args": _lib.PfnArgs, "dfb_pfn_bwd_args": _lib.PfnBwdArgs, "dfb_eval_tables": _lib.EvalTables}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "deflow_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, what, val = line.split()
+        cls = pairs[cname]
+        if what == "size":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, what).offset == int(val), (cname, what, getattr(cls, what).offset, val)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
