@@ -6,7 +6,6 @@ Reference: ConvGRUDecoder.forward_single / LinearDecoder.forward_single (OSF/src
 81-104) -- per-sample Python loops over cuDNN/cuBLAS calls there."""
 from __future__ import annotations
 
-import ctypes as C
 import os
 
 import torch

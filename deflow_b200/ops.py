@@ -7,7 +7,7 @@ OSF = /root/reference/OpenSceneFlow.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 
