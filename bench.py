@@ -515,7 +515,7 @@ def run_native(args):
             for tname in ("r02_traffic.json", "r01_traffic.json"):
                 tpath = os.path.join(ROOT, "profiles", tname)
                 if traffic is None and os.path.exists(tpath):
-                    traffic = json.load(open(tpath)).get(top["kernel"], {}).get("dram_bytes_per_launch")
+                    traffic = _traffic_lookup(json.load(open(tpath)), top["kernel"])
             roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": peaks["bf16_tflops_sustained"],
                     "unit": "TFLOP/s", "frac": top["frac_of_sustained_peak"], "traffic": traffic,
                     "avg_launch_ms": top["avg_launch_ms"], "share_of_step": top["ms_per_step"] / ms,
@@ -554,6 +554,18 @@ def run_native(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def _traffic_lookup(table: dict, kernel: str):
+    """DRAM bytes per launch of a kernel family from a profiles/r0N_traffic.json table.  The table is keyed by the kernel's
+    name as ncu prints it (with template arguments, e.g. 'k_gru_fused_bwd<16>'); the timing records name the family
+    ('k_gru_fused_bwd', 'k_conv_igemm_halo<128>'): exact key first, then the family's instantiations (mean)."""
+    hit = table.get(kernel)
+    if isinstance(hit, dict) and "dram_bytes_per_launch" in hit:
+        return hit["dram_bytes_per_launch"]
+    vals = [v["dram_bytes_per_launch"] for k, v in table.items()
+            if isinstance(v, dict) and "dram_bytes_per_launch" in v and k.startswith(kernel + "<")]
+    return sum(vals) / len(vals) if vals else None
 
 
 def main():
